@@ -1,0 +1,151 @@
+/* libtmc — C ABI of the B200-native spectral-bipartition engine for
+ * `too-many-cells make-tree`.
+ *
+ * The reference has no FFI of its own for this path; the seam is the Haskell
+ * call in src/TooManyCells/MakeTree/Cluster.hs:147-156,169
+ *     hierarchicalSpectralCluster eigenGroup False numEigen Nothing minMod runs items (Left mat)
+ * and the one-liner src/TooManyCells/Matrix/Preprocess.hs:204-205
+ *     tfidfScaleSparseMat = MatObsRow . unB2 . b1ToB2 . B1 . unMatObsRow
+ * Every entry point below names the reference / upstream function it replaces.
+ * INTEGRATION.md shows the `foreign import ccall` stubs a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only.  Inputs are borrowed HOST memory
+ * for the duration of the call unless the name says `_dev`.  Outputs are
+ * caller-allocated unless documented as library-owned.  Every function returns
+ * 0 on success or a negative tmc_status; tmc_last_error() gives a thread-local
+ * message.  Nothing aborts, nothing hangs: NaN / zero-norm rows / negative
+ * entries are detected up front (the reference hangs in SVDLIBC on those,
+ * src/TooManyCells/Program/LoadMatrix.hs:189-193).
+ * There is NO CPU fallback: without a CUDA device every compute entry point
+ * returns TMC_ERR_NO_DEVICE.
+ */
+#ifndef TMC_H
+#define TMC_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  TMC_OK = 0,
+  TMC_ERR_INVALID = -1,     /* bad argument (null pointer, unsorted / out-of-range column, ...) */
+  TMC_ERR_NO_DEVICE = -2,   /* no CUDA device / driver */
+  TMC_ERR_CUDA = -3,        /* CUDA runtime error (message in tmc_last_error) */
+  TMC_ERR_ZERO_ROW = -4,    /* a row has zero L2 norm (reference: NaN -> svdlibc hang) */
+  TMC_ERR_NAN = -5,         /* NaN / Inf in the values */
+  TMC_ERR_NEGATIVE = -6,    /* negative entry (engine requires B >= 0, as tf-idf of counts is) */
+  TMC_ERR_NOMEM = -7,
+  TMC_ERR_COMM = -8,        /* NCCL error */
+  TMC_ERR_UNSUPPORTED = -9  /* e.g. eigen_group = KMeansGroup, num_runs > 0 */
+} tmc_status;
+
+/* cells x features CSR, rows = cells (MatObsRow, src/TooManyCells/Matrix/Types.hs:152-158).
+ * Columns need not be sorted within a row; duplicates are not allowed. */
+typedef struct {
+  int64_t n_rows, n_cols, nnz;
+  const int64_t* row_ptr;   /* n_rows + 1 */
+  const int32_t* col_idx;   /* nnz */
+  const double*  val;       /* nnz */
+} tmc_csr;
+
+/* Flag contract of the make-tree engine call (src/TooManyCells/Program/Options.hs:172-178,
+ * src/TooManyCells/MakeTree/Cluster.hs:147-156). Zero-initialise, then tmc_opts_default(). */
+typedef struct {
+  int32_t eigen_group;      /* 0 = SignGroup (default), 1 = KMeansGroup (unsupported)   Options.hs:172 */
+  int32_t num_eigen;        /* default 1                                                Options.hs:173 */
+  double  min_modularity;   /* default 0.0; split iff Q > min_modularity                Options.hs:178 */
+  int32_t min_size;         /* make-tree always passes 1 (Nothing)                      Cluster.hs:152 */
+  int32_t normalize;        /* 0 from make-tree (tf-idf done by caller), 1 = idf inside Cluster.hs:150 */
+  int32_t num_runs;         /* permutation test, 0 = off (unsupported > 0)              Options.hs:174 */
+  uint64_t seed;            /* start-vector seed */
+  /* engine knobs (no reference counterpart) */
+  double  tol;              /* Lanczos residual tolerance ||M u - theta u|| <= tol*theta; default 1e-10 */
+  int32_t max_lanczos;      /* Krylov dimension before an explicit restart; default 320 */
+  int32_t max_restarts;     /* default 8 */
+  int32_t max_active;       /* concurrently iterating tree nodes (y-vector slots); default 2048 */
+  int32_t device;           /* CUDA device ordinal, -1 = current */
+  int32_t profile;          /* 1 = time the SpMV kernels with CUDA events (fills tmc_tree.spmv_ms) */
+  int32_t reserved[6];
+} tmc_opts;
+
+/* Result tree: flat, pre-order (node 0 = root, children [label 0, label 1]) exactly as
+ * birch-beer's treeToGraph numbers it (src/TooManyCells/MakeTree/Cluster.hs:171-181), so
+ * node ids equal the `cluster` ids of clusters.csv.  Library-owned until tmc_tree_free. */
+typedef struct {
+  int64_t n_nodes, n_rows;
+  const int64_t* left;        /* n_nodes; -1 for a leaf */
+  const int64_t* right;
+  const int64_t* parent;      /* -1 for the root */
+  const double*  q;           /* Newman-Girvan Q of the node's bipartition (also computed for leaves;
+                                 the host maps leaf -> Nothing as clusteringTreeToTree does) */
+  const double*  theta;       /* sigma_2(C)^2 at the node */
+  const int32_t* iters;       /* Lanczos steps spent on the node */
+  const int64_t* item_begin;  /* n_nodes; [item_begin,item_end) into perm: the node's cells */
+  const int64_t* item_end;
+  const int64_t* perm;        /* n_rows original row ids; ascending inside every node (stable splits) */
+  /* engine statistics for the roofline report */
+  int64_t n_sweeps;           /* kernel sweeps over the active node set */
+  int64_t spmv_pairs_nnz;     /* sum over Lanczos steps of nnz touched (one pair = 2 passes) */
+  int64_t kernel_launches;
+  double  engine_ms;          /* device time of the tree build (CUDA events) */
+  double  spmv_ms;            /* device time inside the scatter+gather kernels (only if opts.profile) */
+  double  spmv_alg_bytes;     /* algorithmic bytes of those SpMV pairs (BASELINE.md section 4 formula) */
+} tmc_tree;
+
+/* Device-resident matrix handle: B = row-L2-normalised (tf-idf) CSR kept in HBM. */
+typedef struct tmc_matrix tmc_matrix;
+
+void        tmc_opts_default(tmc_opts* o);
+const char* tmc_last_error(void);
+const char* tmc_version(void);
+int         tmc_device_count(void);
+
+/* == b1ToB2 (spectral-clustering), drop-in for Preprocess.hs:204-205.
+ * val_out[k] = val[k] * ln(n_rows / df[col[k]]), df_j = #{entries > 0 in column j}; idf_out optional. */
+int tmc_tfidf(const tmc_csr* b1, double* val_out, double* idf_out);
+
+/* == b2ToB: val_out = row-L2-normalised values; norm_out (n_rows, optional) = the row norms. */
+int tmc_row_l2(const tmc_csr* b2, double* val_out, double* norm_out);
+
+/* Upload a B2 matrix (host CSR) and keep B = b2ToB(B2) on the device (normalize=1 applies idf first). */
+int  tmc_matrix_upload(const tmc_csr* b2, int normalize, int device, tmc_matrix** out);
+/* Adopt DEVICE arrays (row_ptr int64, col int32, val double; not copied, caller keeps them alive).
+ * Values are normalised in place (idf if normalize, then row L2). */
+int  tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* row_ptr_dev,
+                          const int32_t* col_dev, double* val_dev, int normalize, int device, tmc_matrix** out);
+void tmc_matrix_free(tmc_matrix*);
+
+/* == hierarchicalSpectralCluster ... (Left mat)  (Cluster.hs:147-156): the whole tree. */
+int  tmc_make_tree(const tmc_csr* b2, const tmc_opts* opts, tmc_tree** out);
+int  tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out);
+void tmc_tree_free(tmc_tree*);
+
+/* Fine-grained exports so every row of SURVEY.md 8(a) is individually parity-testable.
+ * `rows` (n_sel original row ids, ascending) selects the node S; NULL = all rows. */
+/* == bToD: d = |B_S| (|B_S|^T 1) */
+int tmc_degree(tmc_matrix* b, const int64_t* rows, int64_t n_sel, double* d_out);
+/* == secondLeft 2 1 (bdToC B D) via sparseSvd: u2 (n_sel), theta = sigma_2^2, Lanczos steps used. */
+int tmc_second_left(tmc_matrix* b, const int64_t* rows, int64_t n_sel, const tmc_opts* opts,
+                    double* u2_out, double* theta_out, int32_t* iters_out);
+/* == getBModularity labels B_S */
+int tmc_modularity(tmc_matrix* b, const int64_t* rows, int64_t n_sel, const uint8_t* labels, double* q_out);
+/* == stable row split (extractRow/fromRowsL over the sorted index lists): rows_out = [label0 | label1] */
+int tmc_partition(const int64_t* rows, int64_t n_sel, const uint8_t* labels, int64_t* rows_out, int64_t* n_left);
+/* one fused pair x' = C_S (C_S^T x) (the las2 `opb`), for the roofline harness and parity tests */
+int tmc_spmv_pair(tmc_matrix* b, const int64_t* rows, int64_t n_sel, const double* x, double* x_out);
+
+/* Kernel-only timing of the SpMV pair on the full matrix: `reps` launches, average ms per
+ * scatter (y = C^T x) and gather (x' = C y) kernel, measured with CUDA events on the engine stream. */
+int tmc_bench_spmv_pair(tmc_matrix* b, int reps, double* scatter_ms, double* gather_ms);
+
+/* Multi-GPU (one process per GPU): NCCL communicator owned by the library.
+ * Rank 0 calls tmc_comm_unique_id and ships the 128 bytes to the other ranks (torch.distributed),
+ * then every rank calls tmc_comm_init. */
+int  tmc_comm_unique_id(uint8_t id_out[128]);
+int  tmc_comm_init(const uint8_t id[128], int rank, int world, int device);
+void tmc_comm_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,241 @@
+"""CPU oracle for the too-many-cells `make-tree` spectral-bipartition path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package may import this
+module; only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` /
+`--impl reference` legs of `bench.py` do, and only as the checker.
+
+PARITY UNPINNED.  The arithmetic of this path is not in /root/reference: the
+reference only *calls* it (`hierarchicalSpectralCluster`,
+src/TooManyCells/MakeTree/Cluster.hs:147-156; `b1ToB2`,
+src/TooManyCells/Matrix/Preprocess.hs:204-205).  The bodies live in un-vendored
+Hackage packages (hierarchical-spectral-clustering 0.5.0.1, spectral-clustering
+>= 0.3.0.2 @18729ec5, modularity 0.2.1.1, sparse-linear-algebra @dbad792f,
+hmatrix-svdlibc 0.5.0.1 = SVDLIBC las2), none of which is in this container,
+and the reference ships no tests or numeric fixtures for the path (its only
+result artefacts, workshop/out/*, have no input matrix).  This file therefore
+restates the *published* algorithm (Shu et al. 2011, "Efficient spectral
+neighborhood blocking for entity resolution"; Newman-Girvan modularity on the
+implicit graph A = B B^T - I) in exact-math fp64, anchored on the reference's
+call sites.  Every function cites the call site / package function it follows.
+Switches for the unsettled upstream details are module constants below.
+
+The eigen-solve is *exact* (dense LAPACK `eigh` for small nodes, ARPACK at
+tol ~ 1e-14 for large ones), so both the reference binary (SVDLIBC, kappa=1e-6)
+and the GPU engine are approximations of this oracle.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+# ---- switches for [UPSTREAM-RECALL] details -------------
+IDF_LOG = math.log          # (1) natural log of m/df, df = #entries > 0
+DEGREE_USES_ABS = True      # (2) d = |B| (|B|^T 1)
+SIGN_RULE_GE_ZERO_IS_ONE = True   # (3) label 1 iff u2_i >= 0
+STRICT_Q_GT_MINMOD = True   # (5) split iff Q > minMod
+DENSE_MAX_ROWS = 2600       # nodes up to this many rows use dense eigh
+
+
+# ---- A1: b1ToB2 (spectral-clustering; call site Preprocess.hs:204-205) ---------
+def b1_to_b2(b1: sp.csr_matrix) -> sp.csr_matrix:
+    """idf column scaling: B2[i,j] = B1[i,j] * ln(m / df_j), df_j = #{i: B1[i,j] > 0}."""
+    b1 = sp.csr_matrix(b1, dtype=np.float64)
+    m, n = b1.shape
+    df = np.zeros(n, dtype=np.int64)
+    np.add.at(df, b1.indices[b1.data > 0], 1)
+    with np.errstate(divide="ignore"):
+        idf = np.where(df > 0, np.log(m / np.maximum(df, 1)), 0.0)
+    out = b1.copy()
+    out.data = b1.data * idf[b1.indices]
+    return out
+
+
+# ---- A2: b2ToB (spectral-clustering; evidence Classify/Classify.hs:44-51) ------
+def b2_to_b(b2: sp.csr_matrix) -> sp.csr_matrix:
+    """L2-normalise every row (done once at the root; Cluster.hs:150 passes normFlag False)."""
+    b2 = sp.csr_matrix(b2, dtype=np.float64)
+    norms = np.sqrt(np.asarray(b2.multiply(b2).sum(axis=1)).ravel())
+    if np.any(norms == 0):
+        raise ValueError("zero-norm row: the reference yields NaN / hangs (LoadMatrix.hs:189-193)")
+    out = b2.copy()
+    out.data = b2.data / np.repeat(norms, np.diff(b2.indptr))
+    return out
+
+
+# ---- A3: bToD / bdToC ------------------------------------------------------------
+def b_to_d(b: sp.csr_matrix) -> np.ndarray:
+    """d = |B| (|B|^T 1): row sums of the implicit cosine-similarity matrix (self included)."""
+    a = abs(b) if DEGREE_USES_ABS else b
+    t = np.asarray(a.sum(axis=0)).ravel()
+    return a @ t
+
+
+def bd_to_c(b: sp.csr_matrix, d: np.ndarray) -> sp.csr_matrix:
+    return sp.diags(1.0 / np.sqrt(d)) @ b
+
+
+# ---- A4/A5: secondLeft -> sparseSvd(2) -> u2 (twin idiom Preprocess.hs:512-520) --
+def second_left(c: sp.csr_matrix, d: np.ndarray | None = None):
+    """Second left singular vector of C (exact).  Returns (u2, sigma2^2, gap).
+
+    sigma_1 = 1 with u_1 ~ D^{1/2} 1 always; u2 is the top eigenvector of
+    C C^T restricted to the complement of u_1.
+    """
+    m = c.shape[0]
+    if m <= DENSE_MAX_ROWS:
+        g = (c @ c.T).toarray()
+        w, v = np.linalg.eigh(g)
+        u2 = v[:, -2]
+        th2 = w[-2]
+        gap = w[-2] - (w[-3] if m >= 3 else 0.0)
+        return u2, float(th2), float(gap)
+    # large node: ARPACK on the deflated operator
+    u1 = np.sqrt(d) / math.sqrt(d.sum())
+    ct = c.T.tocsr()
+
+    def mv(x):
+        x = x - u1 * (u1 @ x)
+        y = c @ (ct @ x)
+        return y - u1 * (u1 @ y)
+
+    op = spla.LinearOperator((m, m), matvec=mv, dtype=np.float64)
+    rng = np.random.default_rng(12345)
+    v0 = rng.standard_normal(m)
+    w, v = spla.eigsh(op, k=2, which="LA", tol=1e-14, v0=v0, ncv=min(m - 1, 64), maxiter=200000)
+    order = np.argsort(w)
+    return v[:, order[-1]], float(w[order[-1]]), float(w[order[-1]] - w[order[-2]])
+
+
+# ---- A6: spectralCluster ----------------------------------------------------------
+def spectral_cluster(b: sp.csr_matrix):
+    """labels (0/1) from the sign of u2.  Returns (labels, u2, theta2, gap, d)."""
+    m = b.shape[0]
+    if m < 1:
+        return np.zeros(0, dtype=np.int8), np.zeros(0), 0.0, 0.0, np.zeros(0)
+    d = b_to_d(b)
+    if m == 1:
+        return np.zeros(1, dtype=np.int8), np.zeros(1), 0.0, 0.0, d
+    c = bd_to_c(b, d)
+    u2, th2, gap = second_left(c, d)
+    if SIGN_RULE_GE_ZERO_IS_ONE:
+        labels = (u2 >= 0).astype(np.int8)
+    else:
+        labels = (u2 > 0).astype(np.int8)
+    return labels, u2, th2, gap, d
+
+
+# ---- A7: getBModularity (modularity 0.2.1.1, Math.Modularity.Sparse) ---------------
+def get_b_modularity(labels: np.ndarray, b: sp.csr_matrix) -> float:
+    """Newman-Girvan Q of the 2-way split on A = B B^T - I (self loops removed)."""
+    m = b.shape[0]
+    ones = np.ones(m)
+    t = b.T @ ones
+    d = b @ t
+    big_l = d.sum() - m
+    if big_l == 0:
+        return 0.0
+    q = 0.0
+    for cval in (0, 1):
+        ind = (labels == cval).astype(np.float64)
+        tc = b.T @ ind
+        o_c = tc @ tc - ind.sum()
+        l_c = ind @ d - ind.sum()
+        q += o_c / big_l - (l_c / big_l) ** 2
+    return float(q)
+
+
+# ---- A0: hierarchicalSpectralCluster (call site Cluster.hs:147-156,169) ----------
+@dataclass
+class OracleTree:
+    """Flat pre-order tree, children order [label 0, label 1] (A9)."""
+    left: list = field(default_factory=list)
+    right: list = field(default_factory=list)
+    q: list = field(default_factory=list)          # Q of every vertex (leaf Q is discarded by the host)
+    theta: list = field(default_factory=list)      # sigma_2^2 of C at the node
+    gap: list = field(default_factory=list)        # theta2 - theta3 (conditioning of u2)
+    margin: list = field(default_factory=list)     # min |u2_i| / max |u2_i|  (sign margin)
+    items: list = field(default_factory=list)      # ascending original row ids of every vertex
+    u2: list = field(default_factory=list)         # optional per-node u2 (only if keep_u2)
+
+    @property
+    def n_nodes(self):
+        return len(self.left)
+
+    def leaves(self):
+        return [i for i in range(self.n_nodes) if self.left[i] < 0]
+
+    def leaf_sets(self):
+        return sorted(tuple(int(x) for x in self.items[i]) for i in self.leaves())
+
+
+def hierarchical_spectral_cluster(b2, min_modularity=0.0, min_size=1, normalize=False,
+                                  keep_u2=False, max_nodes=None) -> OracleTree:
+    """Divisive recursion `go items B` (Appendix B of SURVEY.md).
+
+    `b2` is what `hSpecClust` hands over as `Left mat`: already tf-idf scaled by
+    `loadAllSSM` (LoadMatrix.hs:218) unless normalize=True asks for idf here.
+    Rows are L2-normalised once (getB False = b2ToB . B2); children take rows of
+    the already-normalised B.
+    """
+    b2 = sp.csr_matrix(b2, dtype=np.float64)
+    if normalize:
+        b2 = b1_to_b2(b2)
+    b0 = b2_to_b(b2)
+    tree = OracleTree()
+
+    def go(rows: np.ndarray) -> int:
+        idx = tree.n_nodes
+        for lst in (tree.left, tree.right):
+            lst.append(-1)
+        tree.items.append(rows)
+        b = b0[rows]
+        m = rows.size
+        if m <= 1:
+            tree.q.append(0.0); tree.theta.append(0.0); tree.gap.append(0.0)
+            tree.margin.append(0.0); tree.u2.append(None)
+            return idx
+        labels, u2, th2, gap, _ = spectral_cluster(b)
+        q = get_b_modularity(labels, b)
+        tree.q.append(q); tree.theta.append(th2); tree.gap.append(gap)
+        au = np.abs(u2)
+        tree.margin.append(float(au.min() / au.max()) if au.max() > 0 else 0.0)
+        tree.u2.append(u2 if keep_u2 else None)
+        li = rows[labels == 0]
+        ri = rows[labels == 1]
+        ok = (q > min_modularity) if STRICT_Q_GT_MINMOD else (q >= min_modularity)
+        if ok and li.size >= max(1, min_size) and ri.size >= max(1, min_size) and m > 1:
+            if max_nodes is not None and tree.n_nodes >= max_nodes:
+                return idx
+            tree.left[idx] = go(li)
+            tree.right[idx] = go(ri)
+        return idx
+
+    import sys
+    old = sys.getrecursionlimit()
+    sys.setrecursionlimit(max(old, 100000))
+    try:
+        go(np.arange(b0.shape[0], dtype=np.int64))
+    finally:
+        sys.setrecursionlimit(old)
+    return tree
+
+
+# ---- helpers for the parity checker -------------------------------------------------
+def canonical_tree(left, right, items_of):
+    """Canonical nested form of a tree modulo child swap: frozenset of leaf item tuples per vertex."""
+    def rec(i):
+        if left[i] < 0:
+            return ("L", tuple(sorted(int(x) for x in items_of(i))))
+        a, b = rec(left[i]), rec(right[i])
+        return ("N",) + tuple(sorted((a, b)))
+    import sys
+    old = sys.getrecursionlimit()
+    sys.setrecursionlimit(max(old, 100000))
+    try:
+        return rec(0)
+    finally:
+        sys.setrecursionlimit(old)

@@ -1,0 +1,6 @@
+"""B200-native spectral-bipartition engine for `too-many-cells make-tree` (libtmc + host mirror)."""
+from . import _lib  # noqa: F401
+from .spectral import (DeviceB, ClusteringTree, TmcError, b1_to_b2, b2_to_b, b_to_d, second_left, spectral_cluster,  # noqa: F401
+                       get_b_modularity, partition_rows, spmv_pair, bench_spmv_pair, tfidf_scale_sparse_mat,
+                       hierarchical_spectral_cluster, h_spec_clust, make_opts)
+from . import tree_io  # noqa: F401

@@ -1,0 +1,760 @@
+// libtmc: host scheduler + C ABI (include/tmc.h) of the B200 spectral-bipartition engine.
+//
+// Replaces `hierarchicalSpectralCluster ... (Left mat)` as called from
+// src/TooManyCells/MakeTree/Cluster.hs:147-156,169 and `b1ToB2` as called from
+// src/TooManyCells/Matrix/Preprocess.hs:204-205.  The recursion `go items B` of the
+// reference is sequential, one node at a time, re-materialising a sparse matrix per
+// node; here the tree is a permutation with segment boundaries and every live node
+// advances in the same kernel sweep.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "../../include/tmc.h"
+#include "tmc_kernels.cuh"
+
+using namespace tmc;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      throw TmcError(e_ == cudaErrorMemoryAllocation ? TMC_ERR_NOMEM : TMC_ERR_CUDA,               \
+                     std::string(#call) + ": " + cudaGetErrorString(e_));                          \
+    }                                                                                              \
+  } while (0)
+
+struct TmcError { int code; std::string msg; TmcError(int c, std::string m) : code(c), msg(std::move(m)) {} };
+
+// ----------------------------------------------------------------------------- NCCL via dlopen (no link-time dependency)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct Nccl {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int i = 0; names[i] && !lib; ++i) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && CommDestroy && AllReduce;
+  }
+};
+static Nccl g_nccl;
+enum { NCCL_UINT8 = 1, NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+// ----------------------------------------------------------------------------- device matrix
+struct Workspace;
+struct tmc_matrix {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  int64_t* row_ptr = nullptr; int32_t* col = nullptr; double* val = nullptr;
+  bool owns = false;
+  int device = 0;
+  Workspace* ws = nullptr;
+};
+
+template <class T> static T* dalloc(size_t n) {
+  T* p = nullptr;
+  CK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  return p;
+}
+
+struct Workspace {
+  Ctx c{};
+  int K = 0, max_active = 0;
+  int64_t m = 0;
+  Report* h_rep = nullptr; Activation* h_act = nullptr; Activation* d_act = nullptr;
+  int* h_err = nullptr; unsigned long long* h_stats = nullptr;
+  cudaStream_t stream = nullptr;
+  std::vector<void*> allocs;
+  template <class T> T* A(size_t n) { T* p = dalloc<T>(n); allocs.push_back(p); return p; }
+  ~Workspace() {
+    for (void* p : allocs) cudaFree(p);
+    if (h_rep) cudaFreeHost(h_rep);
+    if (h_act) cudaFreeHost(h_act);
+    if (h_err) cudaFreeHost(h_err);
+    if (h_stats) cudaFreeHost(h_stats);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+static int pick_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) throw TmcError(TMC_ERR_NO_DEVICE, "no CUDA device: libtmc has no CPU fallback");
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  if (device >= n) throw TmcError(TMC_ERR_INVALID, "device ordinal out of range");
+  CK(cudaSetDevice(device));
+  return device;
+}
+
+static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
+  const int64_t m = b->n_rows;
+  int K = std::max(2, (int)std::min<int64_t>(o.max_lanczos > 0 ? o.max_lanczos : 320, m));
+  int max_active = (int)std::min<int64_t>(std::max<int64_t>(1, m / 2), o.max_active > 0 ? o.max_active : 2048);
+  max_active = std::min(max_active, 4096);
+  if (b->ws && b->ws->K == K && b->ws->max_active == max_active) return b->ws;
+  delete b->ws; b->ws = nullptr;
+  Workspace* w = new Workspace();
+  try {
+    w->K = K; w->max_active = max_active; w->m = m;
+    CK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    Ctx& c = w->c;
+    c.row_ptr = b->row_ptr; c.col = b->col; c.val = b->val;
+    c.n_rows = (int)m; c.n_cols = (int)b->n_cols;
+    c.perm = w->A<int>(m); c.perm_tmp = w->A<int>(m);
+    c.d = w->A<double>(m); c.sdeg = w->A<double>(m); c.xin = w->A<double>(m); c.w = w->A<double>(m); c.u2 = w->A<double>(m);
+    c.label = w->A<uint8_t>(m);
+    c.vstride = (m + 15) / 16 * 16;
+    c.V = w->A<double>((size_t)c.vstride * (K + 2));
+    c.ystride = (b->n_cols + 15) / 16 * 16;
+    c.Y = w->A<double>((size_t)c.ystride * max_active);
+    c.st = w->A<Slot>(max_active); c.rep = w->A<Report>(max_active); c.max_active = max_active;
+    c.redA = w->A<double>((size_t)(K + 2) * max_active); c.redB = w->A<double>((size_t)(K + 2) * max_active);
+    c.scal = w->A<double>((size_t)R_NSCAL * max_active);
+    c.red2 = w->A<double>(2 * (size_t)max_active);
+    c.alpha = w->A<double>((size_t)(K + 2) * max_active); c.beta = w->A<double>((size_t)(K + 2) * max_active);
+    c.zvec = w->A<double>((size_t)(K + 2) * max_active); c.scratch = w->A<double>((size_t)2 * (K + 2) * max_active);
+    c.K = K;
+    c.chunks = w->A<Chunk>((size_t)m / 8 + max_active + 8);
+    c.n_chunks = w->A<int>(1);
+    c.err = w->A<int>(1);
+    c.stats = w->A<unsigned long long>(4);
+    w->d_act = w->A<Activation>(max_active);
+    CK(cudaMemset(c.st, 0, sizeof(Slot) * max_active));
+    CK(cudaMemset(c.err, 0, sizeof(int)));
+    CK(cudaMemset(c.stats, 0, 4 * sizeof(unsigned long long)));
+    CK(cudaMemset(c.red2, 0, 2 * sizeof(double) * max_active));
+    CK(cudaMallocHost(&w->h_rep, sizeof(Report) * max_active));
+    CK(cudaMallocHost(&w->h_act, sizeof(Activation) * max_active));
+    CK(cudaMallocHost(&w->h_err, sizeof(int)));
+    CK(cudaMallocHost(&w->h_stats, 4 * sizeof(unsigned long long)));
+  } catch (...) { delete w; throw; }
+  b->ws = w;
+  return w;
+}
+
+static int err_to_status(int e, std::string* msg) {
+  switch (e) {
+    case 0: return TMC_OK;
+    case 1: *msg = "column index out of range"; return TMC_ERR_INVALID;
+    case 4: *msg = "zero-norm row (reference: NaN row -> SVDLIBC hang, LoadMatrix.hs:189-193)"; return TMC_ERR_ZERO_ROW;
+    case 5: *msg = "NaN/Inf in matrix values"; return TMC_ERR_NAN;
+    case 6: *msg = "negative matrix entry (engine requires B >= 0)"; return TMC_ERR_NEGATIVE;
+    case 7: *msg = "zero / non-finite degree in a node"; return TMC_ERR_ZERO_ROW;
+    default: *msg = "device error flag " + std::to_string(e); return TMC_ERR_CUDA;
+  }
+}
+
+// normalise the device values in place: optional idf (b1ToB2), then row L2 (b2ToB)
+static void normalise_dev(tmc_matrix* b, int normalize, double* norm_out_dev, double* idf_out_dev, bool do_l2) {
+  int* d_err = dalloc<int>(1);
+  int* df = nullptr; double* idf = nullptr;
+  try {
+    CK(cudaMemset(d_err, 0, sizeof(int)));
+    const int grid = 148 * 8;
+    if (normalize) {
+      df = dalloc<int>(b->n_cols); idf = idf_out_dev ? idf_out_dev : dalloc<double>(b->n_cols);
+      CK(cudaMemset(df, 0, sizeof(int) * b->n_cols));
+      k_df_count<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, df, d_err);
+      k_idf<<<(int)((b->n_cols + 255) / 256), 256>>>(df, (int)b->n_cols, (double)b->n_rows, idf);
+      k_idf_scale<<<grid, 256>>>(b->col, b->val, b->nnz, idf);
+    }
+    if (do_l2) k_row_l2<<<grid, 256>>>(b->row_ptr, b->col, b->val, (int)b->n_rows, (int)b->n_cols, norm_out_dev, d_err);
+    CK(cudaGetLastError());
+    int e = 0;
+    CK(cudaMemcpy(&e, d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_err); d_err = nullptr;
+    if (df) cudaFree(df);
+    if (idf && !idf_out_dev) cudaFree(idf);
+    df = nullptr; idf = nullptr;
+    std::string msg;
+    int st = err_to_status(e, &msg);
+    if (st != TMC_OK) throw TmcError(st, msg);
+  } catch (...) {
+    if (d_err) cudaFree(d_err);
+    if (df) cudaFree(df);
+    if (idf && !idf_out_dev) cudaFree(idf);
+    throw;
+  }
+}
+
+static void validate_csr(const tmc_csr* a) {
+  if (!a || !a->row_ptr || (a->nnz > 0 && (!a->col_idx || !a->val))) throw TmcError(TMC_ERR_INVALID, "null CSR pointer");
+  if (a->n_rows < 0 || a->n_cols < 0 || a->nnz < 0) throw TmcError(TMC_ERR_INVALID, "negative dimension");
+  if (a->n_rows >= (int64_t)1 << 31 || a->n_cols >= (int64_t)1 << 31) throw TmcError(TMC_ERR_INVALID, "dimension exceeds int32");
+  if (a->row_ptr[0] != 0 || a->row_ptr[a->n_rows] != a->nnz) throw TmcError(TMC_ERR_INVALID, "row_ptr does not span [0, nnz]");
+}
+
+static tmc_matrix* upload(const tmc_csr* a, int device) {
+  validate_csr(a);
+  tmc_matrix* b = new tmc_matrix();
+  try {
+    b->device = pick_device(device);
+    b->n_rows = a->n_rows; b->n_cols = a->n_cols; b->nnz = a->nnz; b->owns = true;
+    b->row_ptr = dalloc<int64_t>(a->n_rows + 1); b->col = dalloc<int32_t>(a->nnz); b->val = dalloc<double>(a->nnz);
+    CK(cudaMemcpy(b->row_ptr, a->row_ptr, sizeof(int64_t) * (a->n_rows + 1), cudaMemcpyHostToDevice));
+    if (a->nnz) {
+      CK(cudaMemcpy(b->col, a->col_idx, sizeof(int32_t) * a->nnz, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(b->val, a->val, sizeof(double) * a->nnz, cudaMemcpyHostToDevice));
+    }
+  } catch (...) { tmc_matrix_free(b); throw; }
+  return b;
+}
+
+// ----------------------------------------------------------------------------- the scheduler
+struct HostNode { int begin, end, parent, left, right, iters; double q, theta; };
+
+struct Engine {
+  tmc_matrix* b; Workspace* w; tmc_opts o; Ctx c; cudaStream_t s;
+  std::vector<int> hstate, slot_node, free_slots;
+  std::vector<HostNode> nodes;
+  std::deque<int> pending;
+  int hi_slot = 0;
+  int64_t n_sweeps = 0, n_launch = 0;
+  double alg_vec_bytes = 0;     // non-matrix part of the spmv_pair algorithmic bytes
+  bool profile = false;
+  std::vector<cudaEvent_t> evs;
+
+  Engine(tmc_matrix* b_, const tmc_opts& o_) : b(b_), o(o_) {
+    pick_device(b->device);
+    w = get_workspace(b, o);
+    c = w->c; s = w->stream;
+    c.tol = o.tol > 0 ? o.tol : 1e-10;
+    c.min_modularity = o.min_modularity; c.min_size = std::max(1, o.min_size);
+    c.max_restarts = o.max_restarts >= 0 ? o.max_restarts : 8; c.seed = o.seed;
+    c.rank = g_nccl.comm ? g_nccl.rank : 0; c.world = g_nccl.comm ? g_nccl.world : 1;
+    hstate.assign(w->max_active, ST_IDLE); slot_node.assign(w->max_active, -1);
+    for (int i = w->max_active - 1; i >= 0; --i) free_slots.push_back(i);
+    profile = o.profile != 0;
+    CK(cudaMemsetAsync(c.st, 0, sizeof(Slot) * w->max_active, s));
+    CK(cudaMemsetAsync(c.err, 0, sizeof(int), s));
+    CK(cudaMemsetAsync(c.stats, 0, 4 * sizeof(unsigned long long), s));
+  }
+  ~Engine() { for (auto e : evs) cudaEventDestroy(e); }
+
+  void init_perm(const int64_t* rows, int64_t n_sel) {
+    const int m = (int)b->n_rows;
+    if (!rows) {
+      k_iota<<<(m + 255) / 256, 256, 0, s>>>(c.perm, m);
+    } else {
+      std::vector<int> h(n_sel);
+      for (int64_t i = 0; i < n_sel; ++i) {
+        if (rows[i] < 0 || rows[i] >= m) throw TmcError(TMC_ERR_INVALID, "row id out of range");
+        h[i] = (int)rows[i];
+      }
+      CK(cudaMemcpyAsync(c.perm, h.data(), sizeof(int) * n_sel, cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));
+    }
+  }
+
+  int activate_pending(int stop_after) {
+    int n = 0;
+    while (!pending.empty() && !free_slots.empty()) {
+      int node = pending.front(); pending.pop_front();
+      int slot = free_slots.back(); free_slots.pop_back();
+      w->h_act[n++] = Activation{slot, nodes[node].begin, nodes[node].end, node, stop_after};
+      hstate[slot] = ST_DEG; slot_node[slot] = node;
+      hi_slot = std::max(hi_slot, slot + 1);
+    }
+    if (n) {
+      CK(cudaMemcpyAsync(w->d_act, w->h_act, sizeof(Activation) * n, cudaMemcpyHostToDevice, s));
+      k_activate<<<(n + 127) / 128, 128, 0, s>>>(c, w->d_act, n); n_launch++;
+    }
+    return n;
+  }
+
+  cudaEvent_t ev() { cudaEvent_t e; CK(cudaEventCreate(&e)); evs.push_back(e); CK(cudaEventRecord(e, s)); return e; }
+
+  struct ProfPair { cudaEvent_t a, b, c; };
+  std::vector<ProfPair> prof_pairs;
+
+  void nccl_check(int r, const char* what) {
+    if (r != 0) throw TmcError(TMC_ERR_COMM, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  }
+  void allreduce_f64(double* p, size_t n) {
+    if (c.world > 1 && n) nccl_check(g_nccl.AllReduce(p, p, n, NCCL_FLOAT64, NCCL_SUM, g_nccl.comm, s), "ncclAllReduce(f64)");
+  }
+  void allreduce_u8(uint8_t* p, size_t n) {
+    if (c.world > 1 && n) nccl_check(g_nccl.AllReduce(p, p, n, NCCL_UINT8, NCCL_SUM, g_nccl.comm, s), "ncclAllReduce(u8)");
+  }
+  int local_len(int len) const { return (int)((int64_t)len * (c.rank + 1) / c.world) - (int)((int64_t)len * c.rank / c.world); }
+
+  // One sweep: every live slot advances by one step of its lifecycle
+  // (degree pass | start-vector orthogonalisation | Lanczos step | modularity + split).
+  void sweep(bool only_spmv = false) {
+    int n_sc = 0, n_ga = 0, n_mod = 0, n_or = 0, live_n = 0; int64_t rows = 0;
+    int mod_lo = INT32_MAX, mod_hi = 0;
+    for (int sl = 0; sl < hi_slot; ++sl) {
+      int st = hstate[sl];
+      if (st < ST_DEG || st > ST_MOD) continue;
+      live_n++;
+      const HostNode& nd = nodes[slot_node[sl]];
+      int len = nd.end - nd.begin;
+      rows += local_len(len);
+      if (st == ST_DEG || st == ST_LAN || st == ST_MOD) n_sc++;
+      if (st == ST_DEG || st == ST_LAN) { n_ga++; alg_vec_bytes += 16.0 * (len + 1) + 32.0 * len + 16.0 * (double)b->n_cols; }
+      if (st == ST_MOD) { n_mod++; mod_lo = std::min(mod_lo, nd.begin); mod_hi = std::max(mod_hi, nd.end); }
+      if (st == ST_ORTH0 || st == ST_LAN) n_or++;
+    }
+    if (!live_n) return;
+    int R = 8;
+    if (rows > 8 * 2368) R = (int)std::min<int64_t>(TMC_MAX_CHUNK, ((rows / 2368) + 7) / 8 * 8);
+    c.chunk_rows = R; c.n_slots = hi_slot;
+    int nch = 0;
+    for (int sl = 0; sl < hi_slot; ++sl) {
+      int st = hstate[sl];
+      if (st < ST_DEG || st > ST_MOD) continue;
+      const HostNode& nd = nodes[slot_node[sl]];
+      nch += (local_len(nd.end - nd.begin) + R - 1) / R;
+    }
+    const int ny = std::max(1, (int)std::min<int64_t>(64, c.ystride / 8192));
+    k_prepare<<<1, 1024, 0, s>>>(c); n_launch++;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    if (n_sc) {
+      k_zero_y<<<dim3(hi_slot, ny), 256, 0, s>>>(c); n_launch++;
+      if (profile) e0 = ev();
+      if (nch) { k_scatter<<<nch, 256, 0, s>>>(c); n_launch++; }
+      if (profile) e1 = ev();
+      allreduce_f64(c.Y, (size_t)c.ystride * hi_slot);
+    }
+    if (n_ga && nch) { k_gather<<<nch, 256, 0, s>>>(c); n_launch++; }
+    if (profile && n_sc) { e2 = ev(); prof_pairs.push_back({e0, e1, e2}); }
+    if (only_spmv) { CK(cudaGetLastError()); return; }
+    if (n_mod) { k_ynorm<<<dim3(hi_slot, ny), 256, 0, s>>>(c); n_launch++; }
+    const size_t upd_smem = sizeof(double) * ((size_t)c.K + 2 + 8 * (size_t)R);
+    if (n_or && nch) {
+      k_dots<<<nch, 256, 0, s>>>(c, 0); n_launch++;
+      allreduce_f64(c.redA, (size_t)(c.K + 2) * hi_slot);
+      k_update<<<nch, 256, upd_smem, s>>>(c, 0); n_launch++;
+      k_dots<<<nch, 256, 0, s>>>(c, 1); n_launch++;
+      allreduce_f64(c.redB, (size_t)(c.K + 2) * hi_slot);
+      k_update<<<nch, 256, upd_smem, s>>>(c, 1); n_launch++;
+    }
+    allreduce_f64(c.scal, (size_t)R_NSCAL * hi_slot);
+    k_finish<<<(hi_slot * 32 + 255) / 256, 256, 0, s>>>(c); n_launch++;
+    if (nch) { k_advance<<<nch, 256, 0, s>>>(c); n_launch++; }
+    allreduce_f64(c.red2, 2 * (size_t)hi_slot);
+    if (n_mod) {
+      if (c.world > 1) {
+        k_mask_labels<<<hi_slot, 256, 0, s>>>(c); n_launch++;
+        allreduce_u8(c.label + mod_lo, (size_t)(mod_hi - mod_lo));
+      }
+      k_partition<<<hi_slot, 1024, 0, s>>>(c); n_launch++;
+    }
+    k_commit<<<(hi_slot + 127) / 128, 128, 0, s>>>(c, hi_slot); n_launch++;
+    CK(cudaMemcpyAsync(w->h_rep, c.rep, sizeof(Report) * hi_slot, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(w->h_err, c.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    n_sweeps++;
+    if (*w->h_err) { std::string msg; int st = err_to_status(*w->h_err, &msg); throw TmcError(st, msg); }
+  }
+
+  // harvest reports: update host mirror, record finished nodes, enqueue children
+  void harvest(bool build_tree) {
+    for (int sl = 0; sl < hi_slot; ++sl) {
+      if (hstate[sl] < ST_DEG || hstate[sl] > ST_MOD) continue;
+      const Report& r = w->h_rep[sl];
+      hstate[sl] = r.state;
+      if (r.state != ST_DONE) continue;
+      int node = slot_node[sl];
+      HostNode& nd = nodes[node];
+      nd.q = r.q; nd.theta = r.theta; nd.iters = r.iters;
+      if (build_tree && r.split) {
+        int b0 = nd.begin, e0 = nd.end, n0 = r.n0;
+        int li = (int)nodes.size(), ri = li + 1;
+        nodes[node].left = li; nodes[node].right = ri;
+        nodes.push_back(HostNode{b0, b0 + n0, node, -1, -1, 0, 0.0, 0.0});
+        nodes.push_back(HostNode{b0 + n0, e0, node, -1, -1, 0, 0.0, 0.0});
+        if (n0 >= 2) pending.push_back(li);
+        if (e0 - b0 - n0 >= 2) pending.push_back(ri);
+      }
+      hstate[sl] = ST_IDLE; slot_node[sl] = -1; free_slots.push_back(sl);
+    }
+    while (hi_slot > 0 && hstate[hi_slot - 1] == ST_IDLE) hi_slot--;
+  }
+
+  int live() const { int n = 0; for (int sl = 0; sl < hi_slot; ++sl) n += (hstate[sl] >= ST_DEG && hstate[sl] <= ST_MOD); return n; }
+
+  void run_tree() {
+    const int m = (int)b->n_rows;
+    nodes.clear(); pending.clear();
+    nodes.push_back(HostNode{0, m, -1, -1, -1, 0, 0.0, 0.0});
+    if (m >= 2) pending.push_back(0);
+    for (;;) {
+      activate_pending(0);
+      if (!live()) break;
+      sweep();
+      harvest(true);
+    }
+  }
+
+  // run slot 0 over rows [0,n) until it reports DONE
+  void run_single(int n, int stop_after) {
+    nodes.clear(); pending.clear();
+    nodes.push_back(HostNode{0, n, -1, -1, -1, 0, 0.0, 0.0});
+    pending.push_back(0);
+    activate_pending(stop_after);
+    const int64_t cap = (int64_t)(w->K + 8) * (c.max_restarts + 2) + 16;     // Lanczos always terminates within this
+    for (int64_t it = 0; live(); ++it) {
+      if (it > cap) throw TmcError(TMC_ERR_CUDA, "internal: node did not finish within the sweep cap");
+      sweep(); harvest(false);
+    }
+  }
+};
+
+// ----------------------------------------------------------------------------- C ABI
+template <class F> static int guarded(F&& f) {
+  try { f(); g_err.clear(); return TMC_OK; }
+  catch (const TmcError& e) { return fail(e.code, e.msg); }
+  catch (const std::bad_alloc&) { return fail(TMC_ERR_NOMEM, "host allocation failed"); }
+  catch (const std::exception& e) { return fail(TMC_ERR_INVALID, e.what()); }
+}
+
+extern "C" {
+
+void tmc_opts_default(tmc_opts* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->eigen_group = 0; o->num_eigen = 1; o->min_modularity = 0.0; o->min_size = 1; o->normalize = 0; o->num_runs = 0;
+  o->seed = 0x2545F4914F6CDD1Dull; o->tol = 1e-10; o->max_lanczos = 320; o->max_restarts = 8; o->max_active = 2048; o->device = -1;
+}
+const char* tmc_last_error(void) { return g_err.c_str(); }
+const char* tmc_version(void) { return "libtmc 0.1 (sm_100a)"; }
+int tmc_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+static void check_opts(const tmc_opts* o) {
+  if (!o) throw TmcError(TMC_ERR_INVALID, "null opts");
+  if (o->eigen_group != 0) throw TmcError(TMC_ERR_UNSUPPORTED, "eigen_group KMeansGroup is not implemented (SURVEY 8(f) N4)");
+  if (o->num_runs > 0) throw TmcError(TMC_ERR_UNSUPPORTED, "permutation test (--numRuns) is not implemented (SURVEY 8(f) N4)");
+}
+
+int tmc_tfidf(const tmc_csr* b1, double* val_out, double* idf_out) {
+  return guarded([&] {
+    if (!val_out) throw TmcError(TMC_ERR_INVALID, "null val_out");
+    tmc_matrix* b = upload(b1, -1);
+    double* idf_dev = nullptr;
+    try {
+      idf_dev = dalloc<double>(b->n_cols);
+      normalise_dev(b, 1, nullptr, idf_dev, false);
+      if (b->nnz) CK(cudaMemcpy(val_out, b->val, sizeof(double) * b->nnz, cudaMemcpyDeviceToHost));
+      if (idf_out) CK(cudaMemcpy(idf_out, idf_dev, sizeof(double) * b->n_cols, cudaMemcpyDeviceToHost));
+    } catch (...) { if (idf_dev) cudaFree(idf_dev); tmc_matrix_free(b); throw; }
+    cudaFree(idf_dev); tmc_matrix_free(b);
+  });
+}
+
+int tmc_row_l2(const tmc_csr* b2, double* val_out, double* norm_out) {
+  return guarded([&] {
+    if (!val_out) throw TmcError(TMC_ERR_INVALID, "null val_out");
+    tmc_matrix* b = upload(b2, -1);
+    double* nd = nullptr;
+    try {
+      nd = dalloc<double>(b->n_rows);
+      normalise_dev(b, 0, nd, nullptr, true);
+      if (b->nnz) CK(cudaMemcpy(val_out, b->val, sizeof(double) * b->nnz, cudaMemcpyDeviceToHost));
+      if (norm_out) CK(cudaMemcpy(norm_out, nd, sizeof(double) * b->n_rows, cudaMemcpyDeviceToHost));
+    } catch (...) { if (nd) cudaFree(nd); tmc_matrix_free(b); throw; }
+    cudaFree(nd); tmc_matrix_free(b);
+  });
+}
+
+int tmc_matrix_upload(const tmc_csr* b2, int normalize, int device, tmc_matrix** out) {
+  return guarded([&] {
+    if (!out) throw TmcError(TMC_ERR_INVALID, "null out");
+    tmc_matrix* b = upload(b2, device);
+    try { normalise_dev(b, normalize, nullptr, nullptr, true); } catch (...) { tmc_matrix_free(b); throw; }
+    *out = b;
+  });
+}
+
+int tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* row_ptr_dev, const int32_t* col_dev,
+                         double* val_dev, int normalize, int device, tmc_matrix** out) {
+  return guarded([&] {
+    if (!out || !row_ptr_dev || !col_dev || !val_dev) throw TmcError(TMC_ERR_INVALID, "null pointer");
+    if (n_rows >= (int64_t)1 << 31 || n_cols >= (int64_t)1 << 31) throw TmcError(TMC_ERR_INVALID, "dimension exceeds int32");
+    tmc_matrix* b = new tmc_matrix();
+    try {
+      b->device = pick_device(device);
+      b->n_rows = n_rows; b->n_cols = n_cols; b->nnz = nnz; b->owns = false;
+      b->row_ptr = const_cast<int64_t*>(row_ptr_dev); b->col = const_cast<int32_t*>(col_dev); b->val = val_dev;
+      normalise_dev(b, normalize, nullptr, nullptr, true);
+    } catch (...) { tmc_matrix_free(b); throw; }
+    *out = b;
+  });
+}
+
+void tmc_matrix_free(tmc_matrix* b) {
+  if (!b) return;
+  delete b->ws;
+  if (b->owns) { cudaFree(b->row_ptr); cudaFree(b->col); cudaFree(b->val); }
+  delete b;
+}
+
+struct TreeStorage {
+  tmc_tree t;
+  std::vector<int64_t> left, right, parent, item_begin, item_end, perm;
+  std::vector<double> q, theta; std::vector<int32_t> iters;
+};
+
+int tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out) {
+  return guarded([&] {
+    if (!b || !out) throw TmcError(TMC_ERR_INVALID, "null pointer");
+    check_opts(opts);
+    if (b->n_rows < 1) throw TmcError(TMC_ERR_INVALID, "empty matrix (reference: error, LoadMatrix.hs:255)");
+    Engine eng(b, *opts);
+    cudaEvent_t t0, t1;
+    CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+    CK(cudaEventRecord(t0, eng.s));
+    eng.init_perm(nullptr, 0);
+    eng.run_tree();
+    CK(cudaEventRecord(t1, eng.s));
+    const int m = (int)b->n_rows;
+    std::vector<int> hperm(m);
+    CK(cudaMemcpyAsync(hperm.data(), eng.c.perm, sizeof(int) * m, cudaMemcpyDeviceToHost, eng.s));
+    CK(cudaMemcpyAsync(eng.w->h_stats, eng.c.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, eng.s));
+    CK(cudaStreamSynchronize(eng.s));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, t0, t1));
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    // pre-order renumbering, children [label 0, label 1]  (birch-beer treeToGraph, Cluster.hs:171-181)
+    const size_t nn = eng.nodes.size();
+    TreeStorage* ts = new TreeStorage();
+    ts->left.assign(nn, -1); ts->right.assign(nn, -1); ts->parent.assign(nn, -1);
+    ts->item_begin.resize(nn); ts->item_end.resize(nn); ts->q.resize(nn); ts->theta.resize(nn); ts->iters.resize(nn);
+    std::vector<int64_t> newid(nn, -1); std::vector<int> stack; stack.push_back(0); int64_t next = 0;
+    std::vector<int> order; order.reserve(nn);
+    while (!stack.empty()) {
+      int u = stack.back(); stack.pop_back();
+      newid[u] = next++; order.push_back(u);
+      if (eng.nodes[u].left >= 0) { stack.push_back(eng.nodes[u].right); stack.push_back(eng.nodes[u].left); }
+    }
+    for (int u : order) {
+      const HostNode& nd = eng.nodes[u]; int64_t id = newid[u];
+      ts->left[id] = nd.left >= 0 ? newid[nd.left] : -1; ts->right[id] = nd.right >= 0 ? newid[nd.right] : -1;
+      ts->parent[id] = nd.parent >= 0 ? newid[nd.parent] : -1;
+      ts->item_begin[id] = nd.begin; ts->item_end[id] = nd.end; ts->q[id] = nd.q; ts->theta[id] = nd.theta; ts->iters[id] = nd.iters;
+    }
+    ts->perm.assign(hperm.begin(), hperm.end());
+    tmc_tree& t = ts->t;
+    t.n_nodes = (int64_t)nn; t.n_rows = m;
+    t.left = ts->left.data(); t.right = ts->right.data(); t.parent = ts->parent.data(); t.q = ts->q.data(); t.theta = ts->theta.data();
+    t.iters = ts->iters.data(); t.item_begin = ts->item_begin.data(); t.item_end = ts->item_end.data(); t.perm = ts->perm.data();
+    t.n_sweeps = eng.n_sweeps; t.spmv_pairs_nnz = (int64_t)(eng.w->h_stats[0] + eng.w->h_stats[1]); t.kernel_launches = eng.n_launch;
+    t.engine_ms = ms; t.spmv_ms = 0.0;
+    if (eng.profile) {
+      double tot = 0; for (auto& p : eng.prof_pairs) { float a = 0; cudaEventElapsedTime(&a, p.a, p.c); tot += a; }
+      t.spmv_ms = tot;
+    }
+    t.spmv_alg_bytes = 24.0 * (double)t.spmv_pairs_nnz + eng.alg_vec_bytes;
+    *out = &ts->t;
+  });
+}
+
+int tmc_make_tree(const tmc_csr* b2, const tmc_opts* opts, tmc_tree** out) {
+  tmc_matrix* b = nullptr;
+  if (!opts) return fail(TMC_ERR_INVALID, "null opts");
+  int st = tmc_matrix_upload(b2, opts->normalize, opts->device, &b);
+  if (st != TMC_OK) return st;
+  st = tmc_make_tree_dev(b, opts, out);
+  std::string keep = g_err;
+  tmc_matrix_free(b);
+  g_err = keep;
+  return st;
+}
+
+void tmc_tree_free(tmc_tree* t) {
+  if (!t) return;
+  delete reinterpret_cast<TreeStorage*>(t);   // tmc_tree is the first member
+}
+
+// ---- fine-grained exports, each through the same kernels as the tree build
+static int64_t sel_count(tmc_matrix* b, const int64_t* rows, int64_t n_sel) {
+  if (!b) throw TmcError(TMC_ERR_INVALID, "null matrix");
+  int64_t n = rows ? n_sel : b->n_rows;
+  if (n < 1 || n > b->n_rows) throw TmcError(TMC_ERR_INVALID, "bad row selection size");
+  return n;
+}
+
+int tmc_degree(tmc_matrix* b, const int64_t* rows, int64_t n_sel, double* d_out) {
+  return guarded([&] {
+    int64_t n = sel_count(b, rows, n_sel);
+    if (!d_out) throw TmcError(TMC_ERR_INVALID, "null d_out");
+    tmc_opts o; tmc_opts_default(&o);
+    Engine eng(b, o);
+    eng.init_perm(rows, n);
+    eng.run_single((int)n, ST_ORTH0);
+    CK(cudaMemcpyAsync(d_out, eng.c.d, sizeof(double) * n, cudaMemcpyDeviceToHost, eng.s));
+    CK(cudaStreamSynchronize(eng.s));
+  });
+}
+
+int tmc_second_left(tmc_matrix* b, const int64_t* rows, int64_t n_sel, const tmc_opts* opts, double* u2_out,
+                    double* theta_out, int32_t* iters_out) {
+  return guarded([&] {
+    int64_t n = sel_count(b, rows, n_sel);
+    check_opts(opts);
+    if (n < 2) throw TmcError(TMC_ERR_INVALID, "second_left needs at least 2 rows");
+    Engine eng(b, *opts);
+    eng.init_perm(rows, n);
+    eng.run_single((int)n, ST_MOD);
+    if (u2_out) CK(cudaMemcpyAsync(u2_out, eng.c.u2, sizeof(double) * n, cudaMemcpyDeviceToHost, eng.s));
+    CK(cudaStreamSynchronize(eng.s));
+    if (theta_out) *theta_out = eng.nodes[0].theta;
+    if (iters_out) *iters_out = eng.nodes[0].iters;
+  });
+}
+
+int tmc_modularity(tmc_matrix* b, const int64_t* rows, int64_t n_sel, const uint8_t* labels, double* q_out) {
+  return guarded([&] {
+    int64_t n = sel_count(b, rows, n_sel);
+    if (!labels || !q_out) throw TmcError(TMC_ERR_INVALID, "null pointer");
+    tmc_opts o; tmc_opts_default(&o);
+    Engine eng(b, o);
+    eng.init_perm(rows, n);
+    eng.run_single((int)n, ST_ORTH0);                     // degree pass: d, sum d
+    uint8_t* dl = dalloc<uint8_t>(n);
+    try {
+      CK(cudaMemcpyAsync(dl, labels, n, cudaMemcpyHostToDevice, eng.s));
+      // re-open slot 0 directly in the modularity state with the caller's labels
+      eng.nodes.clear(); eng.nodes.push_back(HostNode{0, (int)n, -1, -1, -1, 0, 0.0, 0.0});
+      eng.hstate[0] = ST_MOD; eng.slot_node[0] = 0; eng.hi_slot = 1;
+      eng.free_slots.erase(std::remove(eng.free_slots.begin(), eng.free_slots.end(), 0), eng.free_slots.end());
+      k_force_state<<<1, 1, 0, eng.s>>>(eng.c, 0, ST_MOD, 0, ST_DONE);
+      k_set_labels<<<(int)((n + 255) / 256), 256, 0, eng.s>>>(eng.c, dl, (int)n, 0);
+      while (eng.live()) { eng.sweep(); eng.harvest(false); }
+      *q_out = eng.nodes[0].q;
+    } catch (...) { cudaFree(dl); throw; }
+    cudaFree(dl);
+  });
+}
+
+int tmc_partition(const int64_t* rows, int64_t n_sel, const uint8_t* labels, int64_t* rows_out, int64_t* n_left) {
+  return guarded([&] {
+    if (!rows || !labels || !rows_out || n_sel < 0) throw TmcError(TMC_ERR_INVALID, "null pointer");
+    pick_device(-1);
+    const int n = (int)n_sel;
+    std::vector<int> h(n); int n1 = 0;
+    for (int i = 0; i < n; ++i) { h[i] = (int)rows[i]; n1 += labels[i] ? 1 : 0; }
+    Ctx c{};
+    int* perm = dalloc<int>(n); int* tmp = dalloc<int>(n); uint8_t* lab = dalloc<uint8_t>(n); Slot* st = dalloc<Slot>(1);
+    try {
+      c.perm = perm; c.perm_tmp = tmp; c.label = lab; c.st = st;
+      std::vector<uint8_t> l01(n); for (int i = 0; i < n; ++i) l01[i] = labels[i] ? 1 : 0;
+      CK(cudaMemcpy(perm, h.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(lab, l01.data(), n, cudaMemcpyHostToDevice));
+      k_force_partition<<<1, 1>>>(c, 0, 0, n, n - n1);
+      k_partition<<<1, 1024>>>(c);
+      CK(cudaGetLastError());
+      CK(cudaMemcpy(h.data(), perm, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    } catch (...) { cudaFree(perm); cudaFree(tmp); cudaFree(lab); cudaFree(st); throw; }
+    cudaFree(perm); cudaFree(tmp); cudaFree(lab); cudaFree(st);
+    for (int i = 0; i < n; ++i) rows_out[i] = h[i];
+    if (n_left) *n_left = n - n1;
+  });
+}
+
+// set slot 0 up over rows [0,n) in the Lanczos state with xin = D^{-1/2} x  (degree pass first)
+static void setup_pair(Engine& eng, const int64_t* rows, int64_t n, const double* x_dev) {
+  eng.init_perm(rows, n);
+  eng.run_single((int)n, ST_ORTH0);
+  eng.nodes.clear(); eng.nodes.push_back(HostNode{0, (int)n, -1, -1, -1, 0, 0.0, 0.0});
+  eng.hstate[0] = ST_LAN; eng.slot_node[0] = 0; eng.hi_slot = 1;
+  eng.free_slots.erase(std::remove(eng.free_slots.begin(), eng.free_slots.end(), 0), eng.free_slots.end());
+  k_force_state<<<1, 1, 0, eng.s>>>(eng.c, 0, ST_LAN, 1, 0);
+  k_set_xin_scaled<<<(int)((n + 255) / 256), 256, 0, eng.s>>>(eng.c, x_dev, (int)n);
+}
+
+int tmc_spmv_pair(tmc_matrix* b, const int64_t* rows, int64_t n_sel, const double* x, double* x_out) {
+  return guarded([&] {
+    int64_t n = sel_count(b, rows, n_sel);
+    if (!x || !x_out) throw TmcError(TMC_ERR_INVALID, "null pointer");
+    tmc_opts o; tmc_opts_default(&o);
+    Engine eng(b, o);
+    double* xd = dalloc<double>(n);
+    try {
+      CK(cudaMemcpy(xd, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+      setup_pair(eng, rows, n, xd);
+      eng.sweep(true);
+      CK(cudaMemcpyAsync(x_out, eng.c.w, sizeof(double) * n, cudaMemcpyDeviceToHost, eng.s));
+      CK(cudaStreamSynchronize(eng.s));
+      CK(cudaGetLastError());
+    } catch (...) { cudaFree(xd); throw; }
+    cudaFree(xd);
+  });
+}
+
+int tmc_bench_spmv_pair(tmc_matrix* b, int reps, double* scatter_ms, double* gather_ms) {
+  return guarded([&] {
+    int64_t n = sel_count(b, nullptr, 0);
+    if (reps < 1) reps = 1;
+    tmc_opts o; tmc_opts_default(&o);
+    Engine eng(b, o);
+    std::vector<double> hx(n);
+    for (int64_t i = 0; i < n; ++i) hx[i] = 1.0 / (1.0 + (double)(i % 7));
+    double* xd = dalloc<double>(n);
+    try {
+      CK(cudaMemcpy(xd, hx.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+      setup_pair(eng, nullptr, n, xd);
+      eng.profile = true;
+      for (int r = 0; r < reps + 2; ++r) eng.sweep(true);
+      CK(cudaStreamSynchronize(eng.s));
+      double sc = 0, ga = 0;
+      for (int r = 2; r < reps + 2; ++r) {
+        float a = 0, g = 0;
+        CK(cudaEventElapsedTime(&a, eng.prof_pairs[r].a, eng.prof_pairs[r].b));
+        CK(cudaEventElapsedTime(&g, eng.prof_pairs[r].b, eng.prof_pairs[r].c));
+        sc += a; ga += g;
+      }
+      if (scatter_ms) *scatter_ms = sc / reps;
+      if (gather_ms) *gather_ms = ga / reps;
+    } catch (...) { cudaFree(xd); throw; }
+    cudaFree(xd);
+  });
+}
+
+// ---- multi-GPU plumbing: NCCL communicator owned by the library (one process per GPU)
+int tmc_comm_unique_id(uint8_t id_out[128]) {
+  return guarded([&] {
+    if (!g_nccl.load()) throw TmcError(TMC_ERR_COMM, "libnccl.so.2 not found (dlopen)");
+    ncclUniqueId id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclGetUniqueId failed");
+    memcpy(id_out, id.internal, 128);
+  });
+}
+int tmc_comm_init(const uint8_t id_in[128], int rank, int world, int device) {
+  return guarded([&] {
+    if (!g_nccl.load()) throw TmcError(TMC_ERR_COMM, "libnccl.so.2 not found (dlopen)");
+    if (g_nccl.comm) throw TmcError(TMC_ERR_COMM, "communicator already initialised");
+    pick_device(device);
+    ncclUniqueId id; memcpy(id.internal, id_in, 128);
+    ncclComm_t comm = nullptr;
+    int r = g_nccl.CommInitRank(&comm, world, id, rank);
+    if (r != 0) throw TmcError(TMC_ERR_COMM, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    g_nccl.comm = comm; g_nccl.rank = rank; g_nccl.world = world;
+  });
+}
+void tmc_comm_destroy(void) {
+  if (g_nccl.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g_nccl.comm);
+  g_nccl.comm = nullptr; g_nccl.rank = 0; g_nccl.world = 1;
+}
+
+}  // extern "C"

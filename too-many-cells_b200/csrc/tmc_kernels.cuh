@@ -1,0 +1,609 @@
+// sm_100a kernels of the spectral-bipartition engine.
+//
+// Data model (DESIGN.md "HBM layout"): one immutable CSR of B (row-L2-normalised
+// tf-idf values) and a permutation `perm` of row ids; every live tree node owns a
+// contiguous position range [begin,end) of `perm` (quicksort-style), so all
+// per-cell vectors (degree, Lanczos basis, labels) are position-indexed and a
+// single launch advances EVERY live node by one step ("sweep").  No matrix is
+// ever re-materialised per node, unlike the reference's IntMap copies
+// (SURVEY.md 8(a) A3/A8).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tmc_tridiag.cuh"
+
+namespace tmc {
+
+enum SlotState : int { ST_IDLE = 0, ST_DEG = 1, ST_ORTH0 = 2, ST_LAN = 3, ST_MOD = 4, ST_DONE = 5 };
+enum SlotAction : int { ACT_NONE = 0, ACT_INIT = 1, ACT_NEXT = 2, ACT_RITZ_LABEL = 3, ACT_RITZ_RESTART = 4, ACT_FINISH = 5 };
+
+// scalar slots at the tail of a reduction row
+enum { R_NRM2 = 0, R_SUMD = 1, R_YNORM2 = 2, R_NSCAL = 4 };
+
+struct Slot {              // one live tree node (device resident)
+  int begin, end;          // position range in perm
+  int lbegin, lend;        // this rank's share of the range (row sharding)
+  int state, action;
+  int j;                   // Lanczos vectors q_1..q_j stored in V[1..j]
+  int iters, restarts;
+  int node;                // host node id
+  int split, n0;
+  int stop_after;          // 0 = full lifecycle, else stop when reaching this state (fine-grained API)
+  int pad;
+  double sumd, inv_sqrt_sumd, beta, theta, resid, q, theta_hint;
+};
+
+struct Report {            // what the host reads back after every sweep
+  int state, split, n0, iters;
+  double q, theta;
+};
+
+struct Chunk { int slot, begin, len; };
+struct Activation { int slot, begin, end, node, stop_after; };
+
+struct Ctx {
+  // matrix B (CSR, rows = cells)
+  const int64_t* row_ptr; const int32_t* col; const double* val;
+  int n_rows, n_cols;
+  // position-indexed state
+  int* perm; int* perm_tmp;
+  double* d; double* sdeg; double* xin; double* w; double* u2; uint8_t* label;
+  double* V; int64_t vstride;      // basis arena V[l*vstride + p], l = 0 is the locked u1
+  double* Y; int64_t ystride;      // per-slot feature vectors y = B_S^T x
+  // per-slot state
+  Slot* st; Report* rep; int max_active;
+  double* redA; double* redB;      // [slot][K+2]: CGS pass-0 / pass-1 coefficients h_l = <V_l, w>
+  double* scal;                    // [slot][R_NSCAL]
+  int n_slots;                     // slots [0, n_slots) may be live this sweep
+  double* red2;                    // [slot][2] : n1, sum_{c1} d (accumulated by k_advance)
+  double* alpha; double* beta; double* zvec; double* scratch;   // [slot][K+2] (scratch: 2*(K+2))
+  int K;
+  Chunk* chunks; int* n_chunks; int chunk_rows;
+  int* err;                        // device error flag
+  unsigned long long* stats;       // [0] nnz gathered in Lanczos pairs, [1] nnz gathered in degree pairs
+  // options
+  double tol, min_modularity; int min_size, max_restarts; uint64_t seed;
+  int rank, world;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum for 256-thread CTAs; result valid on thread 0
+__device__ __forceinline__ double block_sum_256(double v, double* sm8) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sm8[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x < 32) {
+    t = (threadIdx.x < (blockDim.x >> 5)) ? sm8[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+  }
+  __syncthreads();
+  return t;
+}
+
+__device__ __forceinline__ double hash_unit(uint64_t seed, uint64_t row) {
+  uint64_t x = seed + (row + 1) * 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  x = x ^ (x >> 31);
+  return (double)(x >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+
+// ------------------------------------------------------------------ load-time kernels (K1, K2)
+// K1: df_j = #{entries > 0 in column j}  (b1ToB2)
+__global__ void k_df_count(const int32_t* __restrict__ col, const double* __restrict__ val, int64_t nnz,
+                           int n_cols, int* __restrict__ df, int* __restrict__ err) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) {
+    int c = col[i];
+    if (c < 0 || c >= n_cols) { atomicMax(err, 1); continue; }
+    if (val[i] > 0) atomicAdd(&df[c], 1);
+  }
+}
+__global__ void k_idf(const int* __restrict__ df, int n_cols, double m, double* __restrict__ idf) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_cols) idf[j] = df[j] > 0 ? log(m / (double)df[j]) : 0.0;
+}
+__global__ void k_idf_scale(const int32_t* __restrict__ col, double* __restrict__ val, int64_t nnz,
+                            const double* __restrict__ idf) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) val[i] *= idf[col[i]];
+}
+// K2: row L2 normalisation in place (b2ToB, A2) + validation (NaN, negative, zero rows, column range)
+__global__ void k_row_l2(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                         double* __restrict__ val, int n_rows, int n_cols, double* __restrict__ norm_out,
+                         int* __restrict__ err) {
+  int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  int lane = threadIdx.x & 31;
+  int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+  for (int r = warp; r < n_rows; r += nwarps) {
+    int64_t rs = row_ptr[r], re = row_ptr[r + 1];
+    double ss = 0.0; int bad = 0;
+    for (int64_t k = rs + lane; k < re; k += 32) {
+      double v = val[k]; int c = col[k];
+      if (!(v == v) || isinf(v)) bad |= 1;
+      if (v < 0) bad |= 2;
+      if (c < 0 || c >= n_cols) bad |= 4;
+      ss += v * v;
+    }
+    ss = warp_sum(ss);
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    double nrm = sqrt(ss);
+    if (bad & 1) atomicMax(err, 5); else if (bad & 4) atomicMax(err, 1); else if (bad & 2) atomicMax(err, 6);
+    else if (!(nrm > 0)) atomicMax(err, 4);
+    if (lane == 0 && norm_out) norm_out[r] = nrm;
+    double inv = nrm > 0 ? 1.0 / nrm : 0.0;
+    for (int64_t k = rs + lane; k < re; k += 32) val[k] *= inv;
+  }
+}
+
+// ------------------------------------------------------------------ per-sweep bookkeeping
+__global__ void k_activate(Ctx c, const Activation* __restrict__ acts, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Activation a = acts[i];
+  Slot s;
+  s.begin = a.begin; s.end = a.end;
+  int len = a.end - a.begin;
+  s.lbegin = a.begin + (int)((int64_t)len * c.rank / c.world);
+  s.lend = a.begin + (int)((int64_t)len * (c.rank + 1) / c.world);
+  s.state = ST_DEG; s.action = ACT_NONE; s.j = 0; s.iters = 0; s.restarts = 0; s.node = a.node;
+  s.split = 0; s.n0 = 0; s.stop_after = a.stop_after; s.pad = 0;
+  s.sumd = 0; s.inv_sqrt_sumd = 0; s.beta = 0; s.theta = 0; s.resid = 0; s.q = 0; s.theta_hint = -1e300;
+  c.st[a.slot] = s;
+}
+
+// zero the reduction rows of live slots and build the chunk list (single CTA, 1024 threads)
+__global__ void __launch_bounds__(1024) k_prepare(Ctx c) {
+  __shared__ int offs[4097];
+  __shared__ int wsum[32];
+  const int tid = threadIdx.x;
+  const int per = (c.n_slots + 1023) / 1024;        // slots per thread (<= 4)
+  int cnt[4]; int mine = 0;
+  for (int q = 0; q < per; ++q) {
+    int slot = tid * per + q; int n = 0;
+    if (slot < c.n_slots) {
+      const Slot& s = c.st[slot];
+      if (s.state >= ST_DEG && s.state <= ST_MOD) n = (s.lend - s.lbegin + c.chunk_rows - 1) / c.chunk_rows;
+    }
+    cnt[q] = n; mine += n;
+  }
+  // block exclusive scan of `mine`
+  int lane = tid & 31, wid = tid >> 5;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int v = wsum[lane]; int iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+    wsum[lane] = iv - v;
+  }
+  __syncthreads();
+  int base = wsum[wid] + incl - mine;
+  for (int q = 0; q < per; ++q) {
+    int slot = tid * per + q;
+    if (slot < c.n_slots) offs[slot] = base;
+    base += cnt[q];
+  }
+  if (tid == 1023) { offs[c.n_slots] = base; *c.n_chunks = base; }
+  __syncthreads();
+  const int total = offs[c.n_slots];
+  for (int ci = tid; ci < total; ci += 1024) {
+    int lo = 0, hi = c.n_slots;               // last slot with offs[slot] <= ci
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (offs[mid] <= ci) lo = mid; else hi = mid; }
+    const Slot& s = c.st[lo];
+    int k = ci - offs[lo];
+    Chunk ch; ch.slot = lo; ch.begin = s.lbegin + k * c.chunk_rows;
+    ch.len = min(c.chunk_rows, s.lend - ch.begin);
+    c.chunks[ci] = ch;
+  }
+  // zero reduction rows (dots of both passes up to j+1, and the scalars): one warp per slot
+  for (int slot = wid; slot < c.n_slots; slot += 32) {
+    const Slot& s = c.st[slot];
+    if (s.state < ST_DEG || s.state > ST_MOD) continue;
+    double* ra = c.redA + (int64_t)slot * (c.K + 2);
+    double* rb = c.redB + (int64_t)slot * (c.K + 2);
+    int nv = min(s.j + 2, c.K + 2);
+    for (int i = lane; i < nv; i += 32) { ra[i] = 0.0; rb[i] = 0.0; }
+    if (lane < R_NSCAL) c.scal[slot * R_NSCAL + lane] = 0.0;
+  }
+}
+
+// zero y of every slot that scatters this sweep; grid (max_active_used, ny)
+__global__ void k_zero_y(Ctx c) {
+  int slot = blockIdx.x;
+  int st = c.st[slot].state;
+  if (st != ST_DEG && st != ST_LAN && st != ST_MOD) return;
+  double2* y = reinterpret_cast<double2*>(c.Y + (int64_t)slot * c.ystride);
+  int n2 = (int)(c.ystride >> 1);
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n2; i += gridDim.y * blockDim.x) y[i] = make_double2(0.0, 0.0);
+}
+
+// ------------------------------------------------------------------ K4 half 1: y_S = B_S^T (xin)   (scatter)
+// xin = D^{-1/2} q_j for Lanczos (so y = C^T q_j), 1 for the degree pass, the 0/1 label for modularity.
+__global__ void __launch_bounds__(256) k_scatter(Ctx c) {
+  if ((int)blockIdx.x >= *c.n_chunks) return;
+  const Chunk ch = c.chunks[blockIdx.x];
+  const int state = c.st[ch.slot].state;
+  if (state != ST_DEG && state != ST_LAN && state != ST_MOD) return;
+  double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < ch.len; r += 8) {
+    const int p = ch.begin + r;
+    const double xi = (state == ST_DEG) ? 1.0 : c.xin[p];
+    if (xi == 0.0) continue;
+    const int row = c.perm[p];
+    const int64_t rs = c.row_ptr[row], re = c.row_ptr[row + 1];
+    int64_t k = rs + lane;
+    for (; k + 96 < re; k += 128) {
+      int c0 = __ldg(c.col + k), c1 = __ldg(c.col + k + 32), c2 = __ldg(c.col + k + 64), c3 = __ldg(c.col + k + 96);
+      double v0 = __ldg(c.val + k), v1 = __ldg(c.val + k + 32), v2 = __ldg(c.val + k + 64), v3 = __ldg(c.val + k + 96);
+      atomicAdd(y + c0, v0 * xi); atomicAdd(y + c1, v1 * xi); atomicAdd(y + c2, v2 * xi); atomicAdd(y + c3, v3 * xi);
+    }
+    for (; k < re; k += 32) atomicAdd(y + __ldg(c.col + k), __ldg(c.val + k) * xi);
+  }
+}
+
+// ------------------------------------------------------------------ K4 half 2: w = D^{-1/2} B_S y   (gather)
+__global__ void __launch_bounds__(256) k_gather(Ctx c) {
+  __shared__ double sm8[8];
+  if ((int)blockIdx.x >= *c.n_chunks) return;
+  const Chunk ch = c.chunks[blockIdx.x];
+  const int state = c.st[ch.slot].state;
+  if (state != ST_DEG && state != ST_LAN) return;
+  const double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double dsum = 0.0;
+  long long nz = 0;
+  for (int r = warp; r < ch.len; r += 8) {
+    const int p = ch.begin + r;
+    const int row = c.perm[p];
+    const int64_t rs = c.row_ptr[row], re = c.row_ptr[row + 1];
+    nz += re - rs;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int64_t k = rs + lane;
+    for (; k + 96 < re; k += 128) {
+      int c0 = __ldg(c.col + k), c1 = __ldg(c.col + k + 32), c2 = __ldg(c.col + k + 64), c3 = __ldg(c.col + k + 96);
+      double v0 = __ldg(c.val + k), v1 = __ldg(c.val + k + 32), v2 = __ldg(c.val + k + 64), v3 = __ldg(c.val + k + 96);
+      a0 += v0 * y[c0]; a1 += v1 * y[c1]; a2 += v2 * y[c2]; a3 += v3 * y[c3];
+    }
+    for (; k < re; k += 32) a0 += __ldg(c.val + k) * y[__ldg(c.col + k)];
+    double s = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) {
+      if (state == ST_DEG) { c.d[p] = s; dsum += s; }
+      else c.w[p] = c.sdeg[p] * s;
+    }
+  }
+  if (lane == 0 && nz) atomicAdd(c.stats + (state == ST_DEG ? 1 : 0), (unsigned long long)nz);
+  if (state == ST_DEG) {
+    double t = block_sum_256(dsum, sm8);
+    if (threadIdx.x == 0) atomicAdd(c.scal + ch.slot * R_NSCAL + R_SUMD, t);
+  }
+}
+
+// ||y_S||^2 for slots in the modularity state; grid (slots_used, ny). Columns are split over ranks.
+__global__ void __launch_bounds__(256) k_ynorm(Ctx c) {
+  __shared__ double sm8[8];
+  int slot = blockIdx.x;
+  if (c.st[slot].state != ST_MOD) return;
+  const double* __restrict__ y = c.Y + (int64_t)slot * c.ystride;
+  int lo = (int)((int64_t)c.n_cols * c.rank / c.world), hi = (int)((int64_t)c.n_cols * (c.rank + 1) / c.world);
+  double s = 0.0;
+  for (int i = lo + blockIdx.y * blockDim.x + threadIdx.x; i < hi; i += gridDim.y * blockDim.x) { double v = y[i]; s += v * v; }
+  double t = block_sum_256(s, sm8);
+  if (threadIdx.x == 0) atomicAdd(c.scal + slot * R_NSCAL + R_YNORM2, t);
+}
+
+// ------------------------------------------------------------------ K5: full re-orthogonalisation (CGS2)
+// h_l = <V_l, w>, l = 0..j  (l = 0 is the locked trivial vector u1 = D^{1/2}1/||.||, the deflation)
+#define TMC_MAX_CHUNK 256
+__global__ void __launch_bounds__(256) k_dots(Ctx c, int pass) {
+  __shared__ double ws[TMC_MAX_CHUNK];
+  if ((int)blockIdx.x >= *c.n_chunks) return;
+  const Chunk ch = c.chunks[blockIdx.x];
+  const Slot& s = c.st[ch.slot];
+  const int state = s.state;
+  if (state != ST_ORTH0 && state != ST_LAN) return;
+  const int j = s.j;
+  for (int i = threadIdx.x; i < ch.len; i += 256) ws[i] = c.w[ch.begin + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* r = (pass ? c.redB : c.redA) + (int64_t)ch.slot * (c.K + 2);
+  for (int l = warp; l <= j; l += 8) {
+    const double* __restrict__ v = c.V + (int64_t)l * c.vstride + ch.begin;
+    double a = 0.0;
+    for (int i = lane; i < ch.len; i += 32) a += v[i] * ws[i];
+    a = warp_sum(a);
+    if (lane == 0) atomicAdd(r + l, a);
+  }
+}
+
+// w -= sum_l h_l V_l ; after the second pass also accumulates ||w||^2 (= beta_{j+1}^2)
+__global__ void __launch_bounds__(256) k_update(Ctx c, int pass) {
+  extern __shared__ double smem[];
+  double* hs = smem;                       // K+2
+  double* part = smem + (c.K + 2);         // 8 * chunk_rows
+  __shared__ double sm8[8];
+  if ((int)blockIdx.x >= *c.n_chunks) return;
+  const Chunk ch = c.chunks[blockIdx.x];
+  const Slot& s = c.st[ch.slot];
+  const int state = s.state;
+  if (state != ST_ORTH0 && state != ST_LAN) return;
+  const int j = s.j;
+  const double* r = (pass ? c.redB : c.redA) + (int64_t)ch.slot * (c.K + 2);
+  for (int l = threadIdx.x; l <= j; l += 256) hs[l] = r[l];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = lane; i < ch.len; i += 32) {
+    double a = 0.0;
+    for (int l = warp; l <= j; l += 8) a += hs[l] * c.V[(int64_t)l * c.vstride + ch.begin + i];
+    part[warp * c.chunk_rows + i] = a;
+  }
+  __syncthreads();
+  double nn = 0.0;
+  for (int i = threadIdx.x; i < ch.len; i += 256) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += part[q * c.chunk_rows + i];
+    double wv = c.w[ch.begin + i] - t;
+    c.w[ch.begin + i] = wv;
+    nn += wv * wv;
+  }
+  if (pass == 1) {
+    double t = block_sum_256(nn, sm8);
+    if (threadIdx.x == 0) atomicAdd(c.scal + ch.slot * R_NSCAL + R_NRM2, t);
+  }
+}
+
+// ------------------------------------------------------------------ per-node scalar logic: one warp per slot
+__global__ void __launch_bounds__(256) k_finish(Ctx c) {
+  const int slot = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (slot >= c.n_slots) return;
+  Slot* s = c.st + slot;
+  const int state = s->state;
+  if (state < ST_DEG || state > ST_MOD) return;
+  const int K2 = c.K + 2;
+  const double* redA = c.redA + (int64_t)slot * K2;
+  const double* redB = c.redB + (int64_t)slot * K2;
+  const double* scal = c.scal + slot * R_NSCAL;
+  if (state == ST_DEG) {
+    if (lane == 0) {
+      double sumd = scal[R_SUMD];
+      s->sumd = sumd;
+      if (!(sumd > 0) || isinf(sumd)) { atomicMax(c.err, 7); s->inv_sqrt_sumd = 0; }
+      else s->inv_sqrt_sumd = 1.0 / sqrt(sumd);
+      s->action = ACT_INIT;
+    }
+    return;
+  }
+  if (state == ST_ORTH0) {
+    if (lane == 0) {
+      double b = sqrt(fmax(scal[R_NRM2], 0.0));
+      s->beta = b;
+      if (!(b > 0)) { s->action = ACT_FINISH; s->split = 0; s->q = 0.0; s->theta = 0.0; }   // degenerate start (cannot happen for len >= 2)
+      else s->action = ACT_NEXT;
+    }
+    return;
+  }
+  if (state == ST_LAN) {
+    const int j = s->j;
+    double* A = c.alpha + (int64_t)slot * K2;
+    double* B = c.beta + (int64_t)slot * K2;
+    double beta = 0.0;
+    if (lane == 0) {
+      A[j - 1] = redA[j] + redB[j];
+      beta = sqrt(fmax(scal[R_NRM2], 0.0));
+      B[j] = beta;
+      if (j == 1) B[0] = 0.0;
+      s->beta = beta;
+      s->iters += 1;
+    }
+    __syncwarp();
+    beta = __shfl_sync(0xffffffffu, beta, 0);
+    const int len = s->end - s->begin;
+    const bool exhausted = (j >= len - 1);
+    const bool breakdown = !(beta > 1e-13);
+    const bool full = (j >= c.K);
+    const bool check = exhausted || breakdown || full || j <= 8 || (j & 3) == 0;
+    if (!check) { if (lane == 0) s->action = ACT_NEXT; return; }
+    __threadfence_block();
+    const double theta = tmc_top_eig_warp(A, B, j, s->theta_hint);
+    if (lane == 0) {
+      double* z = c.zvec + (int64_t)slot * K2;
+      double* scr = c.scratch + (int64_t)slot * 2 * K2;
+      double lo, hi, piv;
+      tmc_gershgorin(A, B, j, &lo, &hi, &piv);
+      tmc_twisted_vector(A, B, j, theta, scr, scr + K2, z, piv);
+      double resid = beta * fabs(z[j - 1]);
+      s->theta = theta; s->resid = resid;
+      s->theta_hint = theta - 1e-13 * fmax(1.0, fabs(theta));
+      bool conv = exhausted || breakdown || resid <= c.tol * theta || resid <= 1e-14;
+      if (conv || (full && s->restarts >= c.max_restarts)) {
+        s->action = ACT_RITZ_LABEL;
+        c.red2[2 * slot] = 0.0; c.red2[2 * slot + 1] = 0.0;
+      } else if (full) {
+        s->action = ACT_RITZ_RESTART; s->restarts += 1; s->theta_hint = -1e300;
+      } else s->action = ACT_NEXT;
+    }
+    return;
+  }
+  // ST_MOD: Newman-Girvan Q of the split on A = B B^T - I  (getBModularity).
+  // With t = B^T 1 (||t||^2 = sum d), t1 = B^T 1_{c1}:  O_1 = ||t1||^2 - n1,
+  // O_0 = ||t - t1||^2 - n0 = sum d - 2 sum_{c1} d + ||t1||^2 - n0,  L_c = sum_{c} d - n_c,  L = sum d - m.
+  if (lane == 0) {
+    const double m = (double)(s->end - s->begin);
+    const double n1 = c.red2[2 * slot], sd1 = c.red2[2 * slot + 1];
+    const double n0 = m - n1, sd = s->sumd, t1 = scal[R_YNORM2];
+    const double L = sd - m;
+    double q = 0.0;
+    if (L != 0.0) {
+      const double O1 = t1 - n1, O0 = sd - 2.0 * sd1 + t1 - n0;
+      const double L1 = sd1 - n1, L0 = (sd - sd1) - n0;
+      q = (O0 / L - (L0 / L) * (L0 / L)) + (O1 / L - (L1 / L) * (L1 / L));
+    }
+    s->q = q;
+    s->n0 = (int)(n0 + 0.5);
+    const int in0 = s->n0, in1 = (int)(n1 + 0.5);
+    bool split = (q > c.min_modularity) && in0 >= 1 && in1 >= 1 && in0 >= c.min_size && in1 >= c.min_size;
+    if (s->stop_after == ST_DONE) split = false;     // fine-grained API: report Q only
+    s->split = split ? 1 : 0;
+    s->action = ACT_FINISH;
+  }
+}
+
+// ------------------------------------------------------------------ per-position transitions
+__global__ void __launch_bounds__(256) k_advance(Ctx c) {
+  __shared__ double sm8[8];
+  if ((int)blockIdx.x >= *c.n_chunks) return;
+  const Chunk ch = c.chunks[blockIdx.x];
+  const Slot& s = c.st[ch.slot];
+  const int action = s.action;
+  if (action == ACT_NONE || action == ACT_FINISH) return;
+  if (action == ACT_INIT) {
+    const double isd = s.inv_sqrt_sumd;
+    for (int i = threadIdx.x; i < ch.len; i += 256) {
+      const int p = ch.begin + i;
+      const double dd = c.d[p];
+      if (!(dd > 0)) atomicMax(c.err, 7);
+      const double sq = sqrt(dd);
+      c.sdeg[p] = 1.0 / sq;
+      c.V[p] = sq * isd;                                   // V_0 = u1
+      c.w[p] = hash_unit(c.seed, (uint64_t)c.perm[p]);
+    }
+    return;
+  }
+  if (action == ACT_NEXT) {
+    const int jn = (s.state == ST_ORTH0) ? 1 : s.j + 1;
+    const double ib = 1.0 / s.beta;
+    double* __restrict__ vn = c.V + (int64_t)jn * c.vstride;
+    for (int i = threadIdx.x; i < ch.len; i += 256) {
+      const int p = ch.begin + i;
+      const double v = c.w[p] * ib;
+      vn[p] = v;
+      c.xin[p] = c.sdeg[p] * v;
+    }
+    return;
+  }
+  // Ritz vector u = sum_{l=1..j} z_l V_l
+  const int j = s.j;
+  const double* __restrict__ z = c.zvec + (int64_t)ch.slot * (c.K + 2);
+  double n1 = 0.0, sd1 = 0.0;
+  for (int i = threadIdx.x; i < ch.len; i += 256) {
+    const int p = ch.begin + i;
+    double u = 0.0;
+    for (int l = 1; l <= j; ++l) u += z[l - 1] * c.V[(int64_t)l * c.vstride + p];
+    if (action == ACT_RITZ_RESTART) { c.w[p] = u; continue; }
+    c.u2[p] = u;
+    const int lab = (u >= 0.0) ? 1 : 0;                   // spectralCluster sign rule (A6)
+    c.label[p] = (uint8_t)lab;
+    c.xin[p] = (double)lab;
+    n1 += lab; sd1 += lab ? c.d[p] : 0.0;
+  }
+  if (action == ACT_RITZ_LABEL) {
+    double t = block_sum_256(n1, sm8);
+    double t2 = block_sum_256(sd1, sm8);
+    if (threadIdx.x == 0) { atomicAdd(c.red2 + 2 * ch.slot, t); atomicAdd(c.red2 + 2 * ch.slot + 1, t2); }
+  }
+}
+
+// ------------------------------------------------------------------ K7: stable partition of the node's position range
+// one CTA per slot (grid = slots used); children = [label 0 | label 1], original order kept (A8).
+__global__ void __launch_bounds__(1024) k_partition(Ctx c) {
+  __shared__ int wtot[32];
+  __shared__ int run1_s;
+  const int slot = blockIdx.x;
+  const Slot& s = c.st[slot];
+  if (s.state != ST_MOD || s.action != ACT_FINISH || !s.split) return;
+  const int begin = s.begin, end = s.end, n0 = s.n0;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) run1_s = 0;
+  __syncthreads();
+  for (int base = begin; base < end; base += 1024) {
+    const int p = base + tid;
+    const int f = (p < end) ? (int)c.label[p] : 0;
+    unsigned bal = __ballot_sync(0xffffffffu, f);
+    int before = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) wtot[wid] = __popc(bal);
+    __syncthreads();
+    int run1 = run1_s;
+    int wbase = 0;
+    for (int q = 0; q < wid; ++q) wbase += wtot[q];
+    int ones_before = run1 + wbase + before;               // label-1 positions before p in the node
+    if (p < end) {
+      int idx = p - begin;
+      int dest = f ? (begin + n0 + ones_before) : (begin + (idx - ones_before));
+      c.perm_tmp[dest] = c.perm[p];
+    }
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int q = 0; q < 32; ++q) t += wtot[q]; run1_s = run1 + t; }
+    __syncthreads();
+  }
+  for (int p = begin + tid; p < end; p += 1024) c.perm[p] = c.perm_tmp[p];
+}
+
+// apply the pending action to the slot state and publish the report the host reads
+__global__ void k_commit(Ctx c, int n_slots) {
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_slots) return;
+  Slot* s = c.st + slot;
+  int state = s->state;
+  switch (s->action) {
+    case ACT_INIT: state = ST_ORTH0; s->j = 0; break;
+    case ACT_NEXT: if (state == ST_ORTH0) { state = ST_LAN; s->j = 1; } else s->j += 1; break;
+    case ACT_RITZ_LABEL: state = ST_MOD; break;
+    case ACT_RITZ_RESTART: state = ST_ORTH0; s->j = 0; break;
+    case ACT_FINISH: state = ST_DONE; break;
+    default: break;
+  }
+  if (s->stop_after != 0 && state == s->stop_after && state != s->state) state = ST_DONE;   // fine-grained API stop
+  s->action = ACT_NONE;
+  s->state = state;
+  Report r; r.state = state; r.split = s->split; r.n0 = s->n0; r.iters = s->iters; r.q = s->q; r.theta = s->theta;
+  c.rep[slot] = r;
+}
+
+// helpers for the fine-grained API
+__global__ void k_iota(int* p, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
+__global__ void k_set_xin_scaled(Ctx c, const double* __restrict__ x, int n) {   // xin = D^{-1/2} x
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) c.xin[i] = c.sdeg[i] * x[i];
+}
+__global__ void k_set_labels(Ctx c, const uint8_t* __restrict__ lab, int n, int slot) {
+  __shared__ double sm8[8];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double n1 = 0.0, sd1 = 0.0;
+  if (i < n) { int l = lab[i] ? 1 : 0; c.label[i] = (uint8_t)l; c.xin[i] = (double)l; n1 = l; sd1 = l ? c.d[i] : 0.0; }
+  double t = block_sum_256(n1, sm8);
+  double t2 = block_sum_256(sd1, sm8);
+  if (threadIdx.x == 0) { atomicAdd(c.red2 + 2 * slot, t); atomicAdd(c.red2 + 2 * slot + 1, t2); }
+}
+__global__ void k_force_state(Ctx c, int slot, int state, int j, int stop_after) {
+  c.st[slot].state = state; c.st[slot].j = j; c.st[slot].action = ACT_NONE; c.st[slot].stop_after = stop_after;
+  c.red2[2 * slot] = 0.0; c.red2[2 * slot + 1] = 0.0;
+}
+
+// tmc_partition API: set up slot `slot` so that k_partition splits [begin,end) with n0 label-0 rows
+__global__ void k_force_partition(Ctx c, int slot, int begin, int end, int n0) {
+  Slot& s = c.st[slot];
+  s.begin = begin; s.end = end; s.lbegin = begin; s.lend = end; s.state = ST_MOD; s.action = ACT_FINISH; s.split = 1; s.n0 = n0;
+}
+// multi-GPU: zero the labels outside this rank's share of a splitting node so that an
+// allreduce(sum) over the byte vector assembles the full label vector on every rank
+__global__ void k_mask_labels(Ctx c) {
+  const Slot& s = c.st[blockIdx.x];
+  if (s.state != ST_MOD || s.action != ACT_FINISH || !s.split) return;
+  for (int p = s.begin + threadIdx.x; p < s.lbegin; p += blockDim.x) c.label[p] = 0;
+  for (int p = s.lend + threadIdx.x; p < s.end; p += blockDim.x) c.label[p] = 0;
+}
+
+}  // namespace tmc

@@ -1,0 +1,295 @@
+"""Host-side mirror of the reference's operator interface for the make-tree hot path.
+
+The reference's host is Haskell (no GHC in this image), so this is the Python
+mirror of the same call surface, bound to libtmc.so over the C ABI in
+include/tmc.h.  Names, argument meaning and error behaviour follow the
+reference call sites:
+
+  tfidf_scale_sparse_mat        src/TooManyCells/Matrix/Preprocess.hs:204-205   (unB2 . b1ToB2 . B1)
+  b1_to_b2 / b2_to_b            Math.Clustering.Spectral.Sparse (spectral-clustering)
+  b_to_d / second_left /
+  spectral_cluster              Math.Clustering.Spectral.Sparse
+  get_b_modularity              Math.Modularity.Sparse (modularity)
+  hierarchical_spectral_cluster Math.Clustering.Hierarchical.Spectral.Sparse, called at
+                                src/TooManyCells/MakeTree/Cluster.hs:147-156,169
+  h_spec_clust                  src/TooManyCells/MakeTree/Cluster.hs:135-187
+
+Every function runs on the GPU through libtmc; there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import Csr, Opts, Tree, TmcError, check
+
+
+# ----------------------------------------------------------------------------- marshalling
+class HostCsr:
+    """Borrowed host CSR (cells x features) in the dtypes the C ABI wants."""
+
+    def __init__(self, mat):
+        if hasattr(mat, "indptr"):              # scipy.sparse CSR
+            indptr, indices, data, shape = mat.indptr, mat.indices, mat.data, mat.shape
+        else:
+            indptr, indices, data, shape = mat
+        self.indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        self.indices = np.ascontiguousarray(indices, dtype=np.int32)
+        self.data = np.ascontiguousarray(data, dtype=np.float64)
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.c = Csr(self.shape[0], self.shape[1], int(self.data.size),
+                     self.indptr.ctypes.data, self.indices.ctypes.data, self.data.ctypes.data)
+
+    @property
+    def nnz(self):
+        return int(self.data.size)
+
+
+def make_opts(min_modularity=0.0, min_size=1, normalize=False, eigen_group="SignGroup", num_eigen=1,
+              num_runs=0, seed=None, tol=None, max_lanczos=None, max_restarts=None, max_active=None,
+              device=-1, profile=False) -> Opts:
+    lib = _lib.load()
+    o = Opts()
+    lib.tmc_opts_default(C.byref(o))
+    o.eigen_group = {"SignGroup": 0, "KMeansGroup": 1}[eigen_group] if isinstance(eigen_group, str) else int(eigen_group)
+    o.num_eigen = int(num_eigen)
+    o.min_modularity = float(min_modularity)
+    o.min_size = int(min_size)
+    o.normalize = int(bool(normalize))
+    o.num_runs = int(num_runs or 0)
+    if seed is not None:
+        o.seed = int(seed)
+    if tol is not None:
+        o.tol = float(tol)
+    if max_lanczos is not None:
+        o.max_lanczos = int(max_lanczos)
+    if max_restarts is not None:
+        o.max_restarts = int(max_restarts)
+    if max_active is not None:
+        o.max_active = int(max_active)
+    o.device = int(device)
+    o.profile = int(bool(profile))
+    return o
+
+
+# ----------------------------------------------------------------------------- device matrix handle
+class DeviceB:
+    """B = b2ToB(B2) resident in HBM (optionally idf-scaled first: getB True)."""
+
+    def __init__(self, handle, shape, nnz, keepalive=None):
+        self.handle = handle
+        self.shape = shape
+        self.nnz = nnz
+        self._keep = keepalive
+
+    @classmethod
+    def from_host(cls, b2, normalize=False, device=-1):
+        lib = _lib.load()
+        h = HostCsr(b2)
+        out = C.c_void_p()
+        check(lib.tmc_matrix_upload(C.byref(h.c), int(bool(normalize)), int(device), C.byref(out)))
+        return cls(out, h.shape, h.nnz)
+
+    @classmethod
+    def adopt_device(cls, n_rows, n_cols, row_ptr, col, val, normalize=False, device=-1):
+        """Adopt torch CUDA tensors (int64 row_ptr, int32 col, float64 val) without copying; val is normalised in place."""
+        lib = _lib.load()
+        out = C.c_void_p()
+        check(lib.tmc_matrix_adopt_dev(int(n_rows), int(n_cols), int(val.numel()), row_ptr.data_ptr(), col.data_ptr(),
+                                       val.data_ptr(), int(bool(normalize)), int(device), C.byref(out)))
+        return cls(out, (int(n_rows), int(n_cols)), int(val.numel()), keepalive=(row_ptr, col, val))
+
+    def free(self):
+        if self.handle:
+            _lib.load().tmc_matrix_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _rows_arg(rows):
+    if rows is None:
+        return None, 0, None
+    r = np.ascontiguousarray(rows, dtype=np.int64)
+    return r.ctypes.data, int(r.size), r
+
+
+# ----------------------------------------------------------------------------- A1 / A2
+def b1_to_b2(b1):
+    """idf column scaling (b1ToB2).  Returns (values, idf) for the same sparsity pattern."""
+    lib = _lib.load()
+    h = HostCsr(b1)
+    val = np.empty(h.nnz, dtype=np.float64)
+    idf = np.empty(h.shape[1], dtype=np.float64)
+    check(lib.tmc_tfidf(C.byref(h.c), val.ctypes.data, idf.ctypes.data))
+    return val, idf
+
+
+def tfidf_scale_sparse_mat(mat):
+    """Preprocess.hs:204-205 — returns a scipy CSR with the tf-idf scaled values."""
+    import scipy.sparse as sp
+    val, _ = b1_to_b2(mat)
+    h = HostCsr(mat)
+    return sp.csr_matrix((val, h.indices.copy(), h.indptr.copy()), shape=h.shape)
+
+
+def b2_to_b(b2):
+    """Row L2 normalisation (b2ToB).  Returns (values, row_norms)."""
+    lib = _lib.load()
+    h = HostCsr(b2)
+    val = np.empty(h.nnz, dtype=np.float64)
+    nrm = np.empty(h.shape[0], dtype=np.float64)
+    check(lib.tmc_row_l2(C.byref(h.c), val.ctypes.data, nrm.ctypes.data))
+    return val, nrm
+
+
+# ----------------------------------------------------------------------------- A3 - A8 (per node)
+def b_to_d(b: DeviceB, rows=None):
+    lib = _lib.load()
+    p, n, keep = _rows_arg(rows)
+    out = np.empty(n if rows is not None else b.shape[0], dtype=np.float64)
+    check(lib.tmc_degree(b.handle, p, n, out.ctypes.data))
+    return out
+
+
+def second_left(b: DeviceB, rows=None, **opt_kw):
+    """u2 of C = D^{-1/2} B_S.  Returns (u2, theta = sigma_2^2, lanczos_steps)."""
+    lib = _lib.load()
+    p, n, keep = _rows_arg(rows)
+    m = n if rows is not None else b.shape[0]
+    u2 = np.empty(m, dtype=np.float64)
+    th = C.c_double()
+    it = C.c_int32()
+    o = make_opts(**opt_kw)
+    check(lib.tmc_second_left(b.handle, p, n, C.byref(o), u2.ctypes.data, C.byref(th), C.byref(it)))
+    return u2, th.value, it.value
+
+
+def spectral_cluster(b: DeviceB, rows=None, **opt_kw):
+    """0/1 labels: 1 iff u2_i >= 0 (spectralCluster)."""
+    u2, _, _ = second_left(b, rows, **opt_kw)
+    return (u2 >= 0).astype(np.uint8)
+
+
+def get_b_modularity(labels, b: DeviceB, rows=None) -> float:
+    lib = _lib.load()
+    p, n, keep = _rows_arg(rows)
+    lab = np.ascontiguousarray(labels, dtype=np.uint8)
+    q = C.c_double()
+    check(lib.tmc_modularity(b.handle, p, n, lab.ctypes.data, C.byref(q)))
+    return q.value
+
+
+def partition_rows(rows, labels):
+    """Stable split of sorted row ids into [label 0 | label 1]. Returns (rows_out, n_left)."""
+    lib = _lib.load()
+    r = np.ascontiguousarray(rows, dtype=np.int64)
+    lab = np.ascontiguousarray(labels, dtype=np.uint8)
+    out = np.empty_like(r)
+    nl = C.c_int64()
+    check(lib.tmc_partition(r.ctypes.data, int(r.size), lab.ctypes.data, out.ctypes.data, C.byref(nl)))
+    return out, nl.value
+
+
+def spmv_pair(b: DeviceB, x, rows=None):
+    """x' = C_S (C_S^T x)  (the las2 operator)."""
+    lib = _lib.load()
+    p, n, keep = _rows_arg(rows)
+    xx = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(xx)
+    check(lib.tmc_spmv_pair(b.handle, p, n, xx.ctypes.data, out.ctypes.data))
+    return out
+
+
+def bench_spmv_pair(b: DeviceB, reps=20):
+    lib = _lib.load()
+    sc, ga = C.c_double(), C.c_double()
+    check(lib.tmc_bench_spmv_pair(b.handle, int(reps), C.byref(sc), C.byref(ga)))
+    return sc.value, ga.value
+
+
+# ----------------------------------------------------------------------------- A0 / A9: the tree
+@dataclass
+class ClusteringTree:
+    """Flat pre-order ClusteringTree (children order [label 0, label 1])."""
+    left: np.ndarray
+    right: np.ndarray
+    parent: np.ndarray
+    q: np.ndarray            # _ngMod of every vertex (leaf Q is discarded by clusteringTreeToTree)
+    theta: np.ndarray
+    iters: np.ndarray
+    item_begin: np.ndarray
+    item_end: np.ndarray
+    perm: np.ndarray         # original row ids; node i holds perm[item_begin[i]:item_end[i]] (ascending)
+    stats: dict
+
+    @property
+    def n_nodes(self):
+        return int(self.left.size)
+
+    def items(self, i):
+        return self.perm[self.item_begin[i]:self.item_end[i]]
+
+    def is_leaf(self, i):
+        return self.left[i] < 0
+
+    def leaves(self):
+        return np.nonzero(self.left < 0)[0]
+
+    def leaf_sets(self):
+        return sorted(tuple(int(x) for x in self.items(i)) for i in self.leaves())
+
+
+def _tree_from_c(tp) -> ClusteringTree:
+    t = tp.contents
+    n, m = int(t.n_nodes), int(t.n_rows)
+
+    def arr(ptr, count, dtype):
+        return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True) if count else np.zeros(0, dtype)
+
+    out = ClusteringTree(
+        left=arr(t.left, n, np.int64), right=arr(t.right, n, np.int64), parent=arr(t.parent, n, np.int64),
+        q=arr(t.q, n, np.float64), theta=arr(t.theta, n, np.float64), iters=arr(t.iters, n, np.int32),
+        item_begin=arr(t.item_begin, n, np.int64), item_end=arr(t.item_end, n, np.int64), perm=arr(t.perm, m, np.int64),
+        stats=dict(n_sweeps=int(t.n_sweeps), spmv_pairs_nnz=int(t.spmv_pairs_nnz), kernel_launches=int(t.kernel_launches),
+                   engine_ms=float(t.engine_ms), spmv_ms=float(t.spmv_ms), spmv_alg_bytes=float(t.spmv_alg_bytes)))
+    _lib.load().tmc_tree_free(tp)
+    return out
+
+
+def hierarchical_spectral_cluster(mat, eigen_group="SignGroup", normalize=False, num_eigen=None, min_size=None,
+                                  min_modularity=None, num_runs=None, **engine_kw) -> ClusteringTree:
+    """hierarchicalSpectralCluster eigenGroup normFlag numEigen minSize minMod runs items (Left mat).
+
+    `mat` is a host CSR (scipy / (indptr, indices, data, shape)) — copied to the GPU inside the call —
+    or a DeviceB already resident in HBM.  `None` arguments mean Haskell `Nothing`.
+    """
+    lib = _lib.load()
+    o = make_opts(min_modularity=0.0 if min_modularity is None else min_modularity,
+                  min_size=1 if min_size is None else min_size, normalize=normalize, eigen_group=eigen_group,
+                  num_eigen=1 if num_eigen is None else num_eigen, num_runs=num_runs or 0, **engine_kw)
+    tp = C.POINTER(Tree)()
+    if isinstance(mat, DeviceB):
+        check(lib.tmc_make_tree_dev(mat.handle, C.byref(o), C.byref(tp)))
+    else:
+        h = HostCsr(mat)
+        check(lib.tmc_make_tree(C.byref(h.c), C.byref(o), C.byref(tp)))
+    return _tree_from_c(tp)
+
+
+def h_spec_clust(matrix, row_names, eigen_group="SignGroup", num_eigen=None, min_modularity=None, num_runs=None,
+                 dense=False, **engine_kw):
+    """hSpecClust (Cluster.hs:135-187): returns (cluster_list, tree) where cluster_list is
+    [(barcode, row, [leaf, ..., 0])] in DFS-leaf order and tree is the ClusteringTree."""
+    if dense:
+        raise TmcError(_lib.ERR_UNSUPPORTED, "--dense (hmatrix path, Cluster.hs:157-167) is out of scope")
+    from .tree_io import cluster_list
+    tree = hierarchical_spectral_cluster(matrix, eigen_group, False, num_eigen, None, min_modularity, num_runs, **engine_kw)
+    return cluster_list(tree, row_names), tree

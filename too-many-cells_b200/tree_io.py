@@ -1,0 +1,293 @@
+"""make-tree output contract on flat pre-order trees.
+
+Byte-exact writers for the artefacts `too-many-cells make-tree` produces from the
+ClusteringTree, pinned in tests/test_tree_io.py against the reference's own golden
+outputs (workshop/out/*, workshop/clusters.csv):
+
+  cluster_tree.json   aeson Data.Tree encoding, src/TooManyCells/Program/MakeTree.hs:321-330
+  cluster_list.json   src/TooManyCells/MakeTree/Types.hs:82-85
+  clusters.csv        stdout of make-tree, src/TooManyCells/Program/MakeTree.hs:383-396
+  cluster_info.csv    src/TooManyCells/MakeTree/Print.hs:61-88
+  node_info.csv       src/TooManyCells/MakeTree/Print.hs:109-154
+  graph.dot           fgl/graphviz dump of treeToGraph (pre-order ids)
+
+CSV bodies use cassava's CRLF record terminator after an LF-terminated header, as the
+reference does.  Doubles use Haskell `show` (shortest round-trip digits).
+"""
+from __future__ import annotations
+
+import json
+from collections import Counter
+from decimal import Decimal
+
+import numpy as np
+
+
+def haskell_show_double(x: float) -> str:
+    """Haskell `show :: Double -> String` (also what aeson emits for the golden files)."""
+    x = float(x)
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "Infinity" if x > 0 else "-Infinity"
+    if x == 0:
+        return "-0.0" if str(x).startswith("-") else "0.0"
+    sign = "-" if x < 0 else ""
+    t = Decimal(repr(abs(x))).as_tuple()
+    digits = "".join(map(str, t.digits)).rstrip("0") or "0"
+    # value = 0.d1d2... * 10^e
+    e = len(t.digits) + t.exponent
+    if 0.1 <= abs(x) < 1e7:
+        if e <= 0:
+            s = "0." + "0" * (-e) + digits
+        elif e >= len(digits):
+            s = digits + "0" * (e - len(digits)) + ".0"
+        else:
+            s = digits[:e] + "." + digits[e:]
+        return sign + s
+    mant = digits[0] + "." + (digits[1:] if len(digits) > 1 else "0")
+    return f"{sign}{mant}e{e - 1}"
+
+
+# ----------------------------------------------------------------------------- flat tree <-> nested
+class FlatTree:
+    """Minimal flat pre-order tree: what the writers need (left/right/q/items)."""
+
+    def __init__(self, left, right, q, items):
+        self.left = np.asarray(left, dtype=np.int64)
+        self.right = np.asarray(right, dtype=np.int64)
+        self.q = np.asarray(q, dtype=np.float64)
+        self._items = items           # leaf id -> sequence of row ids (None for inner nodes is fine)
+
+    @property
+    def n_nodes(self):
+        return int(self.left.size)
+
+    def items(self, i):
+        return self._items[i]
+
+
+def _as_flat(tree):
+    if hasattr(tree, "items") and hasattr(tree, "left"):
+        return tree
+    raise TypeError("expected a flat tree (ClusteringTree / FlatTree)")
+
+
+def parents_of(tree):
+    par = np.full(tree.n_nodes, -1, dtype=np.int64)
+    for i in range(tree.n_nodes):
+        if tree.left[i] >= 0:
+            par[tree.left[i]] = i
+            par[tree.right[i]] = i
+    return par
+
+
+def leaf_paths(tree):
+    """DFS-leaf order list of (leaf, [leaf, parent, ..., 0])  (getGraphLeavesWithParents gr 0)."""
+    par = parents_of(tree)
+    out = []
+    for i in range(tree.n_nodes):       # pre-order ids => ascending id over leaves is DFS order
+        if tree.left[i] < 0:
+            path, u = [], i
+            while u >= 0:
+                path.append(int(u))
+                u = par[u]
+            out.append((i, path))
+    return out
+
+
+def subtree_sizes(tree):
+    size = np.zeros(tree.n_nodes, dtype=np.int64)
+    for i in range(tree.n_nodes - 1, -1, -1):
+        if tree.left[i] < 0:
+            size[i] = len(tree.items(i))
+        else:
+            size[i] = size[tree.left[i]] + size[tree.right[i]]
+    return size
+
+
+def _cell_info(barcode, row):
+    return {"_barcode": {"unCell": barcode}, "_cellRow": {"unRow": int(row)}}
+
+
+class _HsFloat(float):
+    pass
+
+
+def _dumps(obj) -> str:
+    """Compact JSON with Haskell-show doubles (aeson's encoding of Double in the golden files)."""
+    if obj is None:
+        return "null"
+    if isinstance(obj, bool):
+        return "true" if obj else "false"
+    if isinstance(obj, (int, np.integer)):
+        return str(int(obj))
+    if isinstance(obj, float):
+        return haskell_show_double(obj)
+    if isinstance(obj, str):
+        return json.dumps(obj, ensure_ascii=False)
+    if isinstance(obj, (list, tuple)):
+        return "[" + ",".join(_dumps(x) for x in obj) + "]"
+    if isinstance(obj, dict):
+        return "{" + ",".join(json.dumps(k) + ":" + _dumps(v) for k, v in obj.items()) + "}"
+    raise TypeError(type(obj))
+
+
+def cluster_tree_json(tree, row_names, significance=False) -> str:
+    """`[label,[children]]`; inner: _item null, _distance Q; leaf: _item cells, _distance null.
+    `significance=True` adds the `_significance` key current birch-beer emits (absent in the golden file)."""
+    tree = _as_flat(tree)
+    # iterative post-order string assembly (trees can be ~1e5 nodes deep-ish)
+    strs = [None] * tree.n_nodes
+    for i in range(tree.n_nodes - 1, -1, -1):
+        if tree.left[i] < 0:
+            label = {"_item": [_cell_info(row_names[r], r) for r in tree.items(i)], "_distance": None}
+            kids = "[]"
+        else:
+            label = {"_item": None, "_distance": float(tree.q[i])}
+            kids = "[" + strs[tree.left[i]] + "," + strs[tree.right[i]] + "]"
+            strs[tree.left[i]] = strs[tree.right[i]] = None
+        if significance:
+            label["_significance"] = None
+        strs[i] = "[" + _dumps(label) + "," + kids + "]"
+    return strs[0]
+
+
+def parse_cluster_tree_json(text: str):
+    """Inverse of cluster_tree_json: returns (FlatTree, row_names dict row->barcode)."""
+    nested = json.loads(text)
+    left, right, q, items, names = [], [], [], [], {}
+    stack = [(nested, -1, 0)]
+    # explicit pre-order walk, children [0] then [1]
+    def walk(node):
+        order = []
+        st = [node]
+        while st:
+            n = st.pop()
+            order.append(n)
+            for ch in reversed(n[1]):
+                st.append(ch)
+        return order
+    order = walk(nested)
+    ids = {id(n): i for i, n in enumerate(order)}
+    for n in order:
+        label, kids = n
+        if kids:
+            assert len(kids) == 2
+            left.append(ids[id(kids[0])]); right.append(ids[id(kids[1])])
+            q.append(label["_distance"]); items.append(None)
+        else:
+            left.append(-1); right.append(-1); q.append(float("nan"))
+            rows = []
+            for ci in label["_item"]:
+                rows.append(ci["_cellRow"]["unRow"]); names[ci["_cellRow"]["unRow"]] = ci["_barcode"]["unCell"]
+            items.append(rows)
+    return FlatTree(left, right, q, items), names
+
+
+def cluster_list(tree, row_names):
+    """[(barcode, row, [leaf,...,0])] in DFS-leaf order, item order inside the leaf (treeToClusterList)."""
+    tree = _as_flat(tree)
+    out = []
+    for leaf, path in leaf_paths(tree):
+        for r in tree.items(leaf):
+            out.append((row_names[r], int(r), path))
+    return out
+
+
+def cluster_list_json(tree, row_names) -> str:
+    parts = []
+    for bc, r, path in cluster_list(tree, row_names):
+        parts.append("[" + _dumps(_cell_info(bc, r)) + "," + _dumps([{"unCluster": c} for c in path]) + "]")
+    return "[" + ",".join(parts) + "]"
+
+
+def _csv_field(s: str) -> str:
+    if any(ch in s for ch in ',"\r\n'):
+        return '"' + s.replace('"', '""') + '"'
+    return s
+
+
+def _csv(header: str, rows) -> str:
+    return header + "\n" + "".join(",".join(_csv_field(str(f)) for f in r) + "\r\n" for r in rows)
+
+
+def clusters_csv(tree, row_names) -> str:
+    """stdout of make-tree: header `cell,cluster,path` (Program/MakeTree.hs:383-396)."""
+    rows = ((bc, path[0], "/".join(map(str, path))) for bc, _, path in cluster_list(tree, row_names))
+    return _csv("cell,cluster,path", rows) + "\n"       # B.putStrLn appends the final LF
+
+
+def cluster_info_csv(tree) -> str:
+    """cluster,modularity,size — modularity path starts at the leaf's parent (Print.hs:61-88)."""
+    tree = _as_flat(tree)
+    size = subtree_sizes(tree)
+    rows = []
+    for leaf, path in leaf_paths(tree):
+        qs = [haskell_show_double(tree.q[u]) for u in path if tree.left[u] >= 0]
+        rows.append((leaf, "/".join(qs), "/".join(str(int(size[u])) for u in path)))
+    return _csv("cluster,modularity,size", rows)
+
+
+def node_info_csv(tree, label_of_row=None, significance=True) -> str:
+    """node,size,proportion,modularity,[significance,]composition,subtree (Print.hs:109-154).
+    `significance=False` reproduces the older header of the shipped golden file."""
+    tree = _as_flat(tree)
+    n = tree.n_nodes
+    size = subtree_sizes(tree)
+    # subtree node sets: pre-order => node i's subtree is the id range [i, i + count_i)
+    count = np.ones(n, dtype=np.int64)
+    for i in range(n - 1, -1, -1):
+        if tree.left[i] >= 0:
+            count[i] += count[tree.left[i]] + count[tree.right[i]]
+    comp = [None] * n
+    if label_of_row is not None:
+        for i in range(n - 1, -1, -1):
+            if tree.left[i] < 0:
+                comp[i] = Counter(label_of_row[r] for r in tree.items(i) if r in label_of_row)
+            else:
+                comp[i] = comp[tree.left[i]] + comp[tree.right[i]]
+    rows = []
+    for i in range(n):
+        inner = tree.left[i] >= 0
+        prop = haskell_show_double(size[tree.left[i]] / size[tree.right[i]]) if inner else ""
+        mod = haskell_show_double(tree.q[i]) if inner else ""
+        if comp[i] is not None:
+            tot = sum(comp[i].values())
+            cs = "/".join(f"{k}: {haskell_show_double(v / tot)} ({v})" for k, v in sorted(comp[i].items()))
+        else:
+            cs = ""
+        sub = "/".join(str(j) for j in range(i, i + int(count[i])))
+        row = [i, int(size[i]), prop, mod] + ([""] if significance else []) + [cs, sub]
+        rows.append(row)
+    hdr = "node,size,proportion,modularity," + ("significance," if significance else "") + "composition,subtree"
+    return _csv(hdr, rows)
+
+
+def graph_dot(tree) -> str:
+    tree = _as_flat(tree)
+    lines = ["digraph {"]
+    lines += [f"    {i};" for i in range(tree.n_nodes)]
+    for i in range(tree.n_nodes):
+        if tree.left[i] >= 0:
+            lines.append(f"    {i} -> {int(tree.left[i])};")
+            lines.append(f"    {i} -> {int(tree.right[i])};")
+    return "\n".join(lines) + "\n}"
+
+
+def write_make_tree_outputs(tree, row_names, out_dir, label_of_row=None):
+    """Write the files `make-tree --output DIR` writes from the clustering (no plots)."""
+    import os
+    os.makedirs(out_dir, exist_ok=True)
+    files = {
+        "cluster_tree.json": cluster_tree_json(tree, row_names, significance=True),
+        "cluster_list.json": cluster_list_json(tree, row_names),
+        "cluster_info.csv": cluster_info_csv(tree),
+        "node_info.csv": node_info_csv(tree, label_of_row),
+        "graph.dot": graph_dot(tree),
+        "clusters.csv": clusters_csv(tree, row_names),
+    }
+    for name, text in files.items():
+        with open(os.path.join(out_dir, name), "w", newline="") as f:
+            f.write(text)
+    return sorted(files)
