@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py — `ms per full make-tree` on synthetic 10x-like matrices (BASELINE.json metric).
+
+One "step" = one complete make-tree hot path over the workload: tf-idf + row-L2
+normalisation, then the whole recursive spectral bipartition (degree, Lanczos SpMV
+pairs, sign split, modularity, stable row partition) down to the leaves.
+
+  value  : device-resident input (raw counts already in HBM), ms per tree
+  e2e    : the same through the host-buffer C-ABI call `tmc_make_tree` (pinned host CSR ->
+           H2D -> tree -> D2H of the flat tree), ms per tree
+  roofline: SpMV pair kernels (scatter y=C^T x, gather x'=C y): algorithmic bytes
+            / CUDA-event time of those launches inside the timed steps
+  cpu_baseline / --impl reference: the oracle's CPU implementation of the same path.
+
+N>1 (torchrun, one rank per GPU): the tree build is row-sharded across ranks with NCCL
+all-reduces of the feature-dimension vectors; total work is fixed => "strong" scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ms per full make-tree"
+UNIT = "ms"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("TMC_BENCH_WORKLOAD", "c2"))
+    ap.add_argument("--cpu-sample-cells", type=int, default=2500)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_desc(name):
+    from too_many_cells_b200 import synth
+    n, g, k, d, s, binary = synth.CONFIGS[name]
+    return {"workload": f"{name}: synthetic 10x-like {n} cells x {g} genes, ~{k} nnz/cell, planted depth {d}, seed {s}, "
+                        f"tf-idf + default min-modularity 0 stop",
+            "cells": n, "features": g, "l2": "inputs larger than L2 (CSR >> 126 MB)" if n * k * 12 > 2.5e8 else
+            "matrix smaller than L2; no flush (the tree build re-reads it by design)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_reference_run(name, sample_cells, steps=1, warmup=0):
+    """The oracle's CPU make-tree on a bounded sample (first `sample_cells` cells of the workload).
+    Returns (ms per sample tree, work rate nnz-passes/s, description)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import scipy.sparse as sp
+    from too_many_cells_b200 import synth
+    import tmc_oracle as O
+    n, g, k, d, s, binary = synth.CONFIGS[name]
+    ns = min(n, sample_cells)
+    ip, ix, dv, _ = synth.synth_counts(ns, g, k, d, s, binary)
+    a = sp.csr_matrix((dv, ix, ip), shape=(ns, g))
+    times = []
+    for it in range(warmup + steps):
+        t = time.perf_counter()
+        tr = O.hierarchical_spectral_cluster(a, normalize=True)
+        dt = time.perf_counter() - t
+        if it >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    desc = (f"oracle (numpy/scipy LAPACK+ARPACK, exact eigen-solve) make-tree on the first {ns} cells x {g} genes of {name} "
+            f"({a.nnz} nnz, {tr.n_nodes} nodes)")
+    return ms, ns, a.nnz, desc
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    name = args.workload
+    cfg = workload_desc(name)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ncores = os.cpu_count() or 1
+        ms, ns, nnz, desc = cpu_reference_run(name, args.cpu_sample_cells, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": ms, "unit": UNIT, "cores": ncores, "kind": "port", "sample": desc +
+                                 "; each step is one tree on that sample, NOT the full workload"},
+                "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import too_many_cells_b200 as T
+    from too_many_cells_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (libtmc has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = T._lib.load()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            import ctypes
+            buf = (ctypes.c_uint8 * 128)()
+            T._lib.check(lib.tmc_comm_unique_id(buf))
+            idt = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        dist.broadcast(idt, 0)
+        idb = bytes(idt.cpu().tolist())
+        import ctypes
+        T._lib.check(lib.tmc_comm_init(ctypes.create_string_buffer(idb, 128), rank, world, local_rank))
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    n, g, k, d, s, binary = synth.CONFIGS[name]
+    t0 = time.time()
+    row_ptr, col, val_raw = synth.synth_counts_torch(n, g, k, d, s, dev, binary)
+    torch.cuda.synchronize()
+    nnz = int(val_raw.numel())
+    gen_s = time.time() - t0
+    work = torch.empty_like(val_raw)
+
+    def step_dev(profile):
+        work.copy_(val_raw)                       # raw counts resident in HBM; tf-idf + L2 happen inside the step
+        torch.cuda.synchronize()
+        b = T.DeviceB.adopt_device(n, g, row_ptr, col, work, normalize=True, device=local_rank)
+        tree = T.hierarchical_spectral_cluster(b, profile=profile)
+        b.free()
+        return tree
+
+    for _ in range(args.warmup):
+        step_dev(False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    trees = [step_dev(True) for _ in range(args.steps)]
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        tt = torch.tensor([ms_step], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        ms_step = float(tt.item())
+
+    # ---- end-to-end through the host-buffer C-ABI (rank 0's numbers; every rank participates when N>1)
+    h_ptr = row_ptr.cpu().pin_memory()
+    h_col = col.cpu().pin_memory()
+    h_val = val_raw.cpu().pin_memory()
+    host = (h_ptr.numpy(), h_col.numpy(), h_val.numpy(), (n, g))
+    e2e_steps = max(1, min(args.steps, 2))
+    T.hierarchical_spectral_cluster(host, normalize=True)     # warm
+    barrier()
+    t = time.perf_counter()
+    for _ in range(e2e_steps):
+        tr_e = T.hierarchical_spectral_cluster(host, normalize=True)
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t) / e2e_steps
+    h2d = int(h_ptr.numel() * 8 + h_col.numel() * 4 + h_val.numel() * 8)
+    d2h = int(tr_e.n_nodes * (8 * 5 + 8 * 2 + 4) + n * 8)
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    tr = trees[-1]
+    spmv_ms = sum(t_.stats["spmv_ms"] for t_ in trees)
+    alg = sum(t_.stats["spmv_alg_bytes"] for t_ in trees)
+    launches = sum(t_.stats["kernel_launches"] for t_ in trees)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+    achieved = alg / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
+    # root-level pair in isolation (largest single launch pair)
+    work.copy_(val_raw)
+    b = T.DeviceB.adopt_device(n, g, row_ptr, col, work, normalize=True, device=local_rank)
+    sc_ms, ga_ms = T.bench_spmv_pair(b, 10)
+    b.free()
+    pair_bytes = 24.0 * nnz + 16.0 * (n + 1) + 32.0 * n + 16.0 * g
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+            "traffic": None, "peak_source": peak_src, "kernel": "k_scatter+k_gather (SpMV pair y=C^T x, x'=C y), all launches of the timed steps",
+            "algorithmic_bytes_per_step": alg / len(trees), "spmv_ms_per_step": spmv_ms / len(trees),
+            "spmv_share_of_step": spmv_ms / len(trees) / ms_step,
+            "root_pair": {"scatter_ms": sc_ms, "gather_ms": ga_ms, "bytes": pair_bytes,
+                          "scatter_gbs": 0.5 * pair_bytes / (sc_ms * 1e-3) / 1e9, "gather_gbs": 0.5 * pair_bytes / (ga_ms * 1e-3) / 1e9}}
+    line = {"metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dict(cfg, nnz=nnz, parallelism=f"rows sharded over {world} GPU(s)"),
+            "clocks": clocks,
+            "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "roofline": roof,
+            "tree": {"nodes": tr.n_nodes, "leaves": int(len(tr.leaves())), "sweeps": tr.stats["n_sweeps"],
+                     "lanczos_steps": int(tr.iters.sum()), "engine_ms_last": tr.stats["engine_ms"], "gen_s": gen_s}}
+    if not args.no_cpu_baseline:
+        ms_c, ns, nnz_c, desc = cpu_reference_run(name, args.cpu_sample_cells)
+        line["cpu_baseline"] = {"value": ms_c, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": desc + "; value is ms for ONE tree on that sample, not the full workload"}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

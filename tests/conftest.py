@@ -1,0 +1,32 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def load_golden(name):
+    import numpy as np
+    import scipy.sparse as sp
+    z = np.load(os.path.join(GOLDEN, f"synth_{name}.npz"))
+    n, g = (int(x) for x in z["shape"])
+    a = sp.csr_matrix((z["counts"].astype(np.float64), z["indices"], z["indptr"]), shape=(n, g))
+    return a, z
+
+
+@pytest.fixture(scope="session")
+def golden_tiny():
+    return load_golden("tiny")
+
+
+@pytest.fixture(scope="session")
+def golden_small():
+    return load_golden("small")

@@ -1,0 +1,104 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol include/tmc.h
+declares, the host/device tridiagonal helpers agree with LAPACK, struct layouts match, and the
+product fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+import too_many_cells_b200 as T
+from too_many_cells_b200 import _lib
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "tmc.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(tmc_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"libtmc.so does not export {n}"
+    assert set(names) == set(_lib.SIGNATURES), "ctypes binding and header disagree"
+
+
+def test_opts_default_and_layout():
+    o = T.make_opts()
+    assert o.eigen_group == 0 and o.num_eigen == 1 and o.min_modularity == 0.0 and o.min_size == 1
+    assert o.normalize == 0 and o.num_runs == 0 and o.tol == 1e-10 and o.max_lanczos == 320 and o.device == -1
+    assert C.sizeof(_lib.Opts) == 96 and C.sizeof(_lib.Tree) == 136      # static_assert-ed in tmc_engine.cu
+
+
+def test_no_cpu_fallback_without_device():
+    lib = _lib.load()
+    if lib.tmc_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    import scipy.sparse as sp
+    a = sp.random(20, 10, 0.5, format="csr", random_state=0)
+    with pytest.raises(T.TmcError) as ei:
+        T.hierarchical_spectral_cluster(a)
+    assert ei.value.code == _lib.ERR_NO_DEVICE
+    with pytest.raises(T.TmcError):
+        T.b1_to_b2(a)
+
+
+def test_unsupported_flags_are_reported():
+    lib = _lib.load()
+    if lib.tmc_device_count() > 0:
+        pytest.skip("checked on the GPU box in test_gpu_parity")
+    # without a device the device check comes first; just make sure the call returns an error, not a crash
+    import scipy.sparse as sp
+    a = sp.random(20, 10, 0.5, format="csr", random_state=0)
+    with pytest.raises(T.TmcError):
+        T.hierarchical_spectral_cluster(a, eigen_group="KMeansGroup")
+
+
+@pytest.fixture(scope="module")
+def tridiag_lib(tmp_path_factory):
+    out = tmp_path_factory.mktemp("th") / "libth.so"
+    src = os.path.join(ROOT, "tests", "helpers", "tridiag_host.cpp")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", src, "-o", str(out)], check=True)
+    lib = C.CDLL(str(out))
+    P = C.POINTER(C.c_double)
+    lib.th_top_eig.restype = C.c_double
+    lib.th_top_eig.argtypes = [P, P, C.c_int, C.c_double]
+    lib.th_vector.argtypes = [P, P, C.c_int, C.c_double, P, P, P]
+    return lib
+
+
+def test_tridiagonal_helpers_match_lapack(tridiag_lib):
+    from scipy.linalg import eigh_tridiagonal
+    P = C.POINTER(C.c_double)
+    rng = np.random.default_rng(0)
+    for trial in range(120):
+        j = int(rng.integers(1, 330))
+        if trial % 3 == 0:
+            a = rng.random(j); b = rng.random(j) * 0.3
+        elif trial % 3 == 1:
+            a = np.sort(rng.random(j))[::-1].copy(); b = rng.random(j) * 10.0 ** (-rng.integers(0, 12, size=j))
+        else:
+            a = np.full(j, 0.5); b = np.full(j, 0.25)
+        b[0] = 0
+        w = eigh_tridiagonal(a, b[1:], eigvals_only=True) if j > 1 else a
+        th = tridiag_lib.th_top_eig(a.ctypes.data_as(P), b.ctypes.data_as(P), j, -1e300)
+        assert abs(th - w[-1]) <= 3e-14 * max(1.0, abs(w[-1]))
+        z, dp, dm = np.zeros(j), np.zeros(j), np.zeros(j)
+        tridiag_lib.th_vector(a.ctypes.data_as(P), b.ctypes.data_as(P), j, th, dp.ctypes.data_as(P), dm.ctypes.data_as(P),
+                              z.ctypes.data_as(P))
+        tm = np.diag(a) + np.diag(b[1:], 1) + np.diag(b[1:], -1)
+        assert np.linalg.norm(tm @ z - th * z) < 1e-13 and abs(np.linalg.norm(z) - 1) < 1e-12
+
+
+def test_synth_is_deterministic(golden_tiny):
+    from too_many_cells_b200 import synth
+    a, z = golden_tiny
+    ip, ix, dv, _ = synth.synth_config("tiny")
+    assert np.array_equal(ip, z["indptr"]) and np.array_equal(ix, z["indices"]) and np.array_equal(dv, z["counts"])

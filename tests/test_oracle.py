@@ -1,0 +1,100 @@
+"""The oracle against its committed golden vectors + the algebraic properties the reference's
+algorithm must satisfy (the reference ships no tests: SURVEY.md section 4 / 8(c))."""
+import numpy as np
+import scipy.sparse as sp
+import pytest
+
+import tmc_oracle as O
+
+
+def test_oracle_matches_golden_tiny(golden_tiny):
+    a, z = golden_tiny
+    b2 = O.b1_to_b2(a)
+    assert np.allclose(b2.data[:4096], z["tfidf_head"], rtol=1e-14, atol=0)
+    tr = O.hierarchical_spectral_cluster(b2)
+    assert np.array_equal(np.array(tr.left), z["left"]) and np.array_equal(np.array(tr.right), z["right"])
+    assert np.allclose(np.array(tr.q), z["q"], rtol=1e-9, atol=1e-13)
+    leaf_of_row = np.full(a.shape[0], -1)
+    for i in tr.leaves():
+        leaf_of_row[tr.items[i]] = i
+    assert np.array_equal(leaf_of_row, z["leaf_of_row"])
+
+
+def test_tfidf_definition():
+    a = sp.csr_matrix(np.array([[1.0, 0, 2], [0, 3, 4], [5, 0, 6], [0, 0, 7]]))
+    b2 = O.b1_to_b2(a).toarray()
+    idf = np.log(4 / np.array([2, 1, 4]))
+    assert np.allclose(b2, a.toarray() * idf)
+
+
+def test_top_singular_pair_is_trivial(golden_tiny):
+    a, _ = golden_tiny
+    b = O.b2_to_b(O.b1_to_b2(a))[:300]
+    d = O.b_to_d(b)
+    c = O.bd_to_c(b, d).toarray()
+    u, s, _ = np.linalg.svd(c, full_matrices=False)
+    assert abs(s[0] - 1.0) < 1e-12
+    u1 = np.sqrt(d) / np.sqrt(d.sum())
+    assert min(np.linalg.norm(u[:, 0] - u1), np.linalg.norm(u[:, 0] + u1)) < 1e-10
+    u2, th, _ = O.second_left(sp.csr_matrix(c), d)
+    assert abs(th - s[1] ** 2) < 1e-12
+    assert min(np.linalg.norm(u2 - u[:, 1]), np.linalg.norm(u2 + u[:, 1])) < 1e-8
+
+
+def test_dense_and_arpack_agree(golden_small):
+    a, _ = golden_small
+    b = O.b2_to_b(O.b1_to_b2(a))[:1200]
+    d = O.b_to_d(b)
+    c = O.bd_to_c(b, d)
+    u_d, th_d, _ = O.second_left(c, d)
+    old = O.DENSE_MAX_ROWS
+    O.DENSE_MAX_ROWS = 10
+    try:
+        u_a, th_a, _ = O.second_left(c, d)
+    finally:
+        O.DENSE_MAX_ROWS = old
+    assert abs(th_d - th_a) < 1e-12
+    assert min(np.linalg.norm(u_d - u_a), np.linalg.norm(u_d + u_a)) < 1e-9
+
+
+def test_modularity_properties(golden_tiny):
+    a, _ = golden_tiny
+    b = O.b2_to_b(O.b1_to_b2(a))[:200]
+    rng = np.random.default_rng(0)
+    lab = rng.integers(0, 2, 200)
+    q = O.get_b_modularity(lab, b)
+    assert abs(q - O.get_b_modularity(1 - lab, b)) < 1e-14            # label swap
+    p = rng.permutation(200)
+    assert abs(q - O.get_b_modularity(lab[p], b[p])) < 1e-13          # row permutation
+    assert q <= 0.5
+    # direct dense definition on A = B B^T - I
+    g = (b @ b.T).toarray() - np.eye(200)
+    k = g.sum(1); L = g.sum()
+    qd = sum(g[np.ix_(lab == c, lab == c)].sum() / L - (k[lab == c].sum() / L) ** 2 for c in (0, 1))
+    assert abs(q - qd) < 1e-12
+
+
+def test_block_diagonal_split_positive_q():
+    rng = np.random.default_rng(1)
+    a = sp.block_diag([sp.random(40, 30, 0.4, random_state=1, data_rvs=lambda k: rng.integers(1, 5, k).astype(float)) + sp.eye(40, 30),
+                       sp.random(50, 35, 0.4, random_state=2, data_rvs=lambda k: rng.integers(1, 5, k).astype(float)) + sp.eye(50, 35)]).tocsr()
+    b = O.b2_to_b(a)
+    lab, *_ = O.spectral_cluster(b)
+    truth = np.r_[np.zeros(40), np.ones(50)]
+    assert np.array_equal(lab, truth) or np.array_equal(lab, 1 - truth)
+    assert O.get_b_modularity(lab, b) > 0.4
+
+
+def test_tree_invariant_under_feature_permutation(golden_tiny):
+    a, _ = golden_tiny
+    sub = a[:250]
+    t1 = O.hierarchical_spectral_cluster(sub, normalize=True)
+    p = np.random.default_rng(2).permutation(sub.shape[1])
+    t2 = O.hierarchical_spectral_cluster(sub[:, p], normalize=True)
+    assert t1.leaf_sets() == t2.leaf_sets()
+
+
+def test_zero_row_is_an_error():
+    a = sp.csr_matrix(np.array([[1.0, 2.0], [0.0, 0.0], [3.0, 1.0]]))
+    with pytest.raises(ValueError):
+        O.hierarchical_spectral_cluster(a)

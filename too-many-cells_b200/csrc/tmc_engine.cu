@@ -20,6 +20,9 @@
 
 using namespace tmc;
 
+static_assert(sizeof(tmc_opts) == 96, "tmc_opts layout is part of the ABI (mirrored in _lib.py)");
+static_assert(sizeof(tmc_tree) == 136, "tmc_tree layout is part of the ABI (mirrored in _lib.py)");
+
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CK(call)                                                                                   \
