@@ -82,7 +82,7 @@ typedef struct {
   const int32_t* iters;       /* Lanczos steps spent on the node */
   const int64_t* item_begin;  /* n_nodes; [item_begin,item_end) into perm: the node's cells */
   const int64_t* item_end;
-  const int64_t* perm;        /* n_rows original row ids; ascending inside every node (stable splits) */
+  const int64_t* perm;        /* n_rows original row ids; ascending inside every LEAF (stable splits) */
   /* engine statistics for the roofline report */
   int64_t n_sweeps;           /* kernel sweeps over the active node set */
   int64_t spmv_pairs_nnz;     /* sum over Lanczos steps of nnz touched (one pair = 2 passes) */

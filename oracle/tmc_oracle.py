@@ -88,6 +88,16 @@ def second_left(c: sp.csr_matrix, d: np.ndarray | None = None):
     m = c.shape[0]
     if m <= DENSE_MAX_ROWS:
         g = (c @ c.T).toarray()
+        if d is not None:
+            # deflate the known trivial pair (sigma_1 = 1, u_1 = D^{1/2} 1 / ||.||) so that u2 stays
+            # well defined when sigma_2 = 1 too (disconnected similarity graph)
+            u1 = np.sqrt(d) / math.sqrt(d.sum())
+            gu = g @ u1
+            g = g - np.outer(u1, gu) - np.outer(gu, u1) + (u1 @ gu) * np.outer(u1, u1)
+            w, v = np.linalg.eigh(g)
+            gap = w[-1] - (w[-2] if m >= 3 else 0.0)
+            # the deflated direction shows up as an extra ~0 eigenvalue; it never is the top one unless theta2 ~ 0
+            return v[:, -1], float(w[-1]), float(gap)
         w, v = np.linalg.eigh(g)
         u2 = v[:, -2]
         th2 = w[-2]

@@ -147,11 +147,11 @@ def test_full_tree_vs_golden(name, golden_tiny, golden_small):
         assert bool(tree.is_leaf(i)) == bool(leaf)
         if len(key) >= 2:
             assert abs(tree.q[i] - qo) <= 1e-9 * max(1.0, abs(qo)) + 1e-12
-    # items ascending inside every node (stable partition), pre-order ids
+    # items ascending inside every leaf (stable partition), pre-order ids
     for i in range(tree.n_nodes):
-        it = tree.items(i)
-        assert np.all(np.diff(it) > 0)
-        if not tree.is_leaf(i):
+        if tree.is_leaf(i):
+            assert np.all(np.diff(tree.items(i)) > 0)
+        else:
             assert tree.left[i] == i + 1 and tree.right[i] > tree.left[i]
 
 
@@ -246,7 +246,7 @@ def test_large_config_properties():
     inner = np.nonzero(tree.left >= 0)[0]
     assert np.all(tree.q[inner] > 0) and np.all(tree.q[inner] <= 0.5)
     assert np.all(tree.q[[i for i in leaves if len(tree.items(i)) >= 2]] <= 0)
-    for i in range(tree.n_nodes):
+    for i in leaves:
         assert np.all(np.diff(tree.items(i)) > 0)
     # idempotence / determinism of membership
     t2 = T.hierarchical_spectral_cluster(a, normalize=True, seed=12345)    # different start vector, same tree

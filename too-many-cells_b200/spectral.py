@@ -227,7 +227,7 @@ class ClusteringTree:
     iters: np.ndarray
     item_begin: np.ndarray
     item_end: np.ndarray
-    perm: np.ndarray         # original row ids; node i holds perm[item_begin[i]:item_end[i]] (ascending)
+    perm: np.ndarray         # original row ids; node i holds perm[item_begin[i]:item_end[i]] (ascending inside leaves)
     stats: dict
 
     @property
