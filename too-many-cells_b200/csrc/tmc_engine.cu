@@ -138,6 +138,8 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     c.K = K;
     c.chunks = w->A<Chunk>((size_t)m / 8 + max_active + 8);
     c.n_chunks = w->A<int>(1);
+    c.vchunks = w->A<Chunk>((size_t)m / 32 + max_active + 8);
+    c.n_vchunks = w->A<int>(1);
     c.err = w->A<int>(1);
     c.stats = w->A<unsigned long long>(4);
     w->d_act = w->A<Activation>(max_active);
@@ -318,15 +320,20 @@ struct Engine {
       if (st == ST_ORTH0 || st == ST_LAN) n_or++;
     }
     if (!live_n) return;
+    // SpMV chunks: one row per warp while that still gives <= ~16k CTAs; vector chunks: up to 256 positions
     int R = 8;
-    if (rows > 8 * 2368) R = (int)std::min<int64_t>(TMC_MAX_CHUNK, ((rows / 2368) + 7) / 8 * 8);
-    c.chunk_rows = R; c.n_slots = hi_slot;
-    int nch = 0;
+    if (rows > 8 * 16384) R = (int)std::min<int64_t>(TMC_MAX_CHUNK, ((rows / 16384) + 7) / 8 * 8);
+    int RV = 32;
+    if (rows > 32 * 1184) RV = (int)std::min<int64_t>(TMC_MAX_CHUNK, ((rows / 1184) + 31) / 32 * 32);
+    c.chunk_rows = R; c.vchunk_rows = RV; c.n_slots = hi_slot;
+    int nch = 0, nvch = 0;
     for (int sl = 0; sl < hi_slot; ++sl) {
       int st = hstate[sl];
       if (st < ST_DEG || st > ST_MOD) continue;
       const HostNode& nd = nodes[slot_node[sl]];
-      nch += (local_len(nd.end - nd.begin) + R - 1) / R;
+      const int ll = local_len(nd.end - nd.begin);
+      nch += (ll + R - 1) / R;
+      nvch += (ll + RV - 1) / RV;
     }
     const int ny = std::max(1, (int)std::min<int64_t>(64, c.ystride / 8192));
     k_prepare<<<1, 1024, 0, s>>>(c); n_launch++;
@@ -342,18 +349,18 @@ struct Engine {
     if (profile && n_sc) { e2 = ev(); prof_pairs.push_back({e0, e1, e2}); }
     if (only_spmv) { CK(cudaGetLastError()); return; }
     if (n_mod) { k_ynorm<<<dim3(hi_slot, ny), 256, 0, s>>>(c); n_launch++; }
-    const size_t upd_smem = sizeof(double) * ((size_t)c.K + 2 + 8 * (size_t)R);
-    if (n_or && nch) {
-      k_dots<<<nch, 256, 0, s>>>(c, 0); n_launch++;
+    const size_t upd_smem = sizeof(double) * ((size_t)c.K + 2 + 8 * (size_t)RV);
+    if (n_or && nvch) {
+      k_dots<<<nvch, 256, 0, s>>>(c, 0); n_launch++;
       allreduce_f64(c.redA, (size_t)(c.K + 2) * hi_slot);
-      k_update<<<nch, 256, upd_smem, s>>>(c, 0); n_launch++;
-      k_dots<<<nch, 256, 0, s>>>(c, 1); n_launch++;
+      k_update<<<nvch, 256, upd_smem, s>>>(c, 0); n_launch++;
+      k_dots<<<nvch, 256, 0, s>>>(c, 1); n_launch++;
       allreduce_f64(c.redB, (size_t)(c.K + 2) * hi_slot);
-      k_update<<<nch, 256, upd_smem, s>>>(c, 1); n_launch++;
+      k_update<<<nvch, 256, upd_smem, s>>>(c, 1); n_launch++;
     }
     allreduce_f64(c.scal, (size_t)R_NSCAL * hi_slot);
     k_finish<<<(hi_slot * 32 + 255) / 256, 256, 0, s>>>(c); n_launch++;
-    if (nch) { k_advance<<<nch, 256, 0, s>>>(c); n_launch++; }
+    if (nvch) { k_advance<<<nvch, 256, 0, s>>>(c); n_launch++; }
     allreduce_f64(c.red2, 2 * (size_t)hi_slot);
     if (n_mod) {
       if (c.world > 1) {

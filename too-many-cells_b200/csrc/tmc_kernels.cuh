@@ -58,7 +58,8 @@ struct Ctx {
   double* red2;                    // [slot][2] : n1, sum_{c1} d (accumulated by k_advance)
   double* alpha; double* beta; double* zvec; double* scratch;   // [slot][K+2] (scratch: 2*(K+2))
   int K;
-  Chunk* chunks; int* n_chunks; int chunk_rows;
+  Chunk* chunks; int* n_chunks; int chunk_rows;      // SpMV kernels: few rows per CTA (memory-level parallelism)
+  Chunk* vchunks; int* n_vchunks; int vchunk_rows;   // vector kernels (dots/update/advance): up to 256 positions per CTA
   int* err;                        // device error flag
   unsigned long long* stats;       // [0] nnz gathered in Lanczos pairs, [1] nnz gathered in degree pairs
   // options
@@ -160,10 +161,8 @@ __global__ void k_activate(Ctx c, const Activation* __restrict__ acts, int n) {
   c.st[a.slot] = s;
 }
 
-// zero the reduction rows of live slots and build the chunk list (single CTA, 1024 threads)
-__global__ void __launch_bounds__(1024) k_prepare(Ctx c) {
-  __shared__ int offs[4097];
-  __shared__ int wsum[32];
+// block-wide (1024 threads) construction of a chunk list over the live slots' local position ranges
+__device__ void build_chunk_list(const Ctx& c, int csize, Chunk* out, int* out_n, int* offs, int* wsum) {
   const int tid = threadIdx.x;
   const int per = (c.n_slots + 1023) / 1024;        // slots per thread (<= 4)
   int cnt[4]; int mine = 0;
@@ -171,11 +170,10 @@ __global__ void __launch_bounds__(1024) k_prepare(Ctx c) {
     int slot = tid * per + q; int n = 0;
     if (slot < c.n_slots) {
       const Slot& s = c.st[slot];
-      if (s.state >= ST_DEG && s.state <= ST_MOD) n = (s.lend - s.lbegin + c.chunk_rows - 1) / c.chunk_rows;
+      if (s.state >= ST_DEG && s.state <= ST_MOD) n = (s.lend - s.lbegin + csize - 1) / csize;
     }
     cnt[q] = n; mine += n;
   }
-  // block exclusive scan of `mine`
   int lane = tid & 31, wid = tid >> 5;
   int incl = mine;
 #pragma unroll
@@ -195,7 +193,7 @@ __global__ void __launch_bounds__(1024) k_prepare(Ctx c) {
     if (slot < c.n_slots) offs[slot] = base;
     base += cnt[q];
   }
-  if (tid == 1023) { offs[c.n_slots] = base; *c.n_chunks = base; }
+  if (tid == 1023) { offs[c.n_slots] = base; *out_n = base; }
   __syncthreads();
   const int total = offs[c.n_slots];
   for (int ci = tid; ci < total; ci += 1024) {
@@ -203,10 +201,20 @@ __global__ void __launch_bounds__(1024) k_prepare(Ctx c) {
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (offs[mid] <= ci) lo = mid; else hi = mid; }
     const Slot& s = c.st[lo];
     int k = ci - offs[lo];
-    Chunk ch; ch.slot = lo; ch.begin = s.lbegin + k * c.chunk_rows;
-    ch.len = min(c.chunk_rows, s.lend - ch.begin);
-    c.chunks[ci] = ch;
+    Chunk ch; ch.slot = lo; ch.begin = s.lbegin + k * csize;
+    ch.len = min(csize, s.lend - ch.begin);
+    out[ci] = ch;
   }
+  __syncthreads();
+}
+
+// zero the reduction rows of live slots and build the chunk lists (single CTA, 1024 threads)
+__global__ void __launch_bounds__(1024) k_prepare(Ctx c) {
+  __shared__ int offs[4097];
+  __shared__ int wsum[32];
+  build_chunk_list(c, c.chunk_rows, c.chunks, c.n_chunks, offs, wsum);
+  build_chunk_list(c, c.vchunk_rows, c.vchunks, c.n_vchunks, offs, wsum);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // zero reduction rows (dots of both passes up to j+1, and the scalars): one warp per slot
   for (int slot = wid; slot < c.n_slots; slot += 32) {
     const Slot& s = c.st[slot];
@@ -255,6 +263,10 @@ __global__ void __launch_bounds__(256) k_scatter(Ctx c) {
 }
 
 // ------------------------------------------------------------------ K4 half 2: w = D^{-1/2} B_S y   (gather)
+// One warp per row at a time, 4 x 32 entries in flight plus the NEXT 4 x 32 prefetched into registers before the
+// dependent y[col] gathers are issued, and the next row's extent prefetched while the current row streams
+// (measured: 4.2 -> 5.4 TB/s on the c2 root against the non-pipelined loop; tools/exp).  y is read through the
+// read-only path (it is not written in this kernel) so the compiler may keep all four chains in flight.
 __global__ void __launch_bounds__(256) k_gather(Ctx c) {
   __shared__ double sm8[8];
   if ((int)blockIdx.x >= *c.n_chunks) return;
@@ -262,27 +274,47 @@ __global__ void __launch_bounds__(256) k_gather(Ctx c) {
   const int state = c.st[ch.slot].state;
   if (state != ST_DEG && state != ST_LAN) return;
   const double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride;
+  const int32_t* __restrict__ col = c.col;
+  const double* __restrict__ val = c.val;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double dsum = 0.0;
   long long nz = 0;
-  for (int r = warp; r < ch.len; r += 8) {
+  int r = warp;
+  int64_t rs = 0, re = 0;
+  if (r < ch.len) { const int row = c.perm[ch.begin + r]; rs = c.row_ptr[row]; re = c.row_ptr[row + 1]; }
+  while (r < ch.len) {
     const int p = ch.begin + r;
-    const int row = c.perm[p];
-    const int64_t rs = c.row_ptr[row], re = c.row_ptr[row + 1];
+    const int rn = r + 8;
+    int64_t nrs = 0, nre = 0;
+    if (rn < ch.len) { const int nrow = c.perm[ch.begin + rn]; nrs = c.row_ptr[nrow]; nre = c.row_ptr[nrow + 1]; }
     nz += re - rs;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int64_t k = rs + lane;
-    for (; k + 96 < re; k += 128) {
-      int c0 = __ldg(c.col + k), c1 = __ldg(c.col + k + 32), c2 = __ldg(c.col + k + 64), c3 = __ldg(c.col + k + 96);
-      double v0 = __ldg(c.val + k), v1 = __ldg(c.val + k + 32), v2 = __ldg(c.val + k + 64), v3 = __ldg(c.val + k + 96);
-      a0 += v0 * y[c0]; a1 += v1 * y[c1]; a2 += v2 * y[c2]; a3 += v3 * y[c3];
+    bool have = (k + 96 < re);
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0; double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    if (have) {
+      c0 = __ldg(col + k); c1 = __ldg(col + k + 32); c2 = __ldg(col + k + 64); c3 = __ldg(col + k + 96);
+      v0 = __ldg(val + k); v1 = __ldg(val + k + 32); v2 = __ldg(val + k + 64); v3 = __ldg(val + k + 96);
     }
-    for (; k < re; k += 32) a0 += __ldg(c.val + k) * y[__ldg(c.col + k)];
-    double s = warp_sum((a0 + a1) + (a2 + a3));
+    while (have) {
+      const int64_t kn = k + 128;
+      const bool have_n = (kn + 96 < re);
+      int d0 = 0, d1 = 0, d2 = 0, d3 = 0; double u0 = 0, u1 = 0, u2 = 0, u3 = 0;
+      if (have_n) {
+        d0 = __ldg(col + kn); d1 = __ldg(col + kn + 32); d2 = __ldg(col + kn + 64); d3 = __ldg(col + kn + 96);
+        u0 = __ldg(val + kn); u1 = __ldg(val + kn + 32); u2 = __ldg(val + kn + 64); u3 = __ldg(val + kn + 96);
+      }
+      a0 += v0 * __ldg(y + c0); a1 += v1 * __ldg(y + c1); a2 += v2 * __ldg(y + c2); a3 += v3 * __ldg(y + c3);
+      c0 = d0; c1 = d1; c2 = d2; c3 = d3; v0 = u0; v1 = u1; v2 = u2; v3 = u3;
+      k = kn; have = have_n;
+    }
+    for (; k < re; k += 32) a0 += __ldg(val + k) * __ldg(y + __ldg(col + k));
+    const double s = warp_sum((a0 + a1) + (a2 + a3));
     if (lane == 0) {
       if (state == ST_DEG) { c.d[p] = s; dsum += s; }
       else c.w[p] = c.sdeg[p] * s;
     }
+    r = rn; rs = nrs; re = nre;
   }
   if (lane == 0 && nz) atomicAdd(c.stats + (state == ST_DEG ? 1 : 0), (unsigned long long)nz);
   if (state == ST_DEG) {
@@ -309,8 +341,8 @@ __global__ void __launch_bounds__(256) k_ynorm(Ctx c) {
 #define TMC_MAX_CHUNK 256
 __global__ void __launch_bounds__(256) k_dots(Ctx c, int pass) {
   __shared__ double ws[TMC_MAX_CHUNK];
-  if ((int)blockIdx.x >= *c.n_chunks) return;
-  const Chunk ch = c.chunks[blockIdx.x];
+  if ((int)blockIdx.x >= *c.n_vchunks) return;
+  const Chunk ch = c.vchunks[blockIdx.x];
   const Slot& s = c.st[ch.slot];
   const int state = s.state;
   if (state != ST_ORTH0 && state != ST_LAN) return;
@@ -334,8 +366,8 @@ __global__ void __launch_bounds__(256) k_update(Ctx c, int pass) {
   double* hs = smem;                       // K+2
   double* part = smem + (c.K + 2);         // 8 * chunk_rows
   __shared__ double sm8[8];
-  if ((int)blockIdx.x >= *c.n_chunks) return;
-  const Chunk ch = c.chunks[blockIdx.x];
+  if ((int)blockIdx.x >= *c.n_vchunks) return;
+  const Chunk ch = c.vchunks[blockIdx.x];
   const Slot& s = c.st[ch.slot];
   const int state = s.state;
   if (state != ST_ORTH0 && state != ST_LAN) return;
@@ -347,14 +379,14 @@ __global__ void __launch_bounds__(256) k_update(Ctx c, int pass) {
   for (int i = lane; i < ch.len; i += 32) {
     double a = 0.0;
     for (int l = warp; l <= j; l += 8) a += hs[l] * c.V[(int64_t)l * c.vstride + ch.begin + i];
-    part[warp * c.chunk_rows + i] = a;
+    part[warp * c.vchunk_rows + i] = a;
   }
   __syncthreads();
   double nn = 0.0;
   for (int i = threadIdx.x; i < ch.len; i += 256) {
     double t = 0.0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t += part[q * c.chunk_rows + i];
+    for (int q = 0; q < 8; ++q) t += part[q * c.vchunk_rows + i];
     double wv = c.w[ch.begin + i] - t;
     c.w[ch.begin + i] = wv;
     nn += wv * wv;
@@ -465,8 +497,8 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
 // ------------------------------------------------------------------ per-position transitions
 __global__ void __launch_bounds__(256) k_advance(Ctx c) {
   __shared__ double sm8[8];
-  if ((int)blockIdx.x >= *c.n_chunks) return;
-  const Chunk ch = c.chunks[blockIdx.x];
+  if ((int)blockIdx.x >= *c.n_vchunks) return;
+  const Chunk ch = c.vchunks[blockIdx.x];
   const Slot& s = c.st[ch.slot];
   const int action = s.action;
   if (action == ACT_NONE || action == ACT_FINISH) return;

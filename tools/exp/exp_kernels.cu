@@ -1,0 +1,180 @@
+// Experimental SpMV-pair kernel variants (NOT product code): used to pick the design by measurement.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#define DI __device__ __forceinline__
+DI double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+DI int ld_stream_i32(const int* p) { int v; asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+DI double ld_stream_f64(const double* p) { double v; asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+
+// ---------------- gather variants: w[p] = s[p] * sum_k val[k] * y[col[k]] over row perm[p]
+template <int MODE>
+__global__ void __launch_bounds__(256) g_base(const int64_t* __restrict__ rp, const int* __restrict__ col, const double* __restrict__ val,
+                                              const int* __restrict__ perm, const double* __restrict__ y, double* __restrict__ w, int n_rows, int rows_per_cta) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * rows_per_cta;
+  for (int r = warp; r < rows_per_cta; r += 8) {
+    int p = r0 + r; if (p >= n_rows) break;
+    int row = perm[p];
+    int64_t rs = rp[row], re = rp[row + 1];
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int64_t k = rs + lane;
+    for (; k + 96 < re; k += 128) {
+      int c0, c1, c2, c3; double v0, v1, v2, v3;
+      if (MODE == 1) { c0 = ld_stream_i32(col + k); c1 = ld_stream_i32(col + k + 32); c2 = ld_stream_i32(col + k + 64); c3 = ld_stream_i32(col + k + 96);
+        v0 = ld_stream_f64(val + k); v1 = ld_stream_f64(val + k + 32); v2 = ld_stream_f64(val + k + 64); v3 = ld_stream_f64(val + k + 96); }
+      else { c0 = __ldg(col + k); c1 = __ldg(col + k + 32); c2 = __ldg(col + k + 64); c3 = __ldg(col + k + 96);
+        v0 = __ldg(val + k); v1 = __ldg(val + k + 32); v2 = __ldg(val + k + 64); v3 = __ldg(val + k + 96); }
+      if (MODE == 2) { a0 += v0 * c0; a1 += v1 * c1; a2 += v2 * c2; a3 += v3 * c3; }     // stream only, no y gather
+      else { a0 += v0 * y[c0]; a1 += v1 * y[c1]; a2 += v2 * y[c2]; a3 += v3 * y[c3]; }
+    }
+    for (; k < re; k += 32) a0 += __ldg(val + k) * (MODE == 2 ? (double)__ldg(col + k) : y[__ldg(col + k)]);
+    double s = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) w[p] = s;
+  }
+}
+
+// pipelined: U-way unroll, register double-buffering, next-row pointer prefetch, streaming loads bypass L1
+template <int U, int NOALLOC>
+__global__ void __launch_bounds__(256) g_pipe(const int64_t* __restrict__ rp, const int* __restrict__ col, const double* __restrict__ val,
+                                              const int* __restrict__ perm, const double* __restrict__ y, double* __restrict__ w, int n_rows, int rows_per_cta) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * rows_per_cta;
+  int p = r0 + warp;
+  if (warp >= rows_per_cta || p >= n_rows) return;
+  int row = perm[p];
+  int64_t rs = rp[row], re = rp[row + 1];
+  for (;;) {
+    // prefetch next row's extent
+    int pn = p + 8; bool has_next = (pn < r0 + rows_per_cta) && (pn < n_rows);
+    int64_t nrs = 0, nre = 0;
+    if (has_next) { int nrow = perm[pn]; nrs = rp[nrow]; nre = rp[nrow + 1]; }
+    double acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = 0.0;
+    int64_t k = rs + lane;
+    int c[U]; double v[U];
+    bool have = (k + 32 * (U - 1) < re);
+    if (have) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) { c[u] = NOALLOC ? ld_stream_i32(col + k + 32 * u) : __ldg(col + k + 32 * u); v[u] = NOALLOC ? ld_stream_f64(val + k + 32 * u) : __ldg(val + k + 32 * u); }
+    }
+    while (have) {
+      int64_t kn = k + 32 * U;
+      bool have_n = (kn + 32 * (U - 1) < re);
+      int cn[U]; double vn[U];
+      if (have_n) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) { cn[u] = NOALLOC ? ld_stream_i32(col + kn + 32 * u) : __ldg(col + kn + 32 * u); vn[u] = NOALLOC ? ld_stream_f64(val + kn + 32 * u) : __ldg(val + kn + 32 * u); }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] += v[u] * y[c[u]];
+      if (have_n) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) { c[u] = cn[u]; v[u] = vn[u]; }
+      }
+      k = kn; have = have_n;
+    }
+    for (; k < re; k += 32) acc[0] += __ldg(val + k) * y[__ldg(col + k)];
+    double s = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) s += acc[u];
+    s = warp_sum(s);
+    if (lane == 0) w[p] = s;
+    if (!has_next) break;
+    p = pn; rs = nrs; re = nre;
+  }
+}
+
+// ---------------- scatter variants: y[col[k]] += val[k] * x[p]
+template <int MODE>
+__global__ void __launch_bounds__(256) s_base(const int64_t* __restrict__ rp, const int* __restrict__ col, const double* __restrict__ val,
+                                              const int* __restrict__ perm, const double* __restrict__ x, double* __restrict__ y, int n_rows, int rows_per_cta,
+                                              int n_cols, int replicas, int64_t ystride) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * rows_per_cta;
+  double* yy = y + (int64_t)(blockIdx.x % replicas) * ystride;
+  for (int r = warp; r < rows_per_cta; r += 8) {
+    int p = r0 + r; if (p >= n_rows) break;
+    int row = perm[p];
+    double xi = x[p];
+    int64_t rs = rp[row], re = rp[row + 1];
+    int64_t k = rs + lane;
+    for (; k + 96 < re; k += 128) {
+      int c0 = __ldg(col + k), c1 = __ldg(col + k + 32), c2 = __ldg(col + k + 64), c3 = __ldg(col + k + 96);
+      double v0 = __ldg(val + k), v1 = __ldg(val + k + 32), v2 = __ldg(val + k + 64), v3 = __ldg(val + k + 96);
+      if (MODE == 1) {   // uniform pseudo-random columns: no hot addresses
+        c0 = (int)(((unsigned)(k * 2654435761u)) % (unsigned)n_cols); c1 = (int)(((unsigned)((k + 32) * 2654435761u)) % (unsigned)n_cols);
+        c2 = (int)(((unsigned)((k + 64) * 2654435761u)) % (unsigned)n_cols); c3 = (int)(((unsigned)((k + 96) * 2654435761u)) % (unsigned)n_cols);
+      }
+      atomicAdd(yy + c0, v0 * xi); atomicAdd(yy + c1, v1 * xi); atomicAdd(yy + c2, v2 * xi); atomicAdd(yy + c3, v3 * xi);
+    }
+    for (; k < re; k += 32) atomicAdd(yy + __ldg(col + k), __ldg(val + k) * xi);
+  }
+}
+
+// transposed product from a column-sorted COO copy (ccol sorted, cpos = row position, cval): each lane owns E
+// consecutive entries, merges runs locally, warp-merges when the whole warp is one run; atomics only per run.
+template <int E>
+__global__ void __launch_bounds__(256) t_coo(const int* __restrict__ ccol, const int* __restrict__ cpos, const double* __restrict__ cval,
+                                             const double* __restrict__ x, double* __restrict__ y, int64_t nnz) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t base = warp_global * (32 * E) + (int64_t)lane * E;
+  if (warp_global * (32 * E) >= nnz) return;
+  int c[E]; double t[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    int64_t k = base + e;
+    if (k < nnz) { c[e] = ld_stream_i32(ccol + k); int p = ld_stream_i32(cpos + k); t[e] = ld_stream_f64(cval + k) * x[p]; }
+    else { c[e] = -1; t[e] = 0.0; }
+  }
+  // whole-warp single run?
+  int cfirst = __shfl_sync(0xffffffffu, c[0], 0);
+  int clast = __shfl_sync(0xffffffffu, c[E - 1], 31);
+  if (cfirst == clast && cfirst >= 0) {
+    double s = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) s += t[e];
+    s = warp_sum(s);
+    if (lane == 0) atomicAdd(y + cfirst, s);
+    return;
+  }
+  double acc = t[0]; int cur = c[0];
+#pragma unroll
+  for (int e = 1; e < E; ++e) {
+    if (c[e] == cur) acc += t[e];
+    else { if (cur >= 0) atomicAdd(y + cur, acc); cur = c[e]; acc = t[e]; }
+  }
+  if (cur >= 0) atomicAdd(y + cur, acc);
+}
+
+extern "C" {
+#define LAUNCH_G(KERN) KERN<<<(n_rows + rpc - 1) / rpc, 256>>>(rp, col, val, perm, y, w, n_rows, rpc)
+void exp_gather(int variant, const int64_t* rp, const int* col, const double* val, const int* perm, const double* y, double* w, int n_rows, int rpc) {
+  switch (variant) {
+    case 0: LAUNCH_G((g_base<0>)); break;
+    case 1: LAUNCH_G((g_base<1>)); break;
+    case 2: LAUNCH_G((g_base<2>)); break;
+    case 3: LAUNCH_G((g_pipe<4, 0>)); break;
+    case 4: LAUNCH_G((g_pipe<4, 1>)); break;
+    case 5: LAUNCH_G((g_pipe<8, 1>)); break;
+    case 6: LAUNCH_G((g_pipe<2, 1>)); break;
+    case 7: LAUNCH_G((g_pipe<8, 0>)); break;
+  }
+}
+void exp_scatter(int variant, const int64_t* rp, const int* col, const double* val, const int* perm, const double* x, double* y, int n_rows, int rpc,
+                 int n_cols, int replicas, int64_t ystride) {
+  int grid = (n_rows + rpc - 1) / rpc;
+  if (variant == 0) s_base<0><<<grid, 256>>>(rp, col, val, perm, x, y, n_rows, rpc, n_cols, replicas, ystride);
+  else s_base<1><<<grid, 256>>>(rp, col, val, perm, x, y, n_rows, rpc, n_cols, replicas, ystride);
+}
+void exp_tcoo(int E, const int* ccol, const int* cpos, const double* cval, const double* x, double* y, int64_t nnz) {
+  if (E == 8) { int64_t warps = (nnz + 255) / 256; t_coo<8><<<(unsigned)((warps + 7) / 8), 256>>>(ccol, cpos, cval, x, y, nnz); }
+  else if (E == 4) { int64_t warps = (nnz + 127) / 128; t_coo<4><<<(unsigned)((warps + 7) / 8), 256>>>(ccol, cpos, cval, x, y, nnz); }
+  else { int64_t warps = (nnz + 511) / 512; t_coo<16><<<(unsigned)((warps + 7) / 8), 256>>>(ccol, cpos, cval, x, y, nnz); }
+}
+}
