@@ -155,17 +155,9 @@ def main():
     lib = T._lib.load()
     if world > 1:
         import torch.distributed as dist
+        from too_many_cells_b200 import dist as tdist
         dist.init_process_group("nccl", device_id=dev)
-        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            import ctypes
-            buf = (ctypes.c_uint8 * 128)()
-            T._lib.check(lib.tmc_comm_unique_id(buf))
-            idt = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
-        dist.broadcast(idt, 0)
-        idb = bytes(idt.cpu().tolist())
-        import ctypes
-        T._lib.check(lib.tmc_comm_init(ctypes.create_string_buffer(idb, 128), rank, world, local_rank))
+        tdist.init_comm(rank, world, local_rank, dev)          # libtmc's own NCCL communicator (ids travel over torch.distributed)
 
     def barrier():
         if world > 1:
@@ -174,16 +166,22 @@ def main():
 
     n, g, k, d, s, binary = synth.CONFIGS[name]
     t0 = time.time()
-    row_ptr, col, val_raw = synth.synth_counts_torch(n, g, k, d, s, dev, binary)
+    lo, hi = (n * rank // world, n * (rank + 1) // world)          # this rank's static row block
+    row_ptr, col, val_raw = synth.synth_counts_torch(n, g, k, d, s, dev, binary, row_range=(lo, hi))
     torch.cuda.synchronize()
-    nnz = int(val_raw.numel())
+    nnz_local = int(val_raw.numel())
+    nnz = nnz_local
+    if world > 1:
+        tn = torch.tensor([nnz_local], device=dev, dtype=torch.int64)
+        torch.distributed.all_reduce(tn)
+        nnz = int(tn.item())
     gen_s = time.time() - t0
     work = torch.empty_like(val_raw)
 
     def step_dev(profile):
         work.copy_(val_raw)                       # raw counts resident in HBM; tf-idf + L2 happen inside the step
         torch.cuda.synchronize()
-        b = T.DeviceB.adopt_device(n, g, row_ptr, col, work, normalize=True, device=local_rank)
+        b = T.DeviceB.adopt_device(hi - lo, g, row_ptr, col, work, normalize=True, device=local_rank, row_offset=lo, n_rows_global=n)
         tree = T.hierarchical_spectral_cluster(b, profile=profile)
         b.free()
         return tree
@@ -210,20 +208,28 @@ def main():
     h_ptr = row_ptr.cpu().pin_memory()
     h_col = col.cpu().pin_memory()
     h_val = val_raw.cpu().pin_memory()
-    host = (h_ptr.numpy(), h_col.numpy(), h_val.numpy(), (n, g))
+    host = (h_ptr.numpy(), h_col.numpy(), h_val.numpy(), (hi - lo, g), lo, n)
     e2e_steps = max(1, min(args.steps, 2))
-    T.hierarchical_spectral_cluster(host, normalize=True)     # warm
+    T.hierarchical_spectral_cluster(host, normalize=True, device=local_rank)     # warm
     barrier()
     t = time.perf_counter()
     for _ in range(e2e_steps):
-        tr_e = T.hierarchical_spectral_cluster(host, normalize=True)
+        tr_e = T.hierarchical_spectral_cluster(host, normalize=True, device=local_rank)
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t) / e2e_steps
     h2d = int(h_ptr.numel() * 8 + h_col.numel() * 4 + h_val.numel() * 8)
     d2h = int(tr_e.n_nodes * (8 * 5 + 8 * 2 + 4) + n * 8)
+    if world > 1:
+        th = torch.tensor([h2d], device=dev, dtype=torch.int64)
+        torch.distributed.all_reduce(th)
+        h2d = int(th.item())
+        te = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
+        e2e_ms = float(te.item())
 
     if rank != 0:
         if world > 1:
+            tdist.destroy_comm()
             torch.distributed.destroy_process_group()
         return
 
@@ -237,21 +243,25 @@ def main():
     else:
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
     achieved = alg / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
-    # root-level pair in isolation (largest single launch pair)
-    work.copy_(val_raw)
-    b = T.DeviceB.adopt_device(n, g, row_ptr, col, work, normalize=True, device=local_rank)
-    sc_ms, ga_ms = T.bench_spmv_pair(b, 10)
-    b.free()
-    pair_bytes = 24.0 * nnz + 16.0 * (n + 1) + 32.0 * n + 16.0 * g
+    # root-level pair in isolation (largest single launch pair) -- single-rank only
+    if world == 1:
+        work.copy_(val_raw)
+        b = T.DeviceB.adopt_device(n, g, row_ptr, col, work, normalize=True, device=local_rank)
+        sc_ms, ga_ms = T.bench_spmv_pair(b, 10)
+        b.free()
+        pair_bytes = 24.0 * nnz + 16.0 * (n + 1) + 32.0 * n + 16.0 * g
+        root_pair = {"scatter_ms": sc_ms, "gather_ms": ga_ms, "bytes": pair_bytes,
+                     "scatter_gbs": 0.5 * pair_bytes / (sc_ms * 1e-3) / 1e9, "gather_gbs": 0.5 * pair_bytes / (ga_ms * 1e-3) / 1e9}
+    else:
+        root_pair = None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
             "traffic": None, "peak_source": peak_src, "kernel": "k_scatter+k_gather (SpMV pair y=C^T x, x'=C y), all launches of the timed steps",
             "algorithmic_bytes_per_step": alg / len(trees), "spmv_ms_per_step": spmv_ms / len(trees),
             "spmv_share_of_step": spmv_ms / len(trees) / ms_step,
-            "root_pair": {"scatter_ms": sc_ms, "gather_ms": ga_ms, "bytes": pair_bytes,
-                          "scatter_gbs": 0.5 * pair_bytes / (sc_ms * 1e-3) / 1e9, "gather_gbs": 0.5 * pair_bytes / (ga_ms * 1e-3) / 1e9}}
+            "per_gpu": True, "root_pair": root_pair}
     line = {"metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": dict(cfg, nnz=nnz, parallelism=f"rows sharded over {world} GPU(s)"),
+            "data": "synthetic", "config": dict(cfg, nnz=nnz, parallelism=f"static row blocks over {world} GPU(s), NCCL all-reduce of y = B^T x per half-step"),
             "clocks": clocks,
             "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roof,
@@ -263,6 +273,7 @@ def main():
                                 "sample": desc + "; value is ms for ONE tree on that sample, not the full workload"}
     print(json.dumps(line))
     if world > 1:
+        tdist.destroy_comm()
         torch.distributed.destroy_process_group()
 
 

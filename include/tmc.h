@@ -46,6 +46,10 @@ typedef struct {
   const int64_t* row_ptr;   /* n_rows + 1 */
   const int32_t* col_idx;   /* nnz */
   const double*  val;       /* nnz */
+  /* multi-GPU row blocks: leave both 0 for a whole matrix.  With a communicator, a whole
+   * matrix passed on every rank is sliced into contiguous row blocks; a rank may instead pass only its
+   * own block: n_rows = rows in the block, row_offset = global id of its first row. */
+  int64_t row_offset, n_rows_global;
 } tmc_csr;
 
 /* Flag contract of the make-tree engine call (src/TooManyCells/Program/Options.hs:172-178,
@@ -110,9 +114,11 @@ int tmc_row_l2(const tmc_csr* b2, double* val_out, double* norm_out);
 /* Upload a B2 matrix (host CSR) and keep B = b2ToB(B2) on the device (normalize=1 applies idf first). */
 int  tmc_matrix_upload(const tmc_csr* b2, int normalize, int device, tmc_matrix** out);
 /* Adopt DEVICE arrays (row_ptr int64, col int32, val double; not copied, caller keeps them alive).
- * Values are normalised in place (idf if normalize, then row L2). */
+ * Values are normalised in place (idf if normalize, then row L2).  row_offset / n_rows_global describe this
+ * rank's row block under a communicator (0, 0 = the whole matrix). */
 int  tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* row_ptr_dev,
-                          const int32_t* col_dev, double* val_dev, int normalize, int device, tmc_matrix** out);
+                          const int32_t* col_dev, double* val_dev, int64_t row_offset, int64_t n_rows_global,
+                          int normalize, int device, tmc_matrix** out);
 void tmc_matrix_free(tmc_matrix*);
 
 /* == hierarchicalSpectralCluster ... (Left mat)  (Cluster.hs:147-156): the whole tree. */

@@ -26,7 +26,8 @@ OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_ZERO_ROW, ERR_NAN, ERR_NEGATIVE, E
 
 class Csr(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("n_cols", C.c_int64), ("nnz", C.c_int64),
-                ("row_ptr", C.c_void_p), ("col_idx", C.c_void_p), ("val", C.c_void_p)]
+                ("row_ptr", C.c_void_p), ("col_idx", C.c_void_p), ("val", C.c_void_p),
+                ("row_offset", C.c_int64), ("n_rows_global", C.c_int64)]
 
 
 class Opts(C.Structure):
@@ -56,7 +57,7 @@ SIGNATURES = {
     "tmc_tfidf": (C.c_int, [C.POINTER(Csr), _P, _P]),
     "tmc_row_l2": (C.c_int, [C.POINTER(Csr), _P, _P]),
     "tmc_matrix_upload": (C.c_int, [C.POINTER(Csr), C.c_int, C.c_int, C.POINTER(_P)]),
-    "tmc_matrix_adopt_dev": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "tmc_matrix_adopt_dev": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(_P)]),
     "tmc_matrix_free": (None, [_P]),
     "tmc_make_tree": (C.c_int, [C.POINTER(Csr), C.POINTER(Opts), C.POINTER(C.POINTER(Tree))]),
     "tmc_make_tree_dev": (C.c_int, [_P, C.POINTER(Opts), C.POINTER(C.POINTER(Tree))]),

@@ -12,6 +12,8 @@
 #include <string.h>
 #include <algorithm>
 #include <deque>
+#include <functional>
+#include <queue>
 #include <string>
 #include <vector>
 
@@ -67,7 +69,8 @@ enum { NCCL_UINT8 = 1, NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
 // ----------------------------------------------------------------------------- device matrix
 struct Workspace;
 struct tmc_matrix {
-  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;   // n_rows = rows owned by this rank
+  int64_t row_offset = 0, n_rows_global = 0; // static row-block ownership across ranks
   int64_t* row_ptr = nullptr; int32_t* col = nullptr; double* val = nullptr;
   bool owns = false;
   int device = 0;
@@ -110,8 +113,8 @@ static int pick_device(int device) {
 
 static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
   const int64_t m = b->n_rows;
-  int K = std::max(2, (int)std::min<int64_t>(o.max_lanczos > 0 ? o.max_lanczos : 320, m));
-  int max_active = (int)std::min<int64_t>(std::max<int64_t>(1, m / 2), o.max_active > 0 ? o.max_active : 2048);
+  int K = std::max(2, (int)std::min<int64_t>(o.max_lanczos > 0 ? o.max_lanczos : 320, b->n_rows_global));
+  int max_active = (int)std::min<int64_t>(std::max<int64_t>(1, b->n_rows_global / 2), o.max_active > 0 ? o.max_active : 2048);
   max_active = std::min(max_active, 4096);
   if (b->ws && b->ws->K == K && b->ws->max_active == max_active) return b->ws;
   delete b->ws; b->ws = nullptr;
@@ -121,7 +124,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     CK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     Ctx& c = w->c;
     c.row_ptr = b->row_ptr; c.col = b->col; c.val = b->val;
-    c.n_rows = (int)m; c.n_cols = (int)b->n_cols;
+    c.n_rows = (int)m; c.n_cols = (int)b->n_cols; c.row_offset = b->row_offset;
     c.perm = w->A<int>(m); c.perm_tmp = w->A<int>(m);
     c.d = w->A<double>(m); c.sdeg = w->A<double>(m); c.xin = w->A<double>(m); c.w = w->A<double>(m); c.u2 = w->A<double>(m);
     c.label = w->A<uint8_t>(m);
@@ -179,7 +182,11 @@ static void normalise_dev(tmc_matrix* b, int normalize, double* norm_out_dev, do
       df = dalloc<int>(b->n_cols); idf = idf_out_dev ? idf_out_dev : dalloc<double>(b->n_cols);
       CK(cudaMemset(df, 0, sizeof(int) * b->n_cols));
       k_df_count<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, df, d_err);
-      k_idf<<<(int)((b->n_cols + 255) / 256), 256>>>(df, (int)b->n_cols, (double)b->n_rows, idf);
+      if (g_nccl.comm && g_nccl.world > 1) {      // df over all ranks' row blocks
+        int r = g_nccl.AllReduce(df, df, (size_t)b->n_cols, NCCL_INT32, NCCL_SUM, g_nccl.comm, 0);
+        if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(df) failed");
+      }
+      k_idf<<<(int)((b->n_cols + 255) / 256), 256>>>(df, (int)b->n_cols, (double)b->n_rows_global, idf);
       k_idf_scale<<<grid, 256>>>(b->col, b->val, b->nnz, idf);
     }
     if (do_l2) k_row_l2<<<grid, 256>>>(b->row_ptr, b->col, b->val, (int)b->n_rows, (int)b->n_cols, norm_out_dev, d_err);
@@ -206,30 +213,48 @@ static void validate_csr(const tmc_csr* a) {
   if (a->n_rows < 0 || a->n_cols < 0 || a->nnz < 0) throw TmcError(TMC_ERR_INVALID, "negative dimension");
   if (a->n_rows >= (int64_t)1 << 31 || a->n_cols >= (int64_t)1 << 31) throw TmcError(TMC_ERR_INVALID, "dimension exceeds int32");
   if (a->row_ptr[0] != 0 || a->row_ptr[a->n_rows] != a->nnz) throw TmcError(TMC_ERR_INVALID, "row_ptr does not span [0, nnz]");
+  if (a->n_rows_global != 0 && (a->row_offset < 0 || a->row_offset + a->n_rows > a->n_rows_global))
+    throw TmcError(TMC_ERR_INVALID, "row block outside [0, n_rows_global)");
 }
 
+// Host CSR -> device.  A full matrix handed to every rank of a communicator is sliced into this rank's
+// contiguous row block; a caller-supplied block (n_rows_global > n_rows) is taken as is.
 static tmc_matrix* upload(const tmc_csr* a, int device) {
   validate_csr(a);
   tmc_matrix* b = new tmc_matrix();
   try {
     b->device = pick_device(device);
-    b->n_rows = a->n_rows; b->n_cols = a->n_cols; b->nnz = a->nnz; b->owns = true;
-    b->row_ptr = dalloc<int64_t>(a->n_rows + 1); b->col = dalloc<int32_t>(a->nnz); b->val = dalloc<double>(a->nnz);
-    CK(cudaMemcpy(b->row_ptr, a->row_ptr, sizeof(int64_t) * (a->n_rows + 1), cudaMemcpyHostToDevice));
-    if (a->nnz) {
-      CK(cudaMemcpy(b->col, a->col_idx, sizeof(int32_t) * a->nnz, cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(b->val, a->val, sizeof(double) * a->nnz, cudaMemcpyHostToDevice));
+    const int world = g_nccl.comm ? g_nccl.world : 1, rank = g_nccl.comm ? g_nccl.rank : 0;
+    const bool is_block = a->n_rows_global != 0 && a->n_rows_global != a->n_rows;
+    int64_t lo = 0, hi = a->n_rows;
+    b->n_rows_global = is_block ? a->n_rows_global : a->n_rows;
+    b->row_offset = is_block ? a->row_offset : 0;
+    if (!is_block && world > 1) { lo = a->n_rows * rank / world; hi = a->n_rows * (rank + 1) / world; b->row_offset = lo; }
+    const int64_t k0 = a->row_ptr[lo], k1 = a->row_ptr[hi];
+    b->n_rows = hi - lo; b->n_cols = a->n_cols; b->nnz = k1 - k0; b->owns = true;
+    b->row_ptr = dalloc<int64_t>(b->n_rows + 1); b->col = dalloc<int32_t>(b->nnz); b->val = dalloc<double>(b->nnz);
+    if (k0 == 0) {
+      CK(cudaMemcpy(b->row_ptr, a->row_ptr + lo, sizeof(int64_t) * (b->n_rows + 1), cudaMemcpyHostToDevice));
+    } else {
+      std::vector<int64_t> rp(b->n_rows + 1);
+      for (int64_t i = 0; i <= b->n_rows; ++i) rp[i] = a->row_ptr[lo + i] - k0;
+      CK(cudaMemcpy(b->row_ptr, rp.data(), sizeof(int64_t) * (b->n_rows + 1), cudaMemcpyHostToDevice));
+    }
+    if (b->nnz) {
+      CK(cudaMemcpy(b->col, a->col_idx + k0, sizeof(int32_t) * b->nnz, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(b->val, a->val + k0, sizeof(double) * b->nnz, cudaMemcpyHostToDevice));
     }
   } catch (...) { tmc_matrix_free(b); throw; }
   return b;
 }
 
 // ----------------------------------------------------------------------------- the scheduler
-struct HostNode { int begin, end, parent, left, right, iters; double q, theta; };
+struct HostNode { int begin, end, gsize, parent, left, right, iters; double q, theta; };   // [begin,end) local, gsize global
 
 struct Engine {
   tmc_matrix* b; Workspace* w; tmc_opts o; Ctx c; cudaStream_t s;
-  std::vector<int> hstate, slot_node, free_slots;
+  std::vector<int> hstate, slot_node;
+  std::priority_queue<int, std::vector<int>, std::greater<int>> free_slots;   // lowest index first: keeps the y arena compact
   std::vector<HostNode> nodes;
   std::deque<int> pending;
   int hi_slot = 0;
@@ -247,7 +272,7 @@ struct Engine {
     c.max_restarts = o.max_restarts >= 0 ? o.max_restarts : 8; c.seed = o.seed;
     c.rank = g_nccl.comm ? g_nccl.rank : 0; c.world = g_nccl.comm ? g_nccl.world : 1;
     hstate.assign(w->max_active, ST_IDLE); slot_node.assign(w->max_active, -1);
-    for (int i = w->max_active - 1; i >= 0; --i) free_slots.push_back(i);
+    for (int i = 0; i < w->max_active; ++i) free_slots.push(i);
     profile = o.profile != 0;
     CK(cudaMemsetAsync(c.st, 0, sizeof(Slot) * w->max_active, s));
     CK(cudaMemsetAsync(c.err, 0, sizeof(int), s));
@@ -274,8 +299,8 @@ struct Engine {
     int n = 0;
     while (!pending.empty() && !free_slots.empty()) {
       int node = pending.front(); pending.pop_front();
-      int slot = free_slots.back(); free_slots.pop_back();
-      w->h_act[n++] = Activation{slot, nodes[node].begin, nodes[node].end, node, stop_after};
+      int slot = free_slots.top(); free_slots.pop();
+      w->h_act[n++] = Activation{slot, nodes[node].begin, nodes[node].end, nodes[node].gsize, node, stop_after};
       hstate[slot] = ST_DEG; slot_node[slot] = node;
       hi_slot = std::max(hi_slot, slot + 1);
     }
@@ -297,26 +322,35 @@ struct Engine {
   void allreduce_f64(double* p, size_t n) {
     if (c.world > 1 && n) nccl_check(g_nccl.AllReduce(p, p, n, NCCL_FLOAT64, NCCL_SUM, g_nccl.comm, s), "ncclAllReduce(f64)");
   }
+  void allreduce_host_i32(std::vector<int>& v) {       // small host-side exchanges at the end of the tree build
+    if (c.world <= 1 || v.empty()) return;
+    int* d = dalloc<int>(v.size());
+    try {
+      CK(cudaMemcpyAsync(d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, s));
+      nccl_check(g_nccl.AllReduce(d, d, v.size(), NCCL_INT32, NCCL_SUM, g_nccl.comm, s), "ncclAllReduce(i32)");
+      CK(cudaMemcpyAsync(v.data(), d, sizeof(int) * v.size(), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+    } catch (...) { cudaFree(d); throw; }
+    cudaFree(d);
+  }
   void allreduce_u8(uint8_t* p, size_t n) {
     if (c.world > 1 && n) nccl_check(g_nccl.AllReduce(p, p, n, NCCL_UINT8, NCCL_SUM, g_nccl.comm, s), "ncclAllReduce(u8)");
   }
-  int local_len(int len) const { return (int)((int64_t)len * (c.rank + 1) / c.world) - (int)((int64_t)len * c.rank / c.world); }
 
   // One sweep: every live slot advances by one step of its lifecycle
   // (degree pass | start-vector orthogonalisation | Lanczos step | modularity + split).
   void sweep(bool only_spmv = false) {
     int n_sc = 0, n_ga = 0, n_mod = 0, n_or = 0, live_n = 0; int64_t rows = 0;
-    int mod_lo = INT32_MAX, mod_hi = 0;
     for (int sl = 0; sl < hi_slot; ++sl) {
       int st = hstate[sl];
       if (st < ST_DEG || st > ST_MOD) continue;
       live_n++;
       const HostNode& nd = nodes[slot_node[sl]];
       int len = nd.end - nd.begin;
-      rows += local_len(len);
+      rows += len;
       if (st == ST_DEG || st == ST_LAN || st == ST_MOD) n_sc++;
-      if (st == ST_DEG || st == ST_LAN) { n_ga++; alg_vec_bytes += 16.0 * (len + 1) + 32.0 * len + 16.0 * (double)b->n_cols; }
-      if (st == ST_MOD) { n_mod++; mod_lo = std::min(mod_lo, nd.begin); mod_hi = std::max(mod_hi, nd.end); }
+      if (st == ST_DEG || st == ST_LAN) { n_ga++; alg_vec_bytes += 16.0 * (len + 1) + 32.0 * len + 16.0 * (double)b->n_cols / c.world; }
+      if (st == ST_MOD) n_mod++;
       if (st == ST_ORTH0 || st == ST_LAN) n_or++;
     }
     if (!live_n) return;
@@ -331,7 +365,7 @@ struct Engine {
       int st = hstate[sl];
       if (st < ST_DEG || st > ST_MOD) continue;
       const HostNode& nd = nodes[slot_node[sl]];
-      const int ll = local_len(nd.end - nd.begin);
+      const int ll = nd.end - nd.begin;
       nch += (ll + R - 1) / R;
       nvch += (ll + RV - 1) / RV;
     }
@@ -350,25 +384,19 @@ struct Engine {
     if (only_spmv) { CK(cudaGetLastError()); return; }
     if (n_mod) { k_ynorm<<<dim3(hi_slot, ny), 256, 0, s>>>(c); n_launch++; }
     const size_t upd_smem = sizeof(double) * ((size_t)c.K + 2 + 8 * (size_t)RV);
-    if (n_or && nvch) {
-      k_dots<<<nvch, 256, 0, s>>>(c, 0); n_launch++;
+    if (n_or) {      // kernels depend on this rank's rows, collectives only on the (rank-identical) slot states
+      if (nvch) { k_dots<<<nvch, 256, 0, s>>>(c, 0); n_launch++; }
       allreduce_f64(c.redA, (size_t)(c.K + 2) * hi_slot);
-      k_update<<<nvch, 256, upd_smem, s>>>(c, 0); n_launch++;
-      k_dots<<<nvch, 256, 0, s>>>(c, 1); n_launch++;
+      if (nvch) { k_update<<<nvch, 256, upd_smem, s>>>(c, 0); n_launch++; }
+      if (nvch) { k_dots<<<nvch, 256, 0, s>>>(c, 1); n_launch++; }
       allreduce_f64(c.redB, (size_t)(c.K + 2) * hi_slot);
-      k_update<<<nvch, 256, upd_smem, s>>>(c, 1); n_launch++;
+      if (nvch) { k_update<<<nvch, 256, upd_smem, s>>>(c, 1); n_launch++; }
     }
     allreduce_f64(c.scal, (size_t)R_NSCAL * hi_slot);
     k_finish<<<(hi_slot * 32 + 255) / 256, 256, 0, s>>>(c); n_launch++;
     if (nvch) { k_advance<<<nvch, 256, 0, s>>>(c); n_launch++; }
     allreduce_f64(c.red2, 2 * (size_t)hi_slot);
-    if (n_mod) {
-      if (c.world > 1) {
-        k_mask_labels<<<hi_slot, 256, 0, s>>>(c); n_launch++;
-        allreduce_u8(c.label + mod_lo, (size_t)(mod_hi - mod_lo));
-      }
-      k_partition<<<hi_slot, 1024, 0, s>>>(c); n_launch++;
-    }
+    if (n_mod) { k_partition<<<hi_slot, 1024, 0, s>>>(c); n_launch++; }      // local: every rank splits its own cells
     k_commit<<<(hi_slot + 127) / 128, 128, 0, s>>>(c, hi_slot); n_launch++;
     CK(cudaMemcpyAsync(w->h_rep, c.rep, sizeof(Report) * hi_slot, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(w->h_err, c.err, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -389,26 +417,27 @@ struct Engine {
       HostNode& nd = nodes[node];
       nd.q = r.q; nd.theta = r.theta; nd.iters = r.iters;
       if (build_tree && r.split) {
-        int b0 = nd.begin, e0 = nd.end, n0 = r.n0;
+        const int b0 = nd.begin, e0 = nd.end, gs = nd.gsize, n0l = r.n0_local, n0g = r.n0;
         int li = (int)nodes.size(), ri = li + 1;
         nodes[node].left = li; nodes[node].right = ri;
-        nodes.push_back(HostNode{b0, b0 + n0, node, -1, -1, 0, 0.0, 0.0});
-        nodes.push_back(HostNode{b0 + n0, e0, node, -1, -1, 0, 0.0, 0.0});
-        if (n0 >= 2) pending.push_back(li);
-        if (e0 - b0 - n0 >= 2) pending.push_back(ri);
+        nodes.push_back(HostNode{b0, b0 + n0l, n0g, node, -1, -1, 0, 0.0, 0.0});
+        nodes.push_back(HostNode{b0 + n0l, e0, gs - n0g, node, -1, -1, 0, 0.0, 0.0});
+        if (n0g >= 2) pending.push_back(li);
+        if (gs - n0g >= 2) pending.push_back(ri);
       }
-      hstate[sl] = ST_IDLE; slot_node[sl] = -1; free_slots.push_back(sl);
+      hstate[sl] = ST_IDLE; slot_node[sl] = -1; free_slots.push(sl);
     }
     while (hi_slot > 0 && hstate[hi_slot - 1] == ST_IDLE) hi_slot--;
   }
 
+  void take_slot0() { if (!free_slots.empty() && free_slots.top() == 0) free_slots.pop(); }
   int live() const { int n = 0; for (int sl = 0; sl < hi_slot; ++sl) n += (hstate[sl] >= ST_DEG && hstate[sl] <= ST_MOD); return n; }
 
   void run_tree() {
     const int m = (int)b->n_rows;
     nodes.clear(); pending.clear();
-    nodes.push_back(HostNode{0, m, -1, -1, -1, 0, 0.0, 0.0});
-    if (m >= 2) pending.push_back(0);
+    nodes.push_back(HostNode{0, m, (int)b->n_rows_global, -1, -1, -1, 0, 0.0, 0.0});
+    if (b->n_rows_global >= 2) pending.push_back(0);
     for (;;) {
       activate_pending(0);
       if (!live()) break;
@@ -420,7 +449,7 @@ struct Engine {
   // run slot 0 over rows [0,n) until it reports DONE
   void run_single(int n, int stop_after) {
     nodes.clear(); pending.clear();
-    nodes.push_back(HostNode{0, n, -1, -1, -1, 0, 0.0, 0.0});
+    nodes.push_back(HostNode{0, n, n, -1, -1, -1, 0, 0.0, 0.0});
     pending.push_back(0);
     activate_pending(stop_after);
     const int64_t cap = (int64_t)(w->K + 8) * (c.max_restarts + 2) + 16;     // Lanczos always terminates within this
@@ -460,6 +489,7 @@ static void check_opts(const tmc_opts* o) {
 int tmc_tfidf(const tmc_csr* b1, double* val_out, double* idf_out) {
   return guarded([&] {
     if (!val_out) throw TmcError(TMC_ERR_INVALID, "null val_out");
+    if (g_nccl.comm && g_nccl.world > 1) throw TmcError(TMC_ERR_UNSUPPORTED, "host-buffer tmc_tfidf is single-rank; use tmc_matrix_upload(normalize=1)");
     tmc_matrix* b = upload(b1, -1);
     double* idf_dev = nullptr;
     try {
@@ -475,6 +505,7 @@ int tmc_tfidf(const tmc_csr* b1, double* val_out, double* idf_out) {
 int tmc_row_l2(const tmc_csr* b2, double* val_out, double* norm_out) {
   return guarded([&] {
     if (!val_out) throw TmcError(TMC_ERR_INVALID, "null val_out");
+    if (g_nccl.comm && g_nccl.world > 1) throw TmcError(TMC_ERR_UNSUPPORTED, "host-buffer tmc_row_l2 is single-rank; use tmc_matrix_upload");
     tmc_matrix* b = upload(b2, -1);
     double* nd = nullptr;
     try {
@@ -497,14 +528,16 @@ int tmc_matrix_upload(const tmc_csr* b2, int normalize, int device, tmc_matrix**
 }
 
 int tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* row_ptr_dev, const int32_t* col_dev,
-                         double* val_dev, int normalize, int device, tmc_matrix** out) {
+                         double* val_dev, int64_t row_offset, int64_t n_rows_global, int normalize, int device, tmc_matrix** out) {
   return guarded([&] {
     if (!out || !row_ptr_dev || !col_dev || !val_dev) throw TmcError(TMC_ERR_INVALID, "null pointer");
-    if (n_rows >= (int64_t)1 << 31 || n_cols >= (int64_t)1 << 31) throw TmcError(TMC_ERR_INVALID, "dimension exceeds int32");
+    if (n_rows >= (int64_t)1 << 31 || n_cols >= (int64_t)1 << 31 || n_rows_global >= (int64_t)1 << 31) throw TmcError(TMC_ERR_INVALID, "dimension exceeds int32");
     tmc_matrix* b = new tmc_matrix();
     try {
       b->device = pick_device(device);
       b->n_rows = n_rows; b->n_cols = n_cols; b->nnz = nnz; b->owns = false;
+      b->n_rows_global = n_rows_global > 0 ? n_rows_global : n_rows; b->row_offset = n_rows_global > 0 ? row_offset : 0;
+      if (b->row_offset < 0 || b->row_offset + n_rows > b->n_rows_global) throw TmcError(TMC_ERR_INVALID, "row block outside [0, n_rows_global)");
       b->row_ptr = const_cast<int64_t*>(row_ptr_dev); b->col = const_cast<int32_t*>(col_dev); b->val = val_dev;
       normalise_dev(b, normalize, nullptr, nullptr, true);
     } catch (...) { tmc_matrix_free(b); throw; }
@@ -529,7 +562,7 @@ int tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out) {
   return guarded([&] {
     if (!b || !out) throw TmcError(TMC_ERR_INVALID, "null pointer");
     check_opts(opts);
-    if (b->n_rows < 1) throw TmcError(TMC_ERR_INVALID, "empty matrix (reference: error, LoadMatrix.hs:255)");
+    if (b->n_rows_global < 1) throw TmcError(TMC_ERR_INVALID, "empty matrix (reference: error, LoadMatrix.hs:255)");
     Engine eng(b, *opts);
     cudaEvent_t t0, t1;
     CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
@@ -538,7 +571,9 @@ int tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out) {
     eng.run_tree();
     CK(cudaEventRecord(t1, eng.s));
     const int m = (int)b->n_rows;
-    std::vector<int> hperm(m);
+    const int64_t M = b->n_rows_global;
+    const int world = eng.c.world, rank = eng.c.rank;
+    std::vector<int> hperm(std::max(m, 1));
     CK(cudaMemcpyAsync(hperm.data(), eng.c.perm, sizeof(int) * m, cudaMemcpyDeviceToHost, eng.s));
     CK(cudaMemcpyAsync(eng.w->h_stats, eng.c.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, eng.s));
     CK(cudaStreamSynchronize(eng.s));
@@ -549,22 +584,48 @@ int tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out) {
     TreeStorage* ts = new TreeStorage();
     ts->left.assign(nn, -1); ts->right.assign(nn, -1); ts->parent.assign(nn, -1);
     ts->item_begin.resize(nn); ts->item_end.resize(nn); ts->q.resize(nn); ts->theta.resize(nn); ts->iters.resize(nn);
-    std::vector<int64_t> newid(nn, -1); std::vector<int> stack; stack.push_back(0); int64_t next = 0;
+    std::vector<int64_t> newid(nn, -1), gbeg(nn, 0); std::vector<int> stack; stack.push_back(0); int64_t next = 0;
     std::vector<int> order; order.reserve(nn);
+    gbeg[0] = 0;
     while (!stack.empty()) {
       int u = stack.back(); stack.pop_back();
       newid[u] = next++; order.push_back(u);
-      if (eng.nodes[u].left >= 0) { stack.push_back(eng.nodes[u].right); stack.push_back(eng.nodes[u].left); }
+      const HostNode& nd = eng.nodes[u];
+      if (nd.left >= 0) {
+        gbeg[nd.left] = gbeg[u]; gbeg[nd.right] = gbeg[u] + eng.nodes[nd.left].gsize;     // global position space
+        stack.push_back(nd.right); stack.push_back(nd.left);
+      }
     }
     for (int u : order) {
       const HostNode& nd = eng.nodes[u]; int64_t id = newid[u];
       ts->left[id] = nd.left >= 0 ? newid[nd.left] : -1; ts->right[id] = nd.right >= 0 ? newid[nd.right] : -1;
       ts->parent[id] = nd.parent >= 0 ? newid[nd.parent] : -1;
-      ts->item_begin[id] = nd.begin; ts->item_end[id] = nd.end; ts->q[id] = nd.q; ts->theta[id] = nd.theta; ts->iters[id] = nd.iters;
+      ts->item_begin[id] = gbeg[u]; ts->item_end[id] = gbeg[u] + nd.gsize; ts->q[id] = nd.q; ts->theta[id] = nd.theta; ts->iters[id] = nd.iters;
     }
-    ts->perm.assign(hperm.begin(), hperm.end());
+    // global permutation: inside a leaf, rank r's cells follow those of ranks < r (row blocks are ascending in rank,
+    // so every leaf stays ascending in original row id)
+    ts->perm.assign(M, 0);
+    if (world == 1) {
+      for (int i = 0; i < m; ++i) ts->perm[i] = hperm[i];
+    } else {
+      std::vector<int> leaves;
+      for (int u : order) if (eng.nodes[u].left < 0) leaves.push_back(u);
+      const size_t nl = leaves.size();
+      std::vector<int> lsz((size_t)world * nl, 0);
+      for (size_t i = 0; i < nl; ++i) lsz[(size_t)rank * nl + i] = eng.nodes[leaves[i]].end - eng.nodes[leaves[i]].begin;
+      eng.allreduce_host_i32(lsz);
+      std::vector<int> gp(M, 0);
+      for (size_t i = 0; i < nl; ++i) {
+        const HostNode& nd = eng.nodes[leaves[i]];
+        int64_t off = gbeg[leaves[i]];
+        for (int r = 0; r < rank; ++r) off += lsz[(size_t)r * nl + i];
+        for (int p = nd.begin; p < nd.end; ++p) gp[off + (p - nd.begin)] = (int)(b->row_offset + hperm[p]);
+      }
+      eng.allreduce_host_i32(gp);
+      for (int64_t i = 0; i < M; ++i) ts->perm[i] = gp[i];
+    }
     tmc_tree& t = ts->t;
-    t.n_nodes = (int64_t)nn; t.n_rows = m;
+    t.n_nodes = (int64_t)nn; t.n_rows = M;
     t.left = ts->left.data(); t.right = ts->right.data(); t.parent = ts->parent.data(); t.q = ts->q.data(); t.theta = ts->theta.data();
     t.iters = ts->iters.data(); t.item_begin = ts->item_begin.data(); t.item_end = ts->item_end.data(); t.perm = ts->perm.data();
     t.n_sweeps = eng.n_sweeps; t.spmv_pairs_nnz = (int64_t)(eng.w->h_stats[0] + eng.w->h_stats[1]); t.kernel_launches = eng.n_launch;
@@ -598,6 +659,7 @@ void tmc_tree_free(tmc_tree* t) {
 // ---- fine-grained exports, each through the same kernels as the tree build
 static int64_t sel_count(tmc_matrix* b, const int64_t* rows, int64_t n_sel) {
   if (!b) throw TmcError(TMC_ERR_INVALID, "null matrix");
+  if (g_nccl.comm && g_nccl.world > 1) throw TmcError(TMC_ERR_UNSUPPORTED, "per-node exports are single-rank (use tmc_make_tree* under a communicator)");
   int64_t n = rows ? n_sel : b->n_rows;
   if (n < 1 || n > b->n_rows) throw TmcError(TMC_ERR_INVALID, "bad row selection size");
   return n;
@@ -644,9 +706,9 @@ int tmc_modularity(tmc_matrix* b, const int64_t* rows, int64_t n_sel, const uint
     try {
       CK(cudaMemcpyAsync(dl, labels, n, cudaMemcpyHostToDevice, eng.s));
       // re-open slot 0 directly in the modularity state with the caller's labels
-      eng.nodes.clear(); eng.nodes.push_back(HostNode{0, (int)n, -1, -1, -1, 0, 0.0, 0.0});
+      eng.nodes.clear(); eng.nodes.push_back(HostNode{0, (int)n, (int)n, -1, -1, -1, 0, 0.0, 0.0});
       eng.hstate[0] = ST_MOD; eng.slot_node[0] = 0; eng.hi_slot = 1;
-      eng.free_slots.erase(std::remove(eng.free_slots.begin(), eng.free_slots.end(), 0), eng.free_slots.end());
+      eng.take_slot0();
       k_force_state<<<1, 1, 0, eng.s>>>(eng.c, 0, ST_MOD, 0, ST_DONE);
       k_set_labels<<<(int)((n + 255) / 256), 256, 0, eng.s>>>(eng.c, dl, (int)n, 0);
       while (eng.live()) { eng.sweep(); eng.harvest(false); }
@@ -670,7 +732,7 @@ int tmc_partition(const int64_t* rows, int64_t n_sel, const uint8_t* labels, int
       std::vector<uint8_t> l01(n); for (int i = 0; i < n; ++i) l01[i] = labels[i] ? 1 : 0;
       CK(cudaMemcpy(perm, h.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
       CK(cudaMemcpy(lab, l01.data(), n, cudaMemcpyHostToDevice));
-      k_force_partition<<<1, 1>>>(c, 0, 0, n, n - n1);
+      k_force_partition<<<1, 1>>>(c, 0, 0, n);
       k_partition<<<1, 1024>>>(c);
       CK(cudaGetLastError());
       CK(cudaMemcpy(h.data(), perm, sizeof(int) * n, cudaMemcpyDeviceToHost));
@@ -685,9 +747,9 @@ int tmc_partition(const int64_t* rows, int64_t n_sel, const uint8_t* labels, int
 static void setup_pair(Engine& eng, const int64_t* rows, int64_t n, const double* x_dev) {
   eng.init_perm(rows, n);
   eng.run_single((int)n, ST_ORTH0);
-  eng.nodes.clear(); eng.nodes.push_back(HostNode{0, (int)n, -1, -1, -1, 0, 0.0, 0.0});
+  eng.nodes.clear(); eng.nodes.push_back(HostNode{0, (int)n, (int)n, -1, -1, -1, 0, 0.0, 0.0});
   eng.hstate[0] = ST_LAN; eng.slot_node[0] = 0; eng.hi_slot = 1;
-  eng.free_slots.erase(std::remove(eng.free_slots.begin(), eng.free_slots.end(), 0), eng.free_slots.end());
+  eng.take_slot0();
   k_force_state<<<1, 1, 0, eng.s>>>(eng.c, 0, ST_LAN, 1, 0);
   k_set_xin_scaled<<<(int)((n + 255) / 256), 256, 0, eng.s>>>(eng.c, x_dev, (int)n);
 }

@@ -21,8 +21,9 @@ enum SlotAction : int { ACT_NONE = 0, ACT_INIT = 1, ACT_NEXT = 2, ACT_RITZ_LABEL
 enum { R_NRM2 = 0, R_SUMD = 1, R_YNORM2 = 2, R_NSCAL = 4 };
 
 struct Slot {              // one live tree node (device resident)
-  int begin, end;          // position range in perm
-  int lbegin, lend;        // this rank's share of the range (row sharding)
+  int begin, end;          // this rank's position range in its local perm (rows are owned statically per rank)
+  int gsize;               // global number of cells in the node (sum over ranks)
+  int n0_local;            // label-0 cells of this rank (set by k_partition)
   int state, action;
   int j;                   // Lanczos vectors q_1..q_j stored in V[1..j]
   int iters, restarts;
@@ -34,17 +35,19 @@ struct Slot {              // one live tree node (device resident)
 };
 
 struct Report {            // what the host reads back after every sweep
-  int state, split, n0, iters;
+  int state, split, n0, iters;   // n0 = global label-0 count
+  int n0_local, pad;
   double q, theta;
 };
 
 struct Chunk { int slot, begin, len; };
-struct Activation { int slot, begin, end, node, stop_after; };
+struct Activation { int slot, begin, end, gsize, node, stop_after; };
 
 struct Ctx {
   // matrix B (CSR, rows = cells)
   const int64_t* row_ptr; const int32_t* col; const double* val;
-  int n_rows, n_cols;
+  int n_rows, n_cols;              // local rows, features
+  int64_t row_offset;              // global id of local row 0
   // position-indexed state
   int* perm; int* perm_tmp;
   double* d; double* sdeg; double* xin; double* w; double* u2; uint8_t* label;
@@ -151,10 +154,7 @@ __global__ void k_activate(Ctx c, const Activation* __restrict__ acts, int n) {
   if (i >= n) return;
   Activation a = acts[i];
   Slot s;
-  s.begin = a.begin; s.end = a.end;
-  int len = a.end - a.begin;
-  s.lbegin = a.begin + (int)((int64_t)len * c.rank / c.world);
-  s.lend = a.begin + (int)((int64_t)len * (c.rank + 1) / c.world);
+  s.begin = a.begin; s.end = a.end; s.gsize = a.gsize; s.n0_local = 0;
   s.state = ST_DEG; s.action = ACT_NONE; s.j = 0; s.iters = 0; s.restarts = 0; s.node = a.node;
   s.split = 0; s.n0 = 0; s.stop_after = a.stop_after; s.pad = 0;
   s.sumd = 0; s.inv_sqrt_sumd = 0; s.beta = 0; s.theta = 0; s.resid = 0; s.q = 0; s.theta_hint = -1e300;
@@ -170,7 +170,7 @@ __device__ void build_chunk_list(const Ctx& c, int csize, Chunk* out, int* out_n
     int slot = tid * per + q; int n = 0;
     if (slot < c.n_slots) {
       const Slot& s = c.st[slot];
-      if (s.state >= ST_DEG && s.state <= ST_MOD) n = (s.lend - s.lbegin + csize - 1) / csize;
+      if (s.state >= ST_DEG && s.state <= ST_MOD) n = (s.end - s.begin + csize - 1) / csize;
     }
     cnt[q] = n; mine += n;
   }
@@ -201,8 +201,8 @@ __device__ void build_chunk_list(const Ctx& c, int csize, Chunk* out, int* out_n
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (offs[mid] <= ci) lo = mid; else hi = mid; }
     const Slot& s = c.st[lo];
     int k = ci - offs[lo];
-    Chunk ch; ch.slot = lo; ch.begin = s.lbegin + k * csize;
-    ch.len = min(csize, s.lend - ch.begin);
+    Chunk ch; ch.slot = lo; ch.begin = s.begin + k * csize;
+    ch.len = min(csize, s.end - ch.begin);
     out[ci] = ch;
   }
   __syncthreads();
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
     }
     __syncwarp();
     beta = __shfl_sync(0xffffffffu, beta, 0);
-    const int len = s->end - s->begin;
+    const int len = s->gsize;
     const bool exhausted = (j >= len - 1);
     const bool breakdown = !(beta > 1e-13);
     const bool full = (j >= c.K);
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
   // With t = B^T 1 (||t||^2 = sum d), t1 = B^T 1_{c1}:  O_1 = ||t1||^2 - n1,
   // O_0 = ||t - t1||^2 - n0 = sum d - 2 sum_{c1} d + ||t1||^2 - n0,  L_c = sum_{c} d - n_c,  L = sum d - m.
   if (lane == 0) {
-    const double m = (double)(s->end - s->begin);
+    const double m = (double)s->gsize;
     const double n1 = c.red2[2 * slot], sd1 = c.red2[2 * slot + 1];
     const double n0 = m - n1, sd = s->sumd, t1 = scal[R_YNORM2];
     const double L = sd - m;
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
       const double sq = sqrt(dd);
       c.sdeg[p] = 1.0 / sq;
       c.V[p] = sq * isd;                                   // V_0 = u1
-      c.w[p] = hash_unit(c.seed, (uint64_t)c.perm[p]);
+      c.w[p] = hash_unit(c.seed, (uint64_t)(c.row_offset + c.perm[p]));
     }
     return;
   }
@@ -555,12 +555,20 @@ __global__ void __launch_bounds__(1024) k_partition(Ctx c) {
   __shared__ int wtot[32];
   __shared__ int run1_s;
   const int slot = blockIdx.x;
-  const Slot& s = c.st[slot];
+  const Slot s = c.st[slot];
   if (s.state != ST_MOD || s.action != ACT_FINISH || !s.split) return;
-  const int begin = s.begin, end = s.end, n0 = s.n0;
+  const int begin = s.begin, end = s.end;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) run1_s = 0;
+  __shared__ int n0_s;
+  // local label-0 count (the node's cells on other ranks are partitioned by their owners)
+  int ones = 0;
+  for (int p = begin + tid; p < end; p += 1024) ones += c.label[p];
+  ones = __reduce_add_sync(0xffffffffu, ones);
+  if (lane == 0) wtot[wid] = ones;
   __syncthreads();
+  if (tid == 0) { int t = 0; for (int q = 0; q < 32; ++q) t += wtot[q]; n0_s = (end - begin) - t; run1_s = 0; c.st[slot].n0_local = n0_s; }
+  __syncthreads();
+  const int n0 = n0_s;
   for (int base = begin; base < end; base += 1024) {
     const int p = base + tid;
     const int f = (p < end) ? (int)c.label[p] : 0;
@@ -601,7 +609,8 @@ __global__ void k_commit(Ctx c, int n_slots) {
   if (s->stop_after != 0 && state == s->stop_after && state != s->state) state = ST_DONE;   // fine-grained API stop
   s->action = ACT_NONE;
   s->state = state;
-  Report r; r.state = state; r.split = s->split; r.n0 = s->n0; r.iters = s->iters; r.q = s->q; r.theta = s->theta;
+  Report r; r.state = state; r.split = s->split; r.n0 = s->n0; r.iters = s->iters; r.n0_local = s->n0_local; r.pad = 0;
+  r.q = s->q; r.theta = s->theta;
   c.rep[slot] = r;
 }
 
@@ -624,18 +633,10 @@ __global__ void k_force_state(Ctx c, int slot, int state, int j, int stop_after)
   c.red2[2 * slot] = 0.0; c.red2[2 * slot + 1] = 0.0;
 }
 
-// tmc_partition API: set up slot `slot` so that k_partition splits [begin,end) with n0 label-0 rows
-__global__ void k_force_partition(Ctx c, int slot, int begin, int end, int n0) {
+// tmc_partition API: set up slot `slot` so that k_partition splits [begin,end)
+__global__ void k_force_partition(Ctx c, int slot, int begin, int end) {
   Slot& s = c.st[slot];
-  s.begin = begin; s.end = end; s.lbegin = begin; s.lend = end; s.state = ST_MOD; s.action = ACT_FINISH; s.split = 1; s.n0 = n0;
-}
-// multi-GPU: zero the labels outside this rank's share of a splitting node so that an
-// allreduce(sum) over the byte vector assembles the full label vector on every rank
-__global__ void k_mask_labels(Ctx c) {
-  const Slot& s = c.st[blockIdx.x];
-  if (s.state != ST_MOD || s.action != ACT_FINISH || !s.split) return;
-  for (int p = s.begin + threadIdx.x; p < s.lbegin; p += blockDim.x) c.label[p] = 0;
-  for (int p = s.lend + threadIdx.x; p < s.end; p += blockDim.x) c.label[p] = 0;
+  s.begin = begin; s.end = end; s.gsize = end - begin; s.state = ST_MOD; s.action = ACT_FINISH; s.split = 1;
 }
 
 }  // namespace tmc

@@ -31,17 +31,20 @@ from ._lib import Csr, Opts, Tree, TmcError, check
 class HostCsr:
     """Borrowed host CSR (cells x features) in the dtypes the C ABI wants."""
 
-    def __init__(self, mat):
+    def __init__(self, mat, row_offset=0, n_rows_global=0):
         if hasattr(mat, "indptr"):              # scipy.sparse CSR
             indptr, indices, data, shape = mat.indptr, mat.indices, mat.data, mat.shape
         else:
-            indptr, indices, data, shape = mat
+            indptr, indices, data, shape = mat[:4]
+            if len(mat) == 6:                   # (indptr, indices, data, shape, row_offset, n_rows_global): a rank's row block
+                row_offset, n_rows_global = mat[4], mat[5]
         self.indptr = np.ascontiguousarray(indptr, dtype=np.int64)
         self.indices = np.ascontiguousarray(indices, dtype=np.int32)
         self.data = np.ascontiguousarray(data, dtype=np.float64)
         self.shape = (int(shape[0]), int(shape[1]))
         self.c = Csr(self.shape[0], self.shape[1], int(self.data.size),
-                     self.indptr.ctypes.data, self.indices.ctypes.data, self.data.ctypes.data)
+                     self.indptr.ctypes.data, self.indices.ctypes.data, self.data.ctypes.data,
+                     int(row_offset), int(n_rows_global))
 
     @property
     def nnz(self):
@@ -94,12 +97,14 @@ class DeviceB:
         return cls(out, h.shape, h.nnz)
 
     @classmethod
-    def adopt_device(cls, n_rows, n_cols, row_ptr, col, val, normalize=False, device=-1):
-        """Adopt torch CUDA tensors (int64 row_ptr, int32 col, float64 val) without copying; val is normalised in place."""
+    def adopt_device(cls, n_rows, n_cols, row_ptr, col, val, normalize=False, device=-1, row_offset=0, n_rows_global=0):
+        """Adopt torch CUDA tensors (int64 row_ptr, int32 col, float64 val) without copying; val is normalised in place.
+        Under a communicator pass this rank's row block with row_offset / n_rows_global."""
         lib = _lib.load()
         out = C.c_void_p()
         check(lib.tmc_matrix_adopt_dev(int(n_rows), int(n_cols), int(val.numel()), row_ptr.data_ptr(), col.data_ptr(),
-                                       val.data_ptr(), int(bool(normalize)), int(device), C.byref(out)))
+                                       val.data_ptr(), int(row_offset), int(n_rows_global), int(bool(normalize)), int(device),
+                                       C.byref(out)))
         return cls(out, (int(n_rows), int(n_cols)), int(val.numel()), keepalive=(row_ptr, col, val))
 
     def free(self):

@@ -82,29 +82,34 @@ def synth_config(name):
     return synth_counts(n, g, k, d, s, binary)
 
 
-def synth_counts_torch(n_cells, n_genes, nnz_per_cell, depth, seed, device, binary=False, block=4096):
-    """Same recipe on a torch device.  Returns (row_ptr int64, col int32, val float64) tensors on `device`."""
+def synth_counts_torch(n_cells, n_genes, nnz_per_cell, depth, seed, device, binary=False, block=4096, row_range=None):
+    """Same recipe on a torch device, seeded PER ROW BLOCK so that any rank can generate exactly its own rows:
+    rows [lo, hi) = row_range (default: all).  Returns (row_ptr int64, col int32, val float64) tensors on `device`
+    for the local rows (row_ptr rebased to 0)."""
     import torch
     rng = np.random.default_rng(seed)
     prof = _programmes(rng, n_genes, depth)
     lib0 = _solve_library(prof.mean(axis=0), nnz_per_cell)
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
+    lo, hi = (0, n_cells) if row_range is None else row_range
     prof_t = torch.from_numpy(prof).to(device=device, dtype=torch.float32)
-    leaf = torch.randint(0, prof.shape[0], (n_cells,), generator=g, device=device)
-    lib = lib0 * torch.exp(0.3 * torch.randn(n_cells, generator=g, device=device))
-    counts_per_row = torch.zeros(n_cells + 1, dtype=torch.int64, device=device)
+    g = torch.Generator(device=device)
+    counts_per_row = torch.zeros(hi - lo + 1, dtype=torch.int64, device=device)
     cols, vals = [], []
-    for b0 in range(0, n_cells, block):
-        b1 = min(n_cells, b0 + block)
-        lam = prof_t[leaf[b0:b1]] * lib[b0:b1, None].float()
+    for bi in range(lo // block, (hi + block - 1) // block):
+        b0, b1 = bi * block, min(n_cells, (bi + 1) * block)
+        g.manual_seed(seed * 1000003 + bi)
+        leaf = torch.randint(0, prof.shape[0], (b1 - b0,), generator=g, device=device)
+        lib = lib0 * torch.exp(0.3 * torch.randn(b1 - b0, generator=g, device=device))
+        lam = prof_t[leaf] * lib[:, None].float()
         cnt = torch.poisson(lam, generator=g)
         empty = cnt.sum(dim=1) == 0
         if bool(empty.any()):
             er = torch.nonzero(empty).flatten()
             cnt[er, lam[er].argmax(dim=1)] = 1
+        s0, s1 = max(lo, b0) - b0, min(hi, b1) - b0          # the part of this block inside [lo, hi)
+        cnt = cnt[s0:s1]
         nz = torch.nonzero(cnt)
-        counts_per_row[b0 + 1:b1 + 1] = torch.bincount(nz[:, 0], minlength=b1 - b0)
+        counts_per_row[b0 + s0 - lo + 1:b0 + s1 - lo + 1] = torch.bincount(nz[:, 0], minlength=s1 - s0)
         cols.append(nz[:, 1].to(torch.int32))
         v = cnt[nz[:, 0], nz[:, 1]].to(torch.float64)
         vals.append(torch.ones_like(v) if binary else v)
