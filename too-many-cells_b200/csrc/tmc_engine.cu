@@ -22,6 +22,7 @@
 
 using namespace tmc;
 
+static_assert(sizeof(tmc_csr) == 64, "tmc_csr layout is part of the ABI (mirrored in _lib.py)");
 static_assert(sizeof(tmc_opts) == 96, "tmc_opts layout is part of the ABI (mirrored in _lib.py)");
 static_assert(sizeof(tmc_tree) == 136, "tmc_tree layout is part of the ABI (mirrored in _lib.py)");
 
