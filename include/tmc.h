@@ -69,7 +69,8 @@ typedef struct {
   int32_t max_active;       /* concurrently iterating tree nodes (y-vector slots); default 2048 */
   int32_t device;           /* CUDA device ordinal, -1 = current */
   int32_t profile;          /* 1 = time the SpMV kernels with CUDA events (fills tmc_tree.spmv_ms) */
-  int32_t reserved[6];
+  int32_t scatter_mode;     /* y = B^T x: 0 = column-sorted transposed copy per node (default), 1 = CSR scatter with fp64 atomics */
+  int32_t reserved[5];
 } tmc_opts;
 
 /* Result tree: flat, pre-order (node 0 = root, children [label 0, label 1]) exactly as

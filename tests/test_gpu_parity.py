@@ -177,6 +177,20 @@ def test_min_modularity_and_min_size_flags(tiny):
     assert t5.leaf_sets() == o5.leaf_sets()
 
 
+def test_scatter_modes_agree(tiny, golden_small):
+    """y = B^T x through the column-sorted transposed blocks (default) and through CSR + fp64 atomics."""
+    _, _, b2, b, db = tiny
+    n = b.shape[0]
+    t0 = T.hierarchical_spectral_cluster(b2, scatter_mode=0)
+    t1 = T.hierarchical_spectral_cluster(b2, scatter_mode=1)
+    assert t0.leaf_sets() == t1.leaf_sets()
+    assert np.max(np.abs(np.sort(t0.q) - np.sort(t1.q))) < 1e-12
+    a, _ = golden_small
+    s0 = T.hierarchical_spectral_cluster(a, normalize=True, scatter_mode=0)
+    s1 = T.hierarchical_spectral_cluster(a, normalize=True, scatter_mode=1)
+    assert s0.leaf_sets() == s1.leaf_sets()
+
+
 def test_slot_pressure_gives_same_tree(tiny):
     _, _, b2, _, _ = tiny
     t1 = T.hierarchical_spectral_cluster(b2, max_active=2)               # nodes queue for slots

@@ -86,7 +86,7 @@ template <class T> static T* dalloc(size_t n) {
 
 struct Workspace {
   Ctx c{};
-  int K = 0, max_active = 0;
+  int K = 0, max_active = 0, use_t = 0, tcap = 0;
   int64_t m = 0;
   Report* h_rep = nullptr; Activation* h_act = nullptr; Activation* d_act = nullptr;
   int* h_err = nullptr; unsigned long long* h_stats = nullptr;
@@ -117,11 +117,11 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
   int K = std::max(2, (int)std::min<int64_t>(o.max_lanczos > 0 ? o.max_lanczos : 320, b->n_rows_global));
   int max_active = (int)std::min<int64_t>(std::max<int64_t>(1, b->n_rows_global / 2), o.max_active > 0 ? o.max_active : 2048);
   max_active = std::min(max_active, 4096);
-  if (b->ws && b->ws->K == K && b->ws->max_active == max_active) return b->ws;
+  if (b->ws && b->ws->K == K && b->ws->max_active == max_active && b->ws->use_t == (o.scatter_mode == 0)) return b->ws;
   delete b->ws; b->ws = nullptr;
   Workspace* w = new Workspace();
   try {
-    w->K = K; w->max_active = max_active; w->m = m;
+    w->K = K; w->max_active = max_active; w->m = m; w->use_t = (o.scatter_mode == 0);
     CK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     Ctx& c = w->c;
     c.row_ptr = b->row_ptr; c.col = b->col; c.val = b->val;
@@ -147,6 +147,16 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     c.err = w->A<int>(1);
     c.stats = w->A<unsigned long long>(4);
     w->d_act = w->A<Activation>(max_active);
+    c.use_t = o.scatter_mode == 0;
+    if (c.use_t) {      // transposed per-node blocks, double buffered (children are written to the other buffer)
+      const size_t tn = (size_t)b->nnz + 4096;
+      for (int q = 0; q < 2; ++q) { c.tcol[q] = w->A<int32_t>(tn); c.tpos[q] = w->A<int32_t>(tn); c.tval[q] = w->A<double>(tn); }
+      w->tcap = 32768 + max_active + 64;
+      c.tchunks = w->A<TChunk>(w->tcap); c.n_tchunks = w->A<int>(1);
+      c.tile_cnt = w->A<int>(w->tcap); c.tile_off = w->A<long long>(w->tcap);
+      c.newpos = w->A<int>(m);
+      c.tb_cnt = w->A<int>(b->n_cols + 1); c.tb_colstart = w->A<long long>(b->n_cols + 2);
+    }
     CK(cudaMemset(c.st, 0, sizeof(Slot) * max_active));
     CK(cudaMemset(c.err, 0, sizeof(int)));
     CK(cudaMemset(c.stats, 0, 4 * sizeof(unsigned long long)));
@@ -250,7 +260,7 @@ static tmc_matrix* upload(const tmc_csr* a, int device) {
 }
 
 // ----------------------------------------------------------------------------- the scheduler
-struct HostNode { int begin, end, gsize, parent, left, right, iters; double q, theta; };   // [begin,end) local, gsize global
+struct HostNode { int begin, end, gsize, parent, left, right, iters; double q, theta; long long tb = 0, te = 0; int tpar = 0; };   // [begin,end) local, gsize global
 
 struct Engine {
   tmc_matrix* b; Workspace* w; tmc_opts o; Ctx c; cudaStream_t s;
@@ -296,12 +306,29 @@ struct Engine {
     }
   }
 
+  // column-sorted copy of the rows at positions [begin,end) into buffer `par` at offset 0 (root / per-node API)
+  void build_tblock(HostNode& nd) {
+    if (!c.use_t) return;
+    const int rows = nd.end - nd.begin;
+    const int grid = std::max(1, std::min(148 * 8, (rows + 7) / 8));
+    CK(cudaMemsetAsync(c.tb_cnt, 0, sizeof(int) * (b->n_cols + 1), s));
+    k_tb_count<<<grid, 256, 0, s>>>(c, nd.begin, nd.end);
+    k_tb_scan<<<1, 1024, 0, s>>>(c);
+    k_tb_fill<<<grid, 256, 0, s>>>(c, nd.begin, nd.end, 0, 0);
+    n_launch += 3;
+    long long tot = 0;
+    CK(cudaMemcpyAsync(&tot, c.tb_colstart + b->n_cols, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    nd.tb = 0; nd.te = tot; nd.tpar = 0;
+  }
+
   int activate_pending(int stop_after) {
     int n = 0;
     while (!pending.empty() && !free_slots.empty()) {
       int node = pending.front(); pending.pop_front();
       int slot = free_slots.top(); free_slots.pop();
-      w->h_act[n++] = Activation{slot, nodes[node].begin, nodes[node].end, nodes[node].gsize, node, stop_after};
+      w->h_act[n++] = Activation{slot, nodes[node].begin, nodes[node].end, nodes[node].gsize, node, stop_after, nodes[node].tpar, 0,
+                                 nodes[node].tb, nodes[node].te};
       hstate[slot] = ST_DEG; slot_node[slot] = node;
       hi_slot = std::max(hi_slot, slot + 1);
     }
@@ -371,12 +398,31 @@ struct Engine {
       nvch += (ll + RV - 1) / RV;
     }
     const int ny = std::max(1, (int)std::min<int64_t>(64, c.ystride / 8192));
+    // chunks of the transposed blocks
+    int ntch = 0;
+    if (c.use_t) {
+      long long tot = 0;
+      for (int sl = 0; sl < hi_slot; ++sl) {
+        int st = hstate[sl];
+        if (st == ST_DEG || st == ST_LAN || st == ST_MOD) tot += nodes[slot_node[sl]].te - nodes[slot_node[sl]].tb;
+      }
+      const long long TC = 2048ll * std::max<long long>(1, (tot + 2048ll * 32768 - 1) / (2048ll * 32768));
+      c.tchunk = (int)TC;
+      for (int sl = 0; sl < hi_slot; ++sl) {
+        int st = hstate[sl];
+        if (st != ST_DEG && st != ST_LAN && st != ST_MOD) continue;
+        const HostNode& nd = nodes[slot_node[sl]];
+        ntch += (int)((nd.te - (nd.tb & ~7ll) + TC - 1) / TC);
+      }
+      if (ntch > w->tcap) throw TmcError(TMC_ERR_CUDA, "internal: transposed chunk list overflow");
+    }
     k_prepare<<<1, 1024, 0, s>>>(c); n_launch++;
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     if (n_sc) {
       k_zero_y<<<dim3(hi_slot, ny), 256, 0, s>>>(c); n_launch++;
       if (profile) e0 = ev();
-      if (nch) { k_scatter<<<nch, 256, 0, s>>>(c); n_launch++; }
+      if (c.use_t) { if (ntch) { k_tgather<<<ntch, 256, 0, s>>>(c); n_launch++; } }
+      else if (nch) { k_scatter<<<nch, 256, 0, s>>>(c); n_launch++; }
       if (profile) e1 = ev();
       allreduce_f64(c.Y, (size_t)c.ystride * hi_slot);
     }
@@ -397,7 +443,13 @@ struct Engine {
     k_finish<<<(hi_slot * 32 + 255) / 256, 256, 0, s>>>(c); n_launch++;
     if (nvch) { k_advance<<<nvch, 256, 0, s>>>(c); n_launch++; }
     allreduce_f64(c.red2, 2 * (size_t)hi_slot);
-    if (n_mod) { k_partition<<<hi_slot, 1024, 0, s>>>(c); n_launch++; }      // local: every rank splits its own cells
+    if (n_mod) {                                                             // local: every rank splits its own cells
+      k_partition<<<hi_slot, 1024, 0, s>>>(c); n_launch++;
+      if (c.use_t && ntch) {       // ... and the transposed blocks of the splitting nodes (stable, into the other buffer)
+        k_tpart_count<<<ntch, 256, 0, s>>>(c); k_tpart_scan<<<hi_slot, 1024, 0, s>>>(c); k_tpart_scatter<<<ntch, 256, 0, s>>>(c);
+        n_launch += 3;
+      }
+    }
     k_commit<<<(hi_slot + 127) / 128, 128, 0, s>>>(c, hi_slot); n_launch++;
     CK(cudaMemcpyAsync(w->h_rep, c.rep, sizeof(Report) * hi_slot, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(w->h_err, c.err, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -421,8 +473,9 @@ struct Engine {
         const int b0 = nd.begin, e0 = nd.end, gs = nd.gsize, n0l = r.n0_local, n0g = r.n0;
         int li = (int)nodes.size(), ri = li + 1;
         nodes[node].left = li; nodes[node].right = ri;
-        nodes.push_back(HostNode{b0, b0 + n0l, n0g, node, -1, -1, 0, 0.0, 0.0});
-        nodes.push_back(HostNode{b0 + n0l, e0, gs - n0g, node, -1, -1, 0, 0.0, 0.0});
+        const long long ptb = nd.tb, pte = nd.te, t0 = r.tnnz0; const int cpar = nd.tpar ^ 1;
+        nodes.push_back(HostNode{b0, b0 + n0l, n0g, node, -1, -1, 0, 0.0, 0.0, ptb, ptb + t0, cpar});
+        nodes.push_back(HostNode{b0 + n0l, e0, gs - n0g, node, -1, -1, 0, 0.0, 0.0, ptb + t0, pte, cpar});
         if (n0g >= 2) pending.push_back(li);
         if (gs - n0g >= 2) pending.push_back(ri);
       }
@@ -438,7 +491,7 @@ struct Engine {
     const int m = (int)b->n_rows;
     nodes.clear(); pending.clear();
     nodes.push_back(HostNode{0, m, (int)b->n_rows_global, -1, -1, -1, 0, 0.0, 0.0});
-    if (b->n_rows_global >= 2) pending.push_back(0);
+    if (b->n_rows_global >= 2) { build_tblock(nodes[0]); pending.push_back(0); }
     for (;;) {
       activate_pending(0);
       if (!live()) break;
@@ -451,6 +504,7 @@ struct Engine {
   void run_single(int n, int stop_after) {
     nodes.clear(); pending.clear();
     nodes.push_back(HostNode{0, n, n, -1, -1, -1, 0, 0.0, 0.0});
+    build_tblock(nodes[0]);
     pending.push_back(0);
     activate_pending(stop_after);
     const int64_t cap = (int64_t)(w->K + 8) * (c.max_restarts + 2) + 16;     // Lanczos always terminates within this
@@ -707,7 +761,7 @@ int tmc_modularity(tmc_matrix* b, const int64_t* rows, int64_t n_sel, const uint
     try {
       CK(cudaMemcpyAsync(dl, labels, n, cudaMemcpyHostToDevice, eng.s));
       // re-open slot 0 directly in the modularity state with the caller's labels
-      eng.nodes.clear(); eng.nodes.push_back(HostNode{0, (int)n, (int)n, -1, -1, -1, 0, 0.0, 0.0});
+      { HostNode keep = eng.nodes[0]; keep.left = keep.right = -1; eng.nodes.clear(); eng.nodes.push_back(keep); }   // keeps the T-block
       eng.hstate[0] = ST_MOD; eng.slot_node[0] = 0; eng.hi_slot = 1;
       eng.take_slot0();
       k_force_state<<<1, 1, 0, eng.s>>>(eng.c, 0, ST_MOD, 0, ST_DONE);
@@ -748,7 +802,7 @@ int tmc_partition(const int64_t* rows, int64_t n_sel, const uint8_t* labels, int
 static void setup_pair(Engine& eng, const int64_t* rows, int64_t n, const double* x_dev) {
   eng.init_perm(rows, n);
   eng.run_single((int)n, ST_ORTH0);
-  eng.nodes.clear(); eng.nodes.push_back(HostNode{0, (int)n, (int)n, -1, -1, -1, 0, 0.0, 0.0});
+  { HostNode keep = eng.nodes[0]; keep.left = keep.right = -1; eng.nodes.clear(); eng.nodes.push_back(keep); }   // keeps the T-block
   eng.hstate[0] = ST_LAN; eng.slot_node[0] = 0; eng.hi_slot = 1;
   eng.take_slot0();
   k_force_state<<<1, 1, 0, eng.s>>>(eng.c, 0, ST_LAN, 1, 0);

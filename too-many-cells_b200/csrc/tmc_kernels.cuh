@@ -30,18 +30,23 @@ struct Slot {              // one live tree node (device resident)
   int node;                // host node id
   int split, n0;
   int stop_after;          // 0 = full lifecycle, else stop when reaching this state (fine-grained API)
-  int pad;
+  int tpar;                // which of the two transposed buffers holds this node's column-sorted block
+  long long tb, te;        // the block: entries [tb, te) of tcol/tpos/tval[tpar], sorted by column
+  long long tnnz0;         // entries of label-0 cells (set by k_tpart_scan): children blocks are [tb, tb+tnnz0) and [tb+tnnz0, te)
+  int tchunk0, ntchunk;    // this sweep's chunks of the block (set by k_prepare)
   double sumd, inv_sqrt_sumd, beta, theta, resid, q, theta_hint;
 };
 
 struct Report {            // what the host reads back after every sweep
   int state, split, n0, iters;   // n0 = global label-0 count
   int n0_local, pad;
+  long long tnnz0;
   double q, theta;
 };
 
 struct Chunk { int slot, begin, len; };
-struct Activation { int slot, begin, end, gsize, node, stop_after; };
+struct TChunk { long long begin; int slot, pad; };        // entries [begin, begin + tchunk) of the slot's transposed block
+struct Activation { int slot, begin, end, gsize, node, stop_after, tpar, pad; long long tb, te; };
 
 struct Ctx {
   // matrix B (CSR, rows = cells)
@@ -63,6 +68,13 @@ struct Ctx {
   int K;
   Chunk* chunks; int* n_chunks; int chunk_rows;      // SpMV kernels: few rows per CTA (memory-level parallelism)
   Chunk* vchunks; int* n_vchunks; int vchunk_rows;   // vector kernels (dots/update/advance): up to 256 positions per CTA
+  // transposed (column-sorted) per-node copy of B: y = B_S^T x as a gather with run merging instead of nnz atomics
+  int use_t;
+  int32_t* tcol[2]; int32_t* tpos[2]; double* tval[2];
+  TChunk* tchunks; int* n_tchunks; int tchunk;       // entries per chunk (multiple of 2048)
+  int* tile_cnt; long long* tile_off;                // per chunk: label-1 entries / exclusive prefix inside the node
+  int* newpos;                                       // [m] where k_partition moved every position
+  int* tb_cnt; long long* tb_colstart;               // [n_cols(+1)] scratch for building a block from CSR rows
   int* err;                        // device error flag
   unsigned long long* stats;       // [0] nnz gathered in Lanczos pairs, [1] nnz gathered in degree pairs
   // options
@@ -156,7 +168,8 @@ __global__ void k_activate(Ctx c, const Activation* __restrict__ acts, int n) {
   Slot s;
   s.begin = a.begin; s.end = a.end; s.gsize = a.gsize; s.n0_local = 0;
   s.state = ST_DEG; s.action = ACT_NONE; s.j = 0; s.iters = 0; s.restarts = 0; s.node = a.node;
-  s.split = 0; s.n0 = 0; s.stop_after = a.stop_after; s.pad = 0;
+  s.split = 0; s.n0 = 0; s.stop_after = a.stop_after;
+  s.tpar = a.tpar; s.tb = a.tb; s.te = a.te; s.tnnz0 = 0; s.tchunk0 = 0; s.ntchunk = 0;
   s.sumd = 0; s.inv_sqrt_sumd = 0; s.beta = 0; s.theta = 0; s.resid = 0; s.q = 0; s.theta_hint = -1e300;
   c.st[a.slot] = s;
 }
@@ -208,12 +221,61 @@ __device__ void build_chunk_list(const Ctx& c, int csize, Chunk* out, int* out_n
   __syncthreads();
 }
 
+// chunk list over the transposed blocks of the slots that form y = B_S^T x this sweep (DEG, LAN, MOD)
+__device__ void build_tchunk_list(Ctx& c, int* offs, int* wsum) {
+  const int tid = threadIdx.x;
+  const int per = (c.n_slots + 1023) / 1024;
+  int cnt[4]; int mine = 0;
+  for (int q = 0; q < per; ++q) {
+    int slot = tid * per + q; int n = 0;
+    if (slot < c.n_slots) {
+      const Slot& s = c.st[slot];
+      if (s.state == ST_DEG || s.state == ST_LAN || s.state == ST_MOD) {
+        long long a0 = s.tb & ~7ll;
+        n = (int)((s.te - a0 + c.tchunk - 1) / c.tchunk);
+      }
+    }
+    cnt[q] = n; mine += n;
+  }
+  int lane = tid & 31, wid = tid >> 5;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int v = wsum[lane]; int iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+    wsum[lane] = iv - v;
+  }
+  __syncthreads();
+  int base = wsum[wid] + incl - mine;
+  for (int q = 0; q < per; ++q) {
+    int slot = tid * per + q;
+    if (slot < c.n_slots) { offs[slot] = base; c.st[slot].tchunk0 = base; c.st[slot].ntchunk = cnt[q]; }
+    base += cnt[q];
+  }
+  if (tid == 1023) { offs[c.n_slots] = base; *c.n_tchunks = base; }
+  __syncthreads();
+  const int total = offs[c.n_slots];
+  for (int ci = tid; ci < total; ci += 1024) {
+    int lo = 0, hi = c.n_slots;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (offs[mid] <= ci) lo = mid; else hi = mid; }
+    const Slot& s = c.st[lo];
+    TChunk ch; ch.slot = lo; ch.pad = 0; ch.begin = (s.tb & ~7ll) + (long long)(ci - offs[lo]) * c.tchunk;
+    c.tchunks[ci] = ch;
+  }
+  __syncthreads();
+}
+
 // zero the reduction rows of live slots and build the chunk lists (single CTA, 1024 threads)
 __global__ void __launch_bounds__(1024) k_prepare(Ctx c) {
   __shared__ int offs[4097];
   __shared__ int wsum[32];
   build_chunk_list(c, c.chunk_rows, c.chunks, c.n_chunks, offs, wsum);
   build_chunk_list(c, c.vchunk_rows, c.vchunks, c.n_vchunks, offs, wsum);
+  if (c.use_t) build_tchunk_list(c, offs, wsum);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // zero reduction rows (dots of both passes up to j+1, and the scalars): one warp per slot
   for (int slot = wid; slot < c.n_slots; slot += 32) {
@@ -259,6 +321,234 @@ __global__ void __launch_bounds__(256) k_scatter(Ctx c) {
       atomicAdd(y + c0, v0 * xi); atomicAdd(y + c1, v1 * xi); atomicAdd(y + c2, v2 * xi); atomicAdd(y + c3, v3 * xi);
     }
     for (; k < re; k += 32) atomicAdd(y + __ldg(c.col + k), __ldg(c.val + k) * xi);
+  }
+}
+
+// ------------------------------------------------------------------ K4 half 1, transposed form: y_S = B_S^T (xin) as a GATHER
+// The node's entries are kept a second time sorted by column ("T-block": tcol, tpos = cell position, tval).
+// Each lane takes 8 consecutive entries (two 128-bit loads per array), multiplies by xin[pos] and merges equal
+// columns locally; a warp whose 256 entries are one column reduces with shuffles.  Only run totals touch y, so
+// the 175 M RED.F64 of the CSR scatter (measured: atomic-throughput bound at 1.6 TB/s) become a few per column.
+__device__ __forceinline__ int4 ldg_i4(const int32_t* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
+__device__ __forceinline__ double2 ldg_d2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+
+__global__ void __launch_bounds__(256) k_tgather(Ctx c) {
+  if ((int)blockIdx.x >= *c.n_tchunks) return;
+  const TChunk ch = c.tchunks[blockIdx.x];
+  const Slot& s = c.st[ch.slot];
+  const int state = s.state;
+  if (state != ST_DEG && state != ST_LAN && state != ST_MOD) return;
+  const long long tb = s.tb, te = s.te;
+  const int par = s.tpar;
+  const int32_t* __restrict__ tcol = par ? c.tcol[1] : c.tcol[0];
+  const int32_t* __restrict__ tpos = par ? c.tpos[1] : c.tpos[0];
+  const double* __restrict__ tval = par ? c.tval[1] : c.tval[0];
+  const double* __restrict__ xin = c.xin;
+  double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long cend = min(ch.begin + (long long)c.tchunk, te);
+  for (long long base = ch.begin + warp * 256; base < cend; base += 8 * 256) {
+    const long long k0 = base + lane * 8;
+    int cc[8]; double t[8];
+    if (k0 < te && k0 + 8 > tb) {
+      const int4 ca = ldg_i4(tcol + k0), cb = ldg_i4(tcol + k0 + 4);
+      const double2 v0 = ldg_d2(tval + k0), v1 = ldg_d2(tval + k0 + 2), v2 = ldg_d2(tval + k0 + 4), v3 = ldg_d2(tval + k0 + 6);
+      cc[0] = ca.x; cc[1] = ca.y; cc[2] = ca.z; cc[3] = ca.w; cc[4] = cb.x; cc[5] = cb.y; cc[6] = cb.z; cc[7] = cb.w;
+      t[0] = v0.x; t[1] = v0.y; t[2] = v1.x; t[3] = v1.y; t[4] = v2.x; t[5] = v2.y; t[6] = v3.x; t[7] = v3.y;
+      if (state != ST_DEG) {
+        const int4 pa = ldg_i4(tpos + k0), pb = ldg_i4(tpos + k0 + 4);
+        const int pp[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const bool ok = (k0 + e >= tb) && (k0 + e < te);
+          t[e] = ok ? t[e] * __ldg(xin + pp[e]) : 0.0;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) if (!((k0 + e >= tb) && (k0 + e < te))) { cc[e] = -1; t[e] = 0.0; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { cc[e] = -1; t[e] = 0.0; }
+    }
+    // whole warp inside one column?
+    const int cfirst = __shfl_sync(0xffffffffu, cc[0], 0);
+    const int clast = __shfl_sync(0xffffffffu, cc[7], 31);
+    if (cfirst == clast && cfirst >= 0) {
+      double a = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+      a = warp_sum(a);
+      if (lane == 0 && a != 0.0) atomicAdd(y + cfirst, a);
+      continue;
+    }
+    double acc = t[0]; int cur = cc[0];
+#pragma unroll
+    for (int e = 1; e < 8; ++e) {
+      if (cc[e] == cur) acc += t[e];
+      else { if (cur >= 0 && acc != 0.0) atomicAdd(y + cur, acc); cur = cc[e]; acc = t[e]; }
+    }
+    if (cur >= 0 && acc != 0.0) atomicAdd(y + cur, acc);
+  }
+}
+
+// ---- building a node's T-block from its CSR rows (root, and the per-node API entry points)
+__global__ void __launch_bounds__(256) k_tb_count(Ctx c, int begin, int end) {
+  const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int nw = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+  for (int p = begin + warp; p < end; p += nw) {
+    const int row = c.perm[p];
+    const int64_t rs = c.row_ptr[row], re = c.row_ptr[row + 1];
+    for (int64_t k = rs + lane; k < re; k += 32) atomicAdd(c.tb_cnt + __ldg(c.col + k), 1);
+  }
+}
+__global__ void __launch_bounds__(1024) k_tb_scan(Ctx c) {      // exclusive scan of tb_cnt -> tb_colstart; tb_cnt := 0 (cursor)
+  __shared__ long long wsum[32];
+  __shared__ long long carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < c.n_cols; base += 1024) {
+    const int j = base + tid;
+    long long v = (j < c.n_cols) ? (long long)c.tb_cnt[j] : 0, incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      long long w = wsum[lane], iw = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, iw, o); if (lane >= o) iw += t; }
+      wsum[lane] = iw - w;
+    }
+    __syncthreads();
+    const long long carry = carry_s;
+    if (j < c.n_cols) { c.tb_colstart[j] = carry + wsum[wid] + incl - v; c.tb_cnt[j] = 0; }
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + wsum[31] + incl;
+    __syncthreads();
+  }
+  if (tid == 0) c.tb_colstart[c.n_cols] = carry_s;
+}
+__global__ void __launch_bounds__(256) k_tb_fill(Ctx c, int begin, int end, long long tb, int par) {
+  const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int nw = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+  for (int p = begin + warp; p < end; p += nw) {
+    const int row = c.perm[p];
+    const int64_t rs = c.row_ptr[row], re = c.row_ptr[row + 1];
+    for (int64_t k = rs + lane; k < re; k += 32) {
+      const int col = __ldg(c.col + k);
+      const long long idx = tb + c.tb_colstart[col] + atomicAdd(c.tb_cnt + col, 1);
+      (par ? c.tcol[1] : c.tcol[0])[idx] = col; (par ? c.tpos[1] : c.tpos[0])[idx] = p; (par ? c.tval[1] : c.tval[0])[idx] = __ldg(c.val + k);
+    }
+  }
+}
+
+// ---- splitting a T-block: stable partition of the parent's entries by the label of their cell into the other buffer
+__device__ __forceinline__ bool slot_splits(const Slot& s) { return s.state == ST_MOD && s.action == ACT_FINISH && s.split; }
+
+__global__ void __launch_bounds__(256) k_tpart_count(Ctx c) {
+  __shared__ int sm[8];
+  if ((int)blockIdx.x >= *c.n_tchunks) return;
+  const TChunk ch = c.tchunks[blockIdx.x];
+  const Slot& s = c.st[ch.slot];
+  if (!slot_splits(s)) return;
+  const long long lo = max(ch.begin, s.tb), hi = min(ch.begin + (long long)c.tchunk, s.te);
+  const int32_t* __restrict__ tpos = s.tpar ? c.tpos[1] : c.tpos[0];
+  int ones = 0;
+  for (long long k = lo + threadIdx.x; k < hi; k += 256) ones += c.label[__ldg(tpos + k)];
+  ones = __reduce_add_sync(0xffffffffu, ones);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = ones;
+  __syncthreads();
+  if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < 8; ++q) t += sm[q]; c.tile_cnt[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) k_tpart_scan(Ctx c) {      // one CTA per slot: prefix of its chunks' label-1 counts
+  __shared__ long long wsum[32];
+  __shared__ long long carry_s;
+  Slot& s = c.st[blockIdx.x];
+  if (!slot_splits(s)) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int c0 = s.tchunk0, nc = s.ntchunk;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nc; base += 1024) {
+    const int i = base + tid;
+    long long v = (i < nc) ? (long long)c.tile_cnt[c0 + i] : 0, incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      long long w = wsum[lane], iw = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, iw, o); if (lane >= o) iw += t; }
+      wsum[lane] = iw - w;
+    }
+    __syncthreads();
+    const long long carry = carry_s;
+    if (i < nc) c.tile_off[c0 + i] = carry + wsum[wid] + incl - v;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + wsum[31] + incl;
+    __syncthreads();
+  }
+  if (tid == 0) s.tnnz0 = (s.te - s.tb) - carry_s;
+}
+__global__ void __launch_bounds__(256) k_tpart_scatter(Ctx c) {
+  __shared__ int wcnt[8];
+  __shared__ long long run_s;
+  if ((int)blockIdx.x >= *c.n_tchunks) return;
+  const TChunk ch = c.tchunks[blockIdx.x];
+  const Slot& s = c.st[ch.slot];
+  if (!slot_splits(s)) return;
+  const long long tb = s.tb, te = s.te, nnz0 = s.tnnz0;
+  const int par = s.tpar;
+  const int32_t* __restrict__ scol = par ? c.tcol[1] : c.tcol[0]; const int32_t* __restrict__ spos = par ? c.tpos[1] : c.tpos[0];
+  const double* __restrict__ sval = par ? c.tval[1] : c.tval[0];
+  int32_t* __restrict__ dcol = par ? c.tcol[0] : c.tcol[1]; int32_t* __restrict__ dpos = par ? c.tpos[0] : c.tpos[1];
+  double* __restrict__ dval = par ? c.tval[0] : c.tval[1];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) run_s = c.tile_off[blockIdx.x];
+  __syncthreads();
+  const long long cend = min(ch.begin + (long long)c.tchunk, te);
+  for (long long base = ch.begin; base < cend; base += 2048) {
+    const long long k0 = base + tid * 8;
+    int cc[8], pp[8], ff[8]; double vv[8];
+    int mine = 0;
+    if (k0 < te && k0 + 8 > tb) {
+      const int4 ca = ldg_i4(scol + k0), cb = ldg_i4(scol + k0 + 4), pa = ldg_i4(spos + k0), pb = ldg_i4(spos + k0 + 4);
+      const double2 v0 = ldg_d2(sval + k0), v1 = ldg_d2(sval + k0 + 2), v2 = ldg_d2(sval + k0 + 4), v3 = ldg_d2(sval + k0 + 6);
+      cc[0] = ca.x; cc[1] = ca.y; cc[2] = ca.z; cc[3] = ca.w; cc[4] = cb.x; cc[5] = cb.y; cc[6] = cb.z; cc[7] = cb.w;
+      pp[0] = pa.x; pp[1] = pa.y; pp[2] = pa.z; pp[3] = pa.w; pp[4] = pb.x; pp[5] = pb.y; pp[6] = pb.z; pp[7] = pb.w;
+      vv[0] = v0.x; vv[1] = v0.y; vv[2] = v1.x; vv[3] = v1.y; vv[4] = v2.x; vv[5] = v2.y; vv[6] = v3.x; vv[7] = v3.y;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const bool ok = (k0 + e >= tb) && (k0 + e < te);
+        ff[e] = ok ? (int)c.label[pp[e]] : -1;
+        mine += (ff[e] == 1);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ff[e] = -1;
+    }
+    // block exclusive scan of `mine`
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wcnt[wid] = incl;
+    __syncthreads();
+    int wbase = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const int w = wcnt[q]; if (q < wid) wbase += w; tot += w; }
+    const long long run = run_s;
+    long long ones_before = run + wbase + incl - mine;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (ff[e] < 0) continue;
+      const long long idx = (k0 + e) - tb;                         // index inside the parent block
+      const long long dest = ff[e] ? (tb + nnz0 + ones_before) : (tb + (idx - ones_before));
+      dcol[dest] = cc[e]; dpos[dest] = c.newpos[pp[e]]; dval[dest] = vv[e];
+      ones_before += ff[e];
+    }
+    __syncthreads();
+    if (tid == 0) run_s = run + tot;
+    __syncthreads();
   }
 }
 
@@ -584,6 +874,7 @@ __global__ void __launch_bounds__(1024) k_partition(Ctx c) {
       int idx = p - begin;
       int dest = f ? (begin + n0 + ones_before) : (begin + (idx - ones_before));
       c.perm_tmp[dest] = c.perm[p];
+      if (c.newpos) c.newpos[p] = dest;
     }
     __syncthreads();
     if (tid == 0) { int t = 0; for (int q = 0; q < 32; ++q) t += wtot[q]; run1_s = run1 + t; }
@@ -609,7 +900,7 @@ __global__ void k_commit(Ctx c, int n_slots) {
   if (s->stop_after != 0 && state == s->stop_after && state != s->state) state = ST_DONE;   // fine-grained API stop
   s->action = ACT_NONE;
   s->state = state;
-  Report r; r.state = state; r.split = s->split; r.n0 = s->n0; r.iters = s->iters; r.n0_local = s->n0_local; r.pad = 0;
+  Report r; r.state = state; r.split = s->split; r.n0 = s->n0; r.iters = s->iters; r.n0_local = s->n0_local; r.pad = 0; r.tnnz0 = s->tnnz0;
   r.q = s->q; r.theta = s->theta;
   c.rep[slot] = r;
 }

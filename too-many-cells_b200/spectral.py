@@ -53,7 +53,7 @@ class HostCsr:
 
 def make_opts(min_modularity=0.0, min_size=1, normalize=False, eigen_group="SignGroup", num_eigen=1,
               num_runs=0, seed=None, tol=None, max_lanczos=None, max_restarts=None, max_active=None,
-              device=-1, profile=False) -> Opts:
+              device=-1, profile=False, scatter_mode=0) -> Opts:
     lib = _lib.load()
     o = Opts()
     lib.tmc_opts_default(C.byref(o))
@@ -75,6 +75,7 @@ def make_opts(min_modularity=0.0, min_size=1, normalize=False, eigen_group="Sign
         o.max_active = int(max_active)
     o.device = int(device)
     o.profile = int(bool(profile))
+    o.scatter_mode = int(scatter_mode)
     return o
 
 
