@@ -121,6 +121,8 @@ int  tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int
                           const int32_t* col_dev, double* val_dev, int64_t row_offset, int64_t n_rows_global,
                           int normalize, int device, tmc_matrix** out);
 void tmc_matrix_free(tmc_matrix*);
+/* tmc_matrix_free keeps one retired workspace (device arenas, pinned buffers) for the next matrix; this releases it. */
+void tmc_cache_clear(void);
 
 /* == hierarchicalSpectralCluster ... (Left mat)  (Cluster.hs:147-156): the whole tree. */
 int  tmc_make_tree(const tmc_csr* b2, const tmc_opts* opts, tmc_tree** out);

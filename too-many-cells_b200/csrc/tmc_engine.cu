@@ -11,13 +11,17 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
+#include <stdlib.h>
 #include <deque>
 #include <functional>
+#include <mutex>
 #include <queue>
 #include <string>
 #include <vector>
 
 #include "../../include/tmc.h"
+#include <cub/device/device_radix_sort.cuh>
 #include "tmc_kernels.cuh"
 
 using namespace tmc;
@@ -86,15 +90,17 @@ template <class T> static T* dalloc(size_t n) {
 
 struct Workspace {
   Ctx c{};
-  int K = 0, max_active = 0, use_t = 0, tcap = 0;
-  int64_t m = 0;
+  int K = 0, max_active = 0, use_t = 0, tcap = 0, device = 0;
+  int64_t m = 0, cap_m = 0, cap_nnz = 0, cap_cols = 0;
   Report* h_rep = nullptr; Activation* h_act = nullptr; Activation* d_act = nullptr;
   int* h_err = nullptr; unsigned long long* h_stats = nullptr;
   cudaStream_t stream = nullptr;
+  void* cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
   std::vector<void*> allocs;
   template <class T> T* A(size_t n) { T* p = dalloc<T>(n); allocs.push_back(p); return p; }
   ~Workspace() {
     for (void* p : allocs) cudaFree(p);
+    if (cub_tmp) cudaFree(cub_tmp);
     if (h_rep) cudaFreeHost(h_rep);
     if (h_act) cudaFreeHost(h_act);
     if (h_err) cudaFreeHost(h_err);
@@ -112,26 +118,51 @@ static int pick_device(int device) {
   return device;
 }
 
+// One retired workspace is kept for re-use: cudaMalloc / cudaFree of the multi-GB arenas costs far more than a
+// whole tree build on c2 (measured: ~280 ms of a 560 ms step), and a host that clusters matrix after matrix
+// (or bench.py's steps) should not pay it every call.  tmc_cache_clear() releases it.
+static std::mutex g_cache_mu;
+static Workspace* g_ws_cache = nullptr;
+
+static void bind_workspace(Workspace* w, tmc_matrix* b) {
+  Ctx& c = w->c;
+  c.row_ptr = b->row_ptr; c.col = b->col; c.val = b->val;
+  c.n_rows = (int)b->n_rows; c.n_cols = (int)b->n_cols; c.row_offset = b->row_offset;
+  c.vstride = (b->n_rows + 15) / 16 * 16;
+  c.ystride = (b->n_cols + 15) / 16 * 16;
+  w->m = b->n_rows;
+}
+
 static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
   const int64_t m = b->n_rows;
   int K = std::max(2, (int)std::min<int64_t>(o.max_lanczos > 0 ? o.max_lanczos : 320, b->n_rows_global));
   int max_active = (int)std::min<int64_t>(std::max<int64_t>(1, b->n_rows_global / 2), o.max_active > 0 ? o.max_active : 2048);
   max_active = std::min(max_active, 4096);
-  if (b->ws && b->ws->K == K && b->ws->max_active == max_active && b->ws->use_t == (o.scatter_mode == 0)) return b->ws;
+  const int use_t = (o.scatter_mode == 0);
+  if (b->ws && b->ws->K == K && b->ws->max_active == max_active && b->ws->use_t == use_t) return b->ws;
   delete b->ws; b->ws = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    Workspace* q = g_ws_cache;
+    if (q && q->device == b->device && q->K == K && q->max_active == max_active && q->use_t == use_t && q->cap_m >= m &&
+        q->cap_nnz >= b->nnz && q->cap_cols >= b->n_cols) {
+      g_ws_cache = nullptr;
+      bind_workspace(q, b);
+      b->ws = q;
+      return q;
+    }
+  }
   Workspace* w = new Workspace();
   try {
-    w->K = K; w->max_active = max_active; w->m = m; w->use_t = (o.scatter_mode == 0);
+    w->K = K; w->max_active = max_active; w->use_t = use_t; w->device = b->device;
+    w->cap_m = m; w->cap_nnz = b->nnz; w->cap_cols = b->n_cols;
     CK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     Ctx& c = w->c;
-    c.row_ptr = b->row_ptr; c.col = b->col; c.val = b->val;
-    c.n_rows = (int)m; c.n_cols = (int)b->n_cols; c.row_offset = b->row_offset;
+    bind_workspace(w, b);
     c.perm = w->A<int>(m); c.perm_tmp = w->A<int>(m);
     c.d = w->A<double>(m); c.sdeg = w->A<double>(m); c.xin = w->A<double>(m); c.w = w->A<double>(m); c.u2 = w->A<double>(m);
     c.label = w->A<uint8_t>(m);
-    c.vstride = (m + 15) / 16 * 16;
     c.V = w->A<double>((size_t)c.vstride * (K + 2));
-    c.ystride = (b->n_cols + 15) / 16 * 16;
     c.Y = w->A<double>((size_t)c.ystride * max_active);
     c.st = w->A<Slot>(max_active); c.rep = w->A<Report>(max_active); c.max_active = max_active;
     c.redA = w->A<double>((size_t)(K + 2) * max_active); c.redB = w->A<double>((size_t)(K + 2) * max_active);
@@ -147,7 +178,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     c.err = w->A<int>(1);
     c.stats = w->A<unsigned long long>(4);
     w->d_act = w->A<Activation>(max_active);
-    c.use_t = o.scatter_mode == 0;
+    c.use_t = use_t;
     if (c.use_t) {      // transposed per-node blocks, double buffered (children are written to the other buffer)
       const size_t tn = (size_t)b->nnz + 4096;
       for (int q = 0; q < 2; ++q) { c.tcol[q] = w->A<int32_t>(tn); c.tpos[q] = w->A<int32_t>(tn); c.tval[q] = w->A<double>(tn); }
@@ -157,9 +188,6 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
       c.newpos = w->A<int>(m);
       c.tb_cnt = w->A<int>(b->n_cols + 1); c.tb_colstart = w->A<long long>(b->n_cols + 2);
     }
-    CK(cudaMemset(c.st, 0, sizeof(Slot) * max_active));
-    CK(cudaMemset(c.err, 0, sizeof(int)));
-    CK(cudaMemset(c.stats, 0, 4 * sizeof(unsigned long long)));
     CK(cudaMemset(c.red2, 0, 2 * sizeof(double) * max_active));
     CK(cudaMallocHost(&w->h_rep, sizeof(Report) * max_active));
     CK(cudaMallocHost(&w->h_act, sizeof(Activation) * max_active));
@@ -168,6 +196,13 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
   } catch (...) { delete w; throw; }
   b->ws = w;
   return w;
+}
+
+static void retire_workspace(Workspace* w) {
+  if (!w) return;
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  if (!g_ws_cache || (g_ws_cache->cap_nnz <= w->cap_nnz && g_ws_cache->cap_m <= w->cap_m)) { delete g_ws_cache; g_ws_cache = w; }
+  else delete w;
 }
 
 static int err_to_status(int e, std::string* msg) {
@@ -271,6 +306,7 @@ struct Engine {
   int hi_slot = 0;
   int64_t n_sweeps = 0, n_launch = 0;
   double alg_vec_bytes = 0;     // non-matrix part of the spmv_pair algorithmic bytes
+  double build_ms = 0;
   bool profile = false;
   std::vector<cudaEvent_t> evs;
 
@@ -320,6 +356,41 @@ struct Engine {
     CK(cudaMemcpyAsync(&tot, c.tb_colstart + b->n_cols, sizeof(long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     nd.tb = 0; nd.te = tot; nd.tpar = 0;
+  }
+
+  // Root block when perm is the identity over all local rows: stable radix sort of the CSR entries by column
+  // (cub::DeviceRadixSort, load-time plumbing) so that positions ascend inside every column; the other buffer and
+  // tval[1] serve as scratch.  Falls back to the atomic-cursor build for > 2^31 - 1 entries.
+  void build_tblock_sorted(HostNode& nd) {
+    if (!c.use_t) return;
+    const auto w0 = std::chrono::steady_clock::now();
+    struct T_ { Engine* e; std::chrono::steady_clock::time_point t; ~T_() { e->build_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); } } timer_{this, w0};
+    const long long n = b->nnz;
+    if (n >= (1ll << 31) - 1 || n == 0) { build_tblock(nd); return; }
+    int32_t* keysA = c.tcol[1]; int32_t* keysB = c.tcol[0];
+    int32_t* valsA = c.tpos[1]; int32_t* valsB = c.tpos[0];
+    int32_t* rowid = reinterpret_cast<int32_t*>(c.tval[1]);
+    CK(cudaMemcpyAsync(keysA, b->col, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
+    k_tb_iota<<<148 * 8, 256, 0, s>>>(valsA, n);
+    k_tb_rowid<<<148 * 8, 256, 0, s>>>(b->row_ptr, (int)b->n_rows, rowid);
+    cub::DoubleBuffer<int32_t> dk(keysA, keysB), dv(valsA, valsB);
+    int end_bit = 1; while ((1ll << end_bit) < b->n_cols) ++end_bit;
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)n, 0, end_bit, s));
+    if (tmp_bytes > w->cub_tmp_bytes) {       // grown once, kept with the workspace (cudaMalloc/cudaFree here cost up to 400 ms)
+      if (w->cub_tmp) cudaFree(w->cub_tmp);
+      w->cub_tmp = nullptr; w->cub_tmp_bytes = 0;
+      CK(cudaMalloc(&w->cub_tmp, tmp_bytes + (tmp_bytes >> 2) + 1024));
+      w->cub_tmp_bytes = tmp_bytes + (tmp_bytes >> 2) + 1024;
+    }
+    size_t avail = w->cub_tmp_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, avail, dk, dv, (int)n, 0, end_bit, s));
+    if (dk.Current() != keysB) CK(cudaMemcpyAsync(keysB, dk.Current(), sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
+    if (dv.Current() != valsB) CK(cudaMemcpyAsync(valsB, dv.Current(), sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
+    k_tb_finish_sorted<<<148 * 8, 256, 0, s>>>(rowid, b->val, valsB, c.tval[0], n);
+    CK(cudaStreamSynchronize(s));
+    n_launch += 6;
+    nd.tb = 0; nd.te = n; nd.tpar = 0;
   }
 
   int activate_pending(int stop_after) {
@@ -491,7 +562,7 @@ struct Engine {
     const int m = (int)b->n_rows;
     nodes.clear(); pending.clear();
     nodes.push_back(HostNode{0, m, (int)b->n_rows_global, -1, -1, -1, 0, 0.0, 0.0});
-    if (b->n_rows_global >= 2) { build_tblock(nodes[0]); pending.push_back(0); }
+    if (b->n_rows_global >= 2) { build_tblock_sorted(nodes[0]); pending.push_back(0); }      // run_tree starts from the identity perm
     for (;;) {
       activate_pending(0);
       if (!live()) break;
@@ -501,10 +572,10 @@ struct Engine {
   }
 
   // run slot 0 over rows [0,n) until it reports DONE
-  void run_single(int n, int stop_after) {
+  void run_single(int n, int stop_after, bool identity = false) {
     nodes.clear(); pending.clear();
     nodes.push_back(HostNode{0, n, n, -1, -1, -1, 0, 0.0, 0.0});
-    build_tblock(nodes[0]);
+    if (identity && n == (int)b->n_rows) build_tblock_sorted(nodes[0]); else build_tblock(nodes[0]);
     pending.push_back(0);
     activate_pending(stop_after);
     const int64_t cap = (int64_t)(w->K + 8) * (c.max_restarts + 2) + 16;     // Lanczos always terminates within this
@@ -600,9 +671,14 @@ int tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int6
   });
 }
 
+void tmc_cache_clear(void) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  delete g_ws_cache; g_ws_cache = nullptr;
+}
+
 void tmc_matrix_free(tmc_matrix* b) {
   if (!b) return;
-  delete b->ws;
+  retire_workspace(b->ws); b->ws = nullptr;
   if (b->owns) { cudaFree(b->row_ptr); cudaFree(b->col); cudaFree(b->val); }
   delete b;
 }
@@ -622,9 +698,14 @@ int tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out) {
     cudaEvent_t t0, t1;
     CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
     CK(cudaEventRecord(t0, eng.s));
+    const bool dbg = getenv("TMC_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double w0 = now();
     eng.init_perm(nullptr, 0);
     eng.run_tree();
     CK(cudaEventRecord(t1, eng.s));
+    if (dbg) fprintf(stderr, "[tmc] run_tree wall %.2f ms (block build %.2f ms), sweeps %lld, nodes %zu\n", now() - w0, eng.build_ms,
+                     (long long)eng.n_sweeps, eng.nodes.size());
     const int m = (int)b->n_rows;
     const int64_t M = b->n_rows_global;
     const int world = eng.c.world, rank = eng.c.rank;
@@ -801,7 +882,7 @@ int tmc_partition(const int64_t* rows, int64_t n_sel, const uint8_t* labels, int
 // set slot 0 up over rows [0,n) in the Lanczos state with xin = D^{-1/2} x  (degree pass first)
 static void setup_pair(Engine& eng, const int64_t* rows, int64_t n, const double* x_dev) {
   eng.init_perm(rows, n);
-  eng.run_single((int)n, ST_ORTH0);
+  eng.run_single((int)n, ST_ORTH0, rows == nullptr);
   { HostNode keep = eng.nodes[0]; keep.left = keep.right = -1; eng.nodes.clear(); eng.nodes.push_back(keep); }   // keeps the T-block
   eng.hstate[0] = ST_LAN; eng.slot_node[0] = 0; eng.hi_slot = 1;
   eng.take_slot0();

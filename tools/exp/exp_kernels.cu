@@ -178,3 +178,53 @@ void exp_tcoo(int E, const int* ccol, const int* cpos, const double* cval, const
   else { int64_t warps = (nnz + 511) / 512; t_coo<16><<<(unsigned)((warps + 7) / 8), 256>>>(ccol, cpos, cval, x, y, nnz); }
 }
 }
+
+// vectorised version of the transposed gather (what the product's k_tgather does), E = 8 consecutive entries per lane
+__device__ __forceinline__ int4 ldg_i4(const int* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
+__device__ __forceinline__ double2 ldg_d2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+template <int MODE>   // 0: lane-local merge; 1: + no atomics at all (upper bound); 2: no x gather
+__global__ void __launch_bounds__(256) t_coo_v8(const int* __restrict__ tcol, const int* __restrict__ tpos, const double* __restrict__ tval,
+                                                const double* __restrict__ xin, double* __restrict__ y, long long nnz) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long cbeg = (long long)blockIdx.x * 8192, cend = min(cbeg + 8192, nnz);
+  double sink = 0;
+  for (long long base = cbeg + warp * 256; base < cend; base += 2048) {
+    const long long k0 = base + lane * 8;
+    int cc[8]; double t[8];
+    if (k0 + 8 <= nnz) {
+      const int4 ca = ldg_i4(tcol + k0), cb = ldg_i4(tcol + k0 + 4);
+      const double2 v0 = ldg_d2(tval + k0), v1 = ldg_d2(tval + k0 + 2), v2 = ldg_d2(tval + k0 + 4), v3 = ldg_d2(tval + k0 + 6);
+      const int4 pa = ldg_i4(tpos + k0), pb = ldg_i4(tpos + k0 + 4);
+      cc[0] = ca.x; cc[1] = ca.y; cc[2] = ca.z; cc[3] = ca.w; cc[4] = cb.x; cc[5] = cb.y; cc[6] = cb.z; cc[7] = cb.w;
+      const int pp[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+      t[0] = v0.x; t[1] = v0.y; t[2] = v1.x; t[3] = v1.y; t[4] = v2.x; t[5] = v2.y; t[6] = v3.x; t[7] = v3.y;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[e] *= (MODE == 2 ? (double)pp[e] : __ldg(xin + pp[e]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { cc[e] = -1; t[e] = 0.0; }
+    }
+    if (MODE == 1) { for (int e = 0; e < 8; ++e) sink += t[e] * cc[e]; continue; }
+    const int cfirst = __shfl_sync(0xffffffffu, cc[0], 0), clast = __shfl_sync(0xffffffffu, cc[7], 31);
+    if (cfirst == clast && cfirst >= 0) {
+      double a = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+      a = warp_sum(a);
+      if (lane == 0) atomicAdd(y + cfirst, a);
+      continue;
+    }
+    double acc = t[0]; int cur = cc[0];
+#pragma unroll
+    for (int e = 1; e < 8; ++e) {
+      if (cc[e] == cur) acc += t[e];
+      else { if (cur >= 0) atomicAdd(y + cur, acc); cur = cc[e]; acc = t[e]; }
+    }
+    if (cur >= 0) atomicAdd(y + cur, acc);
+  }
+  if (MODE == 1 && sink == 1.2345e-300) y[0] = sink;
+}
+extern "C" void exp_tcoo_v8(int mode, const int* ccol, const int* cpos, const double* cval, const double* x, double* y, long long nnz) {
+  unsigned grid = (unsigned)((nnz + 8191) / 8192);
+  if (mode == 0) t_coo_v8<0><<<grid, 256>>>(ccol, cpos, cval, x, y, nnz);
+  else if (mode == 1) t_coo_v8<1><<<grid, 256>>>(ccol, cpos, cval, x, y, nnz);
+  else t_coo_v8<2><<<grid, 256>>>(ccol, cpos, cval, x, y, nnz);
+}
