@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("TMC_BENCH_WORKLOAD", "c2"))
+    ap.add_argument("--workload", default=os.environ.get("TMC_BENCH_WORKLOAD", "c3"))
     ap.add_argument("--cpu-sample-cells", type=int, default=2500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

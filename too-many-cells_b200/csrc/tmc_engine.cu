@@ -165,9 +165,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     c.V = w->A<double>((size_t)c.vstride * (K + 2));
     c.Y = w->A<double>((size_t)c.ystride * max_active);
     c.st = w->A<Slot>(max_active); c.rep = w->A<Report>(max_active); c.max_active = max_active;
-    c.redA = w->A<double>((size_t)(K + 2) * max_active); c.redB = w->A<double>((size_t)(K + 2) * max_active);
-    c.scal = w->A<double>((size_t)R_NSCAL * max_active);
-    c.red2 = w->A<double>(2 * (size_t)max_active);
+    c.redA = w->A<double>((size_t)(K + 2) * max_active); c.redB = w->A<double>((size_t)(K + 2 + R_NSCAL) * max_active);
     c.alpha = w->A<double>((size_t)(K + 2) * max_active); c.beta = w->A<double>((size_t)(K + 2) * max_active);
     c.zvec = w->A<double>((size_t)(K + 2) * max_active); c.scratch = w->A<double>((size_t)2 * (K + 2) * max_active);
     c.K = K;
@@ -188,7 +186,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
       c.newpos = w->A<int>(m);
       c.tb_cnt = w->A<int>(b->n_cols + 1); c.tb_colstart = w->A<long long>(b->n_cols + 2);
     }
-    CK(cudaMemset(c.red2, 0, 2 * sizeof(double) * max_active));
+    CK(cudaMemset(c.redB, 0, sizeof(double) * (size_t)(K + 2 + R_NSCAL) * max_active));
     CK(cudaMallocHost(&w->h_rep, sizeof(Report) * max_active));
     CK(cudaMallocHost(&w->h_act, sizeof(Activation) * max_active));
     CK(cudaMallocHost(&w->h_err, sizeof(int)));
@@ -502,18 +500,18 @@ struct Engine {
     if (only_spmv) { CK(cudaGetLastError()); return; }
     if (n_mod) { k_ynorm<<<dim3(hi_slot, ny), 256, 0, s>>>(c); n_launch++; }
     const size_t upd_smem = sizeof(double) * ((size_t)c.K + 2 + 8 * (size_t)RV);
-    if (n_or) {      // kernels depend on this rank's rows, collectives only on the (rank-identical) slot states
+    // kernels depend on this rank's rows, collectives only on the (rank-identical) slot states.
+    // Three all-reduces per sweep: Y above, the pass-0 coefficients, and the pass-1 coefficients + every scalar.
+    if (n_or) {
       if (nvch) { k_dots<<<nvch, 256, 0, s>>>(c, 0); n_launch++; }
       allreduce_f64(c.redA, (size_t)(c.K + 2) * hi_slot);
       if (nvch) { k_update<<<nvch, 256, upd_smem, s>>>(c, 0); n_launch++; }
       if (nvch) { k_dots<<<nvch, 256, 0, s>>>(c, 1); n_launch++; }
-      allreduce_f64(c.redB, (size_t)(c.K + 2) * hi_slot);
-      if (nvch) { k_update<<<nvch, 256, upd_smem, s>>>(c, 1); n_launch++; }
     }
-    allreduce_f64(c.scal, (size_t)R_NSCAL * hi_slot);
+    allreduce_f64(c.redB, (size_t)(c.K + 2 + R_NSCAL) * hi_slot);
+    if (n_or && nvch) { k_update<<<nvch, 256, upd_smem, s>>>(c, 1); n_launch++; }
     k_finish<<<(hi_slot * 32 + 255) / 256, 256, 0, s>>>(c); n_launch++;
     if (nvch) { k_advance<<<nvch, 256, 0, s>>>(c); n_launch++; }
-    allreduce_f64(c.red2, 2 * (size_t)hi_slot);
     if (n_mod) {                                                             // local: every rank splits its own cells
       k_partition<<<hi_slot, 1024, 0, s>>>(c); n_launch++;
       if (c.use_t && ntch) {       // ... and the transposed blocks of the splitting nodes (stable, into the other buffer)

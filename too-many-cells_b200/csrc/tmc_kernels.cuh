@@ -18,7 +18,8 @@ enum SlotState : int { ST_IDLE = 0, ST_DEG = 1, ST_ORTH0 = 2, ST_LAN = 3, ST_MOD
 enum SlotAction : int { ACT_NONE = 0, ACT_INIT = 1, ACT_NEXT = 2, ACT_RITZ_LABEL = 3, ACT_RITZ_RESTART = 4, ACT_FINISH = 5 };
 
 // scalar slots at the tail of a reduction row
-enum { R_NRM2 = 0, R_SUMD = 1, R_YNORM2 = 2, R_NSCAL = 4 };
+enum { R_NRM2 = 0, R_SUMD = 1, R_YNORM2 = 2, R_N1 = 3, R_SD1 = 4, R_NSCAL = 8 };
+// The scalars live at the tail of the pass-1 coefficient row so that ONE all-reduce per sweep carries both.
 
 struct Slot {              // one live tree node (device resident)
   int begin, end;          // this rank's position range in its local perm (rows are owned statically per rank)
@@ -60,10 +61,8 @@ struct Ctx {
   double* Y; int64_t ystride;      // per-slot feature vectors y = B_S^T x
   // per-slot state
   Slot* st; Report* rep; int max_active;
-  double* redA; double* redB;      // [slot][K+2]: CGS pass-0 / pass-1 coefficients h_l = <V_l, w>
-  double* scal;                    // [slot][R_NSCAL]
+  double* redA; double* redB;      // CGS pass-0 / pass-1 coefficients h_l = <V_l, w>: redA[slot][K+2], redB[slot][K+2+R_NSCAL]
   int n_slots;                     // slots [0, n_slots) may be live this sweep
-  double* red2;                    // [slot][2] : n1, sum_{c1} d (accumulated by k_advance)
   double* alpha; double* beta; double* zvec; double* scratch;   // [slot][K+2] (scratch: 2*(K+2))
   int K;
   Chunk* chunks; int* n_chunks; int chunk_rows;      // SpMV kernels: few rows per CTA (memory-level parallelism)
@@ -81,6 +80,9 @@ struct Ctx {
   double tol, min_modularity; int min_size, max_restarts; uint64_t seed;
   int rank, world;
 };
+
+__device__ __forceinline__ double* slot_scal(const Ctx& c, int slot) { return c.redB + (int64_t)slot * (c.K + 2 + R_NSCAL) + (c.K + 2); }
+__device__ __forceinline__ double* slot_redB(const Ctx& c, int slot) { return c.redB + (int64_t)slot * (c.K + 2 + R_NSCAL); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -172,6 +174,7 @@ __global__ void k_activate(Ctx c, const Activation* __restrict__ acts, int n) {
   s.tpar = a.tpar; s.tb = a.tb; s.te = a.te; s.tnnz0 = 0; s.tchunk0 = 0; s.ntchunk = 0;
   s.sumd = 0; s.inv_sqrt_sumd = 0; s.beta = 0; s.theta = 0; s.resid = 0; s.q = 0; s.theta_hint = -1e300;
   c.st[a.slot] = s;
+  slot_scal(c, a.slot)[R_N1] = 0.0; slot_scal(c, a.slot)[R_SD1] = 0.0;
 }
 
 // block-wide (1024 threads) construction of a chunk list over the live slots' local position ranges
@@ -282,10 +285,10 @@ __global__ void __launch_bounds__(1024) k_prepare(Ctx c) {
     const Slot& s = c.st[slot];
     if (s.state < ST_DEG || s.state > ST_MOD) continue;
     double* ra = c.redA + (int64_t)slot * (c.K + 2);
-    double* rb = c.redB + (int64_t)slot * (c.K + 2);
+    double* rb = slot_redB(c, slot);
     int nv = min(s.j + 2, c.K + 2);
     for (int i = lane; i < nv; i += 32) { ra[i] = 0.0; rb[i] = 0.0; }
-    if (lane < R_NSCAL) c.scal[slot * R_NSCAL + lane] = 0.0;
+    if (lane < 3) slot_scal(c, slot)[lane] = 0.0;       // NRM2, SUMD, YNORM2 (N1/SD1 persist from the previous sweep)
   }
 }
 
@@ -643,7 +646,7 @@ __global__ void __launch_bounds__(256) k_gather(Ctx c) {
   if (lane == 0 && nz) atomicAdd(c.stats + (state == ST_DEG ? 1 : 0), (unsigned long long)nz);
   if (state == ST_DEG) {
     double t = block_sum_256(dsum, sm8);
-    if (threadIdx.x == 0) atomicAdd(c.scal + ch.slot * R_NSCAL + R_SUMD, t);
+    if (threadIdx.x == 0) atomicAdd(slot_scal(c, ch.slot) + R_SUMD, t);
   }
 }
 
@@ -657,7 +660,7 @@ __global__ void __launch_bounds__(256) k_ynorm(Ctx c) {
   double s = 0.0;
   for (int i = lo + blockIdx.y * blockDim.x + threadIdx.x; i < hi; i += gridDim.y * blockDim.x) { double v = y[i]; s += v * v; }
   double t = block_sum_256(s, sm8);
-  if (threadIdx.x == 0) atomicAdd(c.scal + slot * R_NSCAL + R_YNORM2, t);
+  if (threadIdx.x == 0) atomicAdd(slot_scal(c, slot) + R_YNORM2, t);
 }
 
 // ------------------------------------------------------------------ K5: full re-orthogonalisation (CGS2)
@@ -674,7 +677,7 @@ __global__ void __launch_bounds__(256) k_dots(Ctx c, int pass) {
   for (int i = threadIdx.x; i < ch.len; i += 256) ws[i] = c.w[ch.begin + i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* r = (pass ? c.redB : c.redA) + (int64_t)ch.slot * (c.K + 2);
+  double* r = pass ? slot_redB(c, ch.slot) : c.redA + (int64_t)ch.slot * (c.K + 2);
   for (int l = warp; l <= j; l += 8) {
     const double* __restrict__ v = c.V + (int64_t)l * c.vstride + ch.begin;
     double a = 0.0;
@@ -684,7 +687,7 @@ __global__ void __launch_bounds__(256) k_dots(Ctx c, int pass) {
   }
 }
 
-// w -= sum_l h_l V_l ; after the second pass also accumulates ||w||^2 (= beta_{j+1}^2)
+// w -= sum_l h_l V_l ; the first pass also accumulates ||w||^2 (beta_{j+1}^2 = that minus the pass-1 coefficients squared)
 __global__ void __launch_bounds__(256) k_update(Ctx c, int pass) {
   extern __shared__ double smem[];
   double* hs = smem;                       // K+2
@@ -696,7 +699,7 @@ __global__ void __launch_bounds__(256) k_update(Ctx c, int pass) {
   const int state = s.state;
   if (state != ST_ORTH0 && state != ST_LAN) return;
   const int j = s.j;
-  const double* r = (pass ? c.redB : c.redA) + (int64_t)ch.slot * (c.K + 2);
+  const double* r = pass ? slot_redB(c, ch.slot) : c.redA + (int64_t)ch.slot * (c.K + 2);
   for (int l = threadIdx.x; l <= j; l += 256) hs[l] = r[l];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -715,9 +718,9 @@ __global__ void __launch_bounds__(256) k_update(Ctx c, int pass) {
     c.w[ch.begin + i] = wv;
     nn += wv * wv;
   }
-  if (pass == 1) {
+  if (pass == 0) {      // ||w||^2 after the first pass; the second pass' tiny coefficients are subtracted in k_finish
     double t = block_sum_256(nn, sm8);
-    if (threadIdx.x == 0) atomicAdd(c.scal + ch.slot * R_NSCAL + R_NRM2, t);
+    if (threadIdx.x == 0) atomicAdd(slot_scal(c, ch.slot) + R_NRM2, t);
   }
 }
 
@@ -731,8 +734,8 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
   if (state < ST_DEG || state > ST_MOD) return;
   const int K2 = c.K + 2;
   const double* redA = c.redA + (int64_t)slot * K2;
-  const double* redB = c.redB + (int64_t)slot * K2;
-  const double* scal = c.scal + slot * R_NSCAL;
+  const double* redB = slot_redB(c, slot);
+  double* scal = slot_scal(c, slot);
   if (state == ST_DEG) {
     if (lane == 0) {
       double sumd = scal[R_SUMD];
@@ -745,7 +748,7 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
   }
   if (state == ST_ORTH0) {
     if (lane == 0) {
-      double b = sqrt(fmax(scal[R_NRM2], 0.0));
+      double b = sqrt(fmax(scal[R_NRM2] - redB[0] * redB[0], 0.0));
       s->beta = b;
       if (!(b > 0)) { s->action = ACT_FINISH; s->split = 0; s->q = 0.0; s->theta = 0.0; }   // degenerate start (cannot happen for len >= 2)
       else s->action = ACT_NEXT;
@@ -759,7 +762,9 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
     double beta = 0.0;
     if (lane == 0) {
       A[j - 1] = redA[j] + redB[j];
-      beta = sqrt(fmax(scal[R_NRM2], 0.0));
+      double g2 = 0.0;
+      for (int l = 0; l <= j; ++l) g2 += redB[l] * redB[l];
+      beta = sqrt(fmax(scal[R_NRM2] - g2, 0.0));
       B[j] = beta;
       if (j == 1) B[0] = 0.0;
       s->beta = beta;
@@ -771,7 +776,7 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
     const bool exhausted = (j >= len - 1);
     const bool breakdown = !(beta > 1e-13);
     const bool full = (j >= c.K);
-    const bool check = exhausted || breakdown || full || j <= 8 || (j & 3) == 0;
+    const bool check = exhausted || breakdown || full || j <= 64 || (j & 3) == 0;     // T_j is tiny: test every step early on
     if (!check) { if (lane == 0) s->action = ACT_NEXT; return; }
     __threadfence_block();
     const double theta = tmc_top_eig_warp(A, B, j, s->theta_hint);
@@ -787,7 +792,7 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
       bool conv = exhausted || breakdown || resid <= c.tol * theta || resid <= 1e-14;
       if (conv || (full && s->restarts >= c.max_restarts)) {
         s->action = ACT_RITZ_LABEL;
-        c.red2[2 * slot] = 0.0; c.red2[2 * slot + 1] = 0.0;
+        scal[R_N1] = 0.0; scal[R_SD1] = 0.0;
       } else if (full) {
         s->action = ACT_RITZ_RESTART; s->restarts += 1; s->theta_hint = -1e300;
       } else s->action = ACT_NEXT;
@@ -799,7 +804,7 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
   // O_0 = ||t - t1||^2 - n0 = sum d - 2 sum_{c1} d + ||t1||^2 - n0,  L_c = sum_{c} d - n_c,  L = sum d - m.
   if (lane == 0) {
     const double m = (double)s->gsize;
-    const double n1 = c.red2[2 * slot], sd1 = c.red2[2 * slot + 1];
+    const double n1 = scal[R_N1], sd1 = scal[R_SD1];
     const double n0 = m - n1, sd = s->sumd, t1 = scal[R_YNORM2];
     const double L = sd - m;
     double q = 0.0;
@@ -869,7 +874,7 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
   if (action == ACT_RITZ_LABEL) {
     double t = block_sum_256(n1, sm8);
     double t2 = block_sum_256(sd1, sm8);
-    if (threadIdx.x == 0) { atomicAdd(c.red2 + 2 * ch.slot, t); atomicAdd(c.red2 + 2 * ch.slot + 1, t2); }
+    if (threadIdx.x == 0) { atomicAdd(slot_scal(c, ch.slot) + R_N1, t); atomicAdd(slot_scal(c, ch.slot) + R_SD1, t2); }
   }
 }
 
@@ -951,11 +956,11 @@ __global__ void k_set_labels(Ctx c, const uint8_t* __restrict__ lab, int n, int 
   if (i < n) { int l = lab[i] ? 1 : 0; c.label[i] = (uint8_t)l; c.xin[i] = (double)l; n1 = l; sd1 = l ? c.d[i] : 0.0; }
   double t = block_sum_256(n1, sm8);
   double t2 = block_sum_256(sd1, sm8);
-  if (threadIdx.x == 0) { atomicAdd(c.red2 + 2 * slot, t); atomicAdd(c.red2 + 2 * slot + 1, t2); }
+  if (threadIdx.x == 0) { atomicAdd(slot_scal(c, slot) + R_N1, t); atomicAdd(slot_scal(c, slot) + R_SD1, t2); }
 }
 __global__ void k_force_state(Ctx c, int slot, int state, int j, int stop_after) {
   c.st[slot].state = state; c.st[slot].j = j; c.st[slot].action = ACT_NONE; c.st[slot].stop_after = stop_after;
-  c.red2[2 * slot] = 0.0; c.red2[2 * slot + 1] = 0.0;
+  slot_scal(c, slot)[R_N1] = 0.0; slot_scal(c, slot)[R_SD1] = 0.0;
 }
 
 // tmc_partition API: set up slot `slot` so that k_partition splits [begin,end)

@@ -8,7 +8,7 @@ n, g, k, d, s, binary = synth.CONFIGS[name]
 dev = torch.device("cuda", 0)
 rp, col, val = synth.synth_counts_torch(n, g, k, d, s, dev, binary)
 work = torch.empty_like(val)
-for it in range(5):
+for it in range(int(os.environ.get("TMC_ITERS", "5"))):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     work.copy_(val); torch.cuda.synchronize(); t1 = time.perf_counter()
     b = T.DeviceB.adopt_device(n, g, rp, col, work, normalize=True, device=0); t2 = time.perf_counter()
