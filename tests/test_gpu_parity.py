@@ -248,6 +248,30 @@ def test_make_tree_outputs_end_to_end(tmp_path, tiny):
     assert t2.n_nodes == tree.n_nodes and len(nm) == a.shape[0]
 
 
+def test_binary_wide_matrix_like_scatac():
+    """BASELINE.json configs[3] in miniature: binarised peaks, far more features than cells."""
+    ip, ix, dv, _ = synth.synth_counts(700, 40000, 400, 3, 21, binary=True)
+    a = sp.csr_matrix((dv, ix, ip), shape=(700, 40000))
+    assert set(np.unique(a.data)) == {1.0}
+    tree = T.hierarchical_spectral_cluster(a, normalize=True)
+    ot = O.hierarchical_spectral_cluster(a, normalize=True)
+    assert tree.leaf_sets() == ot.leaf_sets() and same_tree(tree, ot)
+
+
+def test_saturated_tree_like_config5():
+    """BASELINE.json configs[4] in miniature: min-modularity low enough that every cell becomes its own leaf."""
+    ip, ix, dv, _ = synth.synth_counts(1500, 3000, 120, 3, 33)
+    a = sp.csr_matrix((dv, ix, ip), shape=(1500, 3000))
+    tree = T.hierarchical_spectral_cluster(a, normalize=True, min_modularity=-1.0)
+    assert len(tree.leaves()) == 1500 and tree.n_nodes == 2 * 1500 - 1
+    assert np.array_equal(np.sort(tree.perm), np.arange(1500))
+    ot = O.hierarchical_spectral_cluster(a[:300], normalize=True, min_modularity=-1.0)
+    t3 = T.hierarchical_spectral_cluster(a[:300], normalize=True, min_modularity=-1.0)
+    # with saturation the topology is sensitive to exact ties only in degenerate nodes; compare the split sequence of the root path
+    assert sorted(len(x) for x in t3.leaf_sets()) == sorted(len(x) for x in ot.leaf_sets())
+    assert abs(t3.q[0] - ot.q[0]) < 1e-12
+
+
 def test_large_config_properties():
     """c1-sized input (BASELINE.json configs[0]): size-independent properties instead of the oracle."""
     ip, ix, dv, _ = synth.synth_config("c1")

@@ -305,6 +305,7 @@ struct Engine {
   int64_t n_sweeps = 0, n_launch = 0;
   double alg_vec_bytes = 0;     // non-matrix part of the spmv_pair algorithmic bytes
   double build_ms = 0;
+  int tg_variant = getenv("TMC_TG") ? atoi(getenv("TMC_TG")) : 0;
   bool profile = false;
   std::vector<cudaEvent_t> evs;
 
@@ -315,6 +316,7 @@ struct Engine {
     c.tol = o.tol > 0 ? o.tol : 1e-10;
     c.min_modularity = o.min_modularity; c.min_size = std::max(1, o.min_size);
     c.max_restarts = o.max_restarts >= 0 ? o.max_restarts : 8; c.seed = o.seed;
+    c.xs_min_rows = getenv("TMC_XS_ROWS") ? atoi(getenv("TMC_XS_ROWS")) : 8192;
     c.rank = g_nccl.comm ? g_nccl.rank : 0; c.world = g_nccl.comm ? g_nccl.world : 1;
     hstate.assign(w->max_active, ST_IDLE); slot_node.assign(w->max_active, -1);
     for (int i = 0; i < w->max_active; ++i) free_slots.push(i);
@@ -490,7 +492,25 @@ struct Engine {
     if (n_sc) {
       k_zero_y<<<dim3(hi_slot, ny), 256, 0, s>>>(c); n_launch++;
       if (profile) e0 = ev();
-      if (c.use_t) { if (ntch) { k_tgather<<<ntch, 256, 0, s>>>(c); n_launch++; } }
+      if (c.use_t) {
+        if (ntch) {
+          // large nodes (long sorted column runs) read x in the strided mapping, small ones in the plain one
+          int n_big = 0, n_small = 0;
+          for (int sl = 0; sl < hi_slot; ++sl) {
+            int st = hstate[sl];
+            if (st != ST_DEG && st != ST_LAN && st != ST_MOD) continue;
+            const HostNode& nd = nodes[slot_node[sl]];
+            if (nd.end - nd.begin >= c.xs_min_rows) n_big++; else n_small++;
+          }
+          if (tg_variant == 1) k_tgather_t<4, 1><<<ntch, 256, 0, s>>>(c, 0);
+          else if (tg_variant == 2) k_tgather_t<4, 0><<<ntch, 256, 0, s>>>(c, 0);
+          else {
+            if (n_big) { k_tgather_t<4, 1><<<ntch, 256, 0, s>>>(c, n_small ? 1 : 0); if (n_small) n_launch++; }
+            if (n_small) k_tgather_t<4, 0><<<ntch, 256, 0, s>>>(c, n_big ? 2 : 0);
+          }
+          n_launch++;
+        }
+      }
       else if (nch) { k_scatter<<<nch, 256, 0, s>>>(c); n_launch++; }
       if (profile) e1 = ev();
       allreduce_f64(c.Y, (size_t)c.ystride * hi_slot);

@@ -69,6 +69,7 @@ struct Ctx {
   Chunk* vchunks; int* n_vchunks; int vchunk_rows;   // vector kernels (dots/update/advance): up to 256 positions per CTA
   // transposed (column-sorted) per-node copy of B: y = B_S^T x as a gather with run merging instead of nnz atomics
   int use_t;
+  int xs_min_rows;                                   // nodes with at least this many local rows read x in the strided mapping
   int32_t* tcol[2]; int32_t* tpos[2]; double* tval[2];
   TChunk* tchunks; int* n_tchunks; int tchunk;       // entries per chunk (multiple of 2048)
   int* tile_cnt; long long* tile_off;                // per chunk: label-1 entries / exclusive prefix inside the node
@@ -335,13 +336,16 @@ __global__ void __launch_bounds__(256) k_scatter(Ctx c) {
 __device__ __forceinline__ int4 ldg_i4(const int32_t* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
 __device__ __forceinline__ double2 ldg_d2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
-__global__ void __launch_bounds__(256) k_tgather(Ctx c) {
-  __shared__ double xs_sm[8][288];          // per warp: 256 x-values in a padded layout (index i -> i + i/8)
+// E = consecutive entries per lane (4 or 8); XS = read x in the strided mapping and change mapping through padded smem
+template <int E, int XS>
+__global__ void __launch_bounds__(256) k_tgather_t(Ctx c, int cls) {       // cls: 0 all nodes, 1 only large (>= xs_min_rows), 2 only small
+  __shared__ double xs_sm[XS ? 8 : 1][XS ? (32 * E + 2 * E) : 1];
   if ((int)blockIdx.x >= *c.n_tchunks) return;
   const TChunk ch = c.tchunks[blockIdx.x];
   const Slot& s = c.st[ch.slot];
   const int state = s.state;
   if (state != ST_DEG && state != ST_LAN && state != ST_MOD) return;
+  if (cls) { const bool big = (s.end - s.begin) >= c.xs_min_rows; if (big != (cls == 1)) return; }
   const long long tb = s.tb, te = s.te;
   const int par = s.tpar;
   const int32_t* __restrict__ tcol = par ? c.tcol[1] : c.tcol[0];
@@ -350,53 +354,73 @@ __global__ void __launch_bounds__(256) k_tgather(Ctx c) {
   const double* __restrict__ xin = c.xin;
   double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* xs = xs_sm[warp];
   const long long cend = min(ch.begin + (long long)c.tchunk, te);
-  for (long long base = ch.begin + warp * 256; base < cend; base += 8 * 256) {
-    // x = xin[pos] read in the STRIDED mapping (entry base + 32e + lane): inside a column the positions ascend, so a
-    // warp-wide load touches a few consecutive lines instead of 32 (measured +0.23 ms on the c2 root when the
-    // gather is issued in the blocked mapping); the values change mapping through padded shared memory.
-    if (state != ST_DEG) {
+  constexpr int W = 32 * E;                 // entries per warp iteration
+  constexpr bool xs_on = (XS == 1);
+  for (long long base = ch.begin + warp * W; base < cend; base += 8 * W) {
+    double* xs = xs_sm[XS ? warp : 0];
+    if (XS && xs_on && state != ST_DEG) {
+      // x = xin[pos] in the STRIDED mapping (entry base + 32e + lane): positions ascend inside a column, so a warp-wide
+      // gather touches a few consecutive lines; padded layout i -> i + i/16 is conflict-free for both mappings.
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
+      for (int e = 0; e < E; ++e) {
         const long long k = base + 32 * e + lane;
         double xv = 0.0;
         if (k >= tb && k < te) xv = __ldg(xin + __ldg(tpos + k));
         const int i = 32 * e + lane;
-        xs[i + (i >> 3)] = xv;
+        xs[i + (i >> 4)] = xv;
       }
       __syncwarp();
     }
-    const long long k0 = base + lane * 8;
-    int cc[8]; double t[8];
-    if (k0 < te && k0 + 8 > tb) {
-      const int4 ca = ldg_i4(tcol + k0), cb = ldg_i4(tcol + k0 + 4);
-      const double2 v0 = ldg_d2(tval + k0), v1 = ldg_d2(tval + k0 + 2), v2 = ldg_d2(tval + k0 + 4), v3 = ldg_d2(tval + k0 + 6);
-      cc[0] = ca.x; cc[1] = ca.y; cc[2] = ca.z; cc[3] = ca.w; cc[4] = cb.x; cc[5] = cb.y; cc[6] = cb.z; cc[7] = cb.w;
-      t[0] = v0.x; t[1] = v0.y; t[2] = v1.x; t[3] = v1.y; t[4] = v2.x; t[5] = v2.y; t[6] = v3.x; t[7] = v3.y;
-      if (state != ST_DEG) {
+    const long long k0 = base + lane * E;
+    int cc[E]; double t[E];
+    if (k0 < te && k0 + E > tb) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) t[e] *= xs[9 * lane + e];
+      for (int q = 0; q < E / 4; ++q) {
+        const int4 ca = ldg_i4(tcol + k0 + 4 * q);
+        cc[4 * q] = ca.x; cc[4 * q + 1] = ca.y; cc[4 * q + 2] = ca.z; cc[4 * q + 3] = ca.w;
       }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) if (!((k0 + e >= tb) && (k0 + e < te))) { cc[e] = -1; t[e] = 0.0; }
+      for (int q = 0; q < E / 2; ++q) { const double2 v = ldg_d2(tval + k0 + 2 * q); t[2 * q] = v.x; t[2 * q + 1] = v.y; }
+      if (state != ST_DEG) {
+        if (XS && xs_on) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) { const int i = E * lane + e; t[e] *= xs[i + (i >> 4)]; }
+        } else {
+          int pp[E];
+#pragma unroll
+          for (int q = 0; q < E / 4; ++q) {
+            const int4 pa = ldg_i4(tpos + k0 + 4 * q);
+            pp[4 * q] = pa.x; pp[4 * q + 1] = pa.y; pp[4 * q + 2] = pa.z; pp[4 * q + 3] = pa.w;
+          }
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const bool ok = (k0 + e >= tb) && (k0 + e < te);
+            t[e] = ok ? t[e] * __ldg(xin + pp[e]) : 0.0;
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) if (!((k0 + e >= tb) && (k0 + e < te))) { cc[e] = -1; t[e] = 0.0; }
     } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { cc[e] = -1; t[e] = 0.0; }
+      for (int e = 0; e < E; ++e) { cc[e] = -1; t[e] = 0.0; }
     }
-    if (state != ST_DEG) __syncwarp();
+    if (XS && xs_on && state != ST_DEG) __syncwarp();
     // whole warp inside one column?
     const int cfirst = __shfl_sync(0xffffffffu, cc[0], 0);
-    const int clast = __shfl_sync(0xffffffffu, cc[7], 31);
+    const int clast = __shfl_sync(0xffffffffu, cc[E - 1], 31);
     if (cfirst == clast && cfirst >= 0) {
-      double a = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+      double a = 0.0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) a += t[e];
       a = warp_sum(a);
       if (lane == 0 && a != 0.0) atomicAdd(y + cfirst, a);
       continue;
     }
     double acc = t[0]; int cur = cc[0];
 #pragma unroll
-    for (int e = 1; e < 8; ++e) {
+    for (int e = 1; e < E; ++e) {
       if (cc[e] == cur) acc += t[e];
       else { if (cur >= 0 && acc != 0.0) atomicAdd(y + cur, acc); cur = cc[e]; acc = t[e]; }
     }
