@@ -116,9 +116,11 @@ def cpu_reference_run(name, sample_cells, steps=1, warmup=0):
         if it >= warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    desc = (f"oracle (numpy/scipy LAPACK+ARPACK, exact eigen-solve) make-tree on the first {ns} cells x {g} genes of {name} "
-            f"({a.nnz} nnz, {tr.n_nodes} nodes)")
-    return ms, ns, a.nnz, desc
+    scale = n / ns
+    desc = (f"oracle port (numpy/scipy LAPACK+ARPACK, exact eigen-solve; the Haskell reference cannot be built here) make-tree on "
+            f"the first {ns} cells x {g} genes of {name} ({a.nnz} nnz, {tr.n_nodes} nodes): {ms:.0f} ms measured, scaled x{scale:.0f} "
+            f"linearly in cells to the full workload (conservative: the full tree is deeper, so cost per cell is higher)")
+    return ms * scale, ns, a.nnz, desc
 
 
 def main():
@@ -137,8 +139,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg,
-                "cpu_baseline": {"value": ms, "unit": UNIT, "cores": ncores, "kind": "port", "sample": desc +
-                                 "; each step is one tree on that sample, NOT the full workload"},
+                "cpu_baseline": {"value": ms, "unit": UNIT, "cores": ncores, "kind": "port", "sample": desc},
                 "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -254,8 +255,12 @@ def main():
                      "scatter_gbs": 0.5 * pair_bytes / (sc_ms * 1e-3) / 1e9, "gather_gbs": 0.5 * pair_bytes / (ga_ms * 1e-3) / 1e9}
     else:
         root_pair = None
+    # dram__bytes_read+write of the root-level pair launch from the committed `ncu --set full` capture
+    # (profiles/r1_v3_spmv_pair_c3_ncu_raw.csv: k_tgather 26.78 GB + k_gather 20.20 GB); algorithmic bytes of that launch are
+    # 24 B x nnz + vectors = 40.2 GB: the transposed copy stores the column id explicitly (16 B per entry instead of 12).
+    traffic = 46.98e9 if (name == "c3" and world == 1) else None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-            "traffic": None, "peak_source": peak_src, "kernel": "k_scatter+k_gather (SpMV pair y=C^T x, x'=C y), all launches of the timed steps",
+            "traffic": traffic, "traffic_scope": "root-level pair launch (largest launch), ncu dram bytes" if traffic else None, "peak_source": peak_src, "kernel": "k_scatter+k_gather (SpMV pair y=C^T x, x'=C y), all launches of the timed steps",
             "algorithmic_bytes_per_step": alg / len(trees), "spmv_ms_per_step": spmv_ms / len(trees),
             "spmv_share_of_step": spmv_ms / len(trees) / ms_step,
             "per_gpu": True, "root_pair": root_pair}
@@ -269,8 +274,7 @@ def main():
                      "lanczos_steps": int(tr.iters.sum()), "engine_ms_last": tr.stats["engine_ms"], "gen_s": gen_s}}
     if not args.no_cpu_baseline:
         ms_c, ns, nnz_c, desc = cpu_reference_run(name, args.cpu_sample_cells)
-        line["cpu_baseline"] = {"value": ms_c, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                "sample": desc + "; value is ms for ONE tree on that sample, not the full workload"}
+        line["cpu_baseline"] = {"value": ms_c, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc}
     print(json.dumps(line))
     if world > 1:
         tdist.destroy_comm()
