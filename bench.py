@@ -250,18 +250,19 @@ def main():
         b = T.DeviceB.adopt_device(n, g, row_ptr, col, work, normalize=True, device=local_rank)
         sc_ms, ga_ms = T.bench_spmv_pair(b, 10)
         b.free()
-        pair_bytes = 24.0 * nnz + 16.0 * (n + 1) + 32.0 * n + 16.0 * g
+        bv = tr.stats["value_bytes"]          # 8: fp64 B; 2: raw counts as uint16 + diagonal factors; 0: all-ones matrix
+        pair_bytes = 2.0 * (bv + 4.0) * nnz + 16.0 * (n + 1) + 32.0 * n + 16.0 * g
         root_pair = {"scatter_ms": sc_ms, "gather_ms": ga_ms, "bytes": pair_bytes,
                      "scatter_gbs": 0.5 * pair_bytes / (sc_ms * 1e-3) / 1e9, "gather_gbs": 0.5 * pair_bytes / (ga_ms * 1e-3) / 1e9}
     else:
         root_pair = None
-    # dram__bytes_read+write of the root-level pair launch from the committed `ncu --set full` capture
-    # (profiles/r1_v3_spmv_pair_c3_ncu_raw.csv: k_tgather 26.78 GB + k_gather 20.20 GB); algorithmic bytes of that launch are
-    # 24 B x nnz + vectors = 40.2 GB: the transposed copy stores the column id explicitly (16 B per entry instead of 12).
-    traffic = 46.98e9 if (name == "c3" and world == 1) else None
+    # filled from the committed `ncu --set full` capture of the root-level pair launch (profiles/README.md) when one exists
+    # for this workload and storage mode
+    traffic = None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
             "traffic": traffic, "traffic_scope": "root-level pair launch (largest launch), ncu dram bytes" if traffic else None, "peak_source": peak_src, "kernel": "k_scatter+k_gather (SpMV pair y=C^T x, x'=C y), all launches of the timed steps",
-            "algorithmic_bytes_per_step": alg / len(trees), "spmv_ms_per_step": spmv_ms / len(trees),
+            "algorithmic_bytes_per_step": alg / len(trees), "value_bytes_b_v": tr.stats["value_bytes"],
+            "algorithmic_bytes_formula": "per SpMV pair 2*nnz*(b_v+4) + 2*(m+1)*8 + (4*m+2*n)*8 (BASELINE.md section 4), b_v = bytes per stored value", "spmv_ms_per_step": spmv_ms / len(trees),
             "spmv_share_of_step": spmv_ms / len(trees) / ms_step,
             "per_gpu": True, "root_pair": root_pair}
     line = {"metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

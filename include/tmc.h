@@ -94,7 +94,9 @@ typedef struct {
   int64_t kernel_launches;
   double  engine_ms;          /* device time of the tree build (CUDA events) */
   double  spmv_ms;            /* device time inside the scatter+gather kernels (only if opts.profile) */
-  double  spmv_alg_bytes;     /* algorithmic bytes of those SpMV pairs (BASELINE.md section 4 formula) */
+  double  spmv_alg_bytes;     /* algorithmic bytes of those SpMV pairs (BASELINE.md section 4 formula, b_v as stored) */
+  int32_t value_bytes;        /* b_v: 8 = B kept as fp64; 2 = raw counts kept as uint16 + diagonal factors; 0 = all-ones matrix */
+  int32_t pad_;
 } tmc_tree;
 
 /* Device-resident matrix handle: B = row-L2-normalised (tf-idf) CSR kept in HBM. */

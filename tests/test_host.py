@@ -34,7 +34,7 @@ def test_opts_default_and_layout():
     o = T.make_opts()
     assert o.eigen_group == 0 and o.num_eigen == 1 and o.min_modularity == 0.0 and o.min_size == 1
     assert o.normalize == 0 and o.num_runs == 0 and o.tol == 1e-10 and o.max_lanczos == 320 and o.device == -1
-    assert C.sizeof(_lib.Opts) == 96 and C.sizeof(_lib.Tree) == 136      # static_assert-ed in tmc_engine.cu
+    assert C.sizeof(_lib.Opts) == 96 and C.sizeof(_lib.Tree) == 144      # static_assert-ed in tmc_engine.cu
 
 
 def test_no_cpu_fallback_without_device():

@@ -44,7 +44,8 @@ class Tree(C.Structure):
                 ("q", C.POINTER(C.c_double)), ("theta", C.POINTER(C.c_double)), ("iters", C.POINTER(C.c_int32)),
                 ("item_begin", C.POINTER(C.c_int64)), ("item_end", C.POINTER(C.c_int64)), ("perm", C.POINTER(C.c_int64)),
                 ("n_sweeps", C.c_int64), ("spmv_pairs_nnz", C.c_int64), ("kernel_launches", C.c_int64),
-                ("engine_ms", C.c_double), ("spmv_ms", C.c_double), ("spmv_alg_bytes", C.c_double)]
+                ("engine_ms", C.c_double), ("spmv_ms", C.c_double), ("spmv_alg_bytes", C.c_double),
+                ("value_bytes", C.c_int32), ("pad_", C.c_int32)]
 
 
 # every symbol include/tmc.h declares: (restype, argtypes)

@@ -28,7 +28,7 @@ using namespace tmc;
 
 static_assert(sizeof(tmc_csr) == 64, "tmc_csr layout is part of the ABI (mirrored in _lib.py)");
 static_assert(sizeof(tmc_opts) == 96, "tmc_opts layout is part of the ABI (mirrored in _lib.py)");
-static_assert(sizeof(tmc_tree) == 136, "tmc_tree layout is part of the ABI (mirrored in _lib.py)");
+static_assert(sizeof(tmc_tree) == 144, "tmc_tree layout is part of the ABI (mirrored in _lib.py)");
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -79,8 +79,21 @@ struct tmc_matrix {
   int64_t* row_ptr = nullptr; int32_t* col = nullptr; double* val = nullptr;
   bool owns = false;
   int device = 0;
+  // storage mode (DESIGN.md "factored values"): VT_F64 = val holds B itself; VT_U16 / VT_ONE = B = diag(rrow) A diag(w)
+  // with A the caller's small-integer values kept as uint16 (valc) / implicit ones
+  int vt = VT_F64;
+  void* valc = nullptr; double* rrow = nullptr; double* w2col = nullptr; double* invw = nullptr;
   Workspace* ws = nullptr;
 };
+
+#define VT_DISPATCH(vt, ...)                                                        \
+  do {                                                                              \
+    switch (vt) {                                                                   \
+      case VT_U16: { constexpr int VT = VT_U16; __VA_ARGS__; } break;               \
+      case VT_ONE: { constexpr int VT = VT_ONE; __VA_ARGS__; } break;               \
+      default: { constexpr int VT = VT_F64; __VA_ARGS__; } break;                   \
+    }                                                                               \
+  } while (0)
 
 template <class T> static T* dalloc(size_t n) {
   T* p = nullptr;
@@ -90,7 +103,8 @@ template <class T> static T* dalloc(size_t n) {
 
 struct Workspace {
   Ctx c{};
-  int K = 0, max_active = 0, use_t = 0, tcap = 0, device = 0;
+  int K = 0, max_active = 0, use_t = 0, tcap = 0, device = 0, vt = 0;
+  int32_t* rowid_scratch = nullptr;
   int64_t m = 0, cap_m = 0, cap_nnz = 0, cap_cols = 0;
   Report* h_rep = nullptr; Activation* h_act = nullptr; Activation* d_act = nullptr;
   int* h_err = nullptr; unsigned long long* h_stats = nullptr;
@@ -126,7 +140,8 @@ static Workspace* g_ws_cache = nullptr;
 
 static void bind_workspace(Workspace* w, tmc_matrix* b) {
   Ctx& c = w->c;
-  c.row_ptr = b->row_ptr; c.col = b->col; c.val = b->val;
+  c.row_ptr = b->row_ptr; c.col = b->col; c.val = (b->vt == VT_F64) ? (const void*)b->val : (const void*)b->valc;
+  c.vt = b->vt; c.rrow = b->rrow; c.w2col = b->w2col; c.invw = b->invw;
   c.n_rows = (int)b->n_rows; c.n_cols = (int)b->n_cols; c.row_offset = b->row_offset;
   c.vstride = (b->n_rows + 15) / 16 * 16;
   c.ystride = (b->n_cols + 15) / 16 * 16;
@@ -139,12 +154,12 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
   int max_active = (int)std::min<int64_t>(std::max<int64_t>(1, b->n_rows_global / 2), o.max_active > 0 ? o.max_active : 2048);
   max_active = std::min(max_active, 4096);
   const int use_t = (o.scatter_mode == 0);
-  if (b->ws && b->ws->K == K && b->ws->max_active == max_active && b->ws->use_t == use_t) return b->ws;
+  if (b->ws && b->ws->K == K && b->ws->max_active == max_active && b->ws->use_t == use_t && b->ws->vt == b->vt) return b->ws;
   delete b->ws; b->ws = nullptr;
   {
     std::lock_guard<std::mutex> lk(g_cache_mu);
     Workspace* q = g_ws_cache;
-    if (q && q->device == b->device && q->K == K && q->max_active == max_active && q->use_t == use_t && q->cap_m >= m &&
+    if (q && q->device == b->device && q->K == K && q->max_active == max_active && q->use_t == use_t && q->vt == b->vt && q->cap_m >= m &&
         q->cap_nnz >= b->nnz && q->cap_cols >= b->n_cols) {
       g_ws_cache = nullptr;
       bind_workspace(q, b);
@@ -154,7 +169,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
   }
   Workspace* w = new Workspace();
   try {
-    w->K = K; w->max_active = max_active; w->use_t = use_t; w->device = b->device;
+    w->K = K; w->max_active = max_active; w->use_t = use_t; w->device = b->device; w->vt = b->vt;
     w->cap_m = m; w->cap_nnz = b->nnz; w->cap_cols = b->n_cols;
     CK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     Ctx& c = w->c;
@@ -179,7 +194,9 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     c.use_t = use_t;
     if (c.use_t) {      // transposed per-node blocks, double buffered (children are written to the other buffer)
       const size_t tn = (size_t)b->nnz + 4096;
-      for (int q = 0; q < 2; ++q) { c.tcol[q] = w->A<int32_t>(tn); c.tpos[q] = w->A<int32_t>(tn); c.tval[q] = w->A<double>(tn); }
+      const size_t vsz = b->vt == VT_F64 ? 8 : (b->vt == VT_U16 ? 2 : 0);
+      for (int q = 0; q < 2; ++q) { c.tcol[q] = w->A<int32_t>(tn); c.tpos[q] = w->A<int32_t>(tn); c.tval[q] = w->A<char>(tn * vsz + 64); }
+      w->rowid_scratch = w->A<int32_t>(tn);
       w->tcap = 32768 + max_active + 64;
       c.tchunks = w->A<TChunk>(w->tcap); c.n_tchunks = w->A<int>(1);
       c.tile_cnt = w->A<int>(w->tcap); c.tile_off = w->A<long long>(w->tcap);
@@ -248,6 +265,64 @@ static void normalise_dev(tmc_matrix* b, int normalize, double* norm_out_dev, do
     if (d_err) cudaFree(d_err);
     if (df) cudaFree(df);
     if (idf && !idf_out_dev) cudaFree(idf);
+    throw;
+  }
+}
+
+// Decide the storage mode and compute what the engine needs from the device-resident input values.
+//  * all values are integers in [0, 65535] (raw counts; the usual make-tree input when the engine applies tf-idf itself):
+//    keep A as uint16 (or nothing when every value is 1) and the factors w_j = idf_j (or 1), r_i = 1/||(A diag w)_i||;
+//    the caller's fp64 array is left untouched.
+//  * otherwise: materialise B in place as before (idf scaling if asked, row L2).
+static void prepare_matrix(tmc_matrix* b, int normalize) {
+  int* d_flags = dalloc<int>(2);
+  int* df = nullptr; double* idf = nullptr;
+  try {
+    CK(cudaMemset(d_flags, 0, 2 * sizeof(int)));
+    const int grid = 148 * 8;
+    k_scan_values<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, d_flags);
+    int f[2] = {0, 0};
+    CK(cudaMemcpy(f, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    if (f[0] & 1) throw TmcError(TMC_ERR_NAN, "NaN/Inf in matrix values");
+    if (f[0] & 4) throw TmcError(TMC_ERR_INVALID, "column index out of range");
+    if (f[0] & 2) throw TmcError(TMC_ERR_NEGATIVE, "negative matrix entry (engine requires B >= 0)");
+    const bool small_int = !(f[0] & 8) && getenv("TMC_NO_FACTORED") == nullptr;
+    if (!small_int) {
+      cudaFree(d_flags); d_flags = nullptr;
+      b->vt = VT_F64;
+      normalise_dev(b, normalize, nullptr, nullptr, true);
+      return;
+    }
+    b->vt = (f[0] & 16) ? VT_U16 : VT_ONE;
+    if (normalize) {
+      df = dalloc<int>(b->n_cols); idf = dalloc<double>(b->n_cols);
+      CK(cudaMemset(df, 0, sizeof(int) * b->n_cols));
+      k_df_count<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, df, d_flags + 1);
+      if (g_nccl.comm && g_nccl.world > 1) {
+        int r = g_nccl.AllReduce(df, df, (size_t)b->n_cols, NCCL_INT32, NCCL_SUM, g_nccl.comm, 0);
+        if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(df) failed");
+      }
+      k_idf<<<(int)((b->n_cols + 255) / 256), 256>>>(df, (int)b->n_cols, (double)b->n_rows_global, idf);
+    }
+    b->rrow = dalloc<double>(b->n_rows); b->w2col = dalloc<double>(b->n_cols); b->invw = dalloc<double>(b->n_cols);
+    k_row_factor<<<grid, 256>>>(b->row_ptr, b->col, b->val, idf, (int)b->n_rows, b->rrow, d_flags + 1);
+    k_col_factors<<<(int)((b->n_cols + 255) / 256), 256>>>(idf, (int)b->n_cols, b->w2col, b->invw);
+    if (b->vt == VT_U16) {
+      b->valc = dalloc<unsigned short>(b->nnz + 64);
+      k_to_u16<<<grid, 256>>>(b->val, reinterpret_cast<unsigned short*>(b->valc), b->nnz);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(f, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    if (b->owns && b->val) { cudaFree(b->val); b->val = nullptr; }       // the fp64 copy is not needed any more
+    cudaFree(d_flags); d_flags = nullptr;
+    if (df) cudaFree(df);
+    if (idf) cudaFree(idf);
+    df = nullptr; idf = nullptr;
+    if (f[1]) { std::string msg; int st = err_to_status(f[1], &msg); throw TmcError(st, msg); }
+  } catch (...) {
+    if (d_flags) cudaFree(d_flags);
+    if (df) cudaFree(df);
+    if (idf) cudaFree(idf);
     throw;
   }
 }
@@ -350,7 +425,7 @@ struct Engine {
     CK(cudaMemsetAsync(c.tb_cnt, 0, sizeof(int) * (b->n_cols + 1), s));
     k_tb_count<<<grid, 256, 0, s>>>(c, nd.begin, nd.end);
     k_tb_scan<<<1, 1024, 0, s>>>(c);
-    k_tb_fill<<<grid, 256, 0, s>>>(c, nd.begin, nd.end, 0, 0);
+    VT_DISPATCH(c.vt, k_tb_fill<VT><<<grid, 256, 0, s>>>(c, nd.begin, nd.end, 0, 0));
     n_launch += 3;
     long long tot = 0;
     CK(cudaMemcpyAsync(&tot, c.tb_colstart + b->n_cols, sizeof(long long), cudaMemcpyDeviceToHost, s));
@@ -369,7 +444,7 @@ struct Engine {
     if (n >= (1ll << 31) - 1 || n == 0) { build_tblock(nd); return; }
     int32_t* keysA = c.tcol[1]; int32_t* keysB = c.tcol[0];
     int32_t* valsA = c.tpos[1]; int32_t* valsB = c.tpos[0];
-    int32_t* rowid = reinterpret_cast<int32_t*>(c.tval[1]);
+    int32_t* rowid = w->rowid_scratch;
     CK(cudaMemcpyAsync(keysA, b->col, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
     k_tb_iota<<<148 * 8, 256, 0, s>>>(valsA, n);
     k_tb_rowid<<<148 * 8, 256, 0, s>>>(b->row_ptr, (int)b->n_rows, rowid);
@@ -387,7 +462,7 @@ struct Engine {
     CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, avail, dk, dv, (int)n, 0, end_bit, s));
     if (dk.Current() != keysB) CK(cudaMemcpyAsync(keysB, dk.Current(), sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
     if (dv.Current() != valsB) CK(cudaMemcpyAsync(valsB, dv.Current(), sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
-    k_tb_finish_sorted<<<148 * 8, 256, 0, s>>>(rowid, b->val, valsB, c.tval[0], n);
+    VT_DISPATCH(c.vt, k_tb_finish_sorted<VT><<<148 * 8, 256, 0, s>>>(rowid, c.val, valsB, c.tval[0], n));
     CK(cudaStreamSynchronize(s));
     n_launch += 6;
     nd.tb = 0; nd.te = n; nd.tpar = 0;
@@ -439,7 +514,7 @@ struct Engine {
   // One sweep: every live slot advances by one step of its lifecycle
   // (degree pass | start-vector orthogonalisation | Lanczos step | modularity + split).
   void sweep(bool only_spmv = false) {
-    int n_sc = 0, n_ga = 0, n_mod = 0, n_or = 0, live_n = 0; int64_t rows = 0;
+    int n_sc = 0, n_ga = 0, n_mod = 0, n_or = 0, n_deg = 0, live_n = 0; int64_t rows = 0;
     for (int sl = 0; sl < hi_slot; ++sl) {
       int st = hstate[sl];
       if (st < ST_DEG || st > ST_MOD) continue;
@@ -450,6 +525,7 @@ struct Engine {
       if (st == ST_DEG || st == ST_LAN || st == ST_MOD) n_sc++;
       if (st == ST_DEG || st == ST_LAN) { n_ga++; alg_vec_bytes += 16.0 * (len + 1) + 32.0 * len + 16.0 * (double)b->n_cols / c.world; }
       if (st == ST_MOD) n_mod++;
+      if (st == ST_DEG) n_deg++;
       if (st == ST_ORTH0 || st == ST_LAN) n_or++;
     }
     if (!live_n) return;
@@ -488,6 +564,7 @@ struct Engine {
       if (ntch > w->tcap) throw TmcError(TMC_ERR_CUDA, "internal: transposed chunk list overflow");
     }
     k_prepare<<<1, 1024, 0, s>>>(c); n_launch++;
+    if (c.vt != VT_F64 && n_deg && nvch) { k_deg_xin<<<nvch, 256, 0, s>>>(c); n_launch++; }
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     if (n_sc) {
       k_zero_y<<<dim3(hi_slot, ny), 256, 0, s>>>(c); n_launch++;
@@ -502,20 +579,21 @@ struct Engine {
             const HostNode& nd = nodes[slot_node[sl]];
             if (nd.end - nd.begin >= c.xs_min_rows) n_big++; else n_small++;
           }
-          if (tg_variant == 1) k_tgather_t<4, 1><<<ntch, 256, 0, s>>>(c, 0);
-          else if (tg_variant == 2) k_tgather_t<4, 0><<<ntch, 256, 0, s>>>(c, 0);
-          else {
-            if (n_big) { k_tgather_t<4, 1><<<ntch, 256, 0, s>>>(c, n_small ? 1 : 0); if (n_small) n_launch++; }
-            if (n_small) k_tgather_t<4, 0><<<ntch, 256, 0, s>>>(c, n_big ? 2 : 0);
-          }
+          VT_DISPATCH(c.vt,
+            if (tg_variant == 1) k_tgather_t<4, 1, VT><<<ntch, 256, 0, s>>>(c, 0);
+            else if (tg_variant == 2) k_tgather_t<4, 0, VT><<<ntch, 256, 0, s>>>(c, 0);
+            else {
+              if (n_big) { k_tgather_t<4, 1, VT><<<ntch, 256, 0, s>>>(c, n_small ? 1 : 0); if (n_small) n_launch++; }
+              if (n_small) k_tgather_t<4, 0, VT><<<ntch, 256, 0, s>>>(c, n_big ? 2 : 0);
+            });
           n_launch++;
         }
       }
-      else if (nch) { k_scatter<<<nch, 256, 0, s>>>(c); n_launch++; }
+      else if (nch) { VT_DISPATCH(c.vt, k_scatter<VT><<<nch, 256, 0, s>>>(c)); n_launch++; }
       if (profile) e1 = ev();
       allreduce_f64(c.Y, (size_t)c.ystride * hi_slot);
     }
-    if (n_ga && nch) { k_gather<<<nch, 256, 0, s>>>(c); n_launch++; }
+    if (n_ga && nch) { VT_DISPATCH(c.vt, k_gather<VT><<<nch, 256, 0, s>>>(c)); n_launch++; }
     if (profile && n_sc) { e2 = ev(); prof_pairs.push_back({e0, e1, e2}); }
     if (only_spmv) { CK(cudaGetLastError()); return; }
     if (n_mod) { k_ynorm<<<dim3(hi_slot, ny), 256, 0, s>>>(c); n_launch++; }
@@ -535,7 +613,8 @@ struct Engine {
     if (n_mod) {                                                             // local: every rank splits its own cells
       k_partition<<<hi_slot, 1024, 0, s>>>(c); n_launch++;
       if (c.use_t && ntch) {       // ... and the transposed blocks of the splitting nodes (stable, into the other buffer)
-        k_tpart_count<<<ntch, 256, 0, s>>>(c); k_tpart_scan<<<hi_slot, 1024, 0, s>>>(c); k_tpart_scatter<<<ntch, 256, 0, s>>>(c);
+        k_tpart_count<<<ntch, 256, 0, s>>>(c); k_tpart_scan<<<hi_slot, 1024, 0, s>>>(c);
+        VT_DISPATCH(c.vt, k_tpart_scatter<VT><<<ntch, 256, 0, s>>>(c));
         n_launch += 3;
       }
     }
@@ -666,7 +745,7 @@ int tmc_matrix_upload(const tmc_csr* b2, int normalize, int device, tmc_matrix**
   return guarded([&] {
     if (!out) throw TmcError(TMC_ERR_INVALID, "null out");
     tmc_matrix* b = upload(b2, device);
-    try { normalise_dev(b, normalize, nullptr, nullptr, true); } catch (...) { tmc_matrix_free(b); throw; }
+    try { prepare_matrix(b, normalize); } catch (...) { tmc_matrix_free(b); throw; }
     *out = b;
   });
 }
@@ -683,7 +762,7 @@ int tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int6
       b->n_rows_global = n_rows_global > 0 ? n_rows_global : n_rows; b->row_offset = n_rows_global > 0 ? row_offset : 0;
       if (b->row_offset < 0 || b->row_offset + n_rows > b->n_rows_global) throw TmcError(TMC_ERR_INVALID, "row block outside [0, n_rows_global)");
       b->row_ptr = const_cast<int64_t*>(row_ptr_dev); b->col = const_cast<int32_t*>(col_dev); b->val = val_dev;
-      normalise_dev(b, normalize, nullptr, nullptr, true);
+      prepare_matrix(b, normalize);
     } catch (...) { tmc_matrix_free(b); throw; }
     *out = b;
   });
@@ -697,6 +776,10 @@ void tmc_cache_clear(void) {
 void tmc_matrix_free(tmc_matrix* b) {
   if (!b) return;
   retire_workspace(b->ws); b->ws = nullptr;
+  if (b->valc) cudaFree(b->valc);
+  if (b->rrow) cudaFree(b->rrow);
+  if (b->w2col) cudaFree(b->w2col);
+  if (b->invw) cudaFree(b->invw);
   if (b->owns) { cudaFree(b->row_ptr); cudaFree(b->col); cudaFree(b->val); }
   delete b;
 }
@@ -788,7 +871,9 @@ int tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out) {
       double tot = 0; for (auto& p : eng.prof_pairs) { float a = 0; cudaEventElapsedTime(&a, p.a, p.c); tot += a; }
       t.spmv_ms = tot;
     }
-    t.spmv_alg_bytes = 24.0 * (double)t.spmv_pairs_nnz + eng.alg_vec_bytes;
+    const double bv = b->vt == VT_F64 ? 8.0 : (b->vt == VT_U16 ? 2.0 : 0.0);      // b_v of BASELINE.md section 4 as actually stored
+    t.spmv_alg_bytes = 2.0 * (bv + 4.0) * (double)t.spmv_pairs_nnz + eng.alg_vec_bytes;
+    t.value_bytes = (int32_t)bv;
     *out = &ts->t;
   });
 }

@@ -14,6 +14,7 @@
 
 namespace tmc {
 
+enum ValType : int { VT_F64 = 0, VT_U16 = 1, VT_ONE = 2 };
 enum SlotState : int { ST_IDLE = 0, ST_DEG = 1, ST_ORTH0 = 2, ST_LAN = 3, ST_MOD = 4, ST_DONE = 5 };
 enum SlotAction : int { ACT_NONE = 0, ACT_INIT = 1, ACT_NEXT = 2, ACT_RITZ_LABEL = 3, ACT_RITZ_RESTART = 4, ACT_FINISH = 5 };
 
@@ -51,7 +52,11 @@ struct Activation { int slot, begin, end, gsize, node, stop_after, tpar, pad; lo
 
 struct Ctx {
   // matrix B (CSR, rows = cells)
-  const int64_t* row_ptr; const int32_t* col; const double* val;
+  const int64_t* row_ptr; const int32_t* col; const void* val;   // val: double (B itself) | uint16 | absent, see vt
+  int vt;                          // VT_F64: val = B.  VT_U16 / VT_ONE: B = diag(rrow) * A * diag(wcol), A = small integer counts / all ones
+  const double* rrow;              // [n_rows] 1/||row of A diag(w)||  (factored modes)
+  const double* w2col;             // [n_cols] w_j^2
+  const double* invw;              // [n_cols] 1/w_j (0 where w_j = 0)
   int n_rows, n_cols;              // local rows, features
   int64_t row_offset;              // global id of local row 0
   // position-indexed state
@@ -70,7 +75,7 @@ struct Ctx {
   // transposed (column-sorted) per-node copy of B: y = B_S^T x as a gather with run merging instead of nnz atomics
   int use_t;
   int xs_min_rows;                                   // nodes with at least this many local rows read x in the strided mapping
-  int32_t* tcol[2]; int32_t* tpos[2]; double* tval[2];
+  int32_t* tcol[2]; int32_t* tpos[2]; void* tval[2];   // tval element type follows vt
   TChunk* tchunks; int* n_tchunks; int tchunk;       // entries per chunk (multiple of 2048)
   int* tile_cnt; long long* tile_off;                // per chunk: label-1 entries / exclusive prefix inside the node
   int* newpos;                                       // [m] where k_partition moved every position
@@ -84,6 +89,28 @@ struct Ctx {
 
 __device__ __forceinline__ double* slot_scal(const Ctx& c, int slot) { return c.redB + (int64_t)slot * (c.K + 2 + R_NSCAL) + (c.K + 2); }
 __device__ __forceinline__ double* slot_redB(const Ctx& c, int slot) { return c.redB + (int64_t)slot * (c.K + 2 + R_NSCAL); }
+
+// Value access by storage type.  In the factored modes the kernels work with A (raw counts) and the diagonal factors
+// ride on the vectors: xin carries rrow, y is kept as y' = w^2 (A^T xin) so the gather needs no column factor.
+template <int VT> __device__ __forceinline__ double ld_val(const void* base, int64_t k) {
+  if (VT == VT_F64) return __ldg(reinterpret_cast<const double*>(base) + k);
+  if (VT == VT_U16) return (double)__ldg(reinterpret_cast<const unsigned short*>(base) + k);
+  return 1.0;
+}
+template <int VT> __device__ __forceinline__ void ld_val4(const void* base, long long k0, double* t) {   // k0 % 4 == 0
+  if (VT == VT_F64) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(reinterpret_cast<const double*>(base) + k0));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(reinterpret_cast<const double*>(base) + k0 + 2));
+    t[0] = a.x; t[1] = a.y; t[2] = b.x; t[3] = b.y;
+  } else if (VT == VT_U16) {
+    const ushort4 a = __ldg(reinterpret_cast<const ushort4*>(reinterpret_cast<const unsigned short*>(base) + k0));
+    t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w;
+  } else { t[0] = t[1] = t[2] = t[3] = 1.0; }
+}
+template <int VT> __device__ __forceinline__ void st_val(void* base, long long k, double v) {
+  if (VT == VT_F64) reinterpret_cast<double*>(base)[k] = v;
+  else if (VT == VT_U16) reinterpret_cast<unsigned short*>(base)[k] = (unsigned short)v;
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -161,6 +188,47 @@ __global__ void k_row_l2(const int64_t* __restrict__ row_ptr, const int32_t* __r
     double inv = nrm > 0 ? 1.0 / nrm : 0.0;
     for (int64_t k = rs + lane; k < re; k += 32) val[k] *= inv;
   }
+}
+
+// value scan: validity + can the values be stored as small integers / are they all ones?
+// flags: 1 NaN/Inf, 2 negative, 4 column out of range, 8 not an integer <= 65535, 16 not all ones
+__global__ void k_scan_values(const int32_t* __restrict__ col, const double* __restrict__ val, int64_t nnz, int n_cols, int* __restrict__ flags) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int f = 0;
+  for (; i < nnz; i += stride) {
+    const double v = val[i]; const int cj = col[i];
+    if (!(v == v) || isinf(v)) f |= 1;
+    if (v < 0) f |= 2;
+    if (cj < 0 || cj >= n_cols) f |= 4;
+    if (!(v >= 0 && v <= 65535.0 && v == floor(v))) f |= 8;
+    if (v != 1.0) f |= 16;
+  }
+  f = __reduce_or_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+__global__ void k_to_u16(const double* __restrict__ val, unsigned short* __restrict__ out, int64_t nnz) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) out[i] = (unsigned short)val[i];
+}
+// rrow_i = 1 / || (A diag(w))_i ||_2 ; flags zero rows
+__global__ void k_row_factor(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                             const double* __restrict__ w, int n_rows, double* __restrict__ rrow, int* __restrict__ err) {
+  int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+  for (int r = warp; r < n_rows; r += nwarps) {
+    const int64_t rs = row_ptr[r], re = row_ptr[r + 1];
+    double ss = 0.0;
+    for (int64_t k = rs + lane; k < re; k += 32) { const double v = val[k] * (w ? w[col[k]] : 1.0); ss += v * v; }
+    ss = warp_sum(ss);
+    if (lane == 0) { if (!(ss > 0)) { atomicMax(err, 4); rrow[r] = 0.0; } else rrow[r] = 1.0 / sqrt(ss); }
+  }
+}
+__global__ void k_col_factors(const double* __restrict__ w, int n_cols, double* __restrict__ w2, double* __restrict__ invw) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_cols) { const double x = w ? w[j] : 1.0; w2[j] = x * x; invw[j] = x != 0.0 ? 1.0 / x : 0.0; }
 }
 
 // ------------------------------------------------------------------ per-sweep bookkeeping
@@ -305,6 +373,7 @@ __global__ void k_zero_y(Ctx c) {
 
 // ------------------------------------------------------------------ K4 half 1: y_S = B_S^T (xin)   (scatter)
 // xin = D^{-1/2} q_j for Lanczos (so y = C^T q_j), 1 for the degree pass, the 0/1 label for modularity.
+template <int VT>
 __global__ void __launch_bounds__(256) k_scatter(Ctx c) {
   if ((int)blockIdx.x >= *c.n_chunks) return;
   const Chunk ch = c.chunks[blockIdx.x];
@@ -314,17 +383,16 @@ __global__ void __launch_bounds__(256) k_scatter(Ctx c) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = warp; r < ch.len; r += 8) {
     const int p = ch.begin + r;
-    const double xi = (state == ST_DEG) ? 1.0 : c.xin[p];
-    if (xi == 0.0) continue;
     const int row = c.perm[p];
+    const double xi = (state == ST_DEG) ? (VT == VT_F64 ? 1.0 : c.rrow[row]) : c.xin[p];
+    if (xi == 0.0) continue;
     const int64_t rs = c.row_ptr[row], re = c.row_ptr[row + 1];
-    int64_t k = rs + lane;
-    for (; k + 96 < re; k += 128) {
-      int c0 = __ldg(c.col + k), c1 = __ldg(c.col + k + 32), c2 = __ldg(c.col + k + 64), c3 = __ldg(c.col + k + 96);
-      double v0 = __ldg(c.val + k), v1 = __ldg(c.val + k + 32), v2 = __ldg(c.val + k + 64), v3 = __ldg(c.val + k + 96);
-      atomicAdd(y + c0, v0 * xi); atomicAdd(y + c1, v1 * xi); atomicAdd(y + c2, v2 * xi); atomicAdd(y + c3, v3 * xi);
+    for (int64_t k = rs + lane; k < re; k += 32) {
+      const int cj = __ldg(c.col + k);
+      double v = ld_val<VT>(c.val, k) * xi;
+      if (VT != VT_F64) v *= __ldg(c.w2col + cj);
+      atomicAdd(y + cj, v);
     }
-    for (; k < re; k += 32) atomicAdd(y + __ldg(c.col + k), __ldg(c.val + k) * xi);
   }
 }
 
@@ -337,7 +405,7 @@ __device__ __forceinline__ int4 ldg_i4(const int32_t* p) { return __ldg(reinterp
 __device__ __forceinline__ double2 ldg_d2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 // E = consecutive entries per lane (4 or 8); XS = read x in the strided mapping and change mapping through padded smem
-template <int E, int XS>
+template <int E, int XS, int VT>
 __global__ void __launch_bounds__(256) k_tgather_t(Ctx c, int cls) {       // cls: 0 all nodes, 1 only large (>= xs_min_rows), 2 only small
   __shared__ double xs_sm[XS ? 8 : 1][XS ? (32 * E + 2 * E) : 1];
   if ((int)blockIdx.x >= *c.n_tchunks) return;
@@ -350,16 +418,18 @@ __global__ void __launch_bounds__(256) k_tgather_t(Ctx c, int cls) {       // cl
   const int par = s.tpar;
   const int32_t* __restrict__ tcol = par ? c.tcol[1] : c.tcol[0];
   const int32_t* __restrict__ tpos = par ? c.tpos[1] : c.tpos[0];
-  const double* __restrict__ tval = par ? c.tval[1] : c.tval[0];
+  const void* __restrict__ tval = par ? c.tval[1] : c.tval[0];
   const double* __restrict__ xin = c.xin;
   double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long cend = min(ch.begin + (long long)c.tchunk, te);
+  constexpr bool FACT = (VT != VT_F64);
+  const bool use_x = FACT || state != ST_DEG;      // factored: even the degree pass multiplies by xin = rrow
   constexpr int W = 32 * E;                 // entries per warp iteration
   constexpr bool xs_on = (XS == 1);
   for (long long base = ch.begin + warp * W; base < cend; base += 8 * W) {
     double* xs = xs_sm[XS ? warp : 0];
-    if (XS && xs_on && state != ST_DEG) {
+    if (XS && xs_on && use_x) {
       // x = xin[pos] in the STRIDED mapping (entry base + 32e + lane): positions ascend inside a column, so a warp-wide
       // gather touches a few consecutive lines; padded layout i -> i + i/16 is conflict-free for both mappings.
 #pragma unroll
@@ -381,8 +451,8 @@ __global__ void __launch_bounds__(256) k_tgather_t(Ctx c, int cls) {       // cl
         cc[4 * q] = ca.x; cc[4 * q + 1] = ca.y; cc[4 * q + 2] = ca.z; cc[4 * q + 3] = ca.w;
       }
 #pragma unroll
-      for (int q = 0; q < E / 2; ++q) { const double2 v = ldg_d2(tval + k0 + 2 * q); t[2 * q] = v.x; t[2 * q + 1] = v.y; }
-      if (state != ST_DEG) {
+      for (int q = 0; q < E / 4; ++q) ld_val4<VT>(tval, k0 + 4 * q, t + 4 * q);
+      if (use_x) {
         if (XS && xs_on) {
 #pragma unroll
           for (int e = 0; e < E; ++e) { const int i = E * lane + e; t[e] *= xs[i + (i >> 4)]; }
@@ -406,7 +476,7 @@ __global__ void __launch_bounds__(256) k_tgather_t(Ctx c, int cls) {       // cl
 #pragma unroll
       for (int e = 0; e < E; ++e) { cc[e] = -1; t[e] = 0.0; }
     }
-    if (XS && xs_on && state != ST_DEG) __syncwarp();
+    if (XS && xs_on && use_x) __syncwarp();
     // whole warp inside one column?
     const int cfirst = __shfl_sync(0xffffffffu, cc[0], 0);
     const int clast = __shfl_sync(0xffffffffu, cc[E - 1], 31);
@@ -415,16 +485,16 @@ __global__ void __launch_bounds__(256) k_tgather_t(Ctx c, int cls) {       // cl
 #pragma unroll
       for (int e = 0; e < E; ++e) a += t[e];
       a = warp_sum(a);
-      if (lane == 0 && a != 0.0) atomicAdd(y + cfirst, a);
+      if (lane == 0 && a != 0.0) atomicAdd(y + cfirst, FACT ? a * __ldg(c.w2col + cfirst) : a);
       continue;
     }
     double acc = t[0]; int cur = cc[0];
 #pragma unroll
     for (int e = 1; e < E; ++e) {
       if (cc[e] == cur) acc += t[e];
-      else { if (cur >= 0 && acc != 0.0) atomicAdd(y + cur, acc); cur = cc[e]; acc = t[e]; }
+      else { if (cur >= 0 && acc != 0.0) atomicAdd(y + cur, FACT ? acc * __ldg(c.w2col + cur) : acc); cur = cc[e]; acc = t[e]; }
     }
-    if (cur >= 0 && acc != 0.0) atomicAdd(y + cur, acc);
+    if (cur >= 0 && acc != 0.0) atomicAdd(y + cur, FACT ? acc * __ldg(c.w2col + cur) : acc);
   }
 }
 
@@ -443,11 +513,12 @@ __global__ void k_tb_iota(int32_t* __restrict__ p, long long n) {
   const long long st = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += st) p[i] = (int32_t)i;
 }
-__global__ void k_tb_finish_sorted(const int32_t* __restrict__ rowid, const double* __restrict__ val, int32_t* __restrict__ tpos,
-                                   double* __restrict__ tval, long long n) {
+template <int VT>
+__global__ void k_tb_finish_sorted(const int32_t* __restrict__ rowid, const void* __restrict__ val, int32_t* __restrict__ tpos,
+                                   void* __restrict__ tval, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long st = (long long)gridDim.x * blockDim.x;
-  for (; i < n; i += st) { const int32_t e = tpos[i]; tpos[i] = __ldg(rowid + e); tval[i] = __ldg(val + e); }
+  for (; i < n; i += st) { const int32_t e = tpos[i]; tpos[i] = __ldg(rowid + e); st_val<VT>(tval, i, ld_val<VT>(val, e)); }
 }
 
 // ---- building a node's T-block from its CSR rows (root, and the per-node API entry points)
@@ -488,6 +559,7 @@ __global__ void __launch_bounds__(1024) k_tb_scan(Ctx c) {      // exclusive sca
   }
   if (tid == 0) c.tb_colstart[c.n_cols] = carry_s;
 }
+template <int VT>
 __global__ void __launch_bounds__(256) k_tb_fill(Ctx c, int begin, int end, long long tb, int par) {
   const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   const int nw = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
@@ -497,7 +569,7 @@ __global__ void __launch_bounds__(256) k_tb_fill(Ctx c, int begin, int end, long
     for (int64_t k = rs + lane; k < re; k += 32) {
       const int col = __ldg(c.col + k);
       const long long idx = tb + c.tb_colstart[col] + atomicAdd(c.tb_cnt + col, 1);
-      (par ? c.tcol[1] : c.tcol[0])[idx] = col; (par ? c.tpos[1] : c.tpos[0])[idx] = p; (par ? c.tval[1] : c.tval[0])[idx] = __ldg(c.val + k);
+      (par ? c.tcol[1] : c.tcol[0])[idx] = col; (par ? c.tpos[1] : c.tpos[0])[idx] = p; st_val<VT>(par ? c.tval[1] : c.tval[0], idx, ld_val<VT>(c.val, k));
     }
   }
 }
@@ -551,6 +623,7 @@ __global__ void __launch_bounds__(1024) k_tpart_scan(Ctx c) {      // one CTA pe
   }
   if (tid == 0) s.tnnz0 = (s.te - s.tb) - carry_s;
 }
+template <int VT>
 __global__ void __launch_bounds__(256) k_tpart_scatter(Ctx c) {
   __shared__ int wcnt[8];
   __shared__ long long run_s;
@@ -561,9 +634,9 @@ __global__ void __launch_bounds__(256) k_tpart_scatter(Ctx c) {
   const long long tb = s.tb, te = s.te, nnz0 = s.tnnz0;
   const int par = s.tpar;
   const int32_t* __restrict__ scol = par ? c.tcol[1] : c.tcol[0]; const int32_t* __restrict__ spos = par ? c.tpos[1] : c.tpos[0];
-  const double* __restrict__ sval = par ? c.tval[1] : c.tval[0];
+  const void* __restrict__ sval = par ? c.tval[1] : c.tval[0];
   int32_t* __restrict__ dcol = par ? c.tcol[0] : c.tcol[1]; int32_t* __restrict__ dpos = par ? c.tpos[0] : c.tpos[1];
-  double* __restrict__ dval = par ? c.tval[0] : c.tval[1];
+  void* __restrict__ dval = par ? c.tval[0] : c.tval[1];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) run_s = c.tile_off[blockIdx.x];
   __syncthreads();
@@ -574,10 +647,9 @@ __global__ void __launch_bounds__(256) k_tpart_scatter(Ctx c) {
     int mine = 0;
     if (k0 < te && k0 + 8 > tb) {
       const int4 ca = ldg_i4(scol + k0), cb = ldg_i4(scol + k0 + 4), pa = ldg_i4(spos + k0), pb = ldg_i4(spos + k0 + 4);
-      const double2 v0 = ldg_d2(sval + k0), v1 = ldg_d2(sval + k0 + 2), v2 = ldg_d2(sval + k0 + 4), v3 = ldg_d2(sval + k0 + 6);
+      ld_val4<VT>(sval, k0, vv); ld_val4<VT>(sval, k0 + 4, vv + 4);
       cc[0] = ca.x; cc[1] = ca.y; cc[2] = ca.z; cc[3] = ca.w; cc[4] = cb.x; cc[5] = cb.y; cc[6] = cb.z; cc[7] = cb.w;
       pp[0] = pa.x; pp[1] = pa.y; pp[2] = pa.z; pp[3] = pa.w; pp[4] = pb.x; pp[5] = pb.y; pp[6] = pb.z; pp[7] = pb.w;
-      vv[0] = v0.x; vv[1] = v0.y; vv[2] = v1.x; vv[3] = v1.y; vv[4] = v2.x; vv[5] = v2.y; vv[6] = v3.x; vv[7] = v3.y;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const bool ok = (k0 + e >= tb) && (k0 + e < te);
@@ -604,7 +676,7 @@ __global__ void __launch_bounds__(256) k_tpart_scatter(Ctx c) {
       if (ff[e] < 0) continue;
       const long long idx = (k0 + e) - tb;                         // index inside the parent block
       const long long dest = ff[e] ? (tb + nnz0 + ones_before) : (tb + (idx - ones_before));
-      dcol[dest] = cc[e]; dpos[dest] = c.newpos[pp[e]]; dval[dest] = vv[e];
+      dcol[dest] = cc[e]; dpos[dest] = c.newpos[pp[e]]; st_val<VT>(dval, dest, vv[e]);
       ones_before += ff[e];
     }
     __syncthreads();
@@ -618,6 +690,7 @@ __global__ void __launch_bounds__(256) k_tpart_scatter(Ctx c) {
 // dependent y[col] gathers are issued, and the next row's extent prefetched while the current row streams
 // (measured: 4.2 -> 5.4 TB/s on the c2 root against the non-pipelined loop; tools/exp).  y is read through the
 // read-only path (it is not written in this kernel) so the compiler may keep all four chains in flight.
+template <int VT>
 __global__ void __launch_bounds__(256) k_gather(Ctx c) {
   __shared__ double sm8[8];
   if ((int)blockIdx.x >= *c.n_chunks) return;
@@ -626,18 +699,20 @@ __global__ void __launch_bounds__(256) k_gather(Ctx c) {
   if (state != ST_DEG && state != ST_LAN) return;
   const double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride;
   const int32_t* __restrict__ col = c.col;
-  const double* __restrict__ val = c.val;
+  const void* __restrict__ val = c.val;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double dsum = 0.0;
   long long nz = 0;
   int r = warp;
   int64_t rs = 0, re = 0;
-  if (r < ch.len) { const int row = c.perm[ch.begin + r]; rs = c.row_ptr[row]; re = c.row_ptr[row + 1]; }
+  int row_cur = 0;
+  if (r < ch.len) { row_cur = c.perm[ch.begin + r]; rs = c.row_ptr[row_cur]; re = c.row_ptr[row_cur + 1]; }
   while (r < ch.len) {
     const int p = ch.begin + r;
     const int rn = r + 8;
     int64_t nrs = 0, nre = 0;
-    if (rn < ch.len) { const int nrow = c.perm[ch.begin + rn]; nrs = c.row_ptr[nrow]; nre = c.row_ptr[nrow + 1]; }
+    int nrow = 0;
+    if (rn < ch.len) { nrow = c.perm[ch.begin + rn]; nrs = c.row_ptr[nrow]; nre = c.row_ptr[nrow + 1]; }
     nz += re - rs;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int64_t k = rs + lane;
@@ -645,7 +720,7 @@ __global__ void __launch_bounds__(256) k_gather(Ctx c) {
     int c0 = 0, c1 = 0, c2 = 0, c3 = 0; double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
     if (have) {
       c0 = __ldg(col + k); c1 = __ldg(col + k + 32); c2 = __ldg(col + k + 64); c3 = __ldg(col + k + 96);
-      v0 = __ldg(val + k); v1 = __ldg(val + k + 32); v2 = __ldg(val + k + 64); v3 = __ldg(val + k + 96);
+      v0 = ld_val<VT>(val, k); v1 = ld_val<VT>(val, k + 32); v2 = ld_val<VT>(val, k + 64); v3 = ld_val<VT>(val, k + 96);
     }
     while (have) {
       const int64_t kn = k + 128;
@@ -653,19 +728,19 @@ __global__ void __launch_bounds__(256) k_gather(Ctx c) {
       int d0 = 0, d1 = 0, d2 = 0, d3 = 0; double u0 = 0, u1 = 0, u2 = 0, u3 = 0;
       if (have_n) {
         d0 = __ldg(col + kn); d1 = __ldg(col + kn + 32); d2 = __ldg(col + kn + 64); d3 = __ldg(col + kn + 96);
-        u0 = __ldg(val + kn); u1 = __ldg(val + kn + 32); u2 = __ldg(val + kn + 64); u3 = __ldg(val + kn + 96);
+        u0 = ld_val<VT>(val, kn); u1 = ld_val<VT>(val, kn + 32); u2 = ld_val<VT>(val, kn + 64); u3 = ld_val<VT>(val, kn + 96);
       }
       a0 += v0 * __ldg(y + c0); a1 += v1 * __ldg(y + c1); a2 += v2 * __ldg(y + c2); a3 += v3 * __ldg(y + c3);
       c0 = d0; c1 = d1; c2 = d2; c3 = d3; v0 = u0; v1 = u1; v2 = u2; v3 = u3;
       k = kn; have = have_n;
     }
-    for (; k < re; k += 32) a0 += __ldg(val + k) * __ldg(y + __ldg(col + k));
+    for (; k < re; k += 32) a0 += ld_val<VT>(val, k) * __ldg(y + __ldg(col + k));
     const double s = warp_sum((a0 + a1) + (a2 + a3));
     if (lane == 0) {
-      if (state == ST_DEG) { c.d[p] = s; dsum += s; }
+      if (state == ST_DEG) { const double dv = (VT == VT_F64) ? s : s * c.rrow[row_cur]; c.d[p] = dv; dsum += dv; }
       else c.w[p] = c.sdeg[p] * s;
     }
-    r = rn; rs = nrs; re = nre;
+    r = rn; rs = nrs; re = nre; row_cur = nrow;
   }
   if (lane == 0 && nz) atomicAdd(c.stats + (state == ST_DEG ? 1 : 0), (unsigned long long)nz);
   if (state == ST_DEG) {
@@ -682,7 +757,11 @@ __global__ void __launch_bounds__(256) k_ynorm(Ctx c) {
   const double* __restrict__ y = c.Y + (int64_t)slot * c.ystride;
   int lo = (int)((int64_t)c.n_cols * c.rank / c.world), hi = (int)((int64_t)c.n_cols * (c.rank + 1) / c.world);
   double s = 0.0;
-  for (int i = lo + blockIdx.y * blockDim.x + threadIdx.x; i < hi; i += gridDim.y * blockDim.x) { double v = y[i]; s += v * v; }
+  for (int i = lo + blockIdx.y * blockDim.x + threadIdx.x; i < hi; i += gridDim.y * blockDim.x) {
+    double v = y[i];
+    if (c.vt != VT_F64) v *= c.invw[i];            // stored y' = w * y
+    s += v * v;
+  }
   double t = block_sum_256(s, sm8);
   if (threadIdx.x == 0) atomicAdd(slot_scal(c, slot) + R_YNORM2, t);
 }
@@ -862,7 +941,7 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
       const double dd = c.d[p];
       if (!(dd > 0)) atomicMax(c.err, 7);
       const double sq = sqrt(dd);
-      c.sdeg[p] = 1.0 / sq;
+      c.sdeg[p] = (c.vt == VT_F64 ? 1.0 : c.rrow[c.perm[p]]) / sq;      // D^{-1/2} (times the row factor in the factored modes)
       c.V[p] = sq * isd;                                   // V_0 = u1
       c.w[p] = hash_unit(c.seed, (uint64_t)(c.row_offset + c.perm[p]));
     }
@@ -892,7 +971,7 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
     c.u2[p] = u;
     const int lab = (u >= 0.0) ? 1 : 0;                   // spectralCluster sign rule (A6)
     c.label[p] = (uint8_t)lab;
-    c.xin[p] = (double)lab;
+    c.xin[p] = lab ? (c.vt == VT_F64 ? 1.0 : c.rrow[c.perm[p]]) : 0.0;
     n1 += lab; sd1 += lab ? c.d[p] : 0.0;
   }
   if (action == ACT_RITZ_LABEL) {
@@ -968,6 +1047,14 @@ __global__ void k_commit(Ctx c, int n_slots) {
   c.rep[slot] = r;
 }
 
+// factored modes: the degree pass needs xin = rrow on the node's positions
+__global__ void __launch_bounds__(256) k_deg_xin(Ctx c) {
+  if ((int)blockIdx.x >= *c.n_vchunks) return;
+  const Chunk ch = c.vchunks[blockIdx.x];
+  if (c.st[ch.slot].state != ST_DEG) return;
+  for (int i = threadIdx.x; i < ch.len; i += 256) { const int p = ch.begin + i; c.xin[p] = c.rrow[c.perm[p]]; }
+}
+
 // helpers for the fine-grained API
 __global__ void k_iota(int* p, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
 __global__ void k_set_xin_scaled(Ctx c, const double* __restrict__ x, int n) {   // xin = D^{-1/2} x
@@ -977,7 +1064,7 @@ __global__ void k_set_labels(Ctx c, const uint8_t* __restrict__ lab, int n, int 
   __shared__ double sm8[8];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   double n1 = 0.0, sd1 = 0.0;
-  if (i < n) { int l = lab[i] ? 1 : 0; c.label[i] = (uint8_t)l; c.xin[i] = (double)l; n1 = l; sd1 = l ? c.d[i] : 0.0; }
+  if (i < n) { int l = lab[i] ? 1 : 0; c.label[i] = (uint8_t)l; c.xin[i] = l ? (c.vt == VT_F64 ? 1.0 : c.rrow[c.perm[i]]) : 0.0; n1 = l; sd1 = l ? c.d[i] : 0.0; }
   double t = block_sum_256(n1, sm8);
   double t2 = block_sum_256(sd1, sm8);
   if (threadIdx.x == 0) { atomicAdd(slot_scal(c, slot) + R_N1, t); atomicAdd(slot_scal(c, slot) + R_SD1, t2); }

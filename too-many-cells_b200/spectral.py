@@ -265,7 +265,8 @@ def _tree_from_c(tp) -> ClusteringTree:
         q=arr(t.q, n, np.float64), theta=arr(t.theta, n, np.float64), iters=arr(t.iters, n, np.int32),
         item_begin=arr(t.item_begin, n, np.int64), item_end=arr(t.item_end, n, np.int64), perm=arr(t.perm, m, np.int64),
         stats=dict(n_sweeps=int(t.n_sweeps), spmv_pairs_nnz=int(t.spmv_pairs_nnz), kernel_launches=int(t.kernel_launches),
-                   engine_ms=float(t.engine_ms), spmv_ms=float(t.spmv_ms), spmv_alg_bytes=float(t.spmv_alg_bytes)))
+                   engine_ms=float(t.engine_ms), spmv_ms=float(t.spmv_ms), spmv_alg_bytes=float(t.spmv_alg_bytes),
+                   value_bytes=int(t.value_bytes)))
     _lib.load().tmc_tree_free(tp)
     return out
 
