@@ -83,6 +83,7 @@ struct tmc_matrix {
   // with A the caller's small-integer values kept as uint16 (valc) / implicit ones
   int vt = VT_F64;
   void* valc = nullptr; double* rrow = nullptr; double* w2col = nullptr; double* invw = nullptr;
+  size_t fb_cap_nnz = 0; void* fb_valc_spare = nullptr;
   Workspace* ws = nullptr;
 };
 
@@ -269,12 +270,80 @@ static void normalise_dev(tmc_matrix* b, int normalize, double* norm_out_dev, do
   }
 }
 
+// Retired factor buffers of the last matrix (same reason as the workspace cache: cudaFree of GB-sized buffers takes
+// hundreds of ms).  Released by tmc_cache_clear().
+struct FactorBufs { void* valc = nullptr; double* rrow = nullptr; double* w2col = nullptr; double* invw = nullptr;
+                    size_t cap_nnz = 0, cap_rows = 0, cap_cols = 0; int device = -1; };
+static FactorBufs g_fb_cache;
+static void factor_bufs_release(FactorBufs& f) {
+  if (f.valc) cudaFree(f.valc);
+  if (f.rrow) cudaFree(f.rrow);
+  if (f.w2col) cudaFree(f.w2col);
+  if (f.invw) cudaFree(f.invw);
+  f = FactorBufs();
+}
+static void factor_bufs_acquire(tmc_matrix* b, bool need_valc) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  FactorBufs& f = g_fb_cache;
+  const bool fits = f.device == b->device && f.cap_rows >= (size_t)b->n_rows && f.cap_cols >= (size_t)b->n_cols &&
+                    (!need_valc || (f.valc && f.cap_nnz >= (size_t)b->nnz));
+  if (fits) {
+    b->rrow = f.rrow; b->w2col = f.w2col; b->invw = f.invw; b->valc = need_valc ? f.valc : nullptr;
+    b->fb_cap_nnz = f.cap_nnz; b->fb_valc_spare = need_valc ? nullptr : f.valc;
+    f = FactorBufs();
+    return;
+  }
+  b->rrow = dalloc<double>(b->n_rows); b->w2col = dalloc<double>(b->n_cols); b->invw = dalloc<double>(b->n_cols);
+  if (need_valc) { b->valc = dalloc<unsigned short>(b->nnz + 64); b->fb_cap_nnz = b->nnz; }
+}
+static void factor_bufs_retire(tmc_matrix* b) {
+  if (!b->rrow) return;
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  factor_bufs_release(g_fb_cache);
+  g_fb_cache.valc = b->valc ? b->valc : b->fb_valc_spare; g_fb_cache.rrow = b->rrow; g_fb_cache.w2col = b->w2col; g_fb_cache.invw = b->invw;
+  g_fb_cache.cap_nnz = g_fb_cache.valc ? b->fb_cap_nnz : 0; g_fb_cache.cap_rows = b->n_rows; g_fb_cache.cap_cols = b->n_cols;
+  g_fb_cache.device = b->device;
+  b->valc = nullptr; b->rrow = nullptr; b->w2col = nullptr; b->invw = nullptr; b->fb_valc_spare = nullptr;
+}
+
 // Decide the storage mode and compute what the engine needs from the device-resident input values.
 //  * all values are integers in [0, 65535] (raw counts; the usual make-tree input when the engine applies tf-idf itself):
 //    keep A as uint16 (or nothing when every value is 1) and the factors w_j = idf_j (or 1), r_i = 1/||(A diag w)_i||;
 //    the caller's fp64 array is left untouched.
 //  * otherwise: materialise B in place as before (idf scaling if asked, row L2).
+// EXPERIMENT, off by default (TMC_RENUMBER=1): renumber the columns of the device CSR in place by descending global
+// frequency.  It helped a non-pipelined prototype (+10 %) but measured 4 % SLOWER in the product kernels (rows lose
+// their ascending column order, so neighbouring lanes no longer hit neighbouring sectors of y).
+static void renumber_columns(tmc_matrix* b) {
+  if (!getenv("TMC_RENUMBER") || b->nnz == 0) return;
+  const int n = (int)b->n_cols;
+  int* buf = dalloc<int>(4 * (size_t)n + 2);
+  void* tmp = nullptr;
+  try {
+    int* cnt = buf; int* cnt_out = buf + n; int* ids = buf + 2 * n; int* ids_out = buf + 3 * n; int* flags = buf + 4 * n;
+    CK(cudaMemset(buf, 0, sizeof(int) * (4 * (size_t)n + 2)));
+    k_col_hist<<<148 * 8, 256>>>(b->col, b->nnz, n, cnt, flags);
+    if (g_nccl.comm && g_nccl.world > 1) {
+      int r = g_nccl.AllReduce(cnt, cnt, (size_t)n, NCCL_INT32, NCCL_SUM, g_nccl.comm, 0);
+      if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(column counts) failed");
+    }
+    int f = 0; CK(cudaMemcpy(&f, flags, sizeof(int), cudaMemcpyDeviceToHost));
+    if (f) throw TmcError(TMC_ERR_INVALID, "column index out of range");
+    k_iota_i32<<<(n + 255) / 256, 256>>>(ids, n);
+    size_t bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, cnt, cnt_out, ids, ids_out, n));
+    CK(cudaMalloc(&tmp, std::max<size_t>(bytes, 16)));
+    CK(cub::DeviceRadixSort::SortPairsDescending(tmp, bytes, cnt, cnt_out, ids, ids_out, n));
+    k_rank_from_order<<<(n + 255) / 256, 256>>>(ids_out, n, ids);          // ids := rank of every old column id
+    k_remap_cols<<<148 * 8, 256>>>(b->col, b->nnz, ids);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+  } catch (...) { cudaFree(buf); if (tmp) cudaFree(tmp); throw; }
+  cudaFree(buf); cudaFree(tmp);
+}
+
 static void prepare_matrix(tmc_matrix* b, int normalize) {
+  renumber_columns(b);
   int* d_flags = dalloc<int>(2);
   int* df = nullptr; double* idf = nullptr;
   try {
@@ -304,11 +373,10 @@ static void prepare_matrix(tmc_matrix* b, int normalize) {
       }
       k_idf<<<(int)((b->n_cols + 255) / 256), 256>>>(df, (int)b->n_cols, (double)b->n_rows_global, idf);
     }
-    b->rrow = dalloc<double>(b->n_rows); b->w2col = dalloc<double>(b->n_cols); b->invw = dalloc<double>(b->n_cols);
+    factor_bufs_acquire(b, b->vt == VT_U16);
     k_row_factor<<<grid, 256>>>(b->row_ptr, b->col, b->val, idf, (int)b->n_rows, b->rrow, d_flags + 1);
     k_col_factors<<<(int)((b->n_cols + 255) / 256), 256>>>(idf, (int)b->n_cols, b->w2col, b->invw);
     if (b->vt == VT_U16) {
-      b->valc = dalloc<unsigned short>(b->nnz + 64);
       k_to_u16<<<grid, 256>>>(b->val, reinterpret_cast<unsigned short*>(b->valc), b->nnz);
     }
     CK(cudaGetLastError());
@@ -381,6 +449,35 @@ struct Engine {
   double alg_vec_bytes = 0;     // non-matrix part of the spmv_pair algorithmic bytes
   double build_ms = 0;
   int tg_variant = getenv("TMC_TG") ? atoi(getenv("TMC_TG")) : 0;
+  // TMC_DEBUG=2: per-phase device time (CUDA events between the launches of a sweep), printed after the tree build
+  bool phase_prof = getenv("TMC_DEBUG") && atoi(getenv("TMC_DEBUG")) >= 2;
+  enum { PH_PREPARE, PH_ZEROY, PH_TGATHER, PH_AR_Y, PH_GATHER, PH_YNORM, PH_DOTS, PH_AR_COEF, PH_UPDATE, PH_FINISH, PH_ADVANCE,
+         PH_PARTITION, PH_TPART, PH_COMMIT_D2H, PH_N };
+  double phase_ms[PH_N] = {0};
+  std::vector<cudaEvent_t> ph_pool; std::vector<std::pair<cudaEvent_t, int>> ph_marks; size_t ph_used = 0;
+  void mark(int phase) {        // the time since the previous mark is charged to `phase`
+    if (!phase_prof) return;
+    if (ph_used == ph_pool.size()) { cudaEvent_t e; CK(cudaEventCreate(&e)); ph_pool.push_back(e); }
+    cudaEvent_t e = ph_pool[ph_used++];
+    CK(cudaEventRecord(e, s));
+    ph_marks.push_back({e, phase});
+  }
+  void mark_flush() {
+    if (!phase_prof) return;
+    for (size_t i = 1; i < ph_marks.size(); ++i) {
+      float ms = 0; cudaEventElapsedTime(&ms, ph_marks[i - 1].first, ph_marks[i].first);
+      phase_ms[ph_marks[i].second] += ms;
+    }
+    ph_marks.clear(); ph_used = 0;
+  }
+  void phase_report() {
+    if (!phase_prof) return;
+    static const char* nm[PH_N] = {"prepare", "zero_y", "tgather/scatter", "allreduce(Y)", "gather", "ynorm", "dots", "allreduce(coef+scal)",
+                                   "update", "finish", "advance", "partition", "tpart(re-pack)", "commit+D2H"};
+    double tot = 0; for (int i = 0; i < PH_N; ++i) tot += phase_ms[i];
+    fprintf(stderr, "[tmc] rank %d device time by phase (sum %.1f ms over %lld sweeps):\n", c.rank, tot, (long long)n_sweeps);
+    for (int i = 0; i < PH_N; ++i) fprintf(stderr, "[tmc]   %-22s %9.2f ms  %5.1f%%\n", nm[i], phase_ms[i], 100.0 * phase_ms[i] / std::max(tot, 1e-9));
+  }
   bool profile = false;
   std::vector<cudaEvent_t> evs;
 
@@ -400,7 +497,7 @@ struct Engine {
     CK(cudaMemsetAsync(c.err, 0, sizeof(int), s));
     CK(cudaMemsetAsync(c.stats, 0, 4 * sizeof(unsigned long long), s));
   }
-  ~Engine() { for (auto e : evs) cudaEventDestroy(e); }
+  ~Engine() { for (auto e : evs) cudaEventDestroy(e); for (auto e : ph_pool) cudaEventDestroy(e); }
 
   void init_perm(const int64_t* rows, int64_t n_sel) {
     const int m = (int)b->n_rows;
@@ -563,11 +660,14 @@ struct Engine {
       }
       if (ntch > w->tcap) throw TmcError(TMC_ERR_CUDA, "internal: transposed chunk list overflow");
     }
+    mark(PH_COMMIT_D2H);
     k_prepare<<<1, 1024, 0, s>>>(c); n_launch++;
     if (c.vt != VT_F64 && n_deg && nvch) { k_deg_xin<<<nvch, 256, 0, s>>>(c); n_launch++; }
+    mark(PH_PREPARE);
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     if (n_sc) {
       k_zero_y<<<dim3(hi_slot, ny), 256, 0, s>>>(c); n_launch++;
+      mark(PH_ZEROY);
       if (profile) e0 = ev();
       if (c.use_t) {
         if (ntch) {
@@ -583,7 +683,11 @@ struct Engine {
             if (tg_variant == 1) k_tgather_t<4, 1, VT><<<ntch, 256, 0, s>>>(c, 0);
             else if (tg_variant == 2) k_tgather_t<4, 0, VT><<<ntch, 256, 0, s>>>(c, 0);
             else {
-              if (n_big) { k_tgather_t<4, 1, VT><<<ntch, 256, 0, s>>>(c, n_small ? 1 : 0); if (n_small) n_launch++; }
+              if (n_big) {
+                if (tg_variant == 3) k_tgather_t<2, 0, VT><<<ntch, 256, 0, s>>>(c, n_small ? 1 : 0);
+                else k_tgather_t<4, 1, VT><<<ntch, 256, 0, s>>>(c, n_small ? 1 : 0);
+                if (n_small) n_launch++;
+              }
               if (n_small) k_tgather_t<4, 0, VT><<<ntch, 256, 0, s>>>(c, n_big ? 2 : 0);
             });
           n_launch++;
@@ -591,38 +695,51 @@ struct Engine {
       }
       else if (nch) { VT_DISPATCH(c.vt, k_scatter<VT><<<nch, 256, 0, s>>>(c)); n_launch++; }
       if (profile) e1 = ev();
+      mark(PH_TGATHER);
       allreduce_f64(c.Y, (size_t)c.ystride * hi_slot);
+      if (c.world > 1) mark(PH_AR_Y);
     }
     if (n_ga && nch) { VT_DISPATCH(c.vt, k_gather<VT><<<nch, 256, 0, s>>>(c)); n_launch++; }
+    mark(PH_GATHER);
     if (profile && n_sc) { e2 = ev(); prof_pairs.push_back({e0, e1, e2}); }
     if (only_spmv) { CK(cudaGetLastError()); return; }
-    if (n_mod) { k_ynorm<<<dim3(hi_slot, ny), 256, 0, s>>>(c); n_launch++; }
+    if (n_mod) { k_ynorm<<<dim3(hi_slot, ny), 256, 0, s>>>(c); n_launch++; mark(PH_YNORM); }
     const size_t upd_smem = sizeof(double) * ((size_t)c.K + 2 + 8 * (size_t)RV);
     // kernels depend on this rank's rows, collectives only on the (rank-identical) slot states.
     // Three all-reduces per sweep: Y above, the pass-0 coefficients, and the pass-1 coefficients + every scalar.
     if (n_or) {
       if (nvch) { k_dots<<<nvch, 256, 0, s>>>(c, 0); n_launch++; }
+      mark(PH_DOTS);
       allreduce_f64(c.redA, (size_t)(c.K + 2) * hi_slot);
+      if (c.world > 1) mark(PH_AR_COEF);
       if (nvch) { k_update<<<nvch, 256, upd_smem, s>>>(c, 0); n_launch++; }
+      mark(PH_UPDATE);
       if (nvch) { k_dots<<<nvch, 256, 0, s>>>(c, 1); n_launch++; }
+      mark(PH_DOTS);
     }
     allreduce_f64(c.redB, (size_t)(c.K + 2 + R_NSCAL) * hi_slot);
-    if (n_or && nvch) { k_update<<<nvch, 256, upd_smem, s>>>(c, 1); n_launch++; }
+    if (c.world > 1) mark(PH_AR_COEF);
+    if (n_or && nvch) { k_update<<<nvch, 256, upd_smem, s>>>(c, 1); n_launch++; mark(PH_UPDATE); }
     k_finish<<<(hi_slot * 32 + 255) / 256, 256, 0, s>>>(c); n_launch++;
-    if (nvch) { k_advance<<<nvch, 256, 0, s>>>(c); n_launch++; }
+    mark(PH_FINISH);
+    if (nvch) { k_advance<<<nvch, 256, 0, s>>>(c); n_launch++; mark(PH_ADVANCE); }
     if (n_mod) {                                                             // local: every rank splits its own cells
       k_partition<<<hi_slot, 1024, 0, s>>>(c); n_launch++;
+      mark(PH_PARTITION);
       if (c.use_t && ntch) {       // ... and the transposed blocks of the splitting nodes (stable, into the other buffer)
         k_tpart_count<<<ntch, 256, 0, s>>>(c); k_tpart_scan<<<hi_slot, 1024, 0, s>>>(c);
         VT_DISPATCH(c.vt, k_tpart_scatter<VT><<<ntch, 256, 0, s>>>(c));
         n_launch += 3;
+        mark(PH_TPART);
       }
     }
     k_commit<<<(hi_slot + 127) / 128, 128, 0, s>>>(c, hi_slot); n_launch++;
     CK(cudaMemcpyAsync(w->h_rep, c.rep, sizeof(Report) * hi_slot, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(w->h_err, c.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    mark(PH_COMMIT_D2H);
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
+    mark_flush();
     n_sweeps++;
     if (*w->h_err) { std::string msg; int st = err_to_status(*w->h_err, &msg); throw TmcError(st, msg); }
   }
@@ -771,15 +888,13 @@ int tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int6
 void tmc_cache_clear(void) {
   std::lock_guard<std::mutex> lk(g_cache_mu);
   delete g_ws_cache; g_ws_cache = nullptr;
+  factor_bufs_release(g_fb_cache);
 }
 
 void tmc_matrix_free(tmc_matrix* b) {
   if (!b) return;
   retire_workspace(b->ws); b->ws = nullptr;
-  if (b->valc) cudaFree(b->valc);
-  if (b->rrow) cudaFree(b->rrow);
-  if (b->w2col) cudaFree(b->w2col);
-  if (b->invw) cudaFree(b->invw);
+  factor_bufs_retire(b);
   if (b->owns) { cudaFree(b->row_ptr); cudaFree(b->col); cudaFree(b->val); }
   delete b;
 }
@@ -805,6 +920,7 @@ int tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out) {
     eng.init_perm(nullptr, 0);
     eng.run_tree();
     CK(cudaEventRecord(t1, eng.s));
+    eng.phase_report();
     if (dbg) fprintf(stderr, "[tmc] run_tree wall %.2f ms (block build %.2f ms), sweeps %lld, nodes %zu\n", now() - w0, eng.build_ms,
                      (long long)eng.n_sweeps, eng.nodes.size());
     const int m = (int)b->n_rows;

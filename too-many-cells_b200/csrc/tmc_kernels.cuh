@@ -107,6 +107,29 @@ template <int VT> __device__ __forceinline__ void ld_val4(const void* base, long
     t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w;
   } else { t[0] = t[1] = t[2] = t[3] = 1.0; }
 }
+template <int VT> __device__ __forceinline__ void ld_val2(const void* base, long long k0, double* t) {   // k0 % 2 == 0
+  if (VT == VT_F64) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(reinterpret_cast<const double*>(base) + k0));
+    t[0] = a.x; t[1] = a.y;
+  } else if (VT == VT_U16) {
+    const ushort2 a = __ldg(reinterpret_cast<const ushort2*>(reinterpret_cast<const unsigned short*>(base) + k0));
+    t[0] = a.x; t[1] = a.y;
+  } else { t[0] = t[1] = 1.0; }
+}
+template <int E> __device__ __forceinline__ void ld_idx(const int32_t* p, int* out) {     // E consecutive int32, p aligned to E*4 bytes
+  if (E == 2) { const int2 a = __ldg(reinterpret_cast<const int2*>(p)); out[0] = a.x; out[1] = a.y; }
+  else {
+#pragma unroll
+    for (int q = 0; q < E / 4; ++q) { const int4 a = __ldg(reinterpret_cast<const int4*>(p) + q); out[4 * q] = a.x; out[4 * q + 1] = a.y; out[4 * q + 2] = a.z; out[4 * q + 3] = a.w; }
+  }
+}
+template <int E, int VT> __device__ __forceinline__ void ld_vals(const void* base, long long k0, double* t) {
+  if (E == 2) ld_val2<VT>(base, k0, t);
+  else {
+#pragma unroll
+    for (int q = 0; q < E / 4; ++q) ld_val4<VT>(base, k0 + 4 * q, t + 4 * q);
+  }
+}
 template <int VT> __device__ __forceinline__ void st_val(void* base, long long k, double v) {
   if (VT == VT_F64) reinterpret_cast<double*>(base)[k] = v;
   else if (VT == VT_U16) reinterpret_cast<unsigned short*>(base)[k] = (unsigned short)v;
@@ -188,6 +211,23 @@ __global__ void k_row_l2(const int64_t* __restrict__ row_ptr, const int32_t* __r
     double inv = nrm > 0 ? 1.0 / nrm : 0.0;
     for (int64_t k = rs + lane; k < re; k += 32) val[k] *= inv;
   }
+}
+
+// column renumbering by descending frequency: the hot part of every feature-dimension vector (y, w^2, 1/w) becomes a
+// compact prefix, which is what the L1 sees in the gathers (measured +10 % on k_gather, tools/exp/run_exp3.py)
+__global__ void k_col_hist(const int32_t* __restrict__ col, int64_t nnz, int n_cols, int* __restrict__ cnt, int* __restrict__ flags) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) { const int cj = col[i]; if (cj < 0 || cj >= n_cols) atomicOr(flags, 4); else atomicAdd(cnt + cj, 1); }
+}
+__global__ void k_iota_i32(int* __restrict__ p, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
+__global__ void k_rank_from_order(const int* __restrict__ order, int n, int* __restrict__ rank) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) rank[order[i]] = i;
+}
+__global__ void k_remap_cols(int32_t* __restrict__ col, int64_t nnz, const int* __restrict__ rank) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) col[i] = __ldg(rank + col[i]);
 }
 
 // value scan: validity + can the values be stored as small integers / are they all ones?
@@ -445,24 +485,15 @@ __global__ void __launch_bounds__(256) k_tgather_t(Ctx c, int cls) {       // cl
     const long long k0 = base + lane * E;
     int cc[E]; double t[E];
     if (k0 < te && k0 + E > tb) {
-#pragma unroll
-      for (int q = 0; q < E / 4; ++q) {
-        const int4 ca = ldg_i4(tcol + k0 + 4 * q);
-        cc[4 * q] = ca.x; cc[4 * q + 1] = ca.y; cc[4 * q + 2] = ca.z; cc[4 * q + 3] = ca.w;
-      }
-#pragma unroll
-      for (int q = 0; q < E / 4; ++q) ld_val4<VT>(tval, k0 + 4 * q, t + 4 * q);
+      ld_idx<E>(tcol + k0, cc);
+      ld_vals<E, VT>(tval, k0, t);
       if (use_x) {
         if (XS && xs_on) {
 #pragma unroll
           for (int e = 0; e < E; ++e) { const int i = E * lane + e; t[e] *= xs[i + (i >> 4)]; }
         } else {
           int pp[E];
-#pragma unroll
-          for (int q = 0; q < E / 4; ++q) {
-            const int4 pa = ldg_i4(tpos + k0 + 4 * q);
-            pp[4 * q] = pa.x; pp[4 * q + 1] = pa.y; pp[4 * q + 2] = pa.z; pp[4 * q + 3] = pa.w;
-          }
+          ld_idx<E>(tpos + k0, pp);
 #pragma unroll
           for (int e = 0; e < E; ++e) {
             const bool ok = (k0 + e >= tb) && (k0 + e < te);
@@ -625,8 +656,14 @@ __global__ void __launch_bounds__(1024) k_tpart_scan(Ctx c) {      // one CTA pe
 }
 template <int VT>
 __global__ void __launch_bounds__(256) k_tpart_scatter(Ctx c) {
+  // Every 2048-entry tile is staged in shared memory in DESTINATION order ([label-0 run | label-1 run]) and then
+  // written out as two contiguous, fully coalesced segments (the direct per-thread stores wrote 4 bytes into 32
+  // different sectors per instruction: 3.4x the ideal time on c3).
   __shared__ int wcnt[8];
   __shared__ long long run_s;
+  __shared__ int s_col[2048], s_pos[2048];
+  __shared__ double s_val[VT == VT_F64 ? 2048 : 1];
+  __shared__ unsigned short s_v16[VT == VT_U16 ? 2048 : 1];
   if ((int)blockIdx.x >= *c.n_tchunks) return;
   const TChunk ch = c.tchunks[blockIdx.x];
   const Slot& s = c.st[ch.slot];
@@ -669,17 +706,30 @@ __global__ void __launch_bounds__(256) k_tpart_scatter(Ctx c) {
     int wbase = 0, tot = 0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) { const int w = wcnt[q]; if (q < wid) wbase += w; tot += w; }
-    const long long run = run_s;
-    long long ones_before = run + wbase + incl - mine;
+    const long long run = run_s;                                 // label-1 entries of the node before this tile
+    const long long lo = max(base, tb), hi = min(base + 2048, te);
+    const int nvalid = (int)(hi - lo);                           // valid entries of the tile form one contiguous index range
+    const int nz = nvalid - tot;                                 // label-0 entries of the tile
+    int ones_local = wbase + incl - mine;                        // label-1 entries of the tile before this thread's
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       if (ff[e] < 0) continue;
-      const long long idx = (k0 + e) - tb;                         // index inside the parent block
-      const long long dest = ff[e] ? (tb + nnz0 + ones_before) : (tb + (idx - ones_before));
-      dcol[dest] = cc[e]; dpos[dest] = c.newpos[pp[e]]; st_val<VT>(dval, dest, vv[e]);
-      ones_before += ff[e];
+      const int idx_t = (int)((k0 + e) - lo);                    // index inside the tile's valid range
+      const int si = ff[e] ? (nz + ones_local) : (idx_t - ones_local);
+      s_col[si] = cc[e]; s_pos[si] = c.newpos[pp[e]];
+      if (VT == VT_F64) s_val[si] = vv[e];
+      if (VT == VT_U16) s_v16[si] = (unsigned short)vv[e];
+      ones_local += ff[e];
     }
     __syncthreads();
+    const long long z0 = tb + ((lo - tb) - run);                 // destination of the tile's first label-0 entry
+    const long long o0 = tb + nnz0 + run;                        // ... and of its first label-1 entry
+    for (int i = tid; i < nvalid; i += 256) {
+      const long long dest = (i < nz) ? (z0 + i) : (o0 + (i - nz));
+      dcol[dest] = s_col[i]; dpos[dest] = s_pos[i];
+      if (VT == VT_F64) reinterpret_cast<double*>(dval)[dest] = s_val[i];
+      if (VT == VT_U16) reinterpret_cast<unsigned short*>(dval)[dest] = s_v16[i];
+    }
     if (tid == 0) run_s = run + tot;
     __syncthreads();
   }
@@ -690,8 +740,13 @@ __global__ void __launch_bounds__(256) k_tpart_scatter(Ctx c) {
 // dependent y[col] gathers are issued, and the next row's extent prefetched while the current row streams
 // (measured: 4.2 -> 5.4 TB/s on the c2 root against the non-pipelined loop; tools/exp).  y is read through the
 // read-only path (it is not written in this kernel) so the compiler may keep all four chains in flight.
+#ifdef TMC_GATHER_MINB
+#define TMC_GATHER_LB __launch_bounds__(256, TMC_GATHER_MINB)
+#else
+#define TMC_GATHER_LB __launch_bounds__(256)
+#endif
 template <int VT>
-__global__ void __launch_bounds__(256) k_gather(Ctx c) {
+__global__ void TMC_GATHER_LB k_gather(Ctx c) {
   __shared__ double sm8[8];
   if ((int)blockIdx.x >= *c.n_chunks) return;
   const Chunk ch = c.chunks[blockIdx.x];

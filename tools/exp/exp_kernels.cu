@@ -228,3 +228,63 @@ extern "C" void exp_tcoo_v8(int mode, const int* ccol, const int* cpos, const do
   else if (mode == 1) t_coo_v8<1><<<grid, 256>>>(ccol, cpos, cval, x, y, nnz);
   else t_coo_v8<2><<<grid, 256>>>(ccol, cpos, cval, x, y, nnz);
 }
+
+// gather with the hot part of y (columns renumbered by descending frequency, ids < H) staged in shared memory
+template <int NT>
+__global__ void __launch_bounds__(NT) g_smem(const int64_t* __restrict__ rp, const int* __restrict__ col, const unsigned short* __restrict__ val,
+                                             const int* __restrict__ perm, const double* __restrict__ y, double* __restrict__ w, int n_rows,
+                                             int rows_per_cta, int H) {
+  extern __shared__ double ys[];
+  for (int i = threadIdx.x; i < H; i += NT) ys[i] = y[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = NT / 32;
+  const int r0 = blockIdx.x * rows_per_cta;
+  for (int r = warp; r < rows_per_cta; r += nw) {
+    int p = r0 + r; if (p >= n_rows) break;
+    int row = perm[p];
+    int64_t rs = rp[row], re = rp[row + 1];
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int64_t k = rs + lane;
+    for (; k + 96 < re; k += 128) {
+      int c0 = __ldg(col + k), c1 = __ldg(col + k + 32), c2 = __ldg(col + k + 64), c3 = __ldg(col + k + 96);
+      double v0 = __ldg(val + k), v1 = __ldg(val + k + 32), v2 = __ldg(val + k + 64), v3 = __ldg(val + k + 96);
+      a0 += v0 * (c0 < H ? ys[c0] : __ldg(y + c0)); a1 += v1 * (c1 < H ? ys[c1] : __ldg(y + c1));
+      a2 += v2 * (c2 < H ? ys[c2] : __ldg(y + c2)); a3 += v3 * (c3 < H ? ys[c3] : __ldg(y + c3));
+    }
+    for (; k < re; k += 32) { int c0 = __ldg(col + k); a0 += (double)__ldg(val + k) * (c0 < H ? ys[c0] : __ldg(y + c0)); }
+    double s = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) w[p] = s;
+  }
+}
+// baseline with u16 values (same structure, no smem)
+__global__ void __launch_bounds__(256) g_u16(const int64_t* __restrict__ rp, const int* __restrict__ col, const unsigned short* __restrict__ val,
+                                            const int* __restrict__ perm, const double* __restrict__ y, double* __restrict__ w, int n_rows, int rows_per_cta) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * rows_per_cta;
+  for (int r = warp; r < rows_per_cta; r += 8) {
+    int p = r0 + r; if (p >= n_rows) break;
+    int row = perm[p];
+    int64_t rs = rp[row], re = rp[row + 1];
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int64_t k = rs + lane;
+    for (; k + 96 < re; k += 128) {
+      int c0 = __ldg(col + k), c1 = __ldg(col + k + 32), c2 = __ldg(col + k + 64), c3 = __ldg(col + k + 96);
+      double v0 = __ldg(val + k), v1 = __ldg(val + k + 32), v2 = __ldg(val + k + 64), v3 = __ldg(val + k + 96);
+      a0 += v0 * __ldg(y + c0); a1 += v1 * __ldg(y + c1); a2 += v2 * __ldg(y + c2); a3 += v3 * __ldg(y + c3);
+    }
+    for (; k < re; k += 32) a0 += (double)__ldg(val + k) * __ldg(y + __ldg(col + k));
+    double s = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) w[p] = s;
+  }
+}
+extern "C" void exp_gather_smem(int nt, const int64_t* rp, const int* col, const unsigned short* val, const int* perm, const double* y, double* w,
+                                int n_rows, int rpc, int H) {
+  size_t sm = (size_t)H * 8;
+  int grid = (n_rows + rpc - 1) / rpc;
+  if (nt == 1024) { cudaFuncSetAttribute(g_smem<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); g_smem<1024><<<grid, 1024, sm>>>(rp, col, val, perm, y, w, n_rows, rpc, H); }
+  else if (nt == 512) { cudaFuncSetAttribute(g_smem<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); g_smem<512><<<grid, 512, sm>>>(rp, col, val, perm, y, w, n_rows, rpc, H); }
+  else { cudaFuncSetAttribute(g_smem<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); g_smem<256><<<grid, 256, sm>>>(rp, col, val, perm, y, w, n_rows, rpc, H); }
+}
+extern "C" void exp_gather_u16(const int64_t* rp, const int* col, const unsigned short* val, const int* perm, const double* y, double* w, int n_rows, int rpc) {
+  g_u16<<<(n_rows + rpc - 1) / rpc, 256>>>(rp, col, val, perm, y, w, n_rows, rpc);
+}
