@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("TMC_BENCH_WORKLOAD", "c3"))
-    ap.add_argument("--cpu-sample-cells", type=int, default=2500)
+    ap.add_argument("--cpu-sample-cells", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -97,13 +97,14 @@ class ClockSampler:
 
 
 def cpu_reference_run(name, sample_cells, steps=1, warmup=0):
-    """The oracle's CPU make-tree on a bounded sample (first `sample_cells` cells of the workload).
-    Returns (ms per sample tree, work rate nnz-passes/s, description)."""
+    """The reference's CPU execution of the path, restated in C (oracle/tmc_port.c: one node at a time, materialised
+    sub-matrices, single-vector Lanczos at SVDLIBC's kappa = 1e-6, one core like the reference), timed on a bounded sample
+    (the first `sample_cells` cells of the workload) and scaled linearly in cells to the metric's unit.
+    Returns (scaled ms per full-size tree, sample cells, sample nnz, description)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
     import scipy.sparse as sp
     from too_many_cells_b200 import synth
-    import tmc_oracle as O
+    import tmc_port as P
     n, g, k, d, s, binary = synth.CONFIGS[name]
     ns = min(n, sample_cells)
     ip, ix, dv, _ = synth.synth_counts(ns, g, k, d, s, binary)
@@ -111,15 +112,16 @@ def cpu_reference_run(name, sample_cells, steps=1, warmup=0):
     times = []
     for it in range(warmup + steps):
         t = time.perf_counter()
-        tr = O.hierarchical_spectral_cluster(a, normalize=True)
+        tr = P.make_tree(a, normalize=True, tol=1e-6)
         dt = time.perf_counter() - t
         if it >= warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     scale = n / ns
-    desc = (f"oracle port (numpy/scipy LAPACK+ARPACK, exact eigen-solve; the Haskell reference cannot be built here) make-tree on "
-            f"the first {ns} cells x {g} genes of {name} ({a.nnz} nnz, {tr.n_nodes} nodes): {ms:.0f} ms measured, scaled x{scale:.0f} "
-            f"linearly in cells to the full workload (conservative: the full tree is deeper, so cost per cell is higher)")
+    desc = (f"C port of the reference's CPU path (oracle/tmc_port.c: sequential recursion, per-node materialised matrices, "
+            f"Lanczos at las2's kappa=1e-6, 1 thread like the reference; the Haskell binary cannot be built here) on the first "
+            f"{ns} cells x {g} genes of {name} ({a.nnz} nnz, {tr.n_nodes} nodes, {tr.steps} Lanczos steps): {ms:.0f} ms measured, "
+            f"scaled x{scale:.0f} linearly in cells to the full workload (conservative: the full tree is deeper)")
     return ms * scale, ns, a.nnz, desc
 
 
@@ -134,7 +136,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        ncores = os.cpu_count() or 1
+        ncores = 1          # the reference path is sequential; the port uses one thread
         ms, ns, nnz, desc = cpu_reference_run(name, args.cpu_sample_cells, steps=max(1, args.steps), warmup=min(args.warmup, 1))
         line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -275,7 +277,7 @@ def main():
                      "lanczos_steps": int(tr.iters.sum()), "engine_ms_last": tr.stats["engine_ms"], "gen_s": gen_s}}
     if not args.no_cpu_baseline:
         ms_c, ns, nnz_c, desc = cpu_reference_run(name, args.cpu_sample_cells)
-        line["cpu_baseline"] = {"value": ms_c, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc}
+        line["cpu_baseline"] = {"value": ms_c, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
     print(json.dumps(line))
     if world > 1:
         tdist.destroy_comm()

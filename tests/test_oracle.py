@@ -98,3 +98,16 @@ def test_zero_row_is_an_error():
     a = sp.csr_matrix(np.array([[1.0, 2.0], [0.0, 0.0], [3.0, 1.0]]))
     with pytest.raises(ValueError):
         O.hierarchical_spectral_cluster(a)
+
+
+def test_c_port_agrees_with_python_oracle(golden_tiny, golden_small):
+    """Two independent restatements (numpy/LAPACK exact solve vs the C Lanczos port that bench.py times) give the same trees."""
+    import tmc_port as P
+    for (a, z), tol in ((golden_tiny, 1e-10), (golden_small, 1e-6)):
+        pt = P.make_tree(a, normalize=True, tol=tol)
+        gold = {}
+        for r, l in enumerate(z["leaf_of_row"]):
+            gold.setdefault(int(l), []).append(r)
+        assert pt.leaf_sets() == sorted(tuple(v) for v in gold.values())
+        assert pt.n_nodes == z["left"].size
+        assert abs(pt.q[0] - z["q"][0]) < 1e-7
