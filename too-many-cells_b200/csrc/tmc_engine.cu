@@ -52,6 +52,7 @@ struct Nccl {
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
@@ -64,8 +65,9 @@ struct Nccl {
     CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    Broadcast = (decltype(Broadcast))dlsym(lib, "ncclBroadcast");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-    return GetUniqueId && CommInitRank && CommDestroy && AllReduce;
+    return GetUniqueId && CommInitRank && CommDestroy && AllReduce && Broadcast;
   }
 };
 static Nccl g_nccl;
@@ -76,6 +78,9 @@ struct Workspace;
 struct tmc_matrix {
   int64_t n_rows = 0, n_cols = 0, nnz = 0;   // n_rows = rows owned by this rank
   int64_t row_offset = 0, n_rows_global = 0; // static row-block ownership across ranks
+  // replicated mode: every rank holds ALL rows (n_rows == n_rows_global) and owns the block [own_lo, own_hi) for the shared
+  // top of the tree; small subtrees are handed to single ranks (no collectives below the hand-off size)
+  bool replicated = false; int64_t own_lo = 0, own_hi = 0;
   int64_t* row_ptr = nullptr; int32_t* col = nullptr; double* val = nullptr;
   bool owns = false;
   int device = 0;
@@ -106,7 +111,7 @@ struct Workspace {
   Ctx c{};
   int K = 0, max_active = 0, use_t = 0, tcap = 0, device = 0, vt = 0;
   int32_t* rowid_scratch = nullptr;
-  int64_t m = 0, cap_m = 0, cap_nnz = 0, cap_cols = 0;
+  int64_t m = 0, cap_m = 0, cap_nnz = 0, cap_cols = 0, tn = 0;
   Report* h_rep = nullptr; Activation* h_act = nullptr; Activation* d_act = nullptr;
   int* h_err = nullptr; unsigned long long* h_stats = nullptr;
   cudaStream_t stream = nullptr;
@@ -144,13 +149,15 @@ static void bind_workspace(Workspace* w, tmc_matrix* b) {
   c.row_ptr = b->row_ptr; c.col = b->col; c.val = (b->vt == VT_F64) ? (const void*)b->val : (const void*)b->valc;
   c.vt = b->vt; c.rrow = b->rrow; c.w2col = b->w2col; c.invw = b->invw;
   c.n_rows = (int)b->n_rows; c.n_cols = (int)b->n_cols; c.row_offset = b->row_offset;
-  c.vstride = (b->n_rows + 15) / 16 * 16;
+  const int64_t mpos = b->replicated ? (b->own_hi - b->own_lo) + b->n_rows : b->n_rows;
+  c.vstride = (mpos + 15) / 16 * 16;
   c.ystride = (b->n_cols + 15) / 16 * 16;
-  w->m = b->n_rows;
+  w->m = mpos;
 }
 
 static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
-  const int64_t m = b->n_rows;
+  // positions: own rows, plus (replicated mode) room for every row that may be handed to this rank as a private subtree
+  const int64_t m = b->replicated ? (b->own_hi - b->own_lo) + b->n_rows : b->n_rows;
   int K = std::max(2, (int)std::min<int64_t>(o.max_lanczos > 0 ? o.max_lanczos : 320, b->n_rows_global));
   int max_active = (int)std::min<int64_t>(std::max<int64_t>(1, b->n_rows_global / 2), o.max_active > 0 ? o.max_active : 2048);
   max_active = std::min(max_active, 4096);
@@ -161,7 +168,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     std::lock_guard<std::mutex> lk(g_cache_mu);
     Workspace* q = g_ws_cache;
     if (q && q->device == b->device && q->K == K && q->max_active == max_active && q->use_t == use_t && q->vt == b->vt && q->cap_m >= m &&
-        q->cap_nnz >= b->nnz && q->cap_cols >= b->n_cols) {
+        q->cap_nnz >= b->nnz && q->cap_cols >= b->n_cols && (!use_t || q->tn >= b->nnz + (b->replicated ? b->nnz / std::max(1, g_nccl.world) + b->nnz / 16 + 65536 : 0) + 4096)) {
       g_ws_cache = nullptr;
       bind_workspace(q, b);
       b->ws = q;
@@ -171,7 +178,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
   Workspace* w = new Workspace();
   try {
     w->K = K; w->max_active = max_active; w->use_t = use_t; w->device = b->device; w->vt = b->vt;
-    w->cap_m = m; w->cap_nnz = b->nnz; w->cap_cols = b->n_cols;
+    w->cap_m = m; w->cap_nnz = b->nnz; w->cap_cols = b->n_cols; w->tn = 0;
     CK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     Ctx& c = w->c;
     bind_workspace(w, b);
@@ -194,8 +201,10 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     w->d_act = w->A<Activation>(max_active);
     c.use_t = use_t;
     if (c.use_t) {      // transposed per-node blocks, double buffered (children are written to the other buffer)
-      const size_t tn = (size_t)b->nnz + 4096;
+      const int64_t own_nnz_est = b->replicated ? b->nnz / std::max(1, g_nccl.world) + b->nnz / 16 + 65536 : 0;
+      const size_t tn = (size_t)b->nnz + (size_t)own_nnz_est + 4096;      // replicated: own block + every handed-off block
       const size_t vsz = b->vt == VT_F64 ? 8 : (b->vt == VT_U16 ? 2 : 0);
+      w->tn = (int64_t)tn;
       for (int q = 0; q < 2; ++q) { c.tcol[q] = w->A<int32_t>(tn); c.tpos[q] = w->A<int32_t>(tn); c.tval[q] = w->A<char>(tn * vsz + 64); }
       w->rowid_scratch = w->A<int32_t>(tn);
       w->tcap = 32768 + max_active + 64;
@@ -244,7 +253,7 @@ static void normalise_dev(tmc_matrix* b, int normalize, double* norm_out_dev, do
       df = dalloc<int>(b->n_cols); idf = idf_out_dev ? idf_out_dev : dalloc<double>(b->n_cols);
       CK(cudaMemset(df, 0, sizeof(int) * b->n_cols));
       k_df_count<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, df, d_err);
-      if (g_nccl.comm && g_nccl.world > 1) {      // df over all ranks' row blocks
+      if (g_nccl.comm && g_nccl.world > 1 && !b->replicated) {      // df over all ranks' row blocks
         int r = g_nccl.AllReduce(df, df, (size_t)b->n_cols, NCCL_INT32, NCCL_SUM, g_nccl.comm, 0);
         if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(df) failed");
       }
@@ -323,7 +332,7 @@ static void renumber_columns(tmc_matrix* b) {
     int* cnt = buf; int* cnt_out = buf + n; int* ids = buf + 2 * n; int* ids_out = buf + 3 * n; int* flags = buf + 4 * n;
     CK(cudaMemset(buf, 0, sizeof(int) * (4 * (size_t)n + 2)));
     k_col_hist<<<148 * 8, 256>>>(b->col, b->nnz, n, cnt, flags);
-    if (g_nccl.comm && g_nccl.world > 1) {
+    if (g_nccl.comm && g_nccl.world > 1 && !b->replicated) {
       int r = g_nccl.AllReduce(cnt, cnt, (size_t)n, NCCL_INT32, NCCL_SUM, g_nccl.comm, 0);
       if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(column counts) failed");
     }
@@ -367,7 +376,7 @@ static void prepare_matrix(tmc_matrix* b, int normalize) {
       df = dalloc<int>(b->n_cols); idf = dalloc<double>(b->n_cols);
       CK(cudaMemset(df, 0, sizeof(int) * b->n_cols));
       k_df_count<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, df, d_flags + 1);
-      if (g_nccl.comm && g_nccl.world > 1) {
+      if (g_nccl.comm && g_nccl.world > 1 && !b->replicated) {
         int r = g_nccl.AllReduce(df, df, (size_t)b->n_cols, NCCL_INT32, NCCL_SUM, g_nccl.comm, 0);
         if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(df) failed");
       }
@@ -413,10 +422,33 @@ static tmc_matrix* upload(const tmc_csr* a, int device) {
     b->device = pick_device(device);
     const int world = g_nccl.comm ? g_nccl.world : 1, rank = g_nccl.comm ? g_nccl.rank : 0;
     const bool is_block = a->n_rows_global != 0 && a->n_rows_global != a->n_rows;
+    const bool replicate = !is_block && world > 1 && getenv("TMC_NO_HANDOFF") == nullptr;
     int64_t lo = 0, hi = a->n_rows;
     b->n_rows_global = is_block ? a->n_rows_global : a->n_rows;
     b->row_offset = is_block ? a->row_offset : 0;
     if (!is_block && world > 1) { lo = a->n_rows * rank / world; hi = a->n_rows * (rank + 1) / world; b->row_offset = lo; }
+    if (replicate) {
+      // every rank uploads only its own row block over PCIe; the blocks are then exchanged over NVLink (ncclBroadcast per
+      // owner) so that every rank ends up with the whole matrix
+      b->replicated = true; b->own_lo = lo; b->own_hi = hi; b->row_offset = 0;
+      b->n_rows = a->n_rows; b->n_cols = a->n_cols; b->nnz = a->nnz; b->owns = true;
+      b->row_ptr = dalloc<int64_t>(b->n_rows + 1); b->col = dalloc<int32_t>(b->nnz); b->val = dalloc<double>(b->nnz);
+      CK(cudaMemcpy(b->row_ptr, a->row_ptr, sizeof(int64_t) * (b->n_rows + 1), cudaMemcpyHostToDevice));
+      const int64_t k0 = a->row_ptr[lo], k1 = a->row_ptr[hi];
+      if (k1 > k0) {
+        CK(cudaMemcpy(b->col + k0, a->col_idx + k0, sizeof(int32_t) * (k1 - k0), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(b->val + k0, a->val + k0, sizeof(double) * (k1 - k0), cudaMemcpyHostToDevice));
+      }
+      for (int r = 0; r < world; ++r) {
+        const int64_t r0 = a->row_ptr[a->n_rows * r / world], r1 = a->row_ptr[a->n_rows * (r + 1) / world];
+        if (r1 == r0) continue;
+        if (g_nccl.Broadcast(b->col + r0, b->col + r0, (size_t)(r1 - r0), NCCL_INT32, r, g_nccl.comm, 0) != 0 ||
+            g_nccl.Broadcast(b->val + r0, b->val + r0, (size_t)(r1 - r0), NCCL_FLOAT64, r, g_nccl.comm, 0) != 0)
+          throw TmcError(TMC_ERR_COMM, "ncclBroadcast(matrix block) failed");
+      }
+      CK(cudaDeviceSynchronize());
+      return b;
+    }
     const int64_t k0 = a->row_ptr[lo], k1 = a->row_ptr[hi];
     b->n_rows = hi - lo; b->n_cols = a->n_cols; b->nnz = k1 - k0; b->owns = true;
     b->row_ptr = dalloc<int64_t>(b->n_rows + 1); b->col = dalloc<int32_t>(b->nnz); b->val = dalloc<double>(b->nnz);
@@ -436,15 +468,23 @@ static tmc_matrix* upload(const tmc_csr* a, int device) {
 }
 
 // ----------------------------------------------------------------------------- the scheduler
-struct HostNode { int begin, end, gsize, parent, left, right, iters; double q, theta; long long tb = 0, te = 0; int tpar = 0; };   // [begin,end) local, gsize global
+struct HostNode { int begin, end, gsize, parent, left, right, iters; double q, theta; long long tb = 0, te = 0; int tpar = 0;
+                  int priv = 0;     // the whole node lives on this rank (handed-off subtree)
+                  int hid = -1;     // >= 0: root of the hid-th handed-off subtree (same numbering on every rank)
+                  int owner = -1; };   // [begin,end) local, gsize global
 
 struct Engine {
   tmc_matrix* b; Workspace* w; tmc_opts o; Ctx c; cudaStream_t s;
   std::vector<int> hstate, slot_node;
   std::priority_queue<int, std::vector<int>, std::greater<int>> free_slots;   // lowest index first: keeps the y arena compact
+  std::priority_queue<int, std::vector<int>, std::greater<int>> free_priv;    // replicated mode: slots of handed-off (private) nodes
   std::vector<HostNode> nodes;
-  std::deque<int> pending;
+  std::deque<int> pending, pending_priv;
   int hi_slot = 0;
+  // replicated mode ("deeper subtrees as per-GPU tasks")
+  bool rmode = false; int n_shared_slots = 0; int handoff_rows = 0;
+  int priv_top = 0; long long t_top = 0;
+  std::vector<int> handoff_list; std::vector<long long> owner_load; int n_handoffs = 0;
   int64_t n_sweeps = 0, n_launch = 0;
   double alg_vec_bytes = 0;     // non-matrix part of the spmv_pair algorithmic bytes
   double build_ms = 0;
@@ -491,7 +531,13 @@ struct Engine {
     c.xs_min_rows = getenv("TMC_XS_ROWS") ? atoi(getenv("TMC_XS_ROWS")) : 8192;
     c.rank = g_nccl.comm ? g_nccl.rank : 0; c.world = g_nccl.comm ? g_nccl.world : 1;
     hstate.assign(w->max_active, ST_IDLE); slot_node.assign(w->max_active, -1);
-    for (int i = 0; i < w->max_active; ++i) free_slots.push(i);
+    rmode = b->replicated && c.world > 1 && c.use_t;
+    n_shared_slots = rmode ? std::max(1, std::min(256, w->max_active / 2)) : w->max_active;
+    for (int i = 0; i < n_shared_slots; ++i) free_slots.push(i);
+    for (int i = n_shared_slots; i < w->max_active; ++i) free_priv.push(i);
+    handoff_rows = getenv("TMC_HANDOFF_ROWS") ? atoi(getenv("TMC_HANDOFF_ROWS")) : 8192;
+    owner_load.assign(c.world, 0);
+    c.collectives = c.world > 1;
     profile = o.profile != 0;
     CK(cudaMemsetAsync(c.st, 0, sizeof(Slot) * w->max_active, s));
     CK(cudaMemsetAsync(c.err, 0, sizeof(int), s));
@@ -502,7 +548,8 @@ struct Engine {
   void init_perm(const int64_t* rows, int64_t n_sel) {
     const int m = (int)b->n_rows;
     if (!rows) {
-      k_iota<<<(m + 255) / 256, 256, 0, s>>>(c.perm, m);
+      const int cnt = rmode ? (int)(b->own_hi - b->own_lo) : m, off = rmode ? (int)b->own_lo : 0;
+      k_iota<<<(cnt + 255) / 256, 256, 0, s>>>(c.perm, cnt, off);
     } else {
       std::vector<int> h(n_sel);
       for (int64_t i = 0; i < n_sel; ++i) {
@@ -515,19 +562,20 @@ struct Engine {
   }
 
   // column-sorted copy of the rows at positions [begin,end) into buffer `par` at offset 0 (root / per-node API)
-  void build_tblock(HostNode& nd) {
+  void build_tblock(HostNode& nd, long long tb = 0) {
     if (!c.use_t) return;
     const int rows = nd.end - nd.begin;
     const int grid = std::max(1, std::min(148 * 8, (rows + 7) / 8));
     CK(cudaMemsetAsync(c.tb_cnt, 0, sizeof(int) * (b->n_cols + 1), s));
     k_tb_count<<<grid, 256, 0, s>>>(c, nd.begin, nd.end);
     k_tb_scan<<<1, 1024, 0, s>>>(c);
-    VT_DISPATCH(c.vt, k_tb_fill<VT><<<grid, 256, 0, s>>>(c, nd.begin, nd.end, 0, 0));
+    VT_DISPATCH(c.vt, k_tb_fill<VT><<<grid, 256, 0, s>>>(c, nd.begin, nd.end, tb, 0));
     n_launch += 3;
     long long tot = 0;
     CK(cudaMemcpyAsync(&tot, c.tb_colstart + b->n_cols, sizeof(long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    nd.tb = 0; nd.te = tot; nd.tpar = 0;
+    if (tb + tot + 8 > w->tn) throw TmcError(TMC_ERR_NOMEM, "internal: transposed buffer too small for the handed-off subtrees");
+    nd.tb = tb; nd.te = tb + tot; nd.tpar = 0;
   }
 
   // Root block when perm is the identity over all local rows: stable radix sort of the CSR entries by column
@@ -537,14 +585,22 @@ struct Engine {
     if (!c.use_t) return;
     const auto w0 = std::chrono::steady_clock::now();
     struct T_ { Engine* e; std::chrono::steady_clock::time_point t; ~T_() { e->build_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); } } timer_{this, w0};
-    const long long n = b->nnz;
+    const int row_lo = rmode ? (int)b->own_lo : 0, row_hi = rmode ? (int)b->own_hi : (int)b->n_rows;
+    long long e0 = 0, e1 = b->nnz;
+    if (rmode) {
+      int64_t pe[2];
+      CK(cudaMemcpy(&pe[0], b->row_ptr + row_lo, sizeof(int64_t), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(&pe[1], b->row_ptr + row_hi, sizeof(int64_t), cudaMemcpyDeviceToHost));
+      e0 = pe[0]; e1 = pe[1];
+    }
+    const long long n = e1 - e0;
     if (n >= (1ll << 31) - 1 || n == 0) { build_tblock(nd); return; }
     int32_t* keysA = c.tcol[1]; int32_t* keysB = c.tcol[0];
     int32_t* valsA = c.tpos[1]; int32_t* valsB = c.tpos[0];
     int32_t* rowid = w->rowid_scratch;
-    CK(cudaMemcpyAsync(keysA, b->col, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(keysA, b->col + e0, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
     k_tb_iota<<<148 * 8, 256, 0, s>>>(valsA, n);
-    k_tb_rowid<<<148 * 8, 256, 0, s>>>(b->row_ptr, (int)b->n_rows, rowid);
+    k_tb_rowid<<<148 * 8, 256, 0, s>>>(b->row_ptr, row_lo, row_hi, (int64_t)e0, rowid);
     cub::DoubleBuffer<int32_t> dk(keysA, keysB), dv(valsA, valsB);
     int end_bit = 1; while ((1ll << end_bit) < b->n_cols) ++end_bit;
     size_t tmp_bytes = 0;
@@ -559,7 +615,7 @@ struct Engine {
     CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, avail, dk, dv, (int)n, 0, end_bit, s));
     if (dk.Current() != keysB) CK(cudaMemcpyAsync(keysB, dk.Current(), sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
     if (dv.Current() != valsB) CK(cudaMemcpyAsync(valsB, dv.Current(), sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
-    VT_DISPATCH(c.vt, k_tb_finish_sorted<VT><<<148 * 8, 256, 0, s>>>(rowid, c.val, valsB, c.tval[0], n));
+    VT_DISPATCH(c.vt, k_tb_finish_sorted<VT><<<148 * 8, 256, 0, s>>>(rowid, c.val, (int64_t)e0, valsB, c.tval[0], n));
     CK(cudaStreamSynchronize(s));
     n_launch += 6;
     nd.tb = 0; nd.te = n; nd.tpar = 0;
@@ -567,14 +623,18 @@ struct Engine {
 
   int activate_pending(int stop_after) {
     int n = 0;
-    while (!pending.empty() && !free_slots.empty()) {
-      int node = pending.front(); pending.pop_front();
-      int slot = free_slots.top(); free_slots.pop();
-      w->h_act[n++] = Activation{slot, nodes[node].begin, nodes[node].end, nodes[node].gsize, node, stop_after, nodes[node].tpar, 0,
-                                 nodes[node].tb, nodes[node].te};
-      hstate[slot] = ST_DEG; slot_node[slot] = node;
-      hi_slot = std::max(hi_slot, slot + 1);
-    }
+    auto act = [&](std::deque<int>& q, std::priority_queue<int, std::vector<int>, std::greater<int>>& fs, int priv) {
+      while (!q.empty() && !fs.empty()) {
+        int node = q.front(); q.pop_front();
+        int slot = fs.top(); fs.pop();
+        w->h_act[n++] = Activation{slot, nodes[node].begin, nodes[node].end, nodes[node].gsize, node, stop_after, nodes[node].tpar, priv,
+                                   nodes[node].tb, nodes[node].te};
+        hstate[slot] = ST_DEG; slot_node[slot] = node;
+        hi_slot = std::max(hi_slot, slot + 1);
+      }
+    };
+    act(pending, free_slots, 0);
+    act(pending_priv, free_priv, 1);
     if (n) {
       CK(cudaMemcpyAsync(w->d_act, w->h_act, sizeof(Activation) * n, cudaMemcpyHostToDevice, s));
       k_activate<<<(n + 127) / 128, 128, 0, s>>>(c, w->d_act, n); n_launch++;
@@ -604,6 +664,17 @@ struct Engine {
     } catch (...) { cudaFree(d); throw; }
     cudaFree(d);
   }
+  void allreduce_host_f64(std::vector<double>& v) {
+    if (c.world <= 1 || v.empty()) return;
+    double* d = dalloc<double>(v.size());
+    try {
+      CK(cudaMemcpyAsync(d, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice, s));
+      nccl_check(g_nccl.AllReduce(d, d, v.size(), NCCL_FLOAT64, NCCL_SUM, g_nccl.comm, s), "ncclAllReduce(f64)");
+      CK(cudaMemcpyAsync(v.data(), d, sizeof(double) * v.size(), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+    } catch (...) { cudaFree(d); throw; }
+    cudaFree(d);
+  }
   void allreduce_u8(uint8_t* p, size_t n) {
     if (c.world > 1 && n) nccl_check(g_nccl.AllReduce(p, p, n, NCCL_UINT8, NCCL_SUM, g_nccl.comm, s), "ncclAllReduce(u8)");
   }
@@ -612,10 +683,17 @@ struct Engine {
   // (degree pass | start-vector orthogonalisation | Lanczos step | modularity + split).
   void sweep(bool only_spmv = false) {
     int n_sc = 0, n_ga = 0, n_mod = 0, n_or = 0, n_deg = 0, live_n = 0; int64_t rows = 0;
+    // collectives are issued from the SHARED slots' states only (identical on every rank); private slots never communicate
+    int sh_sc = 0, sh_or = 0, sh_live = 0, hi_shared = 0;
     for (int sl = 0; sl < hi_slot; ++sl) {
       int st = hstate[sl];
       if (st < ST_DEG || st > ST_MOD) continue;
       live_n++;
+      if (sl < n_shared_slots) {
+        sh_live++; hi_shared = sl + 1;
+        if (st == ST_DEG || st == ST_LAN || st == ST_MOD) sh_sc++;
+        if (st == ST_ORTH0 || st == ST_LAN) sh_or++;
+      }
       const HostNode& nd = nodes[slot_node[sl]];
       int len = nd.end - nd.begin;
       rows += len;
@@ -696,8 +774,7 @@ struct Engine {
       else if (nch) { VT_DISPATCH(c.vt, k_scatter<VT><<<nch, 256, 0, s>>>(c)); n_launch++; }
       if (profile) e1 = ev();
       mark(PH_TGATHER);
-      allreduce_f64(c.Y, (size_t)c.ystride * hi_slot);
-      if (c.world > 1) mark(PH_AR_Y);
+      if (c.collectives && sh_sc) { allreduce_f64(c.Y, (size_t)c.ystride * hi_shared); mark(PH_AR_Y); }
     }
     if (n_ga && nch) { VT_DISPATCH(c.vt, k_gather<VT><<<nch, 256, 0, s>>>(c)); n_launch++; }
     mark(PH_GATHER);
@@ -707,18 +784,16 @@ struct Engine {
     const size_t upd_smem = sizeof(double) * ((size_t)c.K + 2 + 8 * (size_t)RV);
     // kernels depend on this rank's rows, collectives only on the (rank-identical) slot states.
     // Three all-reduces per sweep: Y above, the pass-0 coefficients, and the pass-1 coefficients + every scalar.
-    if (n_or) {
-      if (nvch) { k_dots<<<nvch, 256, 0, s>>>(c, 0); n_launch++; }
+    if (n_or || sh_or) {
+      if (nvch && n_or) { k_dots<<<nvch, 256, 0, s>>>(c, 0); n_launch++; }
       mark(PH_DOTS);
-      allreduce_f64(c.redA, (size_t)(c.K + 2) * hi_slot);
-      if (c.world > 1) mark(PH_AR_COEF);
-      if (nvch) { k_update<<<nvch, 256, upd_smem, s>>>(c, 0); n_launch++; }
+      if (c.collectives && sh_or) { allreduce_f64(c.redA, (size_t)(c.K + 2) * hi_shared); mark(PH_AR_COEF); }
+      if (nvch && n_or) { k_update<<<nvch, 256, upd_smem, s>>>(c, 0); n_launch++; }
       mark(PH_UPDATE);
-      if (nvch) { k_dots<<<nvch, 256, 0, s>>>(c, 1); n_launch++; }
+      if (nvch && n_or) { k_dots<<<nvch, 256, 0, s>>>(c, 1); n_launch++; }
       mark(PH_DOTS);
     }
-    allreduce_f64(c.redB, (size_t)(c.K + 2 + R_NSCAL) * hi_slot);
-    if (c.world > 1) mark(PH_AR_COEF);
+    if (c.collectives && sh_live) { allreduce_f64(c.redB, (size_t)(c.K + 2 + R_NSCAL) * hi_shared); mark(PH_AR_COEF); }
     if (n_or && nvch) { k_update<<<nvch, 256, upd_smem, s>>>(c, 1); n_launch++; mark(PH_UPDATE); }
     k_finish<<<(hi_slot * 32 + 255) / 256, 256, 0, s>>>(c); n_launch++;
     mark(PH_FINISH);
@@ -758,30 +833,82 @@ struct Engine {
         const int b0 = nd.begin, e0 = nd.end, gs = nd.gsize, n0l = r.n0_local, n0g = r.n0;
         int li = (int)nodes.size(), ri = li + 1;
         nodes[node].left = li; nodes[node].right = ri;
-        const long long ptb = nd.tb, pte = nd.te, t0 = r.tnnz0; const int cpar = nd.tpar ^ 1;
-        nodes.push_back(HostNode{b0, b0 + n0l, n0g, node, -1, -1, 0, 0.0, 0.0, ptb, ptb + t0, cpar});
-        nodes.push_back(HostNode{b0 + n0l, e0, gs - n0g, node, -1, -1, 0, 0.0, 0.0, ptb + t0, pte, cpar});
-        if (n0g >= 2) pending.push_back(li);
-        if (gs - n0g >= 2) pending.push_back(ri);
+        const long long ptb = nd.tb, pte = nd.te, t0 = r.tnnz0; const int cpar = nd.tpar ^ 1; const int ppriv = nd.priv;
+        nodes.push_back(HostNode{b0, b0 + n0l, n0g, node, -1, -1, 0, 0.0, 0.0, ptb, ptb + t0, cpar, ppriv});
+        nodes.push_back(HostNode{b0 + n0l, e0, gs - n0g, node, -1, -1, 0, 0.0, 0.0, ptb + t0, pte, cpar, ppriv});
+        for (int ch : {li, ri}) {
+          if (nodes[ch].gsize < 2) continue;                       // single cell: a leaf, nothing to compute
+          if (ppriv) pending_priv.push_back(ch);
+          else if (rmode && nodes[ch].gsize < handoff_rows) handoff_list.push_back(ch);
+          else pending.push_back(ch);
+        }
       }
-      hstate[sl] = ST_IDLE; slot_node[sl] = -1; free_slots.push(sl);
+      hstate[sl] = ST_IDLE; slot_node[sl] = -1; if (sl < n_shared_slots) free_slots.push(sl); else free_priv.push(sl);
     }
     while (hi_slot > 0 && hstate[hi_slot - 1] == ST_IDLE) hi_slot--;
   }
 
   void take_slot0() { if (!free_slots.empty() && free_slots.top() == 0) free_slots.pop(); }
+
+  // Hand small subtrees to single ranks (replicated mode).  Every rank reaches this with the same list.  The cells of a
+  // node are gathered (rank order = ascending row id) with two small int32 all-reduces, the owner appends them to its
+  // private position area, builds the node's column-sorted block from its resident copy of the matrix and from then on
+  // works on the node alone; the other ranks only remember who owns it.
+  void do_handoffs() {
+    if (handoff_list.empty()) return;
+    const int nh = (int)handoff_list.size(), G = c.world, me = c.rank;
+    std::vector<int> lsz((size_t)G * nh, 0);
+    long long total = 0;
+    for (int i = 0; i < nh; ++i) { const HostNode& nd = nodes[handoff_list[i]]; lsz[(size_t)me * nh + i] = nd.end - nd.begin; total += nd.gsize; }
+    allreduce_host_i32(lsz);
+    CK(cudaMemsetAsync(c.perm_tmp, 0, sizeof(int) * total, s));
+    std::vector<long long> off(nh + 1, 0);
+    for (int i = 0; i < nh; ++i) off[i + 1] = off[i] + nodes[handoff_list[i]].gsize;
+    for (int i = 0; i < nh; ++i) {
+      const HostNode& nd = nodes[handoff_list[i]];
+      long long o = off[i];
+      for (int r = 0; r < me; ++r) o += lsz[(size_t)r * nh + i];
+      if (nd.end > nd.begin) CK(cudaMemcpyAsync(c.perm_tmp + o, c.perm + nd.begin, sizeof(int) * (nd.end - nd.begin), cudaMemcpyDeviceToDevice, s));
+    }
+    nccl_check(g_nccl.AllReduce(c.perm_tmp, c.perm_tmp, (size_t)total, NCCL_INT32, NCCL_SUM, g_nccl.comm, s), "ncclAllReduce(hand-off ids)");
+    for (int i = 0; i < nh; ++i) {
+      HostNode& nd = nodes[handoff_list[i]];
+      int owner = 0;
+      for (int r = 1; r < G; ++r) if (owner_load[r] < owner_load[owner]) owner = r;
+      owner_load[owner] += nd.gsize;
+      nd.hid = n_handoffs++; nd.owner = owner;
+      if (owner != me) { nd.begin = nd.end = 0; continue; }
+      if ((long long)priv_top + nd.gsize > w->m) throw TmcError(TMC_ERR_NOMEM, "internal: private position area exhausted");
+      CK(cudaMemcpyAsync(c.perm + priv_top, c.perm_tmp + off[i], sizeof(int) * nd.gsize, cudaMemcpyDeviceToDevice, s));
+      nd.begin = priv_top; nd.end = priv_top + nd.gsize; nd.priv = 1;
+      priv_top += nd.gsize;
+      build_tblock(nd, t_top);
+      t_top = (nd.te + 7) & ~7ll;
+      pending_priv.push_back(handoff_list[i]);
+    }
+    CK(cudaStreamSynchronize(s));
+    handoff_list.clear();
+  }
   int live() const { int n = 0; for (int sl = 0; sl < hi_slot; ++sl) n += (hstate[sl] >= ST_DEG && hstate[sl] <= ST_MOD); return n; }
 
   void run_tree() {
-    const int m = (int)b->n_rows;
-    nodes.clear(); pending.clear();
+    const int m = rmode ? (int)(b->own_hi - b->own_lo) : (int)b->n_rows;
+    nodes.clear(); pending.clear(); pending_priv.clear();
     nodes.push_back(HostNode{0, m, (int)b->n_rows_global, -1, -1, -1, 0, 0.0, 0.0});
     if (b->n_rows_global >= 2) { build_tblock_sorted(nodes[0]); pending.push_back(0); }      // run_tree starts from the identity perm
+    priv_top = m; t_top = (nodes[0].te + 7) & ~7ll;
     for (;;) {
       activate_pending(0);
+      if (rmode && c.collectives) {
+        // the shared top of the tree is finished on every rank at the same sweep: from here on no collective is issued
+        bool shared_left = !pending.empty();
+        for (int sl = 0; sl < std::min(hi_slot, n_shared_slots) && !shared_left; ++sl) shared_left = hstate[sl] >= ST_DEG && hstate[sl] <= ST_MOD;
+        if (!shared_left) c.collectives = 0;
+      }
       if (!live()) break;
       sweep();
       harvest(true);
+      if (rmode) do_handoffs();
     }
   }
 
@@ -878,6 +1005,10 @@ int tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int6
       b->n_rows = n_rows; b->n_cols = n_cols; b->nnz = nnz; b->owns = false;
       b->n_rows_global = n_rows_global > 0 ? n_rows_global : n_rows; b->row_offset = n_rows_global > 0 ? row_offset : 0;
       if (b->row_offset < 0 || b->row_offset + n_rows > b->n_rows_global) throw TmcError(TMC_ERR_INVALID, "row block outside [0, n_rows_global)");
+      if (g_nccl.comm && g_nccl.world > 1 && b->n_rows_global == n_rows && getenv("TMC_NO_HANDOFF") == nullptr) {
+        b->replicated = true;      // the whole matrix is resident on every rank
+        b->own_lo = n_rows * g_nccl.rank / g_nccl.world; b->own_hi = n_rows * (g_nccl.rank + 1) / g_nccl.world;
+      }
       b->row_ptr = const_cast<int64_t*>(row_ptr_dev); b->col = const_cast<int32_t*>(col_dev); b->val = val_dev;
       prepare_matrix(b, normalize);
     } catch (...) { tmc_matrix_free(b); throw; }
@@ -923,56 +1054,105 @@ int tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out) {
     eng.phase_report();
     if (dbg) fprintf(stderr, "[tmc] run_tree wall %.2f ms (block build %.2f ms), sweeps %lld, nodes %zu\n", now() - w0, eng.build_ms,
                      (long long)eng.n_sweeps, eng.nodes.size());
-    const int m = (int)b->n_rows;
+    const int m = eng.rmode ? (int)(b->own_hi - b->own_lo) : (int)b->n_rows;
     const int64_t M = b->n_rows_global;
     const int world = eng.c.world, rank = eng.c.rank;
-    std::vector<int> hperm(std::max(m, 1));
-    CK(cudaMemcpyAsync(hperm.data(), eng.c.perm, sizeof(int) * m, cudaMemcpyDeviceToHost, eng.s));
+    const int used = eng.rmode ? eng.priv_top : m;
+    std::vector<int> hperm(std::max(used, 1));
+    CK(cudaMemcpyAsync(hperm.data(), eng.c.perm, sizeof(int) * used, cudaMemcpyDeviceToHost, eng.s));
     CK(cudaMemcpyAsync(eng.w->h_stats, eng.c.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, eng.s));
     CK(cudaStreamSynchronize(eng.s));
     float ms = 0; CK(cudaEventElapsedTime(&ms, t0, t1));
     cudaEventDestroy(t0); cudaEventDestroy(t1);
-    // pre-order renumbering, children [label 0, label 1]  (birch-beer treeToGraph, Cluster.hs:171-181)
-    const size_t nn = eng.nodes.size();
+    // pre-order renumbering, children [label 0, label 1]  (birch-beer treeToGraph, Cluster.hs:171-181).
+    // Replicated mode: the subtrees handed to single ranks are serialised by their owners (pre-order records) and
+    // exchanged with two small all-reduces; every rank then splices them into the shared top of the tree.
+    struct Rec { int leaf, size, iters; double q, theta; };
+    const int nh = eng.n_handoffs;
+    std::vector<int> hroot(nh, -1);
+    for (size_t u = 0; u < eng.nodes.size(); ++u) if (eng.nodes[u].hid >= 0) hroot[eng.nodes[u].hid] = (int)u;
+    std::vector<int> hcnt(nh, 0);
+    std::vector<std::vector<Rec>> hrec(nh);
+    for (int h = 0; h < nh; ++h) {
+      const int ur = hroot[h];
+      if (eng.nodes[ur].owner != rank) continue;
+      std::vector<int> st2{ur};
+      while (!st2.empty()) {
+        const int u = st2.back(); st2.pop_back();
+        const HostNode& nd = eng.nodes[u];
+        hrec[h].push_back(Rec{nd.left < 0 ? 1 : 0, nd.gsize, nd.iters, nd.q, nd.theta});
+        if (nd.left >= 0) { st2.push_back(nd.right); st2.push_back(nd.left); }
+      }
+      hcnt[h] = (int)hrec[h].size();
+    }
+    if (nh) eng.allreduce_host_i32(hcnt);
+    std::vector<long long> hoff(nh + 1, 0);
+    for (int h = 0; h < nh; ++h) hoff[h + 1] = hoff[h] + hcnt[h];
+    std::vector<int> ri((size_t)3 * hoff[nh], 0); std::vector<double> rd((size_t)2 * hoff[nh], 0.0);
+    for (int h = 0; h < nh; ++h)
+      for (size_t k = 0; k < hrec[h].size(); ++k) {
+        const size_t o = (size_t)hoff[h] + k; const Rec& r = hrec[h][k];
+        ri[3 * o] = r.leaf; ri[3 * o + 1] = r.size; ri[3 * o + 2] = r.iters; rd[2 * o] = r.q; rd[2 * o + 1] = r.theta;
+      }
+    if (nh && hoff[nh]) { eng.allreduce_host_i32(ri); eng.allreduce_host_f64(rd); }
+
     TreeStorage* ts = new TreeStorage();
-    ts->left.assign(nn, -1); ts->right.assign(nn, -1); ts->parent.assign(nn, -1);
-    ts->item_begin.resize(nn); ts->item_end.resize(nn); ts->q.resize(nn); ts->theta.resize(nn); ts->iters.resize(nn);
-    std::vector<int64_t> newid(nn, -1), gbeg(nn, 0); std::vector<int> stack; stack.push_back(0); int64_t next = 0;
-    std::vector<int> order; order.reserve(nn);
-    gbeg[0] = 0;
+    struct Item { int local; long long rec; int64_t parent; int64_t gbeg; };     // local >= 0: engine node; else record index
+    std::vector<Item> stack; stack.push_back(Item{0, -1, -1, 0});
+    std::vector<std::pair<int, int64_t>> shared_leaves;      // (engine node, global begin) of leaves whose cells are spread over ranks
+    std::vector<std::pair<int, int64_t>> handed;             // (hid, global begin)
     while (!stack.empty()) {
-      int u = stack.back(); stack.pop_back();
-      newid[u] = next++; order.push_back(u);
-      const HostNode& nd = eng.nodes[u];
-      if (nd.left >= 0) {
-        gbeg[nd.left] = gbeg[u]; gbeg[nd.right] = gbeg[u] + eng.nodes[nd.left].gsize;     // global position space
-        stack.push_back(nd.right); stack.push_back(nd.left);
+      const Item it = stack.back(); stack.pop_back();
+      const int64_t id = (int64_t)ts->left.size();
+      ts->left.push_back(-1); ts->right.push_back(-1); ts->parent.push_back(it.parent);
+      if (it.parent >= 0) { if (ts->left[it.parent] < 0) ts->left[it.parent] = id; else ts->right[it.parent] = id; }
+      if (it.local >= 0 && eng.nodes[it.local].hid < 0) {
+        const HostNode& nd = eng.nodes[it.local];
+        ts->item_begin.push_back(it.gbeg); ts->item_end.push_back(it.gbeg + nd.gsize);
+        ts->q.push_back(nd.q); ts->theta.push_back(nd.theta); ts->iters.push_back(nd.iters);
+        if (nd.left >= 0) {
+          stack.push_back(Item{nd.right, -1, id, it.gbeg + eng.nodes[nd.left].gsize});
+          stack.push_back(Item{nd.left, -1, id, it.gbeg});
+        } else shared_leaves.push_back({it.local, it.gbeg});
+      } else {
+        // a handed-off subtree (its root arrives as an engine node, its descendants as records in pre-order)
+        long long k = it.rec;
+        if (it.local >= 0) { const int h = eng.nodes[it.local].hid; k = hoff[h]; handed.push_back({h, it.gbeg}); }
+        const int leaf = ri[3 * k], size = ri[3 * k + 1];
+        ts->item_begin.push_back(it.gbeg); ts->item_end.push_back(it.gbeg + size);
+        ts->q.push_back(rd[2 * k]); ts->theta.push_back(rd[2 * k + 1]); ts->iters.push_back(ri[3 * k + 2]);
+        if (!leaf) {
+          // pre-order: the left child is record k+1; the right child follows the whole left subtree
+          long long j = k + 1, need = 1;
+          while (need > 0) { need += ri[3 * j] ? -1 : 1; ++j; }
+          const int lsize = ri[3 * (k + 1) + 1];
+          stack.push_back(Item{-1, j, id, it.gbeg + lsize});
+          stack.push_back(Item{-1, k + 1, id, it.gbeg});
+        }
       }
     }
-    for (int u : order) {
-      const HostNode& nd = eng.nodes[u]; int64_t id = newid[u];
-      ts->left[id] = nd.left >= 0 ? newid[nd.left] : -1; ts->right[id] = nd.right >= 0 ? newid[nd.right] : -1;
-      ts->parent[id] = nd.parent >= 0 ? newid[nd.parent] : -1;
-      ts->item_begin[id] = gbeg[u]; ts->item_end[id] = gbeg[u] + nd.gsize; ts->q[id] = nd.q; ts->theta[id] = nd.theta; ts->iters[id] = nd.iters;
-    }
-    // global permutation: inside a leaf, rank r's cells follow those of ranks < r (row blocks are ascending in rank,
-    // so every leaf stays ascending in original row id)
+    const size_t nn = ts->left.size();
+    // global permutation: inside a shared leaf, rank r's cells follow those of ranks < r (row blocks ascend with the rank,
+    // so every leaf stays ascending in original row id); a handed-off subtree is written by its owner in one piece
     ts->perm.assign(M, 0);
     if (world == 1) {
       for (int i = 0; i < m; ++i) ts->perm[i] = hperm[i];
     } else {
-      std::vector<int> leaves;
-      for (int u : order) if (eng.nodes[u].left < 0) leaves.push_back(u);
-      const size_t nl = leaves.size();
+      const size_t nl = shared_leaves.size();
       std::vector<int> lsz((size_t)world * nl, 0);
-      for (size_t i = 0; i < nl; ++i) lsz[(size_t)rank * nl + i] = eng.nodes[leaves[i]].end - eng.nodes[leaves[i]].begin;
-      eng.allreduce_host_i32(lsz);
+      for (size_t i = 0; i < nl; ++i) { const HostNode& nd = eng.nodes[shared_leaves[i].first]; lsz[(size_t)rank * nl + i] = nd.end - nd.begin; }
+      if (nl) eng.allreduce_host_i32(lsz);
       std::vector<int> gp(M, 0);
       for (size_t i = 0; i < nl; ++i) {
-        const HostNode& nd = eng.nodes[leaves[i]];
-        int64_t off = gbeg[leaves[i]];
+        const HostNode& nd = eng.nodes[shared_leaves[i].first];
+        int64_t off = shared_leaves[i].second;
         for (int r = 0; r < rank; ++r) off += lsz[(size_t)r * nl + i];
         for (int p = nd.begin; p < nd.end; ++p) gp[off + (p - nd.begin)] = (int)(b->row_offset + hperm[p]);
+      }
+      for (auto& hg : handed) {
+        const HostNode& nd = eng.nodes[hroot[hg.first]];
+        if (nd.owner != rank) continue;
+        for (int p = nd.begin; p < nd.end; ++p) gp[hg.second + (p - nd.begin)] = hperm[p];
       }
       eng.allreduce_host_i32(gp);
       for (int64_t i = 0; i < M; ++i) ts->perm[i] = gp[i];

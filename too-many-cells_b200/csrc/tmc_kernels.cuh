@@ -33,6 +33,8 @@ struct Slot {              // one live tree node (device resident)
   int split, n0;
   int stop_after;          // 0 = full lifecycle, else stop when reaching this state (fine-grained API)
   int tpar;                // which of the two transposed buffers holds this node's column-sorted block
+  int priv;                // 1 = the whole node lives on this rank (handed-off subtree): no collectives, gsize = local size
+  int pad2;
   long long tb, te;        // the block: entries [tb, te) of tcol/tpos/tval[tpar], sorted by column
   long long tnnz0;         // entries of label-0 cells (set by k_tpart_scan): children blocks are [tb, tb+tnnz0) and [tb+tnnz0, te)
   int tchunk0, ntchunk;    // this sweep's chunks of the block (set by k_prepare)
@@ -48,7 +50,7 @@ struct Report {            // what the host reads back after every sweep
 
 struct Chunk { int slot, begin, len; };
 struct TChunk { long long begin; int slot, pad; };        // entries [begin, begin + tchunk) of the slot's transposed block
-struct Activation { int slot, begin, end, gsize, node, stop_after, tpar, pad; long long tb, te; };
+struct Activation { int slot, begin, end, gsize, node, stop_after, tpar, priv; long long tb, te; };
 
 struct Ctx {
   // matrix B (CSR, rows = cells)
@@ -85,6 +87,7 @@ struct Ctx {
   // options
   double tol, min_modularity; int min_size, max_restarts; uint64_t seed;
   int rank, world;
+  int collectives;                 // 0 once only private (handed-off) nodes remain: ranks run free
 };
 
 __device__ __forceinline__ double* slot_scal(const Ctx& c, int slot) { return c.redB + (int64_t)slot * (c.K + 2 + R_NSCAL) + (c.K + 2); }
@@ -280,7 +283,7 @@ __global__ void k_activate(Ctx c, const Activation* __restrict__ acts, int n) {
   s.begin = a.begin; s.end = a.end; s.gsize = a.gsize; s.n0_local = 0;
   s.state = ST_DEG; s.action = ACT_NONE; s.j = 0; s.iters = 0; s.restarts = 0; s.node = a.node;
   s.split = 0; s.n0 = 0; s.stop_after = a.stop_after;
-  s.tpar = a.tpar; s.tb = a.tb; s.te = a.te; s.tnnz0 = 0; s.tchunk0 = 0; s.ntchunk = 0;
+  s.tpar = a.tpar; s.priv = a.priv; s.pad2 = 0; s.tb = a.tb; s.te = a.te; s.tnnz0 = 0; s.tchunk0 = 0; s.ntchunk = 0;
   s.sumd = 0; s.inv_sqrt_sumd = 0; s.beta = 0; s.theta = 0; s.resid = 0; s.q = 0; s.theta_hint = -1e300;
   c.st[a.slot] = s;
   slot_scal(c, a.slot)[R_N1] = 0.0; slot_scal(c, a.slot)[R_SD1] = 0.0;
@@ -531,12 +534,13 @@ __global__ void __launch_bounds__(256) k_tgather_t(Ctx c, int cls) {       // cl
 
 // sorted construction of the root block (perm = identity): after a stable radix sort of the CSR entries by column,
 // tpos holds CSR entry indices; replace them by the row (= position) and fetch the values
-__global__ void __launch_bounds__(256) k_tb_rowid(const int64_t* __restrict__ row_ptr, int n_rows, int32_t* __restrict__ rowid) {
+// rows [row_lo, row_hi): rowid[k - e0] = position of the row (= r - row_lo), e0 = row_ptr[row_lo]
+__global__ void __launch_bounds__(256) k_tb_rowid(const int64_t* __restrict__ row_ptr, int row_lo, int row_hi, int64_t e0, int32_t* __restrict__ rowid) {
   const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   const int nw = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
-  for (int r = warp; r < n_rows; r += nw) {
+  for (int r = row_lo + warp; r < row_hi; r += nw) {
     const int64_t rs = row_ptr[r], re = row_ptr[r + 1];
-    for (int64_t k = rs + lane; k < re; k += 32) rowid[k] = r;
+    for (int64_t k = rs + lane; k < re; k += 32) rowid[k - e0] = r - row_lo;
   }
 }
 __global__ void k_tb_iota(int32_t* __restrict__ p, long long n) {
@@ -545,11 +549,11 @@ __global__ void k_tb_iota(int32_t* __restrict__ p, long long n) {
   for (; i < n; i += st) p[i] = (int32_t)i;
 }
 template <int VT>
-__global__ void k_tb_finish_sorted(const int32_t* __restrict__ rowid, const void* __restrict__ val, int32_t* __restrict__ tpos,
+__global__ void k_tb_finish_sorted(const int32_t* __restrict__ rowid, const void* __restrict__ val, int64_t e0, int32_t* __restrict__ tpos,
                                    void* __restrict__ tval, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long st = (long long)gridDim.x * blockDim.x;
-  for (; i < n; i += st) { const int32_t e = tpos[i]; tpos[i] = __ldg(rowid + e); st_val<VT>(tval, i, ld_val<VT>(val, e)); }
+  for (; i < n; i += st) { const int32_t e = tpos[i]; tpos[i] = __ldg(rowid + e); st_val<VT>(tval, i, ld_val<VT>(val, e0 + e)); }
 }
 
 // ---- building a node's T-block from its CSR rows (root, and the per-node API entry points)
@@ -811,6 +815,7 @@ __global__ void __launch_bounds__(256) k_ynorm(Ctx c) {
   if (c.st[slot].state != ST_MOD) return;
   const double* __restrict__ y = c.Y + (int64_t)slot * c.ystride;
   int lo = (int)((int64_t)c.n_cols * c.rank / c.world), hi = (int)((int64_t)c.n_cols * (c.rank + 1) / c.world);
+  if (c.st[slot].priv || !c.collectives) { lo = 0; hi = c.n_cols; }
   double s = 0.0;
   for (int i = lo + blockIdx.y * blockDim.x + threadIdx.x; i < hi; i += gridDim.y * blockDim.x) {
     double v = y[i];
@@ -1111,7 +1116,7 @@ __global__ void __launch_bounds__(256) k_deg_xin(Ctx c) {
 }
 
 // helpers for the fine-grained API
-__global__ void k_iota(int* p, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
+__global__ void k_iota(int* p, int n, int offset) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i + offset; }
 __global__ void k_set_xin_scaled(Ctx c, const double* __restrict__ x, int n) {   // xin = D^{-1/2} x
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) c.xin[i] = c.sdeg[i] * x[i];
 }
