@@ -361,6 +361,16 @@ static void prepare_matrix(tmc_matrix* b, int normalize) {
     k_scan_values<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, d_flags);
     int f[2] = {0, 0};
     CK(cudaMemcpy(f, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    if (g_nccl.comm && g_nccl.world > 1 && !b->replicated) {
+      // row-block inputs: every rank must take the same decision (storage mode, errors), or the others would wait forever
+      int* bits = dalloc<int>(5); int hb[5];
+      for (int i = 0; i < 5; ++i) hb[i] = (f[0] >> i) & 1;
+      cudaMemcpy(bits, hb, sizeof(hb), cudaMemcpyHostToDevice);
+      int r = g_nccl.AllReduce(bits, bits, 5, NCCL_INT32, NCCL_SUM, g_nccl.comm, 0);
+      cudaMemcpy(hb, bits, sizeof(hb), cudaMemcpyDeviceToHost); cudaFree(bits);
+      if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(value flags) failed");
+      f[0] = 0; for (int i = 0; i < 5; ++i) if (hb[i]) f[0] |= 1 << i;
+    }
     if (f[0] & 1) throw TmcError(TMC_ERR_NAN, "NaN/Inf in matrix values");
     if (f[0] & 4) throw TmcError(TMC_ERR_INVALID, "column index out of range");
     if (f[0] & 2) throw TmcError(TMC_ERR_NEGATIVE, "negative matrix entry (engine requires B >= 0)");
