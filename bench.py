@@ -270,15 +270,16 @@ def main():
     # for this workload and storage mode
     traffic = None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-            "traffic": traffic, "traffic_scope": "root-level pair launch (largest launch), ncu dram bytes" if traffic else None, "peak_source": peak_src, "kernel": "k_scatter+k_gather (SpMV pair y=C^T x, x'=C y), all launches of the timed steps",
+            "traffic": traffic, "traffic_scope": "root-level pair launch (largest launch), ncu dram bytes" if traffic else None, "peak_source": peak_src, "kernel": "k_tgather_t + k_gather (SpMV pair y = C^T x from the column-sorted blocks, x' = C y from the CSR), all launches of the timed steps",
             "algorithmic_bytes_per_step": alg / len(trees), "value_bytes_b_v": tr.stats["value_bytes"],
             "algorithmic_bytes_formula": "per SpMV pair 2*nnz*(b_v+4) + 2*(m+1)*8 + (4*m+2*n)*8 (BASELINE.md section 4), b_v = bytes per stored value", "spmv_ms_per_step": spmv_ms / len(trees),
             "spmv_share_of_step": spmv_ms / len(trees) / ms_step,
             "per_gpu": True, "root_pair": root_pair}
     line = {"metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": dict(cfg, nnz=nnz, parallelism=(f"{world} GPU(s): matrix replicated, shared top of the tree row-sharded with NCCL all-reduce of y = B^T x per "
-                                              f"half-step, subtrees below the hand-off size owned by single GPUs (no collectives)")),
+            "data": "synthetic", "config": dict(cfg, nnz=nnz, parallelism=("1 GPU" if world == 1 else
+                                             f"{world} GPUs: matrix replicated, shared top of the tree row-sharded with NCCL all-reduce of y = B^T x "
+                                             f"per half-step, subtrees below the hand-off size owned by single GPUs (no collectives)")),
             "clocks": clocks,
             "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roof,

@@ -82,11 +82,13 @@ def synth_config(name):
     return synth_counts(n, g, k, d, s, binary)
 
 
-def synth_counts_torch(n_cells, n_genes, nnz_per_cell, depth, seed, device, binary=False, block=4096, row_range=None):
+def synth_counts_torch(n_cells, n_genes, nnz_per_cell, depth, seed, device, binary=False, block=None, row_range=None):
     """Same recipe on a torch device, seeded PER ROW BLOCK so that any rank can generate exactly its own rows:
     rows [lo, hi) = row_range (default: all).  Returns (row_ptr int64, col int32, val float64) tensors on `device`
     for the local rows (row_ptr rebased to 0)."""
     import torch
+    if block is None:          # ~1.2e8 dense Poisson draws per block (fixed by the shape, so every rank uses the same blocks)
+        block = max(64, min(4096, (1 << 27) // n_genes // 64 * 64))
     rng = np.random.default_rng(seed)
     prof = _programmes(rng, n_genes, depth)
     lib0 = _solve_library(prof.mean(axis=0), nnz_per_cell)
