@@ -68,3 +68,18 @@ def test_graph_dot(golden_tree):
                                  (7.34341252699784e-2, "7.34341252699784e-2"), (-0.5, "-0.5"), (0.0, "0.0")])
 def test_haskell_show(x, s):
     assert T.haskell_show_double(x) == s
+
+
+def test_prune_min_size_matches_golden_pruned_outputs(golden_tree):
+    """--min-size 30 through --prior (workshop/workshop.org:324-330): every written artefact of the pruned run is reproduced."""
+    _, tree, names = golden_tree
+    pruned = T.prune_min_size(tree, 30)
+    assert pruned.n_nodes == 75 and int((pruned.left < 0).sum()) == 38
+    assert T.cluster_tree_json(pruned, names) == open(os.path.join(W, "pruned_cluster_tree.json")).read()
+    assert T.clusters_csv(pruned, names) == open(os.path.join(W, "clusters_pruned.csv"), newline="").read()
+    assert T.cluster_info_csv(pruned) == open(os.path.join(W, "pruned_cluster_info.csv"), newline="").read()
+    bc2row = {v: k for k, v in names.items()}
+    lab = {bc2row[r[0]]: r[1] for r in list(csv.reader(open(os.path.join(W, "labels.csv"))))[1:] if r[0] in bc2row}
+    assert T.node_info_csv(pruned, lab, significance=False) == open(os.path.join(W, "pruned_node_info.csv"), newline="").read()
+    assert T.prune_min_size(tree, 1).n_nodes == tree.n_nodes                      # no-op
+    assert T.prune_min_size(tree, 10 ** 9).n_nodes == 1                           # everything collapses into the root

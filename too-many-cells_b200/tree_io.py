@@ -53,6 +53,8 @@ def haskell_show_double(x: float) -> str:
 class FlatTree:
     """Minimal flat pre-order tree: what the writers need (left/right/q/items)."""
 
+    keeps_leaf_distance = True    # a leaf made by pruning keeps the Q of the node it collapsed (golden out_pruned tree)
+
     def __init__(self, left, right, q, items):
         self.left = np.asarray(left, dtype=np.int64)
         self.right = np.asarray(right, dtype=np.int64)
@@ -141,7 +143,10 @@ def cluster_tree_json(tree, row_names, significance=False) -> str:
     strs = [None] * tree.n_nodes
     for i in range(tree.n_nodes - 1, -1, -1):
         if tree.left[i] < 0:
-            label = {"_item": [_cell_info(row_names[r], r) for r in tree.items(i)], "_distance": None}
+            dist = None
+            if getattr(tree, "keeps_leaf_distance", False) and tree.q[i] == tree.q[i]:
+                dist = float(tree.q[i])
+            label = {"_item": [_cell_info(row_names[r], r) for r in tree.items(i)], "_distance": dist}
             kids = "[]"
         else:
             label = {"_item": None, "_distance": float(tree.q[i])}
@@ -177,7 +182,8 @@ def parse_cluster_tree_json(text: str):
             left.append(ids[id(kids[0])]); right.append(ids[id(kids[1])])
             q.append(label["_distance"]); items.append(None)
         else:
-            left.append(-1); right.append(-1); q.append(float("nan"))
+            left.append(-1); right.append(-1)
+            q.append(float("nan") if label["_distance"] is None else label["_distance"])
             rows = []
             for ci in label["_item"]:
                 rows.append(ci["_cellRow"]["unRow"]); names[ci["_cellRow"]["unRow"]] = ci["_barcode"]["unCell"]
@@ -262,6 +268,46 @@ def node_info_csv(tree, label_of_row=None, significance=True) -> str:
         rows.append(row)
     hdr = "node,size,proportion,modularity," + ("significance," if significance else "") + "composition,subtree"
     return _csv(hdr, rows)
+
+
+def prune_min_size(tree, min_size: int) -> FlatTree:
+    """`--min-size N` (birch-beer, applied after clustering: Program/MakeTree.hs:98,271; Options.hs:175): a vertex whose
+    either child holds fewer than N cells becomes a leaf holding all cells of its subtree, in DFS-leaf order.  Its
+    `_distance` becomes that of its LEFT child (the Q of the left child if that was an inner vertex, null if it was a leaf) —
+    a quirk of birch-beer's merge that the golden files show.  Pinned against the reference's golden
+    `workshop/out_pruned/*` (made with --min-size 30 from `workshop/out` through --prior)."""
+    tree = _as_flat(tree)
+    size = subtree_sizes(tree)
+    n = tree.n_nodes
+    # leaf items of every subtree: pre-order ids => the leaves of subtree(i) are the leaf ids in [i, i + count_i)
+    count = np.ones(n, dtype=np.int64)
+    for i in range(n - 1, -1, -1):
+        if tree.left[i] >= 0:
+            count[i] += count[tree.left[i]] + count[tree.right[i]]
+    left, right, q, items = [], [], [], []
+    stack = [(0, -1)]
+    while stack:
+        u, parent = stack.pop()
+        i = len(left)
+        left.append(-1); right.append(-1); q.append(float("nan")); items.append(None)
+        if parent >= 0:
+            if left[parent] < 0:
+                left[parent] = i
+            else:
+                right[parent] = i
+        inner = tree.left[u] >= 0
+        if inner and size[tree.left[u]] >= min_size and size[tree.right[u]] >= min_size:
+            q[i] = float(tree.q[u])
+            stack.append((int(tree.right[u]), i)); stack.append((int(tree.left[u]), i))
+        else:
+            merged = []
+            for v in range(u, u + int(count[u])):
+                if tree.left[v] < 0:
+                    merged.extend(int(r) for r in tree.items(v))
+            items[i] = merged
+            if inner and tree.left[tree.left[u]] >= 0:
+                q[i] = float(tree.q[tree.left[u]])
+    return FlatTree(left, right, q, items)
 
 
 def graph_dot(tree) -> str:
