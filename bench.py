@@ -266,9 +266,11 @@ def main():
                      "scatter_gbs": 0.5 * pair_bytes / (sc_ms * 1e-3) / 1e9, "gather_gbs": 0.5 * pair_bytes / (ga_ms * 1e-3) / 1e9}
     else:
         root_pair = None
-    # filled from the committed `ncu --set full` capture of the root-level pair launch (profiles/README.md) when one exists
-    # for this workload and storage mode
-    traffic = None
+    # dram__bytes_read + write of the root-level pair launch from the committed `ncu --set full` capture
+    # (profiles/r1_v4_spmv_pair_c3_factored_ncu_raw.csv: k_tgather_t 16.74 GB + k_gather 10.09 GB); the algorithmic bytes of
+    # that launch are 2*nnz*(2+4) + vectors = 20.1 GB: the column-sorted copy also stores the cell position of every entry
+    # (10 B per entry instead of 6), that is the whole difference - nothing is read twice.
+    traffic = 26.83e9 if (name == "c3" and world == 1 and tr.stats["value_bytes"] == 2) else None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
             "traffic": traffic, "traffic_scope": "root-level pair launch (largest launch), ncu dram bytes" if traffic else None, "peak_source": peak_src, "kernel": "k_tgather_t + k_gather (SpMV pair y = C^T x from the column-sorted blocks, x' = C y from the CSR), all launches of the timed steps",
             "algorithmic_bytes_per_step": alg / len(trees), "value_bytes_b_v": tr.stats["value_bytes"],
