@@ -685,9 +685,6 @@ struct Engine {
     } catch (...) { cudaFree(d); throw; }
     cudaFree(d);
   }
-  void allreduce_u8(uint8_t* p, size_t n) {
-    if (c.world > 1 && n) nccl_check(g_nccl.AllReduce(p, p, n, NCCL_UINT8, NCCL_SUM, g_nccl.comm, s), "ncclAllReduce(u8)");
-  }
 
   // One sweep: every live slot advances by one step of its lifecycle
   // (degree pass | start-vector orthogonalisation | Lanczos step | modularity + split).
@@ -772,8 +769,7 @@ struct Engine {
             else if (tg_variant == 2) k_tgather_t<4, 0, VT><<<ntch, 256, 0, s>>>(c, 0);
             else {
               if (n_big) {
-                if (tg_variant == 3) k_tgather_t<2, 0, VT><<<ntch, 256, 0, s>>>(c, n_small ? 1 : 0);
-                else k_tgather_t<4, 1, VT><<<ntch, 256, 0, s>>>(c, n_small ? 1 : 0);
+                k_tgather_t<4, 1, VT><<<ntch, 256, 0, s>>>(c, n_small ? 1 : 0);
                 if (n_small) n_launch++;
               }
               if (n_small) k_tgather_t<4, 0, VT><<<ntch, 256, 0, s>>>(c, n_big ? 2 : 0);
