@@ -150,6 +150,22 @@ int tmc_spmv_pair(tmc_matrix* b, const int64_t* rows, int64_t n_sel, const doubl
  * scatter (y = C^T x) and gather (x' = C y) kernel, measured with CUDA events on the engine stream. */
 int tmc_bench_spmv_pair(tmc_matrix* b, int reps, double* scatter_ms, double* gather_ms);
 
+/* ---- the steps right before the hot path, on the GPU.  Results are library-owned HOST arrays. */
+typedef struct {
+  int64_t n_rows, n_cols, nnz;
+  const int64_t* row_ptr; const int32_t* col_idx; const double* val;
+  const int64_t* kept_rows; const int64_t* kept_cols;      /* tmc_filter_thresholds: original ids of the kept rows / columns */
+  int64_t n_kept_rows, n_kept_cols;
+} tmc_csr_out;
+/* == readMatrix + matToSpMat + transposeSM + sparsifySM (src/TooManyCells/Matrix/Load.hs:85-152): the text of a 10x
+ * `matrix.mtx` (already gunzipped; features x cells, coordinate real|integer|pattern) -> CSR.  transpose=1 gives
+ * cells x features (what make-tree wants); explicit zeros are dropped; entries sorted by (row, column). */
+int  tmc_mtx_parse(const char* text, int64_t n_bytes, int transpose, tmc_csr_out** out);
+/* == filterNumSparseMat (src/TooManyCells/Matrix/Preprocess.hs:342-386), --filter-thresholds "(MINCELL, MINFEATURE)":
+ * keep rows with sum >= row_thresh and columns with sum >= col_thresh, both sums over the ORIGINAL matrix. */
+int  tmc_filter_thresholds(const tmc_csr* a, double row_thresh, double col_thresh, tmc_csr_out** out);
+void tmc_csr_out_free(tmc_csr_out*);
+
 /* Multi-GPU (one process per GPU): NCCL communicator owned by the library.
  * Rank 0 calls tmc_comm_unique_id and ships the 128 bytes to the other ranks (torch.distributed),
  * then every rank calls tmc_comm_init. */

@@ -1,0 +1,83 @@
+"""SURVEY 8(f) N1 on the GPU: MatrixMarket ingest and --filter-thresholds, bit-exact against scipy / numpy."""
+import gzip
+import io
+import os
+
+import numpy as np
+import scipy.io
+import scipy.sparse as sp
+import pytest
+
+import too_many_cells_b200 as T
+from too_many_cells_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _mtx_bytes(a, field=None):
+    buf = io.BytesIO()
+    scipy.io.mmwrite(buf, a, field=field)
+    return buf.getvalue()
+
+
+def _same(a, b):
+    a = sp.csr_matrix(a); b = sp.csr_matrix(b)
+    a.sort_indices(); b.sort_indices()
+    return a.shape == b.shape and np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices) and np.array_equal(a.data, b.data)
+
+
+def test_parse_counts_transposed():
+    ip, ix, dv, _ = synth.synth_counts(400, 900, 60, 3, 5)
+    cells_by_feat = sp.csr_matrix((dv, ix, ip), shape=(400, 900))
+    text = _mtx_bytes(sp.coo_matrix(cells_by_feat.T), field="integer")          # 10x layout: features x cells
+    got = T.parse_matrix_market(text, transpose=True)
+    assert _same(got, cells_by_feat)
+    assert np.all(np.diff(got.indices[got.indptr[3]:got.indptr[4]]) > 0)       # sorted by feature inside a cell
+    assert _same(T.parse_matrix_market(text, transpose=False), cells_by_feat.T)
+
+
+def test_parse_real_values_exact_and_edge_cases():
+    rng = np.random.default_rng(3)
+    a = sp.random(57, 33, 0.2, random_state=4, data_rvs=lambda k: np.round(rng.uniform(-50, 50, k), 6)).tocoo()
+    text = _mtx_bytes(a)                                                        # `real` field, repr-style decimals
+    ref = scipy.io.mmread(io.BytesIO(text)).tocsr()
+    assert _same(T.parse_matrix_market(text, transpose=False), ref)
+    # comments, CRLF, blank lines, explicit zero (dropped like sparsifySM), exponent, pattern
+    txt = b"%%MatrixMarket matrix coordinate real general\r\n% a comment\r\n3 4 5\r\n1 1 2.5\r\n\r\n3 4 1e-3\r\n2 2 0\r\n2 3 -7\r\n  1   4   12  \r\n"
+    got = T.parse_matrix_market(txt, transpose=False).toarray()
+    exp = np.zeros((3, 4)); exp[0, 0] = 2.5; exp[2, 3] = 1e-3; exp[1, 2] = -7; exp[0, 3] = 12
+    assert np.array_equal(got, exp)
+    pat = b"%%MatrixMarket matrix coordinate pattern general\n2 3 3\n1 1\n2 3\n1 2\n"
+    assert np.array_equal(T.parse_matrix_market(pat, transpose=True).toarray(), np.array([[1, 0], [1, 0], [0, 1]], dtype=float))
+    for bad in (b"2 2 1\n1 1 1\n", b"%%MatrixMarket matrix coordinate real general\n2 2 1\n3 1 1\n", b"%%MatrixMarket matrix coordinate real general\n2 2 1\n1 x 1\n",
+                b"%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n"):
+        with pytest.raises(T.TmcError):
+            T.parse_matrix_market(bad)
+
+
+def test_load_cellranger_directory_and_tree(tmp_path):
+    ip, ix, dv, _ = synth.synth_counts(300, 800, 70, 3, 8)
+    a = sp.csr_matrix((dv, ix, ip), shape=(300, 800))
+    with gzip.open(tmp_path / "matrix.mtx.gz", "wb") as f:
+        f.write(_mtx_bytes(sp.coo_matrix(a.T), field="integer"))
+    with gzip.open(tmp_path / "features.tsv.gz", "wt") as f:
+        f.write("".join(f"ENSG{j:06d}\tGENE{j}\tGene Expression\n" for j in range(800)))
+    with gzip.open(tmp_path / "barcodes.tsv.gz", "wt") as f:
+        f.write("".join(f"CELL{i:05d}-1\n" for i in range(300)))
+    mat, barcodes, features = T.load_cellranger_data(str(tmp_path), feature_column=2)
+    assert _same(mat, a) and barcodes[7] == "CELL00007-1" and features[5] == "GENE5"
+    cl, tree = T.h_spec_clust(T.tfidf_scale_sparse_mat(mat), barcodes)
+    assert len(cl) == 300 and sorted(r for _, r, _ in cl) == list(range(300))
+
+
+def test_filter_thresholds_vs_numpy():
+    rng = np.random.default_rng(11)
+    a = sp.random(500, 300, 0.05, random_state=5, data_rvs=lambda k: rng.integers(1, 9, k).astype(float)).tocsr()
+    for rt, ct in ((15.0, 20.0), (1.0, 1.0), (0.0, 0.0), (30.0, 5.0)):
+        got, kr, kc = T.filter_num_sparse_mat(a, rt, ct)
+        rs = np.asarray(a.sum(axis=1)).ravel(); cs = np.asarray(a.sum(axis=0)).ravel()       # both on the ORIGINAL matrix
+        er, ec = np.nonzero(rs >= rt)[0], np.nonzero(cs >= ct)[0]
+        assert np.array_equal(kr, er) and np.array_equal(kc, ec)
+        assert _same(got, a[er][:, ec])
+    with pytest.raises(T.TmcError):
+        T.filter_num_sparse_mat(a, 1e9, 1.0)                                     # reference: emptyMatCheckErr "cells"

@@ -48,6 +48,13 @@ class Tree(C.Structure):
                 ("value_bytes", C.c_int32), ("pad_", C.c_int32)]
 
 
+class CsrOut(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("n_cols", C.c_int64), ("nnz", C.c_int64),
+                ("row_ptr", C.POINTER(C.c_int64)), ("col_idx", C.POINTER(C.c_int32)), ("val", C.POINTER(C.c_double)),
+                ("kept_rows", C.POINTER(C.c_int64)), ("kept_cols", C.POINTER(C.c_int64)),
+                ("n_kept_rows", C.c_int64), ("n_kept_cols", C.c_int64)]
+
+
 # every symbol include/tmc.h declares: (restype, argtypes)
 _P = C.c_void_p
 SIGNATURES = {
@@ -70,6 +77,9 @@ SIGNATURES = {
     "tmc_partition": (C.c_int, [_P, C.c_int64, _P, _P, C.POINTER(C.c_int64)]),
     "tmc_spmv_pair": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "tmc_bench_spmv_pair": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "tmc_mtx_parse": (C.c_int, [C.c_char_p, C.c_int64, C.c_int, C.POINTER(C.POINTER(CsrOut))]),
+    "tmc_filter_thresholds": (C.c_int, [C.POINTER(Csr), C.c_double, C.c_double, C.POINTER(C.POINTER(CsrOut))]),
+    "tmc_csr_out_free": (None, [C.POINTER(CsrOut)]),
     "tmc_comm_unique_id": (C.c_int, [_P]),
     "tmc_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "tmc_comm_destroy": (None, []),

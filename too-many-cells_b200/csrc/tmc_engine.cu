@@ -504,6 +504,8 @@ struct Engine {
   enum { PH_PREPARE, PH_ZEROY, PH_TGATHER, PH_AR_Y, PH_GATHER, PH_YNORM, PH_DOTS, PH_AR_COEF, PH_UPDATE, PH_FINISH, PH_ADVANCE,
          PH_PARTITION, PH_TPART, PH_COMMIT_D2H, PH_N };
   double phase_ms[PH_N] = {0};
+  double host_ms[4] = {0, 0, 0, 0};     // launch (host side of a sweep), sync wait, harvest+handoff, activate
+  static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
   std::vector<cudaEvent_t> ph_pool; std::vector<std::pair<cudaEvent_t, int>> ph_marks; size_t ph_used = 0;
   void mark(int phase) {        // the time since the previous mark is charged to `phase`
     if (!phase_prof) return;
@@ -527,6 +529,8 @@ struct Engine {
     double tot = 0; for (int i = 0; i < PH_N; ++i) tot += phase_ms[i];
     fprintf(stderr, "[tmc] rank %d device time by phase (sum %.1f ms over %lld sweeps):\n", c.rank, tot, (long long)n_sweeps);
     for (int i = 0; i < PH_N; ++i) fprintf(stderr, "[tmc]   %-22s %9.2f ms  %5.1f%%\n", nm[i], phase_ms[i], 100.0 * phase_ms[i] / std::max(tot, 1e-9));
+    fprintf(stderr, "[tmc]   host: launching %.1f ms, waiting in sync %.1f ms, harvest+hand-off %.1f ms, activate %.1f ms\n", host_ms[0], host_ms[1],
+            host_ms[2], host_ms[3]);
   }
   bool profile = false;
   std::vector<cudaEvent_t> evs;
@@ -711,6 +715,7 @@ struct Engine {
       if (st == ST_ORTH0 || st == ST_LAN) n_or++;
     }
     if (!live_n) return;
+    const double sweep_t0 = phase_prof ? now_ms() : 0.0;
     // SpMV chunks: one row per warp while that still gives <= ~16k CTAs; vector chunks: up to 256 positions
     int R = 8;
     if (rows > 8 * 16384) R = (int)std::min<int64_t>(TMC_MAX_CHUNK, ((rows / 16384) + 7) / 8 * 8);
@@ -818,7 +823,9 @@ struct Engine {
     CK(cudaMemcpyAsync(w->h_rep, c.rep, sizeof(Report) * hi_slot, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(w->h_err, c.err, sizeof(int), cudaMemcpyDeviceToHost, s));
     mark(PH_COMMIT_D2H);
+    const double tsync0 = phase_prof ? now_ms() : 0.0;
     CK(cudaStreamSynchronize(s));
+    if (phase_prof) { const double t1 = now_ms(); host_ms[1] += t1 - tsync0; host_ms[0] += tsync0 - sweep_t0; }
     CK(cudaGetLastError());
     mark_flush();
     n_sweeps++;
@@ -904,7 +911,7 @@ struct Engine {
     if (b->n_rows_global >= 2) { build_tblock_sorted(nodes[0]); pending.push_back(0); }      // run_tree starts from the identity perm
     priv_top = m; t_top = (nodes[0].te + 7) & ~7ll;
     for (;;) {
-      activate_pending(0);
+      { const double t0 = phase_prof ? now_ms() : 0.0; activate_pending(0); if (phase_prof) host_ms[3] += now_ms() - t0; }
       if (rmode && c.collectives) {
         // the shared top of the tree is finished on every rank at the same sweep: from here on no collective is issued
         bool shared_left = !pending.empty();
@@ -913,8 +920,10 @@ struct Engine {
       }
       if (!live()) break;
       sweep();
+      const double t0 = phase_prof ? now_ms() : 0.0;
       harvest(true);
       if (rmode) do_handoffs();
+      if (phase_prof) host_ms[2] += now_ms() - t0;
     }
   }
 
@@ -1371,3 +1380,5 @@ void tmc_comm_destroy(void) {
 }
 
 }  // extern "C"
+
+#include "tmc_ingest.cuh"

@@ -1,0 +1,74 @@
+"""SURVEY.md 8(f) N1 — the steps right before the hot path, through libtmc on the GPU.
+
+  load_cellranger_data   src/TooManyCells/Matrix/Load.hs:85-152 (10x directory: matrix.mtx[.gz], features.tsv[.gz] /
+                         genes.tsv, barcodes.tsv[.gz]; the MTX file is features x cells and is transposed to cells x features)
+  filter_num_sparse_mat  src/TooManyCells/Matrix/Preprocess.hs:342-386 (--filter-thresholds "(MINCELL, MINFEATURE)")
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import CsrOut, check
+from .spectral import HostCsr
+
+
+def _csr_from_out(op):
+    import scipy.sparse as sp
+    o = op.contents
+    m, n, nnz = int(o.n_rows), int(o.n_cols), int(o.nnz)
+    arr = lambda p, k, dt: (np.ctypeslib.as_array(p, shape=(k,)).astype(dt, copy=True) if k else np.zeros(0, dt))
+    mat = sp.csr_matrix((arr(o.val, nnz, np.float64), arr(o.col_idx, nnz, np.int32), arr(o.row_ptr, m + 1, np.int64)), shape=(m, n))
+    kr = arr(o.kept_rows, int(o.n_kept_rows), np.int64) if o.kept_rows else None
+    kc = arr(o.kept_cols, int(o.n_kept_cols), np.int64) if o.kept_cols else None
+    _lib.load().tmc_csr_out_free(op)
+    return mat, kr, kc
+
+
+def parse_matrix_market(data: bytes, transpose=True):
+    """MatrixMarket coordinate text -> scipy CSR (cells x features when transpose=True, as loadCellrangerData does)."""
+    lib = _lib.load()
+    op = C.POINTER(CsrOut)()
+    check(lib.tmc_mtx_parse(data, len(data), int(bool(transpose)), C.byref(op)))
+    return _csr_from_out(op)[0]
+
+
+def _read(path):
+    with open(path, "rb") as f:
+        raw = f.read()
+    return gzip.decompress(raw) if path.endswith(".gz") else raw
+
+
+def _first_existing(d, names):
+    for nm in names:
+        p = os.path.join(d, nm)
+        if os.path.exists(p):
+            return p
+    raise FileNotFoundError(f"none of {names} in {d}")
+
+
+def load_cellranger_data(folder, feature_column=1):
+    """Returns (matrix cells x features, barcodes, features) like SingleCells{_matrix,_rowNames,_colNames}.
+    `feature_column` is 1-based as the reference's --feature-column."""
+    mtx = _first_existing(folder, ["matrix.mtx.gz", "matrix.mtx"])
+    feat = _first_existing(folder, ["features.tsv.gz", "features.tsv", "genes.tsv.gz", "genes.tsv"])
+    bar = _first_existing(folder, ["barcodes.tsv.gz", "barcodes.tsv"])
+    mat = parse_matrix_market(_read(mtx), transpose=True)
+    features = [ln.split("\t")[min(feature_column - 1, len(ln.split("\t")) - 1)] for ln in _read(feat).decode().splitlines() if ln]
+    barcodes = [ln.split("\t")[0] for ln in _read(bar).decode().splitlines() if ln]
+    if mat.shape != (len(barcodes), len(features)):
+        raise ValueError(f"matrix is {mat.shape} but there are {len(barcodes)} barcodes and {len(features)} features")
+    return mat, barcodes, features
+
+
+def filter_num_sparse_mat(mat, row_thresh, col_thresh):
+    """filterNumSparseMat: returns (filtered matrix, kept row ids, kept column ids)."""
+    lib = _lib.load()
+    h = HostCsr(mat)
+    op = C.POINTER(CsrOut)()
+    check(lib.tmc_filter_thresholds(C.byref(h.c), float(row_thresh), float(col_thresh), C.byref(op)))
+    return _csr_from_out(op)
