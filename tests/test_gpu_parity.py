@@ -289,3 +289,33 @@ def test_large_config_properties():
     # idempotence / determinism of membership
     t2 = T.hierarchical_spectral_cluster(a, normalize=True, seed=12345)    # different start vector, same tree
     assert tree.leaf_sets() == t2.leaf_sets()
+
+
+def test_full_size_config2_properties():
+    """BASELINE.json configs[1] at full size (100k cells x 30k genes, ~1.75e8 nnz, generated on the device): the oracle
+    cannot run here in seconds, so the tree is checked through size-independent properties."""
+    import torch
+    n, g, k, d, s, binary = synth.CONFIGS["c2"]
+    dev = torch.device("cuda", 0)
+    rp, col, val = synth.synth_counts_torch(n, g, k, d, s, dev, binary)
+    b = T.DeviceB.adopt_device(n, g, rp, col, val, normalize=True, device=0)
+    t1 = T.hierarchical_spectral_cluster(b)
+    assert np.array_equal(np.sort(t1.perm), np.arange(n))                         # every cell in exactly one leaf
+    leaves = t1.leaves()
+    assert sum(len(t1.items(i)) for i in leaves) == n and len(leaves) > 100
+    inner = np.nonzero(t1.left >= 0)[0]
+    assert np.all(t1.q[inner] > 0) and np.all(t1.q[inner] <= 0.5)                 # split iff Q > 0; Q <= 1/2 for a bipartition
+    assert np.all(t1.q[[i for i in leaves if len(t1.items(i)) >= 2]] <= 0)
+    for i in leaves[:200]:
+        assert np.all(np.diff(t1.items(i)) > 0)                                   # stable partitions: ascending rows in a leaf
+    for i in inner[:200]:                                                          # children partition the parent
+        assert t1.item_begin[t1.left[i]] == t1.item_begin[i] and t1.item_end[t1.right[i]] == t1.item_end[i]
+        assert t1.item_end[t1.left[i]] == t1.item_begin[t1.right[i]]
+    # determinism of the result: another start vector, the other transposed-product path, and a looser-but-safe tolerance
+    t2 = T.hierarchical_spectral_cluster(b, seed=987654321)
+    assert t1.leaf_sets() == t2.leaf_sets()
+    assert np.max(np.abs(np.sort(t1.q) - np.sort(t2.q))) < 1e-9
+    t3 = T.hierarchical_spectral_cluster(b, scatter_mode=1)
+    assert t1.leaf_sets() == t3.leaf_sets()
+    b.free()
+    T._lib.load().tmc_cache_clear()

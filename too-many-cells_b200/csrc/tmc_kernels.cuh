@@ -942,7 +942,9 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
     const bool check = exhausted || breakdown || full || j <= 64 || (j & 3) == 0;     // T_j is tiny: test every step early on
     if (!check) { if (lane == 0) s->action = ACT_NEXT; return; }
     __threadfence_block();
-    const double theta = tmc_top_eig_warp(A, B, j, s->theta_hint);
+    // bracket from the previous test: theta grows monotonically with j and (when the nearest eigenvalue of T_j is the top
+    // one) by no more than the previous residual; both hints are verified with a Sturm count before use
+    const double theta = tmc_top_eig_warp(A, B, j, s->theta_hint, (s->theta_hint > -1e299) ? s->theta + 1.0001 * s->resid + 1e-15 : 1e300);
     if (lane == 0) {
       double* z = c.zvec + (int64_t)slot * K2;
       double* scr = c.scratch + (int64_t)slot * 2 * K2;

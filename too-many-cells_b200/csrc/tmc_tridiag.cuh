@@ -105,13 +105,17 @@ TMC_HD double tmc_top_eig_serial(const double* a, const double* b, int j, double
 #if defined(__CUDACC__)
 // Warp-cooperative 32-way multisection: every lane evaluates one Sturm count per round.
 // All 32 lanes must call; returns the same value on every lane.
-__device__ __forceinline__ double tmc_top_eig_warp(const double* a, const double* b, int j, double lo_hint) {
+__device__ __forceinline__ double tmc_top_eig_warp(const double* a, const double* b, int j, double lo_hint, double hi_hint = 1e300) {
   const unsigned lane = threadIdx.x & 31u;
   double lo, hi, pivmin;
   tmc_gershgorin(a, b, j, &lo, &hi, &pivmin);
   if (lo_hint > lo && lo_hint < hi) {
     int c = tmc_sturm_count(a, b, j, lo_hint, pivmin);
     if (c < j) lo = lo_hint;
+  }
+  if (hi_hint > lo && hi_hint < hi) {        // e.g. previous theta + previous residual: usually a valid, much tighter upper bound
+    int c = tmc_sturm_count(a, b, j, hi_hint, pivmin);
+    if (c >= j) hi = hi_hint;
   }
   for (int round = 0; round < 40; ++round) {
     double w = (hi - lo) / 33.0;
