@@ -166,6 +166,13 @@ int  tmc_mtx_parse(const char* text, int64_t n_bytes, int transpose, tmc_csr_out
 int  tmc_filter_thresholds(const tmc_csr* a, double row_thresh, double col_thresh, tmc_csr_out** out);
 void tmc_csr_out_free(tmc_csr_out*);
 
+/* ---- == secondLeft 1 N (b1ToB2 mat) (lsaSparseMat, src/TooManyCells/Matrix/Preprocess.hs:560-571): the first
+ * n_vec left singular vectors of the (optionally idf-scaled) matrix, by Lanczos over the same SpMV pair as the tree.
+ * u_out: n_rows x n_vec row-major (one n_vec-vector per cell, as S.fromRowsL builds it; each column unit-norm, sign arbitrary);
+ * sigma_out: n_vec singular values, descending; converged_out: 1 if every pair met opts->tol. */
+int tmc_left_singular(const tmc_csr* a, int normalize, int n_vec, const tmc_opts* opts, double* u_out, double* sigma_out,
+                      int* converged_out);
+
 /* Multi-GPU (one process per GPU): NCCL communicator owned by the library.
  * Rank 0 calls tmc_comm_unique_id and ships the 128 bytes to the other ranks (torch.distributed),
  * then every rank calls tmc_comm_init. */

@@ -319,3 +319,20 @@ def test_full_size_config2_properties():
     assert t1.leaf_sets() == t3.leaf_sets()
     b.free()
     T._lib.load().tmc_cache_clear()
+
+
+def test_lsa_truncated_svd_vs_lapack(tiny):
+    """lsaSparseMat = secondLeft 1 N . b1ToB2 — first N left singular vectors of the idf-scaled matrix."""
+    a, _, b2, _, _ = tiny
+    sub = a[:350]
+    for n_dim, normalize in ((5, True), (12, True), (3, False)):
+        u, sig, conv = T.lsa_sparse_mat(sub, n_dim, normalize=normalize)
+        dense = (O.b1_to_b2(sub) if normalize else sp.csr_matrix(sub, dtype=np.float64)).toarray()
+        uu, ss, _ = np.linalg.svd(dense, full_matrices=False)
+        assert conv and u.shape == (350, n_dim)
+        assert np.allclose(sig, ss[:n_dim], rtol=1e-9, atol=0)
+        for i in range(n_dim):
+            gap = min(abs(ss[i] - ss[i - 1]) if i else np.inf, abs(ss[i] - ss[i + 1]))
+            if gap / ss[0] > 1e-6:
+                assert abs(abs(u[:, i] @ uu[:, i]) - 1.0) < 1e-7, (n_dim, i)
+        assert np.allclose(u.T @ u, np.eye(n_dim), atol=1e-8)

@@ -80,6 +80,7 @@ SIGNATURES = {
     "tmc_mtx_parse": (C.c_int, [C.c_char_p, C.c_int64, C.c_int, C.POINTER(C.POINTER(CsrOut))]),
     "tmc_filter_thresholds": (C.c_int, [C.POINTER(Csr), C.c_double, C.c_double, C.POINTER(C.POINTER(CsrOut))]),
     "tmc_csr_out_free": (None, [C.POINTER(CsrOut)]),
+    "tmc_left_singular": (C.c_int, [C.POINTER(Csr), C.c_int, C.c_int, C.POINTER(Opts), _P, _P, C.POINTER(C.c_int)]),
     "tmc_comm_unique_id": (C.c_int, [_P]),
     "tmc_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "tmc_comm_destroy": (None, []),

@@ -351,7 +351,7 @@ static void renumber_columns(tmc_matrix* b) {
   cudaFree(buf); cudaFree(tmp);
 }
 
-static void prepare_matrix(tmc_matrix* b, int normalize) {
+static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
   renumber_columns(b);
   int* d_flags = dalloc<int>(2);
   int* df = nullptr; double* idf = nullptr;
@@ -378,7 +378,7 @@ static void prepare_matrix(tmc_matrix* b, int normalize) {
     if (!small_int) {
       cudaFree(d_flags); d_flags = nullptr;
       b->vt = VT_F64;
-      normalise_dev(b, normalize, nullptr, nullptr, true);
+      normalise_dev(b, normalize, nullptr, nullptr, do_l2);
       return;
     }
     b->vt = (f[0] & 16) ? VT_U16 : VT_ONE;
@@ -393,7 +393,8 @@ static void prepare_matrix(tmc_matrix* b, int normalize) {
       k_idf<<<(int)((b->n_cols + 255) / 256), 256>>>(df, (int)b->n_cols, (double)b->n_rows_global, idf);
     }
     factor_bufs_acquire(b, b->vt == VT_U16);
-    k_row_factor<<<grid, 256>>>(b->row_ptr, b->col, b->val, idf, (int)b->n_rows, b->rrow, d_flags + 1);
+    if (do_l2) k_row_factor<<<grid, 256>>>(b->row_ptr, b->col, b->val, idf, (int)b->n_rows, b->rrow, d_flags + 1);
+    else k_fill_f64<<<(unsigned)((b->n_rows + 255) / 256), 256>>>(b->rrow, b->n_rows, 1.0);      // truncated SVD of B2 itself: no row factor
     k_col_factors<<<(int)((b->n_cols + 255) / 256), 256>>>(idf, (int)b->n_cols, b->w2col, b->invw);
     if (b->vt == VT_U16) {
       k_to_u16<<<grid, 256>>>(b->val, reinterpret_cast<unsigned short*>(b->valc), b->nnz);
@@ -492,6 +493,7 @@ struct Engine {
   std::deque<int> pending, pending_priv;
   int hi_slot = 0;
   // replicated mode ("deeper subtrees as per-GPU tasks")
+  int act_nev = 0;      // > 0: the next activation runs in truncated-SVD mode
   bool rmode = false; int n_shared_slots = 0; int handoff_rows = 0;
   int priv_top = 0; long long t_top = 0;
   std::vector<int> handoff_list; std::vector<long long> owner_load; int n_handoffs = 0;
@@ -642,7 +644,7 @@ struct Engine {
         int node = q.front(); q.pop_front();
         int slot = fs.top(); fs.pop();
         w->h_act[n++] = Activation{slot, nodes[node].begin, nodes[node].end, nodes[node].gsize, node, stop_after, nodes[node].tpar, priv,
-                                   nodes[node].tb, nodes[node].te};
+                                   nodes[node].tb, nodes[node].te, act_nev, 0};
         hstate[slot] = ST_DEG; slot_node[slot] = node;
         hi_slot = std::max(hi_slot, slot + 1);
       }
@@ -1349,6 +1351,41 @@ int tmc_bench_spmv_pair(tmc_matrix* b, int reps, double* scatter_ms, double* gat
       if (gather_ms) *gather_ms = ga / reps;
     } catch (...) { cudaFree(xd); throw; }
     cudaFree(xd);
+  });
+}
+
+// ---- truncated SVD through the same SpMV pair (LSA = `secondLeft 1 N . unB2 . b1ToB2 . B1`,
+// src/TooManyCells/Matrix/Preprocess.hs:560-571; `sparseSvd` idiom :512-520)
+int tmc_left_singular(const tmc_csr* a, int normalize, int n_vec, const tmc_opts* opts, double* u_out, double* sigma_out, int* converged_out) {
+  return guarded([&] {
+    check_opts(opts);
+    if (!a || !u_out || n_vec < 1) throw TmcError(TMC_ERR_INVALID, "bad arguments");
+    if (g_nccl.comm && g_nccl.world > 1) throw TmcError(TMC_ERR_UNSUPPORTED, "tmc_left_singular is single-rank");
+    if (n_vec > a->n_rows || n_vec > a->n_cols) throw TmcError(TMC_ERR_INVALID, "more singular vectors requested than min(rows, cols)");
+    tmc_matrix* b = upload(a, opts->device);
+    double *zm = nullptr, *uo = nullptr, *ev = nullptr; int* cv = nullptr;
+    try {
+      prepare_matrix(b, normalize, /*do_l2=*/false);
+      tmc_opts o = *opts;
+      o.max_lanczos = (int)std::min<int64_t>(std::max(o.max_lanczos, 8 * n_vec + 64), std::min(a->n_rows, a->n_cols) + 1);
+      o.max_active = 1;
+      Engine eng(b, o);
+      const int K2 = eng.w->K + 2;
+      zm = dalloc<double>((size_t)n_vec * K2); uo = dalloc<double>((size_t)a->n_rows * n_vec); ev = dalloc<double>(n_vec); cv = dalloc<int>(1);
+      CK(cudaMemset(cv, 0, sizeof(int)));
+      eng.c.zmulti = zm; eng.c.uout = uo; eng.c.ev_out = ev; eng.c.svd_conv = cv;
+      eng.act_nev = n_vec;
+      eng.init_perm(nullptr, 0);
+      eng.run_single((int)a->n_rows, 0, true);
+      CK(cudaMemcpyAsync(u_out, uo, sizeof(double) * (size_t)a->n_rows * n_vec, cudaMemcpyDeviceToHost, eng.s));
+      std::vector<double> hev(n_vec); int hcv = 0;
+      CK(cudaMemcpyAsync(hev.data(), ev, sizeof(double) * n_vec, cudaMemcpyDeviceToHost, eng.s));
+      CK(cudaMemcpyAsync(&hcv, cv, sizeof(int), cudaMemcpyDeviceToHost, eng.s));
+      CK(cudaStreamSynchronize(eng.s));
+      if (sigma_out) for (int i = 0; i < n_vec; ++i) sigma_out[i] = sqrt(std::max(hev[i], 0.0));
+      if (converged_out) *converged_out = hcv;
+    } catch (...) { cudaFree(zm); cudaFree(uo); cudaFree(ev); cudaFree(cv); tmc_matrix_free(b); throw; }
+    cudaFree(zm); cudaFree(uo); cudaFree(ev); cudaFree(cv); tmc_matrix_free(b);
   });
 }
 

@@ -16,7 +16,7 @@ namespace tmc {
 
 enum ValType : int { VT_F64 = 0, VT_U16 = 1, VT_ONE = 2 };
 enum SlotState : int { ST_IDLE = 0, ST_DEG = 1, ST_ORTH0 = 2, ST_LAN = 3, ST_MOD = 4, ST_DONE = 5 };
-enum SlotAction : int { ACT_NONE = 0, ACT_INIT = 1, ACT_NEXT = 2, ACT_RITZ_LABEL = 3, ACT_RITZ_RESTART = 4, ACT_FINISH = 5 };
+enum SlotAction : int { ACT_NONE = 0, ACT_INIT = 1, ACT_NEXT = 2, ACT_RITZ_LABEL = 3, ACT_RITZ_RESTART = 4, ACT_FINISH = 5, ACT_RITZ_MULTI = 6 };
 
 // scalar slots at the tail of a reduction row
 enum { R_NRM2 = 0, R_SUMD = 1, R_YNORM2 = 2, R_N1 = 3, R_SD1 = 4, R_NSCAL = 8 };
@@ -34,7 +34,7 @@ struct Slot {              // one live tree node (device resident)
   int stop_after;          // 0 = full lifecycle, else stop when reaching this state (fine-grained API)
   int tpar;                // which of the two transposed buffers holds this node's column-sorted block
   int priv;                // 1 = the whole node lives on this rank (handed-off subtree): no collectives, gsize = local size
-  int pad2;
+  int nev;                 // > 0: truncated-SVD mode: top `nev` left singular vectors of B, no deflation, no split
   long long tb, te;        // the block: entries [tb, te) of tcol/tpos/tval[tpar], sorted by column
   long long tnnz0;         // entries of label-0 cells (set by k_tpart_scan): children blocks are [tb, tb+tnnz0) and [tb+tnnz0, te)
   int tchunk0, ntchunk;    // this sweep's chunks of the block (set by k_prepare)
@@ -50,7 +50,7 @@ struct Report {            // what the host reads back after every sweep
 
 struct Chunk { int slot, begin, len; };
 struct TChunk { long long begin; int slot, pad; };        // entries [begin, begin + tchunk) of the slot's transposed block
-struct Activation { int slot, begin, end, gsize, node, stop_after, tpar, priv; long long tb, te; };
+struct Activation { int slot, begin, end, gsize, node, stop_after, tpar, priv; long long tb, te; int nev, pad; };
 
 struct Ctx {
   // matrix B (CSR, rows = cells)
@@ -88,6 +88,8 @@ struct Ctx {
   double tol, min_modularity; int min_size, max_restarts; uint64_t seed;
   int rank, world;
   int collectives;                 // 0 once only private (handed-off) nodes remain: ranks run free
+  // truncated-SVD mode (one slot): Ritz vectors of T for the top nev values [nev][K+2], output U [m][nev] (cells x nev), sigma^2 [nev]
+  double* zmulti; double* uout; double* ev_out; int* svd_conv;
 };
 
 __device__ __forceinline__ double* slot_scal(const Ctx& c, int slot) { return c.redB + (int64_t)slot * (c.K + 2 + R_NSCAL) + (c.K + 2); }
@@ -269,6 +271,7 @@ __global__ void k_row_factor(const int64_t* __restrict__ row_ptr, const int32_t*
     if (lane == 0) { if (!(ss > 0)) { atomicMax(err, 4); rrow[r] = 0.0; } else rrow[r] = 1.0 / sqrt(ss); }
   }
 }
+__global__ void k_fill_f64(double* __restrict__ p, int64_t n, double v) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 __global__ void k_col_factors(const double* __restrict__ w, int n_cols, double* __restrict__ w2, double* __restrict__ invw) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n_cols) { const double x = w ? w[j] : 1.0; w2[j] = x * x; invw[j] = x != 0.0 ? 1.0 / x : 0.0; }
@@ -283,7 +286,7 @@ __global__ void k_activate(Ctx c, const Activation* __restrict__ acts, int n) {
   s.begin = a.begin; s.end = a.end; s.gsize = a.gsize; s.n0_local = 0;
   s.state = ST_DEG; s.action = ACT_NONE; s.j = 0; s.iters = 0; s.restarts = 0; s.node = a.node;
   s.split = 0; s.n0 = 0; s.stop_after = a.stop_after;
-  s.tpar = a.tpar; s.priv = a.priv; s.pad2 = 0; s.tb = a.tb; s.te = a.te; s.tnnz0 = 0; s.tchunk0 = 0; s.ntchunk = 0;
+  s.tpar = a.tpar; s.priv = a.priv; s.nev = a.nev; s.tb = a.tb; s.te = a.te; s.tnnz0 = 0; s.tchunk0 = 0; s.ntchunk = 0;
   s.sumd = 0; s.inv_sqrt_sumd = 0; s.beta = 0; s.theta = 0; s.resid = 0; s.q = 0; s.theta_hint = -1e300;
   c.st[a.slot] = s;
   slot_scal(c, a.slot)[R_N1] = 0.0; slot_scal(c, a.slot)[R_SD1] = 0.0;
@@ -903,7 +906,8 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
     if (lane == 0) {
       double sumd = scal[R_SUMD];
       s->sumd = sumd;
-      if (!(sumd > 0) || isinf(sumd)) { atomicMax(c.err, 7); s->inv_sqrt_sumd = 0; }
+      if (s->nev) s->inv_sqrt_sumd = 0;
+      else if (!(sumd > 0) || isinf(sumd)) { atomicMax(c.err, 7); s->inv_sqrt_sumd = 0; }
       else s->inv_sqrt_sumd = 1.0 / sqrt(sumd);
       s->action = ACT_INIT;
     }
@@ -940,6 +944,36 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
     const bool breakdown = !(beta > 1e-13);
     const bool full = (j >= c.K);
     const bool check = exhausted || breakdown || full || j <= 64 || (j & 3) == 0;     // T_j is tiny: test every step early on
+    if (s->nev) {
+      // truncated SVD: the top nev Ritz pairs of T_j must all have converged (tested every 4th step)
+      const int nev = min(s->nev, j);
+      const bool test = exhausted || breakdown || full || ((j & 3) == 0 && j >= s->nev);
+      if (!test) { if (lane == 0) s->action = ACT_NEXT; return; }
+      __threadfence_block();
+      double* scr = c.scratch + (int64_t)slot * 2 * K2;
+      double lo, hi, piv;
+      tmc_gershgorin(A, B, j, &lo, &hi, &piv);
+      bool all_ok = true;
+      for (int i = 0; i < nev; ++i) {
+        const double th = tmc_top_eig_warp(A, B, j, -1e300, 1e300, i + 1);
+        double r = 0.0;
+        if (lane == 0) {
+          double* z = c.zmulti + (int64_t)i * K2;
+          tmc_twisted_vector(A, B, j, th, scr, scr + K2, z, piv);
+          c.ev_out[i] = th;
+          r = beta * fabs(z[j - 1]);
+        }
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (!(r <= c.tol * fmax(th, 1e-300) || r <= 1e-14)) all_ok = false;
+      }
+      if (lane == 0) {
+        const bool stop = all_ok || exhausted || breakdown || full;
+        *c.svd_conv = all_ok || exhausted || breakdown ? 1 : 0;
+        s->theta = c.ev_out[0];
+        s->action = stop ? ACT_RITZ_MULTI : ACT_NEXT;
+      }
+      return;
+    }
     if (!check) { if (lane == 0) s->action = ACT_NEXT; return; }
     __threadfence_block();
     // bracket from the previous test: theta grows monotonically with j and (when the nearest eigenvalue of T_j is the top
@@ -996,6 +1030,29 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
   const Slot& s = c.st[ch.slot];
   const int action = s.action;
   if (action == ACT_NONE || action == ACT_FINISH) return;
+  if (action == ACT_INIT && s.nev) {      // truncated SVD of B itself: no D^{-1/2}, no deflation (V_0 = 0)
+    for (int i = threadIdx.x; i < ch.len; i += 256) {
+      const int p = ch.begin + i;
+      c.sdeg[p] = (c.vt == VT_F64) ? 1.0 : c.rrow[c.perm[p]];
+      c.V[p] = 0.0;
+      c.w[p] = hash_unit(c.seed, (uint64_t)(c.row_offset + c.perm[p]));
+    }
+    return;
+  }
+  if (action == ACT_RITZ_MULTI) {
+    const int j = s.j, nev = min(s.nev, j);
+    for (int i = threadIdx.x; i < ch.len; i += 256) {
+      const int p = ch.begin + i;
+      for (int e = 0; e < nev; ++e) {
+        const double* z = c.zmulti + (int64_t)e * (c.K + 2);
+        double u = 0.0;
+        for (int l = 1; l <= j; ++l) u += z[l - 1] * c.V[(int64_t)l * c.vstride + p];
+        c.uout[(int64_t)c.perm[p] * s.nev + e] = u;
+      }
+      for (int e = nev; e < s.nev; ++e) c.uout[(int64_t)c.perm[p] * s.nev + e] = 0.0;
+    }
+    return;
+  }
   if (action == ACT_INIT) {
     const double isd = s.inv_sqrt_sumd;
     for (int i = threadIdx.x; i < ch.len; i += 256) {
@@ -1099,6 +1156,7 @@ __global__ void k_commit(Ctx c, int n_slots) {
     case ACT_RITZ_LABEL: state = ST_MOD; break;
     case ACT_RITZ_RESTART: state = ST_ORTH0; s->j = 0; break;
     case ACT_FINISH: state = ST_DONE; break;
+    case ACT_RITZ_MULTI: state = ST_DONE; break;
     default: break;
   }
   if (s->stop_after != 0 && state == s->stop_after && state != s->state) state = ST_DONE;   // fine-grained API stop

@@ -105,24 +105,26 @@ TMC_HD double tmc_top_eig_serial(const double* a, const double* b, int j, double
 #if defined(__CUDACC__)
 // Warp-cooperative 32-way multisection: every lane evaluates one Sturm count per round.
 // All 32 lanes must call; returns the same value on every lane.
-__device__ __forceinline__ double tmc_top_eig_warp(const double* a, const double* b, int j, double lo_hint, double hi_hint = 1e300) {
+__device__ __forceinline__ double tmc_top_eig_warp(const double* a, const double* b, int j, double lo_hint, double hi_hint = 1e300, int kth = 1) {
+  // kth = 1: the largest eigenvalue; kth = i: the i-th largest (smallest x with count(x) >= j - i + 1)
   const unsigned lane = threadIdx.x & 31u;
+  const int target = j - kth + 1;
   double lo, hi, pivmin;
   tmc_gershgorin(a, b, j, &lo, &hi, &pivmin);
   if (lo_hint > lo && lo_hint < hi) {
     int c = tmc_sturm_count(a, b, j, lo_hint, pivmin);
-    if (c < j) lo = lo_hint;
+    if (c < target) lo = lo_hint;
   }
   if (hi_hint > lo && hi_hint < hi) {        // e.g. previous theta + previous residual: usually a valid, much tighter upper bound
     int c = tmc_sturm_count(a, b, j, hi_hint, pivmin);
-    if (c >= j) hi = hi_hint;
+    if (c >= target) hi = hi_hint;
   }
   for (int round = 0; round < 40; ++round) {
     double w = (hi - lo) / 33.0;
     double x = lo + w * (double)(lane + 1);
     bool degenerate = !(x > lo && x < hi);
     int c = degenerate ? -1 : tmc_sturm_count(a, b, j, x, pivmin);
-    unsigned above = __ballot_sync(0xffffffffu, (!degenerate) && c >= j);   // x is an upper bound
+    unsigned above = __ballot_sync(0xffffffffu, (!degenerate) && c >= target);   // x is an upper bound
     unsigned valid = __ballot_sync(0xffffffffu, !degenerate);
     if (valid == 0u) break;
     double nlo = lo, nhi = hi;

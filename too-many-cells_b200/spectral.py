@@ -221,6 +221,19 @@ def bench_spmv_pair(b: DeviceB, reps=20):
     return sc.value, ga.value
 
 
+def lsa_sparse_mat(mat, n_dim, normalize=True, **opt_kw):
+    """lsaSparseMat (Preprocess.hs:560-571): cells x n_dim matrix of the first n_dim left singular vectors of the idf-scaled
+    matrix (`secondLeft 1 N . b1ToB2`).  Returns (U, singular_values, converged)."""
+    lib = _lib.load()
+    h = HostCsr(mat)
+    u = np.empty((h.shape[0], int(n_dim)), dtype=np.float64)
+    sig = np.empty(int(n_dim), dtype=np.float64)
+    conv = C.c_int()
+    o = make_opts(**opt_kw)
+    check(lib.tmc_left_singular(C.byref(h.c), int(bool(normalize)), int(n_dim), C.byref(o), u.ctypes.data, sig.ctypes.data, C.byref(conv)))
+    return u, sig, bool(conv.value)
+
+
 # ----------------------------------------------------------------------------- A0 / A9: the tree
 @dataclass
 class ClusteringTree:
