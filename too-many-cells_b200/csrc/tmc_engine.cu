@@ -501,6 +501,7 @@ struct Engine {
   double alg_vec_bytes = 0;     // non-matrix part of the spmv_pair algorithmic bytes
   double build_ms = 0;
   int tg_variant = getenv("TMC_TG") ? atoi(getenv("TMC_TG")) : 0;
+  int ga_variant = getenv("TMC_GA") ? atoi(getenv("TMC_GA")) : 0;
   // TMC_DEBUG=2: per-phase device time (CUDA events between the launches of a sweep), printed after the tree build
   bool phase_prof = getenv("TMC_DEBUG") && atoi(getenv("TMC_DEBUG")) >= 2;
   enum { PH_PREPARE, PH_ZEROY, PH_TGATHER, PH_AR_Y, PH_GATHER, PH_YNORM, PH_DOTS, PH_AR_COEF, PH_UPDATE, PH_FINISH, PH_ADVANCE,
@@ -789,7 +790,12 @@ struct Engine {
       mark(PH_TGATHER);
       if (c.collectives && sh_sc) { allreduce_f64(c.Y, (size_t)c.ystride * hi_shared); mark(PH_AR_Y); }
     }
-    if (n_ga && nch) { VT_DISPATCH(c.vt, k_gather<VT><<<nch, 256, 0, s>>>(c)); n_launch++; }
+    if (n_ga && nch) {
+      VT_DISPATCH(c.vt,
+        if (ga_variant == 1) k_gather<VT><<<nch, 256, 0, s>>>(c);            // first pipelined version (values converted before the prefetch stage)
+        else k_gather_u<VT, 4><<<nch, 256, 0, s>>>(c));                       // raw values in the prefetch stage: 5-7 % faster on c2/c3 roots
+      n_launch++;
+    }
     mark(PH_GATHER);
     if (profile && n_sc) { e2 = ev(); prof_pairs.push_back({e0, e1, e2}); }
     if (only_spmv) { CK(cudaGetLastError()); return; }

@@ -811,6 +811,85 @@ __global__ void TMC_GATHER_LB k_gather(Ctx c) {
   }
 }
 
+// The gather in use: U x 32 entries in flight, values kept RAW (uint16) through the prefetch stage (k_gather above is the
+// first pipelined version, kept for A/B runs with TMC_GA=1; U = 6 / 8 measured slower: 72 / 80 registers)
+template <int VT> struct RawVal { typedef double T; };
+template <> struct RawVal<VT_U16> { typedef unsigned short T; };
+template <> struct RawVal<VT_ONE> { typedef unsigned char T; };
+template <int VT> __device__ __forceinline__ typename RawVal<VT>::T ld_raw(const void* base, int64_t k) {
+  if (VT == VT_F64) return (typename RawVal<VT>::T)__ldg(reinterpret_cast<const double*>(base) + k);
+  if (VT == VT_U16) return (typename RawVal<VT>::T)__ldg(reinterpret_cast<const unsigned short*>(base) + k);
+  return (typename RawVal<VT>::T)1;
+}
+template <int VT, int U>
+__global__ void __launch_bounds__(256) k_gather_u(Ctx c) {
+  __shared__ double sm8[8];
+  if ((int)blockIdx.x >= *c.n_chunks) return;
+  const Chunk ch = c.chunks[blockIdx.x];
+  const int state = c.st[ch.slot].state;
+  if (state != ST_DEG && state != ST_LAN) return;
+  const double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride;
+  const int32_t* __restrict__ col = c.col;
+  const void* __restrict__ val = c.val;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  typedef typename RawVal<VT>::T RT;
+  double dsum = 0.0;
+  long long nz = 0;
+  int r = warp;
+  int64_t rs = 0, re = 0;
+  int row_cur = 0;
+  if (r < ch.len) { row_cur = c.perm[ch.begin + r]; rs = c.row_ptr[row_cur]; re = c.row_ptr[row_cur + 1]; }
+  while (r < ch.len) {
+    const int p = ch.begin + r;
+    const int rn = r + 8;
+    int64_t nrs = 0, nre = 0;
+    int nrow = 0;
+    if (rn < ch.len) { nrow = c.perm[ch.begin + rn]; nrs = c.row_ptr[nrow]; nre = c.row_ptr[nrow + 1]; }
+    nz += re - rs;
+    double acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = 0.0;
+    int64_t k = rs + lane;
+    bool have = (k + 32 * (U - 1) < re);
+    int cc[U]; RT vv[U];
+    if (have) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) { cc[u] = __ldg(col + k + 32 * u); vv[u] = ld_raw<VT>(val, k + 32 * u); }
+    }
+    while (have) {
+      const int64_t kn = k + 32 * U;
+      const bool have_n = (kn + 32 * (U - 1) < re);
+      int dc[U]; RT dv[U];
+      if (have_n) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) { dc[u] = __ldg(col + kn + 32 * u); dv[u] = ld_raw<VT>(val, kn + 32 * u); }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] += (double)vv[u] * __ldg(y + cc[u]);
+      if (have_n) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) { cc[u] = dc[u]; vv[u] = dv[u]; }
+      }
+      k = kn; have = have_n;
+    }
+    for (; k < re; k += 32) acc[0] += ld_val<VT>(val, k) * __ldg(y + __ldg(col + k));
+    double sacc = 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) sacc += acc[u];
+    const double s = warp_sum(sacc);
+    if (lane == 0) {
+      if (state == ST_DEG) { const double dv2 = (VT == VT_F64) ? s : s * c.rrow[row_cur]; c.d[p] = dv2; dsum += dv2; }
+      else c.w[p] = c.sdeg[p] * s;
+    }
+    r = rn; rs = nrs; re = nre; row_cur = nrow;
+  }
+  if (lane == 0 && nz) atomicAdd(c.stats + (state == ST_DEG ? 1 : 0), (unsigned long long)nz);
+  if (state == ST_DEG) {
+    double t = block_sum_256(dsum, sm8);
+    if (threadIdx.x == 0) atomicAdd(slot_scal(c, ch.slot) + R_SUMD, t);
+  }
+}
+
 // ||y_S||^2 for slots in the modularity state; grid (slots_used, ny). Columns are split over ranks.
 __global__ void __launch_bounds__(256) k_ynorm(Ctx c) {
   __shared__ double sm8[8];
