@@ -81,3 +81,36 @@ def test_filter_thresholds_vs_numpy():
         assert _same(got, a[er][:, ec])
     with pytest.raises(T.TmcError):
         T.filter_num_sparse_mat(a, 1e9, 1.0)                                     # reference: emptyMatCheckErr "cells"
+
+
+def test_make_tree_driver_end_to_end(tmp_path, capsys):
+    """10x directory -> --filter-thresholds -> tf-idf -> tree -> --min-size -> the reference's output files + stdout CSV."""
+    import importlib.util, json
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("make_tree_driver", os.path.join(ROOT, "tools", "make_tree.py"))
+    drv = importlib.util.module_from_spec(spec); spec.loader.exec_module(drv)
+    ip, ix, dv, _ = synth.synth_counts(500, 1200, 80, 3, 12)
+    a = sp.csr_matrix((dv, ix, ip), shape=(500, 1200))
+    d = tmp_path / "tenx"; d.mkdir()
+    with gzip.open(d / "matrix.mtx.gz", "wb") as f:
+        f.write(_mtx_bytes(sp.coo_matrix(a.T), field="integer"))
+    with gzip.open(d / "features.tsv.gz", "wt") as f:
+        f.write("".join(f"G{j}\tGENE{j}\tGene Expression\n" for j in range(1200)))
+    with gzip.open(d / "barcodes.tsv.gz", "wt") as f:
+        f.write("".join(f"CELL{i:05d}-1\n" for i in range(500)))
+    out = tmp_path / "out"
+    flat = drv.main(["--matrix-path", str(d), "--output", str(out), "--filter-thresholds", "(60, 2)", "--min-size", "20"])
+    stdout = capsys.readouterr().out
+    assert stdout.startswith("cell,cluster,path\n") and stdout.count("\r\n") >= 400
+    for name in ("cluster_tree.json", "cluster_list.json", "cluster_info.csv", "node_info.csv", "graph.dot", "clusters.csv"):
+        assert (out / name).exists()
+    sizes = [len(flat.items(i)) for i in range(flat.n_nodes) if flat.left[i] < 0]
+    assert min(sizes) >= 20 or flat.n_nodes == 1
+    nested = json.loads((out / "cluster_tree.json").read_text())
+    assert nested[0]["_item"] is None or flat.n_nodes == 1
+    # the same tree as calling the engine on the filtered matrix directly
+    keep_r = np.asarray(a.sum(axis=1)).ravel() >= 60; keep_c = np.asarray(a.sum(axis=0)).ravel() >= 2
+    t = T.hierarchical_spectral_cluster(a[keep_r][:, keep_c], normalize=True)
+    pruned = T.tree_io.prune_min_size(T.tree_io.FlatTree(t.left, t.right, t.q, [t.items(i) if t.left[i] < 0 else None for i in range(t.n_nodes)]), 20)
+    assert sorted(tuple(flat.items(i)) for i in range(flat.n_nodes) if flat.left[i] < 0) == \
+           sorted(tuple(int(x) for x in pruned.items(i)) for i in range(pruned.n_nodes) if pruned.left[i] < 0)
