@@ -288,3 +288,50 @@ extern "C" void exp_gather_smem(int nt, const int64_t* rp, const int* col, const
 extern "C" void exp_gather_u16(const int64_t* rp, const int* col, const unsigned short* val, const int* perm, const double* y, double* w, int n_rows, int rpc) {
   g_u16<<<(n_rows + rpc - 1) / rpc, 256>>>(rp, col, val, perm, y, w, n_rows, rpc);
 }
+
+// EXPERIMENT: transposed gather with the entries ordered by (position block, column, position) and the x window of the
+// block staged in shared memory (PB positions).  One CTA = one contiguous share of one position block.
+template <int PB>
+__global__ void __launch_bounds__(256) t_posblk(const int* __restrict__ tcol, const int* __restrict__ tpos, const unsigned short* __restrict__ tval,
+                                                const long long* __restrict__ blk_ptr, const double* __restrict__ x, double* __restrict__ y,
+                                                int n_rows, int shares) {
+  extern __shared__ double xs[];
+  const int pb = blockIdx.x / shares, sh = blockIdx.x % shares;
+  const long long b0 = blk_ptr[pb], b1 = blk_ptr[pb + 1];
+  long long per = ((b1 - b0 + shares - 1) / shares + 127) & ~127ll;
+  const long long e0 = b0 + sh * per, e1 = min(b1, e0 + per);
+  if (e0 >= e1) return;
+  const int p0 = pb * PB;
+  for (int i = threadIdx.x; i < PB; i += 256) xs[i] = (p0 + i < n_rows) ? x[p0 + i] : 0.0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long base = e0 + warp * 128; base < e1; base += 8 * 128) {
+    const long long k0 = base + lane * 4;
+    int cc[4]; double t[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long k = k0 + e;
+      if (k < e1) { cc[e] = __ldg(tcol + k); t[e] = (double)__ldg(tval + k) * xs[__ldg(tpos + k) - p0]; }
+      else { cc[e] = -1; t[e] = 0.0; }
+    }
+    const int cfirst = __shfl_sync(0xffffffffu, cc[0], 0), clast = __shfl_sync(0xffffffffu, cc[3], 31);
+    if (cfirst == clast && cfirst >= 0) {
+      double a = warp_sum((t[0] + t[1]) + (t[2] + t[3]));
+      if (lane == 0) atomicAdd(y + cfirst, a);
+      continue;
+    }
+    double acc = t[0]; int cur = cc[0];
+#pragma unroll
+    for (int e = 1; e < 4; ++e) {
+      if (cc[e] == cur) acc += t[e];
+      else { if (cur >= 0) atomicAdd(y + cur, acc); cur = cc[e]; acc = t[e]; }
+    }
+    if (cur >= 0) atomicAdd(y + cur, acc);
+  }
+}
+extern "C" void exp_tposblk(int pbsize, const int* tcol, const int* tpos, const unsigned short* tval, const long long* blk_ptr, int n_blocks,
+                            const double* x, double* y, int n_rows, int shares) {
+  if (pbsize == 8192) { cudaFuncSetAttribute(t_posblk<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8); t_posblk<8192><<<n_blocks * shares, 256, 8192 * 8>>>(tcol, tpos, tval, blk_ptr, x, y, n_rows, shares); }
+  else if (pbsize == 4096) { t_posblk<4096><<<n_blocks * shares, 256, 4096 * 8>>>(tcol, tpos, tval, blk_ptr, x, y, n_rows, shares); }
+  else { cudaFuncSetAttribute(t_posblk<16384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8); t_posblk<16384><<<n_blocks * shares, 256, 16384 * 8>>>(tcol, tpos, tval, blk_ptr, x, y, n_rows, shares); }
+}
