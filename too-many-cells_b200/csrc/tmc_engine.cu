@@ -192,6 +192,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     c.alpha = w->A<double>((size_t)(K + 2) * max_active); c.beta = w->A<double>((size_t)(K + 2) * max_active);
     c.zvec = w->A<double>((size_t)(K + 2) * max_active); c.scratch = w->A<double>((size_t)2 * (K + 2) * max_active);
     c.K = K;
+    c.list_offs = w->A<int>(3 * ((size_t)max_active + 1));
     c.chunks = w->A<Chunk>((size_t)m / 8 + max_active + 8);
     c.n_chunks = w->A<int>(1);
     c.vchunks = w->A<Chunk>((size_t)m / 32 + max_active + 8);
@@ -754,7 +755,9 @@ struct Engine {
       if (ntch > w->tcap) throw TmcError(TMC_ERR_CUDA, "internal: transposed chunk list overflow");
     }
     mark(PH_COMMIT_D2H);
-    k_prepare<<<1, 1024, 0, s>>>(c); n_launch++;
+    k_prepare<<<1, 1024, 0, s>>>(c);
+    k_prepare_fill<<<std::max(1, std::min(148, (std::max(std::max(nch, nvch), ntch) + 255) / 256)), 256, 0, s>>>(c);
+    n_launch += 2;
     if (c.vt != VT_F64 && n_deg && nvch) { k_deg_xin<<<nvch, 256, 0, s>>>(c); n_launch++; }
     mark(PH_PREPARE);
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;

@@ -72,6 +72,7 @@ struct Ctx {
   int n_slots;                     // slots [0, n_slots) may be live this sweep
   double* alpha; double* beta; double* zvec; double* scratch;   // [slot][K+2] (scratch: 2*(K+2))
   int K;
+  int* list_offs;                                    // [3][max_active+1] per-slot offsets into the three chunk lists
   Chunk* chunks; int* n_chunks; int chunk_rows;      // SpMV kernels: few rows per CTA (memory-level parallelism)
   Chunk* vchunks; int* n_vchunks; int vchunk_rows;   // vector kernels (dots/update/advance): up to 256 positions per CTA
   // transposed (column-sorted) per-node copy of B: y = B_S^T x as a gather with run merging instead of nnz atomics
@@ -292,8 +293,11 @@ __global__ void k_activate(Ctx c, const Activation* __restrict__ acts, int n) {
   slot_scal(c, a.slot)[R_N1] = 0.0; slot_scal(c, a.slot)[R_SD1] = 0.0;
 }
 
-// block-wide (1024 threads) construction of a chunk list over the live slots' local position ranges
-__device__ void build_chunk_list(const Ctx& c, int csize, Chunk* out, int* out_n, int* offs, int* wsum) {
+// Work lists, rebuilt on the device every sweep.  k_prepare (one CTA) scans the live slots into three offset tables
+// (SpMV chunks, vector chunks, transposed-block chunks) and zeroes the reduction rows; k_prepare_fill (many CTAs) writes the
+// chunk records (the single-CTA version spent 20-40 us per sweep writing up to 40k records).
+__device__ int block_scan_counts(const Ctx& c, int mode, int* offs, int* wsum) {
+  // mode 0: chunk_rows positions, 1: vchunk_rows positions, 2: tchunk entries of the transposed block (scatter states only)
   const int tid = threadIdx.x;
   const int per = (c.n_slots + 1023) / 1024;        // slots per thread (<= 4)
   int cnt[4]; int mine = 0;
@@ -301,56 +305,11 @@ __device__ void build_chunk_list(const Ctx& c, int csize, Chunk* out, int* out_n
     int slot = tid * per + q; int n = 0;
     if (slot < c.n_slots) {
       const Slot& s = c.st[slot];
-      if (s.state >= ST_DEG && s.state <= ST_MOD) n = (s.end - s.begin + csize - 1) / csize;
-    }
-    cnt[q] = n; mine += n;
-  }
-  int lane = tid & 31, wid = tid >> 5;
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-  if (lane == 31) wsum[wid] = incl;
-  __syncthreads();
-  if (wid == 0) {
-    int v = wsum[lane]; int iv = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
-    wsum[lane] = iv - v;
-  }
-  __syncthreads();
-  int base = wsum[wid] + incl - mine;
-  for (int q = 0; q < per; ++q) {
-    int slot = tid * per + q;
-    if (slot < c.n_slots) offs[slot] = base;
-    base += cnt[q];
-  }
-  if (tid == 1023) { offs[c.n_slots] = base; *out_n = base; }
-  __syncthreads();
-  const int total = offs[c.n_slots];
-  for (int ci = tid; ci < total; ci += 1024) {
-    int lo = 0, hi = c.n_slots;               // last slot with offs[slot] <= ci
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (offs[mid] <= ci) lo = mid; else hi = mid; }
-    const Slot& s = c.st[lo];
-    int k = ci - offs[lo];
-    Chunk ch; ch.slot = lo; ch.begin = s.begin + k * csize;
-    ch.len = min(csize, s.end - ch.begin);
-    out[ci] = ch;
-  }
-  __syncthreads();
-}
-
-// chunk list over the transposed blocks of the slots that form y = B_S^T x this sweep (DEG, LAN, MOD)
-__device__ void build_tchunk_list(Ctx& c, int* offs, int* wsum) {
-  const int tid = threadIdx.x;
-  const int per = (c.n_slots + 1023) / 1024;
-  int cnt[4]; int mine = 0;
-  for (int q = 0; q < per; ++q) {
-    int slot = tid * per + q; int n = 0;
-    if (slot < c.n_slots) {
-      const Slot& s = c.st[slot];
-      if (s.state == ST_DEG || s.state == ST_LAN || s.state == ST_MOD) {
-        long long a0 = s.tb & ~7ll;
-        n = (int)((s.te - a0 + c.tchunk - 1) / c.tchunk);
+      if (mode == 2) {
+        if (s.state == ST_DEG || s.state == ST_LAN || s.state == ST_MOD) n = (int)((s.te - (s.tb & ~7ll) + c.tchunk - 1) / c.tchunk);
+      } else if (s.state >= ST_DEG && s.state <= ST_MOD) {
+        const int cs = mode == 0 ? c.chunk_rows : c.vchunk_rows;
+        n = (s.end - s.begin + cs - 1) / cs;
       }
     }
     cnt[q] = n; mine += n;
@@ -371,29 +330,26 @@ __device__ void build_tchunk_list(Ctx& c, int* offs, int* wsum) {
   int base = wsum[wid] + incl - mine;
   for (int q = 0; q < per; ++q) {
     int slot = tid * per + q;
-    if (slot < c.n_slots) { offs[slot] = base; c.st[slot].tchunk0 = base; c.st[slot].ntchunk = cnt[q]; }
+    if (slot < c.n_slots) {
+      offs[slot] = base;
+      if (mode == 2) { c.st[slot].tchunk0 = base; c.st[slot].ntchunk = cnt[q]; }
+    }
     base += cnt[q];
   }
-  if (tid == 1023) { offs[c.n_slots] = base; *c.n_tchunks = base; }
+  if (tid == 1023) offs[c.n_slots] = base;
   __syncthreads();
   const int total = offs[c.n_slots];
-  for (int ci = tid; ci < total; ci += 1024) {
-    int lo = 0, hi = c.n_slots;
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (offs[mid] <= ci) lo = mid; else hi = mid; }
-    const Slot& s = c.st[lo];
-    TChunk ch; ch.slot = lo; ch.pad = 0; ch.begin = (s.tb & ~7ll) + (long long)(ci - offs[lo]) * c.tchunk;
-    c.tchunks[ci] = ch;
-  }
   __syncthreads();
+  return total;
 }
 
-// zero the reduction rows of live slots and build the chunk lists (single CTA, 1024 threads)
 __global__ void __launch_bounds__(1024) k_prepare(Ctx c) {
-  __shared__ int offs[4097];
   __shared__ int wsum[32];
-  build_chunk_list(c, c.chunk_rows, c.chunks, c.n_chunks, offs, wsum);
-  build_chunk_list(c, c.vchunk_rows, c.vchunks, c.n_vchunks, offs, wsum);
-  if (c.use_t) build_tchunk_list(c, offs, wsum);
+  int* offsA = c.list_offs; int* offsV = c.list_offs + (c.max_active + 1); int* offsT = c.list_offs + 2 * (c.max_active + 1);
+  const int ta = block_scan_counts(c, 0, offsA, wsum);
+  const int tv = block_scan_counts(c, 1, offsV, wsum);
+  const int tt = c.use_t ? block_scan_counts(c, 2, offsT, wsum) : 0;
+  if (threadIdx.x == 0) { *c.n_chunks = ta; *c.n_vchunks = tv; if (c.use_t) *c.n_tchunks = tt; }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // zero reduction rows (dots of both passes up to j+1, and the scalars): one warp per slot
   for (int slot = wid; slot < c.n_slots; slot += 32) {
@@ -404,6 +360,35 @@ __global__ void __launch_bounds__(1024) k_prepare(Ctx c) {
     int nv = min(s.j + 2, c.K + 2);
     for (int i = lane; i < nv; i += 32) { ra[i] = 0.0; rb[i] = 0.0; }
     if (lane < 3) slot_scal(c, slot)[lane] = 0.0;       // NRM2, SUMD, YNORM2 (N1/SD1 persist from the previous sweep)
+  }
+}
+
+__device__ __forceinline__ int find_slot(const int* __restrict__ offs, int n_slots, int ci) {
+  int lo = 0, hi = n_slots;                 // last slot with offs[slot] <= ci
+  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (__ldg(offs + mid) <= ci) lo = mid; else hi = mid; }
+  return lo;
+}
+__global__ void __launch_bounds__(256) k_prepare_fill(Ctx c) {
+  const int* offsA = c.list_offs; const int* offsV = c.list_offs + (c.max_active + 1); const int* offsT = c.list_offs + 2 * (c.max_active + 1);
+  const int ta = *c.n_chunks, tv = *c.n_vchunks, tt = c.use_t ? *c.n_tchunks : 0;
+  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int ci = t0; ci < ta; ci += stride) {
+    const int sl = find_slot(offsA, c.n_slots, ci);
+    const Slot& s = c.st[sl];
+    Chunk ch; ch.slot = sl; ch.begin = s.begin + (ci - offsA[sl]) * c.chunk_rows; ch.len = min(c.chunk_rows, s.end - ch.begin);
+    c.chunks[ci] = ch;
+  }
+  for (int ci = t0; ci < tv; ci += stride) {
+    const int sl = find_slot(offsV, c.n_slots, ci);
+    const Slot& s = c.st[sl];
+    Chunk ch; ch.slot = sl; ch.begin = s.begin + (ci - offsV[sl]) * c.vchunk_rows; ch.len = min(c.vchunk_rows, s.end - ch.begin);
+    c.vchunks[ci] = ch;
+  }
+  for (int ci = t0; ci < tt; ci += stride) {
+    const int sl = find_slot(offsT, c.n_slots, ci);
+    const Slot& s = c.st[sl];
+    TChunk ch; ch.slot = sl; ch.pad = 0; ch.begin = (s.tb & ~7ll) + (long long)(ci - offsT[sl]) * c.tchunk;
+    c.tchunks[ci] = ch;
   }
 }
 
