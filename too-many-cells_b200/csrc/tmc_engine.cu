@@ -817,7 +817,7 @@ struct Engine {
     }
     if (c.collectives && sh_live) { allreduce_f64(c.redB, (size_t)(c.K + 2 + R_NSCAL) * hi_shared); mark(PH_AR_COEF); }
     if (n_or && nvch) { k_update<<<nvch, 256, upd_smem, s>>>(c, 1); n_launch++; mark(PH_UPDATE); }
-    k_finish<<<(hi_slot * 32 + 255) / 256, 256, 0, s>>>(c); n_launch++;
+    k_finish<<<(hi_slot + TMC_FINISH_WARPS - 1) / TMC_FINISH_WARPS, 32 * TMC_FINISH_WARPS, sizeof(double) * TMC_FINISH_WARPS * 5 * (c.K + 2), s>>>(c); n_launch++;
     mark(PH_FINISH);
     if (nvch) { k_advance<<<nvch, 256, 0, s>>>(c); n_launch++; mark(PH_ADVANCE); }
     if (n_mod) {                                                             // local: every rank splits its own cells

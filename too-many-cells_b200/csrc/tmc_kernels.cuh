@@ -955,9 +955,15 @@ __global__ void __launch_bounds__(256) k_update(Ctx c, int pass) {
 }
 
 // ------------------------------------------------------------------ per-node scalar logic: one warp per slot
-__global__ void __launch_bounds__(256) k_finish(Ctx c) {
+// 2 warps per CTA; each warp keeps its node's T (alpha, beta) and the scratch of the eigen-solve in shared memory, so the
+// serial O(j) recurrences of lane 0 run at shared-memory latency instead of an L2 round trip per element.
+#define TMC_FINISH_WARPS 2
+__global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
+  extern __shared__ double fsm[];
   const int slot = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
+  double* sA = fsm + (size_t)(threadIdx.x >> 5) * 5 * (c.K + 2);
+  double* sB = sA + (c.K + 2); double* sdp = sB + (c.K + 2); double* sdm = sdp + (c.K + 2); double* sz = sdm + (c.K + 2);
   if (slot >= c.n_slots) return;
   Slot* s = c.st + slot;
   const int state = s->state;
@@ -988,8 +994,12 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
   }
   if (state == ST_LAN) {
     const int j = s->j;
-    double* A = c.alpha + (int64_t)slot * K2;
-    double* B = c.beta + (int64_t)slot * K2;
+    double* gA = c.alpha + (int64_t)slot * K2;
+    double* gB = c.beta + (int64_t)slot * K2;
+    double* A = sA; double* B = sB;
+    for (int i = lane; i < j - 1; i += 32) { A[i] = gA[i]; B[i + 1] = gB[i + 1]; }     // T_{j-1} from the previous steps
+    if (lane == 0) B[0] = 0.0;
+    __syncwarp();
     double beta = 0.0;
     if (lane == 0) {
       A[j - 1] = redA[j] + redB[j];
@@ -997,7 +1007,8 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
       for (int l = 0; l <= j; ++l) g2 += redB[l] * redB[l];
       beta = sqrt(fmax(scal[R_NRM2] - g2, 0.0));
       B[j] = beta;
-      if (j == 1) B[0] = 0.0;
+      gA[j - 1] = A[j - 1]; gB[j] = beta;
+      if (j == 1) gB[0] = 0.0;
       s->beta = beta;
       s->iters += 1;
     }
@@ -1014,7 +1025,6 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
       const bool test = exhausted || breakdown || full || ((j & 3) == 0 && j >= s->nev);
       if (!test) { if (lane == 0) s->action = ACT_NEXT; return; }
       __threadfence_block();
-      double* scr = c.scratch + (int64_t)slot * 2 * K2;
       double lo, hi, piv;
       tmc_gershgorin(A, B, j, &lo, &hi, &piv);
       bool all_ok = true;
@@ -1023,9 +1033,10 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
         double r = 0.0;
         if (lane == 0) {
           double* z = c.zmulti + (int64_t)i * K2;
-          tmc_twisted_vector(A, B, j, th, scr, scr + K2, z, piv);
+          tmc_twisted_vector(A, B, j, th, sdp, sdm, sz, piv);
+          for (int q = 0; q < j; ++q) z[q] = sz[q];
           c.ev_out[i] = th;
-          r = beta * fabs(z[j - 1]);
+          r = beta * fabs(sz[j - 1]);
         }
         r = __shfl_sync(0xffffffffu, r, 0);
         if (!(r <= c.tol * fmax(th, 1e-300) || r <= 1e-14)) all_ok = false;
@@ -1044,12 +1055,10 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
     // one) by no more than the previous residual; both hints are verified with a Sturm count before use
     const double theta = tmc_top_eig_warp(A, B, j, s->theta_hint, (s->theta_hint > -1e299) ? s->theta + 1.0001 * s->resid + 1e-15 : 1e300);
     if (lane == 0) {
-      double* z = c.zvec + (int64_t)slot * K2;
-      double* scr = c.scratch + (int64_t)slot * 2 * K2;
       double lo, hi, piv;
       tmc_gershgorin(A, B, j, &lo, &hi, &piv);
-      tmc_twisted_vector(A, B, j, theta, scr, scr + K2, z, piv);
-      double resid = beta * fabs(z[j - 1]);
+      tmc_twisted_vector(A, B, j, theta, sdp, sdm, sz, piv);
+      double resid = beta * fabs(sz[j - 1]);
       s->theta = theta; s->resid = resid;
       s->theta_hint = theta - 1e-13 * fmax(1.0, fabs(theta));
       bool conv = exhausted || breakdown || resid <= c.tol * theta || resid <= 1e-14;
@@ -1059,6 +1068,7 @@ __global__ void __launch_bounds__(256) k_finish(Ctx c) {
       } else if (full) {
         s->action = ACT_RITZ_RESTART; s->restarts += 1; s->theta_hint = -1e300;
       } else s->action = ACT_NEXT;
+      if (s->action != ACT_NEXT) { double* z = c.zvec + (int64_t)slot * K2; for (int q = 0; q < j; ++q) z[q] = sz[q]; }   // k_advance forms the Ritz vector
     }
     return;
   }
