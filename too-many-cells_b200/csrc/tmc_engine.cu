@@ -22,6 +22,7 @@
 
 #include "../../include/tmc.h"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include "tmc_kernels.cuh"
 
 using namespace tmc;
@@ -71,7 +72,7 @@ struct Nccl {
   }
 };
 static Nccl g_nccl;
-enum { NCCL_UINT8 = 1, NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+enum { NCCL_UINT8 = 1, NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MIN = 3 };
 
 // ----------------------------------------------------------------------------- device matrix
 struct Workspace;
@@ -89,6 +90,14 @@ struct tmc_matrix {
   int vt = VT_F64;
   void* valc = nullptr; double* rrow = nullptr; double* w2col = nullptr; double* invw = nullptr;
   size_t fb_cap_nnz = 0; void* fb_valc_spare = nullptr;
+  // dense panel (factored modes, DESIGN.md "dense panel"): the P most frequent columns as bytes, the rest as a residual CSR with
+  // renumbered columns (panel columns first); valc then holds the residual values
+  int P = 0, Ppad = 0;
+  uint8_t* panel = nullptr; int64_t* row_ptr_r = nullptr; int32_t* col_r = nullptr; int64_t nnz_r = 0;
+  size_t cap_panel = 0, cap_rp = 0, cap_colr = 0;
+  const int64_t* rp() const { return P ? row_ptr_r : row_ptr; }
+  const int32_t* ci() const { return P ? col_r : col; }
+  int64_t enz() const { return P ? nnz_r : nnz; }      // entries of the CSR the engine walks
   Workspace* ws = nullptr;
 };
 
@@ -146,12 +155,13 @@ static Workspace* g_ws_cache = nullptr;
 
 static void bind_workspace(Workspace* w, tmc_matrix* b) {
   Ctx& c = w->c;
-  c.row_ptr = b->row_ptr; c.col = b->col; c.val = (b->vt == VT_F64) ? (const void*)b->val : (const void*)b->valc;
+  c.row_ptr = b->rp(); c.col = b->ci(); c.val = (b->vt == VT_F64) ? (const void*)b->val : (const void*)b->valc;
   c.vt = b->vt; c.rrow = b->rrow; c.w2col = b->w2col; c.invw = b->invw;
+  c.panel = b->panel; c.P = b->P; c.Ppad = b->Ppad; c.row_ptr0 = b->row_ptr;
   c.n_rows = (int)b->n_rows; c.n_cols = (int)b->n_cols; c.row_offset = b->row_offset;
   const int64_t mpos = b->replicated ? (b->own_hi - b->own_lo) + b->n_rows : b->n_rows;
   c.vstride = (mpos + 15) / 16 * 16;
-  c.ystride = (b->n_cols + 15) / 16 * 16;
+  c.ystride = (b->n_cols + 511) / 512 * 512;        // >= Ppad: the panel kernels read y in whole 512-column steps
   w->m = mpos;
 }
 
@@ -168,7 +178,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     std::lock_guard<std::mutex> lk(g_cache_mu);
     Workspace* q = g_ws_cache;
     if (q && q->device == b->device && q->K == K && q->max_active == max_active && q->use_t == use_t && q->vt == b->vt && q->cap_m >= m &&
-        q->cap_nnz >= b->nnz && q->cap_cols >= b->n_cols && (!use_t || q->tn >= b->nnz + (b->replicated ? b->nnz / std::max(1, g_nccl.world) + b->nnz / 16 + 65536 : 0) + 4096)) {
+        q->cap_nnz >= b->enz() && q->cap_cols >= b->n_cols && (!use_t || q->tn >= b->enz() + (b->replicated ? b->enz() / std::max(1, g_nccl.world) + b->enz() / 16 + 65536 : 0) + 4096)) {
       g_ws_cache = nullptr;
       bind_workspace(q, b);
       b->ws = q;
@@ -178,13 +188,14 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
   Workspace* w = new Workspace();
   try {
     w->K = K; w->max_active = max_active; w->use_t = use_t; w->device = b->device; w->vt = b->vt;
-    w->cap_m = m; w->cap_nnz = b->nnz; w->cap_cols = b->n_cols; w->tn = 0;
+    w->cap_m = m; w->cap_nnz = b->enz(); w->cap_cols = b->n_cols; w->tn = 0;
     CK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     Ctx& c = w->c;
     bind_workspace(w, b);
     c.perm = w->A<int>(m); c.perm_tmp = w->A<int>(m);
     c.d = w->A<double>(m); c.sdeg = w->A<double>(m); c.xin = w->A<double>(m); c.w = w->A<double>(m); c.u2 = w->A<double>(m);
     c.label = w->A<uint8_t>(m);
+    c.pacc = w->A<double>(m);
     c.V = w->A<double>((size_t)c.vstride * (K + 2));
     c.Y = w->A<double>((size_t)c.ystride * max_active);
     c.st = w->A<Slot>(max_active); c.rep = w->A<Report>(max_active); c.max_active = max_active;
@@ -202,8 +213,8 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     w->d_act = w->A<Activation>(max_active);
     c.use_t = use_t;
     if (c.use_t) {      // transposed per-node blocks, double buffered (children are written to the other buffer)
-      const int64_t own_nnz_est = b->replicated ? b->nnz / std::max(1, g_nccl.world) + b->nnz / 16 + 65536 : 0;
-      const size_t tn = (size_t)b->nnz + (size_t)own_nnz_est + 4096;      // replicated: own block + every handed-off block
+      const int64_t own_nnz_est = b->replicated ? b->enz() / std::max(1, g_nccl.world) + b->enz() / 16 + 65536 : 0;
+      const size_t tn = (size_t)b->enz() + (size_t)own_nnz_est + 4096;      // replicated: own block + every handed-off block
       const size_t vsz = b->vt == VT_F64 ? 8 : (b->vt == VT_U16 ? 2 : 0);
       w->tn = (int64_t)tn;
       for (int q = 0; q < 2; ++q) { c.tcol[q] = w->A<int32_t>(tn); c.tpos[q] = w->A<int32_t>(tn); c.tval[q] = w->A<char>(tn * vsz + 64); }
@@ -316,6 +327,131 @@ static void factor_bufs_retire(tmc_matrix* b) {
   b->valc = nullptr; b->rrow = nullptr; b->w2col = nullptr; b->invw = nullptr; b->fb_valc_spare = nullptr;
 }
 
+// Panel buffers of the last matrix, kept for the same reason.
+struct PanelBufs { uint8_t* panel = nullptr; int64_t* row_ptr_r = nullptr; int32_t* col_r = nullptr;
+                   size_t cap_panel = 0, cap_rp = 0, cap_colr = 0; int device = -1; };
+static PanelBufs g_pb_cache;
+static void panel_bufs_release(PanelBufs& f) {
+  if (f.panel) cudaFree(f.panel);
+  if (f.row_ptr_r) cudaFree(f.row_ptr_r);
+  if (f.col_r) cudaFree(f.col_r);
+  f = PanelBufs();
+}
+static void panel_bufs_retire(tmc_matrix* b) {
+  if (!b->panel && !b->row_ptr_r && !b->col_r) return;
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  panel_bufs_release(g_pb_cache);
+  g_pb_cache.panel = b->panel; g_pb_cache.row_ptr_r = b->row_ptr_r; g_pb_cache.col_r = b->col_r;
+  g_pb_cache.cap_panel = b->cap_panel; g_pb_cache.cap_rp = b->cap_rp; g_pb_cache.cap_colr = b->cap_colr; g_pb_cache.device = b->device;
+  b->panel = nullptr; b->row_ptr_r = nullptr; b->col_r = nullptr; b->P = 0; b->Ppad = 0;
+}
+// take what fits from the cache, allocate the rest
+static void panel_bufs_take(tmc_matrix* b, size_t need_panel, size_t need_rp, size_t need_colr) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  PanelBufs& f = g_pb_cache;
+  if (f.device != b->device) panel_bufs_release(f);
+  if (need_panel && !b->panel) {
+    if (f.panel && f.cap_panel >= need_panel) { b->panel = f.panel; b->cap_panel = f.cap_panel; f.panel = nullptr; f.cap_panel = 0; }
+    else { if (f.panel) { cudaFree(f.panel); f.panel = nullptr; f.cap_panel = 0; } b->panel = dalloc<uint8_t>(need_panel); b->cap_panel = need_panel; }
+  }
+  if (need_rp && !b->row_ptr_r) {
+    if (f.row_ptr_r && f.cap_rp >= need_rp) { b->row_ptr_r = f.row_ptr_r; b->cap_rp = f.cap_rp; f.row_ptr_r = nullptr; f.cap_rp = 0; }
+    else { if (f.row_ptr_r) { cudaFree(f.row_ptr_r); f.row_ptr_r = nullptr; f.cap_rp = 0; } b->row_ptr_r = dalloc<int64_t>(need_rp); b->cap_rp = need_rp; }
+  }
+  if (need_colr && !b->col_r) {
+    if (f.col_r && f.cap_colr >= need_colr) { b->col_r = f.col_r; b->cap_colr = f.cap_colr; f.col_r = nullptr; f.cap_colr = 0; }
+    else { if (f.col_r) { cudaFree(f.col_r); f.col_r = nullptr; f.cap_colr = 0; } b->col_r = dalloc<int32_t>(need_colr); b->cap_colr = need_colr; }
+  }
+  f.device = b->device;
+}
+
+// Dense panel (DESIGN.md "dense panel"): columns present in at least `density` of the cells (TMC_PANEL_DENSITY, default 0.10)
+// are renumbered to [0, P) and stored as one byte per (row, column); the other entries (and counts > 255) form the residual
+// CSR, written to new arrays -- the caller's arrays are never modified.  On return (true) b->P/Ppad/panel/row_ptr_r/col_r/nnz_r
+// are set, valc holds the residual values and w2col/invw follow the new column order.  Returns false when no panel pays off.
+static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev, int* d_flags) {
+  if (getenv("TMC_NO_PANEL") || b->nnz == 0 || b->n_cols < 64) return false;
+  const double density = getenv("TMC_PANEL_DENSITY") ? atof(getenv("TMC_PANEL_DENSITY")) : 0.10;
+  if (!(density > 0.0)) return false;
+  const int n = (int)b->n_cols;
+  std::vector<int> df(n);
+  CK(cudaMemcpy(df.data(), df_dev, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  const double thr = std::max(1.0, density * (double)b->n_rows_global);
+  std::vector<int> cand;
+  long long panel_nnz = 0, tot_nnz = 0;
+  for (int j = 0; j < n; ++j) { tot_nnz += df[j]; if ((double)df[j] >= thr) cand.push_back(j); }
+  // memory bound: the panel may take at most a quarter of the free memory; keep the most frequent columns
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (g_pb_cache.device == b->device) free_b += g_pb_cache.cap_panel;
+  }
+  const size_t max_cols_local = std::min<size_t>(65536, (free_b / 4) / (size_t)std::max<int64_t>(1, b->n_rows) / 512 * 512);
+  size_t max_cols = max_cols_local;
+  if (g_nccl.comm && g_nccl.world > 1) {          // every rank must pick the same columns
+    int* d = dalloc<int>(1); int h = (int)max_cols_local;
+    cudaMemcpy(d, &h, sizeof(int), cudaMemcpyHostToDevice);
+    int r = g_nccl.AllReduce(d, d, 1, NCCL_INT32, NCCL_MIN, g_nccl.comm, 0);
+    cudaMemcpy(&h, d, sizeof(int), cudaMemcpyDeviceToHost); cudaFree(d);
+    if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(panel width) failed");
+    max_cols = (size_t)h;
+  }
+  if (cand.size() > max_cols) {
+    std::sort(cand.begin(), cand.end(), [&](int a, int c2) { return df[a] != df[c2] ? df[a] > df[c2] : a < c2; });
+    cand.resize(max_cols);
+    std::sort(cand.begin(), cand.end());
+  }
+  for (int j : cand) panel_nnz += df[j];
+  const int P = (int)cand.size();
+  // worth it only when a real share of the entries moves (df counts are global, so every rank decides alike)
+  if (P < 8 || (double)panel_nnz < 0.10 * (double)tot_nnz) return false;
+  const int Ppad = (P + 511) / 512 * 512;
+  std::vector<int> old2new(n), new2old(n);
+  {
+    std::vector<char> in(n, 0);
+    for (int j : cand) in[j] = 1;
+    int a = 0, r = P;
+    for (int j = 0; j < n; ++j) { const int id = in[j] ? a++ : r++; old2new[j] = id; new2old[id] = j; }
+  }
+  int* maps = dalloc<int>(2 * (size_t)n);
+  long long* cnt = nullptr; void* tmp = nullptr;
+  try {
+    CK(cudaMemcpy(maps, old2new.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(maps + n, new2old.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    panel_bufs_take(b, 0, (size_t)b->n_rows + 1, 0);
+    cnt = reinterpret_cast<long long*>(b->row_ptr_r);
+    const int grid = 148 * 8;
+    k_panel_count<<<grid, 256>>>(b->row_ptr, b->col, b->val, (int)b->n_rows, maps, P, cnt);
+    size_t bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt, cnt, (int)b->n_rows + 1));
+    CK(cudaMalloc(&tmp, std::max<size_t>(bytes, 16)));
+    CK(cub::DeviceScan::ExclusiveSum(tmp, bytes, cnt, cnt, (int)b->n_rows + 1));
+    long long nnz_r = 0;
+    CK(cudaMemcpy(&nnz_r, cnt + b->n_rows, sizeof(long long), cudaMemcpyDeviceToHost));
+    panel_bufs_take(b, (size_t)b->n_rows * Ppad, 0, (size_t)nnz_r + 64);
+    CK(cudaMemsetAsync(b->panel, 0, (size_t)b->n_rows * Ppad));
+    k_panel_fill<<<grid, 256>>>(b->row_ptr, b->col, b->val, (int)b->n_rows, maps, P, Ppad, cnt, b->col_r,
+                                b->vt == VT_U16 ? reinterpret_cast<unsigned short*>(b->valc) : nullptr, b->panel, d_flags);
+    k_col_factors_perm<<<(n + 255) / 256, 256>>>(idf_dev, maps + n, n, b->w2col, b->invw);
+    CK(cudaGetLastError());
+    int f = 0;
+    CK(cudaMemcpy(&f, d_flags, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(maps); maps = nullptr; cudaFree(tmp); tmp = nullptr;
+    if (g_nccl.comm && g_nccl.world > 1) {
+      int* d = dalloc<int>(1); int h = (f & 32) ? 1 : 0;
+      cudaMemcpy(d, &h, sizeof(int), cudaMemcpyHostToDevice);
+      int r = g_nccl.AllReduce(d, d, 1, NCCL_INT32, NCCL_SUM, g_nccl.comm, 0);
+      cudaMemcpy(&h, d, sizeof(int), cudaMemcpyDeviceToHost); cudaFree(d);
+      if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(panel flag) failed");
+      if (h) f |= 32;
+    }
+    if (f & 32) return false;           // duplicated (row, column) entries: the plain CSR path adds them up, a byte cannot
+    b->P = P; b->Ppad = Ppad; b->nnz_r = nnz_r;
+    return true;
+  } catch (...) { if (maps) cudaFree(maps); if (tmp) cudaFree(tmp); throw; }
+}
+
 // Decide the storage mode and compute what the engine needs from the device-resident input values.
 //  * all values are integers in [0, 65535] (raw counts; the usual make-tree input when the engine applies tf-idf itself):
 //    keep A as uint16 (or nothing when every value is 1) and the factors w_j = idf_j (or 1), r_i = 1/||(A diag w)_i||;
@@ -383,25 +519,35 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
       return;
     }
     b->vt = (f[0] & 16) ? VT_U16 : VT_ONE;
-    if (normalize) {
-      df = dalloc<int>(b->n_cols); idf = dalloc<double>(b->n_cols);
+    const bool want_panel = getenv("TMC_NO_PANEL") == nullptr;
+    if (normalize || want_panel) {       // column frequencies: idf, and the choice of the dense panel
+      df = dalloc<int>(b->n_cols);
       CK(cudaMemset(df, 0, sizeof(int) * b->n_cols));
       k_df_count<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, df, d_flags + 1);
       if (g_nccl.comm && g_nccl.world > 1 && !b->replicated) {
         int r = g_nccl.AllReduce(df, df, (size_t)b->n_cols, NCCL_INT32, NCCL_SUM, g_nccl.comm, 0);
         if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(df) failed");
       }
+    }
+    if (normalize) {
+      idf = dalloc<double>(b->n_cols);
       k_idf<<<(int)((b->n_cols + 255) / 256), 256>>>(df, (int)b->n_cols, (double)b->n_rows_global, idf);
     }
     factor_bufs_acquire(b, b->vt == VT_U16);
     if (do_l2) k_row_factor<<<grid, 256>>>(b->row_ptr, b->col, b->val, idf, (int)b->n_rows, b->rrow, d_flags + 1);
     else k_fill_f64<<<(unsigned)((b->n_rows + 255) / 256), 256>>>(b->rrow, b->n_rows, 1.0);      // truncated SVD of B2 itself: no row factor
-    k_col_factors<<<(int)((b->n_cols + 255) / 256), 256>>>(idf, (int)b->n_cols, b->w2col, b->invw);
-    if (b->vt == VT_U16) {
-      k_to_u16<<<grid, 256>>>(b->val, reinterpret_cast<unsigned short*>(b->valc), b->nnz);
+    bool have_panel = false;
+    if (want_panel) {
+      have_panel = build_panel(b, df, idf, d_flags);
+      if (!have_panel) panel_bufs_retire(b);
+    }
+    if (!have_panel) {
+      k_col_factors<<<(int)((b->n_cols + 255) / 256), 256>>>(idf, (int)b->n_cols, b->w2col, b->invw);
+      if (b->vt == VT_U16) k_to_u16<<<grid, 256>>>(b->val, reinterpret_cast<unsigned short*>(b->valc), b->nnz);
     }
     CK(cudaGetLastError());
     CK(cudaMemcpy(f, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    if (have_panel && b->owns && b->col) { cudaFree(b->col); b->col = nullptr; }    // only the residual is walked from here on
     if (b->owns && b->val) { cudaFree(b->val); b->val = nullptr; }       // the fp64 copy is not needed any more
     cudaFree(d_flags); d_flags = nullptr;
     if (df) cudaFree(df);
@@ -500,9 +646,9 @@ struct Engine {
   std::vector<int> handoff_list; std::vector<long long> owner_load; int n_handoffs = 0;
   int64_t n_sweeps = 0, n_launch = 0;
   double alg_vec_bytes = 0;     // non-matrix part of the spmv_pair algorithmic bytes
+  double alg_panel_bytes = 0;   // panel bytes of the pairs: one byte per (row, panel column) and half
   double build_ms = 0;
   int tg_variant = getenv("TMC_TG") ? atoi(getenv("TMC_TG")) : 0;
-  int ga_variant = getenv("TMC_GA") ? atoi(getenv("TMC_GA")) : 0;
   // TMC_DEBUG=2: per-phase device time (CUDA events between the launches of a sweep), printed after the tree build
   bool phase_prof = getenv("TMC_DEBUG") && atoi(getenv("TMC_DEBUG")) >= 2;
   enum { PH_PREPARE, PH_ZEROY, PH_TGATHER, PH_AR_Y, PH_GATHER, PH_YNORM, PH_DOTS, PH_AR_COEF, PH_UPDATE, PH_FINISH, PH_ADVANCE,
@@ -604,11 +750,11 @@ struct Engine {
     const auto w0 = std::chrono::steady_clock::now();
     struct T_ { Engine* e; std::chrono::steady_clock::time_point t; ~T_() { e->build_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); } } timer_{this, w0};
     const int row_lo = rmode ? (int)b->own_lo : 0, row_hi = rmode ? (int)b->own_hi : (int)b->n_rows;
-    long long e0 = 0, e1 = b->nnz;
+    long long e0 = 0, e1 = b->enz();
     if (rmode) {
       int64_t pe[2];
-      CK(cudaMemcpy(&pe[0], b->row_ptr + row_lo, sizeof(int64_t), cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(&pe[1], b->row_ptr + row_hi, sizeof(int64_t), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(&pe[0], b->rp() + row_lo, sizeof(int64_t), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(&pe[1], b->rp() + row_hi, sizeof(int64_t), cudaMemcpyDeviceToHost));
       e0 = pe[0]; e1 = pe[1];
     }
     const long long n = e1 - e0;
@@ -616,9 +762,9 @@ struct Engine {
     int32_t* keysA = c.tcol[1]; int32_t* keysB = c.tcol[0];
     int32_t* valsA = c.tpos[1]; int32_t* valsB = c.tpos[0];
     int32_t* rowid = w->rowid_scratch;
-    CK(cudaMemcpyAsync(keysA, b->col + e0, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(keysA, b->ci() + e0, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
     k_tb_iota<<<148 * 8, 256, 0, s>>>(valsA, n);
-    k_tb_rowid<<<148 * 8, 256, 0, s>>>(b->row_ptr, row_lo, row_hi, (int64_t)e0, rowid);
+    k_tb_rowid<<<148 * 8, 256, 0, s>>>(b->rp(), row_lo, row_hi, (int64_t)e0, rowid);
     cub::DoubleBuffer<int32_t> dk(keysA, keysB), dv(valsA, valsB);
     int end_bit = 1; while ((1ll << end_bit) < b->n_cols) ++end_bit;
     size_t tmp_bytes = 0;
@@ -713,7 +859,8 @@ struct Engine {
       int len = nd.end - nd.begin;
       rows += len;
       if (st == ST_DEG || st == ST_LAN || st == ST_MOD) n_sc++;
-      if (st == ST_DEG || st == ST_LAN) { n_ga++; alg_vec_bytes += 16.0 * (len + 1) + 32.0 * len + 16.0 * (double)b->n_cols / c.world; }
+      if (st == ST_DEG || st == ST_LAN) { n_ga++; alg_vec_bytes += 16.0 * (len + 1) + 32.0 * len + 16.0 * (double)b->n_cols / c.world;
+                                          alg_panel_bytes += 2.0 * (double)len * c.P; }
       if (st == ST_MOD) n_mod++;
       if (st == ST_DEG) n_deg++;
       if (st == ST_ORTH0 || st == ST_LAN) n_or++;
@@ -789,14 +936,20 @@ struct Engine {
         }
       }
       else if (nch) { VT_DISPATCH(c.vt, k_scatter<VT><<<nch, 256, 0, s>>>(c)); n_launch++; }
+      if (c.P && nvch) {          // dense panel half of y = A^T x: slabs of equal width (a multiple of 512 columns, at most 4096)
+        const int G = std::max(1, 512 / RV);
+        const int nslab = (c.Ppad + 4095) / 4096;
+        const int wslab = ((c.Ppad / 512 + nslab - 1) / nslab);      // warps per CTA
+        k_tpanel<4><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G); n_launch++;
+      }
       if (profile) e1 = ev();
       mark(PH_TGATHER);
       if (c.collectives && sh_sc) { allreduce_f64(c.Y, (size_t)c.ystride * hi_shared); mark(PH_AR_Y); }
     }
     if (n_ga && nch) {
+      if (c.P && nvch) { k_gather_panel<4><<<nvch, 256, 0, s>>>(c); n_launch++; }      // dense panel half of u = A y -> pacc
       VT_DISPATCH(c.vt,
-        if (ga_variant == 1) k_gather<VT><<<nch, 256, 0, s>>>(c);            // first pipelined version (values converted before the prefetch stage)
-        else k_gather_u<VT, 4><<<nch, 256, 0, s>>>(c));                       // raw values in the prefetch stage: 5-7 % faster on c2/c3 roots
+        k_gather_u<VT, 4><<<nch, 256, 0, s>>>(c));
       n_launch++;
     }
     mark(PH_GATHER);
@@ -1046,12 +1199,14 @@ void tmc_cache_clear(void) {
   std::lock_guard<std::mutex> lk(g_cache_mu);
   delete g_ws_cache; g_ws_cache = nullptr;
   factor_bufs_release(g_fb_cache);
+  panel_bufs_release(g_pb_cache);
 }
 
 void tmc_matrix_free(tmc_matrix* b) {
   if (!b) return;
   retire_workspace(b->ws); b->ws = nullptr;
   factor_bufs_retire(b);
+  panel_bufs_retire(b);
   if (b->owns) { cudaFree(b->row_ptr); cudaFree(b->col); cudaFree(b->val); }
   delete b;
 }
@@ -1194,7 +1349,8 @@ int tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out) {
       t.spmv_ms = tot;
     }
     const double bv = b->vt == VT_F64 ? 8.0 : (b->vt == VT_U16 ? 2.0 : 0.0);      // b_v of BASELINE.md section 4 as actually stored
-    t.spmv_alg_bytes = 2.0 * (bv + 4.0) * (double)t.spmv_pairs_nnz + eng.alg_vec_bytes;
+    // stored bytes the pairs have to move: (value + column index) per CSR entry and half, plus one byte per panel cell and half
+    t.spmv_alg_bytes = 2.0 * (bv + 4.0) * (double)(b->P ? (int64_t)eng.w->h_stats[2] : t.spmv_pairs_nnz) + eng.alg_panel_bytes + eng.alg_vec_bytes;
     t.value_bytes = (int32_t)bv;
     *out = &ts->t;
   });

@@ -48,6 +48,7 @@ struct Report {            // what the host reads back after every sweep
   double q, theta;
 };
 
+#define TMC_MAX_CHUNK 256
 struct Chunk { int slot, begin, len; };
 struct TChunk { long long begin; int slot, pad; };        // entries [begin, begin + tchunk) of the slot's transposed block
 struct Activation { int slot, begin, end, gsize, node, stop_after, tpar, priv; long long tb, te; int nev, pad; };
@@ -61,6 +62,11 @@ struct Ctx {
   const double* invw;              // [n_cols] 1/w_j (0 where w_j = 0)
   int n_rows, n_cols;              // local rows, features
   int64_t row_offset;              // global id of local row 0
+  // dense panel (factored modes): the P most frequent columns are renumbered to [0, P) and stored as one byte per (row, column),
+  // panel[row * Ppad + j]; row_ptr/col/val then hold only the residual (other columns, counts > 255).  P = 0: no panel.
+  const uint8_t* panel; int P, Ppad;
+  const int64_t* row_ptr0;         // row pointers of the caller's CSR (nnz accounting only)
+  double* pacc;                    // [m] panel half of u = A y per position, consumed by k_gather_u
   // position-indexed state
   int* perm; int* perm_tmp;
   double* d; double* sdeg; double* xin; double* w; double* u2; uint8_t* label;
@@ -276,6 +282,74 @@ __global__ void k_fill_f64(double* __restrict__ p, int64_t n, double v) { int64_
 __global__ void k_col_factors(const double* __restrict__ w, int n_cols, double* __restrict__ w2, double* __restrict__ invw) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n_cols) { const double x = w ? w[j] : 1.0; w2[j] = x * x; invw[j] = x != 0.0 ? 1.0 / x : 0.0; }
+}
+
+__global__ void k_col_factors_perm(const double* __restrict__ w, const int* __restrict__ new2old, int n_cols, double* __restrict__ w2, double* __restrict__ invw) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_cols) { const double x = w ? w[new2old[j]] : 1.0; w2[j] = x * x; invw[j] = x != 0.0 ? 1.0 / x : 0.0; }
+}
+
+// ------------------------------------------------------------------ dense panel construction (load time)
+// An entry goes to the panel when its (renumbered) column is < P and its count fits a byte; everything else stays in the
+// residual CSR.  k_panel_count: residual entries per row (cnt[n_rows] = 0 closes the scan).
+__global__ void __launch_bounds__(256) k_panel_count(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                                                     int n_rows, const int* __restrict__ old2new, int P, long long* __restrict__ cnt) {
+  const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int nw = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+  for (int r = warp; r <= n_rows; r += nw) {
+    if (r == n_rows) { if (lane == 0) cnt[r] = 0; continue; }
+    const int64_t rs = row_ptr[r], re = row_ptr[r + 1];
+    int n = 0;
+    for (int64_t k = rs + lane; k < re; k += 32) {
+      const double v = val[k];
+      n += !(__ldg(old2new + col[k]) < P && v <= 255.0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0) cnt[r] = n;
+  }
+}
+// k_panel_fill: one warp per row writes the panel bytes and compacts the residual (order kept).  A duplicated (row, column)
+// would overwrite a panel byte instead of adding: the warp re-counts its row and raises flag 32 (the caller then drops the panel).
+__global__ void __launch_bounds__(256) k_panel_fill(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                                                    int n_rows, const int* __restrict__ old2new, int P, int Ppad, const long long* __restrict__ row_ptr_r,
+                                                    int32_t* __restrict__ col_r, unsigned short* __restrict__ val_r, uint8_t* __restrict__ panel,
+                                                    int* __restrict__ flags) {
+  const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int nw = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+  for (int r = warp; r < n_rows; r += nw) {
+    const int64_t rs = row_ptr[r], re = row_ptr[r + 1];
+    long long base = row_ptr_r[r];
+    uint8_t* prow = panel + (size_t)r * Ppad;
+    int np = 0;
+    for (int64_t k0 = rs; k0 < re; k0 += 32) {
+      const int64_t k = k0 + lane;
+      const bool valid = k < re;
+      const double v = valid ? val[k] : 0.0;
+      const int nc = valid ? __ldg(old2new + col[k]) : 0;
+      const bool inp = valid && nc < P && v <= 255.0;
+      if (inp && v > 0.0) { prow[nc] = (uint8_t)v; np++; }
+      const bool res = valid && !inp;
+      const unsigned m = __ballot_sync(0xffffffffu, res);
+      if (res) {
+        const long long o = base + __popc(m & ((1u << lane) - 1u));
+        col_r[o] = nc;
+        if (val_r) val_r[o] = (unsigned short)v;
+      }
+      base += __popc(m);
+    }
+    __syncwarp();
+    int nzb = 0;
+    const unsigned* pw = reinterpret_cast<const unsigned*>(prow);
+    for (int i = lane; i < (Ppad >> 2); i += 32) {
+      const unsigned wv = __ldcg(pw + i);
+      nzb += ((wv & 0xffu) != 0) + ((wv & 0xff00u) != 0) + ((wv & 0xff0000u) != 0) + ((wv & 0xff000000u) != 0);
+    }
+    int d = np - nzb;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == 0 && d != 0) atomicOr(flags, 32);
+  }
 }
 
 // ------------------------------------------------------------------ per-sweep bookkeeping
@@ -520,6 +594,143 @@ __global__ void __launch_bounds__(256) k_tgather_t(Ctx c, int cls) {       // cl
   }
 }
 
+// ------------------------------------------------------------------ dense panel halves of the SpMV pair
+// Counts 0..255 as bytes, columns [0, P) contiguous in y: both halves stream the panel rows with coalesced loads and no index
+// traffic.  A byte becomes a double through the 2^52 trick (PRMT + DADD; cvt.f64.u32 runs at a fraction of the fp64 rate).
+__device__ __forceinline__ double u8_f64(unsigned w, int k) {
+  return __hiloint2double(0x43300000, (int)__byte_perm(w, 0u, 0x4440u + (unsigned)k)) - 4503599627370496.0;
+}
+// y[0..P) += w^2 * sum_r panel[r][.] * xin[r] over the rows of G consecutive vector chunks.  Lane = 16 columns (one 16-byte load
+// per row), warp = 512 columns, CTA = blockDim/32 warps side by side (the host sizes the CTA so that the slabs divide Ppad
+// evenly); grid (ceil(n_vchunks / G), slabs).  4 rows in flight per warp plus the next 4 prefetched; one atomicAdd per column
+// per CTA and slot.  (Measured alternatives, tools/exp/panel_kern.cu + profiles/r1_v5: 8-byte lanes 3.1 TB/s, a cp.async ring
+// through shared memory 3.1 TB/s, this one 4.4 TB/s; the same arithmetic on a flat stream reaches 5.9 TB/s.)
+template <int NR>
+__global__ void __launch_bounds__(256) k_tpanel(Ctx c, int G) {
+  __shared__ int s_row[TMC_MAX_CHUNK];
+  __shared__ double s_x[TMC_MAX_CHUNK];
+  const int nv = *c.n_vchunks;
+  const int i0 = blockIdx.x * G;
+  if (i0 >= nv) return;
+  const int i1 = min(nv, i0 + G);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int colw = (blockIdx.y * (blockDim.x >> 5) + warp) * 512;
+  const bool on = colw < c.Ppad;
+  const uint4* __restrict__ pb = reinterpret_cast<const uint4*>(c.panel + colw) + lane;
+  const size_t ws = (size_t)(c.Ppad >> 4);                                       // uint4 per panel row
+  double acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+  int cur = -1;
+  auto flush = [&]() {
+    if (cur >= 0 && on) {
+      double* y = c.Y + (int64_t)cur * c.ystride;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int cj = colw + lane * 16 + k;
+        if (cj < c.P && acc[k] != 0.0) atomicAdd(y + cj, acc[k] * __ldg(c.w2col + cj));
+        acc[k] = 0.0;
+      }
+    }
+  };
+  for (int i = i0; i < i1; ++i) {
+    const Chunk ch = c.vchunks[i];
+    const int state = c.st[ch.slot].state;
+    if (ch.slot != cur) { flush(); cur = ch.slot; }
+    if (state != ST_DEG && state != ST_LAN && state != ST_MOD) continue;
+    __syncthreads();
+    for (int t = threadIdx.x; t < ch.len; t += blockDim.x) { s_row[t] = c.perm[ch.begin + t]; s_x[t] = c.xin[ch.begin + t]; }
+    __syncthreads();
+    if (!on) continue;
+    uint4 d[NR], dn[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) d[q] = __ldg(pb + (size_t)s_row[min(q, ch.len - 1)] * ws);
+    for (int r = 0; r < ch.len; r += NR) {
+      if (r + NR < ch.len) {
+#pragma unroll
+        for (int q = 0; q < NR; ++q) dn[q] = __ldg(pb + (size_t)s_row[min(r + NR + q, ch.len - 1)] * ws);
+      }
+#pragma unroll
+      for (int q = 0; q < NR; ++q) {
+        const double xv = r + q < ch.len ? s_x[r + q] : 0.0;
+        if (xv == 0.0) continue;                       // warp-uniform (modularity pass: half of the rows)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[k] += u8_f64(d[q].x, k) * xv; acc[4 + k] += u8_f64(d[q].y, k) * xv;
+          acc[8 + k] += u8_f64(d[q].z, k) * xv; acc[12 + k] += u8_f64(d[q].w, k) * xv;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NR; ++q) d[q] = dn[q];
+    }
+  }
+  flush();
+}
+// pacc[p] = sum_{j < P} panel[row(p)][j] * y[j]; one CTA per vector chunk.  y is staged in shared memory in blocks of TMC_GP_CB
+// columns, stored so that the eight 16-byte reads of a lane (its 16 columns of a 512-column step) are conflict-free: the pair
+// (16*lane + 2j, 16*lane + 2j + 1) sits at double2 index j*32 + lane.  A warp works on NR rows at a time (every y value read
+// from shared memory is used NR times) with the next step's panel bytes already in flight.
+#define TMC_GP_CB 4096
+template <int NR>
+__global__ void __launch_bounds__(256) k_gather_panel(Ctx c) {
+  __shared__ double2 ys2[TMC_GP_CB / 2];
+  __shared__ double ps[TMC_MAX_CHUNK];
+  if ((int)blockIdx.x >= *c.n_vchunks) return;
+  const Chunk ch = c.vchunks[blockIdx.x];
+  const int state = c.st[ch.slot].state;
+  if (state != ST_DEG && state != ST_LAN) return;
+  const double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int p = threadIdx.x; p < ch.len; p += 256) ps[p] = 0.0;
+  for (int cb = 0; cb < c.Ppad; cb += TMC_GP_CB) {
+    const int nb = min(TMC_GP_CB, c.Ppad - cb);
+    __syncthreads();
+    for (int t = threadIdx.x; t < (nb >> 1); t += 256) {
+      const int w = t & 255;
+      ys2[(t & ~255) + ((w & 7) << 5) + (w >> 3)] = ldg_d2(y + cb + 2 * t);
+    }
+    __syncthreads();
+    const int nit = nb >> 9;
+    for (int r0 = warp * NR; r0 < ch.len; r0 += 8 * NR) {
+      const int nr = min(NR, ch.len - r0);
+      const uint4* pr[NR];
+#pragma unroll
+      for (int q = 0; q < NR; ++q)
+        pr[q] = reinterpret_cast<const uint4*>(c.panel + (size_t)c.perm[ch.begin + r0 + min(q, nr - 1)] * c.Ppad + cb) + lane;
+      double acc[NR];
+#pragma unroll
+      for (int q = 0; q < NR; ++q) acc[q] = 0.0;
+      uint4 d[NR], dn[NR];
+#pragma unroll
+      for (int q = 0; q < NR; ++q) d[q] = __ldg(pr[q]);
+      for (int i = 0; i < nit; ++i) {
+        if (i + 1 < nit) {
+#pragma unroll
+          for (int q = 0; q < NR; ++q) dn[q] = __ldg(pr[q] + 32 * (i + 1));
+        }
+#pragma unroll
+        for (int cpt = 0; cpt < 4; ++cpt) {
+          const double2 ya = ys2[i * 256 + (2 * cpt) * 32 + lane], yb = ys2[i * 256 + (2 * cpt + 1) * 32 + lane];
+#pragma unroll
+          for (int q = 0; q < NR; ++q) {
+            const unsigned w = cpt == 0 ? d[q].x : (cpt == 1 ? d[q].y : (cpt == 2 ? d[q].z : d[q].w));
+            acc[q] += u8_f64(w, 0) * ya.x + u8_f64(w, 1) * ya.y + u8_f64(w, 2) * yb.x + u8_f64(w, 3) * yb.y;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < NR; ++q) d[q] = dn[q];
+      }
+#pragma unroll
+      for (int q = 0; q < NR; ++q) {
+        const double sq = warp_sum(acc[q]);
+        if (lane == 0 && q < nr) ps[r0 + q] += sq;
+      }
+    }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < ch.len; p += 256) c.pacc[ch.begin + p] = ps[p];
+}
+
 // sorted construction of the root block (perm = identity): after a stable radix sort of the CSR entries by column,
 // tpos holds CSR entry indices; replace them by the row (= position) and fetch the values
 // rows [row_lo, row_hi): rowid[k - e0] = position of the row (= r - row_lo), e0 = row_ptr[row_lo]
@@ -732,72 +943,9 @@ __global__ void __launch_bounds__(256) k_tpart_scatter(Ctx c) {
 // dependent y[col] gathers are issued, and the next row's extent prefetched while the current row streams
 // (measured: 4.2 -> 5.4 TB/s on the c2 root against the non-pipelined loop; tools/exp).  y is read through the
 // read-only path (it is not written in this kernel) so the compiler may keep all four chains in flight.
-#ifdef TMC_GATHER_MINB
-#define TMC_GATHER_LB __launch_bounds__(256, TMC_GATHER_MINB)
-#else
-#define TMC_GATHER_LB __launch_bounds__(256)
-#endif
-template <int VT>
-__global__ void TMC_GATHER_LB k_gather(Ctx c) {
-  __shared__ double sm8[8];
-  if ((int)blockIdx.x >= *c.n_chunks) return;
-  const Chunk ch = c.chunks[blockIdx.x];
-  const int state = c.st[ch.slot].state;
-  if (state != ST_DEG && state != ST_LAN) return;
-  const double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride;
-  const int32_t* __restrict__ col = c.col;
-  const void* __restrict__ val = c.val;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double dsum = 0.0;
-  long long nz = 0;
-  int r = warp;
-  int64_t rs = 0, re = 0;
-  int row_cur = 0;
-  if (r < ch.len) { row_cur = c.perm[ch.begin + r]; rs = c.row_ptr[row_cur]; re = c.row_ptr[row_cur + 1]; }
-  while (r < ch.len) {
-    const int p = ch.begin + r;
-    const int rn = r + 8;
-    int64_t nrs = 0, nre = 0;
-    int nrow = 0;
-    if (rn < ch.len) { nrow = c.perm[ch.begin + rn]; nrs = c.row_ptr[nrow]; nre = c.row_ptr[nrow + 1]; }
-    nz += re - rs;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int64_t k = rs + lane;
-    bool have = (k + 96 < re);
-    int c0 = 0, c1 = 0, c2 = 0, c3 = 0; double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-    if (have) {
-      c0 = __ldg(col + k); c1 = __ldg(col + k + 32); c2 = __ldg(col + k + 64); c3 = __ldg(col + k + 96);
-      v0 = ld_val<VT>(val, k); v1 = ld_val<VT>(val, k + 32); v2 = ld_val<VT>(val, k + 64); v3 = ld_val<VT>(val, k + 96);
-    }
-    while (have) {
-      const int64_t kn = k + 128;
-      const bool have_n = (kn + 96 < re);
-      int d0 = 0, d1 = 0, d2 = 0, d3 = 0; double u0 = 0, u1 = 0, u2 = 0, u3 = 0;
-      if (have_n) {
-        d0 = __ldg(col + kn); d1 = __ldg(col + kn + 32); d2 = __ldg(col + kn + 64); d3 = __ldg(col + kn + 96);
-        u0 = ld_val<VT>(val, kn); u1 = ld_val<VT>(val, kn + 32); u2 = ld_val<VT>(val, kn + 64); u3 = ld_val<VT>(val, kn + 96);
-      }
-      a0 += v0 * __ldg(y + c0); a1 += v1 * __ldg(y + c1); a2 += v2 * __ldg(y + c2); a3 += v3 * __ldg(y + c3);
-      c0 = d0; c1 = d1; c2 = d2; c3 = d3; v0 = u0; v1 = u1; v2 = u2; v3 = u3;
-      k = kn; have = have_n;
-    }
-    for (; k < re; k += 32) a0 += ld_val<VT>(val, k) * __ldg(y + __ldg(col + k));
-    const double s = warp_sum((a0 + a1) + (a2 + a3));
-    if (lane == 0) {
-      if (state == ST_DEG) { const double dv = (VT == VT_F64) ? s : s * c.rrow[row_cur]; c.d[p] = dv; dsum += dv; }
-      else c.w[p] = c.sdeg[p] * s;
-    }
-    r = rn; rs = nrs; re = nre; row_cur = nrow;
-  }
-  if (lane == 0 && nz) atomicAdd(c.stats + (state == ST_DEG ? 1 : 0), (unsigned long long)nz);
-  if (state == ST_DEG) {
-    double t = block_sum_256(dsum, sm8);
-    if (threadIdx.x == 0) atomicAdd(slot_scal(c, ch.slot) + R_SUMD, t);
-  }
-}
 
-// The gather in use: U x 32 entries in flight, values kept RAW (uint16) through the prefetch stage (k_gather above is the
-// first pipelined version, kept for A/B runs with TMC_GA=1; U = 6 / 8 measured slower: 72 / 80 registers)
+// The gather in use: U x 32 entries in flight, values kept RAW (uint16) through the prefetch stage (U = 6 / 8 measured
+// slower: 72 / 80 registers).  With a dense panel the panel half of the row sum arrives in pacc (k_gather_panel).
 template <int VT> struct RawVal { typedef double T; };
 template <> struct RawVal<VT_U16> { typedef unsigned short T; };
 template <> struct RawVal<VT_ONE> { typedef unsigned char T; };
@@ -819,7 +967,7 @@ __global__ void __launch_bounds__(256) k_gather_u(Ctx c) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   typedef typename RawVal<VT>::T RT;
   double dsum = 0.0;
-  long long nz = 0;
+  long long nz = 0, nz0 = 0;
   int r = warp;
   int64_t rs = 0, re = 0;
   int row_cur = 0;
@@ -831,6 +979,7 @@ __global__ void __launch_bounds__(256) k_gather_u(Ctx c) {
     int nrow = 0;
     if (rn < ch.len) { nrow = c.perm[ch.begin + rn]; nrs = c.row_ptr[nrow]; nre = c.row_ptr[nrow + 1]; }
     nz += re - rs;
+    if (c.P) nz0 += c.row_ptr0[row_cur + 1] - c.row_ptr0[row_cur];
     double acc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) acc[u] = 0.0;
@@ -861,14 +1010,18 @@ __global__ void __launch_bounds__(256) k_gather_u(Ctx c) {
     double sacc = 0.0;
 #pragma unroll
     for (int u = 0; u < U; ++u) sacc += acc[u];
-    const double s = warp_sum(sacc);
+    double s = warp_sum(sacc);
     if (lane == 0) {
+      if (c.P) s += c.pacc[p];
       if (state == ST_DEG) { const double dv2 = (VT == VT_F64) ? s : s * c.rrow[row_cur]; c.d[p] = dv2; dsum += dv2; }
       else c.w[p] = c.sdeg[p] * s;
     }
     r = rn; rs = nrs; re = nre; row_cur = nrow;
   }
-  if (lane == 0 && nz) atomicAdd(c.stats + (state == ST_DEG ? 1 : 0), (unsigned long long)nz);
+  if (lane == 0 && (nz || nz0)) {
+    atomicAdd(c.stats + (state == ST_DEG ? 1 : 0), (unsigned long long)(c.P ? nz0 : nz));     // nonzeros of the caller's matrix covered
+    if (c.P) atomicAdd(c.stats + 2, (unsigned long long)nz);                                   // of which read from the residual CSR
+  }
   if (state == ST_DEG) {
     double t = block_sum_256(dsum, sm8);
     if (threadIdx.x == 0) atomicAdd(slot_scal(c, ch.slot) + R_SUMD, t);
@@ -895,7 +1048,6 @@ __global__ void __launch_bounds__(256) k_ynorm(Ctx c) {
 
 // ------------------------------------------------------------------ K5: full re-orthogonalisation (CGS2)
 // h_l = <V_l, w>, l = 0..j  (l = 0 is the locked trivial vector u1 = D^{1/2}1/||.||, the deflation)
-#define TMC_MAX_CHUNK 256
 __global__ void __launch_bounds__(256) k_dots(Ctx c, int pass) {
   __shared__ double ws[TMC_MAX_CHUNK];
   if ((int)blockIdx.x >= *c.n_vchunks) return;
