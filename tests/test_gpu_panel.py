@@ -1,0 +1,168 @@
+"""Dense panel (DESIGN.md "dense panel"): frequent columns stored as one byte per (cell, feature), the rest as a residual
+CSR with renumbered columns.  The storage must be invisible: every export and the whole tree equal the plain-CSR path
+(TMC_NO_PANEL=1) and the oracle, including the corner cases of the split (counts that do not fit a byte, duplicated entries,
+all-ones matrices, every column in the panel)."""
+import os
+
+import numpy as np
+import scipy.sparse as sp
+import pytest
+
+import tmc_oracle as O
+import too_many_cells_b200 as T
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(1e-300, float(np.max(np.abs(b)))))
+
+
+class env:
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kw}
+        for k, v in self.kw.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def same_tree(t1, t2):
+    return O.canonical_tree(t1.left, t1.right, t1.items) == O.canonical_tree(t2.left, t2.right, t2.items)
+
+
+def same_as_oracle(tree, ot):
+    return O.canonical_tree(tree.left, tree.right, tree.items) == O.canonical_tree(ot.left, ot.right, lambda i: ot.items[i])
+
+
+def dense_cols_counts(n=700, g=900, seed=5, binary=False, big=False):
+    """Two planted groups; 60 features present in most cells (the panel), the rest sparse."""
+    rng = np.random.default_rng(seed)
+    grp = rng.integers(0, 2, n)
+    lam = np.full((2, g), 0.02)
+    lam[:, :60] = rng.uniform(0.3, 3.0, size=(2, 60))
+    lam[0, 60:200] *= 6.0
+    lam[1, 200:340] *= 6.0
+    cnt = rng.poisson(lam[grp]).astype(np.float64)
+    cnt[cnt.sum(axis=1) == 0, 0] = 1
+    if big:        # counts that do not fit a byte, in panel columns and outside
+        cnt[::7, 3] = 300.0
+        cnt[::11, 5] = 65535.0
+        cnt[::13, 500] = 1000.0
+    if binary:
+        cnt = (cnt > 0).astype(np.float64)
+    return sp.csr_matrix(cnt), grp
+
+
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_panel_is_used_and_invisible(name, golden_tiny, golden_small):
+    a, _ = golden_tiny if name == "tiny" else golden_small
+    db = T.DeviceB.from_host(a, normalize=True)
+    info = db.info()
+    assert info["value_type"] == "u16" and info["panel_cols"] >= 8 and info["panel_width"] % 512 == 0
+    assert 0 < info["residual_nnz"] < info["nnz"] == a.nnz
+    with env(TMC_NO_PANEL=1):
+        dp = T.DeviceB.from_host(a, normalize=True)
+    assert dp.info()["panel_cols"] == 0 and dp.info()["residual_nnz"] == a.nnz
+    b = O.b2_to_b(O.b1_to_b2(a))
+    d0, d1 = T.b_to_d(db), T.b_to_d(dp)
+    assert rel(d0, d1) < 1e-13 and rel(d0, O.b_to_d(b)) < 1e-13
+    rows = np.arange(3, a.shape[0], 4)
+    assert rel(T.b_to_d(db, rows), O.b_to_d(b[rows])) < 1e-13
+    x = np.random.default_rng(1).standard_normal(a.shape[0])
+    assert rel(T.spmv_pair(db, x), T.spmv_pair(dp, x)) < 1e-12
+    u0, th0, _ = T.second_left(db)
+    u1, th1, _ = T.second_left(dp)
+    s = 1.0 if u0 @ u1 >= 0 else -1.0
+    assert abs(th0 - th1) < 1e-12 and np.linalg.norm(s * u0 - u1) < 1e-9
+    t0 = T.hierarchical_spectral_cluster(db)
+    t1 = T.hierarchical_spectral_cluster(dp)
+    assert same_tree(t0, t1) and float(np.max(np.abs(t0.q - t1.q))) < 1e-12
+    db.free(); dp.free()
+
+
+@pytest.mark.parametrize("big", [False, True])
+def test_panel_byte_overflow_and_oracle(big):
+    a, _ = dense_cols_counts(big=big)
+    db = T.DeviceB.from_host(a, normalize=True)
+    info = db.info()
+    assert info["panel_cols"] >= 60
+    b = O.b2_to_b(O.b1_to_b2(a))
+    assert rel(T.b_to_d(db), O.b_to_d(b)) < 1e-13
+    tree = T.hierarchical_spectral_cluster(db)
+    ot = O.hierarchical_spectral_cluster(a, normalize=True)
+    assert same_as_oracle(tree, ot)
+    db.free()
+
+
+def test_panel_all_ones_matrix():
+    a, _ = dense_cols_counts(binary=True, seed=9)
+    db = T.DeviceB.from_host(a, normalize=True)
+    info = db.info()
+    assert info["value_type"] == "one" and info["panel_cols"] >= 60
+    b = O.b2_to_b(O.b1_to_b2(a))
+    assert rel(T.b_to_d(db), O.b_to_d(b)) < 1e-13
+    assert same_as_oracle(T.hierarchical_spectral_cluster(db), O.hierarchical_spectral_cluster(a, normalize=True))
+    db.free()
+
+
+def test_panel_without_idf_and_lsa_mode():
+    a, _ = dense_cols_counts(seed=11)
+    db = T.DeviceB.from_host(a, normalize=False)         # raw counts, row L2 only: the column factor is 1
+    assert db.info()["panel_cols"] >= 60
+    b = O.b2_to_b(a)
+    assert rel(T.b_to_d(db), O.b_to_d(b)) < 1e-13
+    db.free()
+    u, sig, conv = T.lsa_sparse_mat(a, 4)                 # truncated SVD of the idf-scaled matrix (no row factor)
+    with env(TMC_NO_PANEL=1):
+        u1, sig1, conv1 = T.lsa_sparse_mat(a, 4)
+    assert conv and conv1 and rel(sig, sig1) < 1e-10
+    for k in range(u.shape[1]):
+        s = 1.0 if u[:, k] @ u1[:, k] >= 0 else -1.0
+        assert np.linalg.norm(s * u[:, k] - u1[:, k]) < 1e-7
+
+
+def test_duplicate_entries_drop_the_panel():
+    a, _ = dense_cols_counts(seed=13)
+    a = a.tocsr()
+    # duplicate the first entry of every 5th row (same row, same column, value 1): scipy keeps duplicates in raw CSR arrays
+    indptr, indices, data = [0], [], []
+    for r in range(a.shape[0]):
+        s, e = a.indptr[r], a.indptr[r + 1]
+        cols, vals = list(a.indices[s:e]), list(a.data[s:e])
+        if r % 5 == 0:
+            cols.append(cols[0]); vals.append(1.0)
+        indices += cols; data += vals; indptr.append(len(indices))
+    dup = sp.csr_matrix((np.array(data), np.array(indices, dtype=np.int32), np.array(indptr, dtype=np.int64)), shape=a.shape)
+    assert dup.has_canonical_format is False or dup.nnz > a.nnz
+    db = T.DeviceB.from_host(dup, normalize=True)
+    assert db.info()["panel_cols"] == 0 and db.info()["residual_nnz"] == dup.nnz
+    with env(TMC_NO_PANEL=1):
+        dp = T.DeviceB.from_host(dup, normalize=True)
+    assert rel(T.b_to_d(db), T.b_to_d(dp)) < 1e-14
+    db.free(); dp.free()
+
+
+@pytest.mark.parametrize("density", ["0.0001", "0.5"])
+def test_panel_density_knob_extremes(density, golden_tiny):
+    a, _ = golden_tiny
+    ref = T.hierarchical_spectral_cluster(a, normalize=True)
+    with env(TMC_PANEL_DENSITY=density):
+        db = T.DeviceB.from_host(a, normalize=True)
+    info = db.info()
+    if density == "0.0001":
+        assert info["panel_cols"] >= 0.9 * (np.diff(a.tocsc().indptr) > 0).sum()      # (almost) every used column is in the panel
+    tree = T.hierarchical_spectral_cluster(db)
+    assert same_tree(tree, ref)
+    db.free()

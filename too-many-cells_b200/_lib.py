@@ -67,6 +67,7 @@ SIGNATURES = {
     "tmc_matrix_upload": (C.c_int, [C.POINTER(Csr), C.c_int, C.c_int, C.POINTER(_P)]),
     "tmc_matrix_adopt_dev": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(_P)]),
     "tmc_matrix_free": (None, [_P]),
+    "tmc_matrix_info": (C.c_int, [_P, C.POINTER(C.c_int64), C.c_int]),
     "tmc_cache_clear": (None, []),
     "tmc_make_tree": (C.c_int, [C.POINTER(Csr), C.POINTER(Opts), C.POINTER(C.POINTER(Tree))]),
     "tmc_make_tree_dev": (C.c_int, [_P, C.POINTER(Opts), C.POINTER(C.POINTER(Tree))]),

@@ -1195,6 +1195,13 @@ int tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int6
   });
 }
 
+int tmc_matrix_info(const tmc_matrix* b, int64_t* info, int n) {
+  if (!b || !info || n < 0) return fail(TMC_ERR_INVALID, "null pointer");
+  const int64_t v[6] = {(int64_t)b->vt, (int64_t)b->P, (int64_t)b->Ppad, b->enz(), b->nnz, b->n_rows};
+  for (int i = 0; i < n && i < 6; ++i) info[i] = v[i];
+  return TMC_OK;
+}
+
 void tmc_cache_clear(void) {
   std::lock_guard<std::mutex> lk(g_cache_mu);
   delete g_ws_cache; g_ws_cache = nullptr;

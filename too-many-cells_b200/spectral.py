@@ -108,6 +108,13 @@ class DeviceB:
                                        C.byref(out)))
         return cls(out, (int(n_rows), int(n_cols)), int(val.numel()), keepalive=(row_ptr, col, val))
 
+    def info(self):
+        """Storage of the device copy: value type, dense-panel width, residual CSR entries (tmc_matrix_info)."""
+        v = (C.c_int64 * 6)()
+        check(_lib.load().tmc_matrix_info(self.handle, v, 6))
+        return {"value_type": ("f64", "u16", "one")[int(v[0])], "panel_cols": int(v[1]), "panel_width": int(v[2]),
+                "residual_nnz": int(v[3]), "nnz": int(v[4]), "n_rows": int(v[5])}
+
     def free(self):
         if self.handle:
             _lib.load().tmc_matrix_free(self.handle)
