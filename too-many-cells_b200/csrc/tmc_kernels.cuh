@@ -596,10 +596,15 @@ __global__ void __launch_bounds__(256) k_tgather_t(Ctx c, int cls) {       // cl
 
 // ------------------------------------------------------------------ dense panel halves of the SpMV pair
 // Counts 0..255 as bytes, columns [0, P) contiguous in y: both halves stream the panel rows with coalesced loads and no index
-// traffic.  A byte becomes a double through the 2^52 trick (PRMT + DADD; cvt.f64.u32 runs at a fraction of the fp64 rate).
-__device__ __forceinline__ double u8_f64(unsigned w, int k) {
-  return __hiloint2double(0x43300000, (int)__byte_perm(w, 0u, 0x4440u + (unsigned)k)) - 4503599627370496.0;
-}
+// traffic.  A byte b is used as the DENORMAL double with bit pattern (hi = 0, lo = b) = b * 2^-1074 -- exact, one PRMT and no
+// conversion instruction (cvt.f64.u32 runs at a fraction of the fp64 rate; the 2^52 trick costs an extra DADD per entry, which
+// made both kernels fp64-issue bound).  The dense operand (x or y) is pre-scaled by 2^960 where it is staged in shared memory
+// and the sums are scaled back by 2^114 once per row / column: power-of-two scalings are exact and every product is formed
+// exactly inside the FMA, so the result is bit-identical to converting the byte first.  |x| < 2^63 is required (else inf -> the
+// non-finite degree / Ritz checks fire); the engine's vectors are bounded by the row factors and the column sums.
+#define TMC_PANEL_UP 0x1p960
+#define TMC_PANEL_DOWN 0x1p114
+__device__ __forceinline__ double u8_f64(unsigned w, int k) { return __hiloint2double(0, (int)__byte_perm(w, 0u, 0x4440u + (unsigned)k)); }
 // y[0..P) += w^2 * sum_r panel[r][.] * xin[r] over the rows of G consecutive vector chunks.  Lane = 16 columns (one 16-byte load
 // per row), warp = 512 columns, CTA = blockDim/32 warps side by side (the host sizes the CTA so that the slabs divide Ppad
 // evenly); grid (ceil(n_vchunks / G), slabs).  4 rows in flight per warp plus the next 4 prefetched; one atomicAdd per column
@@ -607,8 +612,8 @@ __device__ __forceinline__ double u8_f64(unsigned w, int k) {
 // through shared memory 3.1 TB/s, this one 4.4 TB/s; the same arithmetic on a flat stream reaches 5.9 TB/s.)
 template <int NR>
 __global__ void __launch_bounds__(256) k_tpanel(Ctx c, int G) {
-  __shared__ int s_row[TMC_MAX_CHUNK];
-  __shared__ double s_x[TMC_MAX_CHUNK];
+  __shared__ int s_row[TMC_MAX_CHUNK + 2 * NR];
+  __shared__ double s_x[TMC_MAX_CHUNK + 2 * NR];
   const int nv = *c.n_vchunks;
   const int i0 = blockIdx.x * G;
   if (i0 >= nv) return;
@@ -628,7 +633,7 @@ __global__ void __launch_bounds__(256) k_tpanel(Ctx c, int G) {
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const int cj = colw + lane * 16 + k;
-        if (cj < c.P && acc[k] != 0.0) atomicAdd(y + cj, acc[k] * __ldg(c.w2col + cj));
+        if (cj < c.P && acc[k] != 0.0) atomicAdd(y + cj, acc[k] * TMC_PANEL_DOWN * __ldg(c.w2col + cj));
         acc[k] = 0.0;
       }
     }
@@ -639,29 +644,37 @@ __global__ void __launch_bounds__(256) k_tpanel(Ctx c, int G) {
     if (ch.slot != cur) { flush(); cur = ch.slot; }
     if (state != ST_DEG && state != ST_LAN && state != ST_MOD) continue;
     __syncthreads();
-    for (int t = threadIdx.x; t < ch.len; t += blockDim.x) { s_row[t] = c.perm[ch.begin + t]; s_x[t] = c.xin[ch.begin + t]; }
+    // rows padded to a multiple of 2*NR with x = 0 (and a valid row id), so that the loop below needs no bounds tests
+    const int lenp = (ch.len + 2 * NR - 1) / (2 * NR) * (2 * NR);
+    for (int t = threadIdx.x; t < lenp; t += blockDim.x) {
+      const bool ok = t < ch.len;
+      s_row[t] = c.perm[ch.begin + (ok ? t : ch.len - 1)];
+      s_x[t] = ok ? c.xin[ch.begin + t] * TMC_PANEL_UP : 0.0;
+    }
     __syncthreads();
     if (!on) continue;
-    uint4 d[NR], dn[NR];
+    uint4 d0[NR], d1[NR];
+    auto load = [&](uint4* d, int r) {
 #pragma unroll
-    for (int q = 0; q < NR; ++q) d[q] = __ldg(pb + (size_t)s_row[min(q, ch.len - 1)] * ws);
-    for (int r = 0; r < ch.len; r += NR) {
-      if (r + NR < ch.len) {
-#pragma unroll
-        for (int q = 0; q < NR; ++q) dn[q] = __ldg(pb + (size_t)s_row[min(r + NR + q, ch.len - 1)] * ws);
-      }
+      for (int q = 0; q < NR; ++q) d[q] = __ldg(pb + (size_t)s_row[r + q] * ws);
+    };
+    auto fma_rows = [&](const uint4* d, int r) {
 #pragma unroll
       for (int q = 0; q < NR; ++q) {
-        const double xv = r + q < ch.len ? s_x[r + q] : 0.0;
-        if (xv == 0.0) continue;                       // warp-uniform (modularity pass: half of the rows)
+        const double xv = s_x[r + q];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           acc[k] += u8_f64(d[q].x, k) * xv; acc[4 + k] += u8_f64(d[q].y, k) * xv;
           acc[8 + k] += u8_f64(d[q].z, k) * xv; acc[12 + k] += u8_f64(d[q].w, k) * xv;
         }
       }
-#pragma unroll
-      for (int q = 0; q < NR; ++q) d[q] = dn[q];
+    };
+    load(d0, 0);
+    for (int r = 0; r < lenp; r += 2 * NR) {          // two register sets in ping-pong: the next rows are in flight during the math
+      load(d1, r + NR);
+      fma_rows(d0, r);
+      if (r + 2 * NR < lenp) load(d0, r + 2 * NR);
+      fma_rows(d1, r + NR);
     }
   }
   flush();
@@ -687,7 +700,9 @@ __global__ void __launch_bounds__(256) k_gather_panel(Ctx c) {
     __syncthreads();
     for (int t = threadIdx.x; t < (nb >> 1); t += 256) {
       const int w = t & 255;
-      ys2[(t & ~255) + ((w & 7) << 5) + (w >> 3)] = ldg_d2(y + cb + 2 * t);
+      double2 yv = ldg_d2(y + cb + 2 * t);
+      yv.x *= TMC_PANEL_UP; yv.y *= TMC_PANEL_UP;
+      ys2[(t & ~255) + ((w & 7) << 5) + (w >> 3)] = yv;
     }
     __syncthreads();
     const int nit = nb >> 9;
@@ -700,14 +715,12 @@ __global__ void __launch_bounds__(256) k_gather_panel(Ctx c) {
       double acc[NR];
 #pragma unroll
       for (int q = 0; q < NR; ++q) acc[q] = 0.0;
-      uint4 d[NR], dn[NR];
+      uint4 d0[NR], d1[NR];
+      auto load = [&](uint4* d, int i) {
 #pragma unroll
-      for (int q = 0; q < NR; ++q) d[q] = __ldg(pr[q]);
-      for (int i = 0; i < nit; ++i) {
-        if (i + 1 < nit) {
-#pragma unroll
-          for (int q = 0; q < NR; ++q) dn[q] = __ldg(pr[q] + 32 * (i + 1));
-        }
+        for (int q = 0; q < NR; ++q) d[q] = __ldg(pr[q] + 32 * i);
+      };
+      auto fma_step = [&](const uint4* d, int i) {
 #pragma unroll
         for (int cpt = 0; cpt < 4; ++cpt) {
           const double2 ya = ys2[i * 256 + (2 * cpt) * 32 + lane], yb = ys2[i * 256 + (2 * cpt + 1) * 32 + lane];
@@ -717,13 +730,18 @@ __global__ void __launch_bounds__(256) k_gather_panel(Ctx c) {
             acc[q] += u8_f64(w, 0) * ya.x + u8_f64(w, 1) * ya.y + u8_f64(w, 2) * yb.x + u8_f64(w, 3) * yb.y;
           }
         }
-#pragma unroll
-        for (int q = 0; q < NR; ++q) d[q] = dn[q];
+      };
+      load(d0, 0);
+      for (int i = 0; i < nit; i += 2) {               // two register sets in ping-pong: the next step is in flight during the math
+        if (i + 1 < nit) load(d1, i + 1);
+        fma_step(d0, i);
+        if (i + 2 < nit) load(d0, i + 2);
+        if (i + 1 < nit) fma_step(d1, i + 1);
       }
 #pragma unroll
       for (int q = 0; q < NR; ++q) {
         const double sq = warp_sum(acc[q]);
-        if (lane == 0 && q < nr) ps[r0 + q] += sq;
+        if (lane == 0 && q < nr) ps[r0 + q] += sq * TMC_PANEL_DOWN;
       }
     }
   }
