@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 METRIC = "ms per full make-tree"
 UNIT = "ms"
 # ncu dram bytes (read + write) of the root-level SpMV pair on c3, 1 GPU (profiles/, see the roofline comment below)
-TRAFFIC_C3_ROOT_PAIR = None
+TRAFFIC_C3_ROOT_PAIR = 21.92e9
 
 
 def parse():

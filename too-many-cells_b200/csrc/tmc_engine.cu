@@ -365,13 +365,13 @@ static void panel_bufs_take(tmc_matrix* b, size_t need_panel, size_t need_rp, si
   f.device = b->device;
 }
 
-// Dense panel (DESIGN.md "dense panel"): columns present in at least `density` of the cells (TMC_PANEL_DENSITY, default 0.10)
+// Dense panel (DESIGN.md "dense panel"): columns present in at least `density` of the cells (TMC_PANEL_DENSITY, default 0.07)
 // are renumbered to [0, P) and stored as one byte per (row, column); the other entries (and counts > 255) form the residual
 // CSR, written to new arrays -- the caller's arrays are never modified.  On return (true) b->P/Ppad/panel/row_ptr_r/col_r/nnz_r
 // are set, valc holds the residual values and w2col/invw follow the new column order.  Returns false when no panel pays off.
 static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev, int* d_flags) {
   if (getenv("TMC_NO_PANEL") || b->nnz == 0 || b->n_cols < 64) return false;
-  const double density = getenv("TMC_PANEL_DENSITY") ? atof(getenv("TMC_PANEL_DENSITY")) : 0.10;
+  const double density = getenv("TMC_PANEL_DENSITY") ? atof(getenv("TMC_PANEL_DENSITY")) : 0.07;
   if (!(density > 0.0)) return false;
   const int n = (int)b->n_cols;
   std::vector<int> df(n);
