@@ -125,8 +125,9 @@ int  tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int
                           int normalize, int device, tmc_matrix** out);
 void tmc_matrix_free(tmc_matrix*);
 /* How the device copy is stored (diagnostics, tests, bench accounting): info[0] value storage (0 fp64 B, 1 uint16 counts +
- * diagonal factors, 2 all ones), [1] columns in the dense byte panel, [2] padded panel width in bytes per row, [3] entries
- * left in the residual CSR, [4] entries of the caller's CSR, [5] local rows.  Writes min(n, 6) values. */
+ * diagonal factors, 2 all ones), [1] columns in the dense panel, [2] panel bytes per row, [3] entries left in the residual
+ * CSR, [4] entries of the caller's CSR, [5] local rows, [6] bits per panel cell (8, 4, or 0 without a panel).
+ * Writes min(n, 7) values. */
 int  tmc_matrix_info(const tmc_matrix* b, int64_t* info, int n);
 /* tmc_matrix_free keeps one retired workspace (device arenas, pinned buffers) for the next matrix; this releases it. */
 void tmc_cache_clear(void);

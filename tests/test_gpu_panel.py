@@ -60,17 +60,23 @@ def dense_cols_counts(n=700, g=900, seed=5, binary=False, big=False):
         cnt[::7, 3] = 300.0
         cnt[::11, 5] = 65535.0
         cnt[::13, 500] = 1000.0
+        cnt[::5, 7] = 16.0          # does not fit a nibble, fits a byte
+        cnt[::3, 9] = 15.0
+        cnt[1::3, 9] = 255.0
     if binary:
         cnt = (cnt > 0).astype(np.float64)
     return sp.csr_matrix(cnt), grp
 
 
+@pytest.mark.parametrize("bits", [4, 8])
 @pytest.mark.parametrize("name", ["tiny", "small"])
-def test_panel_is_used_and_invisible(name, golden_tiny, golden_small):
+def test_panel_is_used_and_invisible(name, bits, golden_tiny, golden_small):
     a, _ = golden_tiny if name == "tiny" else golden_small
-    db = T.DeviceB.from_host(a, normalize=True)
+    with env(TMC_PANEL_BITS=bits):
+        db = T.DeviceB.from_host(a, normalize=True)
     info = db.info()
-    assert info["value_type"] == "u16" and info["panel_cols"] >= 8 and info["panel_width"] % 512 == 0
+    assert info["value_type"] == "u16" and info["panel_cols"] >= 8 and info["panel_bits"] == bits
+    assert info["panel_row_bytes"] % 256 == 0 and info["panel_row_bytes"] * 8 // bits >= info["panel_cols"]
     assert 0 < info["residual_nnz"] < info["nnz"] == a.nnz
     with env(TMC_NO_PANEL=1):
         dp = T.DeviceB.from_host(a, normalize=True)
@@ -92,12 +98,28 @@ def test_panel_is_used_and_invisible(name, golden_tiny, golden_small):
     db.free(); dp.free()
 
 
+def test_default_cell_format_follows_the_counts(golden_tiny):
+    a, _ = golden_tiny
+    db = T.DeviceB.from_host(a, normalize=True)              # UMI-like counts: nibbles
+    assert db.info()["panel_bits"] == 4
+    db.free()
+    big = a.copy(); big.data = big.data * 20.0                # nothing fits a nibble any more: bytes
+    db = T.DeviceB.from_host(big, normalize=True)
+    assert db.info()["panel_bits"] == 8 and db.info()["panel_cols"] >= 8
+    db.free()
+
+
+@pytest.mark.parametrize("bits", [4, 8])
 @pytest.mark.parametrize("big", [False, True])
-def test_panel_byte_overflow_and_oracle(big):
+def test_panel_cell_overflow_and_oracle(big, bits):
     a, _ = dense_cols_counts(big=big)
-    db = T.DeviceB.from_host(a, normalize=True)
+    with env(TMC_PANEL_BITS=bits):
+        db = T.DeviceB.from_host(a, normalize=True)
     info = db.info()
-    assert info["panel_cols"] >= 60
+    assert info["panel_cols"] >= 60 and info["panel_bits"] == bits
+    cap = 15 if bits == 4 else 255
+    dense = np.asarray(a.todense())
+    assert info["residual_nnz"] >= int((dense > cap).sum())           # at least the counts that do not fit a cell
     b = O.b2_to_b(O.b1_to_b2(a))
     assert rel(T.b_to_d(db), O.b_to_d(b)) < 1e-13
     tree = T.hierarchical_spectral_cluster(db)

@@ -93,6 +93,7 @@ struct tmc_matrix {
   // dense panel (factored modes, DESIGN.md "dense panel"): the P most frequent columns as bytes, the rest as a residual CSR with
   // renumbered columns (panel columns first); valc then holds the residual values
   int P = 0, Ppad = 0;
+  int pnib = 0, pw = 0;                    // pnib: nibble cells (counts <= 15) instead of byte cells; pw: bytes per panel row
   uint8_t* panel = nullptr; int64_t* row_ptr_r = nullptr; int32_t* col_r = nullptr; int64_t nnz_r = 0;
   size_t cap_panel = 0, cap_rp = 0, cap_colr = 0;
   const int64_t* rp() const { return P ? row_ptr_r : row_ptr; }
@@ -157,7 +158,7 @@ static void bind_workspace(Workspace* w, tmc_matrix* b) {
   Ctx& c = w->c;
   c.row_ptr = b->rp(); c.col = b->ci(); c.val = (b->vt == VT_F64) ? (const void*)b->val : (const void*)b->valc;
   c.vt = b->vt; c.rrow = b->rrow; c.w2col = b->w2col; c.invw = b->invw;
-  c.panel = b->panel; c.P = b->P; c.Ppad = b->Ppad; c.row_ptr0 = b->row_ptr;
+  c.panel = b->panel; c.P = b->P; c.Ppad = b->Ppad; c.pnib = b->pnib; c.pw = b->pw; c.row_ptr0 = b->row_ptr;
   c.n_rows = (int)b->n_rows; c.n_cols = (int)b->n_cols; c.row_offset = b->row_offset;
   const int64_t mpos = b->replicated ? (b->own_hi - b->own_lo) + b->n_rows : b->n_rows;
   c.vstride = (mpos + 15) / 16 * 16;
@@ -343,7 +344,7 @@ static void panel_bufs_retire(tmc_matrix* b) {
   panel_bufs_release(g_pb_cache);
   g_pb_cache.panel = b->panel; g_pb_cache.row_ptr_r = b->row_ptr_r; g_pb_cache.col_r = b->col_r;
   g_pb_cache.cap_panel = b->cap_panel; g_pb_cache.cap_rp = b->cap_rp; g_pb_cache.cap_colr = b->cap_colr; g_pb_cache.device = b->device;
-  b->panel = nullptr; b->row_ptr_r = nullptr; b->col_r = nullptr; b->P = 0; b->Ppad = 0;
+  b->panel = nullptr; b->row_ptr_r = nullptr; b->col_r = nullptr; b->P = 0; b->Ppad = 0; b->pnib = 0; b->pw = 0;
 }
 // take what fits from the cache, allocate the rest
 static void panel_bufs_take(tmc_matrix* b, size_t need_panel, size_t need_rp, size_t need_colr) {
@@ -369,7 +370,7 @@ static void panel_bufs_take(tmc_matrix* b, size_t need_panel, size_t need_rp, si
 // are renumbered to [0, P) and stored as one byte per (row, column); the other entries (and counts > 255) form the residual
 // CSR, written to new arrays -- the caller's arrays are never modified.  On return (true) b->P/Ppad/panel/row_ptr_r/col_r/nnz_r
 // are set, valc holds the residual values and w2col/invw follow the new column order.  Returns false when no panel pays off.
-static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev, int* d_flags) {
+static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev, int* d_flags, int nib) {
   if (getenv("TMC_NO_PANEL") || b->nnz == 0 || b->n_cols < 64) return false;
   const double density = getenv("TMC_PANEL_DENSITY") ? atof(getenv("TMC_PANEL_DENSITY")) : 0.07;
   if (!(density > 0.0)) return false;
@@ -387,7 +388,7 @@ static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev,
     std::lock_guard<std::mutex> lk(g_cache_mu);
     if (g_pb_cache.device == b->device) free_b += g_pb_cache.cap_panel;
   }
-  const size_t max_cols_local = std::min<size_t>(65536, (free_b / 4) / (size_t)std::max<int64_t>(1, b->n_rows) / 512 * 512);
+  const size_t max_cols_local = std::min<size_t>(65536, (free_b / 4) * (nib ? 2 : 1) / (size_t)std::max<int64_t>(1, b->n_rows) / 512 * 512);
   size_t max_cols = max_cols_local;
   if (g_nccl.comm && g_nccl.world > 1) {          // every rank must pick the same columns
     int* d = dalloc<int>(1); int h = (int)max_cols_local;
@@ -407,6 +408,8 @@ static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev,
   // worth it only when a real share of the entries moves (df counts are global, so every rank decides alike)
   if (P < 8 || (double)panel_nnz < 0.10 * (double)tot_nnz) return false;
   const int Ppad = (P + 511) / 512 * 512;
+  const int pw = nib ? Ppad / 2 : Ppad;
+  const double cap = nib ? 15.0 : 255.0;
   std::vector<int> old2new(n), new2old(n);
   {
     std::vector<char> in(n, 0);
@@ -422,16 +425,16 @@ static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev,
     panel_bufs_take(b, 0, (size_t)b->n_rows + 1, 0);
     cnt = reinterpret_cast<long long*>(b->row_ptr_r);
     const int grid = 148 * 8;
-    k_panel_count<<<grid, 256>>>(b->row_ptr, b->col, b->val, (int)b->n_rows, maps, P, cnt);
+    k_panel_count<<<grid, 256>>>(b->row_ptr, b->col, b->val, (int)b->n_rows, maps, P, cap, cnt);
     size_t bytes = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt, cnt, (int)b->n_rows + 1));
     CK(cudaMalloc(&tmp, std::max<size_t>(bytes, 16)));
     CK(cub::DeviceScan::ExclusiveSum(tmp, bytes, cnt, cnt, (int)b->n_rows + 1));
     long long nnz_r = 0;
     CK(cudaMemcpy(&nnz_r, cnt + b->n_rows, sizeof(long long), cudaMemcpyDeviceToHost));
-    panel_bufs_take(b, (size_t)b->n_rows * Ppad, 0, (size_t)nnz_r + 64);
-    CK(cudaMemsetAsync(b->panel, 0, (size_t)b->n_rows * Ppad));
-    k_panel_fill<<<grid, 256>>>(b->row_ptr, b->col, b->val, (int)b->n_rows, maps, P, Ppad, cnt, b->col_r,
+    panel_bufs_take(b, (size_t)b->n_rows * pw, 0, (size_t)nnz_r + 64);
+    CK(cudaMemsetAsync(b->panel, 0, (size_t)b->n_rows * pw));
+    k_panel_fill<<<grid, 256>>>(b->row_ptr, b->col, b->val, (int)b->n_rows, maps, P, pw, nib, cap, cnt, b->col_r,
                                 b->vt == VT_U16 ? reinterpret_cast<unsigned short*>(b->valc) : nullptr, b->panel, d_flags);
     k_col_factors_perm<<<(n + 255) / 256, 256>>>(idf_dev, maps + n, n, b->w2col, b->invw);
     CK(cudaGetLastError());
@@ -447,7 +450,7 @@ static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev,
       if (h) f |= 32;
     }
     if (f & 32) return false;           // duplicated (row, column) entries: the plain CSR path adds them up, a byte cannot
-    b->P = P; b->Ppad = Ppad; b->nnz_r = nnz_r;
+    b->P = P; b->Ppad = Ppad; b->pnib = nib; b->pw = pw; b->nnz_r = nnz_r;
     return true;
   } catch (...) { if (maps) cudaFree(maps); if (tmp) cudaFree(tmp); throw; }
 }
@@ -490,14 +493,17 @@ static void renumber_columns(tmc_matrix* b) {
 
 static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
   renumber_columns(b);
-  int* d_flags = dalloc<int>(2);
+  int* d_flags = dalloc<int>(6);          // [0] value flags, [1] error code, [2..5] two 64-bit counters of small values
   int* df = nullptr; double* idf = nullptr;
   try {
-    CK(cudaMemset(d_flags, 0, 2 * sizeof(int)));
+    CK(cudaMemset(d_flags, 0, 6 * sizeof(int)));
     const int grid = 148 * 8;
-    k_scan_values<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, d_flags);
+    unsigned long long* d_small = reinterpret_cast<unsigned long long*>(d_flags + 2);
+    k_scan_values<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, d_flags, d_small);
     int f[2] = {0, 0};
+    unsigned long long n_small[2] = {0, 0};
     CK(cudaMemcpy(f, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(n_small, d_small, sizeof(n_small), cudaMemcpyDeviceToHost));
     if (g_nccl.comm && g_nccl.world > 1 && !b->replicated) {
       // row-block inputs: every rank must take the same decision (storage mode, errors), or the others would wait forever
       int* bits = dalloc<int>(5); int hb[5];
@@ -507,6 +513,13 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
       cudaMemcpy(hb, bits, sizeof(hb), cudaMemcpyDeviceToHost); cudaFree(bits);
       if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(value flags) failed");
       f[0] = 0; for (int i = 0; i < 5; ++i) if (hb[i]) f[0] |= 1 << i;
+      std::vector<double> ns = {(double)n_small[0], (double)n_small[1]};     // exact below 2^53
+      double* dn = dalloc<double>(2);
+      cudaMemcpy(dn, ns.data(), 16, cudaMemcpyHostToDevice);
+      r = g_nccl.AllReduce(dn, dn, 2, NCCL_FLOAT64, NCCL_SUM, g_nccl.comm, 0);
+      cudaMemcpy(ns.data(), dn, 16, cudaMemcpyDeviceToHost); cudaFree(dn);
+      if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(small-value counts) failed");
+      n_small[0] = (unsigned long long)ns[0]; n_small[1] = (unsigned long long)ns[1];
     }
     if (f[0] & 1) throw TmcError(TMC_ERR_NAN, "NaN/Inf in matrix values");
     if (f[0] & 4) throw TmcError(TMC_ERR_INVALID, "column index out of range");
@@ -538,7 +551,10 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     else k_fill_f64<<<(unsigned)((b->n_rows + 255) / 256), 256>>>(b->rrow, b->n_rows, 1.0);      // truncated SVD of B2 itself: no row factor
     bool have_panel = false;
     if (want_panel) {
-      have_panel = build_panel(b, df, idf, d_flags);
+      // cell format: nibbles when (nearly) everything that fits a byte also fits a nibble (UMI counts), else bytes
+      int nib = (double)n_small[0] >= 0.9 * (double)n_small[1];
+      if (const char* e = getenv("TMC_PANEL_BITS")) nib = atoi(e) == 4;
+      have_panel = build_panel(b, df, idf, d_flags, nib);
       if (!have_panel) panel_bufs_retire(b);
     }
     if (!have_panel) {
@@ -860,7 +876,7 @@ struct Engine {
       rows += len;
       if (st == ST_DEG || st == ST_LAN || st == ST_MOD) n_sc++;
       if (st == ST_DEG || st == ST_LAN) { n_ga++; alg_vec_bytes += 16.0 * (len + 1) + 32.0 * len + 16.0 * (double)b->n_cols / c.world;
-                                          alg_panel_bytes += 2.0 * (double)len * c.P; }
+                                          alg_panel_bytes += 2.0 * (double)len * c.P * (c.pnib ? 0.5 : 1.0); }
       if (st == ST_MOD) n_mod++;
       if (st == ST_DEG) n_deg++;
       if (st == ST_ORTH0 || st == ST_LAN) n_or++;
@@ -940,14 +956,19 @@ struct Engine {
         const int G = std::max(1, 512 / RV);
         const int nslab = (c.Ppad + 4095) / 4096;
         const int wslab = ((c.Ppad / 512 + nslab - 1) / nslab);      // warps per CTA
-        k_tpanel<4><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G); n_launch++;
+        if (c.pnib) k_tpanel<8, 1><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G);
+        else k_tpanel<4, 0><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G);
+        n_launch++;
       }
       if (profile) e1 = ev();
       mark(PH_TGATHER);
       if (c.collectives && sh_sc) { allreduce_f64(c.Y, (size_t)c.ystride * hi_shared); mark(PH_AR_Y); }
     }
     if (n_ga && nch) {
-      if (c.P && nvch) { k_gather_panel<4><<<nvch, 256, 0, s>>>(c); n_launch++; }      // dense panel half of u = A y -> pacc
+      if (c.P && nvch) {      // dense panel half of u = A y -> pacc
+        if (c.pnib) k_gather_panel<4, 1><<<nvch, 256, 0, s>>>(c); else k_gather_panel<4, 0><<<nvch, 256, 0, s>>>(c);
+        n_launch++;
+      }
       VT_DISPATCH(c.vt,
         k_gather_u<VT, 4><<<nch, 256, 0, s>>>(c));
       n_launch++;
@@ -1197,8 +1218,8 @@ int tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int6
 
 int tmc_matrix_info(const tmc_matrix* b, int64_t* info, int n) {
   if (!b || !info || n < 0) return fail(TMC_ERR_INVALID, "null pointer");
-  const int64_t v[6] = {(int64_t)b->vt, (int64_t)b->P, (int64_t)b->Ppad, b->enz(), b->nnz, b->n_rows};
-  for (int i = 0; i < n && i < 6; ++i) info[i] = v[i];
+  const int64_t v[7] = {(int64_t)b->vt, (int64_t)b->P, (int64_t)b->pw, b->enz(), b->nnz, b->n_rows, (int64_t)(b->P ? (b->pnib ? 4 : 8) : 0)};
+  for (int i = 0; i < n && i < 7; ++i) info[i] = v[i];
   return TMC_OK;
 }
 

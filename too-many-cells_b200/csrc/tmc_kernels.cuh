@@ -63,8 +63,9 @@ struct Ctx {
   int n_rows, n_cols;              // local rows, features
   int64_t row_offset;              // global id of local row 0
   // dense panel (factored modes): the P most frequent columns are renumbered to [0, P) and stored as one byte per (row, column),
-  // panel[row * Ppad + j]; row_ptr/col/val then hold only the residual (other columns, counts > 255).  P = 0: no panel.
-  const uint8_t* panel; int P, Ppad;
+  // panel + row * pw; row_ptr/col/val then hold only the residual (other columns, counts that do not fit).  P = 0: no panel.
+  const uint8_t* panel; int P, Ppad;      // Ppad: P rounded up to whole warps of 512 columns
+  int pnib, pw;                            // pnib: 1 = one nibble per cell (counts <= 15), 0 = one byte (<= 255); pw: bytes per panel row
   const int64_t* row_ptr0;         // row pointers of the caller's CSR (nnz accounting only)
   double* pacc;                    // [m] panel half of u = A y per position, consumed by k_gather_u
   // position-indexed state
@@ -244,12 +245,14 @@ __global__ void k_remap_cols(int32_t* __restrict__ col, int64_t nnz, const int* 
 
 // value scan: validity + can the values be stored as small integers / are they all ones?
 // flags: 1 NaN/Inf, 2 negative, 4 column out of range, 8 not an integer <= 65535, 16 not all ones
-__global__ void k_scan_values(const int32_t* __restrict__ col, const double* __restrict__ val, int64_t nnz, int n_cols, int* __restrict__ flags) {
+__global__ void k_scan_values(const int32_t* __restrict__ col, const double* __restrict__ val, int64_t nnz, int n_cols, int* __restrict__ flags,
+                              unsigned long long* __restrict__ n_small) {      // n_small[0] = #{0 < v <= 15}, [1] = #{0 < v <= 255}
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int f = 0;
+  int f = 0; int n15 = 0, n255 = 0;
   for (; i < nnz; i += stride) {
     const double v = val[i]; const int cj = col[i];
+    n15 += (v > 0.0 && v <= 15.0); n255 += (v > 0.0 && v <= 255.0);
     if (!(v == v) || isinf(v)) f |= 1;
     if (v < 0) f |= 2;
     if (cj < 0 || cj >= n_cols) f |= 4;
@@ -258,6 +261,10 @@ __global__ void k_scan_values(const int32_t* __restrict__ col, const double* __r
   }
   f = __reduce_or_sync(0xffffffffu, f);
   if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+  if (n_small) {
+    n15 = __reduce_add_sync(0xffffffffu, n15); n255 = __reduce_add_sync(0xffffffffu, n255);
+    if ((threadIdx.x & 31) == 0) { if (n15) atomicAdd(n_small, (unsigned long long)n15); if (n255) atomicAdd(n_small + 1, (unsigned long long)n255); }
+  }
 }
 __global__ void k_to_u16(const double* __restrict__ val, unsigned short* __restrict__ out, int64_t nnz) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -290,10 +297,10 @@ __global__ void k_col_factors_perm(const double* __restrict__ w, const int* __re
 }
 
 // ------------------------------------------------------------------ dense panel construction (load time)
-// An entry goes to the panel when its (renumbered) column is < P and its count fits a byte; everything else stays in the
-// residual CSR.  k_panel_count: residual entries per row (cnt[n_rows] = 0 closes the scan).
+// An entry goes to the panel when its (renumbered) column is < P and its count fits the cell (cap = 255 or 15); everything else
+// stays in the residual CSR.  k_panel_count: residual entries per row (cnt[n_rows] = 0 closes the scan).
 __global__ void __launch_bounds__(256) k_panel_count(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double* __restrict__ val,
-                                                     int n_rows, const int* __restrict__ old2new, int P, long long* __restrict__ cnt) {
+                                                     int n_rows, const int* __restrict__ old2new, int P, double cap, long long* __restrict__ cnt) {
   const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   const int nw = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
   for (int r = warp; r <= n_rows; r += nw) {
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__(256) k_panel_count(const int64_t* __restrict__
     int n = 0;
     for (int64_t k = rs + lane; k < re; k += 32) {
       const double v = val[k];
-      n += !(__ldg(old2new + col[k]) < P && v <= 255.0);
+      n += !(__ldg(old2new + col[k]) < P && v <= cap);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
@@ -312,7 +319,8 @@ __global__ void __launch_bounds__(256) k_panel_count(const int64_t* __restrict__
 // k_panel_fill: one warp per row writes the panel bytes and compacts the residual (order kept).  A duplicated (row, column)
 // would overwrite a panel byte instead of adding: the warp re-counts its row and raises flag 32 (the caller then drops the panel).
 __global__ void __launch_bounds__(256) k_panel_fill(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double* __restrict__ val,
-                                                    int n_rows, const int* __restrict__ old2new, int P, int Ppad, const long long* __restrict__ row_ptr_r,
+                                                    int n_rows, const int* __restrict__ old2new, int P, int pw, int nib, double cap,
+                                                    const long long* __restrict__ row_ptr_r,
                                                     int32_t* __restrict__ col_r, unsigned short* __restrict__ val_r, uint8_t* __restrict__ panel,
                                                     int* __restrict__ flags) {
   const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
@@ -320,15 +328,19 @@ __global__ void __launch_bounds__(256) k_panel_fill(const int64_t* __restrict__ 
   for (int r = warp; r < n_rows; r += nw) {
     const int64_t rs = row_ptr[r], re = row_ptr[r + 1];
     long long base = row_ptr_r[r];
-    uint8_t* prow = panel + (size_t)r * Ppad;
+    uint8_t* prow = panel + (size_t)r * pw;
     int np = 0;
     for (int64_t k0 = rs; k0 < re; k0 += 32) {
       const int64_t k = k0 + lane;
       const bool valid = k < re;
       const double v = valid ? val[k] : 0.0;
       const int nc = valid ? __ldg(old2new + col[k]) : 0;
-      const bool inp = valid && nc < P && v <= 255.0;
-      if (inp && v > 0.0) { prow[nc] = (uint8_t)v; np++; }
+      const bool inp = valid && nc < P && v <= cap;
+      if (inp && v > 0.0) {
+        if (nib) atomicOr(reinterpret_cast<unsigned*>(prow) + (nc >> 3), (unsigned)v << (4 * (nc & 7)));    // two columns share a byte
+        else prow[nc] = (uint8_t)v;
+        np++;
+      }
       const bool res = valid && !inp;
       const unsigned m = __ballot_sync(0xffffffffu, res);
       if (res) {
@@ -340,10 +352,13 @@ __global__ void __launch_bounds__(256) k_panel_fill(const int64_t* __restrict__ 
     }
     __syncwarp();
     int nzb = 0;
-    const unsigned* pw = reinterpret_cast<const unsigned*>(prow);
-    for (int i = lane; i < (Ppad >> 2); i += 32) {
-      const unsigned wv = __ldcg(pw + i);
-      nzb += ((wv & 0xffu) != 0) + ((wv & 0xff00u) != 0) + ((wv & 0xff0000u) != 0) + ((wv & 0xff000000u) != 0);
+    const unsigned* pwd = reinterpret_cast<const unsigned*>(prow);
+    for (int i = lane; i < (pw >> 2); i += 32) {
+      const unsigned wv = __ldcg(pwd + i);
+      if (nib) {
+        unsigned m = wv | (wv >> 1); m |= m >> 2;            // bit 0 of every nibble = "nibble is non-zero"
+        nzb += __popc(m & 0x11111111u);
+      } else nzb += ((wv & 0xffu) != 0) + ((wv & 0xff00u) != 0) + ((wv & 0xff0000u) != 0) + ((wv & 0xff000000u) != 0);
     }
     int d = np - nzb;
 #pragma unroll
@@ -595,23 +610,59 @@ __global__ void __launch_bounds__(256) k_tgather_t(Ctx c, int cls) {       // cl
 }
 
 // ------------------------------------------------------------------ dense panel halves of the SpMV pair
-// Counts 0..255 as bytes, columns [0, P) contiguous in y: both halves stream the panel rows with coalesced loads and no index
-// traffic.  A byte b is used as the DENORMAL double with bit pattern (hi = 0, lo = b) = b * 2^-1074 -- exact, one PRMT and no
-// conversion instruction (cvt.f64.u32 runs at a fraction of the fp64 rate; the 2^52 trick costs an extra DADD per entry, which
-// made both kernels fp64-issue bound).  The dense operand (x or y) is pre-scaled by 2^960 where it is staged in shared memory
-// and the sums are scaled back by 2^114 once per row / column: power-of-two scalings are exact and every product is formed
-// exactly inside the FMA, so the result is bit-identical to converting the byte first.  |x| < 2^63 is required (else inf -> the
+// Small counts stored densely, columns [0, P) contiguous in y: both halves stream the panel rows with coalesced loads and no
+// index traffic.  Two formats (Ctx::pnib): one byte per cell (counts <= 255) or one nibble per cell (counts <= 15, the usual
+// case for UMI counts; larger counts live in the residual CSR).
+// A stored count b is used as the DENORMAL double with bit pattern (hi = 0, lo = b) = b * 2^-1074 -- exact, one PRMT (byte) or
+// one LOP3 (nibble, masked IN PLACE: lo = w & (15 << 4k) = b * 16^k) and no conversion instruction (cvt.f64.u32 runs at a
+// fraction of the fp64 rate; the 2^52 trick costs an extra DADD per entry, which made both kernels fp64-issue bound).  The dense
+// operand (x or y) is pre-scaled by 2^960 (and y by 16^-k for nibble k) where it is staged in shared memory, the sums are
+// scaled back by 2^114 (and 16^-k) once per row / column: power-of-two scalings are exact and every product is formed exactly
+// inside the FMA, so the result is bit-identical to converting the count first.  |x| < 2^60 is required (else inf -> the
 // non-finite degree / Ritz checks fire); the engine's vectors are bounded by the row factors and the column sums.
 #define TMC_PANEL_UP 0x1p960
 #define TMC_PANEL_DOWN 0x1p114
 __device__ __forceinline__ double u8_f64(unsigned w, int k) { return __hiloint2double(0, (int)__byte_perm(w, 0u, 0x4440u + (unsigned)k)); }
-// y[0..P) += w^2 * sum_r panel[r][.] * xin[r] over the rows of G consecutive vector chunks.  Lane = 16 columns (one 16-byte load
-// per row), warp = 512 columns, CTA = blockDim/32 warps side by side (the host sizes the CTA so that the slabs divide Ppad
-// evenly); grid (ceil(n_vchunks / G), slabs).  4 rows in flight per warp plus the next 4 prefetched; one atomicAdd per column
-// per CTA and slot.  (Measured alternatives, tools/exp/panel_kern.cu + profiles/r1_v5: 8-byte lanes 3.1 TB/s, a cp.async ring
-// through shared memory 3.1 TB/s, this one 4.4 TB/s; the same arithmetic on a flat stream reaches 5.9 TB/s.)
-template <int NR>
+__device__ __forceinline__ double u4_f64(unsigned w, int k) { return __hiloint2double(0, (int)(w & (15u << (4 * k)))); }      // = count * 16^k * 2^-1074
+// 16 columns of one panel row as seen by a lane: 16 bytes, or 8 bytes of nibbles
+template <int NIB> struct PanelLane { typedef uint4 T; };
+template <> struct PanelLane<1> { typedef uint2 T; };
+// acc[0..16) += cells * xv; nibble format: acc[8*i + k] carries the extra factor 16^k (removed by the caller)
+template <int NIB> __device__ __forceinline__ void panel_fma(const typename PanelLane<NIB>::T& d, double xv, double* acc) {
+  if constexpr (NIB != 0) {
+    const unsigned w[2] = {d.x, d.y};
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[8 * i + k] += u4_f64(w[i], k) * xv;
+  } else {
+    const unsigned w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[4 * i + k] += u8_f64(w[i], k) * xv;
+  }
+}
+// one 32-bit word of a lane (4 byte cells / 8 nibble cells) times its y values (2 / 4 double2 holding the format's column scale)
+template <int NIB> __device__ __forceinline__ double panel_word_dot(unsigned w, const double2* yv) {
+  if constexpr (NIB != 0)
+    return u4_f64(w, 0) * yv[0].x + u4_f64(w, 1) * yv[0].y + u4_f64(w, 2) * yv[1].x + u4_f64(w, 3) * yv[1].y +
+           u4_f64(w, 4) * yv[2].x + u4_f64(w, 5) * yv[2].y + u4_f64(w, 6) * yv[3].x + u4_f64(w, 7) * yv[3].y;
+  else
+    return u8_f64(w, 0) * yv[0].x + u8_f64(w, 1) * yv[0].y + u8_f64(w, 2) * yv[1].x + u8_f64(w, 3) * yv[1].y;
+}
+template <int NIB> __device__ __forceinline__ unsigned panel_word(const typename PanelLane<NIB>::T& d, int wi) {
+  if constexpr (NIB != 0) return wi == 0 ? d.x : d.y;
+  else return wi == 0 ? d.x : (wi == 1 ? d.y : (wi == 2 ? d.z : d.w));
+}
+// y[0..P) += w^2 * sum_r panel[r][.] * xin[r] over the rows of G consecutive vector chunks.  Lane = 16 columns (one 16-byte or
+// 8-byte load per row), warp = 512 columns, CTA = blockDim/32 warps side by side (the host sizes the CTA so that the slabs divide
+// Ppad evenly); grid (ceil(n_vchunks / G), slabs).  Two register sets of NR rows in ping-pong: the next rows are in flight during
+// the math; one atomicAdd per column per CTA and slot.  (Measured alternatives, tools/exp/panel_kern.cu + profiles/r1_v5, v6:
+// 8-byte lanes with converted bytes 3.1 TB/s, a cp.async ring through shared memory 3.1 TB/s, this one 6.1 TB/s on bytes.)
+template <int NR, int NIB>
 __global__ void __launch_bounds__(256) k_tpanel(Ctx c, int G) {
+  typedef typename PanelLane<NIB>::T LT;
   __shared__ int s_row[TMC_MAX_CHUNK + 2 * NR];
   __shared__ double s_x[TMC_MAX_CHUNK + 2 * NR];
   const int nv = *c.n_vchunks;
@@ -621,8 +672,8 @@ __global__ void __launch_bounds__(256) k_tpanel(Ctx c, int G) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int colw = (blockIdx.y * (blockDim.x >> 5) + warp) * 512;
   const bool on = colw < c.Ppad;
-  const uint4* __restrict__ pb = reinterpret_cast<const uint4*>(c.panel + colw) + lane;
-  const size_t ws = (size_t)(c.Ppad >> 4);                                       // uint4 per panel row
+  const LT* __restrict__ pb = reinterpret_cast<const LT*>(c.panel + (NIB ? (colw >> 1) : colw)) + lane;
+  const size_t ws = (size_t)c.pw / sizeof(LT);                                    // lane units per panel row
   double acc[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = 0.0;
@@ -633,7 +684,8 @@ __global__ void __launch_bounds__(256) k_tpanel(Ctx c, int G) {
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const int cj = colw + lane * 16 + k;
-        if (cj < c.P && acc[k] != 0.0) atomicAdd(y + cj, acc[k] * TMC_PANEL_DOWN * __ldg(c.w2col + cj));
+        const double down = NIB ? TMC_PANEL_DOWN / (double)(1u << (4 * (k & 7))) : TMC_PANEL_DOWN;
+        if (cj < c.P && acc[k] != 0.0) atomicAdd(y + cj, acc[k] * down * __ldg(c.w2col + cj));
         acc[k] = 0.0;
       }
     }
@@ -653,24 +705,17 @@ __global__ void __launch_bounds__(256) k_tpanel(Ctx c, int G) {
     }
     __syncthreads();
     if (!on) continue;
-    uint4 d0[NR], d1[NR];
-    auto load = [&](uint4* d, int r) {
+    LT d0[NR], d1[NR];
+    auto load = [&](LT* d, int r) {
 #pragma unroll
       for (int q = 0; q < NR; ++q) d[q] = __ldg(pb + (size_t)s_row[r + q] * ws);
     };
-    auto fma_rows = [&](const uint4* d, int r) {
+    auto fma_rows = [&](const LT* d, int r) {
 #pragma unroll
-      for (int q = 0; q < NR; ++q) {
-        const double xv = s_x[r + q];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          acc[k] += u8_f64(d[q].x, k) * xv; acc[4 + k] += u8_f64(d[q].y, k) * xv;
-          acc[8 + k] += u8_f64(d[q].z, k) * xv; acc[12 + k] += u8_f64(d[q].w, k) * xv;
-        }
-      }
+      for (int q = 0; q < NR; ++q) panel_fma<NIB>(d[q], s_x[r + q], acc);
     };
     load(d0, 0);
-    for (int r = 0; r < lenp; r += 2 * NR) {          // two register sets in ping-pong: the next rows are in flight during the math
+    for (int r = 0; r < lenp; r += 2 * NR) {
       load(d1, r + NR);
       fma_rows(d0, r);
       if (r + 2 * NR < lenp) load(d0, r + 2 * NR);
@@ -682,10 +727,11 @@ __global__ void __launch_bounds__(256) k_tpanel(Ctx c, int G) {
 // pacc[p] = sum_{j < P} panel[row(p)][j] * y[j]; one CTA per vector chunk.  y is staged in shared memory in blocks of TMC_GP_CB
 // columns, stored so that the eight 16-byte reads of a lane (its 16 columns of a 512-column step) are conflict-free: the pair
 // (16*lane + 2j, 16*lane + 2j + 1) sits at double2 index j*32 + lane.  A warp works on NR rows at a time (every y value read
-// from shared memory is used NR times) with the next step's panel bytes already in flight.
+// from shared memory is used NR times); two register sets in ping-pong keep the next step's panel bytes in flight.
 #define TMC_GP_CB 4096
-template <int NR>
+template <int NR, int NIB>
 __global__ void __launch_bounds__(256) k_gather_panel(Ctx c) {
+  typedef typename PanelLane<NIB>::T LT;
   __shared__ double2 ys2[TMC_GP_CB / 2];
   __shared__ double ps[TMC_MAX_CHUNK];
   if ((int)blockIdx.x >= *c.n_vchunks) return;
@@ -699,40 +745,42 @@ __global__ void __launch_bounds__(256) k_gather_panel(Ctx c) {
     const int nb = min(TMC_GP_CB, c.Ppad - cb);
     __syncthreads();
     for (int t = threadIdx.x; t < (nb >> 1); t += 256) {
-      const int w = t & 255;
+      const int w = t & 255;                       // pair index inside the 512-column step: columns 2w, 2w + 1
       double2 yv = ldg_d2(y + cb + 2 * t);
-      yv.x *= TMC_PANEL_UP; yv.y *= TMC_PANEL_UP;
+      // nibble format: column j of a lane sits in nibble (j & 7) of its word, read in place as count * 16^(j & 7)
+      const double up0 = NIB ? TMC_PANEL_UP / (double)(1u << (4 * ((2 * w) & 7))) : TMC_PANEL_UP;
+      yv.x *= up0; yv.y *= NIB ? up0 * 0.0625 : up0;
       ys2[(t & ~255) + ((w & 7) << 5) + (w >> 3)] = yv;
     }
     __syncthreads();
     const int nit = nb >> 9;
     for (int r0 = warp * NR; r0 < ch.len; r0 += 8 * NR) {
       const int nr = min(NR, ch.len - r0);
-      const uint4* pr[NR];
+      const LT* pr[NR];
 #pragma unroll
       for (int q = 0; q < NR; ++q)
-        pr[q] = reinterpret_cast<const uint4*>(c.panel + (size_t)c.perm[ch.begin + r0 + min(q, nr - 1)] * c.Ppad + cb) + lane;
+        pr[q] = reinterpret_cast<const LT*>(c.panel + (size_t)c.perm[ch.begin + r0 + min(q, nr - 1)] * c.pw + (NIB ? (cb >> 1) : cb)) + lane;
       double acc[NR];
 #pragma unroll
       for (int q = 0; q < NR; ++q) acc[q] = 0.0;
-      uint4 d0[NR], d1[NR];
-      auto load = [&](uint4* d, int i) {
+      LT d0[NR], d1[NR];
+      auto load = [&](LT* d, int i) {
 #pragma unroll
         for (int q = 0; q < NR; ++q) d[q] = __ldg(pr[q] + 32 * i);
       };
-      auto fma_step = [&](const uint4* d, int i) {
+      auto fma_step = [&](const LT* d, int i) {
+        constexpr int NW = NIB ? 2 : 4, NP = 8 / NW;       // words per lane, y pairs per word
 #pragma unroll
-        for (int cpt = 0; cpt < 4; ++cpt) {
-          const double2 ya = ys2[i * 256 + (2 * cpt) * 32 + lane], yb = ys2[i * 256 + (2 * cpt + 1) * 32 + lane];
+        for (int wi = 0; wi < NW; ++wi) {
+          double2 yv[NP];
 #pragma unroll
-          for (int q = 0; q < NR; ++q) {
-            const unsigned w = cpt == 0 ? d[q].x : (cpt == 1 ? d[q].y : (cpt == 2 ? d[q].z : d[q].w));
-            acc[q] += u8_f64(w, 0) * ya.x + u8_f64(w, 1) * ya.y + u8_f64(w, 2) * yb.x + u8_f64(w, 3) * yb.y;
-          }
+          for (int j = 0; j < NP; ++j) yv[j] = ys2[i * 256 + (wi * NP + j) * 32 + lane];
+#pragma unroll
+          for (int q = 0; q < NR; ++q) acc[q] += panel_word_dot<NIB>(panel_word<NIB>(d[q], wi), yv);
         }
       };
       load(d0, 0);
-      for (int i = 0; i < nit; i += 2) {               // two register sets in ping-pong: the next step is in flight during the math
+      for (int i = 0; i < nit; i += 2) {
         if (i + 1 < nit) load(d1, i + 1);
         fma_step(d0, i);
         if (i + 2 < nit) load(d0, i + 2);

@@ -110,10 +110,10 @@ class DeviceB:
 
     def info(self):
         """Storage of the device copy: value type, dense-panel width, residual CSR entries (tmc_matrix_info)."""
-        v = (C.c_int64 * 6)()
-        check(_lib.load().tmc_matrix_info(self.handle, v, 6))
-        return {"value_type": ("f64", "u16", "one")[int(v[0])], "panel_cols": int(v[1]), "panel_width": int(v[2]),
-                "residual_nnz": int(v[3]), "nnz": int(v[4]), "n_rows": int(v[5])}
+        v = (C.c_int64 * 7)()
+        check(_lib.load().tmc_matrix_info(self.handle, v, 7))
+        return {"value_type": ("f64", "u16", "one")[int(v[0])], "panel_cols": int(v[1]), "panel_row_bytes": int(v[2]),
+                "residual_nnz": int(v[3]), "nnz": int(v[4]), "n_rows": int(v[5]), "panel_bits": int(v[6])}
 
     def free(self):
         if self.handle:
