@@ -643,13 +643,15 @@ template <int NIB> __device__ __forceinline__ void panel_fma(const typename Pane
       for (int k = 0; k < 4; ++k) acc[4 * i + k] += u8_f64(w[i], k) * xv;
   }
 }
-// one 32-bit word of a lane (4 byte cells / 8 nibble cells) times its y values (2 / 4 double2 holding the format's column scale)
-template <int NIB> __device__ __forceinline__ double panel_word_dot(unsigned w, const double2* yv) {
-  if constexpr (NIB != 0)
-    return u4_f64(w, 0) * yv[0].x + u4_f64(w, 1) * yv[0].y + u4_f64(w, 2) * yv[1].x + u4_f64(w, 3) * yv[1].y +
-           u4_f64(w, 4) * yv[2].x + u4_f64(w, 5) * yv[2].y + u4_f64(w, 6) * yv[3].x + u4_f64(w, 7) * yv[3].y;
-  else
-    return u8_f64(w, 0) * yv[0].x + u8_f64(w, 1) * yv[0].y + u8_f64(w, 2) * yv[1].x + u8_f64(w, 3) * yv[1].y;
+// a += one 32-bit word of a lane (4 byte cells / 8 nibble cells) times its y values (2 / 4 double2 holding the format's column scale)
+template <int NIB> __device__ __forceinline__ void panel_word_dot(unsigned w, const double2* yv, double& a) {
+  if constexpr (NIB != 0) {
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) { a = fma(u4_f64(w, k), yv[k >> 1].x, a); a = fma(u4_f64(w, k + 1), yv[k >> 1].y, a); }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) { a = fma(u8_f64(w, k), yv[k >> 1].x, a); a = fma(u8_f64(w, k + 1), yv[k >> 1].y, a); }
+  }
 }
 template <int NIB> __device__ __forceinline__ unsigned panel_word(const typename PanelLane<NIB>::T& d, int wi) {
   if constexpr (NIB != 0) return wi == 0 ? d.x : d.y;
@@ -776,7 +778,7 @@ __global__ void __launch_bounds__(256) k_gather_panel(Ctx c) {
 #pragma unroll
           for (int j = 0; j < NP; ++j) yv[j] = ys2[i * 256 + (wi * NP + j) * 32 + lane];
 #pragma unroll
-          for (int q = 0; q < NR; ++q) acc[q] += panel_word_dot<NIB>(panel_word<NIB>(d[q], wi), yv);
+          for (int q = 0; q < NR; ++q) panel_word_dot<NIB>(panel_word<NIB>(d[q], wi), yv, acc[q]);
         }
       };
       load(d0, 0);
