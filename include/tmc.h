@@ -117,8 +117,9 @@ int tmc_row_l2(const tmc_csr* b2, double* val_out, double* norm_out);
 /* Upload a B2 matrix (host CSR) and keep B = b2ToB(B2) on the device (normalize=1 applies idf first). */
 int  tmc_matrix_upload(const tmc_csr* b2, int normalize, int device, tmc_matrix** out);
 /* Adopt DEVICE arrays (row_ptr int64, col int32, val double; not copied, caller keeps them alive).
- * val_dev is normalised in place (idf if normalize, then row L2) only when the values are not small integers; raw
- * counts are left untouched and a compact uint16 copy is kept instead.  row_offset / n_rows_global describe this
+ * val_dev is normalised in place (idf if normalize, then row L2) only when the values are neither small integers nor
+ * an exactly recognisable B2 = counts * diag(column weight) (a tf-idf matrix, normalize = 0); in those two cases the array
+ * is left untouched and a compact copy of the counts is kept instead.  row_offset / n_rows_global describe this
  * rank's row block under a communicator (0, 0 = the whole matrix). */
 int  tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* row_ptr_dev,
                           const int32_t* col_dev, double* val_dev, int64_t row_offset, int64_t n_rows_global,

@@ -188,3 +188,53 @@ def test_panel_density_knob_extremes(density, golden_tiny):
     tree = T.hierarchical_spectral_cluster(db)
     assert same_tree(tree, ref)
     db.free()
+
+
+# ---------------------------------------------------------------- factor recovery from an already tf-idf-scaled matrix
+@pytest.mark.parametrize("where", ["numpy", "gpu"])
+def test_recover_counts_from_tfidf_matrix(where, golden_tiny):
+    """The reference hands hierarchicalSpectralCluster the tf-idf matrix (Cluster.hs:147, normFlag False).  B2 = A diag(idf) is
+    recognised bit for bit, so the compact storage (and the panel) applies to the reference's own call pattern too."""
+    a, z = golden_tiny
+    b2 = O.b1_to_b2(a) if where == "numpy" else T.tfidf_scale_sparse_mat(a)
+    db = T.DeviceB.from_host(b2)
+    info = db.info()
+    assert info["value_type"] == "u16" and info["panel_cols"] >= 8
+    with env(TMC_NO_RECOVER=1):
+        d64 = T.DeviceB.from_host(b2)
+    assert d64.info()["value_type"] == "f64" and d64.info()["panel_cols"] == 0
+    assert rel(T.b_to_d(db), T.b_to_d(d64)) < 1e-13
+    x = np.random.default_rng(2).standard_normal(a.shape[0])
+    assert rel(T.spmv_pair(db, x), T.spmv_pair(d64, x)) < 1e-12
+    t0, t1 = T.hierarchical_spectral_cluster(db), T.hierarchical_spectral_cluster(d64)
+    assert same_tree(t0, t1) and float(np.max(np.abs(t0.q - t1.q))) < 1e-12
+    gold = {}
+    for r, l in enumerate(z["leaf_of_row"]):
+        gold.setdefault(int(l), []).append(r)
+    assert t0.leaf_sets() == sorted(tuple(v) for v in gold.values())
+    cl, tree = T.h_spec_clust(b2, [f"c{i}" for i in range(a.shape[0])])          # the documented drop-in call
+    assert same_tree(tree, t0)
+    db.free(); d64.free()
+
+
+def test_recover_handles_columns_without_a_unit_count_and_rejects_inexact_input():
+    a, _ = dense_cols_counts(seed=21)
+    a = a.tolil()
+    a[:, 4] = 0; a[::2, 4] = 2; a[1::4, 4] = 6           # every count of this feature is even: w = 2 idf, counts 1 and 3
+    a = sp.csr_matrix(a)
+    b2 = O.b1_to_b2(a)
+    db = T.DeviceB.from_host(b2)
+    assert db.info()["value_type"] == "u16"
+    b = O.b2_to_b(b2)
+    assert rel(T.b_to_d(db), O.b_to_d(b)) < 1e-13
+    db.free()
+    a2 = a.tolil(); a2[0, 4] = 3; a2 = sp.csr_matrix(a2)  # 3 is not a multiple of the smallest count 2: not representable
+    b2 = O.b1_to_b2(a2)
+    db = T.DeviceB.from_host(b2)
+    assert db.info()["value_type"] == "f64"
+    assert rel(T.b_to_d(db), O.b_to_d(O.b2_to_b(b2))) < 1e-13
+    db.free()
+    noisy = b2.copy(); noisy.data = noisy.data * (1.0 + 1e-9 * np.random.default_rng(3).random(noisy.nnz))
+    db = T.DeviceB.from_host(noisy)
+    assert db.info()["value_type"] == "f64"
+    db.free()

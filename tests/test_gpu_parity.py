@@ -27,7 +27,15 @@ def same_tree(tree, ot):
 def tiny(golden_tiny):
     a, z = golden_tiny
     b2 = O.b1_to_b2(a)
-    return a, z, b2, O.b2_to_b(b2), T.DeviceB.from_host(b2)
+    # the fp64-stored path (B materialised): factor recovery off, it has its own tests in test_gpu_panel.py
+    import os
+    os.environ["TMC_NO_RECOVER"] = "1"
+    try:
+        db = T.DeviceB.from_host(b2)
+    finally:
+        del os.environ["TMC_NO_RECOVER"]
+    assert db.info()["value_type"] == "f64"
+    return a, z, b2, O.b2_to_b(b2), db
 
 
 def test_device_present():

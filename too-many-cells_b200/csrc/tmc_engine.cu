@@ -495,6 +495,10 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
   renumber_columns(b);
   int* d_flags = dalloc<int>(6);          // [0] value flags, [1] error code, [2..5] two 64-bit counters of small values
   int* df = nullptr; double* idf = nullptr;
+  double* wrec = nullptr; double* counts = nullptr; double* borrowed_val = nullptr;
+  auto restore_val = [&]() {        // a temporary count array standing in for a borrowed value array
+    if (borrowed_val) { if (b->val && b->val != borrowed_val) cudaFree(b->val); b->val = borrowed_val; borrowed_val = nullptr; }
+  };
   try {
     CK(cudaMemset(d_flags, 0, 6 * sizeof(int)));
     const int grid = 148 * 8;
@@ -524,7 +528,44 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     if (f[0] & 1) throw TmcError(TMC_ERR_NAN, "NaN/Inf in matrix values");
     if (f[0] & 4) throw TmcError(TMC_ERR_INVALID, "column index out of range");
     if (f[0] & 2) throw TmcError(TMC_ERR_NEGATIVE, "negative matrix entry (engine requires B >= 0)");
-    const bool small_int = !(f[0] & 8) && getenv("TMC_NO_FACTORED") == nullptr;
+    bool small_int = !(f[0] & 8) && getenv("TMC_NO_FACTORED") == nullptr;
+    if (!small_int && !normalize && b->nnz > 0 && getenv("TMC_NO_FACTORED") == nullptr && getenv("TMC_NO_RECOVER") == nullptr) {
+      // B2 = A diag(w) handed over already scaled (Cluster.hs:147 receives the tf-idf matrix): recover A and w if that is exact
+      wrec = dalloc<double>(b->n_cols);
+      k_fill_f64<<<(unsigned)((b->n_cols + 255) / 256), 256>>>(wrec, b->n_cols, INFINITY);
+      k_colmin<<<grid, 256>>>(b->col, b->val, b->nnz, reinterpret_cast<unsigned long long*>(wrec));
+      const bool sharded = g_nccl.comm && g_nccl.world > 1 && !b->replicated;
+      if (sharded && g_nccl.AllReduce(wrec, wrec, (size_t)b->n_cols, NCCL_FLOAT64, NCCL_MIN, g_nccl.comm, 0) != 0)
+        throw TmcError(TMC_ERR_COMM, "ncclAllReduce(column minima) failed");
+      k_colmin_fix<<<(int)((b->n_cols + 255) / 256), 256>>>(wrec, (int)b->n_cols);
+      CK(cudaMemset(d_flags + 2, 0, 4 * sizeof(int)));
+      int* d_rf = dalloc<int>(1);
+      CK(cudaMemset(d_rf, 0, sizeof(int)));
+      k_factor_check<<<grid, 256>>>(b->col, b->val, b->nnz, wrec, nullptr, d_rf, d_small);
+      int rf = 0;
+      CK(cudaMemcpy(&rf, d_rf, sizeof(int), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(n_small, d_small, sizeof(n_small), cudaMemcpyDeviceToHost));
+      if (sharded) {
+        std::vector<double> ns = {(double)n_small[0], (double)n_small[1], (rf & 8) ? 1.0 : 0.0, (rf & 16) ? 1.0 : 0.0};
+        double* dn = dalloc<double>(4);
+        cudaMemcpy(dn, ns.data(), 32, cudaMemcpyHostToDevice);
+        int r = g_nccl.AllReduce(dn, dn, 4, NCCL_FLOAT64, NCCL_SUM, g_nccl.comm, 0);
+        cudaMemcpy(ns.data(), dn, 32, cudaMemcpyDeviceToHost); cudaFree(dn);
+        if (r != 0) { cudaFree(d_rf); throw TmcError(TMC_ERR_COMM, "ncclAllReduce(factor check) failed"); }
+        n_small[0] = (unsigned long long)ns[0]; n_small[1] = (unsigned long long)ns[1];
+        rf = (ns[2] > 0 ? 8 : 0) | (ns[3] > 0 ? 16 : 0);
+      }
+      if (!(rf & 8)) {
+        // exact: replace the values by the counts (in place when the engine owns the array, else in a temporary)
+        counts = b->owns ? b->val : dalloc<double>(b->nnz);
+        k_factor_check<<<grid, 256>>>(b->col, b->val, b->nnz, wrec, counts, d_rf, nullptr);
+        borrowed_val = b->owns ? nullptr : b->val;
+        b->val = counts;
+        small_int = true;
+        f[0] = (f[0] & ~(8 | 16)) | (rf & 16);
+      } else { cudaFree(wrec); wrec = nullptr; }
+      cudaFree(d_rf);
+    }
     if (!small_int) {
       cudaFree(d_flags); d_flags = nullptr;
       b->vt = VT_F64;
@@ -532,6 +573,7 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
       return;
     }
     b->vt = (f[0] & 16) ? VT_U16 : VT_ONE;
+    if (wrec) { idf = wrec; wrec = nullptr; }        // the recovered column weights take the place of idf
     const bool want_panel = getenv("TMC_NO_PANEL") == nullptr;
     if (normalize || want_panel) {       // column frequencies: idf, and the choice of the dense panel
       df = dalloc<int>(b->n_cols);
@@ -565,15 +607,18 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     CK(cudaMemcpy(f, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost));
     if (have_panel && b->owns && b->col) { cudaFree(b->col); b->col = nullptr; }    // only the residual is walked from here on
     if (b->owns && b->val) { cudaFree(b->val); b->val = nullptr; }       // the fp64 copy is not needed any more
+    restore_val();
     cudaFree(d_flags); d_flags = nullptr;
     if (df) cudaFree(df);
     if (idf) cudaFree(idf);
     df = nullptr; idf = nullptr;
     if (f[1]) { std::string msg; int st = err_to_status(f[1], &msg); throw TmcError(st, msg); }
   } catch (...) {
+    restore_val();
     if (d_flags) cudaFree(d_flags);
     if (df) cudaFree(df);
     if (idf) cudaFree(idf);
+    if (wrec) cudaFree(wrec);
     throw;
   }
 }

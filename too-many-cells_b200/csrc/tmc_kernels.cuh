@@ -266,6 +266,50 @@ __global__ void k_scan_values(const int32_t* __restrict__ col, const double* __r
     if ((threadIdx.x & 31) == 0) { if (n15) atomicAdd(n_small, (unsigned long long)n15); if (n255) atomicAdd(n_small + 1, (unsigned long long)n255); }
   }
 }
+// ---- factor recovery: a caller-supplied B2 = A diag(w) (tf-idf already applied, the reference's own call pattern at
+// Cluster.hs:147) is recognised so that the compact storage applies: w_j = smallest positive value of column j, A = B2 / w.
+// Accepted only if EVERY entry is reproduced bit for bit by fl(round(v / w_j) * w_j) with a count in [1, 65535].
+__global__ void k_colmin(const int32_t* __restrict__ col, const double* __restrict__ val, int64_t nnz, unsigned long long* __restrict__ cmin) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) {
+    const double v = val[i];
+    if (v > 0.0) {                                 // positive doubles order like their bit patterns
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+      unsigned long long* p = cmin + col[i];
+      if (bits < *p) atomicMin(p, bits);           // racy pre-check: only skips when the stored value is already smaller
+    }
+  }
+}
+__global__ void k_colmin_fix(double* __restrict__ w, int n) {        // columns without a positive entry: weight 0
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n && isinf(w[j])) w[j] = 0.0;
+}
+// cnt_out == nullptr: check only.  flags |= 8 when some entry is not an exact small multiple, |= 16 when some count != 1.
+__global__ void k_factor_check(const int32_t* __restrict__ col, const double* __restrict__ val, int64_t nnz, const double* __restrict__ w,
+                               double* __restrict__ cnt_out, int* __restrict__ flags, unsigned long long* __restrict__ n_small) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int f = 0, n15 = 0, n255 = 0;
+  for (; i < nnz; i += stride) {
+    const double v = val[i];
+    double r = 0.0;
+    if (v > 0.0) {
+      const double wj = __ldg(w + col[i]);
+      r = rint(v / wj);
+      if (!(r >= 1.0 && r <= 65535.0 && __dmul_rn(r, wj) == v)) f |= 8;
+      if (r != 1.0) f |= 16;
+      n15 += (r <= 15.0); n255 += (r <= 255.0);
+    }
+    if (cnt_out) cnt_out[i] = r;
+  }
+  f = __reduce_or_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+  if (n_small) {
+    n15 = __reduce_add_sync(0xffffffffu, n15); n255 = __reduce_add_sync(0xffffffffu, n255);
+    if ((threadIdx.x & 31) == 0) { if (n15) atomicAdd(n_small, (unsigned long long)n15); if (n255) atomicAdd(n_small + 1, (unsigned long long)n255); }
+  }
+}
 __global__ void k_to_u16(const double* __restrict__ val, unsigned short* __restrict__ out, int64_t nnz) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
