@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 METRIC = "ms per full make-tree"
 UNIT = "ms"
 # ncu dram bytes (read + write) of the root-level SpMV pair on c3, 1 GPU (profiles/, see the roofline comment below)
-TRAFFIC_C3_ROOT_PAIR = 21.92e9
+TRAFFIC_C3_ROOT_PAIR = 13.84e9
 
 
 def parse():
@@ -274,13 +274,14 @@ def main():
         b.free()
         bv = tr.stats["value_bytes"]          # 8: fp64 B; 2: raw counts as uint16 + diagonal factors; 0: all-ones matrix
         # stored bytes of one pair: (value + column index) per residual CSR entry and half, one byte per panel cell and half
-        pair_bytes = 2.0 * (bv + 4.0) * storage["residual_nnz"] + 2.0 * n * storage["panel_cols"] + 16.0 * (n + 1) + 32.0 * n + 16.0 * g
+        pair_bytes = (2.0 * (bv + 4.0) * storage["residual_nnz"] + 2.0 * n * storage["panel_cols"] * storage["panel_bits"] / 8.0
+                      + 16.0 * (n + 1) + 32.0 * n + 16.0 * g)
         root_pair = {"scatter_ms": sc_ms, "gather_ms": ga_ms, "bytes": pair_bytes, "storage": storage,
                      "scatter_gbs": 0.5 * pair_bytes / (sc_ms * 1e-3) / 1e9, "gather_gbs": 0.5 * pair_bytes / (ga_ms * 1e-3) / 1e9}
     else:
         root_pair = None
     # dram__bytes_read + write of the root-level pair launches from the committed `ncu --set full` capture
-    # (profiles/r1_v6_panel_pair_c3_ncu_raw.csv: k_tgather_t + k_tpanel + k_gather_panel + k_gather_u); the stored bytes of that
+    # (profiles/r1_v7_nibble_pair_c3_ncu_raw.csv: k_tgather_t + k_tpanel + k_gather_panel + k_gather_u); the stored bytes of that
     # pair are 2*(6 B * residual entries + panel bytes): the column-sorted residual copy also stores the cell position of every
     # entry (10 B per entry instead of 6), that is the whole difference - nothing is read twice.
     traffic = TRAFFIC_C3_ROOT_PAIR if (name == "c3" and world == 1 and tr.stats["value_bytes"] == 2 and root_pair and root_pair["storage"]["panel_cols"] > 0) else None
@@ -289,7 +290,7 @@ def main():
             "algorithmic_bytes_per_step": alg / len(trees), "value_bytes_b_v": tr.stats["value_bytes"],
             "achieved_if_counted_with_fp64_values_b_v8": achieved_nominal,
             "frac_if_counted_with_fp64_values_b_v8": (achieved_nominal / peak) if achieved_nominal else None,
-            "algorithmic_bytes_formula": "per SpMV pair 2*nnz_residual*(b_v+4) + 2*m*P + 2*(m+1)*8 + (4*m+2*n)*8 (BASELINE.md section 4 with the storage actually used: b_v = bytes per stored value, P = dense panel columns at one byte per cell)", "spmv_ms_per_step": spmv_ms / len(trees),
+            "algorithmic_bytes_formula": "per SpMV pair 2*nnz_residual*(b_v+4) + 2*m*P*c + 2*(m+1)*8 + (4*m+2*n)*8 (BASELINE.md section 4 with the storage actually used: b_v = bytes per stored value, P = dense panel columns at one byte or half a byte per cell)", "spmv_ms_per_step": spmv_ms / len(trees),
             "spmv_share_of_step": spmv_ms / len(trees) / ms_step,
             "per_gpu": True, "root_pair": root_pair}
     line = {"metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
