@@ -998,8 +998,9 @@ struct Engine {
       }
       else if (nch) { VT_DISPATCH(c.vt, k_scatter<VT><<<nch, 256, 0, s>>>(c)); n_launch++; }
       if (c.P && nvch) {          // dense panel half of y = A^T x: slabs of equal width (a multiple of 512 columns, at most 4096)
-        const int G = std::max(1, 512 / RV);
         const int nslab = (c.Ppad + 4095) / 4096;
+        // up to 512 rows per CTA (one atomicAdd per column and CTA), fewer when that would leave SMs idle (small matrices, tree tails)
+        const int G = std::max(1, std::min(512 / RV, nvch * nslab / 296));
         const int wslab = ((c.Ppad / 512 + nslab - 1) / nslab);      // warps per CTA
         if (c.pnib) k_tpanel<8, 1><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G);
         else k_tpanel<4, 0><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G);
