@@ -144,3 +144,14 @@ def test_cpp_host_layer_matches_python_mirror(tmp_path, golden_tiny):
     want = T.tree_io.clusters_csv(tree, names).replace("\r\n", "\n").rstrip("\n") + "\n"
     # eigenvector sign may differ between two runs only through the (fixed) seed: same seed => same child order
     assert out == want
+
+
+def test_panel_cells_as_denormal_doubles_are_exact(tmp_path):
+    """The dense-panel kernels feed a stored count to the FMA as the denormal double (hi = 0, lo = count [<< 4k]) against an
+    operand pre-scaled by 2^960: tests/helpers/denormal_cells.c replays that arithmetic on the host (same IEEE fma) and counts
+    the sums that differ from converting the count first -- there must be none."""
+    exe = tmp_path / "denormal_cells"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), os.path.join(ROOT, "tests", "helpers", "denormal_cells.c"), "-lm"],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "0"
