@@ -83,3 +83,101 @@ def test_prune_min_size_matches_golden_pruned_outputs(golden_tree):
     assert T.node_info_csv(pruned, lab, significance=False) == open(os.path.join(W, "pruned_node_info.csv"), newline="").read()
     assert T.prune_min_size(tree, 1).n_nodes == tree.n_nodes                      # no-op
     assert T.prune_min_size(tree, 10 ** 9).n_nodes == 1                           # everything collapses into the root
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The other birch-beer stopping rules (--max-step, --max-proportion, --min-distance, --min-distance-search, --custom-cut,
+# --root-cut, --smart-cutoff).  The reference's golden files only exercise --min-size, and birch-beer is not vendored, so these
+# tests check the semantics the flag help texts state (Options.hs:176-184) as properties on the golden tree.
+def _leaf_cells_in_order(tree):
+    import numpy as np
+    out, stack = [], [0]
+    while stack:
+        u = stack.pop()
+        if tree.left[u] < 0:
+            out.extend(int(r) for r in tree.items(u))
+        else:
+            stack.append(int(tree.right[u])); stack.append(int(tree.left[u]))
+    return out
+
+
+def _check_is_pruning_of(pruned, tree):
+    """Every pruned tree keeps all cells in the same DFS-leaf order and pre-order ids with children [left = id + 1]."""
+    assert _leaf_cells_in_order(pruned) == _leaf_cells_in_order(tree)
+    for i in range(pruned.n_nodes):
+        if pruned.left[i] >= 0:
+            assert pruned.left[i] == i + 1 and pruned.right[i] > pruned.left[i]
+
+
+def test_prune_max_step(golden_tree):
+    _, tree, _ = golden_tree
+    depth0 = T.node_depths(tree)
+    for s in (0, 1, 3, 50):
+        p = T.prune_max_step(tree, s)
+        _check_is_pruning_of(p, tree)
+        d = T.node_depths(p)
+        assert d.max() == min(s, depth0.max())
+        assert sum(1 for i in range(p.n_nodes) if p.left[i] >= 0 and d[i] >= s) == 0
+    assert T.prune_max_step(tree, 0).n_nodes == 1 and T.prune_max_step(tree, 50).n_nodes == tree.n_nodes
+
+
+def test_prune_min_distance_and_search(golden_tree):
+    _, tree, _ = golden_tree
+    import numpy as np
+    qs = sorted(float(tree.q[i]) for i in range(tree.n_nodes) if tree.left[i] >= 0)
+    t = qs[len(qs) // 2]
+    p = T.prune_min_distance(tree, t)
+    _check_is_pruning_of(p, tree)
+    par = T.parents_of(p)
+    for i in range(p.n_nodes):                      # an inner vertex survives only below a split of distance >= t
+        if p.left[i] >= 0 and par[i] >= 0:
+            assert p.q[par[i]] >= t
+    assert 1 < p.n_nodes < tree.n_nodes
+    assert T.prune_min_distance(tree, -1.0).n_nodes == tree.n_nodes          # nothing is below the cutoff
+    s = T.prune_min_distance_search(tree, t)
+    _check_is_pruning_of(s, tree)
+    for i in range(s.n_nodes - 1, -1, -1):          # every surviving split leads to (or is) a split of distance >= t
+        if s.left[i] >= 0:
+            stack, ok = [i], False
+            while stack and not ok:
+                u = stack.pop()
+                if s.left[u] >= 0:
+                    ok = s.q[u] >= t
+                    stack += [int(s.left[u]), int(s.right[u])]
+            assert ok
+    assert s.n_nodes >= 1 and T.prune_min_distance_search(s, t).n_nodes == s.n_nodes      # idempotent
+    assert T.prune_min_distance_search(tree, max(qs) + 1.0).n_nodes == 1
+
+
+def test_prune_max_proportion(golden_tree):
+    _, tree, _ = golden_tree
+    import numpy as np
+    p = T.prune_max_proportion(tree, 0.5)
+    _check_is_pruning_of(p, tree)
+    prop, par = T.split_proportions(p), T.parents_of(p)
+    for i in range(p.n_nodes):                      # below a split more lopsided than 1:2 nothing is split further
+        if p.left[i] >= 0 and par[i] >= 0:
+            assert prop[par[i]] <= 1.0
+    assert T.prune_max_proportion(tree, 1e-9).n_nodes == tree.n_nodes
+
+
+def test_custom_cut_and_root_cut(golden_tree):
+    _, tree, _ = golden_tree
+    inner = [i for i in range(1, tree.n_nodes) if tree.left[i] >= 0][:3]
+    p = T.prune_custom_cut(tree, inner[:1])
+    _check_is_pruning_of(p, tree)
+    sizes = T.subtree_sizes(tree)
+    assert p.n_nodes < tree.n_nodes and any(p.left[i] < 0 and len(p.items(i)) == sizes[inner[0]] for i in range(p.n_nodes))
+    r = T.root_cut(tree, inner[1])
+    assert T.subtree_sizes(r)[0] == sizes[inner[1]] and r.q[0] == tree.q[inner[1]]
+    assert T.root_cut(tree, 0).n_nodes == tree.n_nodes
+
+
+def test_smart_cutoff(golden_tree):
+    _, tree, _ = golden_tree
+    assert T.smart_cutoff([1.0, 2.0, 3.0, 4.0, 100.0], 2.0) == 3.0 + 2.0 * 1.0
+    c = T.smart_cutoffs(tree, 1.0)
+    assert set(c) == {"min_size", "max_proportion", "min_distance", "min_distance_search"}
+    assert 1.0 <= c["min_size"] <= 2312 and c["max_proportion"] >= 1.0 and c["min_distance"] > 0
+    p = T.prune_min_size(tree, int(round(c["min_size"])))
+    _check_is_pruning_of(p, tree)

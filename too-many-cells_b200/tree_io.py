@@ -270,17 +270,13 @@ def node_info_csv(tree, label_of_row=None, significance=True) -> str:
     return _csv(hdr, rows)
 
 
-def prune_min_size(tree, min_size: int) -> FlatTree:
-    """`--min-size N` (birch-beer, applied after clustering: Program/MakeTree.hs:98,271; Options.hs:175): a vertex whose
-    either child holds fewer than N cells becomes a leaf holding all cells of its subtree, in DFS-leaf order.  Its
-    `_distance` becomes that of its LEFT child (the Q of the left child if that was an inner vertex, null if it was a leaf) —
-    a quirk of birch-beer's merge that the golden files show.  Pinned against the reference's golden
-    `workshop/out_pruned/*` (made with --min-size 30 from `workshop/out` through --prior)."""
+def _collapse(tree, becomes_leaf) -> FlatTree:
+    """Rebuild the tree top-down; an inner vertex u with becomes_leaf(u) True turns into a leaf holding all cells of its subtree
+    in DFS-leaf order.  Its `_distance` becomes that of its LEFT child (the Q of the left child if that was an inner vertex, null
+    if it was a leaf) -- a quirk of birch-beer's merge that the reference's golden pruned tree shows."""
     tree = _as_flat(tree)
-    size = subtree_sizes(tree)
     n = tree.n_nodes
-    # leaf items of every subtree: pre-order ids => the leaves of subtree(i) are the leaf ids in [i, i + count_i)
-    count = np.ones(n, dtype=np.int64)
+    count = np.ones(n, dtype=np.int64)            # pre-order ids => subtree(i) = ids [i, i + count_i)
     for i in range(n - 1, -1, -1):
         if tree.left[i] >= 0:
             count[i] += count[tree.left[i]] + count[tree.right[i]]
@@ -296,7 +292,7 @@ def prune_min_size(tree, min_size: int) -> FlatTree:
             else:
                 right[parent] = i
         inner = tree.left[u] >= 0
-        if inner and size[tree.left[u]] >= min_size and size[tree.right[u]] >= min_size:
+        if inner and not becomes_leaf(u):
             q[i] = float(tree.q[u])
             stack.append((int(tree.right[u]), i)); stack.append((int(tree.left[u]), i))
         else:
@@ -308,6 +304,113 @@ def prune_min_size(tree, min_size: int) -> FlatTree:
             if inner and tree.left[tree.left[u]] >= 0:
                 q[i] = float(tree.q[tree.left[u]])
     return FlatTree(left, right, q, items)
+
+
+def prune_min_size(tree, min_size: int) -> FlatTree:
+    """`--min-size N` (birch-beer, applied after clustering: Program/MakeTree.hs:98,271; Options.hs:175): a vertex whose
+    either child holds fewer than N cells becomes a leaf.  Pinned against the reference's golden `workshop/out_pruned/*`
+    (made with --min-size 30 from `workshop/out` through --prior)."""
+    tree = _as_flat(tree)
+    size = subtree_sizes(tree)
+    return _collapse(tree, lambda u: size[tree.left[u]] < min_size or size[tree.right[u]] < min_size)
+
+
+# The remaining birch-beer stopping rules (Program/MakeTree.hs:268-276).  birch-beer itself is an un-vendored dependency: these
+# follow the flag help texts (Options.hs:176-184), which are the only in-tree specification, and are NOT pinned to reference
+# outputs (the golden files only exercise --min-size).  Same merge as above.
+def node_depths(tree):
+    tree = _as_flat(tree)
+    depth = np.zeros(tree.n_nodes, dtype=np.int64)
+    for i in range(tree.n_nodes):
+        if tree.left[i] >= 0:
+            depth[tree.left[i]] = depth[tree.right[i]] = depth[i] + 1
+    return depth
+
+
+def prune_max_step(tree, max_step: int) -> FlatTree:
+    """`--max-step S`: "Only keep clusters that are INT steps from the root" -- vertices S steps below the root become leaves."""
+    depth = node_depths(tree)
+    return _collapse(tree, lambda u: depth[u] >= max_step)
+
+
+def split_proportions(tree):
+    """|log2(|L| / |R|)| of every inner vertex (nan for leaves): the quantity --max-proportion and its smart cutoff use."""
+    tree = _as_flat(tree)
+    size = subtree_sizes(tree)
+    out = np.full(tree.n_nodes, np.nan)
+    for i in range(tree.n_nodes):
+        if tree.left[i] >= 0:
+            out[i] = abs(np.log2(size[tree.left[i]] / size[tree.right[i]]))
+    return out
+
+
+def prune_max_proportion(tree, max_proportion: float) -> FlatTree:
+    """`--max-proportion X`: "stop at the node immediate after a node with DOUBLE proportion split ... at 0.5 if |L| / |R| < 0.5
+    or > 2 (absolute log2 transformed) ... Includes L and R in the final result": the children of such a vertex become leaves."""
+    tree = _as_flat(tree)
+    prop, par = split_proportions(tree), parents_of(tree)
+    cut = abs(np.log2(max_proportion))
+    return _collapse(tree, lambda u: par[u] >= 0 and prop[par[u]] > cut)
+
+
+def prune_min_distance(tree, min_distance: float) -> FlatTree:
+    """`--min-distance t`: "a node N with L and R children will stop with this criteria [if] the distance at N to L and R is
+    < DOUBLE.  Includes L and R in the final result": the children of a vertex with Q < t become leaves."""
+    tree = _as_flat(tree)
+    par = parents_of(tree)
+    return _collapse(tree, lambda u: par[u] >= 0 and tree.q[par[u]] < min_distance)
+
+
+def prune_min_distance_search(tree, min_distance: float) -> FlatTree:
+    """`--min-distance-search t`: "searches from the leaves to the root -- if a path from a subtree contains a distance of at
+    least DOUBLE, keep that path, otherwise prune it": a vertex with no split of distance >= t in its subtree becomes a leaf."""
+    tree = _as_flat(tree)
+    best = np.full(tree.n_nodes, -np.inf)
+    for i in range(tree.n_nodes - 1, -1, -1):
+        if tree.left[i] >= 0:
+            best[i] = max(float(tree.q[i]), best[tree.left[i]], best[tree.right[i]])
+    return _collapse(tree, lambda u: best[u] < min_distance)
+
+
+def prune_custom_cut(tree, nodes) -> FlatTree:
+    """`--custom-cut NODE ...`: "List of nodes to prune (make these nodes leaves)"."""
+    cut = set(int(x) for x in nodes)
+    return _collapse(tree, lambda u: u in cut)
+
+
+def root_cut(tree, node: int) -> FlatTree:
+    """`--root-cut NODE`: "Assign a new root to the tree, removing all nodes outside of the subtree" (ids are renumbered in
+    pre-order from the new root)."""
+    tree = _as_flat(tree)
+    n = tree.n_nodes
+    count = np.ones(n, dtype=np.int64)
+    for i in range(n - 1, -1, -1):
+        if tree.left[i] >= 0:
+            count[i] += count[tree.left[i]] + count[tree.right[i]]
+    lo, hi = int(node), int(node) + int(count[node])
+    rel = lambda v: int(v) - lo if v >= 0 else -1
+    return FlatTree([rel(tree.left[v]) for v in range(lo, hi)], [rel(tree.right[v]) for v in range(lo, hi)],
+                    [float(tree.q[v]) for v in range(lo, hi)],
+                    [list(int(r) for r in tree.items(v)) if tree.left[v] < 0 else None for v in range(lo, hi)])
+
+
+def smart_cutoff(values, n_mads: float) -> float:
+    """`--smart-cutoff k`: median + k * MAD of the distribution over all nodes (MAD = median absolute deviation, unscaled)."""
+    v = np.asarray([x for x in values if np.isfinite(x)], dtype=np.float64)
+    med = float(np.median(v))
+    return med + n_mads * float(np.median(np.abs(v - med)))
+
+
+def smart_cutoffs(tree, n_mads: float) -> dict:
+    """The four data-driven cutoffs of `--smart-cutoff` ("--max-proportion and --min-size distributions are log2 transformed"):
+    pass the one you want to the corresponding prune_* function."""
+    tree = _as_flat(tree)
+    size = subtree_sizes(tree)
+    inner_q = [float(tree.q[i]) for i in range(tree.n_nodes) if tree.left[i] >= 0]
+    return {"min_size": float(2.0 ** smart_cutoff(np.log2(size), n_mads)),
+            "max_proportion": float(2.0 ** smart_cutoff(split_proportions(tree), n_mads)),
+            "min_distance": smart_cutoff(inner_q, n_mads),
+            "min_distance_search": smart_cutoff(inner_q, n_mads)}
 
 
 def graph_dot(tree) -> str:
