@@ -36,7 +36,7 @@ typedef enum {
   TMC_ERR_NEGATIVE = -6,    /* negative entry (engine requires B >= 0, as tf-idf of counts is) */
   TMC_ERR_NOMEM = -7,
   TMC_ERR_COMM = -8,        /* NCCL error */
-  TMC_ERR_UNSUPPORTED = -9  /* e.g. eigen_group = KMeansGroup, num_runs > 0 */
+  TMC_ERR_UNSUPPORTED = -9  /* e.g. the non-default variants (KMeansGroup, num_runs > 0) under a multi-GPU communicator */
 } tmc_status;
 
 /* cells x features CSR, rows = cells (MatObsRow, src/TooManyCells/Matrix/Types.hs:152-158).
@@ -55,13 +55,14 @@ typedef struct {
 /* Flag contract of the make-tree engine call (src/TooManyCells/Program/Options.hs:172-178,
  * src/TooManyCells/MakeTree/Cluster.hs:147-156). Zero-initialise, then tmc_opts_default(). */
 typedef struct {
-  int32_t eigen_group;      /* 0 = SignGroup (default), 1 = KMeansGroup (unsupported)   Options.hs:172 */
-  int32_t num_eigen;        /* default 1                                                Options.hs:173 */
+  int32_t eigen_group;      /* 0 = SignGroup (default), 1 = KMeansGroup (2-means on eigenvectors 2..num_eigen+1; per-node
+                               host recursion over the GPU exports, single rank)        Options.hs:172 */
+  int32_t num_eigen;        /* default 1; only read by KMeansGroup                      Options.hs:173 */
   double  min_modularity;   /* default 0.0; split iff Q > min_modularity                Options.hs:178 */
   int32_t min_size;         /* make-tree always passes 1 (Nothing)                      Cluster.hs:152 */
   int32_t normalize;        /* 0 from make-tree (tf-idf done by caller), 1 = idf inside Cluster.hs:150 */
-  int32_t num_runs;         /* permutation test, 0 = off (unsupported > 0)              Options.hs:174 */
-  uint64_t seed;            /* start-vector seed */
+  int32_t num_runs;         /* permutation test of every split, 0 = off (fills tmc_tree.p_val; single rank)  Options.hs:174 */
+  uint64_t seed;            /* start-vector seed; also seeds the label shuffles of the permutation test */
   /* engine knobs (no reference counterpart) */
   double  tol;              /* Lanczos residual tolerance ||M u - theta u|| <= tol*theta; default 1e-10 */
   int32_t max_lanczos;      /* Krylov dimension before an explicit restart; default 320 */
@@ -97,6 +98,7 @@ typedef struct {
   double  spmv_alg_bytes;     /* algorithmic bytes of those SpMV pairs (BASELINE.md section 4 formula, b_v as stored) */
   int32_t value_bytes;        /* b_v: 8 = B kept as fp64; 2 = raw counts kept as uint16 + diagonal factors; 0 = all-ones matrix */
   int32_t pad_;
+  const double*  p_val;       /* n_nodes; _pVal of the split (MakeTree/Types.hs:124-130): NaN = Nothing (leaf, or num_runs = 0) */
 } tmc_tree;
 
 /* Device-resident matrix handle: B = row-L2-normalised (tf-idf) CSR kept in HBM. */
@@ -136,7 +138,15 @@ void tmc_cache_clear(void);
 /* == hierarchicalSpectralCluster ... (Left mat)  (Cluster.hs:147-156): the whole tree. */
 int  tmc_make_tree(const tmc_csr* b2, const tmc_opts* opts, tmc_tree** out);
 int  tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out);
+/* == HSD.hierarchicalSpectralCluster ... (Left (sparseToHMat mat))  (--dense, Cluster.hs:157-167): `mat` is the dense
+ * cells x features matrix, row-major.  Zeros carry no weight in any product of the path, so the tree is the one the sparse
+ * call builds from the non-zero entries; negative entries are rejected like everywhere else (TMC_ERR_NEGATIVE). */
+int  tmc_make_tree_dense(const double* mat, int64_t n_rows, int64_t n_cols, const tmc_opts* opts, tmc_tree** out);
 void tmc_tree_free(tmc_tree*);
+/* == the `runs` argument of hierarchicalSpectralCluster (--numRuns, Options.hs:174) on a finished tree: for every split the
+ * labels are shuffled num_runs times and Q recomputed on the GPU; p_out[node] = #{Q_shuffled >= Q_observed} / num_runs,
+ * NaN for leaves.  tmc_make_tree* with opts.num_runs > 0 call this and store the result in tmc_tree.p_val. */
+int  tmc_permutation_test(tmc_matrix* b, const tmc_tree* tree, int num_runs, uint64_t seed, double* p_out);
 
 /* Fine-grained exports so every row of SURVEY.md 8(a) is individually parity-testable.
  * `rows` (n_sel original row ids, ascending) selects the node S; NULL = all rows. */

@@ -76,11 +76,9 @@ template <class A> using ClusteringTree = Tree<A>;
 
 // hierarchicalSpectralCluster eigenGroup normFlag numEigen minSize minMod runs items (Left mat)
 // (std::nullopt = Haskell Nothing).  Children order [label 0, label 1]; every vertex carries its items and Q.
-template <class A>
-ClusteringTree<A> hierarchicalSpectralCluster(EigenGroup eigenGroup, bool normFlag, std::optional<int> numEigen, std::optional<int> minSize,
-                                              std::optional<Q> minMod, std::optional<int> runs, const std::vector<A>& items,
-                                              const SpMatrix& mat) {
-  if ((int64_t)items.size() != mat.nrows) throw Error(TMC_ERR_INVALID, "items and matrix rows differ");
+namespace detail {
+inline tmc_opts opts(EigenGroup eigenGroup, bool normFlag, std::optional<int> numEigen, std::optional<int> minSize, std::optional<Q> minMod,
+                     std::optional<int> runs) {
   tmc_opts o; tmc_opts_default(&o);
   o.eigen_group = eigenGroup == EigenGroup::SignGroup ? 0 : 1;
   o.normalize = normFlag ? 1 : 0;
@@ -88,9 +86,38 @@ ClusteringTree<A> hierarchicalSpectralCluster(EigenGroup eigenGroup, bool normFl
   o.min_size = minSize.value_or(1);
   o.min_modularity = minMod ? minMod->unQ : 0.0;
   o.num_runs = runs.value_or(0);
+  return o;
+}
+template <class A> ClusteringTree<A> rebuild(tmc_tree* t, const std::vector<A>& items);
+}  // namespace detail
+
+// row-major dense cells x features matrix (the hmatrix `Matrix Double` of the --dense path, Cluster.hs:157-167)
+struct DenseMatrix { int64_t nrows = 0, ncols = 0; std::vector<double> values; };
+
+template <class A>
+ClusteringTree<A> hierarchicalSpectralCluster(EigenGroup eigenGroup, bool normFlag, std::optional<int> numEigen, std::optional<int> minSize,
+                                              std::optional<Q> minMod, std::optional<int> runs, const std::vector<A>& items,
+                                              const SpMatrix& mat) {
+  if ((int64_t)items.size() != mat.nrows) throw Error(TMC_ERR_INVALID, "items and matrix rows differ");
+  tmc_opts o = detail::opts(eigenGroup, normFlag, numEigen, minSize, minMod, runs);
   tmc_csr v = mat.view();
   tmc_tree* t = nullptr;
   check(tmc_make_tree(&v, &o, &t));
+  return detail::rebuild<A>(t, items);
+}
+// HSD.hierarchicalSpectralCluster (Math.Clustering.Hierarchical.Spectral.Dense), same arguments on a dense matrix
+template <class A>
+ClusteringTree<A> hierarchicalSpectralCluster(EigenGroup eigenGroup, bool normFlag, std::optional<int> numEigen, std::optional<int> minSize,
+                                              std::optional<Q> minMod, std::optional<int> runs, const std::vector<A>& items,
+                                              const DenseMatrix& mat) {
+  if ((int64_t)items.size() != mat.nrows) throw Error(TMC_ERR_INVALID, "items and matrix rows differ");
+  tmc_opts o = detail::opts(eigenGroup, normFlag, numEigen, minSize, minMod, runs);
+  tmc_tree* t = nullptr;
+  check(tmc_make_tree_dense(mat.values.data(), mat.nrows, mat.ncols, &o, &t));
+  return detail::rebuild<A>(t, items);
+}
+
+template <class A> ClusteringTree<A> detail::rebuild(tmc_tree* t, const std::vector<A>& items) {
   std::unique_ptr<tmc_tree, void (*)(tmc_tree*)> guard(t, tmc_tree_free);
   // rebuild the Data.Tree from the flat pre-order arrays (iteratively: trees can be deep)
   std::vector<Tree<A>> built(t->n_nodes);
@@ -98,6 +125,7 @@ ClusteringTree<A> hierarchicalSpectralCluster(EigenGroup eigenGroup, bool normFl
     Tree<A>& n = built[i];
     for (int64_t k = t->item_begin[i]; k < t->item_end[i]; ++k) n.rootLabel._clusteringItems.push_back(items[t->perm[k]]);
     n.rootLabel._ngMod = Q{t->q[i]};
+    if (t->p_val[i] == t->p_val[i]) n.rootLabel._pVal = t->p_val[i];      // NaN = Nothing
     if (t->left[i] >= 0) { n.subForest.push_back(std::move(built[t->left[i]])); n.subForest.push_back(std::move(built[t->right[i]])); }
   }
   return std::move(built[0]);

@@ -158,6 +158,92 @@ def get_b_modularity(labels: np.ndarray, b: sp.csr_matrix) -> float:
     return float(q)
 
 
+# ---- A6 (KMeansGroup): spectralClusterK (spectral-clustering; flag help text Options.hs:172-173) -------------------------
+def kmeans2_labels(pts: np.ndarray) -> np.ndarray:
+    """2-means on the rows of `pts` (n x e).  The reference's k-means is un-vendored and its "starting points are
+    arbitrary" (Options.hs:172), so the convention is fixed here (and in csrc/tmc_variants.cuh): Lloyd from the rows with the
+    smallest / largest first coordinate, ties to cluster 1, at most 100 rounds, label 1 = the cluster started from the largest."""
+    pts = np.asarray(pts, dtype=np.float64).reshape(len(pts), -1)
+    n = pts.shape[0]
+    lo, hi = int(np.argmin(pts[:, 0])), int(np.argmax(pts[:, 0]))
+    if pts[lo, 0] == pts[hi, 0]:
+        return np.ones(n, dtype=np.int8)
+    c0, c1 = pts[lo].copy(), pts[hi].copy()
+    lab = np.zeros(n, dtype=np.int8)
+    for rnd in range(100):
+        d0 = ((pts - c0) ** 2).sum(axis=1)
+        d1 = ((pts - c1) ** 2).sum(axis=1)
+        new = (d1 <= d0).astype(np.int8)
+        changed = rnd == 0 or bool(np.any(new != lab))
+        lab = new
+        n1 = int(lab.sum())
+        if not changed or n1 == 0 or n1 == n:
+            break
+        c0, c1 = pts[lab == 0].mean(axis=0), pts[lab == 1].mean(axis=0)
+    return lab
+
+
+def kmeans_num_eigen(num_eigen: int, m: int, n_cols: int) -> int:
+    """Eigenvectors a node of m cells uses: min(num_eigen, m/4 - 1, n_cols/4 - 1), at least 1 (the engine's rule)."""
+    e = max(1, min(int(num_eigen), m // 4 - 1))
+    if num_eigen > 1:
+        e = max(1, min(e, n_cols // 4 - 1))
+    return e
+
+
+def spectral_cluster_k(b: sp.csr_matrix, num_eigen: int = 1):
+    """labels from 2-means on the rows of singular vectors 2..e+1 of C (`spectral 2 e`).  Returns (labels, coords, theta2)."""
+    m = b.shape[0]
+    d = b_to_d(b)
+    c = bd_to_c(b, d)
+    e = kmeans_num_eigen(num_eigen, m, b.shape[1])
+    g = (c @ c.T).toarray()
+    w, v = np.linalg.eigh(g)
+    coords = v[:, ::-1][:, 1:e + 1]
+    return kmeans2_labels(coords), coords, float(w[-2])
+
+
+# ---- A10: the `runs` argument (--numRuns, Options.hs:174; _pVal, MakeTree/Types.hs:124-130) ---------------------------------
+_M64 = (1 << 64) - 1
+
+
+class SplitMix64:
+    def __init__(self, seed):
+        self.s = seed & _M64
+
+    def next(self):
+        self.s = (self.s + 0x9E3779B97F4A7C15) & _M64
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+        return z ^ (z >> 31)
+
+
+def shuffle_labels(lab: np.ndarray, rng: SplitMix64):
+    """In-place Fisher-Yates, i = n-1 .. 1, j = next() mod (i+1)."""
+    for i in range(len(lab) - 1, 0, -1):
+        j = rng.next() % (i + 1)
+        lab[i], lab[j] = lab[j], lab[i]
+
+
+DEFAULT_SEED = 0x2545F4914F6CDD1D       # tmc_opts_default
+
+
+def permutation_p_value(labels: np.ndarray, b: sp.csr_matrix, rows: np.ndarray, num_runs: int, seed: int = DEFAULT_SEED) -> float:
+    """Empirical p of one split: the node's labels (ascending row order) are shuffled num_runs times and Q recomputed;
+    p = #{Q_shuffled >= Q_observed - 1e-12} / num_runs.  The stream is seeded from (seed, smallest row id, node size) so
+    that it does not depend on how a tree numbers the node ([UPSTREAM-RECALL]: the upstream body is un-vendored)."""
+    q_obs = get_b_modularity(labels, b)
+    rng = SplitMix64(seed ^ ((int(rows[0]) * 0x9E3779B97F4A7C15 + len(rows)) & _M64))
+    lab = np.array(labels, dtype=np.int8)
+    ge = 0
+    for _ in range(num_runs):
+        shuffle_labels(lab, rng)
+        if get_b_modularity(lab, b) >= q_obs - 1e-12:
+            ge += 1
+    return ge / num_runs
+
+
 # ---- A0: hierarchicalSpectralCluster (call site Cluster.hs:147-156,169) ----------
 @dataclass
 class OracleTree:
@@ -170,6 +256,7 @@ class OracleTree:
     margin: list = field(default_factory=list)     # min |u2_i| / max |u2_i|  (sign margin)
     items: list = field(default_factory=list)      # ascending original row ids of every vertex
     u2: list = field(default_factory=list)         # optional per-node u2 (only if keep_u2)
+    p_val: list = field(default_factory=list)      # permutation p-value of the vertex's split (None without num_runs / for leaves)
 
     @property
     def n_nodes(self):
@@ -183,7 +270,8 @@ class OracleTree:
 
 
 def hierarchical_spectral_cluster(b2, min_modularity=0.0, min_size=1, normalize=False,
-                                  keep_u2=False, max_nodes=None) -> OracleTree:
+                                  keep_u2=False, max_nodes=None, eigen_group="SignGroup", num_eigen=1,
+                                  num_runs=0, seed=DEFAULT_SEED) -> OracleTree:
     """Divisive recursion `go items B` (Appendix B of SURVEY.md).
 
     `b2` is what `hSpecClust` hands over as `Left mat`: already tf-idf scaled by
@@ -202,13 +290,18 @@ def hierarchical_spectral_cluster(b2, min_modularity=0.0, min_size=1, normalize=
         for lst in (tree.left, tree.right):
             lst.append(-1)
         tree.items.append(rows)
+        tree.p_val.append(None)
         b = b0[rows]
         m = rows.size
         if m <= 1:
             tree.q.append(0.0); tree.theta.append(0.0); tree.gap.append(0.0)
             tree.margin.append(0.0); tree.u2.append(None)
             return idx
-        labels, u2, th2, gap, _ = spectral_cluster(b)
+        if eigen_group == "KMeansGroup":
+            labels, coords, th2 = spectral_cluster_k(b, num_eigen)
+            u2, gap = coords[:, 0], 0.0
+        else:
+            labels, u2, th2, gap, _ = spectral_cluster(b)
         q = get_b_modularity(labels, b)
         tree.q.append(q); tree.theta.append(th2); tree.gap.append(gap)
         au = np.abs(u2)
@@ -220,6 +313,8 @@ def hierarchical_spectral_cluster(b2, min_modularity=0.0, min_size=1, normalize=
         if ok and li.size >= max(1, min_size) and ri.size >= max(1, min_size) and m > 1:
             if max_nodes is not None and tree.n_nodes >= max_nodes:
                 return idx
+            if num_runs:
+                tree.p_val[idx] = permutation_p_value(labels, b, rows, num_runs, seed)
             tree.left[idx] = go(li)
             tree.right[idx] = go(ri)
         return idx

@@ -237,12 +237,12 @@ def test_edge_cases_and_errors():
     with pytest.raises(T.TmcError) as ei:
         T.hierarchical_spectral_cluster(neg)
     assert ei.value.code == _lib.ERR_NEGATIVE
+    # the non-default variants (KMeansGroup, num_runs, dense) have their own file: test_gpu_variants.py
+    db = T.DeviceB.from_host(two)
     with pytest.raises(T.TmcError) as ei:
-        T.hierarchical_spectral_cluster(two, eigen_group="KMeansGroup")
+        T.second_left(db, eigen_group="KMeansGroup")          # the per-node exports know the default variant only
     assert ei.value.code == _lib.ERR_UNSUPPORTED
-    with pytest.raises(T.TmcError) as ei:
-        T.hierarchical_spectral_cluster(two, num_runs=10)
-    assert ei.value.code == _lib.ERR_UNSUPPORTED
+    db.free()
 
 
 def test_make_tree_outputs_end_to_end(tmp_path, tiny):

@@ -1,0 +1,133 @@
+"""the non-default variants of the engine call — KMeansGroup / --num-eigen, the --numRuns
+permutation test and --dense (Options.hs:172-174, Cluster.hs:157-167) — through the C ABI against the oracle's restatement
+of the same conventions (oracle/tmc_oracle.py: kmeans2_labels, permutation_p_value).  Upstream bodies are un-vendored, so
+like the rest of the numeric path this is parity with the restated algorithm ("parity unpinned")."""
+import numpy as np
+import scipy.sparse as sp
+import pytest
+
+import tmc_oracle as O
+import too_many_cells_b200 as T
+from too_many_cells_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def same_tree(tree, ot):
+    ca = O.canonical_tree(tree.left, tree.right, tree.items)
+    cb = O.canonical_tree(ot.left, ot.right, lambda i: ot.items[i])
+    return ca == cb
+
+
+def by_items(tree_items, n_nodes, values):
+    return {frozenset(int(x) for x in tree_items(i)): values[i] for i in range(n_nodes)}
+
+
+def assert_q_match(tree, ot, tol=1e-9):
+    qa = by_items(tree.items, tree.n_nodes, tree.q)
+    qb = by_items(lambda i: ot.items[i], ot.n_nodes, ot.q)
+    assert qa.keys() == qb.keys()
+    for k, v in qb.items():
+        if len(k) > 1:
+            assert abs(qa[k] - v) <= tol * max(1.0, abs(v)), (len(k), qa[k], v)
+
+
+def test_dense_call_builds_the_sparse_tree(golden_tiny):
+    a, _ = golden_tiny
+    a = a[:200]
+    ts = T.hierarchical_spectral_cluster(a, normalize=True)
+    td = T.hierarchical_spectral_cluster(np.asarray(a.todense()), normalize=True)        # tmc_make_tree_dense
+    assert np.array_equal(ts.left, td.left) and np.array_equal(ts.perm, td.perm) and np.array_equal(ts.q, td.q)
+    assert same_tree(td, O.hierarchical_spectral_cluster(a, normalize=True))
+    cl, th = T.h_spec_clust(T.tfidf_scale_sparse_mat(a), [f"c{i}" for i in range(a.shape[0])], dense=True)   # hSpecCommand True
+    assert th.leaf_sets() == ts.leaf_sets() and len(cl) == a.shape[0]
+    with pytest.raises(T.TmcError) as ei:
+        T.hierarchical_spectral_cluster(np.array([[1.0, -2.0], [1.0, 1.0]]))
+    assert ei.value.code == _lib.ERR_NEGATIVE
+
+
+@pytest.mark.parametrize("num_eigen", [1, 3])
+def test_kmeans_group_vs_oracle(golden_tiny, num_eigen):
+    a, _ = golden_tiny
+    t = T.hierarchical_spectral_cluster(a, eigen_group="KMeansGroup", num_eigen=num_eigen, normalize=True)
+    ot = O.hierarchical_spectral_cluster(a, normalize=True, eigen_group="KMeansGroup", num_eigen=num_eigen)
+    assert t.n_nodes == ot.n_nodes and t.leaf_sets() == ot.leaf_sets()
+    assert same_tree(t, ot)
+    assert_q_match(t, ot)
+    for i in t.leaves():                                      # stable splits: leaves ascend in original row id
+        assert np.all(np.diff(t.items(i)) > 0)
+    assert np.all(np.isnan(t.p_val))                          # no test asked for: every _pVal is Nothing
+
+
+def test_kmeans_group_on_device_matrix_and_flags(golden_tiny):
+    a, _ = golden_tiny
+    a = a[:150]
+    db = T.DeviceB.from_host(a, normalize=True)
+    t = T.hierarchical_spectral_cluster(db, eigen_group="KMeansGroup")
+    ot = O.hierarchical_spectral_cluster(a, normalize=True, eigen_group="KMeansGroup")
+    assert same_tree(t, ot)
+    t5 = T.hierarchical_spectral_cluster(db, eigen_group="KMeansGroup", min_size=5, min_modularity=0.01)
+    o5 = O.hierarchical_spectral_cluster(a, normalize=True, eigen_group="KMeansGroup", min_size=5, min_modularity=0.01)
+    assert same_tree(t5, o5)
+    with pytest.raises(T.TmcError) as ei:                     # several eigenvectors need the host matrix (C_S is assembled per node)
+        T.hierarchical_spectral_cluster(db, eigen_group="KMeansGroup", num_eigen=2)
+    assert ei.value.code == _lib.ERR_UNSUPPORTED
+    db.free()
+    two = sp.csr_matrix(np.array([[1.0, 2.0, 0.0], [0.0, 1.0, 1.0]]))
+    t = T.hierarchical_spectral_cluster(two, eigen_group="KMeansGroup")
+    assert t.n_nodes == 1 and abs(t.q[0] + 0.5) < 1e-12
+    one = sp.csr_matrix(np.array([[1.0, 2.0, 0.0]]))
+    assert T.hierarchical_spectral_cluster(one, eigen_group="KMeansGroup", num_runs=3).n_nodes == 1
+
+
+def check_p_values(t, ot):
+    pa = by_items(t.items, t.n_nodes, t.p_val)
+    pb = by_items(lambda i: ot.items[i], ot.n_nodes, ot.p_val)
+    assert pa.keys() == pb.keys()
+    n_inner = 0
+    for k, v in pb.items():
+        if v is None:
+            assert np.isnan(pa[k])
+        else:
+            n_inner += 1
+            assert pa[k] == v, (len(k), pa[k], v)
+    return n_inner
+
+
+def test_permutation_test_vs_oracle(golden_tiny):
+    a, _ = golden_tiny
+    t = T.hierarchical_spectral_cluster(a, normalize=True, num_runs=20)
+    ot = O.hierarchical_spectral_cluster(a, normalize=True, num_runs=20)
+    assert same_tree(t, ot)
+    assert check_p_values(t, ot) == (t.n_nodes - 1) // 2
+    # a saturated tree splits noise too: p-values away from 0, other seed
+    s = a[:60]
+    ts = T.hierarchical_spectral_cluster(s, normalize=True, num_runs=10, min_modularity=-1.0, seed=7)
+    os_ = O.hierarchical_spectral_cluster(s, normalize=True, num_runs=10, min_modularity=-1.0, seed=7)
+    assert same_tree(ts, os_) and len(ts.leaves()) == 60
+    check_p_values(ts, os_)
+    assert np.nanmax(ts.p_val) > 0.0
+    # the export on a finished tree gives the same numbers as the in-call test
+    db = T.DeviceB.from_host(a, normalize=True)
+    t0 = T.hierarchical_spectral_cluster(db)
+    assert np.all(np.isnan(t0.p_val))
+    p = T.permutation_test(db, t0, 20)
+    assert np.array_equal(np.isnan(p), np.isnan(t.p_val)) and np.array_equal(p[~np.isnan(p)], t.p_val[~np.isnan(t.p_val)])
+    db.free()
+
+
+def test_p_values_reach_the_output_files(golden_tiny):
+    a, _ = golden_tiny
+    a = a[:120]
+    names = [f"CELL{i:04d}-1" for i in range(a.shape[0])]
+    t = T.hierarchical_spectral_cluster(a, normalize=True, num_runs=5)
+    lines = T.tree_io.node_info_csv(t).splitlines()
+    assert lines[0] == "node,size,proportion,modularity,significance,composition,subtree"
+    for i, ln in enumerate(lines[1:]):
+        sig = ln.split(",")[4]
+        assert (sig == "") == bool(t.left[i] < 0)
+        if sig:
+            assert sig == T.tree_io.haskell_show_double(float(t.p_val[i]))
+    back, _ = T.tree_io.parse_cluster_tree_json(T.tree_io.cluster_tree_json(t, names, significance=True))
+    inner = t.left >= 0
+    assert np.array_equal(back.p_val[inner], t.p_val[inner]) and np.all(np.isnan(back.p_val[~inner]))

@@ -34,7 +34,7 @@ def test_opts_default_and_layout():
     o = T.make_opts()
     assert o.eigen_group == 0 and o.num_eigen == 1 and o.min_modularity == 0.0 and o.min_size == 1
     assert o.normalize == 0 and o.num_runs == 0 and o.tol == 1e-10 and o.max_lanczos == 320 and o.device == -1
-    assert C.sizeof(_lib.Opts) == 96 and C.sizeof(_lib.Tree) == 144      # static_assert-ed in tmc_engine.cu
+    assert C.sizeof(_lib.Opts) == 96 and C.sizeof(_lib.Tree) == 152      # static_assert-ed in tmc_engine.cu
 
 
 def test_no_cpu_fallback_without_device():
@@ -155,3 +155,227 @@ def test_panel_cells_as_denormal_doubles_are_exact(tmp_path):
                    check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "0"
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# host logic of the non-default variants (csrc/tmc_variants.cuh), compiled against oracle-backed stand-ins of
+# the six exports it composes (tests/helpers/variants_host.cpp).  The same trees / p-values come out of the GPU library in
+# tests/test_gpu_variants.py.
+@pytest.fixture(scope="module")
+def variants_host(tmp_path_factory):
+    import scipy.sparse as sp
+    import tmc_oracle as O
+    out = tmp_path_factory.mktemp("vh") / "libvh.so"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", os.path.join(ROOT, "tests", "helpers", "variants_host.cpp"),
+                    "-o", str(out)], check=True)
+    lib = C.CDLL(str(out))
+    state = {}
+
+    def csr_of(ap):
+        a = ap.contents
+        n, nnz = int(a.n_rows), int(a.nnz)
+        ip = np.ctypeslib.as_array(C.cast(a.row_ptr, C.POINTER(C.c_int64)), shape=(n + 1,)).copy()
+        ix = np.ctypeslib.as_array(C.cast(a.col_idx, C.POINTER(C.c_int32)), shape=(max(nnz, 1),))[:nnz].copy()
+        v = np.ctypeslib.as_array(C.cast(a.val, C.POINTER(C.c_double)), shape=(max(nnz, 1),))[:nnz].copy()
+        return sp.csr_matrix((v, ix, ip), shape=(n, int(a.n_cols)))
+
+    def rows_of(p, n):
+        return np.ctypeslib.as_array(p, shape=(n,)).copy()
+
+    I64P, U8P, F64P = C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.POINTER(C.c_double)
+
+    @C.CFUNCTYPE(C.c_int, I64P, C.c_int64, U8P, F64P)
+    def cb_mod(rows, n, lab, q):
+        q[0] = O.get_b_modularity(np.ctypeslib.as_array(lab, shape=(n,)).astype(np.int8), state["b"][rows_of(rows, n)])
+        return 0
+
+    @C.CFUNCTYPE(C.c_int, I64P, C.c_int64, F64P, F64P)
+    def cb_sl(rows, n, u2, th):
+        _, u, t2, _, _ = O.spectral_cluster(state["b"][rows_of(rows, n)])
+        np.ctypeslib.as_array(u2, shape=(n,))[:] = -u if state.get("flip") else u        # the sign of u2 is arbitrary
+        th[0] = t2
+        return 0
+
+    @C.CFUNCTYPE(C.c_int, I64P, C.c_int64, F64P)
+    def cb_deg(rows, n, d):
+        np.ctypeslib.as_array(d, shape=(n,))[:] = O.b_to_d(state["b"][rows_of(rows, n)])
+        return 0
+
+    @C.CFUNCTYPE(C.c_int, C.POINTER(_lib.Csr), C.c_int, C.c_int, F64P, F64P)
+    def cb_ls(ap, normalize, n_vec, u, sig):
+        c = csr_of(ap)
+        assert normalize == 0
+        w, v = np.linalg.eigh((c @ c.T).toarray())
+        top = v[:, ::-1][:, :n_vec]
+        if state.get("flip"):
+            top = -top
+        np.ctypeslib.as_array(u, shape=(c.shape[0] * n_vec,))[:] = top.ravel()
+        np.ctypeslib.as_array(sig, shape=(n_vec,))[:] = np.sqrt(np.maximum(w[::-1][:n_vec], 0))
+        return 0
+
+    @C.CFUNCTYPE(C.c_int, C.POINTER(_lib.Csr), F64P)
+    def cb_tfidf(ap, v):
+        a = csr_of(ap)
+        np.ctypeslib.as_array(v, shape=(a.nnz,))[:] = O.b1_to_b2(a).data
+        return 0
+
+    @C.CFUNCTYPE(C.c_int, C.POINTER(_lib.Csr), F64P)
+    def cb_l2(ap, v):
+        a = csr_of(ap)
+        np.ctypeslib.as_array(v, shape=(a.nnz,))[:] = O.b2_to_b(a).data
+        return 0
+
+    lib.vh_set_callbacks(cb_mod, cb_sl, cb_deg, cb_ls, cb_tfidf, cb_l2)
+    lib.vh_last_error.restype = C.c_char_p
+    lib.vh_splitmix.restype = C.c_uint64
+    lib.vh_splitmix.argtypes = [C.c_uint64, C.c_int]
+    lib.vh_dense_to_csr.restype = C.c_int64
+    lib._keep = (cb_mod, cb_sl, cb_deg, cb_ls, cb_tfidf, cb_l2)
+
+    def kmeans_tree(a, normalize=True, **kw):
+        """Runs vh_kmeans_tree on host CSR `a`; returns a T.ClusteringTree."""
+        state["b"] = O.b2_to_b(O.b1_to_b2(a) if normalize else a)
+        state["flip"] = kw.pop("flip", False)
+        h = T.spectral.HostCsr(a)
+        o = T.make_opts(normalize=normalize, eigen_group="KMeansGroup", **kw)
+        tp = C.POINTER(_lib.Tree)()
+        st = lib.vh_kmeans_tree(C.byref(h.c), C.byref(o), C.byref(tp))
+        assert st == 0, lib.vh_last_error()
+        t = tp.contents
+        n, m = int(t.n_nodes), int(t.n_rows)
+        g = lambda ptr, k, dt: np.ctypeslib.as_array(ptr, shape=(k,)).astype(dt, copy=True)
+        tree = T.ClusteringTree(left=g(t.left, n, np.int64), right=g(t.right, n, np.int64), parent=g(t.parent, n, np.int64),
+                                q=g(t.q, n, np.float64), theta=g(t.theta, n, np.float64), iters=g(t.iters, n, np.int32),
+                                item_begin=g(t.item_begin, n, np.int64), item_end=g(t.item_end, n, np.int64),
+                                perm=g(t.perm, m, np.int64), stats={}, p_val=g(t.p_val, n, np.float64))
+        lib.vh_tree_free(tp)
+        return tree
+
+    def permutation_test(a, tree, num_runs, seed, normalize=True):
+        state["b"] = O.b2_to_b(O.b1_to_b2(a) if normalize else a)
+        t, keep = T.spectral._tree_to_c(tree)
+        p = np.empty(tree.n_nodes)
+        st = lib.vh_permutation_test(C.c_int64(a.shape[0]), C.byref(t), int(num_runs), C.c_uint64(seed), p.ctypes.data_as(F64P))
+        assert st == 0, lib.vh_last_error()
+        return p
+
+    lib.kmeans_tree, lib.permutation_test = kmeans_tree, permutation_test
+    return lib
+
+
+def _same_tree(tree, ot):
+    import tmc_oracle as O
+    return O.canonical_tree(tree.left, tree.right, tree.items) == O.canonical_tree(ot.left, ot.right, lambda i: ot.items[i])
+
+
+def _p_by_items(items_of, n, p):
+    return {frozenset(int(x) for x in items_of(i)): p[i] for i in range(n)}
+
+
+def test_variants_splitmix_and_kmeans_match_the_oracle(variants_host):
+    import tmc_oracle as O
+    r = O.SplitMix64(12345)
+    ref = [r.next() for _ in range(5)]
+    assert [variants_host.vh_splitmix(12345, k) for k in range(5)] == ref
+    r = O.SplitMix64(1234567)                                # known-answer vectors of Vigna's splitmix64.c for seed 1234567
+    assert [r.next() for _ in range(3)] == [6457827717110365317, 3203168211198807973, 9817491932198370423]
+    assert variants_host.vh_splitmix(1234567, 2) == 9817491932198370423
+    rng = np.random.default_rng(0)
+    for n, e in [(2, 1), (3, 1), (50, 1), (64, 3), (7, 2)]:
+        pts = rng.standard_normal((n, e))
+        if n == 50:
+            pts[:25] += 4.0
+        lab = np.zeros(n, dtype=np.uint8)
+        variants_host.vh_kmeans2(pts.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(n), e, lab.ctypes.data_as(C.POINTER(C.c_uint8)))
+        assert np.array_equal(lab, O.kmeans2_labels(pts).astype(np.uint8))
+        assert 0 < lab.sum() < n
+    same = np.ones((5, 2))
+    lab = np.zeros(5, dtype=np.uint8)
+    variants_host.vh_kmeans2(same.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(5), 2, lab.ctypes.data_as(C.POINTER(C.c_uint8)))
+    assert lab.sum() == 5 and O.kmeans2_labels(same).sum() == 5       # no spread: one cluster
+
+
+def test_variants_dense_to_csr(variants_host):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(1)
+    d = rng.random((7, 9)) * (rng.random((7, 9)) < 0.4)
+    d[3] = 0.0
+    rp = np.zeros(8, dtype=np.int64); ci = np.zeros(63, dtype=np.int32); v = np.zeros(63)
+    nnz = variants_host.vh_dense_to_csr(d.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(7), C.c_int64(9),
+                                        rp.ctypes.data_as(C.POINTER(C.c_int64)), ci.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        v.ctypes.data_as(C.POINTER(C.c_double)))
+    ref = sp.csr_matrix(d)
+    assert nnz == ref.nnz and np.array_equal(rp, ref.indptr) and np.array_equal(ci[:nnz], ref.indices) and np.array_equal(v[:nnz], ref.data)
+
+
+@pytest.mark.parametrize("num_eigen", [1, 3])
+def test_variants_kmeans_tree_layout_and_oracle(variants_host, golden_tiny, num_eigen):
+    import tmc_oracle as O
+    a, _ = golden_tiny
+    a = a[:240]
+    ot = O.hierarchical_spectral_cluster(a, normalize=True, eigen_group="KMeansGroup", num_eigen=num_eigen)
+    for flip in (False, True):                                # the tree must not depend on the sign the solver returns
+        t = variants_host.kmeans_tree(a, num_eigen=num_eigen, flip=flip)
+        assert t.n_nodes == ot.n_nodes and _same_tree(t, ot)
+        # flat pre-order contract of tmc_tree (include/tmc.h)
+        assert t.parent[0] == -1 and t.item_begin[0] == 0 and t.item_end[0] == a.shape[0]
+        assert sorted(t.perm.tolist()) == list(range(a.shape[0]))
+        for i in range(t.n_nodes):
+            if t.left[i] >= 0:
+                l, r = t.left[i], t.right[i]
+                assert l == i + 1 and t.parent[l] == i and t.parent[r] == i
+                assert t.item_begin[l] == t.item_begin[i] and t.item_end[l] == t.item_begin[r] and t.item_end[r] == t.item_end[i]
+            else:
+                assert np.all(np.diff(t.items(i)) > 0)
+        qa, qb = _p_by_items(t.items, t.n_nodes, t.q), _p_by_items(lambda i: ot.items[i], ot.n_nodes, ot.q)
+        assert all(abs(qa[k] - qb[k]) < 1e-12 for k in qb)
+    assert ot.n_nodes > 5
+    t5 = variants_host.kmeans_tree(a, num_eigen=num_eigen, min_size=7, min_modularity=0.02)
+    o5 = O.hierarchical_spectral_cluster(a, normalize=True, eigen_group="KMeansGroup", num_eigen=num_eigen, min_size=7, min_modularity=0.02)
+    assert _same_tree(t5, o5) and min(len(t5.items(i)) for i in t5.leaves()) >= 7
+
+
+def test_variants_permutation_p_values_match_the_oracle(variants_host, golden_tiny):
+    import tmc_oracle as O
+    a, _ = golden_tiny
+    a = a[:90]
+    for kw in (dict(), dict(min_modularity=-1.0)):
+        ot = O.hierarchical_spectral_cluster(a, normalize=True, eigen_group="KMeansGroup", num_runs=12, seed=99, **kw)
+        t = variants_host.kmeans_tree(a, num_runs=12, seed=99, **kw)
+        assert _same_tree(t, ot)
+        pa, pb = _p_by_items(t.items, t.n_nodes, t.p_val), _p_by_items(lambda i: ot.items[i], ot.n_nodes, ot.p_val)
+        for k, v in pb.items():
+            assert (np.isnan(pa[k]) and v is None) or pa[k] == v
+    assert np.nanmax(t.p_val) > 0                            # the saturated tree splits noise
+    # on a finished SignGroup tree, with children deliberately swapped: p-values belong to the split, not to its numbering
+    os_ = O.hierarchical_spectral_cluster(a, normalize=True, num_runs=8, seed=5)
+    left = [os_.right[i] if os_.left[i] >= 0 else -1 for i in range(os_.n_nodes)]
+    right = [os_.left[i] if os_.left[i] >= 0 else -1 for i in range(os_.n_nodes)]
+    # re-number pre-order with the swapped children
+    order, st = [], [0]
+    while st:
+        u = st.pop(); order.append(u)
+        if left[u] >= 0:
+            st.append(right[u]); st.append(left[u])
+    new_id = {u: i for i, u in enumerate(order)}
+    n = len(order)
+    L = np.full(n, -1, dtype=np.int64); R = np.full(n, -1, dtype=np.int64); P = np.full(n, -1, dtype=np.int64)
+    ib = np.zeros(n, dtype=np.int64); ie = np.zeros(n, dtype=np.int64); perm = []
+    for u in order:
+        i = new_id[u]
+        ib[i] = len(perm)
+        if left[u] >= 0:
+            L[i], R[i] = new_id[left[u]], new_id[right[u]]; P[L[i]] = P[R[i]] = i
+        else:
+            perm.extend(int(x) for x in os_.items[u])
+    for u in reversed(order):
+        i = new_id[u]
+        ie[i] = ib[i] + len(os_.items[u])
+    tree = T.ClusteringTree(left=L, right=R, parent=P, q=np.array([os_.q[u] for u in order]), theta=np.zeros(n), iters=np.zeros(n, np.int32),
+                            item_begin=ib, item_end=ie, perm=np.array(perm, dtype=np.int64), stats={})
+    p = variants_host.permutation_test(a, tree, 8, 5)
+    for u in order:
+        if os_.p_val[u] is None:
+            assert np.isnan(p[new_id[u]])
+        else:
+            assert p[new_id[u]] == os_.p_val[u]

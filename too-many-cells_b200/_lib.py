@@ -45,7 +45,7 @@ class Tree(C.Structure):
                 ("item_begin", C.POINTER(C.c_int64)), ("item_end", C.POINTER(C.c_int64)), ("perm", C.POINTER(C.c_int64)),
                 ("n_sweeps", C.c_int64), ("spmv_pairs_nnz", C.c_int64), ("kernel_launches", C.c_int64),
                 ("engine_ms", C.c_double), ("spmv_ms", C.c_double), ("spmv_alg_bytes", C.c_double),
-                ("value_bytes", C.c_int32), ("pad_", C.c_int32)]
+                ("value_bytes", C.c_int32), ("pad_", C.c_int32), ("p_val", C.POINTER(C.c_double))]
 
 
 class CsrOut(C.Structure):
@@ -71,7 +71,9 @@ SIGNATURES = {
     "tmc_cache_clear": (None, []),
     "tmc_make_tree": (C.c_int, [C.POINTER(Csr), C.POINTER(Opts), C.POINTER(C.POINTER(Tree))]),
     "tmc_make_tree_dev": (C.c_int, [_P, C.POINTER(Opts), C.POINTER(C.POINTER(Tree))]),
+    "tmc_make_tree_dense": (C.c_int, [_P, C.c_int64, C.c_int64, C.POINTER(Opts), C.POINTER(C.POINTER(Tree))]),
     "tmc_tree_free": (None, [C.POINTER(Tree)]),
+    "tmc_permutation_test": (C.c_int, [_P, C.POINTER(Tree), C.c_int, C.c_uint64, _P]),
     "tmc_degree": (C.c_int, [_P, _P, C.c_int64, _P]),
     "tmc_second_left": (C.c_int, [_P, _P, C.c_int64, C.POINTER(Opts), _P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "tmc_modularity": (C.c_int, [_P, _P, C.c_int64, _P, C.POINTER(C.c_double)]),

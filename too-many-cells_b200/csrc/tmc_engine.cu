@@ -14,7 +14,10 @@
 #include <chrono>
 #include <stdlib.h>
 #include <deque>
+#include <cmath>
 #include <functional>
+#include <limits>
+#include <memory>
 #include <mutex>
 #include <queue>
 #include <string>
@@ -29,7 +32,7 @@ using namespace tmc;
 
 static_assert(sizeof(tmc_csr) == 64, "tmc_csr layout is part of the ABI (mirrored in _lib.py)");
 static_assert(sizeof(tmc_opts) == 96, "tmc_opts layout is part of the ABI (mirrored in _lib.py)");
-static_assert(sizeof(tmc_tree) == 144, "tmc_tree layout is part of the ABI (mirrored in _lib.py)");
+static_assert(sizeof(tmc_tree) == 152, "tmc_tree layout is part of the ABI (mirrored in _lib.py)");
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -1193,10 +1196,17 @@ const char* tmc_last_error(void) { return g_err.c_str(); }
 const char* tmc_version(void) { return "libtmc 0.1 (sm_100a)"; }
 int tmc_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 
+// the per-node exports and the sweep engine know the default variant only; tmc_make_tree* dispatch the others (tmc_variants.cuh)
 static void check_opts(const tmc_opts* o) {
   if (!o) throw TmcError(TMC_ERR_INVALID, "null opts");
-  if (o->eigen_group != 0) throw TmcError(TMC_ERR_UNSUPPORTED, "eigen_group KMeansGroup is not implemented (SURVEY 8(f) N4)");
-  if (o->num_runs > 0) throw TmcError(TMC_ERR_UNSUPPORTED, "permutation test (--numRuns) is not implemented (SURVEY 8(f) N4)");
+  if (o->eigen_group != 0) throw TmcError(TMC_ERR_UNSUPPORTED, "eigen_group KMeansGroup: only through tmc_make_tree / tmc_make_tree_dev");
+  if (o->num_runs > 0) throw TmcError(TMC_ERR_UNSUPPORTED, "permutation test (--numRuns): only through tmc_make_tree* / tmc_permutation_test");
+}
+static void check_variant_opts(const tmc_opts* o) {
+  if (!o) throw TmcError(TMC_ERR_INVALID, "null opts");
+  if (o->eigen_group != 0 && o->eigen_group != 1) throw TmcError(TMC_ERR_INVALID, "eigen_group must be 0 (SignGroup) or 1 (KMeansGroup)");
+  if (o->eigen_group == 1 && o->num_eigen < 1) throw TmcError(TMC_ERR_INVALID, "num_eigen must be >= 1");
+  if (o->num_runs < 0) throw TmcError(TMC_ERR_INVALID, "num_runs must be >= 0");
 }
 
 int tmc_tfidf(const tmc_csr* b1, double* val_out, double* idf_out) {
@@ -1285,15 +1295,40 @@ void tmc_matrix_free(tmc_matrix* b) {
   delete b;
 }
 
-struct TreeStorage {
-  tmc_tree t;
-  std::vector<int64_t> left, right, parent, item_begin, item_end, perm;
-  std::vector<double> q, theta; std::vector<int32_t> iters;
-};
+}  // extern "C"
+#include "tmc_variants.cuh"      // TreeStorage + the host-composed variants
+extern "C" {
 
-int tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out) {
+// the non-default variants around a finished / instead of the sweep-engine tree
+static int finish_variants(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out, int st) {
+  if (st != TMC_OK || opts->num_runs < 1) return st;
+  TreeStorage* ts = reinterpret_cast<TreeStorage*>(*out);
+  st = guarded([&] { variants::permutation_pvals(b, ts->t, opts->num_runs, opts->seed, ts->p_val.data()); });
+  if (st != TMC_OK) { std::string keep = g_err; tmc_tree_free(*out); *out = nullptr; g_err = keep; }
+  return st;
+}
+static int make_tree_kmeans(tmc_matrix* b, const variants::HostB* hb, const tmc_opts* opts, tmc_tree** out) {
   return guarded([&] {
     if (!b || !out) throw TmcError(TMC_ERR_INVALID, "null pointer");
+    TreeStorage* ts = variants::kmeans_tree(b, hb, *opts);
+    ts->bind();
+    *out = &ts->t;
+  });
+}
+
+static int make_tree_sweeps(tmc_matrix* b, const tmc_opts* opts_in, tmc_tree** out);
+int tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out) {
+  int st = guarded([&] { check_variant_opts(opts); });
+  if (st != TMC_OK) return st;
+  st = opts->eigen_group == 1 ? make_tree_kmeans(b, nullptr, opts, out) : make_tree_sweeps(b, opts, out);
+  return finish_variants(b, opts, out, st);
+}
+
+static int make_tree_sweeps(tmc_matrix* b, const tmc_opts* opts_in, tmc_tree** out) {
+  return guarded([&] {
+    if (!b || !out) throw TmcError(TMC_ERR_INVALID, "null pointer");
+    tmc_opts sweep_opts = *opts_in; sweep_opts.num_runs = 0;      // the test runs afterwards, on the finished tree
+    const tmc_opts* opts = &sweep_opts;
     check_opts(opts);
     if (b->n_rows_global < 1) throw TmcError(TMC_ERR_INVALID, "empty matrix (reference: error, LoadMatrix.hs:255)");
     Engine eng(b, *opts);
@@ -1414,8 +1449,7 @@ int tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out) {
     }
     tmc_tree& t = ts->t;
     t.n_nodes = (int64_t)nn; t.n_rows = M;
-    t.left = ts->left.data(); t.right = ts->right.data(); t.parent = ts->parent.data(); t.q = ts->q.data(); t.theta = ts->theta.data();
-    t.iters = ts->iters.data(); t.item_begin = ts->item_begin.data(); t.item_end = ts->item_end.data(); t.perm = ts->perm.data();
+    ts->bind();
     t.n_sweeps = eng.n_sweeps; t.spmv_pairs_nnz = (int64_t)(eng.w->h_stats[0] + eng.w->h_stats[1]); t.kernel_launches = eng.n_launch;
     t.engine_ms = ms; t.spmv_ms = 0.0;
     if (eng.profile) {
@@ -1435,11 +1469,37 @@ int tmc_make_tree(const tmc_csr* b2, const tmc_opts* opts, tmc_tree** out) {
   if (!opts) return fail(TMC_ERR_INVALID, "null opts");
   int st = tmc_matrix_upload(b2, opts->normalize, opts->device, &b);
   if (st != TMC_OK) return st;
-  st = tmc_make_tree_dev(b, opts, out);
+  if (opts->eigen_group == 1 && opts->num_eigen > 1) {
+    // KMeansGroup on several eigenvectors assembles C_S per node from the host copy of B (tmc_variants.cuh)
+    st = guarded([&] { check_variant_opts(opts); });
+    variants::HostB hb;
+    if (st == TMC_OK) st = guarded([&] { variants::host_b_from(b2, opts->normalize, hb); });
+    if (st == TMC_OK) st = finish_variants(b, opts, out, make_tree_kmeans(b, &hb, opts, out));
+  } else {
+    st = tmc_make_tree_dev(b, opts, out);
+  }
   std::string keep = g_err;
   tmc_matrix_free(b);
   g_err = keep;
   return st;
+}
+
+/* == HSD.hierarchicalSpectralCluster ... (Left (sparseToHMat mat))  (Cluster.hs:157-167, --dense) */
+int tmc_make_tree_dense(const double* mat, int64_t n_rows, int64_t n_cols, const tmc_opts* opts, tmc_tree** out) {
+  variants::DenseCsr d;
+  int st = guarded([&] { variants::dense_to_csr(mat, n_rows, n_cols, d); });
+  if (st != TMC_OK) return st;
+  return tmc_make_tree(&d.view, opts, out);
+}
+
+/* == the permutation test of hierarchicalSpectralCluster's `runs` argument, for every split of a finished tree */
+int tmc_permutation_test(tmc_matrix* b, const tmc_tree* tree, int num_runs, uint64_t seed, double* p_out) {
+  return guarded([&] {
+    if (!b || !tree || !p_out) throw TmcError(TMC_ERR_INVALID, "null pointer");
+    if (num_runs < 0) throw TmcError(TMC_ERR_INVALID, "num_runs must be >= 0");
+    if (tree->n_rows != b->n_rows) throw TmcError(TMC_ERR_INVALID, "tree and matrix have different numbers of cells");
+    variants::permutation_pvals(b, *tree, num_runs, seed, p_out);
+  });
 }
 
 void tmc_tree_free(tmc_tree* t) {

@@ -255,6 +255,7 @@ class ClusteringTree:
     item_end: np.ndarray
     perm: np.ndarray         # original row ids; node i holds perm[item_begin[i]:item_end[i]] (ascending inside leaves)
     stats: dict
+    p_val: np.ndarray = None  # _pVal of every split (NaN = Nothing: leaves, or no permutation test was asked for)
 
     @property
     def n_nodes(self):
@@ -286,9 +287,33 @@ def _tree_from_c(tp) -> ClusteringTree:
         item_begin=arr(t.item_begin, n, np.int64), item_end=arr(t.item_end, n, np.int64), perm=arr(t.perm, m, np.int64),
         stats=dict(n_sweeps=int(t.n_sweeps), spmv_pairs_nnz=int(t.spmv_pairs_nnz), kernel_launches=int(t.kernel_launches),
                    engine_ms=float(t.engine_ms), spmv_ms=float(t.spmv_ms), spmv_alg_bytes=float(t.spmv_alg_bytes),
-                   value_bytes=int(t.value_bytes)))
+                   value_bytes=int(t.value_bytes)),
+        p_val=arr(t.p_val, n, np.float64))
     _lib.load().tmc_tree_free(tp)
     return out
+
+
+def _tree_to_c(tree: ClusteringTree):
+    """Borrowed C view of a ClusteringTree (only the topology fields tmc_permutation_test reads)."""
+    keep = [np.ascontiguousarray(getattr(tree, k), dtype=np.int64) for k in ("left", "right", "parent", "item_begin", "item_end", "perm")]
+    q = np.ascontiguousarray(tree.q, dtype=np.float64)
+    t = Tree()
+    t.n_nodes, t.n_rows = tree.n_nodes, int(tree.perm.size)
+    for name, a in zip(("left", "right", "parent", "item_begin", "item_end", "perm"), keep):
+        setattr(t, name, a.ctypes.data_as(C.POINTER(C.c_int64)))
+    t.q = q.ctypes.data_as(C.POINTER(C.c_double))
+    return t, keep + [q]
+
+
+def permutation_test(b: DeviceB, tree: ClusteringTree, num_runs, seed=None) -> np.ndarray:
+    """The `runs` argument of hierarchicalSpectralCluster (--numRuns, Options.hs:174) on a finished tree: empirical p-value
+    of every split (NaN for leaves)."""
+    lib = _lib.load()
+    t, keep = _tree_to_c(tree)
+    p = np.empty(tree.n_nodes, dtype=np.float64)
+    seed = make_opts().seed if seed is None else int(seed)
+    check(lib.tmc_permutation_test(b.handle, C.byref(t), int(num_runs), seed, p.ctypes.data))
+    return p
 
 
 def hierarchical_spectral_cluster(mat, eigen_group="SignGroup", normalize=False, num_eigen=None, min_size=None,
@@ -296,7 +321,9 @@ def hierarchical_spectral_cluster(mat, eigen_group="SignGroup", normalize=False,
     """hierarchicalSpectralCluster eigenGroup normFlag numEigen minSize minMod runs items (Left mat).
 
     `mat` is a host CSR (scipy / (indptr, indices, data, shape)) — copied to the GPU inside the call —
-    or a DeviceB already resident in HBM.  `None` arguments mean Haskell `Nothing`.
+    a DeviceB already resident in HBM, or a dense numpy array (cells x features: the `--dense` call,
+    HSD.hierarchicalSpectralCluster, Cluster.hs:157-167).  `None` arguments mean Haskell `Nothing`.
+    `eigen_group="KMeansGroup"` (with `num_eigen`) and `num_runs` select the non-default variants (single GPU).
     """
     lib = _lib.load()
     o = make_opts(min_modularity=0.0 if min_modularity is None else min_modularity,
@@ -305,6 +332,11 @@ def hierarchical_spectral_cluster(mat, eigen_group="SignGroup", normalize=False,
     tp = C.POINTER(Tree)()
     if isinstance(mat, DeviceB):
         check(lib.tmc_make_tree_dev(mat.handle, C.byref(o), C.byref(tp)))
+    elif isinstance(mat, np.ndarray):
+        if mat.ndim != 2:
+            raise TmcError(_lib.ERR_INVALID, "dense matrix must be 2-D (cells x features)")
+        d = np.ascontiguousarray(mat, dtype=np.float64)
+        check(lib.tmc_make_tree_dense(d.ctypes.data, int(d.shape[0]), int(d.shape[1]), C.byref(o), C.byref(tp)))
     else:
         h = HostCsr(mat)
         check(lib.tmc_make_tree(C.byref(h.c), C.byref(o), C.byref(tp)))
@@ -315,8 +347,8 @@ def h_spec_clust(matrix, row_names, eigen_group="SignGroup", num_eigen=None, min
                  dense=False, **engine_kw):
     """hSpecClust (Cluster.hs:135-187): returns (cluster_list, tree) where cluster_list is
     [(barcode, row, [leaf, ..., 0])] in DFS-leaf order and tree is the ClusteringTree."""
-    if dense:
-        raise TmcError(_lib.ERR_UNSUPPORTED, "--dense (hmatrix path, Cluster.hs:157-167) is out of scope")
     from .tree_io import cluster_list
+    if dense and not isinstance(matrix, (np.ndarray, DeviceB)):       # sparseToHMat (Cluster.hs:166)
+        matrix = np.asarray(matrix.todense()) if hasattr(matrix, "todense") else np.asarray(matrix, dtype=np.float64)
     tree = hierarchical_spectral_cluster(matrix, eigen_group, False, num_eigen, None, min_modularity, num_runs, **engine_kw)
     return cluster_list(tree, row_names), tree

@@ -55,10 +55,11 @@ class FlatTree:
 
     keeps_leaf_distance = True    # a leaf made by pruning keeps the Q of the node it collapsed (golden out_pruned tree)
 
-    def __init__(self, left, right, q, items):
+    def __init__(self, left, right, q, items, p_val=None):
         self.left = np.asarray(left, dtype=np.int64)
         self.right = np.asarray(right, dtype=np.int64)
         self.q = np.asarray(q, dtype=np.float64)
+        self.p_val = None if p_val is None else np.asarray(p_val, dtype=np.float64)   # _significance of the kept splits
         self._items = items           # leaf id -> sequence of row ids (None for inner nodes is fine)
 
     @property
@@ -135,6 +136,14 @@ def _dumps(obj) -> str:
     raise TypeError(type(obj))
 
 
+def _p_val(tree, i):
+    """`_significance` of vertex i: the split's permutation p-value (`_pVal`), None = Nothing (leaf / no test run)."""
+    p = getattr(tree, "p_val", None)
+    if p is None or tree.left[i] < 0 or not (p[i] == p[i]):
+        return None
+    return float(p[i])
+
+
 def cluster_tree_json(tree, row_names, significance=False) -> str:
     """`[label,[children]]`; inner: _item null, _distance Q; leaf: _item cells, _distance null.
     `significance=True` adds the `_significance` key current birch-beer emits (absent in the golden file)."""
@@ -153,7 +162,7 @@ def cluster_tree_json(tree, row_names, significance=False) -> str:
             kids = "[" + strs[tree.left[i]] + "," + strs[tree.right[i]] + "]"
             strs[tree.left[i]] = strs[tree.right[i]] = None
         if significance:
-            label["_significance"] = None
+            label["_significance"] = _p_val(tree, i)
         strs[i] = "[" + _dumps(label) + "," + kids + "]"
     return strs[0]
 
@@ -175,8 +184,11 @@ def parse_cluster_tree_json(text: str):
         return order
     order = walk(nested)
     ids = {id(n): i for i, n in enumerate(order)}
+    pv, any_p = [], False
     for n in order:
         label, kids = n
+        sig = label.get("_significance")          # current birch-beer; absent in the shipped golden file (--prior round trip)
+        pv.append(float("nan") if sig is None else float(sig)); any_p = any_p or sig is not None
         if kids:
             assert len(kids) == 2
             left.append(ids[id(kids[0])]); right.append(ids[id(kids[1])])
@@ -188,7 +200,7 @@ def parse_cluster_tree_json(text: str):
             for ci in label["_item"]:
                 rows.append(ci["_cellRow"]["unRow"]); names[ci["_cellRow"]["unRow"]] = ci["_barcode"]["unCell"]
             items.append(rows)
-    return FlatTree(left, right, q, items), names
+    return FlatTree(left, right, q, items, pv if any_p else None), names
 
 
 def cluster_list(tree, row_names):
@@ -264,7 +276,8 @@ def node_info_csv(tree, label_of_row=None, significance=True) -> str:
         else:
             cs = ""
         sub = "/".join(str(j) for j in range(i, i + int(count[i])))
-        row = [i, int(size[i]), prop, mod] + ([""] if significance else []) + [cs, sub]
+        sig = _p_val(tree, i)
+        row = [i, int(size[i]), prop, mod] + (["" if sig is None else haskell_show_double(sig)] if significance else []) + [cs, sub]
         rows.append(row)
     hdr = "node,size,proportion,modularity," + ("significance," if significance else "") + "composition,subtree"
     return _csv(hdr, rows)
@@ -280,12 +293,13 @@ def _collapse(tree, becomes_leaf) -> FlatTree:
     for i in range(n - 1, -1, -1):
         if tree.left[i] >= 0:
             count[i] += count[tree.left[i]] + count[tree.right[i]]
-    left, right, q, items = [], [], [], []
+    left, right, q, items, pv = [], [], [], [], []
+    src_p = getattr(tree, "p_val", None)
     stack = [(0, -1)]
     while stack:
         u, parent = stack.pop()
         i = len(left)
-        left.append(-1); right.append(-1); q.append(float("nan")); items.append(None)
+        left.append(-1); right.append(-1); q.append(float("nan")); items.append(None); pv.append(float("nan"))
         if parent >= 0:
             if left[parent] < 0:
                 left[parent] = i
@@ -294,6 +308,8 @@ def _collapse(tree, becomes_leaf) -> FlatTree:
         inner = tree.left[u] >= 0
         if inner and not becomes_leaf(u):
             q[i] = float(tree.q[u])
+            if src_p is not None:
+                pv[i] = float(src_p[u])
             stack.append((int(tree.right[u]), i)); stack.append((int(tree.left[u]), i))
         else:
             merged = []
@@ -303,7 +319,7 @@ def _collapse(tree, becomes_leaf) -> FlatTree:
             items[i] = merged
             if inner and tree.left[tree.left[u]] >= 0:
                 q[i] = float(tree.q[tree.left[u]])
-    return FlatTree(left, right, q, items)
+    return FlatTree(left, right, q, items, pv if src_p is not None else None)
 
 
 def prune_min_size(tree, min_size: int) -> FlatTree:
@@ -391,7 +407,8 @@ def root_cut(tree, node: int) -> FlatTree:
     rel = lambda v: int(v) - lo if v >= 0 else -1
     return FlatTree([rel(tree.left[v]) for v in range(lo, hi)], [rel(tree.right[v]) for v in range(lo, hi)],
                     [float(tree.q[v]) for v in range(lo, hi)],
-                    [list(int(r) for r in tree.items(v)) if tree.left[v] < 0 else None for v in range(lo, hi)])
+                    [list(int(r) for r in tree.items(v)) if tree.left[v] < 0 else None for v in range(lo, hi)],
+                    None if getattr(tree, "p_val", None) is None else [float(tree.p_val[v]) for v in range(lo, hi)])
 
 
 def smart_cutoff(values, n_mads: float) -> float:
