@@ -37,7 +37,8 @@ def test_dense_call_builds_the_sparse_tree(golden_tiny):
     a = a[:200]
     ts = T.hierarchical_spectral_cluster(a, normalize=True)
     td = T.hierarchical_spectral_cluster(np.asarray(a.todense()), normalize=True)        # tmc_make_tree_dense
-    assert np.array_equal(ts.left, td.left) and np.array_equal(ts.perm, td.perm) and np.array_equal(ts.q, td.q)
+    assert np.array_equal(ts.left, td.left) and np.array_equal(ts.perm, td.perm)
+    assert np.allclose(ts.q, td.q, rtol=0, atol=1e-12)       # two runs of the engine agree to rounding, not bit for bit
     assert same_tree(td, O.hierarchical_spectral_cluster(a, normalize=True))
     cl, th = T.h_spec_clust(T.tfidf_scale_sparse_mat(a), [f"c{i}" for i in range(a.shape[0])], dense=True)   # hSpecCommand True
     assert th.leaf_sets() == ts.leaf_sets() and len(cl) == a.shape[0]
