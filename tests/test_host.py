@@ -379,3 +379,27 @@ def test_variants_permutation_p_values_match_the_oracle(variants_host, golden_ti
             assert np.isnan(p[new_id[u]])
         else:
             assert p[new_id[u]] == os_.p_val[u]
+
+
+def test_haskell_binding_offsets_match_the_header():
+    """integration/haskell/TmcFFI.hs pokes / peeks the C structs by byte offset (no hsc2hs): every off_* / size_* constant in it
+    must equal the layout of include/tmc.h (taken from the ctypes mirror, whose sizes the library static_asserts)."""
+    import re
+    src = open(os.path.join(ROOT, "integration", "haskell", "TmcFFI.hs")).read()
+    structs = {"csr": _lib.Csr, "opts": _lib.Opts, "tree": _lib.Tree}
+    seen = 0
+    for m in re.finditer(r"^(off|size)_(csr|opts|tree)(?:_(\w+))? = (\d+)$", src, re.M):
+        kind, st, field, val = m.group(1), structs[m.group(2)], m.group(3), int(m.group(4))
+        if kind == "size":
+            assert C.sizeof(st) == val, m.group(0)
+        else:
+            assert getattr(st, field).offset == val, m.group(0)
+        seen += 1
+    assert seen >= 25
+    # every foreign import names a real export with that many arguments
+    lib = _lib.load()
+    for m in re.finditer(r'foreign import ccall safe "(\w+)"\s+\w+\s*::\s*(.*)$', src, re.M):
+        name, sig = m.group(1), m.group(2)
+        assert hasattr(lib, name)
+        n_args = sig.count("->")
+        assert n_args == len(_lib.SIGNATURES[name][1]), (name, sig)
