@@ -181,3 +181,100 @@ def test_smart_cutoff(golden_tree):
     assert 1.0 <= c["min_size"] <= 2312 and c["max_proportion"] >= 1.0 and c["min_distance"] > 0
     p = T.prune_min_size(tree, int(round(c["min_size"])))
     _check_is_pruning_of(p, tree)
+
+
+def test_elbow_cutoff(golden_tree):
+    _, tree, _ = golden_tree
+    # a convex curve (long flat start, steep end) dips below its chord: the Min elbow sits where it takes off
+    conv = [0.0, 0.01, 0.02, 0.03, 0.04, 0.05, 0.5, 1.0]
+    assert T.elbow_cutoff(conv, "Min") == 0.05
+    # a concave curve (steep start, long plateau) bulges above the chord: the Max elbow is the top-left hump
+    conc = [0.0, 0.5, 0.95, 0.96, 0.97, 0.98, 0.99, 1.0]
+    assert T.elbow_cutoff(conc, "Max") == 0.95
+    assert T.elbow_cutoff(list(reversed(conc)), "Max") == 0.95                    # order of the input does not matter
+    assert T.elbow_cutoff([10 * v for v in conc], "Max") == 9.5                   # nor do the units
+    assert T.elbow_cutoff([3.0, 3.0, 3.0], "Max") == 3.0 and T.elbow_cutoff([1.0, 2.0], "Min") == 1.0
+    with pytest.raises(ValueError):
+        T.elbow_cutoff(conc, "Median")
+    c = T.elbow_cutoffs(tree, "Max")
+    assert set(c) == {"min_size", "max_proportion", "min_distance", "min_distance_search"}
+    inner_q = [float(tree.q[i]) for i in range(tree.n_nodes) if tree.left[i] >= 0]
+    assert min(inner_q) <= c["min_distance"] <= max(inner_q)
+    _check_is_pruning_of(T.prune_min_distance(tree, c["min_distance"]), tree)
+
+
+def _oracle_as_clustering_tree(ot):
+    """OracleTree -> the flat ClusteringTree the engine returns (pre-order ids are the same; perm = leaves in DFS order)."""
+    import numpy as np
+    from too_many_cells_b200.spectral import ClusteringTree
+    n = ot.n_nodes
+    ib, ie, perm = np.zeros(n, np.int64), np.zeros(n, np.int64), []
+    for i in range(n):
+        ib[i] = len(perm)
+        if ot.left[i] < 0:
+            perm.extend(int(x) for x in ot.items[i])
+    for i in range(n):
+        ie[i] = ib[i] + len(ot.items[i])
+    par = np.full(n, -1, np.int64)
+    for i in range(n):
+        if ot.left[i] >= 0:
+            par[ot.left[i]] = par[ot.right[i]] = i
+    pv = np.array([np.nan if p is None else p for p in ot.p_val])
+    return ClusteringTree(left=np.array(ot.left), right=np.array(ot.right), parent=par, q=np.array(ot.q), theta=np.array(ot.theta),
+                          iters=np.zeros(n, np.int32), item_begin=ib, item_end=ie, perm=np.array(perm, np.int64), stats={}, p_val=pv)
+
+
+def test_make_tree_driver_flag_plumbing(tmp_path, monkeypatch, capsys, golden_tiny):
+    """tools/make_tree.py with the engine call replaced by the oracle (this is the CPU suite: the real call is exercised by
+    tests/test_gpu_ingest.py): the variant flags reach the engine call, p-values reach the files, stopping rules apply in order."""
+    import importlib.util, json
+    import numpy as np
+    import tmc_oracle as O
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("make_tree_driver", os.path.join(ROOT, "tools", "make_tree.py"))
+    drv = importlib.util.module_from_spec(spec); spec.loader.exec_module(drv)
+    a, _ = golden_tiny
+    a = a[:150]
+    names = [f"C{i:03d}-1" for i in range(a.shape[0])]
+    seen = {}
+
+    def fake_cluster(mat, normalize=False, min_modularity=None, eigen_group="SignGroup", num_eigen=None, num_runs=None, **kw):
+        seen.update(normalize=normalize, eigen_group=eigen_group, num_eigen=num_eigen, num_runs=num_runs, dense=isinstance(mat, np.ndarray))
+        import scipy.sparse as sp
+        return _oracle_as_clustering_tree(O.hierarchical_spectral_cluster(
+            sp.csr_matrix(mat), normalize=normalize, min_modularity=min_modularity or 0.0, eigen_group=eigen_group,
+            num_eigen=num_eigen or 1, num_runs=num_runs or 0))
+
+    monkeypatch.setattr(drv.T, "load_cellranger_data", lambda path, col: (a, names, [f"G{j}" for j in range(a.shape[1])]))
+    monkeypatch.setattr(drv.T, "hierarchical_spectral_cluster", fake_cluster)
+    monkeypatch.setattr(drv.T, "tfidf_scale_sparse_mat", O.b1_to_b2)
+    out = tmp_path / "o1"
+    flat = drv.main(["--matrix-path", "x", "--output", str(out), "--numRuns", "6", "--eigen-group", "KMeansGroup", "--num-eigen", "2"])
+    capsys.readouterr()
+    assert seen == dict(normalize=True, eigen_group="KMeansGroup", num_eigen=2, num_runs=6, dense=False)
+    rows = list(csv.reader(open(out / "node_info.csv", newline="")))
+    assert rows[0][4] == "significance"
+    inner = [r for r in rows[1:] if r[3] != ""]
+    assert inner and all(r[4] != "" for r in inner) and all(r[4] == "" for r in rows[1:] if r[3] == "")
+    nested = json.loads((out / "cluster_tree.json").read_text())
+    assert nested[0]["_significance"] is not None and flat.p_val is not None
+    # --dense hands the engine the tf-idf matrix as a dense array and must not ask for idf twice
+    flat_d = drv.main(["--matrix-path", "x", "--output", str(tmp_path / "o2"), "--dense"])
+    capsys.readouterr()
+    assert seen["dense"] and seen["normalize"] is False and seen["num_runs"] is None
+    flat_s = drv.main(["--matrix-path", "x", "--output", str(tmp_path / "o3")])
+    capsys.readouterr()
+    assert np.array_equal(flat_d.left, flat_s.left)
+    # stopping rules: a data-driven cutoff replaces the number on the flag; custom cuts and the root cut come first
+    full = flat_s
+    f1 = drv.main(["--matrix-path", "x", "--output", str(tmp_path / "o4"), "--min-distance", "0", "--elbow-cutoff", "Max"])
+    capsys.readouterr()
+    cut = T.elbow_cutoffs(full, "Max")["min_distance"]
+    assert np.array_equal(f1.left, T.prune_min_distance(full, cut).left)
+    f2 = drv.main(["--matrix-path", "x", "--output", str(tmp_path / "o5"), "--min-size", "1", "--smart-cutoff", "1.0"])
+    capsys.readouterr()
+    assert np.array_equal(f2.left, T.prune_min_size(full, int(round(T.smart_cutoffs(full, 1.0)["min_size"]))).left)
+    first_inner_child = int(full.left[0]) if full.left[int(full.left[0])] >= 0 else int(full.right[0])
+    f3 = drv.main(["--matrix-path", "x", "--output", str(tmp_path / "o6"), "--root-cut", str(first_inner_child), "--max-step", "1"])
+    capsys.readouterr()
+    assert f3.n_nodes == 3

@@ -430,6 +430,39 @@ def smart_cutoffs(tree, n_mads: float) -> dict:
             "min_distance_search": smart_cutoff(inner_q, n_mads)}
 
 
+def elbow_cutoff(values, kind: str = "Max") -> float:
+    """`--elbow-cutoff Max | Min` (Options.hs:184): the elbow point of the distribution of `values`.  birch-beer delegates to the
+    un-vendored `elbow` package (Math.Elbow), so the construction is restated from the help text — "for a distribution in positive
+    x and y on a graph, the top left hump would be Max and the bottom right dip would be Min": the values are sorted ascending and
+    plotted against their rank, the curve is rotated so that the chord from its first to its last point becomes the x axis, and the
+    elbow is the point farthest above (Max) or below (Min) the chord; the cutoff is that point's value.  Both axes are scaled to
+    [0, 1] first so that the answer does not depend on units.  Unpinned (no golden output exercises it)."""
+    if kind not in ("Max", "Min"):
+        raise ValueError("--elbow-cutoff takes Max or Min")
+    y = np.sort(np.asarray(values, dtype=np.float64))
+    if y.size == 0:
+        raise ValueError("elbow of an empty distribution")
+    if y.size < 3 or y[-1] == y[0]:
+        return float(y[0] if kind == "Min" else y[-1])
+    x = np.linspace(0.0, 1.0, y.size)
+    yn = (y - y[0]) / (y[-1] - y[0])
+    # after rotating the chord (0,0)-(1,1) onto the x axis, height above the chord = (yn - x) / sqrt(2)
+    h = yn - x
+    k = int(np.argmax(h)) if kind == "Max" else int(np.argmin(h))
+    return float(y[k])
+
+
+def elbow_cutoffs(tree, kind: str = "Max") -> dict:
+    """The four cutoffs of `--elbow-cutoff` (same distributions as `--smart-cutoff`; it "takes precedent" over it, Options.hs:184)."""
+    tree = _as_flat(tree)
+    size = subtree_sizes(tree)
+    inner_q = [float(tree.q[i]) for i in range(tree.n_nodes) if tree.left[i] >= 0]
+    return {"min_size": float(2.0 ** elbow_cutoff(np.log2(size), kind)),
+            "max_proportion": float(2.0 ** elbow_cutoff(split_proportions(tree), kind)),
+            "min_distance": elbow_cutoff(inner_q, kind),
+            "min_distance_search": elbow_cutoff(inner_q, kind)}
+
+
 def graph_dot(tree) -> str:
     tree = _as_flat(tree)
     lines = ["digraph {"]

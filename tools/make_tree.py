@@ -5,7 +5,9 @@ no R, no --prior): it exists so that the whole path  10x directory -> filter -> 
 can be exercised with the reference's flag names and output files.
 
   python tools/make_tree.py --matrix-path DIR --output OUT [--filter-thresholds "(250, 1)"] [--normalization TfIdfNorm|NoneNorm]
-         [--min-modularity 0] [--min-size N] [--labels-file labels.csv] [--feature-column 1]  > clusters.csv
+         [--min-modularity 0] [--min-size N | --max-step N | --max-proportion X | --min-distance X | --min-distance-search X]
+         [--smart-cutoff K | --elbow-cutoff Max|Min] [--custom-cut NODE]... [--root-cut NODE]
+         [--eigen-group KMeansGroup --num-eigen E] [--numRuns R] [--dense] [--labels-file labels.csv] [--feature-column 1]  > clusters.csv
 """
 import argparse, ast, csv, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -21,6 +23,18 @@ def main(argv=None):
     ap.add_argument("--normalization", default="TfIdfNorm")     # Program/Utility.hs:33-35: make-tree default
     ap.add_argument("--min-modularity", type=float, default=0.0)  # Options.hs:178 -> the only stop flag that reaches the engine
     ap.add_argument("--min-size", type=int)                      # Options.hs:175 -> post-prune (birch-beer)
+    ap.add_argument("--max-step", type=int)                      # Options.hs:176
+    ap.add_argument("--max-proportion", type=float)              # Options.hs:177
+    ap.add_argument("--min-distance", type=float)                # Options.hs:179
+    ap.add_argument("--min-distance-search", type=float)         # Options.hs:180
+    ap.add_argument("--smart-cutoff", type=float)                # Options.hs:181: median + DOUBLE * MAD replaces the cutoff given
+    ap.add_argument("--elbow-cutoff", choices=["Max", "Min"])    # Options.hs:182: takes precedence over --smart-cutoff
+    ap.add_argument("--custom-cut", type=int, action="append", default=[])   # Options.hs:183
+    ap.add_argument("--root-cut", type=int)                      # Options.hs:184
+    ap.add_argument("--eigen-group", default="SignGroup", choices=["SignGroup", "KMeansGroup"])   # Options.hs:172
+    ap.add_argument("--num-eigen", type=int)                     # Options.hs:173
+    ap.add_argument("--numRuns", type=int, dest="num_runs")      # Options.hs:174 -> significance column / _significance
+    ap.add_argument("--dense", action="store_true")              # Options.hs:209 -> tmc_make_tree_dense
     ap.add_argument("--labels-file")
     ap.add_argument("--feature-column", type=int, default=1)
     a = ap.parse_args(argv)
@@ -31,12 +45,33 @@ def main(argv=None):
         barcodes = [barcodes[i] for i in kr]; features = [features[j] for j in kc]
     if a.normalization not in ("TfIdfNorm", "NoneNorm"):
         raise SystemExit("only TfIdfNorm (default) and NoneNorm are on the accelerated path")
-    tree = T.hierarchical_spectral_cluster(mat, normalize=(a.normalization == "TfIdfNorm"), min_modularity=a.min_modularity)
+    if a.dense:                                                  # hSpecCommand True: sparseToHMat, then the dense entry point
+        import numpy as np
+        mat = np.asarray((T.tfidf_scale_sparse_mat(mat) if a.normalization == "TfIdfNorm" else mat).todense())
+    tree = T.hierarchical_spectral_cluster(mat, normalize=(a.normalization == "TfIdfNorm" and not a.dense),
+                                           min_modularity=a.min_modularity, eigen_group=a.eigen_group, num_eigen=a.num_eigen,
+                                           num_runs=a.num_runs)
     # clusteringTreeToTree drops the Q of leaves; pruning is applied to the finished tree, as birch-beer does
     flat = tree_io.FlatTree(tree.left, tree.right, [q if l >= 0 else float("nan") for q, l in zip(tree.q, tree.left)],
-                            [tree.items(i) if tree.left[i] < 0 else None for i in range(tree.n_nodes)])
+                            [tree.items(i) if tree.left[i] < 0 else None for i in range(tree.n_nodes)],
+                            tree.p_val if a.num_runs else None)
+    # stopping rules in the order of Program/MakeTree.hs:268-302; a data-driven cutoff replaces the number given on the flag
+    auto = tree_io.elbow_cutoffs(flat, a.elbow_cutoff) if a.elbow_cutoff else (
+        tree_io.smart_cutoffs(flat, a.smart_cutoff) if a.smart_cutoff is not None else {})
+    if a.root_cut is not None:
+        flat = tree_io.root_cut(flat, a.root_cut)
+    if a.custom_cut:
+        flat = tree_io.prune_custom_cut(flat, a.custom_cut)
     if a.min_size:
-        flat = tree_io.prune_min_size(flat, a.min_size)
+        flat = tree_io.prune_min_size(flat, int(round(auto.get("min_size", a.min_size))))
+    if a.max_step is not None:
+        flat = tree_io.prune_max_step(flat, a.max_step)
+    if a.max_proportion is not None:
+        flat = tree_io.prune_max_proportion(flat, auto.get("max_proportion", a.max_proportion))
+    if a.min_distance is not None:
+        flat = tree_io.prune_min_distance(flat, auto.get("min_distance", a.min_distance))
+    if a.min_distance_search is not None:
+        flat = tree_io.prune_min_distance_search(flat, auto.get("min_distance_search", a.min_distance_search))
     labels = None
     if a.labels_file:
         bc2row = {b: i for i, b in enumerate(barcodes)}
