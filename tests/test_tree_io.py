@@ -245,7 +245,7 @@ def test_make_tree_driver_flag_plumbing(tmp_path, monkeypatch, capsys, golden_ti
             sp.csr_matrix(mat), normalize=normalize, min_modularity=min_modularity or 0.0, eigen_group=eigen_group,
             num_eigen=num_eigen or 1, num_runs=num_runs or 0))
 
-    monkeypatch.setattr(drv.T, "load_cellranger_data", lambda path, col: (a, names, [f"G{j}" for j in range(a.shape[1])]))
+    monkeypatch.setattr(drv.T, "load_all", lambda paths, col: (a, names, [f"G{j}" for j in range(a.shape[1])]))
     monkeypatch.setattr(drv.T, "hierarchical_spectral_cluster", fake_cluster)
     monkeypatch.setattr(drv.T, "tfidf_scale_sparse_mat", O.b1_to_b2)
     out = tmp_path / "o1"
@@ -278,3 +278,45 @@ def test_make_tree_driver_flag_plumbing(tmp_path, monkeypatch, capsys, golden_ti
     f3 = drv.main(["--matrix-path", "x", "--output", str(tmp_path / "o6"), "--root-cut", str(first_inner_child), "--max-step", "1"])
     capsys.readouterr()
     assert f3.n_nodes == 3
+
+
+def test_merge_single_cells_like_the_semigroup_instance():
+    """Several --matrix-path (Matrix/Types.hs:214-254): equal feature lists stack as they are, different ones go to the ascending
+    union of the names."""
+    import numpy as np
+    import scipy.sparse as sp
+    from too_many_cells_b200 import merge_single_cells
+    a = sp.csr_matrix(np.array([[1.0, 0, 2], [0, 3, 0]]))
+    b = sp.csr_matrix(np.array([[0, 4.0, 0]]))
+    m, bc, ft = merge_single_cells([(a, ["a1", "a2"], ["g1", "g2", "g3"]), (b, ["b1"], ["g1", "g2", "g3"])])
+    assert bc == ["a1", "a2", "b1"] and ft == ["g1", "g2", "g3"]
+    assert np.array_equal(m.toarray(), np.array([[1.0, 0, 2], [0, 3, 0], [0, 4, 0]]))
+    c = sp.csr_matrix(np.array([[5.0, 6.0]]))
+    m, bc, ft = merge_single_cells([(a, ["a1", "a2"], ["g3", "g1", "g2"]), (c, ["c1"], ["g0", "g2"])])
+    assert ft == ["g0", "g1", "g2", "g3"] and bc == ["a1", "a2", "c1"]
+    #                  g0  g1  g2  g3      a: g3=col0, g1=col1, g2=col2
+    assert np.array_equal(m.toarray(), np.array([[0, 0, 2.0, 1.0], [0, 3.0, 0, 0], [5.0, 0, 6.0, 0]]))
+    assert m.has_sorted_indices
+    one = merge_single_cells([(a, ["a1", "a2"], ["g1", "g2", "g3"])])
+    assert np.array_equal(one[0].toarray(), a.toarray())
+    with pytest.raises(ValueError):
+        merge_single_cells([])
+
+
+def test_workshop_parity_comparator_on_the_golden_tree(golden_tree):
+    """tools/workshop_parity.py's comparison, fed the golden tree against itself and against a perturbed copy (the tool itself
+    needs the two public 10x tarballs of the workshop, which are not in this image: tests/test_gpu_ingest.py runs it when
+    TMC_WORKSHOP_DATA points at them)."""
+    import importlib.util
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("workshop_parity", os.path.join(ROOT, "tools", "workshop_parity.py"))
+    wp = importlib.util.module_from_spec(spec); spec.loader.exec_module(wp)
+    _, tree, names = golden_tree
+    barcodes = [names[r] for r in range(len(names))]
+    rep = wp.compare(tree, barcodes, tree, names)
+    assert rep["cells_common"] == 2312 and rep["row_numbers_equal"] and rep["leaves_identical"] and rep["topology_identical"]
+    assert rep["cells_in_a_different_leaf"] == 0 and rep["q_max_rel_diff"] == 0.0 and rep["q_compared"] == 115
+    pruned = T.prune_min_size(tree, 30)
+    rep = wp.compare(pruned, barcodes, tree, names)
+    assert not rep["leaves_identical"] and not rep["topology_identical"] and rep["vertices_shared"] >= pruned.n_nodes - len(
+        [i for i in range(pruned.n_nodes) if pruned.left[i] < 0])

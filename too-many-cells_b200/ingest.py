@@ -3,6 +3,7 @@
   load_cellranger_data   src/TooManyCells/Matrix/Load.hs:85-152 (10x directory: matrix.mtx[.gz], features.tsv[.gz] /
                          genes.tsv, barcodes.tsv[.gz]; the MTX file is features x cells and is transposed to cells x features)
   filter_num_sparse_mat  src/TooManyCells/Matrix/Preprocess.hs:342-386 (--filter-thresholds "(MINCELL, MINFEATURE)")
+  merge_single_cells     src/TooManyCells/Matrix/Types.hs:214-254 (several --matrix-path: `mconcat` of SingleCells)
 """
 from __future__ import annotations
 
@@ -72,3 +73,42 @@ def filter_num_sparse_mat(mat, row_thresh, col_thresh):
     op = C.POINTER(CsrOut)()
     check(lib.tmc_filter_thresholds(C.byref(h.c), float(row_thresh), float(col_thresh), C.byref(op)))
     return _csr_from_out(op)
+
+
+def merge_single_cells(parts):
+    """`mconcat` of SingleCells (Semigroup instance, Matrix/Types.hs:214-254) for several `--matrix-path`: `parts` is a list of
+    (matrix, barcodes, features).  Matrices that share their feature list are stacked vertically as they are; otherwise the
+    features become the ascending union of the names (`Set.toAscList . Set.union`) and every matrix is re-indexed into it
+    (`mergeFeaturesSingleCells`).  Cells keep the order of the inputs.  Index arithmetic only: no value is touched."""
+    import scipy.sparse as sp
+    parts = [p for p in parts if p is not None]
+    if not parts:
+        raise ValueError("no matrices to merge")
+    mat, barcodes, features = parts[0]
+    mat, barcodes, features = sp.csr_matrix(mat), list(barcodes), list(features)
+    for m2, b2, f2 in parts[1:]:
+        m2, f2 = sp.csr_matrix(m2), list(f2)
+        if not features or not f2 or features == f2:
+            features = features or f2
+            if mat.shape[1] != m2.shape[1]:
+                raise ValueError("matrices with equal feature lists must have equal widths")
+        else:
+            if len(set(features)) != len(features) or len(set(f2)) != len(f2):
+                raise ValueError("mergeFeaturesSingleCells: duplicated feature names cannot be merged")
+            new = sorted(set(features) | set(f2))
+            pos = {name: j for j, name in enumerate(new)}
+
+            def reindex(m, names):
+                m = m.tocoo()
+                cols = np.fromiter((pos[nm] for nm in names), dtype=np.int64, count=len(names))
+                return sp.csr_matrix((m.data, (m.row, cols[m.col])), shape=(m.shape[0], len(new)))
+            mat, m2, features = reindex(mat, features), reindex(m2, f2), new
+        mat = sp.vstack([mat, m2], format="csr")
+        barcodes += list(b2)
+    mat.sort_indices()
+    return mat, barcodes, features
+
+
+def load_all(folders, feature_column=1):
+    """Every `--matrix-path` loaded on the GPU and merged (loadAllSSM's `mconcat`, Program/LoadMatrix.hs:213-217)."""
+    return merge_single_cells([load_cellranger_data(f, feature_column) for f in folders])

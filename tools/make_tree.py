@@ -17,7 +17,7 @@ from too_many_cells_b200 import tree_io
 
 def main(argv=None):
     ap = argparse.ArgumentParser()
-    ap.add_argument("--matrix-path", required=True)
+    ap.add_argument("--matrix-path", required=True, action="append")   # repeatable: the matrices are merged (Matrix/Types.hs:214-254)
     ap.add_argument("--output", default="out")
     ap.add_argument("--filter-thresholds")                       # Options.hs:118, LoadMatrix.hs:179-183: "(MINCELL, MINFEATURE)"
     ap.add_argument("--normalization", default="TfIdfNorm")     # Program/Utility.hs:33-35: make-tree default
@@ -38,7 +38,7 @@ def main(argv=None):
     ap.add_argument("--labels-file")
     ap.add_argument("--feature-column", type=int, default=1)
     a = ap.parse_args(argv)
-    mat, barcodes, features = T.load_cellranger_data(a.matrix_path, a.feature_column)
+    mat, barcodes, features = T.load_all(a.matrix_path, a.feature_column)
     if a.filter_thresholds:
         rt, ct = ast.literal_eval(a.filter_thresholds)
         mat, kr, kc = T.filter_num_sparse_mat(mat, rt, ct)
