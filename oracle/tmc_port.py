@@ -17,9 +17,35 @@ class _Tree(C.Structure):
                 ("theta", C.POINTER(C.c_double)), ("iters", C.POINTER(C.c_int32))]
 
 
+_PROBE = """
+import ctypes as C, numpy as np, sys
+sys.path.insert(0, HERE)
+import tmc_port as P, scipy.sparse as sp
+P._checked = True
+a = sp.random(40, 30, 0.3, format="csr", random_state=0); a.data[:] = 1.0 + np.arange(a.nnz) % 3
+a = sp.vstack([a, sp.csr_matrix(np.ones((1, 30)))]).tocsr()
+assert P.make_tree(a[np.asarray(a.sum(axis=1)).ravel() > 0], normalize=False).n_nodes >= 1
+"""
+_checked = False
+
+
+def _runs_on_this_host():
+    """The library is compiled with -march=native and travels between machines with the repository snapshot: make sure it does
+    not die with SIGILL on this CPU (a tiny tree in a child process), so that a rebuild can fix it instead of the caller crashing."""
+    import sys
+    return subprocess.run([sys.executable, "-c", _PROBE.replace("HERE", repr(_HERE))], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode == 0
+
+
 def _load():
+    global _checked
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "tmc_port.c")):
         subprocess.run(["make", "-C", _HERE], check=True, stdout=subprocess.DEVNULL)
+    if not _checked:
+        if not _runs_on_this_host():
+            subprocess.run(["make", "-B", "-C", _HERE], check=True, stdout=subprocess.DEVNULL)     # built for another CPU: rebuild here
+            if not _runs_on_this_host():
+                raise RuntimeError("oracle/libtmc_port.so does not run on this host even after a rebuild")
+        _checked = True
     lib = C.CDLL(_SO)
     lib.tmc_port_make_tree.restype = C.c_int64
     lib.tmc_port_make_tree.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int,
