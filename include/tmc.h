@@ -195,6 +195,10 @@ int tmc_left_singular(const tmc_csr* a, int normalize, int n_vec, const tmc_opts
 int  tmc_comm_unique_id(uint8_t id_out[128]);
 int  tmc_comm_init(const uint8_t id[128], int rank, int world, int device);
 void tmc_comm_destroy(void);
+/* Collective self-test of the one-shot all-reduce over NVLink peer memory (csrc/tmc_p2p.cuh, enabled for the tree with
+ * TMC_P2P=1) against ncclAllReduce on n_elems doubles: largest absolute difference and average device microseconds per call of
+ * either path (p2p_us = -1 if the peer windows could not be set up).  tools/p2p_check.py drives it under torchrun. */
+int  tmc_comm_selftest(int64_t n_elems, int reps, double* max_abs_diff, double* p2p_us, double* nccl_us);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,7 @@ SIGNATURES = {
     "tmc_comm_unique_id": (C.c_int, [_P]),
     "tmc_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "tmc_comm_destroy": (None, []),
+    "tmc_comm_selftest": (C.c_int, [C.c_int64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -76,6 +76,7 @@ struct Nccl {
 };
 static Nccl g_nccl;
 enum { NCCL_UINT8 = 1, NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MIN = 3 };
+#include "tmc_p2p.cuh"      // one-shot all-reduce over NVLink peer memory (TMC_P2P=1; off by default until validated on hardware)
 
 // ----------------------------------------------------------------------------- device matrix
 struct Workspace;
@@ -254,6 +255,7 @@ static int err_to_status(int e, std::string* msg) {
     case 5: *msg = "NaN/Inf in matrix values"; return TMC_ERR_NAN;
     case 6: *msg = "negative matrix entry (engine requires B >= 0)"; return TMC_ERR_NEGATIVE;
     case 7: *msg = "zero / non-finite degree in a node"; return TMC_ERR_ZERO_ROW;
+    case 9: *msg = "peer-memory all-reduce timed out waiting for a rank (TMC_P2P)"; return TMC_ERR_COMM;
     default: *msg = "device error flag " + std::to_string(e); return TMC_ERR_CUDA;
   }
 }
@@ -747,6 +749,7 @@ struct Engine {
             host_ms[2], host_ms[3]);
   }
   bool profile = false;
+  bool use_p2p = false;      // the per-sweep all-reduces go through the peer-memory windows (tmc_p2p.cuh) instead of NCCL
   std::vector<cudaEvent_t> evs;
 
   Engine(tmc_matrix* b_, const tmc_opts& o_) : b(b_), o(o_) {
@@ -766,6 +769,12 @@ struct Engine {
     handoff_rows = getenv("TMC_HANDOFF_ROWS") ? atoi(getenv("TMC_HANDOFF_ROWS")) : 8192;
     owner_load.assign(c.world, 0);
     c.collectives = c.world > 1;
+    if (c.collectives && p2p::enabled()) {      // collective: every rank builds its engine at the same point of the call
+      const size_t want = std::max((size_t)c.ystride, (size_t)(c.K + 2 + R_NSCAL)) * (size_t)n_shared_slots;
+      use_p2p = p2p::g_p2p.ensure(want, s);
+      if (getenv("TMC_DEBUG")) fprintf(stderr, "[tmc] rank %d: peer-memory all-reduce %s (window %zu doubles x 2)\n", c.rank,
+                                       use_p2p ? "on" : "unavailable, using NCCL", p2p::g_p2p.cap);
+    }
     profile = o.profile != 0;
     CK(cudaMemsetAsync(c.st, 0, sizeof(Slot) * w->max_active, s));
     CK(cudaMemsetAsync(c.err, 0, sizeof(int), s));
@@ -879,7 +888,10 @@ struct Engine {
     if (r != 0) throw TmcError(TMC_ERR_COMM, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
   }
   void allreduce_f64(double* p, size_t n) {
-    if (c.world > 1 && n) nccl_check(g_nccl.AllReduce(p, p, n, NCCL_FLOAT64, NCCL_SUM, g_nccl.comm, s), "ncclAllReduce(f64)");
+    if (c.world <= 1 || !n) return;
+    // the same decision on every rank: n and the window capacity are rank-identical
+    if (use_p2p && n <= p2p::g_p2p.cap) { p2p::g_p2p.allreduce(p, n, s, c.err); n_launch += 2; return; }
+    nccl_check(g_nccl.AllReduce(p, p, n, NCCL_FLOAT64, NCCL_SUM, g_nccl.comm, s), "ncclAllReduce(f64)");
   }
   void allreduce_host_i32(std::vector<int>& v) {       // small host-side exchanges at the end of the tree build
     if (c.world <= 1 || v.empty()) return;
@@ -1710,7 +1722,58 @@ int tmc_comm_init(const uint8_t id_in[128], int rank, int world, int device) {
     g_nccl.comm = comm; g_nccl.rank = rank; g_nccl.world = world;
   });
 }
+/* Collective check of the peer-memory all-reduce against ncclAllReduce on n_elems doubles (rank-dependent pseudo-random data):
+ * max |p2p - nccl| over the vector (0 expected up to summation order: NCCL's order is not specified, so ~1e-16 relative), and the
+ * average device time per call of either path over `reps` calls.  p2p_us = -1 when the windows could not be set up. */
+int tmc_comm_selftest(int64_t n_elems, int reps, double* max_abs_diff, double* p2p_us, double* nccl_us) {
+  return guarded([&] {
+    if (!g_nccl.comm || g_nccl.world < 2) throw TmcError(TMC_ERR_COMM, "tmc_comm_selftest needs a communicator with >= 2 ranks");
+    if (n_elems < 1 || reps < 1 || !max_abs_diff || !p2p_us || !nccl_us) throw TmcError(TMC_ERR_INVALID, "bad arguments");
+    cudaStream_t s; CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    const size_t n = (size_t)n_elems;
+    std::vector<double> h(n), r1(n), r2(n);
+    uint64_t z = 0x9E3779B97F4A7C15ull * (uint64_t)(g_nccl.rank + 1);
+    for (size_t i = 0; i < n; ++i) { z = z * 6364136223846793005ull + 1442695040888963407ull; h[i] = (double)(z >> 11) / 9007199254740992.0 - 0.5; }
+    double* a = dalloc<double>(n); double* b = dalloc<double>(n); int* err = dalloc<int>(1);
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    try {
+      CK(cudaMemsetAsync(err, 0, sizeof(int), s));
+      const bool ok = p2p::g_p2p.ensure(n, s) && n <= p2p::g_p2p.cap;
+      *p2p_us = -1.0; *max_abs_diff = 0.0;
+      auto fill = [&](double* d) { CK(cudaMemcpyAsync(d, h.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s)); };
+      fill(a);
+      if (g_nccl.AllReduce(a, a, n, NCCL_FLOAT64, NCCL_SUM, g_nccl.comm, s) != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce failed");
+      CK(cudaMemcpyAsync(r1.data(), a, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+      if (ok) {
+        fill(b);
+        p2p::g_p2p.allreduce(b, n, s, err);
+        CK(cudaMemcpyAsync(r2.data(), b, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+      }
+      CK(cudaStreamSynchronize(s));
+      if (ok) {
+        int herr = 0; CK(cudaMemcpy(&herr, err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (herr) throw TmcError(TMC_ERR_COMM, "peer-memory all-reduce timed out");
+        for (size_t i = 0; i < n; ++i) *max_abs_diff = std::max(*max_abs_diff, std::fabs(r1[i] - r2[i]));
+      }
+      float ms = 0;
+      CK(cudaEventRecord(e0, s));
+      for (int k = 0; k < reps; ++k)
+        if (g_nccl.AllReduce(a, a, n, NCCL_FLOAT64, NCCL_SUM, g_nccl.comm, s) != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce failed");
+      CK(cudaEventRecord(e1, s)); CK(cudaStreamSynchronize(s)); CK(cudaEventElapsedTime(&ms, e0, e1));
+      *nccl_us = 1e3 * ms / reps;
+      if (ok) {
+        CK(cudaEventRecord(e0, s));
+        for (int k = 0; k < reps; ++k) p2p::g_p2p.allreduce(b, n, s, err);
+        CK(cudaEventRecord(e1, s)); CK(cudaStreamSynchronize(s)); CK(cudaEventElapsedTime(&ms, e0, e1));
+        *p2p_us = 1e3 * ms / reps;
+      }
+    } catch (...) { cudaFree(a); cudaFree(b); cudaFree(err); cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s); throw; }
+    cudaFree(a); cudaFree(b); cudaFree(err); cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s);
+  });
+}
+
 void tmc_comm_destroy(void) {
+  if (g_nccl.comm) p2p::g_p2p.destroy(0);
   if (g_nccl.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g_nccl.comm);
   g_nccl.comm = nullptr; g_nccl.rank = 0; g_nccl.world = 1;
 }
