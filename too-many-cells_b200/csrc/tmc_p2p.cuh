@@ -95,9 +95,13 @@ struct PeerReduce {
   static size_t bytes_for(size_t cap_doubles) { return HDR_BYTES + 2 * cap_doubles * sizeof(double); }
   double* buf_of(char* w, int which) const { return reinterpret_cast<double*>(w + HDR_BYTES) + (size_t)which * cap; }
 
-  void release_local() {
+  // Collective: unmap the peers' windows, wait until every rank has done so, then free the own window (an exporter must not
+  // free memory that an importer still has mapped).  `in_use`: exchanges may be in flight -> drain them first.
+  void release(cudaStream_t s, bool in_use) {
+    if (in_use) { cudaDeviceSynchronize(); barrier(s); }
     for (int q = 0; q < world; ++q) if (q != rank && peer[q]) { cudaIpcCloseMemHandle(peer[q]); }
     for (int q = 0; q < MAX_PEERS; ++q) peer[q] = nullptr;
+    if (g_nccl.comm && g_nccl.world > 1) barrier(s);
     if (base) cudaFree(base);
     base = nullptr; cap = 0; ok = false;
   }
@@ -107,11 +111,7 @@ struct PeerReduce {
     if (!g_nccl.comm || g_nccl.world < 2 || g_nccl.world > MAX_PEERS) return false;
     if (tried && (!ok || cap >= want)) return ok;
     tried = true;
-    if (ok) {                               // growing: nobody may still be reading the old windows
-      int one = barrier(s);
-      (void)one;
-      release_local();
-    }
+    if (ok) release(s, true);               // growing: drain, unmap everywhere, free, then build the larger windows
     world = g_nccl.world; rank = g_nccl.rank;
     const size_t max_cap = ((size_t)2 << 30) / (2 * sizeof(double));          // at most 2 GB of window; larger messages stay on NCCL
     cap = std::min(std::max(want, (size_t)1 << 16), max_cap);
@@ -145,7 +145,7 @@ struct PeerReduce {
       good = agree(good, s);
     }
     if (d_h) cudaFree(d_h);
-    if (!good) { release_local(); return false; }
+    if (!good) { release(s, false); return false; }
     ok = true;
     return true;
   }
@@ -181,14 +181,9 @@ struct PeerReduce {
     k_p2p_reduce<<<blocks, threads, 0, s>>>(a, p);
   }
 
-  // Collective teardown (tmc_comm_destroy): unmap the peers, wait for everybody, free the own window
+  // Collective teardown (tmc_comm_destroy)
   void destroy(cudaStream_t s) {
-    if (ok) {
-      cudaDeviceSynchronize();
-      for (int q = 0; q < world; ++q) if (q != rank && peer[q]) { cudaIpcCloseMemHandle(peer[q]); peer[q] = nullptr; }
-      barrier(s);
-    }
-    release_local();
+    if (ok || base) release(s, ok);
     tried = false; epoch = 0;
   }
 };
