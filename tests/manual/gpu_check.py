@@ -1,7 +1,8 @@
 """First-contact GPU check: every fine-grained export against the oracle, then a tree."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))      # checker scripts live under tests/: only tests may import the oracle
 import numpy as np, scipy.sparse as sp
 import too_many_cells_b200 as T
 from too_many_cells_b200 import synth

@@ -1,7 +1,8 @@
 """Robustness sweep on odd inputs: must finish (no hang / crash) and return a valid partition of the cells."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))      # checker scripts live under tests/: only tests may import the oracle
 import numpy as np, scipy.sparse as sp
 import too_many_cells_b200 as T
 import tmc_oracle as O
