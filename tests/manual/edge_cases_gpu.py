@@ -1,0 +1,85 @@
+"""Edge cases written after round 1's GPU minutes were spent: run this once on a B200 at the start of round 2
+(`python tests/manual/edge_cases_gpu.py`), then promote the checks that hold into tests/test_gpu_parity.py /
+tests/test_gpu_variants.py.  Every check prints its outcome; the script exits 1 if any expectation fails (nothing here may hang
+or crash the process — that is the point)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np, scipy.sparse as sp
+import tmc_oracle as O
+import too_many_cells_b200 as T
+from too_many_cells_b200 import _lib
+
+fails = []
+
+
+def expect_error(name, code, fn):
+    try:
+        fn()
+    except T.TmcError as e:
+        ok = e.code == code
+        print(f"{'ok  ' if ok else 'FAIL'} {name}: TmcError {e.code} ({e.msg})")
+        if not ok:
+            fails.append(name)
+        return
+    print(f"FAIL {name}: no error raised")
+    fails.append(name)
+
+
+def expect(name, cond, info=""):
+    print(f"{'ok  ' if cond else 'FAIL'} {name} {info}")
+    if not cond:
+        fails.append(name)
+
+
+rng = np.random.default_rng(0)
+# -- empty and degenerate shapes
+expect_error("0 x 5 matrix", _lib.ERR_INVALID, lambda: T.hierarchical_spectral_cluster(sp.csr_matrix((0, 5))))
+expect_error("3 x 0 matrix (every row is a zero row)", _lib.ERR_ZERO_ROW, lambda: T.hierarchical_spectral_cluster(sp.csr_matrix((3, 0))))
+expect_error("dense with an all-zero row", _lib.ERR_ZERO_ROW, lambda: T.hierarchical_spectral_cluster(np.array([[1.0, 0.0], [0.0, 0.0]])))
+expect_error("dense 0 x 0", _lib.ERR_INVALID, lambda: T.hierarchical_spectral_cluster(np.zeros((0, 0))))
+# -- malformed CSR
+a = sp.random(40, 30, 0.3, format="csr", random_state=1); a.data[:] = 1.0 + rng.integers(0, 4, a.nnz)
+a = a[np.asarray(a.sum(axis=1)).ravel() > 0]
+bad = (a.indptr.copy(), a.indices.copy(), a.data.copy(), a.shape)
+bad[1][3] = 30
+expect_error("column index == n_cols", _lib.ERR_INVALID, lambda: T.hierarchical_spectral_cluster(bad))
+bad = (a.indptr.copy(), a.indices.copy(), a.data.copy(), a.shape)
+bad[0][-1] -= 1
+expect_error("row_ptr does not end at nnz", _lib.ERR_INVALID, lambda: T.hierarchical_spectral_cluster(bad))
+# -- unsorted columns inside rows are allowed (include/tmc.h): same tree as the sorted matrix
+ip, ix, dv = a.indptr.copy(), a.indices.copy(), a.data.copy()
+for i in range(a.shape[0]):
+    p = rng.permutation(ip[i + 1] - ip[i]) + ip[i]
+    ix[ip[i]:ip[i + 1]], dv[ip[i]:ip[i + 1]] = ix[p], dv[p]
+t_sorted = T.hierarchical_spectral_cluster(a, normalize=True)
+t_shuf = T.hierarchical_spectral_cluster((ip, ix, dv, a.shape), normalize=True)
+expect("unsorted columns give the sorted matrix's tree", t_sorted.leaf_sets() == t_shuf.leaf_sets())
+# -- ragged rows: one-entry cells next to a cell that has every feature
+r = sp.lil_matrix((60, 50))
+for i in range(59):
+    r[i, i % 50] = 1.0 + (i % 3)
+    if i % 2:
+        r[i, (7 * i) % 50] = 2.0
+r[59, :] = 1.0
+r = r.tocsr()
+tr = T.hierarchical_spectral_cluster(r, normalize=False)
+ot = O.hierarchical_spectral_cluster(r, normalize=False)
+expect("ragged rows vs oracle", tr.leaf_sets() == ot.leaf_sets(), f"nodes {tr.n_nodes} / {ot.n_nodes}")
+# -- variants: invalid flags, mismatched tree
+expect_error("eigen_group = 2", _lib.ERR_INVALID, lambda: T.hierarchical_spectral_cluster(a, eigen_group=2))
+expect_error("num_runs < 0", _lib.ERR_INVALID, lambda: T.hierarchical_spectral_cluster(a, num_runs=-1))
+expect_error("KMeansGroup num_eigen = 0", _lib.ERR_INVALID, lambda: T.hierarchical_spectral_cluster(a, eigen_group="KMeansGroup", num_eigen=0))
+db = T.DeviceB.from_host(a[:20], normalize=False)
+expect_error("permutation test with a tree of another matrix", _lib.ERR_INVALID, lambda: T.permutation_test(db, t_sorted, 3))
+db.free()
+# -- KMeansGroup with more eigenvectors than a small matrix can give, binary matrix, tiny matrices
+tk = T.hierarchical_spectral_cluster(a[:9], eigen_group="KMeansGroup", num_eigen=50, normalize=True)
+ok_ = O.hierarchical_spectral_cluster(a[:9], eigen_group="KMeansGroup", num_eigen=50, normalize=True)
+expect("KMeansGroup, num_eigen far above the node size", tk.leaf_sets() == ok_.leaf_sets(), f"nodes {tk.n_nodes} / {ok_.n_nodes}")
+b = sp.csr_matrix((rng.random((80, 40)) < 0.3).astype(np.float64)); b = b[np.asarray(b.sum(axis=1)).ravel() > 0]
+tb = T.hierarchical_spectral_cluster(b, eigen_group="KMeansGroup", num_eigen=2, num_runs=4)
+ob = O.hierarchical_spectral_cluster(b, eigen_group="KMeansGroup", num_eigen=2, num_runs=4)
+expect("KMeansGroup + numRuns on a binary matrix", tb.leaf_sets() == ob.leaf_sets(), f"nodes {tb.n_nodes} / {ob.n_nodes}")
+print("FAILED:" if fails else "all edge cases behave as expected", fails or "")
+sys.exit(1 if fails else 0)
