@@ -56,13 +56,16 @@ t_sorted = T.hierarchical_spectral_cluster(a, normalize=True)
 t_shuf = T.hierarchical_spectral_cluster((ip, ix, dv, a.shape), normalize=True)
 expect("unsorted columns give the sorted matrix's tree", t_sorted.leaf_sets() == t_shuf.leaf_sets())
 # -- ragged rows: one-entry cells next to a cell that has every feature
-r = sp.lil_matrix((60, 50))
+# (seed 101 was picked on the CPU so that no node has a degenerate sigma_2 or an exactly-zero u2 entry: min gap 1.1e-2,
+#  min sign margin 3.3e-3 in the oracle — otherwise any two correct solvers may disagree)
+rr = np.random.default_rng(101)
+rows_, cols_, vals_ = [], [], []
 for i in range(59):
-    r[i, i % 50] = 1.0 + (i % 3)
-    if i % 2:
-        r[i, (7 * i) % 50] = 2.0
-r[59, :] = 1.0
-r = r.tocsr()
+    for j in rr.choice(12, size=1 + (i % 3), replace=False) + (0 if i < 30 else 8):
+        rows_.append(i); cols_.append(int(j)); vals_.append(float(rr.integers(1, 6)))
+for j in range(20):
+    rows_.append(59); cols_.append(j); vals_.append(1.0)
+r = sp.csr_matrix((vals_, (rows_, cols_)), shape=(60, 20))
 tr = T.hierarchical_spectral_cluster(r, normalize=False)
 ot = O.hierarchical_spectral_cluster(r, normalize=False)
 expect("ragged rows vs oracle", tr.leaf_sets() == ot.leaf_sets(), f"nodes {tr.n_nodes} / {ot.n_nodes}")
