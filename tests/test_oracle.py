@@ -111,3 +111,46 @@ def test_c_port_agrees_with_python_oracle(golden_tiny, golden_small):
         assert pt.leaf_sets() == sorted(tuple(v) for v in gold.values())
         assert pt.n_nodes == z["left"].size
         assert abs(pt.q[0] - z["q"][0]) < 1e-7
+
+
+# ---- SURVEY 8(f) N4 conventions (KMeansGroup, permutation test): properties the restatement must have
+def test_kmeans2_properties():
+    rng = np.random.default_rng(3)
+    two = np.concatenate([rng.normal(-3, 0.3, (40, 2)), rng.normal(3, 0.3, (25, 2))])
+    lab = O.kmeans2_labels(two)
+    assert np.array_equal(lab, np.r_[np.zeros(40), np.ones(25)].astype(np.int8))      # label 1 = the cluster at the high end
+    assert np.array_equal(O.kmeans2_labels(-two), 1 - lab)                            # sign flip of the vectors swaps the labels ...
+    flipped = two * np.array([1.0, -1.0])
+    assert np.array_equal(O.kmeans2_labels(flipped), lab)                             # ... flipping a later column changes nothing
+    perm = rng.permutation(65)
+    assert np.array_equal(O.kmeans2_labels(two[perm]), lab[perm])                     # order of the cells does not matter
+    assert np.array_equal(O.kmeans2_labels(7.5 * two), lab)                           # nor does the scale
+    assert O.kmeans2_labels(np.array([[0.2], [0.9]])).tolist() == [0, 1]
+    assert O.kmeans2_labels(np.ones((4, 1))).tolist() == [1, 1, 1, 1]                  # no spread: a single cluster
+    assert O.kmeans_num_eigen(5, 100, 1000) == 5 and O.kmeans_num_eigen(5, 12, 1000) == 2 and O.kmeans_num_eigen(5, 3, 1000) == 1
+
+
+def test_permutation_p_value_properties(golden_tiny):
+    a, _ = golden_tiny
+    b = O.b2_to_b(O.b1_to_b2(a))[:80]
+    rows = np.arange(80)
+    labels, *_ = O.spectral_cluster(b)
+    p = O.permutation_p_value(labels, b, rows, 30, seed=11)
+    assert 0.0 <= p <= 1.0 and p == O.permutation_p_value(labels, b, rows, 30, seed=11)       # deterministic given the seed
+    assert p == O.permutation_p_value(1 - labels, b, rows, 30, seed=11)                           # a split, not a labelling, is tested
+    assert p <= 0.1                                                                               # the spectral split beats shuffles
+    rnd = (np.random.default_rng(0).random(80) < 0.5).astype(np.int8)
+    assert O.permutation_p_value(rnd, b, rows, 60, seed=11) > 0.1                                 # a random split does not
+    # every shuffle of a 2-cell node is the same split: p = 1 exactly (the 1e-12 slack absorbs rounding)
+    two = b[:2]
+    assert O.permutation_p_value(np.array([0, 1]), two, np.array([0, 1]), 10, seed=5) == 1.0
+    # shuffling keeps the cluster sizes
+    lab = np.array([0] * 5 + [1] * 9, dtype=np.int8)
+    r = O.SplitMix64(1)
+    for _ in range(20):
+        O.shuffle_labels(lab, r)
+        assert lab.sum() == 9
+    # different nodes draw different streams, the same node the same stream wherever it sits in a tree
+    t = O.hierarchical_spectral_cluster(a[:120], normalize=True, num_runs=5, seed=3)
+    sub = O.hierarchical_spectral_cluster(a[:120], normalize=True, num_runs=5, seed=3, min_modularity=0.0)
+    assert t.p_val == sub.p_val
