@@ -24,7 +24,7 @@ namespace p2p {
 
 constexpr int MAX_PEERS = 16;
 constexpr size_t HDR_BYTES = 1024;          // 64 flags (512 B) + counter, padded
-constexpr unsigned long long SPIN_LIMIT = 1ull << 27;      // ~ seconds; then error flag 9
+constexpr unsigned long long SPIN_LIMIT = 1ull << 24;      // ~ 10-20 s of polling (about 1 us per probe); then error flag 9
 
 struct Args {
   const double* win[MAX_PEERS];             // buffer (epoch & 1) of every rank; win[rank] = own
