@@ -84,5 +84,20 @@ b = sp.csr_matrix((rng.random((80, 40)) < 0.3).astype(np.float64)); b = b[np.asa
 tb = T.hierarchical_spectral_cluster(b, eigen_group="KMeansGroup", num_eigen=2, num_runs=4)
 ob = O.hierarchical_spectral_cluster(b, eigen_group="KMeansGroup", num_eigen=2, num_runs=4)
 expect("KMeansGroup + numRuns on a binary matrix", tb.leaf_sets() == ob.leaf_sets(), f"nodes {tb.n_nodes} / {ob.n_nodes}")
+# -- the C++ host layer's variant overloads (tests/helpers/host_cpp_example.cpp, mode "variants")
+import subprocess, tempfile
+with tempfile.TemporaryDirectory() as td:
+    pkg = os.path.join(ROOT, "too-many-cells_b200")
+    exe = os.path.join(td, "host_cpp_example")
+    subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "helpers", "host_cpp_example.cpp"), "-o", exe, "-L", pkg, "-ltmc",
+                    f"-Wl,-rpath,{pkg}"], check=True)
+    with open(os.path.join(td, "m.txt"), "w") as f:
+        f.write(f"{a.shape[0]} {a.shape[1]} {a.nnz}\n" + " ".join(map(str, a.indptr.tolist())) + "\n" + " ".join(map(str, a.indices.tolist())) + "\n"
+                + " ".join(repr(float(x)) for x in a.data.tolist()) + "\n")
+    out = subprocess.run([exe, os.path.join(td, "m.txt"), "variants"], capture_output=True, text=True)
+    tkm = T.hierarchical_spectral_cluster(a, normalize=True, eigen_group="KMeansGroup", num_runs=4)
+    tde = T.hierarchical_spectral_cluster(a, normalize=True)
+    want = f"nodes {tkm.n_nodes} splits-with-p {(tkm.n_nodes - 1) // 2}\nnodes {tde.n_nodes} splits-with-p 0\n"
+    expect("C++ host layer: KMeansGroup + runs, dense overload", out.returncode == 0 and out.stdout == want, repr(out.stdout) + out.stderr[-200:])
 print("FAILED:" if fails else "all edge cases behave as expected", fails or "")
 sys.exit(1 if fails else 0)
