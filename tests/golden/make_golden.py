@@ -33,3 +33,23 @@ for name in ("tiny", "small"):
         size=np.array([x.size for x in tr.items], dtype=np.int64), leaf_of_row=leaf_of_row,
         root_u2=u2, root_d=d, root_q=np.array(O.get_b_modularity(lab, b)))
     print(name, "nodes", tr.n_nodes, "leaves", len(tr.leaves()))
+
+# ---- the non-default variants on `tiny`: KMeansGroup trees and permutation p-values
+ip, ix, dv, _ = synth.synth_config("tiny")
+n, g = synth.CONFIGS["tiny"][:2]
+a = sp.csr_matrix((dv, ix, ip), shape=(n, g))
+out = {}
+for tag, kw in (("km1", dict(eigen_group="KMeansGroup", num_eigen=1)), ("km3", dict(eigen_group="KMeansGroup", num_eigen=3)),
+                ("perm", dict(num_runs=20))):
+    tr = O.hierarchical_spectral_cluster(a, normalize=True, **kw)
+    leaf_of_row = np.full(n, -1, dtype=np.int32)
+    for i in tr.leaves():
+        leaf_of_row[tr.items[i]] = i
+    out[f"{tag}_left"] = np.array(tr.left, dtype=np.int64); out[f"{tag}_right"] = np.array(tr.right, dtype=np.int64)
+    out[f"{tag}_q"] = np.array(tr.q); out[f"{tag}_leaf_of_row"] = leaf_of_row
+    out[f"{tag}_p_val"] = np.array([np.nan if p is None else p for p in tr.p_val])
+    print("variants", tag, "nodes", tr.n_nodes)
+sat = O.hierarchical_spectral_cluster(a[:60], normalize=True, num_runs=10, min_modularity=-1.0, seed=7)
+out["sat_left"] = np.array(sat.left, dtype=np.int64); out["sat_p_val"] = np.array([np.nan if p is None else p for p in sat.p_val])
+out["splitmix_1234567"] = np.array([O.SplitMix64(1234567).next() for _ in range(1)], dtype=np.uint64)
+np.savez_compressed(os.path.join(HERE, "variants_tiny.npz"), **out)

@@ -154,3 +154,27 @@ def test_permutation_p_value_properties(golden_tiny):
     t = O.hierarchical_spectral_cluster(a[:120], normalize=True, num_runs=5, seed=3)
     sub = O.hierarchical_spectral_cluster(a[:120], normalize=True, num_runs=5, seed=3, min_modularity=0.0)
     assert t.p_val == sub.p_val
+
+
+def test_oracle_variants_match_golden(golden_tiny):
+    """tests/golden/variants_tiny.npz (tests/golden/make_golden.py) pins the restated conventions of the non-default variants:
+    the GPU tests compare libtmc with the live oracle, this keeps the oracle itself from drifting."""
+    import os
+    from conftest import GOLDEN
+    a, _ = golden_tiny
+    z = np.load(os.path.join(GOLDEN, "variants_tiny.npz"))
+    assert int(z["splitmix_1234567"][0]) == 6457827717110365317
+    for tag, kw in (("km1", dict(eigen_group="KMeansGroup", num_eigen=1)), ("km3", dict(eigen_group="KMeansGroup", num_eigen=3)),
+                    ("perm", dict(num_runs=20))):
+        tr = O.hierarchical_spectral_cluster(a, normalize=True, **kw)
+        assert np.array_equal(np.array(tr.left), z[f"{tag}_left"]) and np.array_equal(np.array(tr.right), z[f"{tag}_right"])
+        assert np.allclose(np.array(tr.q), z[f"{tag}_q"], rtol=1e-9, atol=1e-13)
+        leaf_of_row = np.full(a.shape[0], -1)
+        for i in tr.leaves():
+            leaf_of_row[tr.items[i]] = i
+        assert np.array_equal(leaf_of_row, z[f"{tag}_leaf_of_row"])
+        p = np.array([np.nan if x is None else x for x in tr.p_val])
+        assert np.array_equal(p, z[f"{tag}_p_val"], equal_nan=True)
+    sat = O.hierarchical_spectral_cluster(a[:60], normalize=True, num_runs=10, min_modularity=-1.0, seed=7)
+    assert np.array_equal(np.array(sat.left), z["sat_left"])
+    assert np.array_equal(np.array([np.nan if x is None else x for x in sat.p_val]), z["sat_p_val"], equal_nan=True)
