@@ -50,15 +50,21 @@ def test_no_cpu_fallback_without_device():
         T.b1_to_b2(a)
 
 
-def test_unsupported_flags_are_reported():
+def test_variant_flags_fail_loudly_without_device():
     lib = _lib.load()
     if lib.tmc_device_count() > 0:
-        pytest.skip("checked on the GPU box in test_gpu_parity")
-    # without a device the device check comes first; just make sure the call returns an error, not a crash
+        pytest.skip("the variants run on the GPU box in test_gpu_variants")
+    # KMeansGroup / dense / num_runs go through the same device check: an error, never a host fallback or a crash
     import scipy.sparse as sp
     a = sp.random(20, 10, 0.5, format="csr", random_state=0)
-    with pytest.raises(T.TmcError):
-        T.hierarchical_spectral_cluster(a, eigen_group="KMeansGroup")
+    import numpy as np
+    for kw in (dict(eigen_group="KMeansGroup"), dict(eigen_group="KMeansGroup", num_eigen=3), dict(num_runs=5)):
+        with pytest.raises(T.TmcError) as ei:
+            T.hierarchical_spectral_cluster(a, **kw)
+        assert ei.value.code == _lib.ERR_NO_DEVICE
+    with pytest.raises(T.TmcError) as ei:
+        T.hierarchical_spectral_cluster(np.asarray(a.todense()))           # tmc_make_tree_dense
+    assert ei.value.code == _lib.ERR_NO_DEVICE
 
 
 @pytest.fixture(scope="module")
