@@ -409,3 +409,30 @@ def test_haskell_binding_offsets_match_the_header():
         assert hasattr(lib, name)
         n_args = sig.count("->")
         assert n_args == len(_lib.SIGNATURES[name][1]), (name, sig)
+
+
+def test_ctypes_mirror_matches_the_header_field_by_field(tmp_path):
+    """Compile include/tmc.h with gcc and compare offsetof / sizeof of every struct field with the ctypes mirror in _lib.py (which
+    the Haskell binding's offsets are in turn checked against)."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "tmc.h")).read()
+    structs = {"tmc_csr": _lib.Csr, "tmc_opts": _lib.Opts, "tmc_tree": _lib.Tree, "tmc_csr_out": _lib.CsrOut}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "tmc.h")}"', "int main(void) {"]
+    for name, st in structs.items():
+        assert re.search(r"}\s*" + name + r"\s*;", hdr), name
+        lines.append(f'  printf("{name} size %zu\\n", sizeof({name}));')
+        for field, _ in st._fields_:
+            lines.append(f'  printf("{name} {field} %zu\\n", offsetof({name}, {field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", str(src), "-o", str(exe)], check=True)      # the header is plain C
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    seen = 0
+    for ln in filter(None, out):
+        name, field, val = ln.split()
+        st = structs[name]
+        assert (C.sizeof(st) if field == "size" else getattr(st, field).offset) == int(val), ln
+        seen += 1
+    assert seen == sum(len(s._fields_) + 1 for s in structs.values())
