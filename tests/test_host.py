@@ -28,6 +28,20 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libtmc.so does not export {n}"
     assert set(names) == set(_lib.SIGNATURES), "ctypes binding and header disagree"
+    # ... and every prototype has as many parameters, of the same width class, as its ctypes signature
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "tmc.h")).read(), flags=re.S)
+    for m in re.finditer(r"\b(tmc_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr):
+        name, params = m.group(1), m.group(2).strip()
+        plist = [] if params in ("", "void") else [x.strip() for x in params.split(",")]
+        res, args = _lib.SIGNATURES[name]
+        assert len(plist) == len(args), (name, plist)
+        for decl, ct in zip(plist, args):
+            is_ptr = "*" in decl or "[" in decl
+            ct_ptr = ct in (C.c_void_p, C.c_char_p) or hasattr(ct, "contents") or isinstance(ct, type(C.POINTER(C.c_int)))
+            assert is_ptr == bool(ct_ptr), (name, decl, ct)
+            if not is_ptr:
+                want = {"int64_t": C.c_int64, "uint64_t": C.c_uint64, "int": C.c_int, "double": C.c_double}[decl.split()[-2] if len(decl.split()) > 1 else decl]
+                assert ct is want, (name, decl, ct)
 
 
 def test_opts_default_and_layout():
