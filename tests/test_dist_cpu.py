@@ -65,3 +65,18 @@ def test_world2_gloo():
     for r in (r0, r1):
         if r["init_rc"] is not None:
             assert r["init_rc"] != 0          # ERR_NO_DEVICE / ERR_COMM, never a silent success
+
+
+def test_peer_window_exchange_protocol_model(tmp_path):
+    """The exchange protocol of csrc/tmc_p2p.cuh (publish into the own double-buffered window, release-signal every peer, wait,
+    pull and sum) modelled with threads and std::atomic (tests/helpers/p2p_protocol_sim.cpp): with random stalls between the
+    steps no rank may ever sum a buffer that a faster rank has already rewritten.  (The CUDA side — cudaIpc windows, .sys-scope
+    ordering — needs N >= 2 GPUs: tools/p2p_check.py.)"""
+    import subprocess
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "p2psim"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", os.path.join(ROOT, "tests", "helpers", "p2p_protocol_sim.cpp"), "-o", str(exe)],
+                   check=True)
+    for ranks, epochs, seed in ((2, 400, 1), (4, 300, 2), (8, 200, 3)):
+        out = subprocess.run([str(exe), str(ranks), str(epochs), "48", "2", str(seed)], capture_output=True, text=True, check=True, timeout=120)
+        assert out.stdout.strip() == "mismatches 0", (ranks, out.stdout)
