@@ -51,6 +51,8 @@ def _load():
     lib.tmc_port_make_tree.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int,
                                        C.c_void_p, C.POINTER(_Tree), C.POINTER(C.c_double)]
     lib.tmc_port_tree_free.argtypes = [C.POINTER(_Tree)]
+    lib.tmc_port_set_threads.argtypes = [C.c_int]
+    lib.tmc_port_get_threads.restype = C.c_int
     return lib
 
 
@@ -70,14 +72,16 @@ class PortTree:
         return sorted(tuple(int(x) for x in self.items(i)) for i in range(self.n_nodes) if self.left[i] < 0)
 
 
-def make_tree(mat, normalize=False, min_modularity=0.0, tol=1e-6, kmax=400) -> PortTree:
-    """The whole path on one CPU core.  tf-idf and row-L2 are done with numpy first (as loadAllSSM does before the engine)."""
+def make_tree(mat, normalize=False, min_modularity=0.0, tol=1e-6, kmax=400, threads=1) -> PortTree:
+    """The whole path on one CPU core (threads=1, like the reference) or with the mat-vecs and the re-orthogonalisation spread over
+    `threads` cores.  tf-idf and row-L2 are done with numpy first (as loadAllSSM does before the engine)."""
     import tmc_oracle as O
     b2 = sp.csr_matrix(mat, dtype=np.float64)
     if normalize:
         b2 = O.b1_to_b2(b2)
     b = O.b2_to_b(b2)
     lib = _load()
+    lib.tmc_port_set_threads(int(threads))
     m, n = b.shape
     ptr = np.ascontiguousarray(b.indptr, dtype=np.int64); col = np.ascontiguousarray(b.indices, dtype=np.int32)
     val = np.ascontiguousarray(b.data, dtype=np.float64)
