@@ -320,3 +320,33 @@ def test_workshop_parity_comparator_on_the_golden_tree(golden_tree):
     rep = wp.compare(pruned, barcodes, tree, names)
     assert not rep["leaves_identical"] and not rep["topology_identical"] and rep["vertices_shared"] >= pruned.n_nodes - len(
         [i for i in range(pruned.n_nodes) if pruned.left[i] < 0])
+
+
+def test_make_tree_driver_prior_reproduces_the_reference_workshop_files(tmp_path, capsys):
+    """The reference's own `--prior` runs (workshop/workshop.org:253-330): from the golden `out/cluster_tree.json` the driver must
+    write, byte for byte, the files the reference wrote — the unpruned set and the `--min-size 30` set (golden-era format: the
+    shipped files predate the significance fields)."""
+    import importlib.util
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("make_tree_driver", os.path.join(ROOT, "tools", "make_tree.py"))
+    drv = importlib.util.module_from_spec(spec); spec.loader.exec_module(drv)
+    rd = lambda p: open(p, newline="").read()
+    labels = os.path.join(W, "labels.csv")
+    out = tmp_path / "plain"
+    drv.main(["--prior", W, "--output", str(out), "--labels-file", labels, "--legacy-format"])
+    assert capsys.readouterr().out == rd(os.path.join(W, "clusters.csv"))
+    for ours, golden in (("cluster_tree.json", "cluster_tree.json"), ("cluster_info.csv", "cluster_info.csv"),
+                         ("node_info.csv", "node_info.csv"), ("graph.dot", "graph.dot"), ("clusters.csv", "clusters.csv")):
+        assert rd(out / ours) == rd(os.path.join(W, golden)), ours
+    assert rd(out / "cluster_list.json") == gzip.open(os.path.join(W, "cluster_list.json.gz"), "rt").read()
+    out = tmp_path / "pruned"
+    drv.main(["--prior", W, "--output", str(out), "--labels-file", labels, "--legacy-format", "--min-size", "30"])
+    assert capsys.readouterr().out == rd(os.path.join(W, "clusters_pruned.csv"))
+    for ours, golden in (("cluster_tree.json", "pruned_cluster_tree.json"), ("cluster_info.csv", "pruned_cluster_info.csv"),
+                         ("node_info.csv", "pruned_node_info.csv")):
+        assert rd(out / ours) == rd(os.path.join(W, golden)), ours
+    # current format: the same run carries the significance fields (all Nothing here: no permutation test was stored)
+    drv.main(["--prior", W, "--output", str(tmp_path / "cur")])
+    capsys.readouterr()
+    assert rd(tmp_path / "cur" / "node_info.csv").startswith("node,size,proportion,modularity,significance,composition,subtree")
+    assert '"_significance":null' in rd(tmp_path / "cur" / "cluster_tree.json")

@@ -474,15 +474,16 @@ def graph_dot(tree) -> str:
     return "\n".join(lines) + "\n}"
 
 
-def write_make_tree_outputs(tree, row_names, out_dir, label_of_row=None):
-    """Write the files `make-tree --output DIR` writes from the clustering (no plots)."""
+def write_make_tree_outputs(tree, row_names, out_dir, label_of_row=None, significance=True):
+    """Write the files `make-tree --output DIR` writes from the clustering (no plots).  `significance=False` writes the format of
+    the program version that made the reference's golden workshop files (no `_significance` key / `significance` column)."""
     import os
     os.makedirs(out_dir, exist_ok=True)
     files = {
-        "cluster_tree.json": cluster_tree_json(tree, row_names, significance=True),
+        "cluster_tree.json": cluster_tree_json(tree, row_names, significance=significance),
         "cluster_list.json": cluster_list_json(tree, row_names),
         "cluster_info.csv": cluster_info_csv(tree),
-        "node_info.csv": node_info_csv(tree, label_of_row),
+        "node_info.csv": node_info_csv(tree, label_of_row, significance=significance),
         "graph.dot": graph_dot(tree),
         "clusters.csv": clusters_csv(tree, row_names),
     }

@@ -4,7 +4,7 @@
 no R, no --prior): it exists so that the whole path  10x directory -> filter -> tf-idf -> tree -> prune -> output files
 can be exercised with the reference's flag names and output files.
 
-  python tools/make_tree.py --matrix-path DIR --output OUT [--filter-thresholds "(250, 1)"] [--normalization TfIdfNorm|NoneNorm]
+  python tools/make_tree.py (--matrix-path DIR ... | --prior PREVIOUS_OUT) --output OUT [--filter-thresholds "(250, 1)"] [--normalization TfIdfNorm|NoneNorm]
          [--min-modularity 0] [--min-size N | --max-step N | --max-proportion X | --min-distance X | --min-distance-search X]
          [--smart-cutoff K | --elbow-cutoff Max|Min] [--custom-cut NODE]... [--root-cut NODE]
          [--eigen-group KMeansGroup --num-eigen E] [--numRuns R] [--dense] [--labels-file labels.csv] [--feature-column 1]  > clusters.csv
@@ -17,7 +17,9 @@ from too_many_cells_b200 import tree_io
 
 def main(argv=None):
     ap = argparse.ArgumentParser()
-    ap.add_argument("--matrix-path", required=True, action="append")   # repeatable: the matrices are merged (Matrix/Types.hs:214-254)
+    ap.add_argument("--matrix-path", action="append")            # repeatable: the matrices are merged (Matrix/Types.hs:214-254)
+    ap.add_argument("--prior")                                   # Options.hs:204: folder of a previous run -> skip clustering
+    ap.add_argument("--legacy-format", action="store_true")      # driver only: files without the significance fields (golden-era format)
     ap.add_argument("--output", default="out")
     ap.add_argument("--filter-thresholds")                       # Options.hs:118, LoadMatrix.hs:179-183: "(MINCELL, MINFEATURE)"
     ap.add_argument("--normalization", default="TfIdfNorm")     # Program/Utility.hs:33-35: make-tree default
@@ -38,6 +40,13 @@ def main(argv=None):
     ap.add_argument("--labels-file")
     ap.add_argument("--feature-column", type=int, default=1)
     a = ap.parse_args(argv)
+    if a.prior:
+        # `--prior`: "skips clustering by using the previous clustering files" (Program/MakeTree.hs:213-225 loads cluster_tree.json);
+        # cells are addressed by the row numbers stored in the tree (the reference's --no-update-tree-rows behaviour)
+        flat, barcodes = tree_io.parse_cluster_tree_json(open(os.path.join(a.prior, "cluster_tree.json")).read())
+        return finish(a, flat, barcodes)
+    if not a.matrix_path:
+        ap.error("--matrix-path is required without --prior")
     mat, barcodes, features = T.load_all(a.matrix_path, a.feature_column)
     if a.filter_thresholds:
         rt, ct = ast.literal_eval(a.filter_thresholds)
@@ -55,6 +64,11 @@ def main(argv=None):
     flat = tree_io.FlatTree(tree.left, tree.right, [q if l >= 0 else float("nan") for q, l in zip(tree.q, tree.left)],
                             [tree.items(i) if tree.left[i] < 0 else None for i in range(tree.n_nodes)],
                             tree.p_val if a.num_runs else None)
+    return finish(a, flat, barcodes)
+
+
+def finish(a, flat, barcodes):
+    """Stopping rules, label composition and the output files: everything after the clustering (also the whole --prior path)."""
     # stopping rules in the order of Program/MakeTree.hs:268-302; a data-driven cutoff replaces the number given on the flag
     auto = tree_io.elbow_cutoffs(flat, a.elbow_cutoff) if a.elbow_cutoff else (
         tree_io.smart_cutoffs(flat, a.smart_cutoff) if a.smart_cutoff is not None else {})
@@ -74,9 +88,9 @@ def main(argv=None):
         flat = tree_io.prune_min_distance_search(flat, auto.get("min_distance_search", a.min_distance_search))
     labels = None
     if a.labels_file:
-        bc2row = {b: i for i, b in enumerate(barcodes)}
+        bc2row = {b: i for i, b in (barcodes.items() if isinstance(barcodes, dict) else enumerate(barcodes))}
         labels = {bc2row[r[0]]: r[1] for r in list(csv.reader(open(a.labels_file)))[1:] if r[0] in bc2row}
-    tree_io.write_make_tree_outputs(flat, barcodes, a.output, labels)
+    tree_io.write_make_tree_outputs(flat, barcodes, a.output, labels, significance=not a.legacy_format)
     sys.stdout.write(tree_io.clusters_csv(flat, barcodes))
     return flat
 
