@@ -350,3 +350,23 @@ def test_make_tree_driver_prior_reproduces_the_reference_workshop_files(tmp_path
     capsys.readouterr()
     assert rd(tmp_path / "cur" / "node_info.csv").startswith("node,size,proportion,modularity,significance,composition,subtree")
     assert '"_significance":null' in rd(tmp_path / "cur" / "cluster_tree.json")
+
+
+def test_write_matrix_like_round_trips_as_a_10x_directory(tmp_path):
+    """--matrix-output FOLDER (Matrix/Utility.hs:220-250): features are rows in matrix.mtx.gz, features.tsv.gz has the reference's
+    three columns; an independent reader (scipy) gets the same matrix back."""
+    import numpy as np
+    import scipy.io, scipy.sparse as sp
+    from too_many_cells_b200 import write_matrix_like
+    rng = np.random.default_rng(5)
+    d = ((rng.random((7, 5)) < 0.5) * rng.integers(1, 9, (7, 5))).astype(np.float64)
+    d[2, 3] = 0.1 + 0.2                                                          # a value that needs all its digits
+    a = sp.csr_matrix(d)
+    bcs, feats = [f"BC{i}-1" for i in range(7)], [f"Gene{j}" for j in range(5)]
+    write_matrix_like(tmp_path / "mo", a, bcs, feats)
+    back = sp.csr_matrix(scipy.io.mmread(str(tmp_path / "mo" / "matrix.mtx.gz"), spmatrix=True))
+    assert back.shape == (5, 7) and np.array_equal(back.T.toarray(), a.toarray())
+    assert gzip.open(tmp_path / "mo" / "features.tsv.gz", "rt").read().splitlines() == [f"{g}\t{g}\tNA" for g in feats]
+    assert gzip.open(tmp_path / "mo" / "barcodes.tsv.gz", "rt").read().splitlines() == bcs
+    with pytest.raises(ValueError):
+        write_matrix_like(tmp_path / "bad", a, bcs[:-1], feats)

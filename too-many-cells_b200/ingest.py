@@ -4,6 +4,7 @@
                          genes.tsv, barcodes.tsv[.gz]; the MTX file is features x cells and is transposed to cells x features)
   filter_num_sparse_mat  src/TooManyCells/Matrix/Preprocess.hs:342-386 (--filter-thresholds "(MINCELL, MINFEATURE)")
   merge_single_cells     src/TooManyCells/Matrix/Types.hs:214-254 (several --matrix-path: `mconcat` of SingleCells)
+  write_matrix_like      src/TooManyCells/Matrix/Utility.hs:220-250 (--matrix-output FOLDER: the 10x directory written back)
 """
 from __future__ import annotations
 
@@ -112,3 +113,25 @@ def merge_single_cells(parts):
 def load_all(folders, feature_column=1):
     """Every `--matrix-path` loaded on the GPU and merged (loadAllSSM's `mconcat`, Program/LoadMatrix.hs:213-217)."""
     return merge_single_cells([load_cellranger_data(f, feature_column) for f in folders])
+
+
+def write_matrix_like(folder, mat, barcodes, features):
+    """`writeSparseMatrixLike (MatrixTranspose False)` (Matrix/Utility.hs:220-250; `--matrix-output FOLDER`): the cells x features
+    matrix written back as a 10x directory — `matrix.mtx.gz` with features as rows ("like input"), `features.tsv.gz` with the
+    reference's three columns `name<TAB>name<TAB>NA`, `barcodes.tsv.gz`.  Coordinate / real / general, 1-based, one entry per line in
+    (cell, feature) order, values in shortest round-trip notation, so that `load_cellranger_data` reads back the same matrix."""
+    import scipy.sparse as sp
+    m = sp.csr_matrix(mat)
+    m.sort_indices()
+    if m.shape != (len(barcodes), len(features)):
+        raise ValueError(f"matrix is {m.shape} but there are {len(barcodes)} barcodes and {len(features)} features")
+    os.makedirs(folder, exist_ok=True)
+    rows = np.repeat(np.arange(m.shape[0], dtype=np.int64), np.diff(m.indptr))
+    lines = ["%%MatrixMarket matrix coordinate real general", f"{m.shape[1]} {m.shape[0]} {m.nnz}"]
+    lines += [f"{j + 1} {i + 1} {repr(float(v))}" for i, j, v in zip(rows.tolist(), m.indices.tolist(), m.data.tolist())]
+    with gzip.open(os.path.join(folder, "matrix.mtx.gz"), "wt") as f:
+        f.write("\n".join(lines) + "\n")
+    with gzip.open(os.path.join(folder, "features.tsv.gz"), "wt") as f:
+        f.write("".join(f"{x}\t{x}\tNA\n" for x in features))
+    with gzip.open(os.path.join(folder, "barcodes.tsv.gz"), "wt") as f:
+        f.write("".join(f"{x}\n" for x in barcodes))

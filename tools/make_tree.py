@@ -37,6 +37,7 @@ def main(argv=None):
     ap.add_argument("--num-eigen", type=int)                     # Options.hs:173
     ap.add_argument("--numRuns", type=int, dest="num_runs")      # Options.hs:174 -> significance column / _significance
     ap.add_argument("--dense", action="store_true")              # Options.hs:209 -> tmc_make_tree_dense
+    ap.add_argument("--matrix-output")                           # Options.hs:186: the filtered matrix as a 10x folder under --output
     ap.add_argument("--labels-file")
     ap.add_argument("--feature-column", type=int, default=1)
     a = ap.parse_args(argv)
@@ -52,6 +53,8 @@ def main(argv=None):
         rt, ct = ast.literal_eval(a.filter_thresholds)
         mat, kr, kc = T.filter_num_sparse_mat(mat, rt, ct)
         barcodes = [barcodes[i] for i in kr]; features = [features[j] for j in kc]
+    if a.matrix_output:                                          # "filtered and normalized (not including TfIdfNorm)", Program/MakeTree.hs:342
+        T.write_matrix_like(os.path.join(a.output, a.matrix_output), mat, barcodes, features)
     if a.normalization not in ("TfIdfNorm", "NoneNorm"):
         raise SystemExit("only TfIdfNorm (default) and NoneNorm are on the accelerated path")
     if a.dense:                                                  # hSpecCommand True: sparseToHMat, then the dense entry point
