@@ -11,7 +11,8 @@ rows x steps (= SpMV work):
   certified      the rule above with delta = theta_1(T) - theta_2(T) - r_2 from the Ritz values, r_2 < delta / 4, nodes of >= MINM cells
   cert_wrong     nodes where the certified stop would have produced a label different from the converged one (must be 0)
 
-Measured (round 1, this container):   default tree   `small` certified 0.67 / sign_stable 0.39 / tol1e-6 0.73, cert_wrong 0
+Measured (round 1, this container):   default tree   c1 certified 0.64 / sign_stable 0.39 / tol1e-6 0.72, cert_wrong 0
+                                                     `small` 0.67 / 0.39 / 0.73, 0 wrong
                                       saturated      `tiny`  0.77 / 0.41 / 0.77, 0 wrong;  `small` 0.78 / 0.44 / 0.77, 0 wrong
   Without the size floor (MINM=0) the rule fails on a handful of 6-12-cell nodes whose theta2 and theta3 are nearly degenerate
   (the Krylov space is then almost the whole space and the second Ritz value still far from theta3): hence MINM = 64.
