@@ -84,6 +84,16 @@ b = sp.csr_matrix((rng.random((80, 40)) < 0.3).astype(np.float64)); b = b[np.asa
 tb = T.hierarchical_spectral_cluster(b, eigen_group="KMeansGroup", num_eigen=2, num_runs=4)
 ob = O.hierarchical_spectral_cluster(b, eigen_group="KMeansGroup", num_eigen=2, num_runs=4)
 expect("KMeansGroup + numRuns on a binary matrix", tb.leaf_sets() == ob.leaf_sets(), f"nodes {tb.n_nodes} / {ob.n_nodes}")
+# -- --matrix-output -> --matrix-path round trip through the GPU MatrixMarket parser, with values in every notation repr() produces
+with __import__("tempfile").TemporaryDirectory() as td:
+    d = np.zeros((6, 5)); d[0, 0] = 1e-05; d[1, 2] = 0.1 + 0.2; d[2, 4] = 12345678.9; d[3, 1] = 3.0; d[4, 3] = 2.5e+17; d[5, 0] = 7.0
+    m0 = sp.csr_matrix(d)
+    T.write_matrix_like(os.path.join(td, "mo"), m0, [f"BC{i}-1" for i in range(6)], [f"G{j}" for j in range(5)])
+    m1, bcs, fts = T.load_cellranger_data(os.path.join(td, "mo"))
+    expect("write_matrix_like -> load_cellranger_data round trip", m1.shape == m0.shape and np.array_equal(m1.toarray(), m0.toarray())
+           and bcs == [f"BC{i}-1" for i in range(6)] and fts == [f"G{j}" for j in range(5)], str(m1.toarray().tolist()))
+    mm, bb, ff = T.load_all([os.path.join(td, "mo"), os.path.join(td, "mo")])
+    expect("two --matrix-path with equal features stack", mm.shape == (12, 5) and np.array_equal(mm.toarray()[6:], m0.toarray()) and len(bb) == 12)
 # -- the C++ host layer's variant overloads (tests/helpers/host_cpp_example.cpp, mode "variants")
 import subprocess, tempfile
 with tempfile.TemporaryDirectory() as td:
