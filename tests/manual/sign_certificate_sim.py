@@ -14,6 +14,8 @@ rows x steps (= SpMV work):
 Measured (round 1, this container):   default tree   c1 certified 0.64 / sign_stable 0.39 / tol1e-6 0.72, cert_wrong 0
                                                      `small` 0.67 / 0.39 / 0.73, 0 wrong
                                       saturated      `tiny`  0.77 / 0.41 / 0.77, 0 wrong;  `small` 0.78 / 0.44 / 0.77, 0 wrong
+                                      other shapes   binarised 3000 x 8000 (scATAC-like) 0.66 / 0.36 / 0.72, 0 wrong;  deeper planted
+                                                     hierarchy 4000 x 6000, depth 7 (377 nodes) 0.73 / 0.37 / 0.74, 0 wrong
   Without the size floor (MINM=0) the rule fails on a handful of 6-12-cell nodes whose theta2 and theta3 are nearly degenerate
   (the Krylov space is then almost the whole space and the second Ritz value still far from theta3): hence MINM = 64.
 
