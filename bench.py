@@ -313,7 +313,8 @@ def main():
             "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roof,
             "tree": {"nodes": tr.n_nodes, "leaves": int(len(tr.leaves())), "sweeps": tr.stats["n_sweeps"],
-                     "lanczos_steps": int(tr.iters.sum()), "engine_ms_last": tr.stats["engine_ms"], "gen_s": gen_s}}
+                     "lanczos_steps": int(tr.iters.sum()), "engine_ms_last": tr.stats["engine_ms"], "gen_s": gen_s,
+                     "hash": tr.tree_hash()}}
     if not args.no_cpu_baseline and world == 1:          # reported on rank 0 at N=1 only
         ms_c, ns, nnz_c, desc, all_cores = cpu_reference_run(name, args.cpu_sample_cells)
         line["cpu_baseline"] = {"value": ms_c, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc, "all_cores": all_cores}

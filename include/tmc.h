@@ -71,7 +71,10 @@ typedef struct {
   int32_t device;           /* CUDA device ordinal, -1 = current */
   int32_t profile;          /* 1 = time the SpMV kernels with CUDA events (fills tmc_tree.spmv_ms) */
   int32_t scatter_mode;     /* y = B^T x: 0 = column-sorted transposed copy per node (default), 1 = CSR scatter with fp64 atomics */
-  int32_t reserved[5];
+  int32_t sign_stop;        /* 0 = default: a node's Lanczos iteration stops as soon as every label (the sign of every entry of
+                               u2) is certified final -- min_i |x_i| > 4 r / gap for the Ritz vector x (Davis-Kahan) --
+                               instead of running on to `tol`; -1 = off (always iterate to `tol`).  The tree is the same either way. */
+  int32_t reserved[4];
 } tmc_opts;
 
 /* Result tree: flat, pre-order (node 0 = root, children [label 0, label 1]) exactly as

@@ -344,3 +344,99 @@ def test_lsa_truncated_svd_vs_lapack(tiny):
             if gap / ss[0] > 1e-6:
                 assert abs(abs(u[:, i] @ uu[:, i]) - 1.0) < 1e-7, (n_dim, i)
         assert np.allclose(u.T @ u, np.eye(n_dim), atol=1e-8)
+
+
+# ----------------------------------------------------------------------------- BASELINE configs at their stated size
+def _c1():
+    ip, ix, dv, _ = synth.synth_config("c1")
+    n, g = synth.CONFIGS["c1"][:2]
+    return sp.csr_matrix((dv, ix, ip), shape=(n, g))
+
+
+def _oracle_signature(ot):
+    """tree_signature of an OracleTree (items per vertex) through the same canonical form."""
+    begin, end, perm = [0] * ot.n_nodes, [0] * ot.n_nodes, []
+    def rec(i):
+        begin[i] = len(perm)
+        if ot.left[i] < 0:
+            perm.extend(int(x) for x in ot.items[i])
+        else:
+            rec(ot.left[i]); rec(ot.right[i])
+        end[i] = len(perm)
+    rec(0)
+    return T.tree_signature(ot.left, ot.right, begin, end, perm)
+
+
+def test_config1_full_tree_vs_oracle_and_port():
+    """BASELINE.json configs[0] (5k cells x 20k genes) at full size: the whole tree against the exact-math oracle (LAPACK /
+    ARPACK, ~20 s) and against the C port of the reference's CPU path at the same tolerance (~3 s)."""
+    import tmc_port as P
+    a = _c1()
+    tree = T.hierarchical_spectral_cluster(a, normalize=True)
+    ot = O.hierarchical_spectral_cluster(a, normalize=True)
+    assert tree.leaf_sets() == ot.leaf_sets() and same_tree(tree, ot)
+    assert tree.tree_hash() == _oracle_signature(ot)
+    qo = {tuple(sorted(int(x) for x in ot.items[i])): ot.q[i] for i in range(ot.n_nodes)}
+    for i in range(tree.n_nodes):
+        key = tuple(sorted(int(x) for x in tree.items(i)))
+        if len(key) >= 2:
+            assert abs(tree.q[i] - qo[key]) <= 1e-9 * max(1.0, abs(qo[key])) + 1e-12      # north_star allows 1e-5 relative
+    pt = P.make_tree(a, normalize=True, tol=1e-10)
+    assert T.tree_signature(pt.left, pt.right, pt.begin, pt.end, pt.perm) == tree.tree_hash()
+    # the sign-certified stop and the plain tolerance stop build the same tree, the former with fewer Lanczos steps
+    t_tol = T.hierarchical_spectral_cluster(a, normalize=True, sign_stop=False)
+    assert t_tol.tree_hash() == tree.tree_hash()
+    assert np.max(np.abs(t_tol.q - tree.q)) < 1e-12            # Q is a function of the labels only
+    assert int(tree.iters.sum()) < 0.9 * int(t_tol.iters.sum())
+
+
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_sign_certified_stop_same_tree(name, golden_tiny, golden_small):
+    a, _ = golden_tiny if name == "tiny" else golden_small
+    for mm in (0.0, -1.0):          # the default tree and the saturated one (every cell its own leaf)
+        t_cert = T.hierarchical_spectral_cluster(a, normalize=True, min_modularity=mm)
+        t_tol = T.hierarchical_spectral_cluster(a, normalize=True, min_modularity=mm, sign_stop=False)
+        assert t_cert.tree_hash() == t_tol.tree_hash(), (name, mm)
+        assert np.max(np.abs(t_cert.q - t_tol.q)) < 1e-12
+        assert int(t_cert.iters.sum()) <= int(t_tol.iters.sum())
+
+
+def test_run_to_run_reproducible_tree_and_q(golden_small):
+    """SURVEY 8(e) determinism clause: the feature-dimension sums use fp64 atomics (summation order varies from run to run), so
+    eigenvector entries agree to rounding, not bit for bit; labels only depend on signs that are certified with a margin
+    (sign_stop) or converged to 1e-10, hence the TREE is identical run to run and Q (a function of the labels) agrees to 1e-12."""
+    a, _ = golden_small
+    runs = [T.hierarchical_spectral_cluster(a, normalize=True) for _ in range(3)]
+    assert len({t.tree_hash() for t in runs}) == 1
+    for t in runs[1:]:
+        assert np.max(np.abs(t.q - runs[0].q)) <= 1e-12
+
+
+def test_full_size_config2_vs_port_and_arpack():
+    """BASELINE.json configs[1] at full size (100k x 30k, 1.75e8 nnz): the root's u2 / theta / Q against the exact-math oracle
+    (ARPACK at 1e-14 on the host copy) and the WHOLE tree against the C port of the reference's CPU path (all host cores)."""
+    import os
+    import torch
+    import tmc_port as P
+    n, g, k, d, s, binary = synth.CONFIGS["c2"]
+    dev = torch.device("cuda", 0)
+    rp, col, val = synth.synth_counts_torch(n, g, k, d, s, dev, binary)
+    a = sp.csr_matrix((val.cpu().numpy(), col.cpu().numpy(), rp.cpu().numpy()), shape=(n, g))
+    b = T.DeviceB.adopt_device(n, g, rp, col, val, normalize=True, device=0)
+    tree = T.hierarchical_spectral_cluster(b)
+    u2, th, it = T.second_left(b)
+    b.free()
+    T._lib.load().tmc_cache_clear()
+    del rp, col, val
+    torch.cuda.empty_cache()
+    bn = O.b2_to_b(O.b1_to_b2(a))
+    lab, uo, tho, gap, _ = O.spectral_cluster(bn)
+    sgn = 1.0 if u2 @ uo >= 0 else -1.0
+    assert abs(th - tho) <= 1e-10 * tho
+    assert np.linalg.norm(sgn * u2 - uo) <= 1e-7                        # unit vectors; north_star: entries within 1e-5 relative
+    glab = (u2 >= 0).astype(np.int8)
+    assert np.array_equal(glab, lab) or np.array_equal(1 - glab, lab)      # identical root bipartition (up to the sign of u2)
+    assert abs(tree.q[0] - O.get_b_modularity(lab, bn)) <= 1e-10
+    pt = P.make_tree(a, normalize=True, tol=1e-10, threads=min(os.cpu_count() or 1, 32))
+    assert pt.n_nodes == tree.n_nodes
+    assert T.tree_signature(pt.left, pt.right, pt.begin, pt.end, pt.perm) == tree.tree_hash()

@@ -178,3 +178,46 @@ def test_oracle_variants_match_golden(golden_tiny):
     sat = O.hierarchical_spectral_cluster(a[:60], normalize=True, num_runs=10, min_modularity=-1.0, seed=7)
     assert np.array_equal(np.array(sat.left), z["sat_left"])
     assert np.array_equal(np.array([np.nan if x is None else x for x in sat.p_val]), z["sat_p_val"], equal_nan=True)
+
+
+def test_port_and_oracle_agree_on_config1_through_the_tree_signature():
+    """BASELINE.json configs[0] at full size on the CPU: the C port (Lanczos, 1e-10) and the exact-math oracle build the same
+    tree; `tree_signature` (the hash bench.py prints and compares across rank counts) sees them as equal and tells a
+    different tree apart."""
+    import scipy.sparse as sp
+    import tmc_port as P
+    import too_many_cells_b200 as T
+    from too_many_cells_b200 import synth
+    ip, ix, dv, _ = synth.synth_config("c1")
+    n, g = synth.CONFIGS["c1"][:2]
+    a = sp.csr_matrix((dv, ix, ip), shape=(n, g))
+    pt = P.make_tree(a, normalize=True, tol=1e-10)
+    ot = O.hierarchical_spectral_cluster(a, normalize=True)
+    assert pt.leaf_sets() == ot.leaf_sets()
+    begin, end, perm = [0] * ot.n_nodes, [0] * ot.n_nodes, []
+    def rec(i):
+        begin[i] = len(perm)
+        if ot.left[i] < 0:
+            perm.extend(int(x) for x in ot.items[i])
+        else:
+            rec(ot.left[i]); rec(ot.right[i])
+        end[i] = len(perm)
+    rec(0)
+    sig_o = T.tree_signature(ot.left, ot.right, begin, end, perm)
+    sig_p = T.tree_signature(pt.left, pt.right, pt.begin, pt.end, pt.perm)
+    assert sig_o == sig_p
+    # swapping the children of the root leaves the signature alone; moving one cell to another leaf changes it
+    l2, r2 = list(ot.left), list(ot.right)
+    l2[0], r2[0] = r2[0], l2[0]
+    b2, e2, p2 = [0] * ot.n_nodes, [0] * ot.n_nodes, []
+    def rec2(i):
+        b2[i] = len(p2)
+        if l2[i] < 0:
+            p2.extend(int(x) for x in ot.items[i])
+        else:
+            rec2(l2[i]); rec2(r2[i])
+        e2[i] = len(p2)
+    rec2(0)
+    assert T.tree_signature(l2, r2, b2, e2, p2) == sig_o
+    p3 = list(perm); p3[0], p3[-1] = p3[-1], p3[0]
+    assert T.tree_signature(ot.left, ot.right, begin, end, p3) != sig_o

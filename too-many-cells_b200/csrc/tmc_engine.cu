@@ -75,7 +75,7 @@ struct Nccl {
   }
 };
 static Nccl g_nccl;
-enum { NCCL_UINT8 = 1, NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MIN = 3 };
+enum { NCCL_UINT8 = 1, NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3 };
 #include "tmc_p2p.cuh"      // one-shot all-reduce over NVLink peer memory (TMC_P2P=1; off by default until validated on hardware)
 
 // ----------------------------------------------------------------------------- device matrix
@@ -176,6 +176,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
   int K = std::max(2, (int)std::min<int64_t>(o.max_lanczos > 0 ? o.max_lanczos : 320, b->n_rows_global));
   int max_active = (int)std::min<int64_t>(std::max<int64_t>(1, b->n_rows_global / 2), o.max_active > 0 ? o.max_active : 2048);
   max_active = std::min(max_active, 4096);
+  if (b->replicated && g_nccl.world > 1) max_active = std::max(max_active, 2);      // one shared + one private slot at least
   const int use_t = (o.scatter_mode == 0);
   if (b->ws && b->ws->K == K && b->ws->max_active == max_active && b->ws->use_t == use_t && b->ws->vt == b->vt) return b->ws;
   delete b->ws; b->ws = nullptr;
@@ -215,6 +216,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     c.n_vchunks = w->A<int>(1);
     c.err = w->A<int>(1);
     c.stats = w->A<unsigned long long>(4);
+    c.certmin = w->A<unsigned long long>(max_active);
     w->d_act = w->A<Activation>(max_active);
     c.use_t = use_t;
     if (c.use_t) {      // transposed per-node blocks, double buffered (children are written to the other buffer)
@@ -224,7 +226,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
       w->tn = (int64_t)tn;
       for (int q = 0; q < 2; ++q) { c.tcol[q] = w->A<int32_t>(tn); c.tpos[q] = w->A<int32_t>(tn); c.tval[q] = w->A<char>(tn * vsz + 64); }
       w->rowid_scratch = w->A<int32_t>(tn);
-      w->tcap = 32768 + max_active + 64;
+      w->tcap = 32768 + 2 * max_active + 64;      // every slot can add up to two partial chunks
       c.tchunks = w->A<TChunk>(w->tcap); c.n_tchunks = w->A<int>(1);
       c.tile_cnt = w->A<int>(w->tcap); c.tile_off = w->A<long long>(w->tcap);
       c.newpos = w->A<int>(m);
@@ -260,6 +262,18 @@ static int err_to_status(int e, std::string* msg) {
   }
 }
 
+// Row-block inputs under a communicator: a device error code raised on one rank (zero-norm row, column out of range, ...)
+// must be seen by every rank, or the others would go on and wait forever in the first collective of the tree build.
+static int agree_error(const tmc_matrix* b, int e) {
+  if (!(g_nccl.comm && g_nccl.world > 1 && !b->replicated)) return e;
+  int* d = dalloc<int>(1);
+  cudaMemcpy(d, &e, sizeof(int), cudaMemcpyHostToDevice);
+  const int r = g_nccl.AllReduce(d, d, 1, NCCL_INT32, NCCL_MAX, g_nccl.comm, 0);
+  cudaMemcpy(&e, d, sizeof(int), cudaMemcpyDeviceToHost); cudaFree(d);
+  if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(error code) failed");
+  return e;
+}
+
 // normalise the device values in place: optional idf (b1ToB2), then row L2 (b2ToB)
 static void normalise_dev(tmc_matrix* b, int normalize, double* norm_out_dev, double* idf_out_dev, bool do_l2) {
   int* d_err = dalloc<int>(1);
@@ -286,6 +300,7 @@ static void normalise_dev(tmc_matrix* b, int normalize, double* norm_out_dev, do
     if (df) cudaFree(df);
     if (idf && !idf_out_dev) cudaFree(idf);
     df = nullptr; idf = nullptr;
+    e = agree_error(b, e);
     std::string msg;
     int st = err_to_status(e, &msg);
     if (st != TMC_OK) throw TmcError(st, msg);
@@ -376,7 +391,7 @@ static void panel_bufs_take(tmc_matrix* b, size_t need_panel, size_t need_rp, si
 // CSR, written to new arrays -- the caller's arrays are never modified.  On return (true) b->P/Ppad/panel/row_ptr_r/col_r/nnz_r
 // are set, valc holds the residual values and w2col/invw follow the new column order.  Returns false when no panel pays off.
 static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev, int* d_flags, int nib) {
-  if (getenv("TMC_NO_PANEL") || b->nnz == 0 || b->n_cols < 64) return false;
+  if (getenv("TMC_NO_PANEL") || b->n_cols < 64) return false;      // rank-agreed conditions only: a collective follows
   const double density = getenv("TMC_PANEL_DENSITY") ? atof(getenv("TMC_PANEL_DENSITY")) : 0.07;
   if (!(density > 0.0)) return false;
   const int n = (int)b->n_cols;
@@ -497,6 +512,8 @@ static void renumber_columns(tmc_matrix* b) {
 }
 
 static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
+  if (b->n_rows_global < 1) throw TmcError(TMC_ERR_INVALID, "empty matrix (reference: error, LoadMatrix.hs:255)");
+  if (b->n_cols < 1) throw TmcError(TMC_ERR_ZERO_ROW, "matrix without features: every row has zero norm");
   renumber_columns(b);
   int* d_flags = dalloc<int>(6);          // [0] value flags, [1] error code, [2..5] two 64-bit counters of small values
   int* df = nullptr; double* idf = nullptr;
@@ -507,6 +524,13 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
   try {
     CK(cudaMemset(d_flags, 0, 6 * sizeof(int)));
     const int grid = 148 * 8;
+    if (!b->owns) {          // adopted device arrays (a host CSR was checked in validate_csr)
+      int bad = 0;
+      k_check_row_ptr<<<(unsigned)(b->n_rows / 256 + 1), 256>>>(b->row_ptr, b->n_rows, b->nnz, d_flags);
+      CK(cudaMemcpy(&bad, d_flags, sizeof(int), cudaMemcpyDeviceToHost));
+      CK(cudaMemset(d_flags, 0, sizeof(int)));
+      if (agree_error(b, bad)) throw TmcError(TMC_ERR_INVALID, "row_ptr is not a non-decreasing sequence from 0 to nnz");
+    }
     unsigned long long* d_small = reinterpret_cast<unsigned long long*>(d_flags + 2);
     k_scan_values<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, d_flags, d_small);
     int f[2] = {0, 0};
@@ -617,6 +641,7 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     if (df) cudaFree(df);
     if (idf) cudaFree(idf);
     df = nullptr; idf = nullptr;
+    f[1] = agree_error(b, f[1]);
     if (f[1]) { std::string msg; int st = err_to_status(f[1], &msg); throw TmcError(st, msg); }
   } catch (...) {
     restore_val();
@@ -633,6 +658,8 @@ static void validate_csr(const tmc_csr* a) {
   if (a->n_rows < 0 || a->n_cols < 0 || a->nnz < 0) throw TmcError(TMC_ERR_INVALID, "negative dimension");
   if (a->n_rows >= (int64_t)1 << 31 || a->n_cols >= (int64_t)1 << 31) throw TmcError(TMC_ERR_INVALID, "dimension exceeds int32");
   if (a->row_ptr[0] != 0 || a->row_ptr[a->n_rows] != a->nnz) throw TmcError(TMC_ERR_INVALID, "row_ptr does not span [0, nnz]");
+  for (int64_t i = 0; i < a->n_rows; ++i)
+    if (a->row_ptr[i + 1] < a->row_ptr[i]) throw TmcError(TMC_ERR_INVALID, "row_ptr is not non-decreasing");
   if (a->n_rows_global != 0 && (a->row_offset < 0 || a->row_offset + a->n_rows > a->n_rows_global))
     throw TmcError(TMC_ERR_INVALID, "row block outside [0, n_rows_global)");
 }
@@ -760,10 +787,17 @@ struct Engine {
     c.min_modularity = o.min_modularity; c.min_size = std::max(1, o.min_size);
     c.max_restarts = o.max_restarts >= 0 ? o.max_restarts : 8; c.seed = o.seed;
     c.xs_min_rows = getenv("TMC_XS_ROWS") ? atoi(getenv("TMC_XS_ROWS")) : 8192;
+    // sign-certified stop (tmc_opts.sign_stop: 0 = on, -1 = off; TMC_NO_CERT=1 switches it off too)
+    c.cert_on = (o.sign_stop >= 0 && getenv("TMC_NO_CERT") == nullptr) ? 1 : 0;
+    c.cert_min_rows = getenv("TMC_CERT_MIN_ROWS") ? atoi(getenv("TMC_CERT_MIN_ROWS")) : 64;
+    c.cert_safe = getenv("TMC_CERT_SAFE") ? atof(getenv("TMC_CERT_SAFE")) : 4.0;
     c.rank = g_nccl.comm ? g_nccl.rank : 0; c.world = g_nccl.comm ? g_nccl.world : 1;
     hstate.assign(w->max_active, ST_IDLE); slot_node.assign(w->max_active, -1);
     rmode = b->replicated && c.world > 1 && c.use_t;
+    // replicated mode needs at least one private slot, or handed-off subtrees could never be placed (get_workspace keeps
+    // max_active >= 2 under a communicator)
     n_shared_slots = rmode ? std::max(1, std::min(256, w->max_active / 2)) : w->max_active;
+    if (rmode && n_shared_slots >= w->max_active) throw TmcError(TMC_ERR_INVALID, "internal: no private slot in replicated mode");
     for (int i = 0; i < n_shared_slots; ++i) free_slots.push(i);
     for (int i = n_shared_slots; i < w->max_active; ++i) free_priv.push(i);
     handoff_rows = getenv("TMC_HANDOFF_ROWS") ? atoi(getenv("TMC_HANDOFF_ROWS")) : 8192;
@@ -786,7 +820,7 @@ struct Engine {
     const int m = (int)b->n_rows;
     if (!rows) {
       const int cnt = rmode ? (int)(b->own_hi - b->own_lo) : m, off = rmode ? (int)b->own_lo : 0;
-      k_iota<<<(cnt + 255) / 256, 256, 0, s>>>(c.perm, cnt, off);
+      if (cnt > 0) k_iota<<<(cnt + 255) / 256, 256, 0, s>>>(c.perm, cnt, off);
     } else {
       std::vector<int> h(n_sel);
       for (int64_t i = 0; i < n_sel; ++i) {
@@ -921,13 +955,15 @@ struct Engine {
   void sweep(bool only_spmv = false) {
     int n_sc = 0, n_ga = 0, n_mod = 0, n_or = 0, n_deg = 0, live_n = 0; int64_t rows = 0;
     // collectives are issued from the SHARED slots' states only (identical on every rank); private slots never communicate
-    int sh_sc = 0, sh_or = 0, sh_live = 0, hi_shared = 0;
+    int sh_sc = 0, sh_or = 0, sh_live = 0, hi_shared = 0, n_lan = 0, sh_lan = 0;
     for (int sl = 0; sl < hi_slot; ++sl) {
       int st = hstate[sl];
       if (st < ST_DEG || st > ST_MOD) continue;
       live_n++;
+      if (st == ST_LAN) n_lan++;
       if (sl < n_shared_slots) {
         sh_live++; hi_shared = sl + 1;
+        if (st == ST_LAN) sh_lan++;
         if (st == ST_DEG || st == ST_LAN || st == ST_MOD) sh_sc++;
         if (st == ST_ORTH0 || st == ST_LAN) sh_or++;
       }
@@ -1054,6 +1090,11 @@ struct Engine {
     if (n_or && nvch) { k_update<<<nvch, 256, upd_smem, s>>>(c, 1); n_launch++; mark(PH_UPDATE); }
     k_finish<<<(hi_slot + TMC_FINISH_WARPS - 1) / TMC_FINISH_WARPS, 32 * TMC_FINISH_WARPS, sizeof(double) * TMC_FINISH_WARPS * 5 * (c.K + 2), s>>>(c); n_launch++;
     mark(PH_FINISH);
+    if (c.cert_on && n_lan && nvch) {        // sign-certified stop: min |x_i| of the Ritz vectors k_finish asked about
+      k_cert_probe<<<nvch, 256, 0, s>>>(c); n_launch++;
+      if (c.collectives && sh_lan)           // a shared node's cells are spread over the ranks
+        nccl_check(g_nccl.AllReduce(c.certmin, c.certmin, (size_t)hi_shared, NCCL_FLOAT64, NCCL_MIN, g_nccl.comm, s), "ncclAllReduce(min |x|)");
+    }
     if (nvch) { k_advance<<<nvch, 256, 0, s>>>(c); n_launch++; mark(PH_ADVANCE); }
     if (n_mod) {                                                             // local: every rank splits its own cells
       k_partition<<<hi_slot, 1024, 0, s>>>(c); n_launch++;
@@ -1164,7 +1205,11 @@ struct Engine {
         for (int sl = 0; sl < std::min(hi_slot, n_shared_slots) && !shared_left; ++sl) shared_left = hstate[sl] >= ST_DEG && hstate[sl] <= ST_MOD;
         if (!shared_left) c.collectives = 0;
       }
-      if (!live()) break;
+      if (!live()) {
+        if (!pending.empty() || !pending_priv.empty() || !handoff_list.empty())
+          throw TmcError(TMC_ERR_CUDA, "internal: nodes left in the queue with no slot to run them");
+        break;
+      }
       sweep();
       const double t0 = phase_prof ? now_ms() : 0.0;
       harvest(true);
@@ -1344,8 +1389,9 @@ static int make_tree_sweeps(tmc_matrix* b, const tmc_opts* opts_in, tmc_tree** o
     check_opts(opts);
     if (b->n_rows_global < 1) throw TmcError(TMC_ERR_INVALID, "empty matrix (reference: error, LoadMatrix.hs:255)");
     Engine eng(b, *opts);
-    cudaEvent_t t0, t1;
-    CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+    struct Ev { cudaEvent_t e = nullptr; ~Ev() { if (e) cudaEventDestroy(e); } } ev0, ev1;
+    CK(cudaEventCreate(&ev0.e)); CK(cudaEventCreate(&ev1.e));
+    cudaEvent_t t0 = ev0.e, t1 = ev1.e;
     CK(cudaEventRecord(t0, eng.s));
     const bool dbg = getenv("TMC_DEBUG") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1365,7 +1411,6 @@ static int make_tree_sweeps(tmc_matrix* b, const tmc_opts* opts_in, tmc_tree** o
     CK(cudaMemcpyAsync(eng.w->h_stats, eng.c.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, eng.s));
     CK(cudaStreamSynchronize(eng.s));
     float ms = 0; CK(cudaEventElapsedTime(&ms, t0, t1));
-    cudaEventDestroy(t0); cudaEventDestroy(t1);
     // pre-order renumbering, children [label 0, label 1]  (birch-beer treeToGraph, Cluster.hs:171-181).
     // Replicated mode: the subtrees handed to single ranks are serialised by their owners (pre-order records) and
     // exchanged with two small all-reduces; every rank then splices them into the shared top of the tree.
@@ -1398,7 +1443,8 @@ static int make_tree_sweeps(tmc_matrix* b, const tmc_opts* opts_in, tmc_tree** o
       }
     if (nh && hoff[nh]) { eng.allreduce_host_i32(ri); eng.allreduce_host_f64(rd); }
 
-    TreeStorage* ts = new TreeStorage();
+    std::unique_ptr<TreeStorage> ts_owner(new TreeStorage());      // released to the caller only when everything below succeeded
+    TreeStorage* ts = ts_owner.get();
     struct Item { int local; long long rec; int64_t parent; int64_t gbeg; };     // local >= 0: engine node; else record index
     std::vector<Item> stack; stack.push_back(Item{0, -1, -1, 0});
     std::vector<std::pair<int, int64_t>> shared_leaves;      // (engine node, global begin) of leaves whose cells are spread over ranks
@@ -1472,7 +1518,7 @@ static int make_tree_sweeps(tmc_matrix* b, const tmc_opts* opts_in, tmc_tree** o
     // stored bytes the pairs have to move: (value + column index) per CSR entry and half, plus one byte per panel cell and half
     t.spmv_alg_bytes = 2.0 * (bv + 4.0) * (double)(b->P ? (int64_t)eng.w->h_stats[2] : t.spmv_pairs_nnz) + eng.alg_panel_bytes + eng.alg_vec_bytes;
     t.value_bytes = (int32_t)bv;
-    *out = &ts->t;
+    *out = &ts_owner.release()->t;
   });
 }
 

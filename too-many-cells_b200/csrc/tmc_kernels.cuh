@@ -39,6 +39,10 @@ struct Slot {              // one live tree node (device resident)
   long long tnnz0;         // entries of label-0 cells (set by k_tpart_scan): children blocks are [tb, tb+tnnz0) and [tb+tnnz0, te)
   int tchunk0, ntchunk;    // this sweep's chunks of the block (set by k_prepare)
   double sumd, inv_sqrt_sumd, beta, theta, resid, q, theta_hint;
+  // sign-certified stop (DESIGN.md "sign-certified stop"): cert_req = this sweep probes min|x_i| of the tentative Ritz vector;
+  // cert_need = SAFE * r / gap it has to exceed; cert_thr = r / gap below which the next probe is worth its pass over V
+  int cert_req, cert_pad;
+  double cert_need, cert_thr;
 };
 
 struct Report {            // what the host reads back after every sweep
@@ -96,6 +100,8 @@ struct Ctx {
   double tol, min_modularity; int min_size, max_restarts; uint64_t seed;
   int rank, world;
   int collectives;                 // 0 once only private (handed-off) nodes remain: ranks run free
+  // sign-certified stop: certmin[slot] = min_i |x_i| of the probed Ritz vector (bit pattern of a non-negative double, atomicMin)
+  unsigned long long* certmin; int cert_on, cert_min_rows; double cert_safe;
   // truncated-SVD mode (one slot): Ritz vectors of T for the top nev values [nev][K+2], output U [m][nev] (cells x nev), sigma^2 [nev]
   double* zmulti; double* uout; double* ev_out; int* svd_conv;
 };
@@ -241,6 +247,13 @@ __global__ void k_remap_cols(int32_t* __restrict__ col, int64_t nnz, const int* 
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < nnz; i += stride) col[i] = __ldg(rank + col[i]);
+}
+
+// adopted device arrays: row_ptr must be a non-decreasing sequence from 0 to nnz before any kernel walks the rows
+__global__ void k_check_row_ptr(const int64_t* __restrict__ rp, int64_t n_rows, int64_t nnz, int* __restrict__ bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && (rp[0] != 0 || rp[n_rows] != nnz)) atomicOr(bad, 1);
+  if (i < n_rows && rp[i + 1] < rp[i]) atomicOr(bad, 1);
 }
 
 // value scan: validity + can the values be stored as small integers / are they all ones?
@@ -422,6 +435,7 @@ __global__ void k_activate(Ctx c, const Activation* __restrict__ acts, int n) {
   s.split = 0; s.n0 = 0; s.stop_after = a.stop_after;
   s.tpar = a.tpar; s.priv = a.priv; s.nev = a.nev; s.tb = a.tb; s.te = a.te; s.tnnz0 = 0; s.tchunk0 = 0; s.ntchunk = 0;
   s.sumd = 0; s.inv_sqrt_sumd = 0; s.beta = 0; s.theta = 0; s.resid = 0; s.q = 0; s.theta_hint = -1e300;
+  s.cert_req = 0; s.cert_pad = 0; s.cert_need = 0.0; s.cert_thr = 0.02;
   c.st[a.slot] = s;
   slot_scal(c, a.slot)[R_N1] = 0.0; slot_scal(c, a.slot)[R_SD1] = 0.0;
 }
@@ -487,10 +501,15 @@ __global__ void __launch_bounds__(1024) k_prepare(Ctx c) {
   // zero reduction rows (dots of both passes up to j+1, and the scalars): one warp per slot
   for (int slot = wid; slot < c.n_slots; slot += 32) {
     const Slot& s = c.st[slot];
-    if (s.state < ST_DEG || s.state > ST_MOD) continue;
     double* ra = c.redA + (int64_t)slot * (c.K + 2);
     double* rb = slot_redB(c, slot);
     int nv = min(s.j + 2, c.K + 2);
+    if (s.state < ST_DEG || s.state > ST_MOD) {
+      // idle slot below the highest live one: its rows still travel through the per-sweep all-reduces (in place), so they
+      // are kept at zero instead of growing by a factor `world` per sweep
+      if (c.world > 1) { for (int i = lane; i < nv; i += 32) { ra[i] = 0.0; rb[i] = 0.0; } if (lane < R_NSCAL) slot_scal(c, slot)[lane] = 0.0; }
+      continue;
+    }
     for (int i = lane; i < nv; i += 32) { ra[i] = 0.0; rb[i] = 0.0; }
     if (lane < 3) slot_scal(c, slot)[lane] = 0.0;       // NRM2, SUMD, YNORM2 (N1/SD1 persist from the previous sweep)
   }
@@ -1318,11 +1337,12 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
     // bracket from the previous test: theta grows monotonically with j and (when the nearest eigenvalue of T_j is the top
     // one) by no more than the previous residual; both hints are verified with a Sturm count before use
     const double theta = tmc_top_eig_warp(A, B, j, s->theta_hint, (s->theta_hint > -1e299) ? s->theta + 1.0001 * s->resid + 1e-15 : 1e300);
+    int want_cert = 0; double resid = 0.0, piv = 0.0;
     if (lane == 0) {
-      double lo, hi, piv;
+      double lo, hi;
       tmc_gershgorin(A, B, j, &lo, &hi, &piv);
       tmc_twisted_vector(A, B, j, theta, sdp, sdm, sz, piv);
-      double resid = beta * fabs(sz[j - 1]);
+      resid = beta * fabs(sz[j - 1]);
       s->theta = theta; s->resid = resid;
       s->theta_hint = theta - 1e-13 * fmax(1.0, fabs(theta));
       bool conv = exhausted || breakdown || resid <= c.tol * theta || resid <= 1e-14;
@@ -1332,7 +1352,25 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
       } else if (full) {
         s->action = ACT_RITZ_RESTART; s->restarts += 1; s->theta_hint = -1e300;
       } else s->action = ACT_NEXT;
-      if (s->action != ACT_NEXT) { double* z = c.zvec + (int64_t)slot * K2; for (int q = 0; q < j; ++q) z[q] = sz[q]; }   // k_advance forms the Ritz vector
+      // sign-certified stop: worth a look once r / theta (a lower bound of r / gap) is under the slot's probe threshold
+      want_cert = s->action == ACT_NEXT && c.cert_on && s->stop_after == 0 && len >= c.cert_min_rows && j >= 3 && resid < s->cert_thr * theta;
+      if (s->action != ACT_NEXT || want_cert) { double* z = c.zvec + (int64_t)slot * K2; for (int q = 0; q < j; ++q) z[q] = sz[q]; }   // k_advance forms the Ritz vector
+    }
+    want_cert = __shfl_sync(0xffffffffu, want_cert, 0);
+    if (want_cert) {
+      // Davis-Kahan: ||x - u2|| <= ~ r / gap, gap = distance of theta to the rest of the spectrum.  The second Ritz value
+      // bounds that from the Krylov space: gap >= theta - theta_2 - r_2 once r_2 is itself small against the distance.
+      const double th2 = tmc_top_eig_warp(A, B, j, -1e300, theta, 2);
+      if (lane == 0) {
+        tmc_twisted_vector(A, B, j, th2, sdp, sdm, sz, piv);
+        const double r2 = beta * fabs(sz[j - 1]);
+        const double sep = theta - th2, gap = sep - r2;
+        if (gap > 0.0 && r2 < 0.25 * sep && resid < s->cert_thr * gap) {
+          s->cert_req = 1; s->cert_need = c.cert_safe * resid / gap;
+          c.certmin[slot] = 0x7FF0000000000000ull;                 // +inf
+          scal[R_N1] = 0.0; scal[R_SD1] = 0.0;                      // in case the probe succeeds and k_advance labels this sweep
+        }
+      }
     }
     return;
   }
@@ -1360,13 +1398,46 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
   }
 }
 
+// ------------------------------------------------------------------ sign-certified stop
+// The tree needs u2 only through the signs of its entries.  For the Ritz pair (theta, x = V z) with residual r, every label
+// is final once min_i |x_i| > SAFE * r / gap (||x|| = 1: z has unit norm and V is orthonormal).  k_finish requests a probe
+// (cert_req, z in zvec), this kernel reduces min_i |x_i| over the node's positions, k_advance / k_commit act on the outcome.
+__device__ __forceinline__ bool cert_passed(const Ctx& c, int slot, const Slot& s) {
+  return s.cert_req && __longlong_as_double((long long)c.certmin[slot]) > s.cert_need;
+}
+__global__ void __launch_bounds__(256) k_cert_probe(Ctx c) {
+  __shared__ double sm8[8];
+  if ((int)blockIdx.x >= *c.n_vchunks) return;
+  const Chunk ch = c.vchunks[blockIdx.x];
+  const Slot& s = c.st[ch.slot];
+  if (s.state != ST_LAN || !s.cert_req) return;
+  const int j = s.j;
+  const double* __restrict__ z = c.zvec + (int64_t)ch.slot * (c.K + 2);
+  double mn = INFINITY;
+  for (int i = threadIdx.x; i < ch.len; i += 256) {
+    const int p = ch.begin + i;
+    double u = 0.0;
+    for (int l = 1; l <= j; ++l) u += z[l - 1] * c.V[(int64_t)l * c.vstride + p];
+    mn = fmin(mn, fabs(u));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if ((threadIdx.x & 31) == 0) sm8[threadIdx.x >> 5] = mn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < 8; ++q) mn = fmin(mn, sm8[q]);
+    atomicMin(c.certmin + ch.slot, (unsigned long long)__double_as_longlong(mn));      // non-negative doubles order like their bits
+  }
+}
+
 // ------------------------------------------------------------------ per-position transitions
 __global__ void __launch_bounds__(256) k_advance(Ctx c) {
   __shared__ double sm8[8];
   if ((int)blockIdx.x >= *c.n_vchunks) return;
   const Chunk ch = c.vchunks[blockIdx.x];
   const Slot& s = c.st[ch.slot];
-  const int action = s.action;
+  int action = s.action;
+  if (action == ACT_NEXT && cert_passed(c, ch.slot, s)) action = ACT_RITZ_LABEL;      // every label certified: stop here
   if (action == ACT_NONE || action == ACT_FINISH) return;
   if (action == ACT_INIT && s.nev) {      // truncated SVD of B itself: no D^{-1/2}, no deflation (V_0 = 0)
     for (int i = threadIdx.x; i < ch.len; i += 256) {
@@ -1488,6 +1559,14 @@ __global__ void k_commit(Ctx c, int n_slots) {
   if (slot >= n_slots) return;
   Slot* s = c.st + slot;
   int state = s->state;
+  if (s->cert_req) {
+    if (s->action == ACT_NEXT && cert_passed(c, slot, *s)) s->action = ACT_RITZ_LABEL;
+    else {          // the smallest entry decides when the next probe can succeed
+      const double mn = __longlong_as_double((long long)c.certmin[slot]);
+      s->cert_thr = (mn > 0.0 && mn < 1e300) ? fmin(mn / c.cert_safe, 0.5 * s->cert_thr) : 0.0;
+    }
+    s->cert_req = 0;
+  }
   switch (s->action) {
     case ACT_INIT: state = ST_ORTH0; s->j = 0; break;
     case ACT_NEXT: if (state == ST_ORTH0) { state = ST_LAN; s->j = 1; } else s->j += 1; break;

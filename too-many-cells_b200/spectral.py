@@ -53,7 +53,7 @@ class HostCsr:
 
 def make_opts(min_modularity=0.0, min_size=1, normalize=False, eigen_group="SignGroup", num_eigen=1,
               num_runs=0, seed=None, tol=None, max_lanczos=None, max_restarts=None, max_active=None,
-              device=-1, profile=False, scatter_mode=0) -> Opts:
+              device=-1, profile=False, scatter_mode=0, sign_stop=True) -> Opts:
     lib = _lib.load()
     o = Opts()
     lib.tmc_opts_default(C.byref(o))
@@ -76,6 +76,7 @@ def make_opts(min_modularity=0.0, min_size=1, normalize=False, eigen_group="Sign
     o.device = int(device)
     o.profile = int(bool(profile))
     o.scatter_mode = int(scatter_mode)
+    o.sign_stop = 0 if sign_stop else -1      # sign-certified Lanczos stop (tmc.h); False = always iterate to `tol`
     return o
 
 
@@ -272,6 +273,42 @@ class ClusteringTree:
 
     def leaf_sets(self):
         return sorted(tuple(int(x) for x in self.items(i)) for i in self.leaves())
+
+    def tree_hash(self):
+        """Canonical SHA-1 of leaf membership + topology (see `tree_signature`)."""
+        return tree_signature(self.left, self.right, self.item_begin, self.item_end, self.perm)
+
+
+def tree_signature(left, right, begin, end, perm) -> str:
+    """SHA-1 of a flat tree that does not depend on the eigenvector sign (child order), the node numbering or the rank
+    count: every vertex is named by (smallest row id among its cells, number of cells) -- distinct vertices of a tree
+    differ in that pair -- and the hash covers (1) for every cell the name of its leaf (membership) and (2) the sorted
+    list of all vertex names (topology: which sets of leaves are merged).  Two trees have the same signature iff they
+    have identical leaf membership and identical topology up to swapping children."""
+    import hashlib
+    left = np.asarray(left, dtype=np.int64); right = np.asarray(right, dtype=np.int64)
+    begin = np.asarray(begin, dtype=np.int64); end = np.asarray(end, dtype=np.int64); perm = np.asarray(perm, dtype=np.int64)
+    n = left.size
+    mn = np.zeros(n, dtype=np.int64)
+    leaves = np.nonzero(left < 0)[0]
+    order = leaves[np.argsort(begin[leaves], kind="stable")]
+    nonempty = order[end[order] > begin[order]]
+    mn[nonempty] = np.minimum.reduceat(perm, begin[nonempty]) if nonempty.size else 0
+    # reduceat runs to the next start: correct because the leaves tile perm in ascending `begin` order
+    for i in range(n - 1, -1, -1):           # pre-order ids: children come after their parent
+        if left[i] >= 0:
+            mn[i] = min(mn[left[i]], mn[right[i]])
+    sizes = (end - begin)[nonempty]
+    if int(sizes.sum()) != perm.size or (nonempty.size and (begin[nonempty[0]] != 0 or np.any(begin[nonempty][1:] != end[nonempty][:-1]))):
+        raise ValueError("the leaves do not tile perm")
+    leaf_name = np.empty(perm.size, dtype=np.int64)
+    leaf_name[perm] = np.repeat(mn[nonempty], sizes)
+    names = np.stack([mn, end - begin], axis=1)
+    names = names[np.lexsort((names[:, 1], names[:, 0]))]
+    h = hashlib.sha1()
+    h.update(np.ascontiguousarray(leaf_name).tobytes())
+    h.update(np.ascontiguousarray(names).tobytes())
+    return h.hexdigest()
 
 
 def _tree_from_c(tp) -> ClusteringTree:
