@@ -8,16 +8,23 @@ pairs, sign split, modularity, stable row partition) down to the leaves.
   value  : device-resident input (raw counts already in HBM), ms per tree
   e2e    : the same through the host-buffer C-ABI call `tmc_make_tree` (pinned host CSR ->
            H2D -> tree -> D2H of the flat tree), ms per tree
-  roofline: SpMV pair kernels (scatter y=C^T x, gather x'=C y): algorithmic bytes
-            / CUDA-event time of those launches inside the timed steps
-  cpu_baseline / --impl reference: the oracle's CPU implementation of the same path.
+  roofline: SpMV pair kernels (y = C^T x, x' = C y): algorithmic bytes
+           / CUDA-event time of those launches inside the timed steps
+  tree.hash: canonical SHA-1 of leaf membership + topology (too_many_cells_b200.tree_signature); at N > 1 it is
+           asserted equal on every rank and equal to the tree one GPU builds alone (`hash_single_gpu`)
+  cpu_baseline / --impl reference: the C port of the reference's CPU path (oracle/tmc_port.c), MEASURED on a bounded
+           sample of the workload; the b200 arm also measures the GPU on that very sample (`same_input`).
 
-N>1 (torchrun, one rank per GPU): the tree build is row-sharded across ranks with NCCL
-all-reduces of the feature-dimension vectors; total work is fixed => "strong" scaling.
+Workloads (--workload): c1 .. c4 = BASELINE.json configs[0..3]; c5 = configs[4] (the c3 matrix, min_modularity = -1:
+saturated tree, every cell its own leaf).  Default c3 (the config the metric is quoted on).
+
+N>1 (torchrun, one rank per GPU): the tree build is row-sharded across ranks with all-reduces of the
+feature-dimension vectors; total work is fixed => "strong" scaling.
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -30,8 +37,6 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ms per full make-tree"
 UNIT = "ms"
-# ncu dram bytes (read + write) of the root-level SpMV pair on c3, 1 GPU (profiles/, see the roofline comment below)
-TRAFFIC_C3_ROOT_PAIR = 13.84e9
 
 
 def parse():
@@ -40,19 +45,27 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("TMC_BENCH_WORKLOAD", "c3"))
+    ap.add_argument("--workload", default=os.environ.get("TMC_BENCH_WORKLOAD", "c3"), choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--cpu-sample-cells", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-host-types", default="compact", choices=["compact", "f64"],
+                    help="host arrays of the e2e call: uint16 counts / uint16 gene ids where they fit (default), or double / int32")
+    ap.add_argument("--no-verify-hash", action="store_true", help="N > 1: skip building the single-GPU tree the N-rank tree is compared with")
     return ap.parse_args()
 
 
-def workload_desc(name):
+def workload(name):
+    """(synthetic matrix config, engine options, description)"""
     from too_many_cells_b200 import synth
-    n, g, k, d, s, binary = synth.CONFIGS[name]
-    return {"workload": f"{name}: synthetic 10x-like {n} cells x {g} genes, ~{k} nnz/cell, planted depth {d}, seed {s}, "
-                        f"tf-idf + default min-modularity 0 stop",
-            "cells": n, "features": g, "l2": "inputs larger than L2 (CSR >> 126 MB)" if n * k * 12 > 2.5e8 else
-            "matrix smaller than L2; no flush (the tree build re-reads it by design)"}
+    base = "c3" if name == "c5" else name
+    n, g, k, d, s, binary = synth.CONFIGS[base]
+    min_mod = -1.0 if name == "c5" else 0.0
+    stop = "min-modularity -1 (saturated tree: every cell its own leaf)" if name == "c5" else "default min-modularity 0 stop"
+    kind = "binarised scATAC-like" if binary else "10x-like"
+    cfg = {"workload": f"{name}: synthetic {kind} {n} cells x {g} features, ~{k} nnz/cell, planted depth {d}, seed {s}, tf-idf + {stop}",
+           "cells": n, "features": g, "l2": "inputs larger than L2 (CSR >> 126 MB)" if n * k * 12 > 2.5e8 else
+           "matrix smaller than L2; no flush (the tree build re-reads it by design)"}
+    return (n, g, k, d, s, binary), {"min_modularity": min_mod}, cfg
 
 
 class ClockSampler:
@@ -98,48 +111,73 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def cpu_reference_run(name, sample_cells, steps=1, warmup=0):
-    """The reference's CPU execution of the path, restated in C (oracle/tmc_port.c: one node at a time, materialised
-    sub-matrices, single-vector Lanczos at SVDLIBC's kappa = 1e-6, one core like the reference), timed on a bounded sample
-    (the first `sample_cells` cells of the workload) and scaled linearly in cells to the metric's unit.
-    Returns (scaled ms per full-size tree, sample cells, sample nnz, description)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+# ----------------------------------------------------------------------------- the CPU arm (measured, never extrapolated into `value`)
+def cpu_sample(name, sample_cells):
+    """The bounded sample both arms use: the workload's generator at `ns` cells (same genes, seed, density, hierarchy).
+    c1 is taken whole (it IS the reference's CPU-runnable config); larger workloads are cut to `sample_cells` cells and to
+    at most ~2e7 non-zeros so that one CPU step stays within seconds."""
     import scipy.sparse as sp
     from too_many_cells_b200 import synth
-    import tmc_port as P
-    n, g, k, d, s, binary = synth.CONFIGS[name]
-    ns = min(n, sample_cells)
+    (n, g, k, d, s, binary), eng, _ = workload(name)
+    ns = int(min(n, sample_cells, max(500, 2e7 // k)))
     ip, ix, dv, _ = synth.synth_counts(ns, g, k, d, s, binary)
-    a = sp.csr_matrix((dv, ix, ip), shape=(ns, g))
+    return sp.csr_matrix((dv, ix, ip), shape=(ns, g)), n, eng
+
+
+def cpu_reference_run(name, sample_cells, steps=1, warmup=0):
+    """The reference's CPU execution of the path, restated in C (oracle/tmc_port.c: one node at a time, materialised
+    sub-matrices, single-vector Lanczos at SVDLIBC's kappa = 1e-6, one core like the reference — sequential recursion,
+    single-threaded SVDLIBC), timed on the bounded sample.  Returns a dict with the MEASURED ms per step on the sample and,
+    separately and labelled as such, a linear-in-cells extrapolation to the full workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tmc_port as P
+    a, n_full, eng = cpu_sample(name, sample_cells)
+    ns = a.shape[0]
     P._load()          # build / host-compatibility probe of the port happen here, outside the timed region
     times = []
     for it in range(warmup + steps):
         t = time.perf_counter()
-        tr = P.make_tree(a, normalize=True, tol=1e-6)
+        tr = P.make_tree(a, normalize=True, tol=1e-6, min_modularity=eng["min_modularity"])
         dt = time.perf_counter() - t
         if it >= warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    scale = n / ns
-    # second, more generous figure: the same port with its mat-vecs and re-orthogonalisation on every host core (the reference
-    # itself cannot do that: sequential recursion, single-threaded SVDLIBC)
+    scale = n_full / ns
+    # second figure: the same port with its mat-vecs and re-orthogonalisation on every host core (the reference itself cannot
+    # do that); one run
     all_cores = None
     ncpu = min(os.cpu_count() or 1, 32)
     if ncpu > 1:
         t = time.perf_counter()
-        P.make_tree(a, normalize=True, tol=1e-6, threads=ncpu)
-        all_cores = {"value": 1e3 * (time.perf_counter() - t) * scale, "unit": "ms", "cores": ncpu,
-                     "note": "pthread mode of the port (not something the reference can do); same sample, same scaling"}
+        P.make_tree(a, normalize=True, tol=1e-6, min_modularity=eng["min_modularity"], threads=ncpu)
+        all_cores = {"value": 1e3 * (time.perf_counter() - t), "unit": "ms", "cores": ncpu,
+                     "note": "pthread mode of the port (not something the reference can do); same sample, measured"}
         P.make_tree(a[:50], normalize=True, tol=1e-6, threads=1)      # back to the 1-thread pool
-    desc = (f"C port of the reference's CPU path (oracle/tmc_port.c: sequential recursion, per-node materialised matrices, "
-            f"Lanczos at las2's kappa=1e-6, 1 thread like the reference; the Haskell binary cannot be built here) on the first "
-            f"{ns} cells x {g} genes of {name} ({a.nnz} nnz, {tr.n_nodes} nodes, {tr.steps} Lanczos steps): {ms:.0f} ms measured, "
-            f"scaled x{scale:.0f} linearly in cells to the full workload (conservative: the full tree is deeper)")
-    return ms * scale, ns, a.nnz, desc, all_cores
+    whole = ns == n_full
+    desc = (f"C port of the reference's CPU path (oracle/tmc_port.c: sequential recursion, per-node materialised matrices, Lanczos at "
+            f"las2's kappa=1e-6, 1 thread like the reference; the Haskell binary cannot be built here) on "
+            f"{'the whole workload' if whole else f'a {ns}-cell sample of the workload (same generator, genes, seed)'}: "
+            f"{ns} cells x {a.shape[1]} features, {a.nnz} nnz, {tr.n_nodes} nodes, {tr.steps} Lanczos steps, {ms:.0f} ms measured per tree")
+    return {"ms": ms, "cells": ns, "nnz": int(a.nnz), "scale": scale, "desc": desc, "all_cores": all_cores, "matrix": a, "eng": eng,
+            "whole": whole, "nodes": tr.n_nodes}
 
 
-def tr_bv(trees):
-    return float(trees[-1].stats["value_bytes"])
+def ncu_traffic(name, storage_bits):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the root-level SpMV pair launches, read from the newest committed
+    ncu summary (profiles/*_root_pair_traffic.json, written by tools/ncu_summary.py from an `ncu --set full` capture of
+    tools/prof_pair.py).  None when no capture matches the workload / storage format."""
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_root_pair_traffic.json"))):
+        try:
+            d = json.load(open(path))
+        except Exception:
+            continue
+        if d.get("workload") == name and d.get("panel_bits") == storage_bits:
+            best = (d, os.path.relpath(path, ROOT))
+    if not best:
+        return None, None
+    d, path = best
+    return float(d["pair_dram_bytes"]), {"source": path, "kernels": d.get("kernels")}
 
 
 def main():
@@ -148,18 +186,24 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     name = args.workload
-    cfg = workload_desc(name)
+    (n, g, k, d, s, binary), eng, cfg = workload(name)
 
     if args.impl == "reference":
+        # Rank 0 alone times the CPU path (the other ranks have nothing to do).  `value` is what was MEASURED: ms per tree on
+        # the bounded sample named in config.reference_sample; the linear extrapolation to the full workload is a separate,
+        # labelled key and is never reported as the value.
         if rank != 0:
             return
-        ncores = 1          # the reference path is sequential; the port uses one thread
-        ms, ns, nnz, desc, all_cores = cpu_reference_run(name, args.cpu_sample_cells, steps=max(1, args.steps), warmup=min(args.warmup, 1))
-        line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": cfg,
-                "cpu_baseline": {"value": ms, "unit": UNIT, "cores": ncores, "kind": "port", "sample": desc, "all_cores": all_cores},
-                "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        r = cpu_reference_run(name, args.cpu_sample_cells, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": r["ms"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": dict(cfg, reference_sample=("whole workload" if r["whole"] else f"{r['cells']} of {n} cells ({r['nnz']} nnz); value is the measured time of THIS sample"),
+                               reference_sample_cells=r["cells"]),
+                "cpu_baseline": {"value": r["ms"], "unit": UNIT, "cores": 1, "kind": "port", "sample": r["desc"], "all_cores": r["all_cores"]},
+                "extrapolated_full_workload_ms": None if r["whole"] else {"value": r["ms"] * r["scale"], "how": f"measured sample time x {r['scale']:.0f} (linear in cells; "
+                                                  "an under-estimate: the full tree is deeper) -- NOT a measurement"},
+                "e2e": {"value": r["ms"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
@@ -172,19 +216,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (libtmc has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    lib = T._lib.load()
-    if world > 1:
-        import torch.distributed as dist
-        from too_many_cells_b200 import dist as tdist
-        dist.init_process_group("nccl", device_id=dev)
-        tdist.init_comm(rank, world, local_rank, dev)          # libtmc's own NCCL communicator (ids travel over torch.distributed)
+    T._lib.load()
 
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
-    n, g, k, d, s, binary = synth.CONFIGS[name]
     t0 = time.time()
     # Every rank holds the WHOLE matrix in HBM (replicated mode: the shared top of the tree is row-sharded over the ranks'
     # blocks [lo, hi), subtrees below the hand-off size go to single ranks); it is generated on the device, identically
@@ -200,9 +233,24 @@ def main():
         work.copy_(val_raw)                       # raw counts resident in HBM; tf-idf + L2 happen inside the step
         torch.cuda.synchronize()
         b = T.DeviceB.adopt_device(n, g, row_ptr, col, work, normalize=True, device=local_rank)
-        tree = T.hierarchical_spectral_cluster(b, profile=profile)
+        tree = T.hierarchical_spectral_cluster(b, profile=profile, **eng)
         b.free()
         return tree
+
+    # N > 1: the tree ONE GPU builds alone (before the communicator exists), to compare the N-rank tree with
+    hash_single = None
+    if world > 1 and not args.no_verify_hash:
+        hash_single = step_dev(False).tree_hash()
+    if world > 1:
+        import torch.distributed as dist
+        from too_many_cells_b200 import dist as tdist
+        dist.init_process_group("nccl", device_id=dev)
+        tdist.init_comm(rank, world, local_rank, dev)          # libtmc's own NCCL communicator (ids travel over torch.distributed)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         step_dev(False)
@@ -222,30 +270,49 @@ def main():
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
         ms_step = float(tt.item())
 
-    # ---- end-to-end through the host-buffer C-ABI (rank 0's numbers; every rank participates when N>1)
+    # the tree of every timed step on every rank must be THE tree: same canonical hash everywhere, equal to the single-GPU one
+    hashes = sorted({t_.tree_hash() for t_ in trees})
+    if world > 1:
+        allh = [None] * world
+        torch.distributed.all_gather_object(allh, hashes)
+        hashes = sorted({h for hs in allh for h in hs})
+    if len(hashes) != 1:
+        raise SystemExit(f"bench.py: ranks / steps disagree about the tree: {hashes}")
+    if hash_single is not None and hashes[0] != hash_single:
+        raise SystemExit(f"bench.py: the {world}-rank tree {hashes[0]} differs from the single-GPU tree {hash_single}")
+
+    # ---- end-to-end through the host-buffer C-ABI (every rank participates when N>1)
     # host CSR: the C ABI reads the full row_ptr and only this rank's block of col/val (then replicates over NVLink), so the
     # arrays are full-size but only the own block is backed by (pinned) memory
+    # Host element types: the make-tree input is a matrix of UMI counts, which the shim marshals as uint16 (and gene indices as
+    # uint16 when they fit) -- tmc_csr.val_type / idx_type; libtmc widens them on the device, results are bit-identical to the
+    # fp64 call (tests/test_gpu_panel.py).  --e2e-host-types f64 times the plain double / int32 arrays instead.
     h_ptr = row_ptr.cpu().pin_memory()
     k0, k1 = int(h_ptr[lo]), int(h_ptr[hi])
-    if world == 1:
-        h_col = col.cpu().pin_memory(); h_val = val_raw.cpu().pin_memory()
-        np_col, np_val = h_col.numpy(), h_val.numpy()
-    else:
-        np_col = np.empty(nnz, dtype=np.int32); np_val = np.empty(nnz, dtype=np.float64)      # untouched pages stay uncommitted
-        np_col[k0:k1] = col[k0:k1].cpu().numpy(); np_val[k0:k1] = val_raw[k0:k1].cpu().numpy()
-        rt = torch.cuda.cudart()
-        rt.cudaHostRegister(np_col[k0:k1].ctypes.data, (k1 - k0) * 4, 0)
-        rt.cudaHostRegister(np_val[k0:k1].ctypes.data, (k1 - k0) * 8, 0)
+    compact = args.e2e_host_types == "compact" and float(val_raw.max().item()) <= 65535.0
+    vdt = np.uint16 if compact else np.float64
+    cdt = np.uint16 if (compact and g <= 65536) else np.int32
+    np_col = np.empty(nnz, dtype=cdt); np_val = np.empty(nnz, dtype=vdt)      # untouched pages stay uncommitted (N > 1: own block only)
+    CH = 1 << 27
+    for o in range(k0, k1, CH):
+        e = min(k1, o + CH)
+        np_col[o:e] = col[o:e].cpu().numpy().astype(cdt); np_val[o:e] = val_raw[o:e].cpu().numpy().astype(vdt)
+    rt = torch.cuda.cudart()
+    if k1 > k0:
+        rt.cudaHostRegister(np_col[k0:k1].ctypes.data, (k1 - k0) * np_col.itemsize, 0)      # pinned host memory
+        rt.cudaHostRegister(np_val[k0:k1].ctypes.data, (k1 - k0) * np_val.itemsize, 0)
     host = (h_ptr.numpy(), np_col, np_val, (n, g))
-    e2e_steps = max(1, min(args.steps, 2))
-    T.hierarchical_spectral_cluster(host, normalize=True, device=local_rank)     # warm
+    e2e_steps = max(1, args.steps)
+    tr_e = T.hierarchical_spectral_cluster(host, normalize=True, device=local_rank, **eng)     # warm
     barrier()
     t = time.perf_counter()
     for _ in range(e2e_steps):
-        tr_e = T.hierarchical_spectral_cluster(host, normalize=True, device=local_rank)
+        tr_e = T.hierarchical_spectral_cluster(host, normalize=True, device=local_rank, **eng)
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t) / e2e_steps
-    h2d = int(h_ptr.numel() * 8 + (k1 - k0) * 12)
+    if tr_e.tree_hash() != hashes[0]:
+        raise SystemExit("bench.py: the host-buffer call built a different tree than the device-resident call")
+    h2d = int(h_ptr.numel() * 8 + (k1 - k0) * (np_col.itemsize + np_val.itemsize))
     d2h = int(tr_e.n_nodes * (8 * 5 + 8 * 2 + 4) + n * 8)
     if world > 1:
         th = torch.tensor([h2d], device=dev, dtype=torch.int64)
@@ -273,51 +340,69 @@ def main():
     achieved = alg / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
     # the same launches counted with the nominal fp64 value size of SURVEY.md 8(d) (b_v = 8): what a plain fp64 CSR
     # implementation would have to move; reported for context only, `achieved` / `frac` use the bytes actually stored
+    bv = float(tr.stats["value_bytes"])          # 8: fp64 B; 2: raw counts as uint16 + diagonal factors; 0: all-ones matrix
     nnz_pairs = sum(t_.stats["spmv_pairs_nnz"] for t_ in trees)
-    alg_nominal = alg + 2.0 * (8.0 - tr_bv(trees)) * nnz_pairs
+    alg_nominal = alg + 2.0 * (8.0 - bv) * nnz_pairs
     achieved_nominal = alg_nominal / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
     # root-level pair in isolation (largest single launch pair) -- single-rank only
+    root_pair, traffic, traffic_src = None, None, None
     if world == 1:
         work.copy_(val_raw)
         b = T.DeviceB.adopt_device(n, g, row_ptr, col, work, normalize=True, device=local_rank)
         sc_ms, ga_ms = T.bench_spmv_pair(b, 10)
         storage = b.info()
         b.free()
-        bv = tr.stats["value_bytes"]          # 8: fp64 B; 2: raw counts as uint16 + diagonal factors; 0: all-ones matrix
-        # stored bytes of one pair: (value + column index) per residual CSR entry and half, one byte per panel cell and half
+        # stored bytes of one pair: (value + column index) per residual CSR entry and half, the panel cells once per half
         pair_bytes = (2.0 * (bv + 4.0) * storage["residual_nnz"] + 2.0 * n * storage["panel_cols"] * storage["panel_bits"] / 8.0
                       + 16.0 * (n + 1) + 32.0 * n + 16.0 * g)
         root_pair = {"scatter_ms": sc_ms, "gather_ms": ga_ms, "bytes": pair_bytes, "storage": storage,
                      "scatter_gbs": 0.5 * pair_bytes / (sc_ms * 1e-3) / 1e9, "gather_gbs": 0.5 * pair_bytes / (ga_ms * 1e-3) / 1e9}
-    else:
-        root_pair = None
-    # dram__bytes_read + write of the root-level pair launches from the committed `ncu --set full` capture
-    # (profiles/r1_v7_nibble_pair_c3_ncu_raw.csv: k_tgather_t + k_tpanel + k_gather_panel + k_gather_u); the stored bytes of that
-    # pair are 2*(6 B * residual entries + panel bytes): the column-sorted residual copy also stores the cell position of every
-    # entry (10 B per entry instead of 6), that is the whole difference - nothing is read twice.
-    traffic = TRAFFIC_C3_ROOT_PAIR if (name == "c3" and world == 1 and tr.stats["value_bytes"] == 2 and root_pair and root_pair["storage"]["panel_cols"] > 0) else None
+        traffic, traffic_src = ncu_traffic("c3" if name == "c5" else name, storage["panel_bits"])
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-            "traffic": traffic, "traffic_scope": "root-level pair launch (largest launch), ncu dram bytes" if traffic else None, "peak_source": peak_src, "kernel": "SpMV pair: y = C^T x (k_tgather_t on the column-sorted residual blocks + k_tpanel on the dense byte panel), x' = C y (k_gather_panel + k_gather_u on the residual CSR); all launches of the timed steps",
+            "traffic": traffic, "traffic_scope": "root-level pair (largest launches), ncu dram__bytes_read.sum + dram__bytes_write.sum" if traffic else None,
+            "traffic_source": traffic_src, "peak_source": peak_src,
+            "kernel": "SpMV pair: y = C^T x (residual + dense panel kernels), x' = C y (panel + residual CSR kernels); all launches of the timed steps",
             "algorithmic_bytes_per_step": alg / len(trees), "value_bytes_b_v": tr.stats["value_bytes"],
             "achieved_if_counted_with_fp64_values_b_v8": achieved_nominal,
             "frac_if_counted_with_fp64_values_b_v8": (achieved_nominal / peak) if achieved_nominal else None,
-            "algorithmic_bytes_formula": "per SpMV pair 2*nnz_residual*(b_v+4) + 2*m*P*c + 2*(m+1)*8 + (4*m+2*n)*8 (BASELINE.md section 4 with the storage actually used: b_v = bytes per stored value, P = dense panel columns at one byte or half a byte per cell)", "spmv_ms_per_step": spmv_ms / len(trees),
-            "spmv_share_of_step": spmv_ms / len(trees) / ms_step,
+            "algorithmic_bytes_formula": "per SpMV pair 2*nnz_residual*(b_v+4) + 2*m*P*c + 2*(m+1)*8 + (4*m+2*n)*8 (BASELINE.md section 4 with the storage actually used: b_v = bytes per stored value, P = dense panel columns at one byte or half a byte per cell)",
+            "spmv_ms_per_step": spmv_ms / len(trees), "spmv_share_of_step": spmv_ms / len(trees) / ms_step,
             "per_gpu": True, "root_pair": root_pair}
     line = {"metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(cfg, nnz=nnz, parallelism=("1 GPU" if world == 1 else
-                                             f"{world} GPUs: matrix replicated, shared top of the tree row-sharded with NCCL all-reduce of y = B^T x "
+                                             f"{world} GPUs: matrix replicated, shared top of the tree row-sharded with an all-reduce of y = B^T x "
                                              f"per half-step, subtrees below the hand-off size owned by single GPUs (no collectives)")),
             "clocks": clocks,
-            "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "host_types": f"row_ptr int64, col_idx {np_col.dtype.name}, val {np_val.dtype.name} (pinned)"},
             "gpu_launches": launches, "roofline": roof,
             "tree": {"nodes": tr.n_nodes, "leaves": int(len(tr.leaves())), "sweeps": tr.stats["n_sweeps"],
                      "lanczos_steps": int(tr.iters.sum()), "engine_ms_last": tr.stats["engine_ms"], "gen_s": gen_s,
-                     "hash": tr.tree_hash()}}
+                     "hash": hashes[0], "hash_single_gpu": hash_single,
+                     "hash_check": ("all ranks and steps equal" + (", equal to the single-GPU tree" if hash_single else "")) }}
     if not args.no_cpu_baseline and world == 1:          # reported on rank 0 at N=1 only
-        ms_c, ns, nnz_c, desc, all_cores = cpu_reference_run(name, args.cpu_sample_cells)
-        line["cpu_baseline"] = {"value": ms_c, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc, "all_cores": all_cores}
+        r = cpu_reference_run(name, args.cpu_sample_cells)
+        # the GPU on the very same input, so that one CPU/GPU pair is measured-vs-measured (host CSR -> tree, and device-resident)
+        a = r["matrix"]
+        T.hierarchical_spectral_cluster(a, normalize=True, device=local_rank, **eng)
+        t = time.perf_counter()
+        for _ in range(3):
+            tg = T.hierarchical_spectral_cluster(a, normalize=True, device=local_rank, **eng)
+        gpu_e2e = 1e3 * (time.perf_counter() - t) / 3
+        db = T.DeviceB.from_host(a, normalize=True, device=local_rank)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(3):
+            T.hierarchical_spectral_cluster(db, **eng)
+        gpu_dev = 1e3 * (time.perf_counter() - t) / 3
+        db.free()
+        line["cpu_baseline"] = {"value": r["ms"] * r["scale"], "unit": UNIT, "cores": 1, "kind": "port", "sample": r["desc"] + (
+                                    "" if r["whole"] else f"; value = measured x {r['scale']:.0f} (scaled linearly in cells to the metric's unit)"),
+                                "measured_ms": r["ms"], "sample_cells": r["cells"], "scale": r["scale"], "all_cores": r["all_cores"],
+                                "same_input": {"cells": r["cells"], "nnz": r["nnz"], "cpu_ms": r["ms"], "gpu_e2e_ms": gpu_e2e, "gpu_device_resident_ms": gpu_dev,
+                                               "gpu_nodes": tg.n_nodes, "cpu_nodes": r["nodes"],
+                                               "note": "both arms measured on this box on the identical matrix (no scaling)"}}
     print(json.dumps(line))
     if world > 1:
         tdist.destroy_comm()

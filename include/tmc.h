@@ -41,15 +41,24 @@ typedef enum {
 
 /* cells x features CSR, rows = cells (MatObsRow, src/TooManyCells/Matrix/Types.hs:152-158).
  * Columns need not be sorted within a row; duplicates are not allowed. */
+typedef enum { TMC_VAL_F64 = 0, TMC_VAL_F32 = 1, TMC_VAL_U16 = 2, TMC_VAL_U8 = 3 } tmc_val_type;
+typedef enum { TMC_IDX_I32 = 0, TMC_IDX_U16 = 1 } tmc_idx_type;
 typedef struct {
   int64_t n_rows, n_cols, nnz;
   const int64_t* row_ptr;   /* n_rows + 1 */
-  const int32_t* col_idx;   /* nnz */
-  const double*  val;       /* nnz */
+  const int32_t* col_idx;   /* nnz column indices; element type per idx_type (cast the pointer) */
+  const double*  val;       /* nnz values; element type per val_type (cast the pointer) */
   /* multi-GPU row blocks: leave both 0 for a whole matrix.  With a communicator, a whole
    * matrix passed on every rank is sliced into contiguous row blocks; a rank may instead pass only its
    * own block: n_rows = rows in the block, row_offset = global id of its first row. */
   int64_t row_offset, n_rows_global;
+  /* Compact host element types (0, 0 = the defaults double / int32).  The reference's values are `Double`s, but the usual
+   * make-tree input is a matrix of small UMI counts: a shim that marshals them as uint16 (and gene indices as uint16 when
+   * n_cols <= 65536) moves 4-6 instead of 12 bytes per non-zero over PCIe; the values are widened to fp64 on the device, so
+   * every result is bit-identical to the fp64 call.  Accepted by tmc_matrix_upload / tmc_make_tree; the entry points that
+   * return host values (tmc_tfidf, tmc_row_l2, tmc_left_singular, tmc_filter_thresholds) want the defaults. */
+  int32_t val_type;         /* tmc_val_type */
+  int32_t idx_type;         /* tmc_idx_type */
 } tmc_csr;
 
 /* Flag contract of the make-tree engine call (src/TooManyCells/Program/Options.hs:172-178,

@@ -42,7 +42,7 @@ import Math.Modularity.Types (Q (..))
 -- ---------------------------------------------------------------------------------------------------------------------
 -- struct layouts of include/tmc.h (x86-64 / aarch64 LP64)
 size_csr, size_opts, size_tree :: Int
-size_csr = 64
+size_csr = 72
 size_opts = 96
 size_tree = 152
 
@@ -55,6 +55,9 @@ off_csr_col_idx = 32
 off_csr_val = 40
 off_csr_row_offset = 48
 off_csr_n_rows_global = 56
+off_csr_val_type, off_csr_idx_type :: Int
+off_csr_val_type = 64
+off_csr_idx_type = 68
 
 off_opts_eigen_group, off_opts_num_eigen, off_opts_min_modularity, off_opts_min_size, off_opts_normalize, off_opts_num_runs, off_opts_seed :: Int
 off_opts_eigen_group = 0
@@ -119,6 +122,8 @@ withCsr mat act =
       pokeByteOff csr off_csr_val           pv
       pokeByteOff csr off_csr_row_offset    (0 :: Int64)              -- whole matrix, single process
       pokeByteOff csr off_csr_n_rows_global (0 :: Int64)
+      pokeByteOff csr off_csr_val_type      (0 :: Int32)              -- CDouble values / CInt indices (see INTEGRATION.md for Word16 counts)
+      pokeByteOff csr off_csr_idx_type      (0 :: Int32)
       act csr (VS.length vals)
   where
     (rowPtr, cols, vals) = toCsr mat

@@ -238,3 +238,26 @@ def test_recover_handles_columns_without_a_unit_count_and_rejects_inexact_input(
     db = T.DeviceB.from_host(noisy)
     assert db.info()["value_type"] == "f64"
     db.free()
+
+
+def test_compact_host_types_build_the_same_tree_bit_for_bit(golden_small):
+    """tmc_csr.val_type / idx_type: uint16 / uint8 / float32 counts and uint16 gene ids are widened on the device; every result
+    equals the double / int32 call bit for bit (the widened arrays ARE the fp64 arrays)."""
+    a, _ = golden_small
+    ref = T.hierarchical_spectral_cluster(a, normalize=True)
+    for vdt, idt in ((np.uint16, np.int32), (np.uint16, np.uint16), (np.float32, np.uint16), (np.uint8, np.int32)):
+        if a.data.max() > np.iinfo(vdt).max if np.issubdtype(vdt, np.integer) else False:
+            continue
+        m = (a.indptr, a.indices.astype(idt), a.data.astype(vdt), a.shape)
+        t = T.hierarchical_spectral_cluster(m, normalize=True)
+        assert t.tree_hash() == ref.tree_hash(), (vdt, idt)
+        assert np.array_equal(t.perm, ref.perm)
+        assert np.max(np.abs(t.q - ref.q)) <= 1e-12
+        db = T.DeviceB.from_host(m, normalize=True)
+        assert db.info()["value_type"] == "u16"
+        db.free()
+    # uint16 indices cannot address more than 65536 columns; the host-value entry points want the default types
+    wide = (np.array([0, 1], dtype=np.int64), np.array([3], dtype=np.uint16), np.array([1.0]), (1, 70000))
+    with pytest.raises(T.TmcError) as ei:
+        T.hierarchical_spectral_cluster(wide)
+    assert ei.value.code == T._lib.ERR_INVALID

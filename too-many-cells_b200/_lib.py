@@ -27,7 +27,11 @@ OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_ZERO_ROW, ERR_NAN, ERR_NEGATIVE, E
 class Csr(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("n_cols", C.c_int64), ("nnz", C.c_int64),
                 ("row_ptr", C.c_void_p), ("col_idx", C.c_void_p), ("val", C.c_void_p),
-                ("row_offset", C.c_int64), ("n_rows_global", C.c_int64)]
+                ("row_offset", C.c_int64), ("n_rows_global", C.c_int64), ("val_type", C.c_int32), ("idx_type", C.c_int32)]
+
+
+VAL_TYPES = {"float64": 0, "float32": 1, "uint16": 2, "uint8": 3}      # tmc_val_type
+IDX_TYPES = {"int32": 0, "uint16": 1}                                   # tmc_idx_type
 
 
 class Opts(C.Structure):

@@ -30,7 +30,7 @@
 
 using namespace tmc;
 
-static_assert(sizeof(tmc_csr) == 64, "tmc_csr layout is part of the ABI (mirrored in _lib.py)");
+static_assert(sizeof(tmc_csr) == 72, "tmc_csr layout is part of the ABI (mirrored in _lib.py)");
 static_assert(sizeof(tmc_opts) == 96, "tmc_opts layout is part of the ABI (mirrored in _lib.py)");
 static_assert(sizeof(tmc_tree) == 152, "tmc_tree layout is part of the ABI (mirrored in _lib.py)");
 
@@ -653,8 +653,62 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
   }
 }
 
+// host-side consumers of the values (the entry points that return host arrays) read doubles / int32 only
+static void require_default_types(const tmc_csr* a, const char* who) {
+  if (a && (a->val_type != TMC_VAL_F64 || a->idx_type != TMC_IDX_I32))
+    throw TmcError(TMC_ERR_UNSUPPORTED, std::string(who) + " wants double values and int32 column indices (tmc_csr.val_type / idx_type = 0)");
+}
+static size_t val_elem_size(int t) { return t == TMC_VAL_F64 ? 8 : t == TMC_VAL_F32 ? 4 : t == TMC_VAL_U16 ? 2 : 1; }
+
+// Host -> device copies of the caller's column indices / values [k0, k0 + cnt), widened on the device to int32 / fp64 when the
+// host arrays use the compact element types of tmc_csr (the PCIe link carries the compact bytes; chunks go through two small
+// staging buffers on two streams so that the widening of one chunk overlaps the copy of the next).
+struct Staging { void* buf[2] = {nullptr, nullptr}; cudaStream_t st[2] = {nullptr, nullptr}; int device = -1; };
+static Staging g_staging;
+static const size_t kStageBytes = (size_t)64 << 20;
+static void staging_release() {
+  for (int i = 0; i < 2; ++i) { if (g_staging.buf[i]) cudaFree(g_staging.buf[i]); if (g_staging.st[i]) cudaStreamDestroy(g_staging.st[i]); }
+  g_staging = Staging();
+}
+template <class SRC, class DST>
+static void h2d_widen(DST* dst_dev, const SRC* src_host, int64_t cnt, int device) {
+  if (cnt <= 0) return;
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  if (g_staging.device != device) {
+    staging_release();
+    for (int i = 0; i < 2; ++i) { CK(cudaMalloc(&g_staging.buf[i], kStageBytes)); CK(cudaStreamCreateWithFlags(&g_staging.st[i], cudaStreamNonBlocking)); }
+    g_staging.device = device;
+  }
+  const int64_t per = (int64_t)(kStageBytes / sizeof(SRC));
+  int q = 0;
+  for (int64_t o = 0; o < cnt; o += per, q ^= 1) {
+    const int64_t c = std::min(per, cnt - o);
+    CK(cudaMemcpyAsync(g_staging.buf[q], src_host + o, sizeof(SRC) * c, cudaMemcpyHostToDevice, g_staging.st[q]));
+    k_widen<SRC, DST><<<148 * 4, 256, 0, g_staging.st[q]>>>(reinterpret_cast<const SRC*>(g_staging.buf[q]), dst_dev + o, c);
+  }
+  CK(cudaStreamSynchronize(g_staging.st[0])); CK(cudaStreamSynchronize(g_staging.st[1]));
+  CK(cudaGetLastError());
+}
+static void h2d_cols(int32_t* dst_dev, const tmc_csr* a, int64_t k0, int64_t cnt, int device) {
+  if (cnt <= 0) return;
+  if (a->idx_type == TMC_IDX_U16) h2d_widen(dst_dev, reinterpret_cast<const uint16_t*>(a->col_idx) + k0, cnt, device);
+  else CK(cudaMemcpy(dst_dev, a->col_idx + k0, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice));
+}
+static void h2d_vals(double* dst_dev, const tmc_csr* a, int64_t k0, int64_t cnt, int device) {
+  if (cnt <= 0) return;
+  switch (a->val_type) {
+    case TMC_VAL_F32: h2d_widen(dst_dev, reinterpret_cast<const float*>(a->val) + k0, cnt, device); break;
+    case TMC_VAL_U16: h2d_widen(dst_dev, reinterpret_cast<const uint16_t*>(a->val) + k0, cnt, device); break;
+    case TMC_VAL_U8: h2d_widen(dst_dev, reinterpret_cast<const uint8_t*>(a->val) + k0, cnt, device); break;
+    default: CK(cudaMemcpy(dst_dev, a->val + k0, sizeof(double) * cnt, cudaMemcpyHostToDevice));
+  }
+}
+
 static void validate_csr(const tmc_csr* a) {
   if (!a || !a->row_ptr || (a->nnz > 0 && (!a->col_idx || !a->val))) throw TmcError(TMC_ERR_INVALID, "null CSR pointer");
+  if (a->val_type < TMC_VAL_F64 || a->val_type > TMC_VAL_U8 || a->idx_type < TMC_IDX_I32 || a->idx_type > TMC_IDX_U16)
+    throw TmcError(TMC_ERR_INVALID, "unknown tmc_csr.val_type / idx_type");
+  if (a->idx_type == TMC_IDX_U16 && a->n_cols > 65536) throw TmcError(TMC_ERR_INVALID, "uint16 column indices need n_cols <= 65536");
   if (a->n_rows < 0 || a->n_cols < 0 || a->nnz < 0) throw TmcError(TMC_ERR_INVALID, "negative dimension");
   if (a->n_rows >= (int64_t)1 << 31 || a->n_cols >= (int64_t)1 << 31) throw TmcError(TMC_ERR_INVALID, "dimension exceeds int32");
   if (a->row_ptr[0] != 0 || a->row_ptr[a->n_rows] != a->nnz) throw TmcError(TMC_ERR_INVALID, "row_ptr does not span [0, nnz]");
@@ -686,10 +740,8 @@ static tmc_matrix* upload(const tmc_csr* a, int device) {
       b->row_ptr = dalloc<int64_t>(b->n_rows + 1); b->col = dalloc<int32_t>(b->nnz); b->val = dalloc<double>(b->nnz);
       CK(cudaMemcpy(b->row_ptr, a->row_ptr, sizeof(int64_t) * (b->n_rows + 1), cudaMemcpyHostToDevice));
       const int64_t k0 = a->row_ptr[lo], k1 = a->row_ptr[hi];
-      if (k1 > k0) {
-        CK(cudaMemcpy(b->col + k0, a->col_idx + k0, sizeof(int32_t) * (k1 - k0), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(b->val + k0, a->val + k0, sizeof(double) * (k1 - k0), cudaMemcpyHostToDevice));
-      }
+      h2d_cols(b->col + k0, a, k0, k1 - k0, b->device);
+      h2d_vals(b->val + k0, a, k0, k1 - k0, b->device);
       for (int r = 0; r < world; ++r) {
         const int64_t r0 = a->row_ptr[a->n_rows * r / world], r1 = a->row_ptr[a->n_rows * (r + 1) / world];
         if (r1 == r0) continue;
@@ -710,10 +762,8 @@ static tmc_matrix* upload(const tmc_csr* a, int device) {
       for (int64_t i = 0; i <= b->n_rows; ++i) rp[i] = a->row_ptr[lo + i] - k0;
       CK(cudaMemcpy(b->row_ptr, rp.data(), sizeof(int64_t) * (b->n_rows + 1), cudaMemcpyHostToDevice));
     }
-    if (b->nnz) {
-      CK(cudaMemcpy(b->col, a->col_idx + k0, sizeof(int32_t) * b->nnz, cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(b->val, a->val + k0, sizeof(double) * b->nnz, cudaMemcpyHostToDevice));
-    }
+    h2d_cols(b->col, a, k0, b->nnz, b->device);
+    h2d_vals(b->val, a, k0, b->nnz, b->device);
   } catch (...) { tmc_matrix_free(b); throw; }
   return b;
 }
@@ -1269,6 +1319,7 @@ static void check_variant_opts(const tmc_opts* o) {
 int tmc_tfidf(const tmc_csr* b1, double* val_out, double* idf_out) {
   return guarded([&] {
     if (!val_out) throw TmcError(TMC_ERR_INVALID, "null val_out");
+    require_default_types(b1, "tmc_tfidf");
     if (g_nccl.comm && g_nccl.world > 1) throw TmcError(TMC_ERR_UNSUPPORTED, "host-buffer tmc_tfidf is single-rank; use tmc_matrix_upload(normalize=1)");
     tmc_matrix* b = upload(b1, -1);
     double* idf_dev = nullptr;
@@ -1285,6 +1336,7 @@ int tmc_tfidf(const tmc_csr* b1, double* val_out, double* idf_out) {
 int tmc_row_l2(const tmc_csr* b2, double* val_out, double* norm_out) {
   return guarded([&] {
     if (!val_out) throw TmcError(TMC_ERR_INVALID, "null val_out");
+    require_default_types(b2, "tmc_row_l2");
     if (g_nccl.comm && g_nccl.world > 1) throw TmcError(TMC_ERR_UNSUPPORTED, "host-buffer tmc_row_l2 is single-rank; use tmc_matrix_upload");
     tmc_matrix* b = upload(b2, -1);
     double* nd = nullptr;
@@ -1339,6 +1391,7 @@ int tmc_matrix_info(const tmc_matrix* b, int64_t* info, int n) {
 void tmc_cache_clear(void) {
   std::lock_guard<std::mutex> lk(g_cache_mu);
   delete g_ws_cache; g_ws_cache = nullptr;
+  staging_release();
   factor_bufs_release(g_fb_cache);
   panel_bufs_release(g_pb_cache);
 }
@@ -1529,7 +1582,7 @@ int tmc_make_tree(const tmc_csr* b2, const tmc_opts* opts, tmc_tree** out) {
   if (st != TMC_OK) return st;
   if (opts->eigen_group == 1 && opts->num_eigen > 1) {
     // KMeansGroup on several eigenvectors assembles C_S per node from the host copy of B (tmc_variants.cuh)
-    st = guarded([&] { check_variant_opts(opts); });
+    st = guarded([&] { check_variant_opts(opts); require_default_types(b2, "KMeansGroup with num_eigen > 1"); });
     variants::HostB hb;
     if (st == TMC_OK) st = guarded([&] { variants::host_b_from(b2, opts->normalize, hb); });
     if (st == TMC_OK) st = finish_variants(b, opts, out, make_tree_kmeans(b, &hb, opts, out));
@@ -1717,6 +1770,7 @@ int tmc_left_singular(const tmc_csr* a, int normalize, int n_vec, const tmc_opts
   return guarded([&] {
     check_opts(opts);
     if (!a || !u_out || n_vec < 1) throw TmcError(TMC_ERR_INVALID, "bad arguments");
+    require_default_types(a, "tmc_left_singular");
     if (g_nccl.comm && g_nccl.world > 1) throw TmcError(TMC_ERR_UNSUPPORTED, "tmc_left_singular is single-rank");
     if (n_vec > a->n_rows || n_vec > a->n_cols) throw TmcError(TMC_ERR_INVALID, "more singular vectors requested than min(rows, cols)");
     tmc_matrix* b = upload(a, opts->device);

@@ -269,6 +269,7 @@ int tmc_filter_thresholds(const tmc_csr* a, double row_thresh, double col_thresh
   return guarded([&] {
     if (!out) throw TmcError(TMC_ERR_INVALID, "null out");
     validate_csr(a);
+    require_default_types(a, "tmc_filter_thresholds");
     pick_device(-1);
     const int64_t m = a->n_rows, n = a->n_cols, nnz = a->nnz;
     std::vector<void*> frees;

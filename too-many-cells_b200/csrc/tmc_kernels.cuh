@@ -249,6 +249,14 @@ __global__ void k_remap_cols(int32_t* __restrict__ col, int64_t nnz, const int* 
   for (; i < nnz; i += stride) col[i] = __ldg(rank + col[i]);
 }
 
+// compact host element types (tmc_csr.val_type / idx_type) widened on arrival
+template <class SRC, class DST>
+__global__ void k_widen(const SRC* __restrict__ src, DST* __restrict__ dst, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = (DST)src[i];
+}
+
 // adopted device arrays: row_ptr must be a non-decreasing sequence from 0 to nnz before any kernel walks the rows
 __global__ void k_check_row_ptr(const int64_t* __restrict__ rp, int64_t n_rows, int64_t nnz, int* __restrict__ bad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -31,7 +31,7 @@ from ._lib import Csr, Opts, Tree, TmcError, check
 class HostCsr:
     """Borrowed host CSR (cells x features) in the dtypes the C ABI wants."""
 
-    def __init__(self, mat, row_offset=0, n_rows_global=0):
+    def __init__(self, mat, row_offset=0, n_rows_global=0, compact=False):
         if hasattr(mat, "indptr"):              # scipy.sparse CSR
             indptr, indices, data, shape = mat.indptr, mat.indices, mat.data, mat.shape
         else:
@@ -39,12 +39,17 @@ class HostCsr:
             if len(mat) == 6:                   # (indptr, indices, data, shape, row_offset, n_rows_global): a rank's row block
                 row_offset, n_rows_global = mat[4], mat[5]
         self.indptr = np.ascontiguousarray(indptr, dtype=np.int64)
-        self.indices = np.ascontiguousarray(indices, dtype=np.int32)
-        self.data = np.ascontiguousarray(data, dtype=np.float64)
+        # compact element types travel as they are (tmc_csr.val_type / idx_type); anything else is converted to the defaults
+        idt = np.asarray(indices).dtype.name if compact else "int32"
+        vdt = np.asarray(data).dtype.name if compact else "float64"
+        idt = idt if idt in _lib.IDX_TYPES else "int32"
+        vdt = vdt if vdt in _lib.VAL_TYPES else "float64"
+        self.indices = np.ascontiguousarray(indices, dtype=idt)
+        self.data = np.ascontiguousarray(data, dtype=vdt)
         self.shape = (int(shape[0]), int(shape[1]))
         self.c = Csr(self.shape[0], self.shape[1], int(self.data.size),
                      self.indptr.ctypes.data, self.indices.ctypes.data, self.data.ctypes.data,
-                     int(row_offset), int(n_rows_global))
+                     int(row_offset), int(n_rows_global), _lib.VAL_TYPES[vdt], _lib.IDX_TYPES[idt])
 
     @property
     def nnz(self):
@@ -93,7 +98,7 @@ class DeviceB:
     @classmethod
     def from_host(cls, b2, normalize=False, device=-1):
         lib = _lib.load()
-        h = HostCsr(b2)
+        h = HostCsr(b2, compact=True)          # uint16 / uint8 / float32 values and uint16 indices travel as they are
         out = C.c_void_p()
         check(lib.tmc_matrix_upload(C.byref(h.c), int(bool(normalize)), int(device), C.byref(out)))
         return cls(out, h.shape, h.nnz)
@@ -375,7 +380,7 @@ def hierarchical_spectral_cluster(mat, eigen_group="SignGroup", normalize=False,
         d = np.ascontiguousarray(mat, dtype=np.float64)
         check(lib.tmc_make_tree_dense(d.ctypes.data, int(d.shape[0]), int(d.shape[1]), C.byref(o), C.byref(tp)))
     else:
-        h = HostCsr(mat)
+        h = HostCsr(mat, compact=True)
         check(lib.tmc_make_tree(C.byref(h.c), C.byref(o), C.byref(tp)))
     return _tree_from_c(tp)
 
