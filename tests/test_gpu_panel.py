@@ -261,3 +261,31 @@ def test_compact_host_types_build_the_same_tree_bit_for_bit(golden_small):
     with pytest.raises(T.TmcError) as ei:
         T.hierarchical_spectral_cluster(wide)
     assert ei.value.code == T._lib.ERR_INVALID
+
+
+def test_shared_memory_gather_matches_the_plain_gather(golden_small):
+    """k_gather_smem (large nodes: the residual part of y resident in shared memory) against k_gather_u (TMC_GS=0): same products,
+    same tree.  TMC_GS_ROWS is lowered so that most nodes of `small` take the shared-memory kernel, with and without a panel."""
+    a, _ = golden_small
+    for extra in ({}, {"TMC_NO_PANEL": "1"}):
+        outs = []
+        for gs in ({"TMC_GS": "0"}, {"TMC_GS": "1", "TMC_GS_ROWS": "48", "TMC_GS_CHUNK": "256"}):
+            env = dict(extra, **gs)
+            for k, v in env.items():
+                os.environ[k] = v
+            try:
+                db = T.DeviceB.from_host(a, normalize=True)
+                d = T.b_to_d(db)
+                x = np.random.default_rng(5).standard_normal(a.shape[0])
+                px = T.spmv_pair(db, x)
+                tree = T.hierarchical_spectral_cluster(db)
+                db.free()
+            finally:
+                for k in env:
+                    del os.environ[k]
+            outs.append((d, px, tree))
+        (d0, p0, t0), (d1, p1, t1) = outs
+        assert np.max(np.abs(d0 - d1)) <= 1e-12 * np.max(np.abs(d0))
+        assert np.max(np.abs(p0 - p1)) <= 1e-12 * np.max(np.abs(p0))
+        assert t0.tree_hash() == t1.tree_hash()
+        assert np.max(np.abs(t0.q - t1.q)) <= 1e-12

@@ -86,6 +86,11 @@ struct tmc_matrix {
   // replicated mode: every rank holds ALL rows (n_rows == n_rows_global) and owns the block [own_lo, own_hi) for the shared
   // top of the tree; small subtrees are handed to single ranks (no collectives below the hand-off size)
   bool replicated = false; int64_t own_lo = 0, own_hi = 0;
+  // replicated mode, load time: every rank prepares only its own row block (tf-idf factors, panel rows, residual) and the
+  // ranks exchange the PREPARED blocks; the raw col/val of the other ranks' blocks are fetched only if a fallback needs them
+  bool raw_complete = true;          // raw col/val of every block are on this device
+  bool own_prepare = false;          // prepare_matrix is working on [own_lo, own_hi) and uses collectives
+  std::vector<int64_t> blk_e;        // raw entry boundaries of the ranks' row blocks: row_ptr[n_rows * r / world], r = 0..world
   int64_t* row_ptr = nullptr; int32_t* col = nullptr; double* val = nullptr;
   bool owns = false;
   int device = 0;
@@ -209,11 +214,13 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     c.alpha = w->A<double>((size_t)(K + 2) * max_active); c.beta = w->A<double>((size_t)(K + 2) * max_active);
     c.zvec = w->A<double>((size_t)(K + 2) * max_active); c.scratch = w->A<double>((size_t)2 * (K + 2) * max_active);
     c.K = K;
-    c.list_offs = w->A<int>(3 * ((size_t)max_active + 1));
+    c.list_offs = w->A<int>(4 * ((size_t)max_active + 1));
     c.chunks = w->A<Chunk>((size_t)m / 8 + max_active + 8);
     c.n_chunks = w->A<int>(1);
     c.vchunks = w->A<Chunk>((size_t)m / 32 + max_active + 8);
     c.n_vchunks = w->A<int>(1);
+    c.gchunks = w->A<Chunk>((size_t)m / 256 + max_active + 8);      // k_gather_smem: at least 256 positions per chunk
+    c.n_gchunks = w->A<int>(1);
     c.err = w->A<int>(1);
     c.stats = w->A<unsigned long long>(4);
     c.certmin = w->A<unsigned long long>(max_active);
@@ -262,10 +269,32 @@ static int err_to_status(int e, std::string* msg) {
   }
 }
 
+// load-time collectives are needed when this rank holds (or is preparing) only a row block of the matrix
+static bool sharded_coll(const tmc_matrix* b) { return g_nccl.comm && g_nccl.world > 1 && (!b->replicated || b->own_prepare); }
+static int64_t blk_row(const tmc_matrix* b, int r) { return b->n_rows * r / g_nccl.world; }
+// all-gather by one broadcast per owner: rank r owns bytes [off(r), off(r + 1)) of `base` (same buffer layout on every rank)
+template <class OFF> static void gather_blocks(void* base, OFF off, const char* what) {
+  for (int r = 0; r < g_nccl.world; ++r) {
+    const int64_t o0 = off(r), o1 = off(r + 1);
+    if (o1 <= o0) continue;
+    char* p = reinterpret_cast<char*>(base) + o0;
+    if (g_nccl.Broadcast(p, p, (size_t)(o1 - o0), NCCL_UINT8, r, g_nccl.comm, 0) != 0)
+      throw TmcError(TMC_ERR_COMM, std::string("ncclBroadcast(") + what + ") failed");
+  }
+}
+// replicated mode: fetch the raw blocks of the other ranks (only the fallbacks that walk the caller's CSR need them)
+static void ensure_raw_complete(tmc_matrix* b) {
+  if (b->raw_complete) return;
+  gather_blocks(b->col, [&](int r) { return b->blk_e[r] * (int64_t)sizeof(int32_t); }, "raw column indices");
+  gather_blocks(b->val, [&](int r) { return b->blk_e[r] * (int64_t)sizeof(double); }, "raw values");
+  CK(cudaDeviceSynchronize());
+  b->raw_complete = true;
+}
+
 // Row-block inputs under a communicator: a device error code raised on one rank (zero-norm row, column out of range, ...)
 // must be seen by every rank, or the others would go on and wait forever in the first collective of the tree build.
 static int agree_error(const tmc_matrix* b, int e) {
-  if (!(g_nccl.comm && g_nccl.world > 1 && !b->replicated)) return e;
+  if (!sharded_coll(b)) return e;
   int* d = dalloc<int>(1);
   cudaMemcpy(d, &e, sizeof(int), cudaMemcpyHostToDevice);
   const int r = g_nccl.AllReduce(d, d, 1, NCCL_INT32, NCCL_MAX, g_nccl.comm, 0);
@@ -285,7 +314,7 @@ static void normalise_dev(tmc_matrix* b, int normalize, double* norm_out_dev, do
       df = dalloc<int>(b->n_cols); idf = idf_out_dev ? idf_out_dev : dalloc<double>(b->n_cols);
       CK(cudaMemset(df, 0, sizeof(int) * b->n_cols));
       k_df_count<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, df, d_err);
-      if (g_nccl.comm && g_nccl.world > 1 && !b->replicated) {      // df over all ranks' row blocks
+      if (sharded_coll(b)) {      // df over all ranks' row blocks
         int r = g_nccl.AllReduce(df, df, (size_t)b->n_cols, NCCL_INT32, NCCL_SUM, g_nccl.comm, 0);
         if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(df) failed");
       }
@@ -391,6 +420,9 @@ static void panel_bufs_take(tmc_matrix* b, size_t need_panel, size_t need_rp, si
 // CSR, written to new arrays -- the caller's arrays are never modified.  On return (true) b->P/Ppad/panel/row_ptr_r/col_r/nnz_r
 // are set, valc holds the residual values and w2col/invw follow the new column order.  Returns false when no panel pays off.
 static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev, int* d_flags, int nib) {
+  // rows this rank prepares: all of them, or (replicated mode, own_prepare) its own block -- the blocks are gathered below
+  const int64_t rl = b->own_prepare ? b->own_lo : 0, rh = b->own_prepare ? b->own_hi : b->n_rows;
+  const int nr = (int)(rh - rl);
   if (getenv("TMC_NO_PANEL") || b->n_cols < 64) return false;      // rank-agreed conditions only: a collective follows
   const double density = getenv("TMC_PANEL_DENSITY") ? atof(getenv("TMC_PANEL_DENSITY")) : 0.07;
   if (!(density > 0.0)) return false;
@@ -445,7 +477,11 @@ static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev,
     panel_bufs_take(b, 0, (size_t)b->n_rows + 1, 0);
     cnt = reinterpret_cast<long long*>(b->row_ptr_r);
     const int grid = 148 * 8;
-    k_panel_count<<<grid, 256>>>(b->row_ptr, b->col, b->val, (int)b->n_rows, maps, P, cap, cnt);
+    k_panel_count<<<grid, 256>>>(b->row_ptr + rl, b->col, b->val, nr, maps, P, cap, cnt + rl);
+    if (b->own_prepare) {       // residual entries per row of every block, then the closing zero of the scan
+      gather_blocks(cnt, [&](int r) { return blk_row(b, r) * (int64_t)sizeof(long long); }, "residual row counts");
+      CK(cudaMemset(cnt + b->n_rows, 0, sizeof(long long)));
+    }
     size_t bytes = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt, cnt, (int)b->n_rows + 1));
     CK(cudaMalloc(&tmp, std::max<size_t>(bytes, 16)));
@@ -453,9 +489,9 @@ static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev,
     long long nnz_r = 0;
     CK(cudaMemcpy(&nnz_r, cnt + b->n_rows, sizeof(long long), cudaMemcpyDeviceToHost));
     panel_bufs_take(b, (size_t)b->n_rows * pw, 0, (size_t)nnz_r + 64);
-    CK(cudaMemsetAsync(b->panel, 0, (size_t)b->n_rows * pw));
-    k_panel_fill<<<grid, 256>>>(b->row_ptr, b->col, b->val, (int)b->n_rows, maps, P, pw, nib, cap, cnt, b->col_r,
-                                b->vt == VT_U16 ? reinterpret_cast<unsigned short*>(b->valc) : nullptr, b->panel, d_flags);
+    CK(cudaMemsetAsync(b->panel + (size_t)rl * pw, 0, (size_t)nr * pw));
+    k_panel_fill<<<grid, 256>>>(b->row_ptr + rl, b->col, b->val, nr, maps, P, pw, nib, cap, cnt + rl, b->col_r,
+                                b->vt == VT_U16 ? reinterpret_cast<unsigned short*>(b->valc) : nullptr, b->panel + (size_t)rl * pw, d_flags);
     k_col_factors_perm<<<(n + 255) / 256, 256>>>(idf_dev, maps + n, n, b->w2col, b->invw);
     CK(cudaGetLastError());
     int f = 0;
@@ -470,6 +506,14 @@ static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev,
       if (h) f |= 32;
     }
     if (f & 32) return false;           // duplicated (row, column) entries: the plain CSR path adds them up, a byte cannot
+    if (b->own_prepare) {
+      // exchange the prepared blocks: panel rows and the residual entries (the scan above gave every rank the global offsets)
+      std::vector<long long> rb(g_nccl.world + 1);
+      for (int r = 0; r <= g_nccl.world; ++r) CK(cudaMemcpy(&rb[r], cnt + blk_row(b, r), sizeof(long long), cudaMemcpyDeviceToHost));
+      gather_blocks(b->panel, [&](int r) { return blk_row(b, r) * (int64_t)pw; }, "panel rows");
+      gather_blocks(b->col_r, [&](int r) { return (int64_t)rb[r] * (int64_t)sizeof(int32_t); }, "residual columns");
+      if (b->vt == VT_U16) gather_blocks(b->valc, [&](int r) { return (int64_t)rb[r] * 2; }, "residual values");
+    }
     b->P = P; b->Ppad = Ppad; b->pnib = nib; b->pw = pw; b->nnz_r = nnz_r;
     return true;
   } catch (...) { if (maps) cudaFree(maps); if (tmp) cudaFree(tmp); throw; }
@@ -514,6 +558,11 @@ static void renumber_columns(tmc_matrix* b) {
 static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
   if (b->n_rows_global < 1) throw TmcError(TMC_ERR_INVALID, "empty matrix (reference: error, LoadMatrix.hs:255)");
   if (b->n_cols < 1) throw TmcError(TMC_ERR_ZERO_ROW, "matrix without features: every row has zero norm");
+  const int world = g_nccl.comm ? g_nccl.world : 1, rank = g_nccl.comm ? g_nccl.rank : 0;
+  // replicated mode: prepare the own row block only and gather the prepared blocks (TMC_REPL_PREPARE=1: the first version, every
+  // rank prepares the whole matrix); the fallbacks below (no compact storage / no panel) fetch the raw blocks and do just that
+  b->own_prepare = b->replicated && world > 1 && do_l2 && getenv("TMC_REPL_PREPARE") == nullptr && (int)b->blk_e.size() == world + 1;
+  if (!b->own_prepare) ensure_raw_complete(b);
   renumber_columns(b);
   int* d_flags = dalloc<int>(6);          // [0] value flags, [1] error code, [2..5] two 64-bit counters of small values
   int* df = nullptr; double* idf = nullptr;
@@ -531,13 +580,20 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
       CK(cudaMemset(d_flags, 0, sizeof(int)));
       if (agree_error(b, bad)) throw TmcError(TMC_ERR_INVALID, "row_ptr is not a non-decreasing sequence from 0 to nnz");
     }
+    // the block this rank walks: rows [rl, rh), raw entries [e0, e1)
+    int64_t rl = 0, rh = b->n_rows, e0 = 0, e1 = b->nnz;
+    auto set_range = [&]() {
+      rl = b->own_prepare ? b->own_lo : 0; rh = b->own_prepare ? b->own_hi : b->n_rows;
+      e0 = b->own_prepare ? b->blk_e[rank] : 0; e1 = b->own_prepare ? b->blk_e[rank + 1] : b->nnz;
+    };
+    set_range();
     unsigned long long* d_small = reinterpret_cast<unsigned long long*>(d_flags + 2);
-    k_scan_values<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, d_flags, d_small);
+    k_scan_values<<<grid, 256>>>(b->col + e0, b->val + e0, e1 - e0, (int)b->n_cols, d_flags, d_small);
     int f[2] = {0, 0};
     unsigned long long n_small[2] = {0, 0};
     CK(cudaMemcpy(f, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(n_small, d_small, sizeof(n_small), cudaMemcpyDeviceToHost));
-    if (g_nccl.comm && g_nccl.world > 1 && !b->replicated) {
+    if (sharded_coll(b)) {
       // row-block inputs: every rank must take the same decision (storage mode, errors), or the others would wait forever
       int* bits = dalloc<int>(5); int hb[5];
       for (int i = 0; i < 5; ++i) hb[i] = (f[0] >> i) & 1;
@@ -562,15 +618,15 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
       // B2 = A diag(w) handed over already scaled (Cluster.hs:147 receives the tf-idf matrix): recover A and w if that is exact
       wrec = dalloc<double>(b->n_cols);
       k_fill_f64<<<(unsigned)((b->n_cols + 255) / 256), 256>>>(wrec, b->n_cols, INFINITY);
-      k_colmin<<<grid, 256>>>(b->col, b->val, b->nnz, reinterpret_cast<unsigned long long*>(wrec));
-      const bool sharded = g_nccl.comm && g_nccl.world > 1 && !b->replicated;
+      k_colmin<<<grid, 256>>>(b->col + e0, b->val + e0, e1 - e0, reinterpret_cast<unsigned long long*>(wrec));
+      const bool sharded = sharded_coll(b);
       if (sharded && g_nccl.AllReduce(wrec, wrec, (size_t)b->n_cols, NCCL_FLOAT64, NCCL_MIN, g_nccl.comm, 0) != 0)
         throw TmcError(TMC_ERR_COMM, "ncclAllReduce(column minima) failed");
       k_colmin_fix<<<(int)((b->n_cols + 255) / 256), 256>>>(wrec, (int)b->n_cols);
       CK(cudaMemset(d_flags + 2, 0, 4 * sizeof(int)));
       int* d_rf = dalloc<int>(1);
       CK(cudaMemset(d_rf, 0, sizeof(int)));
-      k_factor_check<<<grid, 256>>>(b->col, b->val, b->nnz, wrec, nullptr, d_rf, d_small);
+      k_factor_check<<<grid, 256>>>(b->col + e0, b->val + e0, e1 - e0, wrec, nullptr, d_rf, d_small);
       int rf = 0;
       CK(cudaMemcpy(&rf, d_rf, sizeof(int), cudaMemcpyDeviceToHost));
       CK(cudaMemcpy(n_small, d_small, sizeof(n_small), cudaMemcpyDeviceToHost));
@@ -587,7 +643,7 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
       if (!(rf & 8)) {
         // exact: replace the values by the counts (in place when the engine owns the array, else in a temporary)
         counts = b->owns ? b->val : dalloc<double>(b->nnz);
-        k_factor_check<<<grid, 256>>>(b->col, b->val, b->nnz, wrec, counts, d_rf, nullptr);
+        k_factor_check<<<grid, 256>>>(b->col + e0, b->val + e0, e1 - e0, wrec, counts + e0, d_rf, nullptr);
         borrowed_val = b->owns ? nullptr : b->val;
         b->val = counts;
         small_int = true;
@@ -598,6 +654,7 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     if (!small_int) {
       cudaFree(d_flags); d_flags = nullptr;
       b->vt = VT_F64;
+      if (b->own_prepare) { ensure_raw_complete(b); b->own_prepare = false; }      // B itself is materialised: every rank does all of it
       normalise_dev(b, normalize, nullptr, nullptr, do_l2);
       return;
     }
@@ -607,8 +664,8 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     if (normalize || want_panel) {       // column frequencies: idf, and the choice of the dense panel
       df = dalloc<int>(b->n_cols);
       CK(cudaMemset(df, 0, sizeof(int) * b->n_cols));
-      k_df_count<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, df, d_flags + 1);
-      if (g_nccl.comm && g_nccl.world > 1 && !b->replicated) {
+      k_df_count<<<grid, 256>>>(b->col + e0, b->val + e0, e1 - e0, (int)b->n_cols, df, d_flags + 1);
+      if (sharded_coll(b)) {
         int r = g_nccl.AllReduce(df, df, (size_t)b->n_cols, NCCL_INT32, NCCL_SUM, g_nccl.comm, 0);
         if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(df) failed");
       }
@@ -618,8 +675,11 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
       k_idf<<<(int)((b->n_cols + 255) / 256), 256>>>(df, (int)b->n_cols, (double)b->n_rows_global, idf);
     }
     factor_bufs_acquire(b, b->vt == VT_U16);
-    if (do_l2) k_row_factor<<<grid, 256>>>(b->row_ptr, b->col, b->val, idf, (int)b->n_rows, b->rrow, d_flags + 1);
-    else k_fill_f64<<<(unsigned)((b->n_rows + 255) / 256), 256>>>(b->rrow, b->n_rows, 1.0);      // truncated SVD of B2 itself: no row factor
+    auto row_factors = [&]() {
+      if (do_l2) k_row_factor<<<grid, 256>>>(b->row_ptr + rl, b->col, b->val, idf, (int)(rh - rl), b->rrow + rl, d_flags + 1);
+      else k_fill_f64<<<(unsigned)((b->n_rows + 255) / 256), 256>>>(b->rrow, b->n_rows, 1.0);      // truncated SVD of B2 itself: no row factor
+    };
+    row_factors();
     bool have_panel = false;
     if (want_panel) {
       // cell format: nibbles when (nearly) everything that fits a byte also fits a nibble (UMI counts), else bytes
@@ -628,12 +688,21 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
       have_panel = build_panel(b, df, idf, d_flags, nib);
       if (!have_panel) panel_bufs_retire(b);
     }
+    if (have_panel && b->own_prepare)
+      gather_blocks(b->rrow, [&](int r) { return blk_row(b, r) * (int64_t)sizeof(double); }, "row factors");
     if (!have_panel) {
+      if (b->own_prepare) {        // the engine will walk the caller's CSR: fetch the other blocks, finish on every rank alike
+        ensure_raw_complete(b); b->own_prepare = false;
+        set_range();
+        row_factors();
+      }
       k_col_factors<<<(int)((b->n_cols + 255) / 256), 256>>>(idf, (int)b->n_cols, b->w2col, b->invw);
       if (b->vt == VT_U16) k_to_u16<<<grid, 256>>>(b->val, reinterpret_cast<unsigned short*>(b->valc), b->nnz);
     }
     CK(cudaGetLastError());
     CK(cudaMemcpy(f, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    f[1] = agree_error(b, f[1]);
+    b->own_prepare = false;
     if (have_panel && b->owns && b->col) { cudaFree(b->col); b->col = nullptr; }    // only the residual is walked from here on
     if (b->owns && b->val) { cudaFree(b->val); b->val = nullptr; }       // the fp64 copy is not needed any more
     restore_val();
@@ -641,9 +710,9 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     if (df) cudaFree(df);
     if (idf) cudaFree(idf);
     df = nullptr; idf = nullptr;
-    f[1] = agree_error(b, f[1]);
     if (f[1]) { std::string msg; int st = err_to_status(f[1], &msg); throw TmcError(st, msg); }
   } catch (...) {
+    b->own_prepare = false;
     restore_val();
     if (d_flags) cudaFree(d_flags);
     if (df) cudaFree(df);
@@ -742,14 +811,11 @@ static tmc_matrix* upload(const tmc_csr* a, int device) {
       const int64_t k0 = a->row_ptr[lo], k1 = a->row_ptr[hi];
       h2d_cols(b->col + k0, a, k0, k1 - k0, b->device);
       h2d_vals(b->val + k0, a, k0, k1 - k0, b->device);
-      for (int r = 0; r < world; ++r) {
-        const int64_t r0 = a->row_ptr[a->n_rows * r / world], r1 = a->row_ptr[a->n_rows * (r + 1) / world];
-        if (r1 == r0) continue;
-        if (g_nccl.Broadcast(b->col + r0, b->col + r0, (size_t)(r1 - r0), NCCL_INT32, r, g_nccl.comm, 0) != 0 ||
-            g_nccl.Broadcast(b->val + r0, b->val + r0, (size_t)(r1 - r0), NCCL_FLOAT64, r, g_nccl.comm, 0) != 0)
-          throw TmcError(TMC_ERR_COMM, "ncclBroadcast(matrix block) failed");
-      }
-      CK(cudaDeviceSynchronize());
+      // the other ranks' raw blocks stay where they are: prepare_matrix works on the own block and the ranks exchange the
+      // prepared blocks over NVLink (ensure_raw_complete fetches the raw ones only for the fallbacks)
+      b->raw_complete = false;
+      b->blk_e.resize(world + 1);
+      for (int r = 0; r <= world; ++r) b->blk_e[r] = a->row_ptr[a->n_rows * r / world];
       return b;
     }
     const int64_t k0 = a->row_ptr[lo], k1 = a->row_ptr[hi];
@@ -785,6 +851,7 @@ struct Engine {
   // replicated mode ("deeper subtrees as per-GPU tasks")
   int act_nev = 0;      // > 0: the next activation runs in truncated-SVD mode
   bool rmode = false; int n_shared_slots = 0; int handoff_rows = 0;
+  size_t gs_smem = 0;           // dynamic shared memory of k_gather_smem
   int priv_top = 0; long long t_top = 0;
   std::vector<int> handoff_list; std::vector<long long> owner_load; int n_handoffs = 0;
   int64_t n_sweeps = 0, n_launch = 0;
@@ -837,6 +904,19 @@ struct Engine {
     c.min_modularity = o.min_modularity; c.min_size = std::max(1, o.min_size);
     c.max_restarts = o.max_restarts >= 0 ? o.max_restarts : 8; c.seed = o.seed;
     c.xs_min_rows = getenv("TMC_XS_ROWS") ? atoi(getenv("TMC_XS_ROWS")) : 8192;
+    // residual gather of large nodes with y[P, n) in shared memory: only when that vector fits one CTA (and a panel or a narrow
+    // matrix makes it so); TMC_GS=0 switches it off, TMC_GS_ROWS / TMC_GS_CHUNK tune the node-size threshold and the chunk
+    {
+      const size_t need = sizeof(double) * (size_t)(c.n_cols - c.P + 2);
+      int dev_max = 0; cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device);
+      c.gs_on = c.use_t && (getenv("TMC_GS") ? atoi(getenv("TMC_GS")) != 0 : 1) && need + 1024 <= (size_t)dev_max;
+      c.gs_min_rows = getenv("TMC_GS_ROWS") ? atoi(getenv("TMC_GS_ROWS")) : 4096;
+      c.gs_chunk_rows = getenv("TMC_GS_CHUNK") ? std::max(256, atoi(getenv("TMC_GS_CHUNK"))) : 1024;
+      gs_smem = need;
+      if (c.gs_on) {
+        VT_DISPATCH(c.vt, CK(cudaFuncSetAttribute(k_gather_smem<VT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need)));
+      }
+    }
     // sign-certified stop (tmc_opts.sign_stop: 0 = on, -1 = off; TMC_NO_CERT=1 switches it off too)
     c.cert_on = (o.sign_stop >= 0 && getenv("TMC_NO_CERT") == nullptr) ? 1 : 0;
     c.cert_min_rows = getenv("TMC_CERT_MIN_ROWS") ? atoi(getenv("TMC_CERT_MIN_ROWS")) : 64;
@@ -1035,13 +1115,15 @@ struct Engine {
     int RV = 32;
     if (rows > 32 * 1184) RV = (int)std::min<int64_t>(TMC_MAX_CHUNK, ((rows / 1184) + 31) / 32 * 32);
     c.chunk_rows = R; c.vchunk_rows = RV; c.n_slots = hi_slot;
-    int nch = 0, nvch = 0;
+    int nch = 0, nvch = 0, ngch = 0;
     for (int sl = 0; sl < hi_slot; ++sl) {
       int st = hstate[sl];
       if (st < ST_DEG || st > ST_MOD) continue;
       const HostNode& nd = nodes[slot_node[sl]];
       const int ll = nd.end - nd.begin;
-      nch += (ll + R - 1) / R;
+      const bool big = c.gs_on && ll >= c.gs_min_rows;      // gathered by k_gather_smem (same rule as k_prepare)
+      if (!big) nch += (ll + R - 1) / R;
+      else if (st == ST_DEG || st == ST_LAN) ngch += (ll + c.gs_chunk_rows - 1) / c.gs_chunk_rows;
       nvch += (ll + RV - 1) / RV;
     }
     const int ny = std::max(1, (int)std::min<int64_t>(64, c.ystride / 8192));
@@ -1065,7 +1147,7 @@ struct Engine {
     }
     mark(PH_COMMIT_D2H);
     k_prepare<<<1, 1024, 0, s>>>(c);
-    k_prepare_fill<<<std::max(1, std::min(148, (std::max(std::max(nch, nvch), ntch) + 255) / 256)), 256, 0, s>>>(c);
+    k_prepare_fill<<<std::max(1, std::min(148, (std::max(std::max(std::max(nch, ngch), nvch), ntch) + 255) / 256)), 256, 0, s>>>(c);
     n_launch += 2;
     if (c.vt != VT_F64 && n_deg && nvch) { k_deg_xin<<<nvch, 256, 0, s>>>(c); n_launch++; }
     mark(PH_PREPARE);
@@ -1111,14 +1193,13 @@ struct Engine {
       mark(PH_TGATHER);
       if (c.collectives && sh_sc) { allreduce_f64(c.Y, (size_t)c.ystride * hi_shared); mark(PH_AR_Y); }
     }
-    if (n_ga && nch) {
+    if (n_ga && (nch || ngch)) {
       if (c.P && nvch) {      // dense panel half of u = A y -> pacc
         if (c.pnib) k_gather_panel<4, 1><<<nvch, 256, 0, s>>>(c); else k_gather_panel<4, 0><<<nvch, 256, 0, s>>>(c);
         n_launch++;
       }
-      VT_DISPATCH(c.vt,
-        k_gather_u<VT, 4><<<nch, 256, 0, s>>>(c));
-      n_launch++;
+      if (ngch) { VT_DISPATCH(c.vt, k_gather_smem<VT, 4><<<ngch, 1024, gs_smem, s>>>(c)); n_launch++; }      // large nodes: y[P, n) in shared memory
+      if (nch) { VT_DISPATCH(c.vt, k_gather_u<VT, 4><<<nch, 256, 0, s>>>(c)); n_launch++; }
     }
     mark(PH_GATHER);
     if (profile && n_sc) { e2 = ev(); prof_pairs.push_back({e0, e1, e2}); }
@@ -1373,6 +1454,9 @@ int tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int6
       if (g_nccl.comm && g_nccl.world > 1 && b->n_rows_global == n_rows && getenv("TMC_NO_HANDOFF") == nullptr) {
         b->replicated = true;      // the whole matrix is resident on every rank
         b->own_lo = n_rows * g_nccl.rank / g_nccl.world; b->own_hi = n_rows * (g_nccl.rank + 1) / g_nccl.world;
+        b->blk_e.resize(g_nccl.world + 1);
+        for (int r = 0; r <= g_nccl.world; ++r)
+          CK(cudaMemcpy(&b->blk_e[r], row_ptr_dev + n_rows * r / g_nccl.world, sizeof(int64_t), cudaMemcpyDeviceToHost));
       }
       b->row_ptr = const_cast<int64_t*>(row_ptr_dev); b->col = const_cast<int32_t*>(col_dev); b->val = val_dev;
       prepare_matrix(b, normalize);

@@ -88,6 +88,10 @@ struct Ctx {
   Chunk* vchunks; int* n_vchunks; int vchunk_rows;   // vector kernels (dots/update/advance): up to 256 positions per CTA
   // transposed (column-sorted) per-node copy of B: y = B_S^T x as a gather with run merging instead of nnz atomics
   int use_t;
+  // residual gather with the dense vector resident in shared memory (k_gather_smem): nodes of at least gs_min_rows local rows,
+  // when the residual part of y (n_cols - P doubles) fits one CTA's shared memory; their rows leave the plain chunk list
+  int gs_on, gs_min_rows, gs_chunk_rows;
+  Chunk* gchunks; int* n_gchunks;
   int xs_min_rows;                                   // nodes with at least this many local rows read x in the strided mapping
   int32_t* tcol[2]; int32_t* tpos[2]; void* tval[2];   // tval element type follows vt
   TChunk* tchunks; int* n_tchunks; int tchunk;       // entries per chunk (multiple of 2048)
@@ -452,7 +456,8 @@ __global__ void k_activate(Ctx c, const Activation* __restrict__ acts, int n) {
 // (SpMV chunks, vector chunks, transposed-block chunks) and zeroes the reduction rows; k_prepare_fill (many CTAs) writes the
 // chunk records (the single-CTA version spent 20-40 us per sweep writing up to 40k records).
 __device__ int block_scan_counts(const Ctx& c, int mode, int* offs, int* wsum) {
-  // mode 0: chunk_rows positions, 1: vchunk_rows positions, 2: tchunk entries of the transposed block (scatter states only)
+  // mode 0: chunk_rows positions, 1: vchunk_rows positions, 2: tchunk entries of the transposed block (scatter states only),
+  // 3: gs_chunk_rows positions of the large gathering nodes
   const int tid = threadIdx.x;
   const int per = (c.n_slots + 1023) / 1024;        // slots per thread (<= 4)
   int cnt[4]; int mine = 0;
@@ -462,9 +467,12 @@ __device__ int block_scan_counts(const Ctx& c, int mode, int* offs, int* wsum) {
       const Slot& s = c.st[slot];
       if (mode == 2) {
         if (s.state == ST_DEG || s.state == ST_LAN || s.state == ST_MOD) n = (int)((s.te - (s.tb & ~7ll) + c.tchunk - 1) / c.tchunk);
+      } else if (mode == 3) {
+        if ((s.state == ST_DEG || s.state == ST_LAN) && s.end - s.begin >= c.gs_min_rows) n = (s.end - s.begin + c.gs_chunk_rows - 1) / c.gs_chunk_rows;
       } else if (s.state >= ST_DEG && s.state <= ST_MOD) {
         const int cs = mode == 0 ? c.chunk_rows : c.vchunk_rows;
         n = (s.end - s.begin + cs - 1) / cs;
+        if (mode == 0 && c.gs_on && s.end - s.begin >= c.gs_min_rows) n = 0;      // gathered by k_gather_smem
       }
     }
     cnt[q] = n; mine += n;
@@ -504,7 +512,9 @@ __global__ void __launch_bounds__(1024) k_prepare(Ctx c) {
   const int ta = block_scan_counts(c, 0, offsA, wsum);
   const int tv = block_scan_counts(c, 1, offsV, wsum);
   const int tt = c.use_t ? block_scan_counts(c, 2, offsT, wsum) : 0;
-  if (threadIdx.x == 0) { *c.n_chunks = ta; *c.n_vchunks = tv; if (c.use_t) *c.n_tchunks = tt; }
+  int* offsG = c.list_offs + 3 * (c.max_active + 1);
+  const int tg = c.gs_on ? block_scan_counts(c, 3, offsG, wsum) : 0;
+  if (threadIdx.x == 0) { *c.n_chunks = ta; *c.n_vchunks = tv; if (c.use_t) *c.n_tchunks = tt; *c.n_gchunks = tg; }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // zero reduction rows (dots of both passes up to j+1, and the scalars): one warp per slot
   for (int slot = wid; slot < c.n_slots; slot += 32) {
@@ -549,6 +559,16 @@ __global__ void __launch_bounds__(256) k_prepare_fill(Ctx c) {
     const Slot& s = c.st[sl];
     TChunk ch; ch.slot = sl; ch.pad = 0; ch.begin = (s.tb & ~7ll) + (long long)(ci - offsT[sl]) * c.tchunk;
     c.tchunks[ci] = ch;
+  }
+  if (c.gs_on) {
+    const int* offsG = c.list_offs + 3 * (c.max_active + 1);
+    const int tg = *c.n_gchunks;
+    for (int ci = t0; ci < tg; ci += stride) {
+      const int sl = find_slot(offsG, c.n_slots, ci);
+      const Slot& s = c.st[sl];
+      Chunk ch; ch.slot = sl; ch.begin = s.begin + (ci - offsG[sl]) * c.gs_chunk_rows; ch.len = min(c.gs_chunk_rows, s.end - ch.begin);
+      c.gchunks[ci] = ch;
+    }
   }
 }
 
@@ -1164,6 +1184,95 @@ __global__ void __launch_bounds__(256) k_gather_u(Ctx c) {
   if (state == ST_DEG) {
     double t = block_sum_256(dsum, sm8);
     if (threadIdx.x == 0) atomicAdd(slot_scal(c, ch.slot) + R_SUMD, t);
+  }
+}
+
+// The same gather for LARGE nodes with the residual part of y resident in shared memory: one CTA of 32 warps per gs_chunk_rows
+// positions stages y[P, n_cols) (up to ~200 KB: a 20-25 k-gene residual fits) once and then streams its rows; the dependent
+// y[col] reads cost a shared-memory access instead of an L2 round trip (k_gather_u on the c3 root: 14 long-scoreboard stalls
+// per issue, 2.4 TB/s).  Launched only when Ctx::gs_on (the host checks that the vector fits); those nodes' rows are not in
+// the plain chunk list.
+template <int VT, int U>
+__global__ void __launch_bounds__(1024, 1) k_gather_smem(Ctx c) {
+  extern __shared__ double gs_y[];
+  __shared__ double sm32[32];
+  if ((int)blockIdx.x >= *c.n_gchunks) return;
+  const Chunk ch = c.gchunks[blockIdx.x];
+  const int state = c.st[ch.slot].state;
+  if (state != ST_DEG && state != ST_LAN) return;
+  const double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride + c.P;
+  const int ny = c.n_cols - c.P;
+  for (int i = threadIdx.x; i < ny; i += 1024) gs_y[i] = y[i];
+  __syncthreads();
+  const int32_t* __restrict__ col = c.col;
+  const void* __restrict__ val = c.val;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  typedef typename RawVal<VT>::T RT;
+  const int P = c.P;
+  double dsum = 0.0;
+  long long nz = 0, nz0 = 0;
+  int r = warp;
+  int64_t rs = 0, re = 0;
+  int row_cur = 0;
+  if (r < ch.len) { row_cur = c.perm[ch.begin + r]; rs = c.row_ptr[row_cur]; re = c.row_ptr[row_cur + 1]; }
+  while (r < ch.len) {
+    const int p = ch.begin + r;
+    const int rn = r + 32;
+    int64_t nrs = 0, nre = 0;
+    int nrow = 0;
+    if (rn < ch.len) { nrow = c.perm[ch.begin + rn]; nrs = c.row_ptr[nrow]; nre = c.row_ptr[nrow + 1]; }
+    nz += re - rs;
+    if (P) nz0 += c.row_ptr0[row_cur + 1] - c.row_ptr0[row_cur];
+    double acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = 0.0;
+    int64_t k = rs + lane;
+    bool have = (k + 32 * (U - 1) < re);
+    int cc[U]; RT vv[U];
+    if (have) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) { cc[u] = __ldg(col + k + 32 * u); vv[u] = ld_raw<VT>(val, k + 32 * u); }
+    }
+    while (have) {
+      const int64_t kn = k + 32 * U;
+      const bool have_n = (kn + 32 * (U - 1) < re);
+      int dc[U]; RT dv[U];
+      if (have_n) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) { dc[u] = __ldg(col + kn + 32 * u); dv[u] = ld_raw<VT>(val, kn + 32 * u); }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] += (double)vv[u] * gs_y[cc[u] - P];
+      if (have_n) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) { cc[u] = dc[u]; vv[u] = dv[u]; }
+      }
+      k = kn; have = have_n;
+    }
+    for (; k < re; k += 32) acc[0] += ld_val<VT>(val, k) * gs_y[__ldg(col + k) - P];
+    double sacc = 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) sacc += acc[u];
+    double s = warp_sum(sacc);
+    if (lane == 0) {
+      if (P) s += c.pacc[p];
+      if (state == ST_DEG) { const double dv2 = (VT == VT_F64) ? s : s * c.rrow[row_cur]; c.d[p] = dv2; dsum += dv2; }
+      else c.w[p] = c.sdeg[p] * s;
+    }
+    r = rn; rs = nrs; re = nre; row_cur = nrow;
+  }
+  if (lane == 0 && (nz || nz0)) {
+    atomicAdd(c.stats + (state == ST_DEG ? 1 : 0), (unsigned long long)(P ? nz0 : nz));
+    if (P) atomicAdd(c.stats + 2, (unsigned long long)nz);
+  }
+  if (state == ST_DEG) {
+    dsum = warp_sum(dsum);
+    if (lane == 0) sm32[warp] = dsum;
+    __syncthreads();
+    if (warp == 0) {
+      double t = warp_sum(sm32[lane]);
+      if (lane == 0) atomicAdd(slot_scal(c, ch.slot) + R_SUMD, t);
+    }
   }
 }
 

@@ -1,4 +1,10 @@
-"""torchrun --nproc-per-node N tools/mgpu_check.py : the N-rank tree must equal the 1-rank tree."""
+"""torchrun --nproc-per-node N tools/mgpu_check.py [names...] : the N-rank tree must equal the 1-rank tree (canonical hash,
+Q to 1e-12) through every multi-GPU entry: (a) the whole host matrix on every rank (replicated mode: own block uploaded and
+prepared, prepared blocks exchanged), (b) every rank passes only its own row block (row-sharded throughout), (c) device-resident
+arrays adopted on every rank, and (a) once more with TMC_REPL_PREPARE=1 (every rank prepares the whole matrix: the first version).
+
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 tools/mgpu_check.py
+"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import numpy as np, scipy.sparse as sp, torch
@@ -10,8 +16,7 @@ rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 
 torch.cuda.set_device(lr)
 dev = torch.device("cuda", lr)
 names = sys.argv[1:] or ["tiny", "small", "c1"]
-single = {}
-mats = {}
+single, mats = {}, {}
 for name in names:
     ip, ix, dv, _ = synth.synth_config(name)
     n, g = synth.CONFIGS[name][:2]
@@ -20,19 +25,41 @@ for name in names:
 dist.init_process_group("nccl", device_id=dev)
 tdist.init_comm(rank, world, lr, dev)
 ok = True
+
+
+def check(name, how, tr, ms):
+    global ok
+    ref = single[name]
+    same = tr.tree_hash() == ref.tree_hash()
+    dq = float(np.max(np.abs(np.sort(tr.q) - np.sort(ref.q)))) if tr.n_nodes == ref.n_nodes else float("inf")
+    good = same and dq <= 1e-12
+    ok &= good
+    print(f"[rank {rank}] {name:6s} {how:34s} nodes {tr.n_nodes:5d} vs {ref.n_nodes:5d}  hash equal {same}  max|dQ| {dq:.1e}  "
+          f"wall {ms:7.1f} ms  engine {tr.stats['engine_ms']:7.1f} ms (1 GPU {ref.stats['engine_ms']:.1f})  {'ok' if good else 'FAIL'}", flush=True)
+
+
 for name in names:
     a = mats[name]
-    t0 = time.time()
-    tr = T.hierarchical_spectral_cluster(a, normalize=True, device=lr)       # whole host matrix on every rank, sliced inside
-    t1 = time.time()
+    t0 = time.time(); tr = T.hierarchical_spectral_cluster(a, normalize=True, device=lr)
+    check(name, "host matrix, replicated", tr, 1e3 * (time.time() - t0))
+    u16 = (a.indptr, a.indices.astype(np.uint16) if a.shape[1] <= 65536 else a.indices, a.data.astype(np.uint16), a.shape)
+    t0 = time.time(); tr = T.hierarchical_spectral_cluster(u16, normalize=True, device=lr)
+    check(name, "host matrix, uint16 counts", tr, 1e3 * (time.time() - t0))
     lo, hi = tdist.row_block(a.shape[0], rank, world)
     blk = a[lo:hi]
-    tr2 = T.hierarchical_spectral_cluster((blk.indptr, blk.indices, blk.data, blk.shape, lo, a.shape[0]), normalize=True, device=lr)  # own block
-    same = tr.leaf_sets() == single[name].leaf_sets() and tr2.leaf_sets() == single[name].leaf_sets()
-    dq = float(np.max(np.abs(np.sort(tr.q) - np.sort(single[name].q))))
-    ok &= same
-    print(f"[rank {rank}] {name}: nodes {tr.n_nodes} vs {single[name].n_nodes}  leaf sets equal {same}  max|dQ| {dq:.2e}  "
-          f"engine {tr.stats['engine_ms']:.1f} ms (1 GPU {single[name].stats['engine_ms']:.1f} ms) sweeps {tr.stats['n_sweeps']}", flush=True)
+    t0 = time.time(); tr = T.hierarchical_spectral_cluster((blk.indptr, blk.indices, blk.data, blk.shape, lo, a.shape[0]), normalize=True, device=lr)
+    check(name, "own row block per rank", tr, 1e3 * (time.time() - t0))
+    rp = torch.from_numpy(a.indptr.astype(np.int64)).to(dev); ci = torch.from_numpy(a.indices.astype(np.int32)).to(dev)
+    va = torch.from_numpy(a.data.astype(np.float64)).to(dev)
+    t0 = time.time()
+    b = T.DeviceB.adopt_device(a.shape[0], a.shape[1], rp, ci, va, normalize=True, device=lr)
+    tr = T.hierarchical_spectral_cluster(b); b.free()
+    check(name, "device-resident arrays adopted", tr, 1e3 * (time.time() - t0))
+    b2 = T.tfidf_scale_sparse_mat(a) if world == 0 else None      # (single-rank API; the B2 path is covered by tools/b2_path.py)
+    os.environ["TMC_REPL_PREPARE"] = "1"
+    t0 = time.time(); tr = T.hierarchical_spectral_cluster(a, normalize=True, device=lr)
+    check(name, "host matrix, TMC_REPL_PREPARE=1", tr, 1e3 * (time.time() - t0))
+    del os.environ["TMC_REPL_PREPARE"]
 tdist.destroy_comm()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
