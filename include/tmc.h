@@ -13,8 +13,8 @@
  * for the duration of the call unless the name says `_dev`.  Outputs are
  * caller-allocated unless documented as library-owned.  Every function returns
  * 0 on success or a negative tmc_status; tmc_last_error() gives a thread-local
- * message.  Nothing aborts, nothing hangs: NaN / zero-norm rows / negative
- * entries are detected up front (the reference hangs in SVDLIBC on those,
+ * message.  Nothing aborts, nothing hangs: NaN / zero-norm rows are detected up
+ * front (the reference hangs in SVDLIBC on those,
  * src/TooManyCells/Program/LoadMatrix.hs:189-193).
  * There is NO CPU fallback: without a CUDA device every compute entry point
  * returns TMC_ERR_NO_DEVICE.
@@ -33,7 +33,8 @@ typedef enum {
   TMC_ERR_CUDA = -3,        /* CUDA runtime error (message in tmc_last_error) */
   TMC_ERR_ZERO_ROW = -4,    /* a row has zero L2 norm (reference: NaN -> svdlibc hang) */
   TMC_ERR_NAN = -5,         /* NaN / Inf in the values */
-  TMC_ERR_NEGATIVE = -6,    /* negative entry (engine requires B >= 0, as tf-idf of counts is) */
+  TMC_ERR_NEGATIVE = -6,    /* (no longer raised: signed matrices are accepted -- the degrees use |B| as the reference's bToD does,
+                               everything else B itself; kept so that the numbering of the codes does not move) */
   TMC_ERR_NOMEM = -7,
   TMC_ERR_COMM = -8,        /* NCCL error */
   TMC_ERR_UNSUPPORTED = -9  /* e.g. the non-default variants (KMeansGroup, num_runs > 0) under a multi-GPU communicator */
@@ -152,7 +153,7 @@ int  tmc_make_tree(const tmc_csr* b2, const tmc_opts* opts, tmc_tree** out);
 int  tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out);
 /* == HSD.hierarchicalSpectralCluster ... (Left (sparseToHMat mat))  (--dense, Cluster.hs:157-167): `mat` is the dense
  * cells x features matrix, row-major.  Zeros carry no weight in any product of the path, so the tree is the one the sparse
- * call builds from the non-zero entries; negative entries are rejected like everywhere else (TMC_ERR_NEGATIVE). */
+ * call builds from the non-zero entries (signed entries, the usual case after PCA / batch correction, included). */
 int  tmc_make_tree_dense(const double* mat, int64_t n_rows, int64_t n_cols, const tmc_opts* opts, tmc_tree** out);
 void tmc_tree_free(tmc_tree*);
 /* == the `runs` argument of hierarchicalSpectralCluster (--numRuns, Options.hs:174) on a finished tree: for every split the

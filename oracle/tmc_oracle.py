@@ -120,6 +120,17 @@ def second_left(c: sp.csr_matrix, d: np.ndarray | None = None):
     return v[:, order[-1]], float(w[order[-1]]), float(w[order[-1]] - w[order[-2]])
 
 
+def second_left_signed(c: sp.csr_matrix):
+    """Second left singular vector of C with nothing deflated (signed input).  Returns (u2, sigma2^2, gap to sigma3^2)."""
+    m = c.shape[0]
+    if m <= DENSE_MAX_ROWS:
+        w, v = np.linalg.eigh((c @ c.T).toarray())
+        return v[:, -2], float(w[-2]), float(w[-2] - (w[-3] if m >= 3 else 0.0))
+    u, sv, _ = spla.svds(c, k=3, tol=1e-14, v0=np.random.default_rng(12345).standard_normal(min(c.shape)))
+    order = np.argsort(sv)
+    return u[:, order[-2]], float(sv[order[-2]] ** 2), float(sv[order[-2]] ** 2 - sv[order[-3]] ** 2)
+
+
 # ---- A6: spectralCluster ----------------------------------------------------------
 def spectral_cluster(b: sp.csr_matrix):
     """labels (0/1) from the sign of u2.  Returns (labels, u2, theta2, gap, d)."""
@@ -130,7 +141,12 @@ def spectral_cluster(b: sp.csr_matrix):
     if m == 1:
         return np.zeros(1, dtype=np.int8), np.zeros(1), 0.0, 0.0, d
     c = bd_to_c(b, d)
-    u2, th2, gap = second_left(c, d)
+    if b.nnz and b.data.min() < 0:
+        # signed B (a centred / PCA-reduced matrix): d comes from |B| but C = D^{-1/2} B keeps the signs, so D^{1/2} 1 is not a
+        # singular vector any more -- `secondLeft 2 1` is then literally the second left singular vector of C
+        u2, th2, gap = second_left_signed(c)
+    else:
+        u2, th2, gap = second_left(c, d)
     if SIGN_RULE_GE_ZERO_IS_ONE:
         labels = (u2 >= 0).astype(np.int8)
     else:
@@ -242,6 +258,42 @@ def permutation_p_value(labels: np.ndarray, b: sp.csr_matrix, rows: np.ndarray, 
         if get_b_modularity(lab, b) >= q_obs - 1e-12:
             ge += 1
     return ge / num_runs
+
+
+# ---- N3: --svd / --pca pre-reductions (src/TooManyCells/Matrix/Preprocess.hs:263-271, 543-556, 573-585) ----------------------
+def center_scale_sparse(vec_rows: sp.csr_matrix) -> sp.csr_matrix:
+    """centerScaleSparseCell on every row (Preprocess.hs:263-271): the STORED entries become (x - mu) / sigma with mu, sigma the
+    mean and the sample standard deviation (n - 1) of the whole dense row, zeros stay zeros (`fmap` over a sparse vector);
+    sigma = 0 gives 0.  [UPSTREAM-RECALL: `S.toVector` is the dense vector; `stdDev` of `statistics` is the n - 1 estimator.]"""
+    a = sp.csr_matrix(vec_rows, dtype=np.float64)
+    n = a.shape[1]
+    s1 = np.asarray(a.sum(axis=1)).ravel()
+    s2 = np.asarray(a.multiply(a).sum(axis=1)).ravel()
+    mu = s1 / n
+    var = (s2 - n * mu * mu) / max(n - 1, 1)
+    sigma = np.sqrt(np.maximum(var, 0.0))
+    out = a.copy()
+    rows = np.repeat(np.arange(a.shape[0]), np.diff(a.indptr))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out.data = np.where(sigma[rows] == 0, 0.0, (a.data - mu[rows]) / sigma[rows])
+    return out
+
+
+def svd_sparse_mat(mat, n_dim):
+    """svdSparseMat (Preprocess.hs:573-585): `secondLeft 1 N` of the cell-standardised matrix = its first N left singular vectors,
+    one N-vector per cell.  Exact (LAPACK).  Returns (U [cells x N], sigma [N])."""
+    x = center_scale_sparse(mat).toarray()
+    u, sv, _ = np.linalg.svd(x, full_matrices=False)
+    return u[:, :n_dim], sv[:n_dim]
+
+
+def pca_sparse_mat(mat, n_dim):
+    """pcaSparseMat (Preprocess.hs:543-556): features standardised (`centerScaleSparseCell` on the columns), then the matrix times
+    its first N right singular vectors = U_N diag(sigma_N).  Returns the cells x N score matrix and sigma."""
+    scaled = center_scale_sparse(sp.csr_matrix(mat).T.tocsr()).T.tocsr()
+    x = scaled.toarray()
+    u, sv, vt = np.linalg.svd(x, full_matrices=False)
+    return x @ vt[:n_dim].T, sv[:n_dim]
 
 
 # ---- A0: hierarchicalSpectralCluster (call site Cluster.hs:147-156,169) ----------

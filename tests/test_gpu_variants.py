@@ -132,3 +132,74 @@ def test_p_values_reach_the_output_files(golden_tiny):
     back, _ = T.tree_io.parse_cluster_tree_json(T.tree_io.cluster_tree_json(t, names, significance=True))
     inner = t.left >= 0
     assert np.array_equal(back.p_val[inner], t.p_val[inner]) and np.all(np.isnan(back.p_val[~inner]))
+
+
+# ----------------------------------------------------------------------------- signed matrices, --svd / --pca
+def _signed_matrix(seed=3, n=260, g=900):
+    """A centred count matrix with planted structure: entries of both signs, sparsity kept (what `--svd`-style inputs look like)."""
+    import scipy.sparse as sp
+    from too_many_cells_b200 import synth
+    ip, ix, dv, _ = synth.synth_counts(n, g, 90, 3, seed)
+    sg = sp.csc_matrix(sp.csr_matrix((dv, ix, ip), shape=(n, g)))
+    sg.data = np.log1p(sg.data)
+    for j in range(g):          # log counts centred per feature over the stored entries: both signs, sparsity kept
+        seg = slice(sg.indptr[j], sg.indptr[j + 1])
+        if seg.stop - seg.start > 1:
+            sg.data[seg] -= sg.data[seg].mean() - 0.01
+    return sp.csr_matrix(sg)
+
+
+def test_signed_matrix_per_node_exports_vs_oracle():
+    """Negative entries: d = |B| (|B|^T 1) (bToD), C keeps the signs, nothing is deflated and u2 is the second singular vector."""
+    import scipy.sparse as sp
+    a = _signed_matrix()
+    assert a.data.min() < 0
+    b = O.b2_to_b(a)
+    db = T.DeviceB.from_host(a)
+    assert db.info()["value_type"] == "f64"
+    d = T.b_to_d(db)
+    assert np.max(np.abs(d - O.b_to_d(b))) <= 1e-12 * np.max(np.abs(d))
+    lab, uo, tho, gap, _ = O.spectral_cluster(b)
+    u2, th, it = T.second_left(db)
+    assert abs(th - tho) <= 1e-10
+    sgn = 1.0 if u2 @ uo >= 0 else -1.0
+    assert np.linalg.norm(sgn * u2 - uo) <= 1e-7 / max(gap, 1e-3)
+    glab = (u2 >= 0).astype(np.uint8)
+    assert abs(T.get_b_modularity(glab, db) - O.get_b_modularity(glab, b)) <= 1e-12
+    rows = np.arange(3, a.shape[0], 4)
+    assert np.max(np.abs(T.b_to_d(db, rows) - O.b_to_d(b[rows]))) <= 1e-12 * np.max(np.abs(d))
+    db.free()
+
+
+def test_signed_matrix_full_tree_vs_oracle():
+    a = _signed_matrix(seed=8)
+    tree = T.hierarchical_spectral_cluster(a)
+    ot = O.hierarchical_spectral_cluster(a)
+    assert tree.n_nodes == ot.n_nodes and tree.leaf_sets() == ot.leaf_sets()
+    qo = {tuple(sorted(int(x) for x in ot.items[i])): ot.q[i] for i in range(ot.n_nodes)}
+    for i in range(tree.n_nodes):
+        key = tuple(sorted(int(x) for x in tree.items(i)))
+        if len(key) >= 2:
+            assert abs(tree.q[i] - qo[key]) <= 1e-9
+    # the dense call (typical after PCA / batch correction) builds the same tree
+    td = T.hierarchical_spectral_cluster(np.asarray(a.todense()))
+    assert td.tree_hash() == tree.tree_hash()
+
+
+def test_svd_and_pca_pre_reductions_vs_lapack():
+    """`--svd N` / `--pca N` (Preprocess.hs:543-556, 573-585) through tmc_left_singular on the standardised (signed) matrix."""
+    import scipy.sparse as sp
+    from too_many_cells_b200 import synth
+    ip, ix, dv, _ = synth.synth_counts(220, 700, 80, 3, 17)
+    a = sp.csr_matrix((dv, ix, ip), shape=(220, 700))
+    u, sig, conv = T.svd_sparse_mat(a, 6)
+    uo, so = O.svd_sparse_mat(a, 6)
+    assert conv and np.allclose(sig, so, rtol=1e-9)
+    for i in range(6):
+        assert abs(abs(u[:, i] @ uo[:, i]) - 1.0) < 1e-7
+    sc, sig, conv = T.pca_sparse_mat(a, 5)
+    so_, sgo = O.pca_sparse_mat(a, 5)
+    assert conv and np.allclose(sig, sgo, rtol=1e-9)
+    for i in range(5):      # scores are defined up to the sign of the principal direction
+        s = 1.0 if sc[:, i] @ so_[:, i] >= 0 else -1.0
+        assert np.linalg.norm(s * sc[:, i] - so_[:, i]) <= 1e-6 * np.linalg.norm(so_[:, i])

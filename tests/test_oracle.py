@@ -221,3 +221,42 @@ def test_port_and_oracle_agree_on_config1_through_the_tree_signature():
     assert T.tree_signature(l2, r2, b2, e2, p2) == sig_o
     p3 = list(perm); p3[0], p3[-1] = p3[-1], p3[0]
     assert T.tree_signature(ot.left, ot.right, begin, end, p3) != sig_o
+
+
+def test_signed_input_semantics_of_the_oracle():
+    """Negative entries (`--svd`, `--pca`, `--dense` inputs): the degrees come from |B|, everything else from B
+    itself, and u2 is the plain second left singular vector of C = D^{-1/2} B (nothing to deflate)."""
+    import scipy.sparse as sp
+    import too_many_cells_b200 as T
+    from too_many_cells_b200 import synth
+    ip, ix, dv, _ = synth.synth_counts(120, 400, 60, 2, 5)
+    a = sp.csr_matrix((dv, ix, ip), shape=(120, 400))
+    cs = O.center_scale_sparse(a)
+    mine = T.center_scale_sparse_cell(a)
+    assert abs(cs - mine).max() < 1e-13
+    dense = a.toarray()
+    mu, sd = dense.mean(axis=1, keepdims=True), dense.std(axis=1, ddof=1, keepdims=True)
+    want = np.where(dense != 0, (dense - mu) / sd, 0.0)
+    assert np.allclose(cs.toarray(), want, atol=1e-12)
+    # a genuinely signed matrix: log counts centred per feature over the stored entries (sparsity kept)
+    sg = a.tocsc(copy=True)
+    sg.data = np.log1p(sg.data)
+    for j in range(sg.shape[1]):
+        seg = slice(sg.indptr[j], sg.indptr[j + 1])
+        if seg.stop - seg.start > 1:
+            sg.data[seg] -= sg.data[seg].mean() - 0.01
+    cs = sp.csr_matrix(sg)
+    assert cs.data.min() < 0 < cs.data.max()
+    b = O.b2_to_b(cs)
+    d = O.b_to_d(b)
+    assert np.allclose(d, abs(b) @ (abs(b).T @ np.ones(b.shape[0])))
+    lab, u2, th2, gap, _ = O.spectral_cluster(b)
+    c = O.bd_to_c(b, d).toarray()
+    uu, ss, _ = np.linalg.svd(c, full_matrices=False)
+    assert abs(th2 - ss[1] ** 2) < 1e-12 and abs(abs(u2 @ uu[:, 1]) - 1.0) < 1e-9
+    tr = O.hierarchical_spectral_cluster(cs)
+    assert sum(len(x) for x in tr.leaf_sets()) == 120
+    u, sv = O.svd_sparse_mat(a, 4)
+    assert u.shape == (120, 4) and np.all(np.diff(sv) <= 0)
+    sc, sv2 = O.pca_sparse_mat(a, 3)
+    assert sc.shape == (120, 3)

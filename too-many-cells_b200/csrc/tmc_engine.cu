@@ -97,6 +97,7 @@ struct tmc_matrix {
   // storage mode (DESIGN.md "factored values"): VT_F64 = val holds B itself; VT_U16 / VT_ONE = B = diag(rrow) A diag(w)
   // with A the caller's small-integer values kept as uint16 (valc) / implicit ones
   int vt = VT_F64;
+  bool has_neg = false;                    // entries < 0 (centred / PCA-reduced input): fp64 storage, no deflation, two degree passes
   void* valc = nullptr; double* rrow = nullptr; double* w2col = nullptr; double* invw = nullptr;
   size_t fb_cap_nnz = 0; void* fb_valc_spare = nullptr;
   // dense panel (factored modes, DESIGN.md "dense panel"): the P most frequent columns as bytes, the rest as a residual CSR with
@@ -169,6 +170,7 @@ static void bind_workspace(Workspace* w, tmc_matrix* b) {
   c.vt = b->vt; c.rrow = b->rrow; c.w2col = b->w2col; c.invw = b->invw;
   c.panel = b->panel; c.P = b->P; c.Ppad = b->Ppad; c.pnib = b->pnib; c.pw = b->pw; c.row_ptr0 = b->row_ptr;
   c.n_rows = (int)b->n_rows; c.n_cols = (int)b->n_cols; c.row_offset = b->row_offset;
+  c.signed_mode = b->has_neg ? 1 : 0;
   const int64_t mpos = b->replicated ? (b->own_hi - b->own_lo) + b->n_rows : b->n_rows;
   c.vstride = (mpos + 15) / 16 * 16;
   c.ystride = (b->n_cols + 511) / 512 * 512;        // >= Ppad: the panel kernels read y in whole 512-column steps
@@ -207,6 +209,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     c.d = w->A<double>(m); c.sdeg = w->A<double>(m); c.xin = w->A<double>(m); c.w = w->A<double>(m); c.u2 = w->A<double>(m);
     c.label = w->A<uint8_t>(m);
     c.pacc = w->A<double>(m);
+    c.d2 = w->A<double>(m);
     c.V = w->A<double>((size_t)c.vstride * (K + 2));
     c.Y = w->A<double>((size_t)c.ystride * max_active);
     c.st = w->A<Slot>(max_active); c.rep = w->A<Report>(max_active); c.max_active = max_active;
@@ -612,9 +615,9 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     }
     if (f[0] & 1) throw TmcError(TMC_ERR_NAN, "NaN/Inf in matrix values");
     if (f[0] & 4) throw TmcError(TMC_ERR_INVALID, "column index out of range");
-    if (f[0] & 2) throw TmcError(TMC_ERR_NEGATIVE, "negative matrix entry (engine requires B >= 0)");
+    b->has_neg = (f[0] & 2) != 0;        // signed input (the reference takes |B| for the degrees only): see Ctx::signed_mode
     bool small_int = !(f[0] & 8) && getenv("TMC_NO_FACTORED") == nullptr;
-    if (!small_int && !normalize && b->nnz > 0 && getenv("TMC_NO_FACTORED") == nullptr && getenv("TMC_NO_RECOVER") == nullptr) {
+    if (!small_int && !b->has_neg && !normalize && b->nnz > 0 && getenv("TMC_NO_FACTORED") == nullptr && getenv("TMC_NO_RECOVER") == nullptr) {
       // B2 = A diag(w) handed over already scaled (Cluster.hs:147 receives the tf-idf matrix): recover A and w if that is exact
       wrec = dalloc<double>(b->n_cols);
       k_fill_f64<<<(unsigned)((b->n_cols + 255) / 256), 256>>>(wrec, b->n_cols, INFINITY);
@@ -913,12 +916,14 @@ struct Engine {
       c.gs_min_rows = getenv("TMC_GS_ROWS") ? atoi(getenv("TMC_GS_ROWS")) : 4096;
       c.gs_chunk_rows = getenv("TMC_GS_CHUNK") ? std::max(256, atoi(getenv("TMC_GS_CHUNK"))) : 1024;
       gs_smem = need;
+      c.ts_on = c.gs_on && getenv("TMC_TS") && atoi(getenv("TMC_TS")) != 0;      // experimental: off unless asked for
       if (c.gs_on) {
         VT_DISPATCH(c.vt, CK(cudaFuncSetAttribute(k_gather_smem<VT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need)));
+        VT_DISPATCH(c.vt, CK(cudaFuncSetAttribute(k_tscatter_smem<VT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need)));
       }
     }
     // sign-certified stop (tmc_opts.sign_stop: 0 = on, -1 = off; TMC_NO_CERT=1 switches it off too)
-    c.cert_on = (o.sign_stop >= 0 && getenv("TMC_NO_CERT") == nullptr) ? 1 : 0;
+    c.cert_on = (o.sign_stop >= 0 && getenv("TMC_NO_CERT") == nullptr && !c.signed_mode) ? 1 : 0;
     c.cert_min_rows = getenv("TMC_CERT_MIN_ROWS") ? atoi(getenv("TMC_CERT_MIN_ROWS")) : 64;
     c.cert_safe = getenv("TMC_CERT_SAFE") ? atof(getenv("TMC_CERT_SAFE")) : 4.0;
     c.rank = g_nccl.comm ? g_nccl.rank : 0; c.world = g_nccl.comm ? g_nccl.world : 1;
@@ -1123,7 +1128,7 @@ struct Engine {
       const int ll = nd.end - nd.begin;
       const bool big = c.gs_on && ll >= c.gs_min_rows;      // gathered by k_gather_smem (same rule as k_prepare)
       if (!big) nch += (ll + R - 1) / R;
-      else if (st == ST_DEG || st == ST_LAN) ngch += (ll + c.gs_chunk_rows - 1) / c.gs_chunk_rows;
+      else if (st == ST_DEG || st == ST_LAN || (st == ST_MOD && c.ts_on)) ngch += (ll + c.gs_chunk_rows - 1) / c.gs_chunk_rows;
       nvch += (ll + RV - 1) / RV;
     }
     const int ny = std::max(1, (int)std::min<int64_t>(64, c.ystride / 8192));
@@ -1157,6 +1162,7 @@ struct Engine {
       mark(PH_ZEROY);
       if (profile) e0 = ev();
       if (c.use_t) {
+        if (c.ts_on && ngch) { VT_DISPATCH(c.vt, k_tscatter_smem<VT, 4><<<ngch, 1024, gs_smem, s>>>(c)); n_launch++; }
         if (ntch) {
           // large nodes (long sorted column runs) read x in the strided mapping, small ones in the plain one
           int n_big = 0, n_small = 0;

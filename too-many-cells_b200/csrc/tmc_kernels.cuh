@@ -41,8 +41,10 @@ struct Slot {              // one live tree node (device resident)
   double sumd, inv_sqrt_sumd, beta, theta, resid, q, theta_hint;
   // sign-certified stop (DESIGN.md "sign-certified stop"): cert_req = this sweep probes min|x_i| of the tentative Ritz vector;
   // cert_need = SAFE * r / gap it has to exceed; cert_thr = r / gap below which the next probe is worth its pass over V
-  int cert_req, cert_pad;
+  int cert_req;
+  int deg_phase;           // signed matrices: 0 = degree pass on |B| (d, for D^{-1/2}), 1 = on B itself (d2, for the modularity)
   double cert_need, cert_thr;
+  double sumd2;            // signed matrices: sum of d2 = ||B^T 1||^2
 };
 
 struct Report {            // what the host reads back after every sweep
@@ -75,6 +77,10 @@ struct Ctx {
   // position-indexed state
   int* perm; int* perm_tmp;
   double* d; double* sdeg; double* xin; double* w; double* u2; uint8_t* label;
+  // signed matrices (entries < 0: a centred / PCA-reduced input; fp64 storage only).  The reference takes d = |B| (|B|^T 1) for
+  // D^{-1/2} but B itself everywhere else, so D^{1/2} 1 is no longer a singular vector of C: no deflation, u2 = the SECOND Ritz
+  // vector, and the modularity needs the degrees of B itself (d2) from a second degree pass.
+  int signed_mode; double* d2;
   double* V; int64_t vstride;      // basis arena V[l*vstride + p], l = 0 is the locked u1
   double* Y; int64_t ystride;      // per-slot feature vectors y = B_S^T x
   // per-slot state
@@ -91,6 +97,7 @@ struct Ctx {
   // residual gather with the dense vector resident in shared memory (k_gather_smem): nodes of at least gs_min_rows local rows,
   // when the residual part of y (n_cols - P doubles) fits one CTA's shared memory; their rows leave the plain chunk list
   int gs_on, gs_min_rows, gs_chunk_rows;
+  int ts_on;                                         // the same nodes form y[P, n) from their CSR rows into shared memory (k_tscatter_smem)
   Chunk* gchunks; int* n_gchunks;
   int xs_min_rows;                                   // nodes with at least this many local rows read x in the strided mapping
   int32_t* tcol[2]; int32_t* tpos[2]; void* tval[2];   // tval element type follows vt
@@ -228,7 +235,7 @@ __global__ void k_row_l2(const int64_t* __restrict__ row_ptr, const int32_t* __r
     ss = warp_sum(ss);
     bad = __reduce_or_sync(0xffffffffu, bad);
     double nrm = sqrt(ss);
-    if (bad & 1) atomicMax(err, 5); else if (bad & 4) atomicMax(err, 1); else if (bad & 2) atomicMax(err, 6);
+    if (bad & 1) atomicMax(err, 5); else if (bad & 4) atomicMax(err, 1);
     else if (!(nrm > 0)) atomicMax(err, 4);
     if (lane == 0 && norm_out) norm_out[r] = nrm;
     double inv = nrm > 0 ? 1.0 / nrm : 0.0;
@@ -447,7 +454,7 @@ __global__ void k_activate(Ctx c, const Activation* __restrict__ acts, int n) {
   s.split = 0; s.n0 = 0; s.stop_after = a.stop_after;
   s.tpar = a.tpar; s.priv = a.priv; s.nev = a.nev; s.tb = a.tb; s.te = a.te; s.tnnz0 = 0; s.tchunk0 = 0; s.ntchunk = 0;
   s.sumd = 0; s.inv_sqrt_sumd = 0; s.beta = 0; s.theta = 0; s.resid = 0; s.q = 0; s.theta_hint = -1e300;
-  s.cert_req = 0; s.cert_pad = 0; s.cert_need = 0.0; s.cert_thr = 0.02;
+  s.cert_req = 0; s.deg_phase = 0; s.cert_need = 0.0; s.cert_thr = 0.02; s.sumd2 = 0.0;
   c.st[a.slot] = s;
   slot_scal(c, a.slot)[R_N1] = 0.0; slot_scal(c, a.slot)[R_SD1] = 0.0;
 }
@@ -468,7 +475,8 @@ __device__ int block_scan_counts(const Ctx& c, int mode, int* offs, int* wsum) {
       if (mode == 2) {
         if (s.state == ST_DEG || s.state == ST_LAN || s.state == ST_MOD) n = (int)((s.te - (s.tb & ~7ll) + c.tchunk - 1) / c.tchunk);
       } else if (mode == 3) {
-        if ((s.state == ST_DEG || s.state == ST_LAN) && s.end - s.begin >= c.gs_min_rows) n = (s.end - s.begin + c.gs_chunk_rows - 1) / c.gs_chunk_rows;
+        if ((s.state == ST_DEG || s.state == ST_LAN || (s.state == ST_MOD && c.ts_on)) && s.end - s.begin >= c.gs_min_rows)
+          n = (s.end - s.begin + c.gs_chunk_rows - 1) / c.gs_chunk_rows;
       } else if (s.state >= ST_DEG && s.state <= ST_MOD) {
         const int cs = mode == 0 ? c.chunk_rows : c.vchunk_rows;
         n = (s.end - s.begin + cs - 1) / cs;
@@ -597,10 +605,13 @@ __global__ void __launch_bounds__(256) k_scatter(Ctx c) {
     const int row = c.perm[p];
     const double xi = (state == ST_DEG) ? (VT == VT_F64 ? 1.0 : c.rrow[row]) : c.xin[p];
     if (xi == 0.0) continue;
+    const bool absv = (VT == VT_F64) && c.signed_mode && state == ST_DEG && c.st[ch.slot].deg_phase == 0;
     const int64_t rs = c.row_ptr[row], re = c.row_ptr[row + 1];
     for (int64_t k = rs + lane; k < re; k += 32) {
       const int cj = __ldg(c.col + k);
-      double v = ld_val<VT>(c.val, k) * xi;
+      double v = ld_val<VT>(c.val, k);
+      if (absv) v = fabs(v);
+      v *= xi;
       if (VT != VT_F64) v *= __ldg(c.w2col + cj);
       atomicAdd(y + cj, v);
     }
@@ -624,6 +635,7 @@ __global__ void __launch_bounds__(256) k_tgather_t(Ctx c, int cls) {       // cl
   const Slot& s = c.st[ch.slot];
   const int state = s.state;
   if (state != ST_DEG && state != ST_LAN && state != ST_MOD) return;
+  if (c.ts_on && s.end - s.begin >= c.gs_min_rows) return;          // residual product of this node: k_tscatter_smem
   if (cls) { const bool big = (s.end - s.begin) >= c.xs_min_rows; if (big != (cls == 1)) return; }
   const long long tb = s.tb, te = s.te;
   const int par = s.tpar;
@@ -636,6 +648,7 @@ __global__ void __launch_bounds__(256) k_tgather_t(Ctx c, int cls) {       // cl
   const long long cend = min(ch.begin + (long long)c.tchunk, te);
   constexpr bool FACT = (VT != VT_F64);
   const bool use_x = FACT || state != ST_DEG;      // factored: even the degree pass multiplies by xin = rrow
+  const bool absv = !FACT && c.signed_mode && state == ST_DEG && s.deg_phase == 0;      // d = |B| (|B|^T 1)
   constexpr int W = 32 * E;                 // entries per warp iteration
   constexpr bool xs_on = (XS == 1);
   for (long long base = ch.begin + warp * W; base < cend; base += 8 * W) {
@@ -658,6 +671,10 @@ __global__ void __launch_bounds__(256) k_tgather_t(Ctx c, int cls) {       // cl
     if (k0 < te && k0 + E > tb) {
       ld_idx<E>(tcol + k0, cc);
       ld_vals<E, VT>(tval, k0, t);
+      if (absv) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) t[e] = fabs(t[e]);
+      }
       if (use_x) {
         if (XS && xs_on) {
 #pragma unroll
@@ -1125,6 +1142,9 @@ __global__ void __launch_bounds__(256) k_gather_u(Ctx c) {
   const void* __restrict__ val = c.val;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   typedef typename RawVal<VT>::T RT;
+  const int dphase = (VT == VT_F64 && c.signed_mode && state == ST_DEG) ? c.st[ch.slot].deg_phase : -1;
+  const bool absv = dphase == 0;
+  double* __restrict__ dout = dphase == 1 ? c.d2 : c.d;
   double dsum = 0.0;
   long long nz = 0, nz0 = 0;
   int r = warp;
@@ -1158,21 +1178,21 @@ __global__ void __launch_bounds__(256) k_gather_u(Ctx c) {
         for (int u = 0; u < U; ++u) { dc[u] = __ldg(col + kn + 32 * u); dv[u] = ld_raw<VT>(val, kn + 32 * u); }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) acc[u] += (double)vv[u] * __ldg(y + cc[u]);
+      for (int u = 0; u < U; ++u) acc[u] += (absv ? fabs((double)vv[u]) : (double)vv[u]) * __ldg(y + cc[u]);
       if (have_n) {
 #pragma unroll
         for (int u = 0; u < U; ++u) { cc[u] = dc[u]; vv[u] = dv[u]; }
       }
       k = kn; have = have_n;
     }
-    for (; k < re; k += 32) acc[0] += ld_val<VT>(val, k) * __ldg(y + __ldg(col + k));
+    for (; k < re; k += 32) { const double v = ld_val<VT>(val, k); acc[0] += (absv ? fabs(v) : v) * __ldg(y + __ldg(col + k)); }
     double sacc = 0.0;
 #pragma unroll
     for (int u = 0; u < U; ++u) sacc += acc[u];
     double s = warp_sum(sacc);
     if (lane == 0) {
       if (c.P) s += c.pacc[p];
-      if (state == ST_DEG) { const double dv2 = (VT == VT_F64) ? s : s * c.rrow[row_cur]; c.d[p] = dv2; dsum += dv2; }
+      if (state == ST_DEG) { const double dv2 = (VT == VT_F64) ? s : s * c.rrow[row_cur]; dout[p] = dv2; dsum += dv2; }
       else c.w[p] = c.sdeg[p] * s;
     }
     r = rn; rs = nrs; re = nre; row_cur = nrow;
@@ -1209,6 +1229,9 @@ __global__ void __launch_bounds__(1024, 1) k_gather_smem(Ctx c) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   typedef typename RawVal<VT>::T RT;
   const int P = c.P;
+  const int dphase = (VT == VT_F64 && c.signed_mode && state == ST_DEG) ? c.st[ch.slot].deg_phase : -1;
+  const bool absv = dphase == 0;
+  double* __restrict__ dout = dphase == 1 ? c.d2 : c.d;
   double dsum = 0.0;
   long long nz = 0, nz0 = 0;
   int r = warp;
@@ -1242,21 +1265,21 @@ __global__ void __launch_bounds__(1024, 1) k_gather_smem(Ctx c) {
         for (int u = 0; u < U; ++u) { dc[u] = __ldg(col + kn + 32 * u); dv[u] = ld_raw<VT>(val, kn + 32 * u); }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) acc[u] += (double)vv[u] * gs_y[cc[u] - P];
+      for (int u = 0; u < U; ++u) acc[u] += (absv ? fabs((double)vv[u]) : (double)vv[u]) * gs_y[cc[u] - P];
       if (have_n) {
 #pragma unroll
         for (int u = 0; u < U; ++u) { cc[u] = dc[u]; vv[u] = dv[u]; }
       }
       k = kn; have = have_n;
     }
-    for (; k < re; k += 32) acc[0] += ld_val<VT>(val, k) * gs_y[__ldg(col + k) - P];
+    for (; k < re; k += 32) { const double v = ld_val<VT>(val, k); acc[0] += (absv ? fabs(v) : v) * gs_y[__ldg(col + k) - P]; }
     double sacc = 0.0;
 #pragma unroll
     for (int u = 0; u < U; ++u) sacc += acc[u];
     double s = warp_sum(sacc);
     if (lane == 0) {
       if (P) s += c.pacc[p];
-      if (state == ST_DEG) { const double dv2 = (VT == VT_F64) ? s : s * c.rrow[row_cur]; c.d[p] = dv2; dsum += dv2; }
+      if (state == ST_DEG) { const double dv2 = (VT == VT_F64) ? s : s * c.rrow[row_cur]; dout[p] = dv2; dsum += dv2; }
       else c.w[p] = c.sdeg[p] * s;
     }
     r = rn; rs = nrs; re = nre; row_cur = nrow;
@@ -1273,6 +1296,51 @@ __global__ void __launch_bounds__(1024, 1) k_gather_smem(Ctx c) {
       double t = warp_sum(sm32[lane]);
       if (lane == 0) atomicAdd(slot_scal(c, ch.slot) + R_SUMD, t);
     }
+  }
+}
+
+// Transposed product of the LARGE nodes' residual, y[P, n) += A_res^T xin, from the CSR rows (no column-sorted copy is read): a
+// CTA accumulates its gs_chunk_rows rows into a private copy of y[P, n) in shared memory (fp64 shared-memory atomics: a CAS loop,
+// but conflicts are rare -- 20 k columns, 1024 threads) and flushes the non-zero totals with one global atomic per column.
+// 6 bytes per entry instead of the T-block's 10, and no gather of x at all (x_r is a per-row scalar).  Experimental: TMC_TS=1.
+template <int VT, int U>
+__global__ void __launch_bounds__(1024, 1) k_tscatter_smem(Ctx c) {
+  extern __shared__ double gs_y[];
+  if ((int)blockIdx.x >= *c.n_gchunks) return;
+  const Chunk ch = c.gchunks[blockIdx.x];
+  const int state = c.st[ch.slot].state;
+  if (state != ST_DEG && state != ST_LAN && state != ST_MOD) return;
+  const int ny = c.n_cols - c.P, P = c.P;
+  for (int i = threadIdx.x; i < ny; i += 1024) gs_y[i] = 0.0;
+  __syncthreads();
+  const int32_t* __restrict__ col = c.col;
+  const void* __restrict__ val = c.val;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  typedef typename RawVal<VT>::T RT;
+  constexpr bool FACT = (VT != VT_F64);
+  const bool use_x = FACT || state != ST_DEG;
+  const bool absv = !FACT && c.signed_mode && state == ST_DEG && c.st[ch.slot].deg_phase == 0;
+  for (int r = warp; r < ch.len; r += 32) {
+    const int p = ch.begin + r;
+    const double xr = use_x ? c.xin[p] : 1.0;
+    if (xr == 0.0) continue;                       // label-0 cells of the modularity product
+    const int row = c.perm[p];
+    const int64_t rs = c.row_ptr[row], re = c.row_ptr[row + 1];
+    int64_t k = rs + lane;
+    for (; k + 32 * (U - 1) < re; k += 32 * U) {
+      int cc[U]; RT vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { cc[u] = __ldg(col + k + 32 * u); vv[u] = ld_raw<VT>(val, k + 32 * u); }
+#pragma unroll
+      for (int u = 0; u < U; ++u) atomicAdd(gs_y + (cc[u] - P), (absv ? fabs((double)vv[u]) : (double)vv[u]) * xr);
+    }
+    for (; k < re; k += 32) { const double v = ld_val<VT>(val, k); atomicAdd(gs_y + (__ldg(col + k) - P), (absv ? fabs(v) : v) * xr); }
+  }
+  __syncthreads();
+  double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride + P;
+  for (int i = threadIdx.x; i < ny; i += 1024) {
+    const double v = gs_y[i];
+    if (v != 0.0) atomicAdd(y + i, FACT ? v * __ldg(c.w2col + P + i) : v);
   }
 }
 
@@ -1373,13 +1441,17 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
   const double* redB = slot_redB(c, slot);
   double* scal = slot_scal(c, slot);
   if (state == ST_DEG) {
-    if (lane == 0) {
+    if (lane == 0 && c.signed_mode && !s->nev && s->deg_phase == 1) {      // second pass done: degrees of B itself
+      s->sumd2 = scal[R_SUMD];
+      s->action = ACT_INIT;
+    } else if (lane == 0) {
       double sumd = scal[R_SUMD];
-      s->sumd = sumd;
+      s->sumd = sumd; s->sumd2 = sumd;
       if (s->nev) s->inv_sqrt_sumd = 0;
       else if (!(sumd > 0) || isinf(sumd)) { atomicMax(c.err, 7); s->inv_sqrt_sumd = 0; }
       else s->inv_sqrt_sumd = 1.0 / sqrt(sumd);
-      s->action = ACT_INIT;
+      if (c.signed_mode && !s->nev) { s->deg_phase = 1; s->action = ACT_NONE; }      // stay in ST_DEG for the pass on B itself
+      else s->action = ACT_INIT;
     }
     return;
   }
@@ -1449,6 +1521,29 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
       }
       return;
     }
+    if (c.signed_mode) {
+      // signed matrix: nothing is deflated, the wanted vector belongs to the SECOND largest Ritz value of T_j
+      const bool exh = (j >= len);                    // the Krylov space is the whole space
+      const bool chk = exh || breakdown || full || j <= 64 || (j & 3) == 0;
+      if (j < 2 && !exh && !breakdown) { if (lane == 0) s->action = ACT_NEXT; return; }
+      if (!chk) { if (lane == 0) s->action = ACT_NEXT; return; }
+      __threadfence_block();
+      const double th1 = tmc_top_eig_warp(A, B, j, -1e300, 1e300, 1);
+      const double th2 = j >= 2 ? tmc_top_eig_warp(A, B, j, -1e300, th1, 2) : th1;
+      if (lane == 0) {
+        double lo, hi, piv;
+        tmc_gershgorin(A, B, j, &lo, &hi, &piv);
+        tmc_twisted_vector(A, B, j, th2, sdp, sdm, sz, piv);
+        const double resid = beta * fabs(sz[j - 1]);
+        s->theta = th2; s->resid = resid;
+        const bool conv = exh || breakdown || resid <= c.tol * fmax(th2, 1e-3 * th1) || resid <= 1e-14;
+        if (conv || (full && s->restarts >= c.max_restarts)) { s->action = ACT_RITZ_LABEL; scal[R_N1] = 0.0; scal[R_SD1] = 0.0; }
+        else if (full) { s->action = ACT_RITZ_RESTART; s->restarts += 1; }
+        else s->action = ACT_NEXT;
+        if (s->action != ACT_NEXT) { double* z = c.zvec + (int64_t)slot * K2; for (int q = 0; q < j; ++q) z[q] = sz[q]; }
+      }
+      return;
+    }
     if (!check) { if (lane == 0) s->action = ACT_NEXT; return; }
     __threadfence_block();
     // bracket from the previous test: theta grows monotonically with j and (when the nearest eigenvalue of T_j is the top
@@ -1497,7 +1592,7 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
   if (lane == 0) {
     const double m = (double)s->gsize;
     const double n1 = scal[R_N1], sd1 = scal[R_SD1];
-    const double n0 = m - n1, sd = s->sumd, t1 = scal[R_YNORM2];
+    const double n0 = m - n1, sd = c.signed_mode ? s->sumd2 : s->sumd, t1 = scal[R_YNORM2];
     const double L = sd - m;
     double q = 0.0;
     if (L != 0.0) {
@@ -1587,7 +1682,7 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
       if (!(dd > 0)) atomicMax(c.err, 7);
       const double sq = sqrt(dd);
       c.sdeg[p] = (c.vt == VT_F64 ? 1.0 : c.rrow[c.perm[p]]) / sq;      // D^{-1/2} (times the row factor in the factored modes)
-      c.V[p] = sq * isd;                                   // V_0 = u1
+      c.V[p] = c.signed_mode ? 0.0 : sq * isd;             // V_0 = u1 (nothing to deflate when B has negative entries)
       c.w[p] = hash_unit(c.seed, (uint64_t)(c.row_offset + c.perm[p]));
     }
     return;
@@ -1617,7 +1712,7 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
     const int lab = (u >= 0.0) ? 1 : 0;                   // spectralCluster sign rule (A6)
     c.label[p] = (uint8_t)lab;
     c.xin[p] = lab ? (c.vt == VT_F64 ? 1.0 : c.rrow[c.perm[p]]) : 0.0;
-    n1 += lab; sd1 += lab ? c.d[p] : 0.0;
+    n1 += lab; sd1 += lab ? (c.signed_mode ? c.d2[p] : c.d[p]) : 0.0;
   }
   if (action == ACT_RITZ_LABEL) {
     double t = block_sum_256(n1, sm8);
@@ -1718,7 +1813,7 @@ __global__ void k_set_labels(Ctx c, const uint8_t* __restrict__ lab, int n, int 
   __shared__ double sm8[8];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   double n1 = 0.0, sd1 = 0.0;
-  if (i < n) { int l = lab[i] ? 1 : 0; c.label[i] = (uint8_t)l; c.xin[i] = l ? (c.vt == VT_F64 ? 1.0 : c.rrow[c.perm[i]]) : 0.0; n1 = l; sd1 = l ? c.d[i] : 0.0; }
+  if (i < n) { int l = lab[i] ? 1 : 0; c.label[i] = (uint8_t)l; c.xin[i] = l ? (c.vt == VT_F64 ? 1.0 : c.rrow[c.perm[i]]) : 0.0; n1 = l; sd1 = l ? (c.signed_mode ? c.d2[i] : c.d[i]) : 0.0; }
   double t = block_sum_256(n1, sm8);
   double t2 = block_sum_256(sd1, sm8);
   if (threadIdx.x == 0) { atomicAdd(slot_scal(c, slot) + R_N1, t); atomicAdd(slot_scal(c, slot) + R_SD1, t2); }

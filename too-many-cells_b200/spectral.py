@@ -247,6 +247,40 @@ def lsa_sparse_mat(mat, n_dim, normalize=True, **opt_kw):
     return u, sig, bool(conv.value)
 
 
+def center_scale_sparse_cell(mat):
+    """centerScaleSparseCell on every row (Preprocess.hs:263-271): stored entries -> (x - mu) / sigma with the mean and the
+    sample standard deviation of the whole (dense) row; zeros stay zeros; sigma = 0 -> 0.  O(nnz) host pass (scipy CSR in / out)."""
+    import scipy.sparse as sp
+    a = sp.csr_matrix(mat, dtype=np.float64)
+    n = a.shape[1]
+    s1 = np.asarray(a.sum(axis=1)).ravel()
+    s2 = np.asarray(a.multiply(a).sum(axis=1)).ravel()
+    mu = s1 / n
+    sigma = np.sqrt(np.maximum((s2 - n * mu * mu) / max(n - 1, 1), 0.0))
+    rows = np.repeat(np.arange(a.shape[0]), np.diff(a.indptr))
+    out = a.copy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out.data = np.where(sigma[rows] == 0, 0.0, (a.data - mu[rows]) / sigma[rows])
+    out.eliminate_zeros()
+    return out
+
+
+def svd_sparse_mat(mat, n_dim, **opt_kw):
+    """svdSparseMat (`--svd N`, Preprocess.hs:573-585): `secondLeft 1 N` of the cell-standardised matrix — its first N left
+    singular vectors, through the same GPU Lanczos as `--lsa` (the matrix is signed: tmc_left_singular takes it as it is).
+    Returns (U [cells x N], singular_values, converged)."""
+    return lsa_sparse_mat(center_scale_sparse_cell(mat), n_dim, normalize=False, **opt_kw)
+
+
+def pca_sparse_mat(mat, n_dim, **opt_kw):
+    """pcaSparseMat (`--pca N`, Preprocess.hs:543-556): features standardised, then `scaled #~# V_N` = U_N diag(sigma_N), the
+    scores on the first N principal directions.  Returns (scores [cells x N], singular_values, converged)."""
+    import scipy.sparse as sp
+    scaled = center_scale_sparse_cell(sp.csr_matrix(mat).T.tocsr()).T.tocsr()
+    u, sig, conv = lsa_sparse_mat(scaled, n_dim, normalize=False, **opt_kw)
+    return u * sig[None, :], sig, conv
+
+
 # ----------------------------------------------------------------------------- A0 / A9: the tree
 @dataclass
 class ClusteringTree:
