@@ -1227,9 +1227,9 @@ struct Engine {
     if (n_or && nvch) { k_update<<<nvch, 256, upd_smem, s>>>(c, 1); n_launch++; mark(PH_UPDATE); }
     k_finish<<<(hi_slot + TMC_FINISH_WARPS - 1) / TMC_FINISH_WARPS, 32 * TMC_FINISH_WARPS, sizeof(double) * TMC_FINISH_WARPS * 5 * (c.K + 2), s>>>(c); n_launch++;
     mark(PH_FINISH);
-    if (c.cert_on && n_lan && nvch) {        // sign-certified stop: min |x_i| of the Ritz vectors k_finish asked about
-      k_cert_probe<<<nvch, 256, 0, s>>>(c); n_launch++;
-      if (c.collectives && sh_lan)           // a shared node's cells are spread over the ranks
+    if (c.cert_on && n_lan) {        // sign-certified stop: min |x_i| of the Ritz vectors k_finish asked about
+      if (nvch) { k_cert_probe<<<nvch, 256, 0, s>>>(c); n_launch++; }
+      if (c.collectives && sh_lan)   // a shared node's cells are spread over the ranks (issued from rank-identical state only)
         nccl_check(g_nccl.AllReduce(c.certmin, c.certmin, (size_t)hi_shared, NCCL_FLOAT64, NCCL_MIN, g_nccl.comm, s), "ncclAllReduce(min |x|)");
     }
     if (nvch) { k_advance<<<nvch, 256, 0, s>>>(c); n_launch++; mark(PH_ADVANCE); }

@@ -1220,7 +1220,8 @@ __global__ void __launch_bounds__(1024, 1) k_gather_smem(Ctx c) {
   const Chunk ch = c.gchunks[blockIdx.x];
   const int state = c.st[ch.slot].state;
   if (state != ST_DEG && state != ST_LAN) return;
-  const double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride + c.P;
+  const double* __restrict__ y0 = c.Y + (int64_t)ch.slot * c.ystride;      // columns < P (counts too large for a panel cell) stay in HBM / L2
+  const double* __restrict__ y = y0 + c.P;
   const int ny = c.n_cols - c.P;
   for (int i = threadIdx.x; i < ny; i += 1024) gs_y[i] = y[i];
   __syncthreads();
@@ -1265,14 +1266,17 @@ __global__ void __launch_bounds__(1024, 1) k_gather_smem(Ctx c) {
         for (int u = 0; u < U; ++u) { dc[u] = __ldg(col + kn + 32 * u); dv[u] = ld_raw<VT>(val, kn + 32 * u); }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) acc[u] += (absv ? fabs((double)vv[u]) : (double)vv[u]) * gs_y[cc[u] - P];
+      for (int u = 0; u < U; ++u) acc[u] += (absv ? fabs((double)vv[u]) : (double)vv[u]) * (cc[u] >= P ? gs_y[cc[u] - P] : __ldg(y0 + cc[u]));
       if (have_n) {
 #pragma unroll
         for (int u = 0; u < U; ++u) { cc[u] = dc[u]; vv[u] = dv[u]; }
       }
       k = kn; have = have_n;
     }
-    for (; k < re; k += 32) { const double v = ld_val<VT>(val, k); acc[0] += (absv ? fabs(v) : v) * gs_y[__ldg(col + k) - P]; }
+    for (; k < re; k += 32) {
+      const double v = ld_val<VT>(val, k); const int cj = __ldg(col + k);
+      acc[0] += (absv ? fabs(v) : v) * (cj >= P ? gs_y[cj - P] : __ldg(y0 + cj));
+    }
     double sacc = 0.0;
 #pragma unroll
     for (int u = 0; u < U; ++u) sacc += acc[u];
@@ -1320,6 +1324,11 @@ __global__ void __launch_bounds__(1024, 1) k_tscatter_smem(Ctx c) {
   constexpr bool FACT = (VT != VT_F64);
   const bool use_x = FACT || state != ST_DEG;
   const bool absv = !FACT && c.signed_mode && state == ST_DEG && c.st[ch.slot].deg_phase == 0;
+  double* __restrict__ y0 = c.Y + (int64_t)ch.slot * c.ystride;
+  auto add = [&](int cj, double v) {      // columns < P (counts too large for a panel cell): straight to y in global memory
+    if (cj >= P) atomicAdd(gs_y + (cj - P), v);
+    else atomicAdd(y0 + cj, FACT ? v * __ldg(c.w2col + cj) : v);
+  };
   for (int r = warp; r < ch.len; r += 32) {
     const int p = ch.begin + r;
     const double xr = use_x ? c.xin[p] : 1.0;
@@ -1332,12 +1341,12 @@ __global__ void __launch_bounds__(1024, 1) k_tscatter_smem(Ctx c) {
 #pragma unroll
       for (int u = 0; u < U; ++u) { cc[u] = __ldg(col + k + 32 * u); vv[u] = ld_raw<VT>(val, k + 32 * u); }
 #pragma unroll
-      for (int u = 0; u < U; ++u) atomicAdd(gs_y + (cc[u] - P), (absv ? fabs((double)vv[u]) : (double)vv[u]) * xr);
+      for (int u = 0; u < U; ++u) add(cc[u], (absv ? fabs((double)vv[u]) : (double)vv[u]) * xr);
     }
-    for (; k < re; k += 32) { const double v = ld_val<VT>(val, k); atomicAdd(gs_y + (__ldg(col + k) - P), (absv ? fabs(v) : v) * xr); }
+    for (; k < re; k += 32) { const double v = ld_val<VT>(val, k); add(__ldg(col + k), (absv ? fabs(v) : v) * xr); }
   }
   __syncthreads();
-  double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride + P;
+  double* __restrict__ y = y0 + P;
   for (int i = threadIdx.x; i < ny; i += 1024) {
     const double v = gs_y[i];
     if (v != 0.0) atomicAdd(y + i, FACT ? v * __ldg(c.w2col + P + i) : v);

@@ -1,19 +1,27 @@
 #!/bin/bash
-# Round-2 opening sequence on the GPU box: everything that was written at the end of round 1 without GPU minutes left.
-# Each step is bounded by its own timeout; run through gpurun, e.g.
-#   gpurun --timeout 900 -- 'bash tools/round2_gpu.sh single > gpurun_out/round2_single.log 2>&1; tail -40 gpurun_out/round2_single.log'
-#   gpurun --gpus 2 --timeout 600 -- 'bash tools/round2_gpu.sh p2p > gpurun_out/round2_p2p.log 2>&1; tail -40 gpurun_out/round2_p2p.log'
+# Multi-GPU checks of round 2 (run through gpurun --gpus N):
+#   bash tools/round2_gpu.sh check N    the N-rank tree equals the 1-rank tree through every entry path; peer-memory all-reduce vs NCCL
+#   bash tools/round2_gpu.sh bench N    bench.py at N ranks with NCCL and with TMC_P2P=1 (c3), hashes checked against the single-GPU tree
 set -u
-case "${1:-single}" in
-  single)
-    timeout 600 python -m pytest tests -m gpu -x -q
-    timeout 120 python tests/manual/edge_cases_gpu.py                 # promote what holds into tests/
-    timeout 300 python bench.py --steps 3 --warmup 3
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+N=${2:-2}
+case "${1:-check}" in
+  check)
+    timeout 600 $TR --nproc-per-node "$N" --master-port 29521 tools/mgpu_check.py tiny small c1
+    timeout 300 $TR --nproc-per-node "$N" --master-port 29511 tools/p2p_check.py
     ;;
-  p2p)                                                                 # N >= 2: the peer-memory all-reduce against NCCL, then in the tree
-    N=${2:-2}
-    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29511 tools/p2p_check.py
-    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus "$N" --steps 3 --warmup 3
-    TMC_P2P=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus "$N" --steps 3 --warmup 3
+  bench)
+    W=${3:-c3}
+    timeout 900 $TR --nproc-per-node "$N" --master-port 29512 bench.py --gpus "$N" --steps 3 --warmup 2 --workload "$W" > gpurun_out/r2_bench_${W}_n${N}_nccl.json 2> gpurun_out/r2_bench_${W}_n${N}_nccl.err
+    TMC_P2P=1 timeout 900 $TR --nproc-per-node "$N" --master-port 29513 bench.py --gpus "$N" --steps 3 --warmup 2 --workload "$W" > gpurun_out/r2_bench_${W}_n${N}_p2p.json 2> gpurun_out/r2_bench_${W}_n${N}_p2p.err
+    for f in nccl p2p; do python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/r2_bench_${W}_n${N}_$f.json"))
+    print("$W N=$N $f value %.1f e2e %.1f steps %d sweeps %d hash %s %s" % (d["value"], d["e2e"]["value"], d["tree"]["lanczos_steps"], d["tree"]["sweeps"], d["tree"]["hash"][:10], d["tree"]["hash_check"]))
+except Exception as e:
+    print("$W N=$N $f FAILED", e); print(open("gpurun_out/r2_bench_${W}_n${N}_$f.err").read()[-800:])
+PY
+    done
     ;;
 esac
