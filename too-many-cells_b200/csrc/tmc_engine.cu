@@ -1496,6 +1496,40 @@ void tmc_matrix_free(tmc_matrix* b) {
 }
 
 }  // extern "C"
+
+// Under a communicator the host-composed variants (KMeansGroup, the permutation test) run as REPLICAS: the matrix is resident on
+// every rank (replicated mode), so every rank builds the same result on its own GPU with the communicator hidden, and the ranks
+// then check that they agree (agree_hash).  A rank that only holds a row block cannot do that: TMC_ERR_UNSUPPORTED.
+struct LocalReplica {
+  ncclComm_t comm; int rank, world; bool active;
+  explicit LocalReplica(const tmc_matrix* b) : comm(g_nccl.comm), rank(g_nccl.rank), world(g_nccl.world), active(g_nccl.comm && g_nccl.world > 1) {
+    if (!active) return;
+    if (!b || !b->replicated) {
+      active = false;
+      throw TmcError(TMC_ERR_UNSUPPORTED, "the non-default variants need the whole matrix on every rank (pass the full matrix, not a row block)");
+    }
+    g_nccl.comm = nullptr; g_nccl.rank = 0; g_nccl.world = 1;
+  }
+  bool was_active() const { return comm && world > 1; }
+  void restore() { if (active) { g_nccl.comm = comm; g_nccl.rank = rank; g_nccl.world = world; active = false; } }
+  ~LocalReplica() { restore(); }
+};
+static uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
+  const unsigned char* c = static_cast<const unsigned char*>(p);
+  for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 0x100000001B3ull; }
+  return h;
+}
+// every rank must hold the same 64-bit digest (two int32 MIN / MAX all-reduces); else TMC_ERR_COMM
+static void agree_hash(uint64_t h, const char* what) {
+  if (!(g_nccl.comm && g_nccl.world > 1)) return;
+  int v[4] = {(int)(h & 0x7fffffff), (int)((h >> 31) & 0x7fffffff), -(int)(h & 0x7fffffff), -(int)((h >> 31) & 0x7fffffff)};
+  int* d = dalloc<int>(4);
+  cudaMemcpy(d, v, sizeof(v), cudaMemcpyHostToDevice);
+  const int r = g_nccl.AllReduce(d, d, 4, NCCL_INT32, NCCL_MIN, g_nccl.comm, 0);
+  int o[4]; cudaMemcpy(o, d, sizeof(o), cudaMemcpyDeviceToHost); cudaFree(d);
+  if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(replica digest) failed");
+  if (o[0] != -o[2] || o[1] != -o[3]) throw TmcError(TMC_ERR_COMM, std::string("the ranks built different results for ") + what);
+}
 #include "tmc_variants.cuh"      // TreeStorage + the host-composed variants
 extern "C" {
 
@@ -1503,16 +1537,26 @@ extern "C" {
 static int finish_variants(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out, int st) {
   if (st != TMC_OK || opts->num_runs < 1) return st;
   TreeStorage* ts = reinterpret_cast<TreeStorage*>(*out);
-  st = guarded([&] { variants::permutation_pvals(b, ts->t, opts->num_runs, opts->seed, ts->p_val.data()); });
+  st = guarded([&] {
+    LocalReplica local(b);
+    variants::permutation_pvals(b, ts->t, opts->num_runs, opts->seed, ts->p_val.data());
+    local.restore();
+    agree_hash(fnv1a(0xcbf29ce484222325ull, ts->p_val.data(), sizeof(double) * ts->p_val.size()), "the permutation test");
+  });
   if (st != TMC_OK) { std::string keep = g_err; tmc_tree_free(*out); *out = nullptr; g_err = keep; }
   return st;
 }
 static int make_tree_kmeans(tmc_matrix* b, const variants::HostB* hb, const tmc_opts* opts, tmc_tree** out) {
   return guarded([&] {
     if (!b || !out) throw TmcError(TMC_ERR_INVALID, "null pointer");
-    TreeStorage* ts = variants::kmeans_tree(b, hb, *opts);
+    LocalReplica local(b);
+    std::unique_ptr<TreeStorage> ts(variants::kmeans_tree(b, hb, *opts));
+    local.restore();
+    uint64_t h = fnv1a(0xcbf29ce484222325ull, ts->left.data(), sizeof(int64_t) * ts->left.size());
+    h = fnv1a(h, ts->perm.data(), sizeof(int64_t) * ts->perm.size());
+    agree_hash(h, "the KMeansGroup tree");
     ts->bind();
-    *out = &ts->t;
+    *out = &ts.release()->t;
   });
 }
 
@@ -1699,7 +1743,10 @@ int tmc_permutation_test(tmc_matrix* b, const tmc_tree* tree, int num_runs, uint
     if (!b || !tree || !p_out) throw TmcError(TMC_ERR_INVALID, "null pointer");
     if (num_runs < 0) throw TmcError(TMC_ERR_INVALID, "num_runs must be >= 0");
     if (tree->n_rows != b->n_rows) throw TmcError(TMC_ERR_INVALID, "tree and matrix have different numbers of cells");
+    LocalReplica local(b);
     variants::permutation_pvals(b, *tree, num_runs, seed, p_out);
+    local.restore();
+    agree_hash(fnv1a(0xcbf29ce484222325ull, p_out, sizeof(double) * (size_t)tree->n_nodes), "the permutation test");
   });
 }
 

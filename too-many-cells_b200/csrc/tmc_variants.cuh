@@ -56,6 +56,7 @@ static void shuffle_labels(std::vector<uint8_t>& lab, SplitMix64& rng) {
 
 static inline void must(int st) { if (st != TMC_OK) throw TmcError(st, g_err); }
 
+// (under a communicator the callers hide it and every rank runs the variant as a replica: LocalReplica in tmc_engine.cu)
 static void single_rank_only(const char* what) {
   if (g_nccl.comm && g_nccl.world > 1) throw TmcError(TMC_ERR_UNSUPPORTED, std::string(what) + " is single-rank in this version");
 }
