@@ -22,6 +22,9 @@ for name in names:
     n, g = synth.CONFIGS[name][:2]
     mats[name] = sp.csr_matrix((dv, ix, ip), shape=(n, g))
     single[name] = T.hierarchical_spectral_cluster(mats[name], normalize=True, device=lr)      # before the communicator exists
+vname = names[0]
+v_single = (T.hierarchical_spectral_cluster(mats[vname][:300], normalize=True, eigen_group="KMeansGroup"),
+            T.hierarchical_spectral_cluster(mats[vname][:300], normalize=True, num_runs=6))
 dist.init_process_group("nccl", device_id=dev)
 tdist.init_comm(rank, world, lr, dev)
 ok = True
@@ -60,6 +63,13 @@ for name in names:
     t0 = time.time(); tr = T.hierarchical_spectral_cluster(a, normalize=True, device=lr)
     check(name, "host matrix, TMC_REPL_PREPARE=1", tr, 1e3 * (time.time() - t0))
     del os.environ["TMC_REPL_PREPARE"]
+# the non-default variants under a communicator: every rank runs them as a replica, results checked across ranks inside libtmc
+tk = T.hierarchical_spectral_cluster(mats[vname][:300], normalize=True, eigen_group="KMeansGroup", device=lr)
+tp = T.hierarchical_spectral_cluster(mats[vname][:300], normalize=True, num_runs=6, device=lr)
+good = tk.tree_hash() == v_single[0].tree_hash() and tp.tree_hash() == v_single[1].tree_hash() and \
+    np.array_equal(np.nan_to_num(tp.p_val, nan=-1.0), np.nan_to_num(v_single[1].p_val, nan=-1.0))
+ok &= good
+print(f"[rank {rank}] variants under {world} ranks (KMeansGroup, numRuns): {'ok' if good else 'FAIL'}", flush=True)
 tdist.destroy_comm()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
