@@ -182,7 +182,11 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
   const int64_t m = b->replicated ? (b->own_hi - b->own_lo) + b->n_rows : b->n_rows;
   int K = std::max(2, (int)std::min<int64_t>(o.max_lanczos > 0 ? o.max_lanczos : 320, b->n_rows_global));
   int max_active = (int)std::min<int64_t>(std::max<int64_t>(1, b->n_rows_global / 2), o.max_active > 0 ? o.max_active : 2048);
-  max_active = std::min(max_active, 4096);
+  max_active = std::min(max_active, 16384);      // k_prepare scans up to 16 slots per thread
+  {     // the per-slot feature vectors (Y arena) stay under 8 GB: wide matrices get fewer slots
+    const int64_t ystride = (b->n_cols + 511) / 512 * 512;
+    max_active = (int)std::max<int64_t>(std::min<int64_t>(max_active, 64), std::min<int64_t>(max_active, ((int64_t)8 << 30) / (ystride * 8)));
+  }
   if (b->replicated && g_nccl.world > 1) max_active = std::max(max_active, 2);      // one shared + one private slot at least
   const int use_t = (o.scatter_mode == 0);
   if (b->ws && b->ws->K == K && b->ws->max_active == max_active && b->ws->use_t == use_t && b->ws->vt == b->vt) return b->ws;
@@ -855,6 +859,7 @@ struct Engine {
   int act_nev = 0;      // > 0: the next activation runs in truncated-SVD mode
   bool rmode = false; int n_shared_slots = 0; int handoff_rows = 0;
   size_t gs_smem = 0;           // dynamic shared memory of k_gather_smem
+  bool gs_chunk_fixed = false;
   int priv_top = 0; long long t_top = 0;
   std::vector<int> handoff_list; std::vector<long long> owner_load; int n_handoffs = 0;
   int64_t n_sweeps = 0, n_launch = 0;
@@ -914,7 +919,8 @@ struct Engine {
       int dev_max = 0; cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device);
       c.gs_on = c.use_t && (getenv("TMC_GS") ? atoi(getenv("TMC_GS")) != 0 : 1) && need + 1024 <= (size_t)dev_max;
       c.gs_min_rows = getenv("TMC_GS_ROWS") ? atoi(getenv("TMC_GS_ROWS")) : 4096;
-      c.gs_chunk_rows = getenv("TMC_GS_CHUNK") ? std::max(256, atoi(getenv("TMC_GS_CHUNK"))) : 1024;
+      gs_chunk_fixed = getenv("TMC_GS_CHUNK") != nullptr;      // else chosen per sweep (Engine::sweep)
+      c.gs_chunk_rows = gs_chunk_fixed ? std::max(256, atoi(getenv("TMC_GS_CHUNK"))) : 1024;
       gs_smem = need;
       c.ts_on = c.gs_on && getenv("TMC_TS") && atoi(getenv("TMC_TS")) != 0;      // experimental: off unless asked for
       if (c.gs_on) {
@@ -1121,6 +1127,19 @@ struct Engine {
     if (rows > 32 * 1184) RV = (int)std::min<int64_t>(TMC_MAX_CHUNK, ((rows / 1184) + 31) / 32 * 32);
     c.chunk_rows = R; c.vchunk_rows = RV; c.n_slots = hi_slot;
     int nch = 0, nvch = 0, ngch = 0;
+    if (c.gs_on && !gs_chunk_fixed) {
+      // one CTA per SM at a time (the vector takes most of the shared memory): size the chunks of the large nodes so that their
+      // CTAs fill whole waves of 148, four waves when there is enough work
+      int64_t big_rows = 0;
+      for (int sl = 0; sl < hi_slot; ++sl) {
+        int st = hstate[sl];
+        if (st < ST_DEG || st > ST_MOD) continue;
+        const int ll = nodes[slot_node[sl]].end - nodes[slot_node[sl]].begin;
+        if (ll >= c.gs_min_rows) big_rows += ll;
+      }
+      const int64_t per = (big_rows + 148 * 4 - 1) / (148 * 4);
+      c.gs_chunk_rows = (int)std::min<int64_t>(4096, std::max<int64_t>(256, (per + 31) / 32 * 32));
+    }
     for (int sl = 0; sl < hi_slot; ++sl) {
       int st = hstate[sl];
       if (st < ST_DEG || st > ST_MOD) continue;

@@ -466,8 +466,8 @@ __device__ int block_scan_counts(const Ctx& c, int mode, int* offs, int* wsum) {
   // mode 0: chunk_rows positions, 1: vchunk_rows positions, 2: tchunk entries of the transposed block (scatter states only),
   // 3: gs_chunk_rows positions of the large gathering nodes
   const int tid = threadIdx.x;
-  const int per = (c.n_slots + 1023) / 1024;        // slots per thread (<= 4)
-  int cnt[4]; int mine = 0;
+  const int per = (c.n_slots + 1023) / 1024;        // slots per thread (<= 16: the host caps max_active at 16384)
+  int cnt[16]; int mine = 0;
   for (int q = 0; q < per; ++q) {
     int slot = tid * per + q; int n = 0;
     if (slot < c.n_slots) {
