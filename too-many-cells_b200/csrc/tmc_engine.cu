@@ -912,12 +912,14 @@ struct Engine {
     c.min_modularity = o.min_modularity; c.min_size = std::max(1, o.min_size);
     c.max_restarts = o.max_restarts >= 0 ? o.max_restarts : 8; c.seed = o.seed;
     c.xs_min_rows = getenv("TMC_XS_ROWS") ? atoi(getenv("TMC_XS_ROWS")) : 8192;
-    // residual gather of large nodes with y[P, n) in shared memory: only when that vector fits one CTA (and a panel or a narrow
-    // matrix makes it so); TMC_GS=0 switches it off, TMC_GS_ROWS / TMC_GS_CHUNK tune the node-size threshold and the chunk
+    // EXPERIMENTS, off by default (measured on the c3 tree, profiles/r2_residual_smem_experiments.md: no gain over the kernels
+    // they replace).  TMC_GS=1: residual gather of large nodes with y[P, n) in shared memory, when that vector fits one CTA;
+    // TMC_TS=1 (needs TMC_GS=1): their transposed product from the CSR rows with shared-memory atomics.  TMC_GS_ROWS /
+    // TMC_GS_CHUNK tune the node-size threshold and the chunk.
     {
       const size_t need = sizeof(double) * (size_t)(c.n_cols - c.P + 2);
       int dev_max = 0; cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device);
-      c.gs_on = c.use_t && (getenv("TMC_GS") ? atoi(getenv("TMC_GS")) != 0 : 1) && need + 1024 <= (size_t)dev_max;
+      c.gs_on = c.use_t && (getenv("TMC_GS") ? atoi(getenv("TMC_GS")) != 0 : 0) && need + 1024 <= (size_t)dev_max;
       c.gs_min_rows = getenv("TMC_GS_ROWS") ? atoi(getenv("TMC_GS_ROWS")) : 4096;
       gs_chunk_fixed = getenv("TMC_GS_CHUNK") != nullptr;      // else chosen per sweep (Engine::sweep)
       c.gs_chunk_rows = gs_chunk_fixed ? std::max(256, atoi(getenv("TMC_GS_CHUNK"))) : 1024;
