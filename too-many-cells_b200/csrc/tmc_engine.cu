@@ -867,6 +867,7 @@ struct Engine {
   double alg_panel_bytes = 0;   // panel bytes of the pairs: one byte per (row, panel column) and half
   double build_ms = 0;
   int tg_variant = getenv("TMC_TG") ? atoi(getenv("TMC_TG")) : 0;
+  int gu_lpr = getenv("TMC_GU_LPR") ? atoi(getenv("TMC_GU_LPR")) : 32;      // lanes per row of the residual gather (32 | 16 | 8)
   // TMC_DEBUG=2: per-phase device time (CUDA events between the launches of a sweep), printed after the tree build
   bool phase_prof = getenv("TMC_DEBUG") && atoi(getenv("TMC_DEBUG")) >= 2;
   enum { PH_PREPARE, PH_ZEROY, PH_TGATHER, PH_AR_Y, PH_GATHER, PH_YNORM, PH_DOTS, PH_AR_COEF, PH_UPDATE, PH_FINISH, PH_ADVANCE,
@@ -1226,7 +1227,13 @@ struct Engine {
         n_launch++;
       }
       if (ngch) { VT_DISPATCH(c.vt, k_gather_smem<VT, 4><<<ngch, 1024, gs_smem, s>>>(c)); n_launch++; }      // large nodes: y[P, n) in shared memory
-      if (nch) { VT_DISPATCH(c.vt, k_gather_u<VT, 4><<<nch, 256, 0, s>>>(c)); n_launch++; }
+      if (nch) {
+        VT_DISPATCH(c.vt,
+          if (gu_lpr == 16) k_gather_u<VT, 4, 16><<<nch, 256, 0, s>>>(c);
+          else if (gu_lpr == 8) k_gather_u<VT, 4, 8><<<nch, 256, 0, s>>>(c);
+          else k_gather_u<VT, 4, 32><<<nch, 256, 0, s>>>(c));
+        n_launch++;
+      }
     }
     mark(PH_GATHER);
     if (profile && n_sc) { e2 = ev(); prof_pairs.push_back({e0, e1, e2}); }

@@ -1130,7 +1130,10 @@ template <int VT> __device__ __forceinline__ typename RawVal<VT>::T ld_raw(const
   if (VT == VT_U16) return (typename RawVal<VT>::T)__ldg(reinterpret_cast<const unsigned short*>(base) + k);
   return (typename RawVal<VT>::T)1;
 }
-template <int VT, int U>
+// LPR = lanes per row (32: one row per warp at a time; 16 / 8: two / four rows per warp side by side -- the residual rows are
+// short, ~340 entries on c3, and a warp sits behind a dependent chain perm -> row_ptr -> col/val -> y per row, so more rows in
+// flight per warp is what hides it; the sub-warp segments are reduced with width-LPR shuffles)
+template <int VT, int U, int LPR>
 __global__ void __launch_bounds__(256) k_gather_u(Ctx c) {
   __shared__ double sm8[8];
   if ((int)blockIdx.x >= *c.n_chunks) return;
@@ -1140,42 +1143,46 @@ __global__ void __launch_bounds__(256) k_gather_u(Ctx c) {
   const double* __restrict__ y = c.Y + (int64_t)ch.slot * c.ystride;
   const int32_t* __restrict__ col = c.col;
   const void* __restrict__ val = c.val;
+  constexpr int RPW = 32 / LPR;                       // rows per warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;        // which of the warp's rows, lane inside the row's segment
   typedef typename RawVal<VT>::T RT;
   const int dphase = (VT == VT_F64 && c.signed_mode && state == ST_DEG) ? c.st[ch.slot].deg_phase : -1;
   const bool absv = dphase == 0;
   double* __restrict__ dout = dphase == 1 ? c.d2 : c.d;
   double dsum = 0.0;
   long long nz = 0, nz0 = 0;
-  int r = warp;
+  constexpr int RSTEP = 8 * RPW;                      // rows a CTA advances per iteration
+  int r = warp * RPW + sub;
   int64_t rs = 0, re = 0;
   int row_cur = 0;
   if (r < ch.len) { row_cur = c.perm[ch.begin + r]; rs = c.row_ptr[row_cur]; re = c.row_ptr[row_cur + 1]; }
-  while (r < ch.len) {
+  // all lanes of a warp run the same number of outer iterations (the shuffles below are warp-wide): rows past the end are empty
+  for (int r0 = warp * RPW; r0 < ch.len; r0 += RSTEP) {
+    const bool live = r < ch.len;
     const int p = ch.begin + r;
-    const int rn = r + 8;
+    const int rn = r + RSTEP;
     int64_t nrs = 0, nre = 0;
     int nrow = 0;
     if (rn < ch.len) { nrow = c.perm[ch.begin + rn]; nrs = c.row_ptr[nrow]; nre = c.row_ptr[nrow + 1]; }
-    nz += re - rs;
-    if (c.P) nz0 += c.row_ptr0[row_cur + 1] - c.row_ptr0[row_cur];
+    if (live && sl == 0) { nz += re - rs; if (c.P) nz0 += c.row_ptr0[row_cur + 1] - c.row_ptr0[row_cur]; }
     double acc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) acc[u] = 0.0;
-    int64_t k = rs + lane;
-    bool have = (k + 32 * (U - 1) < re);
+    int64_t k = rs + sl;
+    bool have = live && (k + LPR * (U - 1) < re);
     int cc[U]; RT vv[U];
     if (have) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) { cc[u] = __ldg(col + k + 32 * u); vv[u] = ld_raw<VT>(val, k + 32 * u); }
+      for (int u = 0; u < U; ++u) { cc[u] = __ldg(col + k + LPR * u); vv[u] = ld_raw<VT>(val, k + LPR * u); }
     }
     while (have) {
-      const int64_t kn = k + 32 * U;
-      const bool have_n = (kn + 32 * (U - 1) < re);
+      const int64_t kn = k + LPR * U;
+      const bool have_n = (kn + LPR * (U - 1) < re);
       int dc[U]; RT dv[U];
       if (have_n) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) { dc[u] = __ldg(col + kn + 32 * u); dv[u] = ld_raw<VT>(val, kn + 32 * u); }
+        for (int u = 0; u < U; ++u) { dc[u] = __ldg(col + kn + LPR * u); dv[u] = ld_raw<VT>(val, kn + LPR * u); }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) acc[u] += (absv ? fabs((double)vv[u]) : (double)vv[u]) * __ldg(y + cc[u]);
@@ -1185,19 +1192,20 @@ __global__ void __launch_bounds__(256) k_gather_u(Ctx c) {
       }
       k = kn; have = have_n;
     }
-    for (; k < re; k += 32) { const double v = ld_val<VT>(val, k); acc[0] += (absv ? fabs(v) : v) * __ldg(y + __ldg(col + k)); }
-    double sacc = 0.0;
+    if (live) for (; k < re; k += LPR) { const double v = ld_val<VT>(val, k); acc[0] += (absv ? fabs(v) : v) * __ldg(y + __ldg(col + k)); }
+    double s = 0.0;
 #pragma unroll
-    for (int u = 0; u < U; ++u) sacc += acc[u];
-    double s = warp_sum(sacc);
-    if (lane == 0) {
+    for (int u = 0; u < U; ++u) s += acc[u];
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);      // stays inside the row's LPR-lane segment
+    if (live && sl == 0) {
       if (c.P) s += c.pacc[p];
       if (state == ST_DEG) { const double dv2 = (VT == VT_F64) ? s : s * c.rrow[row_cur]; dout[p] = dv2; dsum += dv2; }
       else c.w[p] = c.sdeg[p] * s;
     }
     r = rn; rs = nrs; re = nre; row_cur = nrow;
   }
-  if (lane == 0 && (nz || nz0)) {
+  if (sl == 0 && (nz || nz0)) {
     atomicAdd(c.stats + (state == ST_DEG ? 1 : 0), (unsigned long long)(c.P ? nz0 : nz));     // nonzeros of the caller's matrix covered
     if (c.P) atomicAdd(c.stats + 2, (unsigned long long)nz);                                   // of which read from the residual CSR
   }
