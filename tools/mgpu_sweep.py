@@ -31,11 +31,18 @@ if os.environ.get("SWEEP_ONLY"):
     CONFIGS = [c for c in CONFIGS if c[0] in os.environ["SWEEP_ONLY"].split(",")]
 
 
+load_ms, tree_ms = [], []
+
+
 def one(profile=False):
     work.copy_(val); torch.cuda.synchronize()
-    b = T.DeviceB.adopt_device(n, g, rp, col, work, normalize=True, device=lr)
+    t0 = time.perf_counter()
+    b = T.DeviceB.adopt_device(n, g, rp, col, work, normalize=True, device=lr)      # load: prepare (+ exchange of the prepared blocks)
+    torch.cuda.synchronize(); t1 = time.perf_counter()
     t = T.hierarchical_spectral_cluster(b, profile=profile)
+    t2 = time.perf_counter()
     b.free()
+    load_ms.append(1e3 * (t1 - t0)); tree_ms.append(1e3 * (t2 - t1))
     return t
 
 
@@ -50,13 +57,14 @@ for label, env in CONFIGS:
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        del load_ms[:], tree_ms[:]
         for _ in range(steps):
             t = one(True)
         e1.record(); torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+        ms = torch.tensor([e0.elapsed_time(e1) / steps, sum(load_ms) / steps, sum(tree_ms) / steps], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        rec = {"config": label, "ms": float(ms.item()), "engine_ms": t.stats["engine_ms"], "spmv_ms": t.stats["spmv_ms"], "steps": int(t.iters.sum()),
+        rec = {"config": label, "ms": float(ms[0].item()), "load_ms": float(ms[1].item()), "tree_wall_ms": float(ms[2].item()), "engine_ms": t.stats["engine_ms"], "spmv_ms": t.stats["spmv_ms"], "steps": int(t.iters.sum()),
                "sweeps": t.stats["n_sweeps"], "nodes": t.n_nodes, "hash": t.tree_hash()[:12]}
     except Exception as e:      # a configuration that fails must not take the others down (all ranks fail alike)
         rec = {"config": label, "error": str(e)[:200]}
