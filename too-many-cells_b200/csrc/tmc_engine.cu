@@ -93,6 +93,7 @@ struct tmc_matrix {
   std::vector<int64_t> blk_e;        // raw entry boundaries of the ranks' row blocks: row_ptr[n_rows * r / world], r = 0..world
   int64_t* row_ptr = nullptr; int32_t* col = nullptr; double* val = nullptr;
   bool owns = false;
+  size_t raw_cap[3] = {0, 0, 0};             // owned arrays: byte capacities of row_ptr / col / val (they go back to the raw-buffer cache)
   int device = 0;
   // storage mode (DESIGN.md "factored values"): VT_F64 = val holds B itself; VT_U16 / VT_ONE = B = diag(rrow) A diag(w)
   // with A the caller's small-integer values kept as uint16 (valc) / implicit ones
@@ -422,6 +423,36 @@ static void panel_bufs_take(tmc_matrix* b, size_t need_panel, size_t need_rp, si
   f.device = b->device;
 }
 
+// The device copies of the caller's host CSR (tmc_matrix_upload / tmc_make_tree): 20 GB for c3, allocated and freed once per call
+// -- cudaFree of buffers that size takes 100-400 ms and made the end-to-end time jump between 1.12 and 1.55 s.  One retired set
+// is kept (the larger of each array), released by tmc_cache_clear().
+struct RawBufs { void* p[3] = {nullptr, nullptr, nullptr}; size_t cap[3] = {0, 0, 0}; int device = -1; };
+static RawBufs g_raw_cache;
+static void raw_bufs_release() { for (int i = 0; i < 3; ++i) { if (g_raw_cache.p[i]) cudaFree(g_raw_cache.p[i]); } g_raw_cache = RawBufs(); }
+template <class T> static T* raw_take(int which, size_t n, int device, size_t* cap_out) {
+  const size_t need = std::max<size_t>(n, 1) * sizeof(T);
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (g_raw_cache.device == device && g_raw_cache.p[which] && g_raw_cache.cap[which] >= need) {
+      T* p = static_cast<T*>(g_raw_cache.p[which]);
+      *cap_out = g_raw_cache.cap[which];
+      g_raw_cache.p[which] = nullptr; g_raw_cache.cap[which] = 0;
+      return p;
+    }
+  }
+  *cap_out = need;
+  return dalloc<T>(n);
+}
+static void raw_retire(int which, void* p, size_t cap, int device) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  if (g_raw_cache.device != device) { for (int i = 0; i < 3; ++i) { if (g_raw_cache.p[i]) cudaFree(g_raw_cache.p[i]); } g_raw_cache = RawBufs(); g_raw_cache.device = device; }
+  if (!g_raw_cache.p[which] || g_raw_cache.cap[which] < cap) {
+    if (g_raw_cache.p[which]) cudaFree(g_raw_cache.p[which]);
+    g_raw_cache.p[which] = p; g_raw_cache.cap[which] = cap;
+  } else cudaFree(p);
+}
+
 // Dense panel (DESIGN.md "dense panel"): columns present in at least `density` of the cells (TMC_PANEL_DENSITY, default 0.07)
 // are renumbered to [0, P) and stored as one byte per (row, column); the other entries (and counts > 255) form the residual
 // CSR, written to new arrays -- the caller's arrays are never modified.  On return (true) b->P/Ppad/panel/row_ptr_r/col_r/nnz_r
@@ -710,8 +741,8 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     CK(cudaMemcpy(f, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost));
     f[1] = agree_error(b, f[1]);
     b->own_prepare = false;
-    if (have_panel && b->owns && b->col) { cudaFree(b->col); b->col = nullptr; }    // only the residual is walked from here on
-    if (b->owns && b->val) { cudaFree(b->val); b->val = nullptr; }       // the fp64 copy is not needed any more
+    if (have_panel && b->owns && b->col) { raw_retire(1, b->col, b->raw_cap[1], b->device); b->col = nullptr; }    // only the residual is walked from here on
+    if (b->owns && b->val) { raw_retire(2, b->val, b->raw_cap[2], b->device); b->val = nullptr; }       // the fp64 copy is not needed any more
     restore_val();
     cudaFree(d_flags); d_flags = nullptr;
     if (df) cudaFree(df);
@@ -813,7 +844,8 @@ static tmc_matrix* upload(const tmc_csr* a, int device) {
       // owner) so that every rank ends up with the whole matrix
       b->replicated = true; b->own_lo = lo; b->own_hi = hi; b->row_offset = 0;
       b->n_rows = a->n_rows; b->n_cols = a->n_cols; b->nnz = a->nnz; b->owns = true;
-      b->row_ptr = dalloc<int64_t>(b->n_rows + 1); b->col = dalloc<int32_t>(b->nnz); b->val = dalloc<double>(b->nnz);
+      b->row_ptr = raw_take<int64_t>(0, b->n_rows + 1, b->device, &b->raw_cap[0]); b->col = raw_take<int32_t>(1, b->nnz, b->device, &b->raw_cap[1]);
+      b->val = raw_take<double>(2, b->nnz, b->device, &b->raw_cap[2]);
       CK(cudaMemcpy(b->row_ptr, a->row_ptr, sizeof(int64_t) * (b->n_rows + 1), cudaMemcpyHostToDevice));
       const int64_t k0 = a->row_ptr[lo], k1 = a->row_ptr[hi];
       h2d_cols(b->col + k0, a, k0, k1 - k0, b->device);
@@ -827,7 +859,8 @@ static tmc_matrix* upload(const tmc_csr* a, int device) {
     }
     const int64_t k0 = a->row_ptr[lo], k1 = a->row_ptr[hi];
     b->n_rows = hi - lo; b->n_cols = a->n_cols; b->nnz = k1 - k0; b->owns = true;
-    b->row_ptr = dalloc<int64_t>(b->n_rows + 1); b->col = dalloc<int32_t>(b->nnz); b->val = dalloc<double>(b->nnz);
+    b->row_ptr = raw_take<int64_t>(0, b->n_rows + 1, b->device, &b->raw_cap[0]); b->col = raw_take<int32_t>(1, b->nnz, b->device, &b->raw_cap[1]);
+    b->val = raw_take<double>(2, b->nnz, b->device, &b->raw_cap[2]);
     if (k0 == 0) {
       CK(cudaMemcpy(b->row_ptr, a->row_ptr + lo, sizeof(int64_t) * (b->n_rows + 1), cudaMemcpyHostToDevice));
     } else {
@@ -1510,6 +1543,7 @@ void tmc_cache_clear(void) {
   std::lock_guard<std::mutex> lk(g_cache_mu);
   delete g_ws_cache; g_ws_cache = nullptr;
   staging_release();
+  raw_bufs_release();
   factor_bufs_release(g_fb_cache);
   panel_bufs_release(g_pb_cache);
 }
@@ -1519,7 +1553,7 @@ void tmc_matrix_free(tmc_matrix* b) {
   retire_workspace(b->ws); b->ws = nullptr;
   factor_bufs_retire(b);
   panel_bufs_retire(b);
-  if (b->owns) { cudaFree(b->row_ptr); cudaFree(b->col); cudaFree(b->val); }
+  if (b->owns) { raw_retire(0, b->row_ptr, b->raw_cap[0], b->device); raw_retire(1, b->col, b->raw_cap[1], b->device); raw_retire(2, b->val, b->raw_cap[2], b->device); }
   delete b;
 }
 
