@@ -63,6 +63,32 @@ for name in names:
     t0 = time.time(); tr = T.hierarchical_spectral_cluster(a, normalize=True, device=lr)
     check(name, "host matrix, TMC_REPL_PREPARE=1", tr, 1e3 * (time.time() - t0))
     del os.environ["TMC_REPL_PREPARE"]
+# a zero-norm row in ONE rank's block must fail on EVERY rank (no rank may go on into the tree's collectives), in
+# both multi-GPU modes; and a slot budget of 1 must not silently truncate handed-off subtrees
+a = mats[names[0]].tolil(copy=True)
+a[a.shape[0] - 1, :] = 0          # the last rank's block gets an empty cell
+bad = sp.csr_matrix(a)
+bad.eliminate_zeros()
+codes = []
+for how in ("whole", "block"):
+    try:
+        if how == "whole":
+            T.hierarchical_spectral_cluster(bad, normalize=True, device=lr)
+        else:
+            lo, hi = tdist.row_block(bad.shape[0], rank, world)
+            blk = bad[lo:hi]
+            T.hierarchical_spectral_cluster((blk.indptr, blk.indices, blk.data, blk.shape, lo, bad.shape[0]), normalize=True, device=lr)
+        codes.append(0)
+    except T.TmcError as e:
+        codes.append(e.code)
+good = codes == [T._lib.ERR_ZERO_ROW, T._lib.ERR_ZERO_ROW]
+ok &= good
+print(f"[rank {rank}] zero-norm row in the last rank's block -> status on this rank {codes}: {'ok' if good else 'FAIL'}", flush=True)
+t1 = T.hierarchical_spectral_cluster(mats[names[0]], normalize=True, device=lr, max_active=1)
+good = t1.tree_hash() == single[names[0]].tree_hash()
+ok &= good
+print(f"[rank {rank}] max_active = 1 under {world} ranks builds the whole tree: {'ok' if good else 'FAIL'}", flush=True)
+
 # the non-default variants under a communicator: every rank runs them as a replica, results checked across ranks inside libtmc
 tk = T.hierarchical_spectral_cluster(mats[vname][:300], normalize=True, eigen_group="KMeansGroup", device=lr)
 tp = T.hierarchical_spectral_cluster(mats[vname][:300], normalize=True, num_runs=6, device=lr)
