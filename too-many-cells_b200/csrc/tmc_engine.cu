@@ -1649,8 +1649,9 @@ static int make_tree_sweeps(tmc_matrix* b, const tmc_opts* opts_in, tmc_tree** o
     eng.run_tree();
     CK(cudaEventRecord(t1, eng.s));
     eng.phase_report();
-    if (dbg) fprintf(stderr, "[tmc] run_tree wall %.2f ms (block build %.2f ms), sweeps %lld, nodes %zu\n", now() - w0, eng.build_ms,
-                     (long long)eng.n_sweeps, eng.nodes.size());
+    if (dbg) fprintf(stderr, "[tmc] rank %d: run_tree wall %.2f ms (block build %.2f ms), sweeps %lld, nodes %zu, hand-offs %d\n", eng.c.rank, now() - w0, eng.build_ms,
+                     (long long)eng.n_sweeps, eng.nodes.size(), eng.n_handoffs);
+    const double w_asm = now();
     const int m = eng.rmode ? (int)(b->own_hi - b->own_lo) : (int)b->n_rows;
     const int64_t M = b->n_rows_global;
     const int world = eng.c.world, rank = eng.c.rank;
@@ -1754,6 +1755,7 @@ static int make_tree_sweeps(tmc_matrix* b, const tmc_opts* opts_in, tmc_tree** o
       eng.allreduce_host_i32(gp);
       for (int64_t i = 0; i < M; ++i) ts->perm[i] = gp[i];
     }
+    if (dbg) fprintf(stderr, "[tmc] rank %d: tree assembly + exchange after the engine %.2f ms (includes waiting for the slowest rank)\n", rank, now() - w_asm);
     tmc_tree& t = ts->t;
     t.n_nodes = (int64_t)nn; t.n_rows = M;
     ts->bind();

@@ -24,7 +24,8 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
     tdist.init_comm(rank, world, lr, dev)
 
-CONFIGS = [("default", {}), ("p2p", {"TMC_P2P": "1"}), ("handoff 32768", {"TMC_HANDOFF_ROWS": "32768"}),
+CONFIGS = [("default", {}), ("p2p", {"TMC_P2P": "1"}), ("handoff 2048", {"TMC_HANDOFF_ROWS": "2048"}), ("handoff 8192", {"TMC_HANDOFF_ROWS": "8192"}),
+           ("handoff 16384", {"TMC_HANDOFF_ROWS": "16384"}), ("handoff 32768", {"TMC_HANDOFF_ROWS": "32768"}), ("handoff 65536", {"TMC_HANDOFF_ROWS": "65536"}),
            ("handoff 131072", {"TMC_HANDOFF_ROWS": "131072"}), ("p2p + handoff 32768", {"TMC_P2P": "1", "TMC_HANDOFF_ROWS": "32768"}),
            ("replicated prepare", {"TMC_REPL_PREPARE": "1"}), ("no sign stop", {"TMC_NO_CERT": "1"})]
 if os.environ.get("SWEEP_ONLY"):
@@ -64,7 +65,10 @@ for label, env in CONFIGS:
         ms = torch.tensor([e0.elapsed_time(e1) / steps, sum(load_ms) / steps, sum(tree_ms) / steps], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        rec = {"config": label, "ms": float(ms[0].item()), "load_ms": float(ms[1].item()), "tree_wall_ms": float(ms[2].item()), "engine_ms": t.stats["engine_ms"], "spmv_ms": t.stats["spmv_ms"], "steps": int(t.iters.sum()),
+        eng_all = [None] * world
+        if world > 1:
+            dist.all_gather_object(eng_all, round(t.stats["engine_ms"], 1))
+        rec = {"config": label, "ms": float(ms[0].item()), "load_ms": float(ms[1].item()), "tree_wall_ms": float(ms[2].item()), "engine_ms_by_rank": eng_all, "engine_ms": t.stats["engine_ms"], "spmv_ms": t.stats["spmv_ms"], "steps": int(t.iters.sum()),
                "sweeps": t.stats["n_sweeps"], "nodes": t.n_nodes, "hash": t.tree_hash()[:12]}
     except Exception as e:      # a configuration that fails must not take the others down (all ranks fail alike)
         rec = {"config": label, "error": str(e)[:200]}
