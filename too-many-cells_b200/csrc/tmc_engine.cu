@@ -943,6 +943,7 @@ struct Engine {
     w = get_workspace(b, o);
     c = w->c; s = w->stream;
     c.tol = o.tol > 0 ? o.tol : 1e-10;
+    if (getenv("TMC_TOL") && atof(getenv("TMC_TOL")) > 0) c.tol = atof(getenv("TMC_TOL"));      // experiments: overrides opts.tol
     c.min_modularity = o.min_modularity; c.min_size = std::max(1, o.min_size);
     c.max_restarts = o.max_restarts >= 0 ? o.max_restarts : 8; c.seed = o.seed;
     c.xs_min_rows = getenv("TMC_XS_ROWS") ? atoi(getenv("TMC_XS_ROWS")) : 8192;
