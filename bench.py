@@ -259,7 +259,7 @@ def main():
         step_dev(False)
     sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
+    if rank == 0 and not os.environ.get("TMC_BENCH_NO_SAMPLER"):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -438,3 +438,38 @@ def test_full_size_config2_vs_port_and_arpack():
     pt = P.make_tree(a, normalize=True, tol=1e-10, threads=min(os.cpu_count() or 1, 32))
     assert pt.n_nodes == tree.n_nodes
     assert T.tree_signature(pt.left, pt.right, pt.begin, pt.end, pt.perm) == tree.tree_hash()
+
+
+def test_full_size_config3_properties_and_sign_stop():
+    """BASELINE.json configs[2] at full size (1 M cells x 30 k genes, 1.67e9 nnz, generated on the device): no CPU restatement
+    finishes here in minutes, so the tree is checked through size-independent properties, and the sign-certified stop against
+    the plain tolerance stop (same canonical hash, same Q, fewer Lanczos steps)."""
+    import torch
+    n, g, k, d, s, binary = synth.CONFIGS["c3"]
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs a B200-sized device")
+    dev = torch.device("cuda", 0)
+    rp, col, val = synth.synth_counts_torch(n, g, k, d, s, dev, binary)
+    b = T.DeviceB.adopt_device(n, g, rp, col, val, normalize=True, device=0)
+    info = b.info()
+    assert info["value_type"] == "u16" and info["panel_cols"] > 1000 and info["panel_bits"] == 4      # counts + nibble panel
+    t1 = T.hierarchical_spectral_cluster(b)
+    assert np.array_equal(np.sort(t1.perm), np.arange(n))                         # every cell in exactly one leaf
+    leaves = t1.leaves()
+    inner = np.nonzero(t1.left >= 0)[0]
+    assert len(leaves) == len(inner) + 1 and len(leaves) > 1000
+    assert np.all(t1.q[inner] > 0) and np.all(t1.q[inner] <= 0.5)                 # split iff Q > 0; Q <= 1/2 for a bipartition
+    sizes = t1.item_end - t1.item_begin
+    assert np.all(t1.q[leaves[sizes[leaves] >= 2]] <= 0)
+    assert np.array_equal(t1.item_end[t1.left[inner]], t1.item_begin[t1.right[inner]])      # children tile the parent
+    assert np.array_equal(sizes[inner], sizes[t1.left[inner]] + sizes[t1.right[inner]])
+    for i in leaves[:: max(1, len(leaves) // 200)]:
+        assert np.all(np.diff(t1.items(i)) > 0)                                   # stable partitions: ascending rows in a leaf
+    t2 = T.hierarchical_spectral_cluster(b, sign_stop=False)
+    assert t2.tree_hash() == t1.tree_hash()
+    assert np.max(np.abs(t2.q - t1.q)) < 1e-12
+    assert int(t1.iters.sum()) < 0.8 * int(t2.iters.sum())
+    t3 = T.hierarchical_spectral_cluster(b, seed=20261020)                        # another start vector: the same tree
+    assert t3.tree_hash() == t1.tree_hash()
+    b.free()
+    T._lib.load().tmc_cache_clear()

@@ -1502,8 +1502,13 @@ int tmc_row_l2(const tmc_csr* b2, double* val_out, double* norm_out) {
 int tmc_matrix_upload(const tmc_csr* b2, int normalize, int device, tmc_matrix** out) {
   return guarded([&] {
     if (!out) throw TmcError(TMC_ERR_INVALID, "null out");
+    const bool dbg = getenv("TMC_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double w0 = now();
     tmc_matrix* b = upload(b2, device);
+    const double w1 = now();
     try { prepare_matrix(b, normalize); } catch (...) { tmc_matrix_free(b); throw; }
+    if (dbg) { cudaDeviceSynchronize(); fprintf(stderr, "[tmc] tmc_matrix_upload: host -> device %.2f ms, prepare %.2f ms\n", w1 - w0, now() - w1); }
     *out = b;
   });
 }
@@ -1527,7 +1532,12 @@ int tmc_matrix_adopt_dev(int64_t n_rows, int64_t n_cols, int64_t nnz, const int6
           CK(cudaMemcpy(&b->blk_e[r], row_ptr_dev + n_rows * r / g_nccl.world, sizeof(int64_t), cudaMemcpyDeviceToHost));
       }
       b->row_ptr = const_cast<int64_t*>(row_ptr_dev); b->col = const_cast<int32_t*>(col_dev); b->val = val_dev;
+      const double w0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
       prepare_matrix(b, normalize);
+      if (getenv("TMC_DEBUG")) {
+        cudaDeviceSynchronize();
+        fprintf(stderr, "[tmc] tmc_matrix_adopt_dev: prepare %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - w0);
+      }
     } catch (...) { tmc_matrix_free(b); throw; }
     *out = b;
   });
@@ -1777,8 +1787,13 @@ static int make_tree_sweeps(tmc_matrix* b, const tmc_opts* opts_in, tmc_tree** o
 int tmc_make_tree(const tmc_csr* b2, const tmc_opts* opts, tmc_tree** out) {
   tmc_matrix* b = nullptr;
   if (!opts) return fail(TMC_ERR_INVALID, "null opts");
+  const bool dbg = getenv("TMC_DEBUG") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double w0 = now();
   int st = tmc_matrix_upload(b2, opts->normalize, opts->device, &b);
   if (st != TMC_OK) return st;
+  const double w1 = now();
+  struct Dbg { bool on; double w0, w1; decltype(now)& clk; ~Dbg() { if (on) fprintf(stderr, "[tmc] tmc_make_tree: upload + prepare %.2f ms, tree + free %.2f ms\n", w1 - w0, clk() - w1); } } dbg_{dbg, w0, w1, now};
   if (opts->eigen_group == 1 && opts->num_eigen > 1) {
     // KMeansGroup on several eigenvectors assembles C_S per node from the host copy of B (tmc_variants.cuh)
     st = guarded([&] { check_variant_opts(opts); require_default_types(b2, "KMeansGroup with num_eigen > 1"); });
