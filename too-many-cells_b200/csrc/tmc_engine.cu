@@ -128,6 +128,52 @@ template <class T> static T* dalloc(size_t n) {
   return p;
 }
 
+// Small device scratch (flags, per-column vectors, scan temporaries, staging of the host-side all-reduces): cudaMalloc / cudaFree
+// calls in the load path showed up as 10-400 ms spikes of the step time, so these buffers come from a pool of retired blocks
+// (power-of-two size classes, at most 512 MB held; tmc_cache_clear() releases them).
+namespace pool {
+static std::mutex mu;
+static std::vector<std::pair<void*, int>> owned;      // every pooled pointer with its size class
+static std::vector<void*> free_list[48];
+static size_t held = 0;
+static int cls_of_bytes(size_t bytes) { int c = 8; while (((size_t)1 << c) < bytes) ++c; return c; }
+static void* take(size_t bytes) {
+  const int c = cls_of_bytes(std::max<size_t>(bytes, 1));
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!free_list[c].empty()) { void* p = free_list[c].back(); free_list[c].pop_back(); held -= (size_t)1 << c; return p; }
+  }
+  void* p = nullptr;
+  CK(cudaMalloc(&p, (size_t)1 << c));
+  std::lock_guard<std::mutex> lk(mu);
+  owned.push_back({p, c});
+  return p;
+}
+static void give(void* p) {
+  if (!p) return;
+  std::unique_lock<std::mutex> lk(mu);
+  for (size_t i = 0; i < owned.size(); ++i)
+    if (owned[i].first == p) {
+      const int c = owned[i].second;
+      if (held + ((size_t)1 << c) <= ((size_t)512 << 20)) { free_list[c].push_back(p); held += (size_t)1 << c; return; }
+      owned[i] = owned.back(); owned.pop_back();
+      break;
+    }
+  lk.unlock();
+  cudaFree(p);
+}
+static void release_all() {
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto& fl : free_list) { for (void* p : fl) cudaFree(p); fl.clear(); }
+  // blocks still handed out stay registered; forget the freed ones
+  std::vector<std::pair<void*, int>> keep;
+  held = 0;
+  owned.swap(keep);
+}
+}  // namespace pool
+template <class T> static T* palloc(size_t n) { return static_cast<T*>(pool::take(std::max<size_t>(n, 1) * sizeof(T))); }
+static void pfree(void* p) { pool::give(p); }
+
 struct Workspace {
   Ctx c{};
   int K = 0, max_active = 0, use_t = 0, tcap = 0, device = 0, vt = 0;
@@ -303,23 +349,23 @@ static void ensure_raw_complete(tmc_matrix* b) {
 // must be seen by every rank, or the others would go on and wait forever in the first collective of the tree build.
 static int agree_error(const tmc_matrix* b, int e) {
   if (!sharded_coll(b)) return e;
-  int* d = dalloc<int>(1);
+  int* d = palloc<int>(1);
   cudaMemcpy(d, &e, sizeof(int), cudaMemcpyHostToDevice);
   const int r = g_nccl.AllReduce(d, d, 1, NCCL_INT32, NCCL_MAX, g_nccl.comm, 0);
-  cudaMemcpy(&e, d, sizeof(int), cudaMemcpyDeviceToHost); cudaFree(d);
+  cudaMemcpy(&e, d, sizeof(int), cudaMemcpyDeviceToHost); pfree(d);
   if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(error code) failed");
   return e;
 }
 
 // normalise the device values in place: optional idf (b1ToB2), then row L2 (b2ToB)
 static void normalise_dev(tmc_matrix* b, int normalize, double* norm_out_dev, double* idf_out_dev, bool do_l2) {
-  int* d_err = dalloc<int>(1);
+  int* d_err = palloc<int>(1);
   int* df = nullptr; double* idf = nullptr;
   try {
     CK(cudaMemset(d_err, 0, sizeof(int)));
     const int grid = 148 * 8;
     if (normalize) {
-      df = dalloc<int>(b->n_cols); idf = idf_out_dev ? idf_out_dev : dalloc<double>(b->n_cols);
+      df = palloc<int>(b->n_cols); idf = idf_out_dev ? idf_out_dev : palloc<double>(b->n_cols);
       CK(cudaMemset(df, 0, sizeof(int) * b->n_cols));
       k_df_count<<<grid, 256>>>(b->col, b->val, b->nnz, (int)b->n_cols, df, d_err);
       if (sharded_coll(b)) {      // df over all ranks' row blocks
@@ -333,18 +379,18 @@ static void normalise_dev(tmc_matrix* b, int normalize, double* norm_out_dev, do
     CK(cudaGetLastError());
     int e = 0;
     CK(cudaMemcpy(&e, d_err, sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(d_err); d_err = nullptr;
-    if (df) cudaFree(df);
-    if (idf && !idf_out_dev) cudaFree(idf);
+    pfree(d_err); d_err = nullptr;
+    if (df) pfree(df);
+    if (idf && !idf_out_dev) pfree(idf);
     df = nullptr; idf = nullptr;
     e = agree_error(b, e);
     std::string msg;
     int st = err_to_status(e, &msg);
     if (st != TMC_OK) throw TmcError(st, msg);
   } catch (...) {
-    if (d_err) cudaFree(d_err);
-    if (df) cudaFree(df);
-    if (idf && !idf_out_dev) cudaFree(idf);
+    if (d_err) pfree(d_err);
+    if (df) pfree(df);
+    if (idf && !idf_out_dev) pfree(idf);
     throw;
   }
 }
@@ -481,10 +527,10 @@ static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev,
   const size_t max_cols_local = std::min<size_t>(65536, (free_b / 4) * (nib ? 2 : 1) / (size_t)std::max<int64_t>(1, b->n_rows) / 512 * 512);
   size_t max_cols = max_cols_local;
   if (g_nccl.comm && g_nccl.world > 1) {          // every rank must pick the same columns
-    int* d = dalloc<int>(1); int h = (int)max_cols_local;
+    int* d = palloc<int>(1); int h = (int)max_cols_local;
     cudaMemcpy(d, &h, sizeof(int), cudaMemcpyHostToDevice);
     int r = g_nccl.AllReduce(d, d, 1, NCCL_INT32, NCCL_MIN, g_nccl.comm, 0);
-    cudaMemcpy(&h, d, sizeof(int), cudaMemcpyDeviceToHost); cudaFree(d);
+    cudaMemcpy(&h, d, sizeof(int), cudaMemcpyDeviceToHost); pfree(d);
     if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(panel width) failed");
     max_cols = (size_t)h;
   }
@@ -507,7 +553,7 @@ static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev,
     int a = 0, r = P;
     for (int j = 0; j < n; ++j) { const int id = in[j] ? a++ : r++; old2new[j] = id; new2old[id] = j; }
   }
-  int* maps = dalloc<int>(2 * (size_t)n);
+  int* maps = palloc<int>(2 * (size_t)n);
   long long* cnt = nullptr; void* tmp = nullptr;
   try {
     CK(cudaMemcpy(maps, old2new.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
@@ -522,7 +568,7 @@ static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev,
     }
     size_t bytes = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt, cnt, (int)b->n_rows + 1));
-    CK(cudaMalloc(&tmp, std::max<size_t>(bytes, 16)));
+    tmp = pool::take(std::max<size_t>(bytes, 16));
     CK(cub::DeviceScan::ExclusiveSum(tmp, bytes, cnt, cnt, (int)b->n_rows + 1));
     long long nnz_r = 0;
     CK(cudaMemcpy(&nnz_r, cnt + b->n_rows, sizeof(long long), cudaMemcpyDeviceToHost));
@@ -534,12 +580,12 @@ static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev,
     CK(cudaGetLastError());
     int f = 0;
     CK(cudaMemcpy(&f, d_flags, sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(maps); maps = nullptr; cudaFree(tmp); tmp = nullptr;
+    pfree(maps); maps = nullptr; pfree(tmp); tmp = nullptr;
     if (g_nccl.comm && g_nccl.world > 1) {
-      int* d = dalloc<int>(1); int h = (f & 32) ? 1 : 0;
+      int* d = palloc<int>(1); int h = (f & 32) ? 1 : 0;
       cudaMemcpy(d, &h, sizeof(int), cudaMemcpyHostToDevice);
       int r = g_nccl.AllReduce(d, d, 1, NCCL_INT32, NCCL_SUM, g_nccl.comm, 0);
-      cudaMemcpy(&h, d, sizeof(int), cudaMemcpyDeviceToHost); cudaFree(d);
+      cudaMemcpy(&h, d, sizeof(int), cudaMemcpyDeviceToHost); pfree(d);
       if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(panel flag) failed");
       if (h) f |= 32;
     }
@@ -554,7 +600,7 @@ static bool build_panel(tmc_matrix* b, const int* df_dev, const double* idf_dev,
     }
     b->P = P; b->Ppad = Ppad; b->pnib = nib; b->pw = pw; b->nnz_r = nnz_r;
     return true;
-  } catch (...) { if (maps) cudaFree(maps); if (tmp) cudaFree(tmp); throw; }
+  } catch (...) { if (maps) pfree(maps); if (tmp) pfree(tmp); throw; }
 }
 
 // Decide the storage mode and compute what the engine needs from the device-resident input values.
@@ -602,7 +648,7 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
   b->own_prepare = b->replicated && world > 1 && do_l2 && getenv("TMC_REPL_PREPARE") == nullptr && (int)b->blk_e.size() == world + 1;
   if (!b->own_prepare) ensure_raw_complete(b);
   renumber_columns(b);
-  int* d_flags = dalloc<int>(6);          // [0] value flags, [1] error code, [2..5] two 64-bit counters of small values
+  int* d_flags = palloc<int>(6);          // [0] value flags, [1] error code, [2..5] two 64-bit counters of small values
   int* df = nullptr; double* idf = nullptr;
   double* wrec = nullptr; double* counts = nullptr; double* borrowed_val = nullptr;
   auto restore_val = [&]() {        // a temporary count array standing in for a borrowed value array
@@ -633,18 +679,18 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     CK(cudaMemcpy(n_small, d_small, sizeof(n_small), cudaMemcpyDeviceToHost));
     if (sharded_coll(b)) {
       // row-block inputs: every rank must take the same decision (storage mode, errors), or the others would wait forever
-      int* bits = dalloc<int>(5); int hb[5];
+      int* bits = palloc<int>(5); int hb[5];
       for (int i = 0; i < 5; ++i) hb[i] = (f[0] >> i) & 1;
       cudaMemcpy(bits, hb, sizeof(hb), cudaMemcpyHostToDevice);
       int r = g_nccl.AllReduce(bits, bits, 5, NCCL_INT32, NCCL_SUM, g_nccl.comm, 0);
-      cudaMemcpy(hb, bits, sizeof(hb), cudaMemcpyDeviceToHost); cudaFree(bits);
+      cudaMemcpy(hb, bits, sizeof(hb), cudaMemcpyDeviceToHost); pfree(bits);
       if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(value flags) failed");
       f[0] = 0; for (int i = 0; i < 5; ++i) if (hb[i]) f[0] |= 1 << i;
       std::vector<double> ns = {(double)n_small[0], (double)n_small[1]};     // exact below 2^53
-      double* dn = dalloc<double>(2);
+      double* dn = palloc<double>(2);
       cudaMemcpy(dn, ns.data(), 16, cudaMemcpyHostToDevice);
       r = g_nccl.AllReduce(dn, dn, 2, NCCL_FLOAT64, NCCL_SUM, g_nccl.comm, 0);
-      cudaMemcpy(ns.data(), dn, 16, cudaMemcpyDeviceToHost); cudaFree(dn);
+      cudaMemcpy(ns.data(), dn, 16, cudaMemcpyDeviceToHost); pfree(dn);
       if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(small-value counts) failed");
       n_small[0] = (unsigned long long)ns[0]; n_small[1] = (unsigned long long)ns[1];
     }
@@ -654,7 +700,7 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     bool small_int = !(f[0] & 8) && getenv("TMC_NO_FACTORED") == nullptr;
     if (!small_int && !b->has_neg && !normalize && b->nnz > 0 && getenv("TMC_NO_FACTORED") == nullptr && getenv("TMC_NO_RECOVER") == nullptr) {
       // B2 = A diag(w) handed over already scaled (Cluster.hs:147 receives the tf-idf matrix): recover A and w if that is exact
-      wrec = dalloc<double>(b->n_cols);
+      wrec = palloc<double>(b->n_cols);
       k_fill_f64<<<(unsigned)((b->n_cols + 255) / 256), 256>>>(wrec, b->n_cols, INFINITY);
       k_colmin<<<grid, 256>>>(b->col + e0, b->val + e0, e1 - e0, reinterpret_cast<unsigned long long*>(wrec));
       const bool sharded = sharded_coll(b);
@@ -662,7 +708,7 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
         throw TmcError(TMC_ERR_COMM, "ncclAllReduce(column minima) failed");
       k_colmin_fix<<<(int)((b->n_cols + 255) / 256), 256>>>(wrec, (int)b->n_cols);
       CK(cudaMemset(d_flags + 2, 0, 4 * sizeof(int)));
-      int* d_rf = dalloc<int>(1);
+      int* d_rf = palloc<int>(1);
       CK(cudaMemset(d_rf, 0, sizeof(int)));
       k_factor_check<<<grid, 256>>>(b->col + e0, b->val + e0, e1 - e0, wrec, nullptr, d_rf, d_small);
       int rf = 0;
@@ -670,11 +716,11 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
       CK(cudaMemcpy(n_small, d_small, sizeof(n_small), cudaMemcpyDeviceToHost));
       if (sharded) {
         std::vector<double> ns = {(double)n_small[0], (double)n_small[1], (rf & 8) ? 1.0 : 0.0, (rf & 16) ? 1.0 : 0.0};
-        double* dn = dalloc<double>(4);
+        double* dn = palloc<double>(4);
         cudaMemcpy(dn, ns.data(), 32, cudaMemcpyHostToDevice);
         int r = g_nccl.AllReduce(dn, dn, 4, NCCL_FLOAT64, NCCL_SUM, g_nccl.comm, 0);
-        cudaMemcpy(ns.data(), dn, 32, cudaMemcpyDeviceToHost); cudaFree(dn);
-        if (r != 0) { cudaFree(d_rf); throw TmcError(TMC_ERR_COMM, "ncclAllReduce(factor check) failed"); }
+        cudaMemcpy(ns.data(), dn, 32, cudaMemcpyDeviceToHost); pfree(dn);
+        if (r != 0) { pfree(d_rf); throw TmcError(TMC_ERR_COMM, "ncclAllReduce(factor check) failed"); }
         n_small[0] = (unsigned long long)ns[0]; n_small[1] = (unsigned long long)ns[1];
         rf = (ns[2] > 0 ? 8 : 0) | (ns[3] > 0 ? 16 : 0);
       }
@@ -686,11 +732,11 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
         b->val = counts;
         small_int = true;
         f[0] = (f[0] & ~(8 | 16)) | (rf & 16);
-      } else { cudaFree(wrec); wrec = nullptr; }
-      cudaFree(d_rf);
+      } else { pfree(wrec); wrec = nullptr; }
+      pfree(d_rf);
     }
     if (!small_int) {
-      cudaFree(d_flags); d_flags = nullptr;
+      pfree(d_flags); d_flags = nullptr;
       b->vt = VT_F64;
       if (b->own_prepare) { ensure_raw_complete(b); b->own_prepare = false; }      // B itself is materialised: every rank does all of it
       normalise_dev(b, normalize, nullptr, nullptr, do_l2);
@@ -700,7 +746,7 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     if (wrec) { idf = wrec; wrec = nullptr; }        // the recovered column weights take the place of idf
     const bool want_panel = getenv("TMC_NO_PANEL") == nullptr;
     if (normalize || want_panel) {       // column frequencies: idf, and the choice of the dense panel
-      df = dalloc<int>(b->n_cols);
+      df = palloc<int>(b->n_cols);
       CK(cudaMemset(df, 0, sizeof(int) * b->n_cols));
       k_df_count<<<grid, 256>>>(b->col + e0, b->val + e0, e1 - e0, (int)b->n_cols, df, d_flags + 1);
       if (sharded_coll(b)) {
@@ -709,7 +755,7 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
       }
     }
     if (normalize) {
-      idf = dalloc<double>(b->n_cols);
+      idf = palloc<double>(b->n_cols);
       k_idf<<<(int)((b->n_cols + 255) / 256), 256>>>(df, (int)b->n_cols, (double)b->n_rows_global, idf);
     }
     factor_bufs_acquire(b, b->vt == VT_U16);
@@ -744,18 +790,18 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     if (have_panel && b->owns && b->col) { raw_retire(1, b->col, b->raw_cap[1], b->device); b->col = nullptr; }    // only the residual is walked from here on
     if (b->owns && b->val) { raw_retire(2, b->val, b->raw_cap[2], b->device); b->val = nullptr; }       // the fp64 copy is not needed any more
     restore_val();
-    cudaFree(d_flags); d_flags = nullptr;
-    if (df) cudaFree(df);
-    if (idf) cudaFree(idf);
+    pfree(d_flags); d_flags = nullptr;
+    if (df) pfree(df);
+    if (idf) pfree(idf);
     df = nullptr; idf = nullptr;
     if (f[1]) { std::string msg; int st = err_to_status(f[1], &msg); throw TmcError(st, msg); }
   } catch (...) {
     b->own_prepare = false;
     restore_val();
-    if (d_flags) cudaFree(d_flags);
-    if (df) cudaFree(df);
-    if (idf) cudaFree(idf);
-    if (wrec) cudaFree(wrec);
+    if (d_flags) pfree(d_flags);
+    if (df) pfree(df);
+    if (idf) pfree(idf);
+    if (wrec) pfree(wrec);
     throw;
   }
 }
@@ -900,6 +946,8 @@ struct Engine {
   double alg_panel_bytes = 0;   // panel bytes of the pairs: one byte per (row, panel column) and half
   double build_ms = 0;
   int tg_variant = getenv("TMC_TG") ? atoi(getenv("TMC_TG")) : 0;
+  int tp_nr = getenv("TMC_TP_NR") ? atoi(getenv("TMC_TP_NR")) : 8;          // rows per register set of the nibble panel kernels (experiments)
+  int gp_nr = getenv("TMC_GP_NR") ? atoi(getenv("TMC_GP_NR")) : 4;
   int gu_lpr = getenv("TMC_GU_LPR") ? atoi(getenv("TMC_GU_LPR")) : 32;      // lanes per row of the residual gather (32 | 16 | 8)
   // TMC_DEBUG=2: per-phase device time (CUDA events between the launches of a sweep), printed after the tree build
   bool phase_prof = getenv("TMC_DEBUG") && atoi(getenv("TMC_DEBUG")) >= 2;
@@ -1107,25 +1155,25 @@ struct Engine {
   }
   void allreduce_host_i32(std::vector<int>& v) {       // small host-side exchanges at the end of the tree build
     if (c.world <= 1 || v.empty()) return;
-    int* d = dalloc<int>(v.size());
+    int* d = palloc<int>(v.size());
     try {
       CK(cudaMemcpyAsync(d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, s));
       nccl_check(g_nccl.AllReduce(d, d, v.size(), NCCL_INT32, NCCL_SUM, g_nccl.comm, s), "ncclAllReduce(i32)");
       CK(cudaMemcpyAsync(v.data(), d, sizeof(int) * v.size(), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
-    } catch (...) { cudaFree(d); throw; }
-    cudaFree(d);
+    } catch (...) { pfree(d); throw; }
+    pfree(d);
   }
   void allreduce_host_f64(std::vector<double>& v) {
     if (c.world <= 1 || v.empty()) return;
-    double* d = dalloc<double>(v.size());
+    double* d = palloc<double>(v.size());
     try {
       CK(cudaMemcpyAsync(d, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice, s));
       nccl_check(g_nccl.AllReduce(d, d, v.size(), NCCL_FLOAT64, NCCL_SUM, g_nccl.comm, s), "ncclAllReduce(f64)");
       CK(cudaMemcpyAsync(v.data(), d, sizeof(double) * v.size(), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
-    } catch (...) { cudaFree(d); throw; }
-    cudaFree(d);
+    } catch (...) { pfree(d); throw; }
+    pfree(d);
   }
 
   // One sweep: every live slot advances by one step of its lifecycle
@@ -1247,7 +1295,9 @@ struct Engine {
         // up to 512 rows per CTA (one atomicAdd per column and CTA), fewer when that would leave SMs idle (small matrices, tree tails)
         const int G = std::max(1, std::min(512 / RV, nvch * nslab / 296));
         const int wslab = ((c.Ppad / 512 + nslab - 1) / nslab);      // warps per CTA
-        if (c.pnib) k_tpanel<8, 1><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G);
+        if (c.pnib && tp_nr == 4) k_tpanel<4, 1><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G);
+        else if (c.pnib && tp_nr == 16) k_tpanel<16, 1><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G);
+        else if (c.pnib) k_tpanel<8, 1><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G);
         else k_tpanel<4, 0><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G);
         n_launch++;
       }
@@ -1257,7 +1307,9 @@ struct Engine {
     }
     if (n_ga && (nch || ngch)) {
       if (c.P && nvch) {      // dense panel half of u = A y -> pacc
-        if (c.pnib) k_gather_panel<4, 1><<<nvch, 256, 0, s>>>(c); else k_gather_panel<4, 0><<<nvch, 256, 0, s>>>(c);
+        if (c.pnib && gp_nr == 2) k_gather_panel<2, 1><<<nvch, 256, 0, s>>>(c);
+        else if (c.pnib && gp_nr == 8) k_gather_panel<8, 1><<<nvch, 256, 0, s>>>(c);
+        else if (c.pnib) k_gather_panel<4, 1><<<nvch, 256, 0, s>>>(c); else k_gather_panel<4, 0><<<nvch, 256, 0, s>>>(c);
         n_launch++;
       }
       if (ngch) { VT_DISPATCH(c.vt, k_gather_smem<VT, 4><<<ngch, 1024, gs_smem, s>>>(c)); n_launch++; }      // large nodes: y[P, n) in shared memory
@@ -1555,6 +1607,7 @@ void tmc_cache_clear(void) {
   delete g_ws_cache; g_ws_cache = nullptr;
   staging_release();
   raw_bufs_release();
+  pool::release_all();
   factor_bufs_release(g_fb_cache);
   panel_bufs_release(g_pb_cache);
 }
@@ -1596,10 +1649,10 @@ static uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
 static void agree_hash(uint64_t h, const char* what) {
   if (!(g_nccl.comm && g_nccl.world > 1)) return;
   int v[4] = {(int)(h & 0x7fffffff), (int)((h >> 31) & 0x7fffffff), -(int)(h & 0x7fffffff), -(int)((h >> 31) & 0x7fffffff)};
-  int* d = dalloc<int>(4);
+  int* d = palloc<int>(4);
   cudaMemcpy(d, v, sizeof(v), cudaMemcpyHostToDevice);
   const int r = g_nccl.AllReduce(d, d, 4, NCCL_INT32, NCCL_MIN, g_nccl.comm, 0);
-  int o[4]; cudaMemcpy(o, d, sizeof(o), cudaMemcpyDeviceToHost); cudaFree(d);
+  int o[4]; cudaMemcpy(o, d, sizeof(o), cudaMemcpyDeviceToHost); pfree(d);
   if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(replica digest) failed");
   if (o[0] != -o[2] || o[1] != -o[3]) throw TmcError(TMC_ERR_COMM, std::string("the ranks built different results for ") + what);
 }
