@@ -648,6 +648,15 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
   b->own_prepare = b->replicated && world > 1 && do_l2 && getenv("TMC_REPL_PREPARE") == nullptr && (int)b->blk_e.size() == world + 1;
   if (!b->own_prepare) ensure_raw_complete(b);
   renumber_columns(b);
+  const bool stage_dbg = getenv("TMC_DEBUG") && atoi(getenv("TMC_DEBUG")) >= 3;
+  double stage_t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  auto stage = [&](const char* what) {      // TMC_DEBUG=3: where the load time goes (synchronises: not for timing runs)
+    if (!stage_dbg) return;
+    cudaDeviceSynchronize();
+    const double t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    fprintf(stderr, "[tmc]   prepare: %-28s %8.2f ms\n", what, t - stage_t);
+    stage_t = t;
+  };
   int* d_flags = palloc<int>(6);          // [0] value flags, [1] error code, [2..5] two 64-bit counters of small values
   int* df = nullptr; double* idf = nullptr;
   double* wrec = nullptr; double* counts = nullptr; double* borrowed_val = nullptr;
@@ -677,6 +686,7 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     unsigned long long n_small[2] = {0, 0};
     CK(cudaMemcpy(f, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(n_small, d_small, sizeof(n_small), cudaMemcpyDeviceToHost));
+    stage("scan values");
     if (sharded_coll(b)) {
       // row-block inputs: every rank must take the same decision (storage mode, errors), or the others would wait forever
       int* bits = palloc<int>(5); int hb[5];
@@ -758,12 +768,15 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
       idf = palloc<double>(b->n_cols);
       k_idf<<<(int)((b->n_cols + 255) / 256), 256>>>(df, (int)b->n_cols, (double)b->n_rows_global, idf);
     }
+    stage("document frequencies, idf");
     factor_bufs_acquire(b, b->vt == VT_U16);
+    stage("factor buffers");
     auto row_factors = [&]() {
       if (do_l2) k_row_factor<<<grid, 256>>>(b->row_ptr + rl, b->col, b->val, idf, (int)(rh - rl), b->rrow + rl, d_flags + 1);
       else k_fill_f64<<<(unsigned)((b->n_rows + 255) / 256), 256>>>(b->rrow, b->n_rows, 1.0);      // truncated SVD of B2 itself: no row factor
     };
     row_factors();
+    stage("row factors");
     bool have_panel = false;
     if (want_panel) {
       // cell format: nibbles when (nearly) everything that fits a byte also fits a nibble (UMI counts), else bytes
@@ -772,6 +785,7 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
       have_panel = build_panel(b, df, idf, d_flags, nib);
       if (!have_panel) panel_bufs_retire(b);
     }
+    stage("panel + residual");
     if (have_panel && b->own_prepare)
       gather_blocks(b->rrow, [&](int r) { return blk_row(b, r) * (int64_t)sizeof(double); }, "row factors");
     if (!have_panel) {
@@ -787,6 +801,7 @@ static void prepare_matrix(tmc_matrix* b, int normalize, bool do_l2 = true) {
     CK(cudaMemcpy(f, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost));
     f[1] = agree_error(b, f[1]);
     b->own_prepare = false;
+    stage("gather / finish");
     if (have_panel && b->owns && b->col) { raw_retire(1, b->col, b->raw_cap[1], b->device); b->col = nullptr; }    // only the residual is walked from here on
     if (b->owns && b->val) { raw_retire(2, b->val, b->raw_cap[2], b->device); b->val = nullptr; }       // the fp64 copy is not needed any more
     restore_val();
