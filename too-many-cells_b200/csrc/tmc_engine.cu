@@ -963,6 +963,7 @@ struct Engine {
   int tg_variant = getenv("TMC_TG") ? atoi(getenv("TMC_TG")) : 0;
   int tp_nr = getenv("TMC_TP_NR") ? atoi(getenv("TMC_TP_NR")) : 8;          // rows per register set of the nibble panel kernels (experiments)
   int gp_nr = getenv("TMC_GP_NR") ? atoi(getenv("TMC_GP_NR")) : 4;
+  int tp_narrow = getenv("TMC_TP_NARROW") ? atoi(getenv("TMC_TP_NARROW")) : 0;      // 8 | 16: k_tpanel_narrow<NR>
   int gu_lpr = getenv("TMC_GU_LPR") ? atoi(getenv("TMC_GU_LPR")) : 32;      // lanes per row of the residual gather (32 | 16 | 8)
   // TMC_DEBUG=2: per-phase device time (CUDA events between the launches of a sweep), printed after the tree build
   bool phase_prof = getenv("TMC_DEBUG") && atoi(getenv("TMC_DEBUG")) >= 2;
@@ -1310,7 +1311,14 @@ struct Engine {
         // up to 512 rows per CTA (one atomicAdd per column and CTA), fewer when that would leave SMs idle (small matrices, tree tails)
         const int G = std::max(1, std::min(512 / RV, nvch * nslab / 296));
         const int wslab = ((c.Ppad / 512 + nslab - 1) / nslab);      // warps per CTA
-        if (c.pnib && tp_nr == 4) k_tpanel<4, 1><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G);
+        if (c.pnib && tp_narrow) {      // experiment: 4-byte lanes, 256 columns per warp, 8 warps (2048 columns) per CTA
+          const int nsl = (c.Ppad + 2047) / 2048;
+          const int Gn = std::max(1, std::min(512 / RV, nvch * nsl / 740));
+          if (tp_narrow == 16) k_tpanel_narrow<16><<<dim3((nvch + Gn - 1) / Gn, nsl), 256, 0, s>>>(c, Gn);
+          else if (tp_narrow == 4) k_tpanel_narrow<4><<<dim3((nvch + Gn - 1) / Gn, nsl), 256, 0, s>>>(c, Gn);
+          else k_tpanel_narrow<8><<<dim3((nvch + Gn - 1) / Gn, nsl), 256, 0, s>>>(c, Gn);
+        }
+        else if (c.pnib && tp_nr == 4) k_tpanel<4, 1><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G);
         else if (c.pnib && tp_nr == 16) k_tpanel<16, 1><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G);
         else if (c.pnib) k_tpanel<8, 1><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G);
         else k_tpanel<4, 0><<<dim3((nvch + G - 1) / G, nslab), 32 * wslab, 0, s>>>(c, G);

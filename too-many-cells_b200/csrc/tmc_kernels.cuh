@@ -834,6 +834,76 @@ __global__ void __launch_bounds__(256) k_tpanel(Ctx c, int G) {
   }
   flush();
 }
+// EXPERIMENT (TMC_TP_NARROW=1): the nibble kernel with 4-byte lanes -- a lane owns ONE 32-bit word (8 columns), a warp 256
+// columns, so 8 accumulators and NR words per register set instead of 16 and 2*NR: about 50 registers, 5 CTAs per SM instead of
+// 3.  Twice the load instructions for the same bytes (they are 1/8 of the instruction stream), more warps to hide them behind.
+template <int NR>
+__global__ void __launch_bounds__(256) k_tpanel_narrow(Ctx c, int G) {
+  __shared__ int s_row[TMC_MAX_CHUNK + 2 * NR];
+  __shared__ double s_x[TMC_MAX_CHUNK + 2 * NR];
+  const int nv = *c.n_vchunks;
+  const int i0 = blockIdx.x * G;
+  if (i0 >= nv) return;
+  const int i1 = min(nv, i0 + G);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int colw = (blockIdx.y * (blockDim.x >> 5) + warp) * 256;
+  const bool on = colw < c.Ppad;
+  const unsigned* __restrict__ pb = reinterpret_cast<const unsigned*>(c.panel + (colw >> 1)) + lane;
+  const size_t ws = (size_t)c.pw / sizeof(unsigned);
+  double acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+  int cur = -1;
+  auto flush = [&]() {
+    if (cur >= 0 && on) {
+      double* y = c.Y + (int64_t)cur * c.ystride;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int cj = colw + lane * 8 + k;
+        const double down = TMC_PANEL_DOWN / (double)(1u << (4 * k));
+        if (cj < c.P && acc[k] != 0.0) atomicAdd(y + cj, acc[k] * down * __ldg(c.w2col + cj));
+        acc[k] = 0.0;
+      }
+    }
+  };
+  for (int i = i0; i < i1; ++i) {
+    const Chunk ch = c.vchunks[i];
+    const int state = c.st[ch.slot].state;
+    if (ch.slot != cur) { flush(); cur = ch.slot; }
+    if (state != ST_DEG && state != ST_LAN && state != ST_MOD) continue;
+    __syncthreads();
+    const int lenp = (ch.len + 2 * NR - 1) / (2 * NR) * (2 * NR);
+    for (int t = threadIdx.x; t < lenp; t += blockDim.x) {
+      const bool ok = t < ch.len;
+      s_row[t] = c.perm[ch.begin + (ok ? t : ch.len - 1)];
+      s_x[t] = ok ? c.xin[ch.begin + t] * TMC_PANEL_UP : 0.0;
+    }
+    __syncthreads();
+    if (!on) continue;
+    unsigned d0[NR], d1[NR];
+    auto load = [&](unsigned* d, int r) {
+#pragma unroll
+      for (int q = 0; q < NR; ++q) d[q] = __ldg(pb + (size_t)s_row[r + q] * ws);
+    };
+    auto fma_rows = [&](const unsigned* d, int r) {
+#pragma unroll
+      for (int q = 0; q < NR; ++q) {
+        const double xv = s_x[r + q];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += u4_f64(d[q], k) * xv;
+      }
+    };
+    load(d0, 0);
+    for (int r = 0; r < lenp; r += 2 * NR) {
+      load(d1, r + NR);
+      fma_rows(d0, r);
+      if (r + 2 * NR < lenp) load(d0, r + 2 * NR);
+      fma_rows(d1, r + NR);
+    }
+  }
+  flush();
+}
+
 // pacc[p] = sum_{j < P} panel[row(p)][j] * y[j]; one CTA per vector chunk.  y is staged in shared memory in blocks of TMC_GP_CB
 // columns, stored so that the eight 16-byte reads of a lane (its 16 columns of a 512-column step) are conflict-free: the pair
 // (16*lane + 2j, 16*lane + 2j + 1) sits at double2 index j*32 + lane.  A warp works on NR rows at a time (every y value read
