@@ -22,9 +22,18 @@ for name in names:
     n, g = synth.CONFIGS[name][:2]
     mats[name] = sp.csr_matrix((dv, ix, ip), shape=(n, g))
     single[name] = T.hierarchical_spectral_cluster(mats[name], normalize=True, device=lr)      # before the communicator exists
+# other value kinds through the load-time fallbacks: a tf-idf matrix handed over as fp64 (factor recovery), an fp64 matrix that is
+# not a count matrix times column weights (B materialised), and a signed matrix (two degree passes, no deflation)
 vname = names[0]
 v_single = (T.hierarchical_spectral_cluster(mats[vname][:300], normalize=True, eigen_group="KMeansGroup"),
             T.hierarchical_spectral_cluster(mats[vname][:300], normalize=True, num_runs=6))
+a0 = mats[names[0]]
+b2 = T.tfidf_scale_sparse_mat(a0)                                   # B2 = counts * diag(idf): recognised bit for bit
+rng = np.random.default_rng(4)
+noisy = b2.copy(); noisy.data = noisy.data * (1.0 + 0.05 * rng.random(noisy.nnz))      # no exact factorisation: fp64 storage
+signed = b2.copy(); signed.data = signed.data - 0.9 * np.median(signed.data)          # entries of both signs
+kinds = {"tf-idf fp64 (recovered counts)": b2, "fp64, not factorable": noisy, "signed fp64": signed}
+kind_single = {k: T.hierarchical_spectral_cluster(m, device=lr) for k, m in kinds.items()}
 dist.init_process_group("nccl", device_id=dev)
 tdist.init_comm(rank, world, lr, dev)
 ok = True
@@ -63,6 +72,13 @@ for name in names:
     t0 = time.time(); tr = T.hierarchical_spectral_cluster(a, normalize=True, device=lr)
     check(name, "host matrix, TMC_REPL_PREPARE=1", tr, 1e3 * (time.time() - t0))
     del os.environ["TMC_REPL_PREPARE"]
+for k, m in kinds.items():
+    t0 = time.time(); tr = T.hierarchical_spectral_cluster(m, device=lr)
+    ref = kind_single[k]
+    good = tr.tree_hash() == ref.tree_hash() and float(np.max(np.abs(np.sort(tr.q) - np.sort(ref.q)))) <= 1e-10
+    ok &= good
+    print(f"[rank {rank}] {names[0]:6s} {k:34s} nodes {tr.n_nodes:5d} vs {ref.n_nodes:5d}  wall {1e3 * (time.time() - t0):7.1f} ms  {'ok' if good else 'FAIL'}", flush=True)
+
 # a zero-norm row in ONE rank's block must fail on EVERY rank (no rank may go on into the tree's collectives), in
 # both multi-GPU modes; and a slot budget of 1 must not silently truncate handed-off subtrees
 a = mats[names[0]].tolil(copy=True)
