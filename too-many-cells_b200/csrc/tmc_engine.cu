@@ -1783,6 +1783,11 @@ static int make_tree_sweeps(tmc_matrix* b, const tmc_opts* opts_in, tmc_tree** o
     std::unique_ptr<TreeStorage> ts_owner(new TreeStorage());      // released to the caller only when everything below succeeded
     TreeStorage* ts = ts_owner.get();
     struct Item { int local; long long rec; int64_t parent; int64_t gbeg; };     // local >= 0: engine node; else record index
+    {     // a saturated tree has 2 M vertices: no re-allocation while the nine arrays grow
+      const size_t expect = eng.nodes.size() + (size_t)(nh ? hoff[nh] : 0);
+      for (auto* v : {&ts->left, &ts->right, &ts->parent, &ts->item_begin, &ts->item_end}) v->reserve(expect);
+      ts->q.reserve(expect); ts->theta.reserve(expect); ts->iters.reserve(expect);
+    }
     std::vector<Item> stack; stack.push_back(Item{0, -1, -1, 0});
     std::vector<std::pair<int, int64_t>> shared_leaves;      // (engine node, global begin) of leaves whose cells are spread over ranks
     std::vector<std::pair<int, int64_t>> handed;             // (hid, global begin)
