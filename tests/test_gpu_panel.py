@@ -289,3 +289,33 @@ def test_shared_memory_gather_matches_the_plain_gather(golden_small):
         assert np.max(np.abs(p0 - p1)) <= 1e-12 * np.max(np.abs(p0))
         assert t0.tree_hash() == t1.tree_hash()
         assert np.max(np.abs(t0.q - t1.q)) <= 1e-12
+
+
+@pytest.mark.parametrize("env", [{"TMC_GU_LPR": "16"}, {"TMC_GU_LPR": "8"}, {"TMC_TP_NARROW": "8"}, {"TMC_TP_NARROW": "4"},
+                                 {"TMC_TP_NR": "4"}, {"TMC_TP_NR": "16"}, {"TMC_GP_NR": "2"}, {"TMC_GP_NR": "8"},
+                                 {"TMC_GS": "1", "TMC_GS_ROWS": "64"}, {"TMC_GS": "1", "TMC_TS": "1", "TMC_GS_ROWS": "64"},
+                                 {"TMC_NO_CERT": "1"}, {"TMC_XS_ROWS": "64"}])
+def test_experimental_kernel_switches_build_the_same_tree(env, golden_small):
+    """Every kernel variant kept behind an environment switch (the measured-and-dropped experiments of DESIGN.md section 4 / 7)
+    computes the same products: same tree, same Q, same SpMV pair as the default kernels."""
+    a, _ = golden_small
+    x = np.random.default_rng(9).standard_normal(a.shape[0])
+
+    def run():
+        db = T.DeviceB.from_host(a, normalize=True)
+        assert db.info()["panel_cols"] > 0 and db.info()["panel_bits"] == 4
+        out = (T.spmv_pair(db, x), T.b_to_d(db), T.hierarchical_spectral_cluster(db))
+        db.free()
+        return out
+
+    p0, d0, t0 = run()
+    for k, v in env.items():
+        os.environ[k] = v
+    try:
+        p1, d1, t1 = run()
+    finally:
+        for k in env:
+            del os.environ[k]
+    assert np.max(np.abs(p0 - p1)) <= 1e-12 * np.max(np.abs(p0))
+    assert np.max(np.abs(d0 - d1)) <= 1e-12 * np.max(np.abs(d0))
+    assert t0.tree_hash() == t1.tree_hash() and np.max(np.abs(t0.q - t1.q)) <= 1e-12
