@@ -22,11 +22,11 @@ for name in names:
     n, g = synth.CONFIGS[name][:2]
     mats[name] = sp.csr_matrix((dv, ix, ip), shape=(n, g))
     single[name] = T.hierarchical_spectral_cluster(mats[name], normalize=True, device=lr)      # before the communicator exists
-# other value kinds through the load-time fallbacks: a tf-idf matrix handed over as fp64 (factor recovery), an fp64 matrix that is
-# not a count matrix times column weights (B materialised), and a signed matrix (two degree passes, no deflation)
 vname = names[0]
 v_single = (T.hierarchical_spectral_cluster(mats[vname][:300], normalize=True, eigen_group="KMeansGroup"),
             T.hierarchical_spectral_cluster(mats[vname][:300], normalize=True, num_runs=6))
+# other value kinds through the load-time fallbacks: a tf-idf matrix handed over as fp64 (factor recovery), an fp64 matrix that is
+# not a count matrix times column weights (B materialised), and a signed matrix (two degree passes, no deflation)
 a0 = mats[names[0]]
 b2 = T.tfidf_scale_sparse_mat(a0)                                   # B2 = counts * diag(idf): recognised bit for bit
 rng = np.random.default_rng(4)
@@ -67,7 +67,6 @@ for name in names:
     b = T.DeviceB.adopt_device(a.shape[0], a.shape[1], rp, ci, va, normalize=True, device=lr)
     tr = T.hierarchical_spectral_cluster(b); b.free()
     check(name, "device-resident arrays adopted", tr, 1e3 * (time.time() - t0))
-    b2 = T.tfidf_scale_sparse_mat(a) if world == 0 else None      # (single-rank API; the B2 path is covered by tools/b2_path.py)
     os.environ["TMC_REPL_PREPARE"] = "1"
     t0 = time.time(); tr = T.hierarchical_spectral_cluster(a, normalize=True, device=lr)
     check(name, "host matrix, TMC_REPL_PREPARE=1", tr, 1e3 * (time.time() - t0))
