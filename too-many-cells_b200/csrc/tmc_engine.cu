@@ -1790,6 +1790,7 @@ static int make_tree_sweeps(tmc_matrix* b, const tmc_opts* opts_in, tmc_tree** o
     }
     std::vector<Item> stack; stack.push_back(Item{0, -1, -1, 0});
     std::vector<std::pair<int, int64_t>> shared_leaves;      // (engine node, global begin) of leaves whose cells are spread over ranks
+    shared_leaves.reserve(eng.nodes.size() / 2 + 1);
     std::vector<std::pair<int, int64_t>> handed;             // (hid, global begin)
     while (!stack.empty()) {
       const Item it = stack.back(); stack.pop_back();
@@ -1801,6 +1802,9 @@ static int make_tree_sweeps(tmc_matrix* b, const tmc_opts* opts_in, tmc_tree** o
         ts->item_begin.push_back(it.gbeg); ts->item_end.push_back(it.gbeg + nd.gsize);
         ts->q.push_back(nd.q); ts->theta.push_back(nd.theta); ts->iters.push_back(nd.iters);
         if (nd.left >= 0) {
+          // the nodes were created sweep by sweep, the walk is depth first: 2 M random accesses into 160 MB for a saturated tree
+          __builtin_prefetch(&eng.nodes[nd.right]);
+          if (eng.nodes[nd.left].left >= 0) { __builtin_prefetch(&eng.nodes[eng.nodes[nd.left].left]); __builtin_prefetch(&eng.nodes[eng.nodes[nd.left].right]); }
           stack.push_back(Item{nd.right, -1, id, it.gbeg + eng.nodes[nd.left].gsize});
           stack.push_back(Item{nd.left, -1, id, it.gbeg});
         } else shared_leaves.push_back({it.local, it.gbeg});

@@ -1659,7 +1659,7 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
     if (want_cert) {
       // Davis-Kahan: ||x - u2|| <= ~ r / gap, gap = distance of theta to the rest of the spectrum.  The second Ritz value
       // bounds that from the Krylov space: gap >= theta - theta_2 - r_2 once r_2 is itself small against the distance.
-      const double th2 = tmc_top_eig_warp(A, B, j, -1e300, theta, 2);
+      const double th2 = tmc_top_eig_warp(A, B, j, -1e300, theta, 2, 1e-7);      // an upper bound of theta_2, good to 1e-7: all the gap needs
       if (lane == 0) {
         tmc_twisted_vector(A, B, j, th2, sdp, sdm, sz, piv);
         const double r2 = beta * fabs(sz[j - 1]);

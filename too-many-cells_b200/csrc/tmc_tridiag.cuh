@@ -105,7 +105,10 @@ TMC_HD double tmc_top_eig_serial(const double* a, const double* b, int j, double
 #if defined(__CUDACC__)
 // Warp-cooperative 32-way multisection: every lane evaluates one Sturm count per round.
 // All 32 lanes must call; returns the same value on every lane.
-__device__ __forceinline__ double tmc_top_eig_warp(const double* a, const double* b, int j, double lo_hint, double hi_hint = 1e300, int kth = 1) {
+// rel_stop > 0: stop as soon as the bracket is narrower than rel_stop * max(|lo|, |hi|) and return its UPPER end (a rigorous upper
+// bound of the eigenvalue: what the sign certificate wants for theta_2, which it needs to three digits only)
+__device__ __forceinline__ double tmc_top_eig_warp(const double* a, const double* b, int j, double lo_hint, double hi_hint = 1e300, int kth = 1,
+                                                   double rel_stop = 0.0) {
   // kth = 1: the largest eigenvalue; kth = i: the i-th largest (smallest x with count(x) >= j - i + 1)
   const unsigned lane = threadIdx.x & 31u;
   const int target = j - kth + 1;
@@ -140,8 +143,8 @@ __device__ __forceinline__ double tmc_top_eig_warp(const double* a, const double
     }
     if (nlo == lo && nhi == hi) break;
     lo = nlo; hi = nhi;
-    if (hi - lo <= 4.0e-16 * fmax(fabs(lo), fabs(hi))) break;
+    if (hi - lo <= fmax(4.0e-16, rel_stop) * fmax(fabs(lo), fabs(hi))) break;
   }
-  return 0.5 * (lo + hi);
+  return rel_stop > 0.0 ? hi : 0.5 * (lo + hi);
 }
 #endif
