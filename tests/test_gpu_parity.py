@@ -473,3 +473,11 @@ def test_full_size_config3_properties_and_sign_stop():
     assert t3.tree_hash() == t1.tree_hash()
     b.free()
     T._lib.load().tmc_cache_clear()
+
+
+def test_row_selection_must_be_ascending_and_unique(tiny):
+    _, _, _, b, db = tiny
+    for rows in (np.array([5, 3, 9]), np.array([2, 2, 7])):
+        with pytest.raises(T.TmcError) as ei:
+            T.b_to_d(db, rows)
+        assert ei.value.code == _lib.ERR_INVALID

@@ -1067,6 +1067,7 @@ struct Engine {
       std::vector<int> h(n_sel);
       for (int64_t i = 0; i < n_sel; ++i) {
         if (rows[i] < 0 || rows[i] >= m) throw TmcError(TMC_ERR_INVALID, "row id out of range");
+        if (i && rows[i] <= rows[i - 1]) throw TmcError(TMC_ERR_INVALID, "row ids must be ascending and unique");
         h[i] = (int)rows[i];
       }
       CK(cudaMemcpyAsync(c.perm, h.data(), sizeof(int) * n_sel, cudaMemcpyHostToDevice, s));
