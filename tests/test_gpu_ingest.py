@@ -50,6 +50,7 @@ def test_parse_real_values_exact_and_edge_cases():
     pat = b"%%MatrixMarket matrix coordinate pattern general\n2 3 3\n1 1\n2 3\n1 2\n"
     assert np.array_equal(T.parse_matrix_market(pat, transpose=True).toarray(), np.array([[1, 0], [1, 0], [0, 1]], dtype=float))
     for bad in (b"2 2 1\n1 1 1\n", b"%%MatrixMarket matrix coordinate real general\n2 2 1\n3 1 1\n", b"%%MatrixMarket matrix coordinate real general\n2 2 1\n1 x 1\n",
+                b"%%MatrixMarket matrix coordinate real general\n2 2 3\n1 1 1\n2 2 5\n1 1 2\n",      # the same (row, column) twice
                 b"%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n"):
         with pytest.raises(T.TmcError):
             T.parse_matrix_market(bad)

@@ -101,10 +101,11 @@ __global__ void k_compact_kv(const int64_t* __restrict__ key, const double* __re
   if (i < n && valid[i]) { okey[off[i]] = key[i]; oidx[off[i]] = i; }
 }
 __global__ void k_unpack_sorted(const int64_t* __restrict__ skey, const int64_t* __restrict__ sidx, const double* __restrict__ val, int64_t n,
-                                int32_t* __restrict__ col, double* __restrict__ oval, int* __restrict__ row_cnt) {
+                                int32_t* __restrict__ col, double* __restrict__ oval, int* __restrict__ row_cnt, int* __restrict__ dup) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t k = skey[i];
+  if (i && skey[i - 1] == k) atomicOr(dup, 1);       // the same (cell, feature) twice: the engine's CSR contract forbids it (tmc.h)
   col[i] = (int32_t)(k & 0xffffffffll); oval[i] = val[sidx[i]];
   atomicAdd(row_cnt + (int)(k >> 32), 1);
 }
@@ -245,7 +246,10 @@ int tmc_mtx_parse(const char* text, int64_t n_bytes, int transpose, tmc_csr_out*
           CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, dk, dv, kept, 0, 63));          // stable: by (row, col)
           d_col = (int32_t*)A(sizeof(int32_t) * kept); d_oval = (double*)A(sizeof(double) * kept);
           int* d_rc = (int*)A(sizeof(int) * (n_rows + 1)); CK(cudaMemset(d_rc, 0, sizeof(int) * (n_rows + 1)));
-          k_unpack_sorted<<<(unsigned)((kept + 255) / 256), 256>>>(dk.Current(), dv.Current(), d_val, kept, d_col, d_oval, d_rc);
+          int* d_dup = (int*)A(sizeof(int)); CK(cudaMemset(d_dup, 0, sizeof(int)));
+          k_unpack_sorted<<<(unsigned)((kept + 255) / 256), 256>>>(dk.Current(), dv.Current(), d_val, kept, d_col, d_oval, d_rc, d_dup);
+          int dup = 0; CK(cudaMemcpy(&dup, d_dup, sizeof(int), cudaMemcpyDeviceToHost));
+          if (dup) throw TmcError(TMC_ERR_INVALID, "duplicate (row, column) entry in the MatrixMarket text");
           d_rp = (int64_t*)A(sizeof(int64_t) * (n_rows + 1));
           exclusive_scan_dev<int>(d_rc, d_rp, n_rows + 1, nullptr);
         }
