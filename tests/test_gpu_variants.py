@@ -115,6 +115,28 @@ def test_permutation_test_vs_oracle(golden_tiny):
     db.free()
 
 
+def test_batched_permutation_test_equals_the_per_node_version(golden_small):
+    """The permutation test runs batched through the sweep engine (one slot per split of a tree depth, one modularity sweep per
+    run); TMC_PERM_COMPOSED=1 is the per-node composition it replaced: identical p-values, also on a signed matrix."""
+    import os
+    import time
+    a, _ = golden_small
+    for mat, kw in ((a, dict(normalize=True)), (_signed_matrix(seed=5, n=200, g=700), dict())):
+        db = T.DeviceB.from_host(mat, **kw)
+        t0 = T.hierarchical_spectral_cluster(db)
+        tb = time.perf_counter(); p_batched = T.permutation_test(db, t0, 12, seed=3); tb = time.perf_counter() - tb
+        os.environ["TMC_PERM_COMPOSED"] = "1"
+        try:
+            tc = time.perf_counter(); p_composed = T.permutation_test(db, t0, 12, seed=3); tc = time.perf_counter() - tc
+        finally:
+            del os.environ["TMC_PERM_COMPOSED"]
+        db.free()
+        assert np.array_equal(np.isnan(p_batched), np.isnan(p_composed))
+        assert np.array_equal(p_batched[~np.isnan(p_batched)], p_composed[~np.isnan(p_composed)])
+        assert np.array_equal(np.isnan(p_batched), t0.left < 0)
+        print(f"permutation test, {t0.n_nodes} nodes x 12 runs: batched {1e3 * tb:.0f} ms, per node {1e3 * tc:.0f} ms")
+
+
 def test_p_values_reach_the_output_files(golden_tiny):
     a, _ = golden_tiny
     a = a[:120]

@@ -1683,13 +1683,112 @@ static void agree_hash(uint64_t h, const char* what) {
 #include "tmc_variants.cuh"      // TreeStorage + the host-composed variants
 extern "C" {
 
+// ---- A10, batched: the permutation test of every split of a finished tree through the sweep engine.
+// Same convention as variants::permutation_pvals (labels in ascending row order, cumulative Fisher-Yates on splitmix64 seeded from
+// (seed, smallest row id, size), p = #{Q_shuffled >= Q_observed - 1e-12} / num_runs), but instead of one tmc_modularity call per
+// node and run -- each a degree pass plus a product on a freshly built block -- the splits of one tree depth (they are disjoint)
+// sit in one slot each: one degree sweep per depth, then ONE modularity sweep per run for all of them (CSR scatter + dense panel,
+// no column-sorted blocks to build).  The shuffles run on the host between sweeps.  TMC_PERM_COMPOSED=1: the per-node version.
+static void permutation_pvals_batched(tmc_matrix* b, const tmc_tree& t, int num_runs, uint64_t seed, double* p) {
+  for (int64_t u = 0; u < t.n_nodes; ++u) p[u] = std::numeric_limits<double>::quiet_NaN();
+  if (num_runs < 1 || t.n_nodes < 2) return;
+  std::vector<int> depth(t.n_nodes, 0); int maxd = 0;
+  for (int64_t u = 1; u < t.n_nodes; ++u) { depth[u] = depth[t.parent[u]] + 1; maxd = std::max(maxd, depth[u]); }      // pre-order: parent < child
+  std::vector<std::vector<int64_t>> by_depth(maxd + 1);
+  for (int64_t u = 0; u < t.n_nodes; ++u) if (t.left[u] >= 0) by_depth[depth[u]].push_back(u);
+  tmc_opts o; tmc_opts_default(&o);
+  o.scatter_mode = 1;          // y = B^T x straight from the CSR rows: nothing to build per node
+  Engine eng(b, o);
+  eng.c.cert_on = 0; eng.c.collectives = 0;
+  const int S = eng.w->max_active;
+  uint8_t* d_lab = nullptr; int* d_p2s = nullptr;
+  std::vector<std::pair<int64_t, uint8_t>> cells;
+  try {
+    for (auto& level : by_depth) {
+      for (size_t k0 = 0; k0 < level.size(); k0 += (size_t)S) {
+        const int ns = (int)std::min<size_t>((size_t)S, level.size() - k0);
+        // the chunk's cells: per node in ascending row order, nodes side by side in one position range
+        std::vector<int> hperm, p2s; std::vector<uint8_t> lab; std::vector<int> nbeg(ns + 1, 0);
+        std::vector<variants::SplitMix64> rng; rng.reserve(ns);
+        for (int i = 0; i < ns; ++i) {
+          const int64_t u = level[k0 + i], beg = t.item_begin[u], end = t.item_end[u], cut = t.item_begin[t.right[u]];
+          cells.clear();
+          for (int64_t k = beg; k < end; ++k) cells.push_back({t.perm[k], (uint8_t)(k >= cut ? 1 : 0)});
+          std::sort(cells.begin(), cells.end());
+          for (auto& cpair : cells) { hperm.push_back((int)cpair.first); lab.push_back(cpair.second); p2s.push_back(i); }
+          nbeg[i + 1] = (int)hperm.size();
+          rng.emplace_back(seed ^ ((uint64_t)cells[0].first * 0x9E3779B97F4A7C15ull + (uint64_t)(end - beg)));
+        }
+        const int m = (int)hperm.size();
+        if (m > eng.w->m) throw TmcError(TMC_ERR_CUDA, "internal: permutation chunk larger than the position arena");
+        if (d_lab) { pfree(d_lab); pfree(d_p2s); }
+        d_lab = palloc<uint8_t>(m); d_p2s = palloc<int>(m);
+        CK(cudaMemcpyAsync(eng.c.perm, hperm.data(), sizeof(int) * m, cudaMemcpyHostToDevice, eng.s));
+        CK(cudaMemcpyAsync(d_p2s, p2s.data(), sizeof(int) * m, cudaMemcpyHostToDevice, eng.s));
+        // one slot per node, degree pass (stop when the slot would enter the start-vector state)
+        eng.nodes.clear();
+        for (int i = 0; i < ns; ++i) {
+          const int n = nbeg[i + 1] - nbeg[i];
+          eng.nodes.push_back(HostNode{nbeg[i], nbeg[i + 1], n, -1, -1, -1, 0, 0.0, 0.0});
+          eng.w->h_act[i] = Activation{i, nbeg[i], nbeg[i + 1], n, i, ST_ORTH0, 0, 0, 0, 0, 0, 0};
+          eng.hstate[i] = ST_DEG; eng.slot_node[i] = i;
+        }
+        eng.hi_slot = ns;
+        CK(cudaMemcpyAsync(eng.w->d_act, eng.w->h_act, sizeof(Activation) * ns, cudaMemcpyHostToDevice, eng.s));
+        k_activate<<<(ns + 127) / 128, 128, 0, eng.s>>>(eng.c, eng.w->d_act, ns);
+        auto run_sweeps = [&](int cap) {       // until every slot of the chunk reports DONE
+          for (int it = 0;; ++it) {
+            bool any = false;
+            for (int sl = 0; sl < ns; ++sl) any |= eng.hstate[sl] >= ST_DEG && eng.hstate[sl] <= ST_MOD;
+            if (!any) break;
+            if (it > cap) throw TmcError(TMC_ERR_CUDA, "internal: permutation sweep did not finish");
+            eng.sweep();
+            for (int sl = 0; sl < ns; ++sl) {
+              if (eng.hstate[sl] < ST_DEG || eng.hstate[sl] > ST_MOD) continue;
+              const Report& r = eng.w->h_rep[sl];
+              eng.hstate[sl] = r.state == ST_DONE ? ST_IDLE : r.state;
+              if (r.state == ST_DONE) eng.nodes[sl].q = r.q;
+            }
+          }
+        };
+        run_sweeps(8);
+        std::vector<double> q_obs(ns, 0.0); std::vector<int64_t> ge(ns, 0);
+        std::vector<uint8_t> cur = lab;
+        for (int r = 0; r <= num_runs; ++r) {
+          if (r > 0)
+            for (int i = 0; i < ns; ++i) {       // cumulative Fisher-Yates on the node's labels (ascending row order)
+              uint8_t* l = cur.data() + nbeg[i]; const int64_t n = nbeg[i + 1] - nbeg[i];
+              for (int64_t a = n - 1; a > 0; --a) { const int64_t bidx = (int64_t)(rng[i].next() % (uint64_t)(a + 1)); std::swap(l[a], l[bidx]); }
+            }
+          CK(cudaMemcpyAsync(d_lab, cur.data(), m, cudaMemcpyHostToDevice, eng.s));
+          k_force_mod_batch<<<(ns + 127) / 128, 128, 0, eng.s>>>(eng.c, ns);
+          k_set_labels_batch<<<(m + 255) / 256, 256, 0, eng.s>>>(eng.c, d_lab, d_p2s, m);
+          for (int sl = 0; sl < ns; ++sl) eng.hstate[sl] = ST_MOD;
+          eng.hi_slot = ns;
+          run_sweeps(4);
+          for (int i = 0; i < ns; ++i) {
+            if (r == 0) q_obs[i] = eng.nodes[i].q;
+            else if (eng.nodes[i].q >= q_obs[i] - 1e-12) ++ge[i];
+          }
+        }
+        for (int i = 0; i < ns; ++i) p[level[k0 + i]] = (double)ge[i] / (double)num_runs;
+      }
+    }
+  } catch (...) { if (d_lab) { pfree(d_lab); pfree(d_p2s); } throw; }
+  if (d_lab) { pfree(d_lab); pfree(d_p2s); }
+}
+static void permutation_pvals_dispatch(tmc_matrix* b, const tmc_tree& t, int num_runs, uint64_t seed, double* p) {
+  if (getenv("TMC_PERM_COMPOSED")) variants::permutation_pvals(b, t, num_runs, seed, p);
+  else permutation_pvals_batched(b, t, num_runs, seed, p);
+}
+
 // the non-default variants around a finished / instead of the sweep-engine tree
 static int finish_variants(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out, int st) {
   if (st != TMC_OK || opts->num_runs < 1) return st;
   TreeStorage* ts = reinterpret_cast<TreeStorage*>(*out);
   st = guarded([&] {
     LocalReplica local(b);
-    variants::permutation_pvals(b, ts->t, opts->num_runs, opts->seed, ts->p_val.data());
+    permutation_pvals_dispatch(b, ts->t, opts->num_runs, opts->seed, ts->p_val.data());
     local.restore();
     agree_hash(fnv1a(0xcbf29ce484222325ull, ts->p_val.data(), sizeof(double) * ts->p_val.size()), "the permutation test");
   });
@@ -1910,7 +2009,7 @@ int tmc_permutation_test(tmc_matrix* b, const tmc_tree* tree, int num_runs, uint
     if (num_runs < 0) throw TmcError(TMC_ERR_INVALID, "num_runs must be >= 0");
     if (tree->n_rows != b->n_rows) throw TmcError(TMC_ERR_INVALID, "tree and matrix have different numbers of cells");
     LocalReplica local(b);
-    variants::permutation_pvals(b, *tree, num_runs, seed, p_out);
+    permutation_pvals_dispatch(b, *tree, num_runs, seed, p_out);
     local.restore();
     agree_hash(fnv1a(0xcbf29ce484222325ull, p_out, sizeof(double) * (size_t)tree->n_nodes), "the permutation test");
   });

@@ -1910,6 +1910,41 @@ __global__ void k_force_state(Ctx c, int slot, int state, int j, int stop_after)
   slot_scal(c, slot)[R_N1] = 0.0; slot_scal(c, slot)[R_SD1] = 0.0;
 }
 
+// Batched permutation test (csrc/tmc_engine.cu, permutation_pvals_batched): many disjoint nodes, one slot each, re-opened in the
+// modularity state run after run with shuffled labels.
+__global__ void k_force_mod_batch(Ctx c, int n_slots) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_slots) return;
+  Slot& s = c.st[slot];
+  s.state = ST_MOD; s.j = 0; s.action = ACT_NONE; s.stop_after = ST_DONE; s.split = 0;      // stop_after = ST_DONE: report Q only, never split
+  slot_scal(c, slot)[R_N1] = 0.0; slot_scal(c, slot)[R_SD1] = 0.0;
+}
+__global__ void __launch_bounds__(256) k_set_labels_batch(Ctx c, const uint8_t* __restrict__ lab, const int* __restrict__ pos2slot, int n) {
+  __shared__ double sm8[8];
+  __shared__ int same_s;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int slot = -1; double n1 = 0.0, sd1 = 0.0;
+  if (i < n) {
+    slot = pos2slot[i];
+    const int l = lab[i] ? 1 : 0;
+    c.label[i] = (uint8_t)l;
+    c.xin[i] = l ? (c.vt == VT_F64 ? 1.0 : c.rrow[c.perm[i]]) : 0.0;
+    n1 = l; sd1 = l ? (c.signed_mode ? c.d2[i] : c.d[i]) : 0.0;
+  }
+  // a block inside one (large) node adds its totals once; blocks that straddle nodes add per cell (small nodes: spread addresses)
+  const int first = pos2slot[min(blockIdx.x * blockDim.x, n - 1)];
+  const int same = __syncthreads_and(slot == first || slot < 0);
+  if (threadIdx.x == 0) same_s = same;
+  __syncthreads();
+  if (same_s) {
+    const double t = block_sum_256(n1, sm8);
+    const double t2 = block_sum_256(sd1, sm8);
+    if (threadIdx.x == 0 && t != 0.0) { atomicAdd(slot_scal(c, first) + R_N1, t); atomicAdd(slot_scal(c, first) + R_SD1, t2); }
+  } else if (slot >= 0 && n1 != 0.0) {
+    atomicAdd(slot_scal(c, slot) + R_N1, n1); atomicAdd(slot_scal(c, slot) + R_SD1, sd1);
+  }
+}
+
 // tmc_partition API: set up slot `slot` so that k_partition splits [begin,end)
 __global__ void k_force_partition(Ctx c, int slot, int begin, int end) {
   Slot& s = c.st[slot];
