@@ -156,17 +156,16 @@ def test_p_values_reach_the_output_files(golden_tiny):
 
 # ----------------------------------------------------------------------------- signed matrices, --svd / --pca
 def _signed_matrix(seed=3, n=260, g=900):
-    """A centred count matrix with planted structure: entries of both signs, sparsity kept (what `--svd`-style inputs look like)."""
+    """A tf-idf matrix with planted structure shifted so that ~40 % of its stored entries are negative (sparsity kept): what a
+    centred / batch-corrected input looks like.  The oracle builds a 60-70 node tree on it (smallest gap ~4e-3)."""
     import scipy.sparse as sp
     from too_many_cells_b200 import synth
     ip, ix, dv, _ = synth.synth_counts(n, g, 90, 3, seed)
-    sg = sp.csc_matrix(sp.csr_matrix((dv, ix, ip), shape=(n, g)))
-    sg.data = np.log1p(sg.data)
-    for j in range(g):          # log counts centred per feature over the stored entries: both signs, sparsity kept
-        seg = slice(sg.indptr[j], sg.indptr[j + 1])
-        if seg.stop - seg.start > 1:
-            sg.data[seg] -= sg.data[seg].mean() - 0.01
-    return sp.csr_matrix(sg)
+    b2 = O.b1_to_b2(sp.csr_matrix((dv, ix, ip), shape=(n, g)))
+    sg = b2.copy()
+    sg.data = sg.data - 0.9 * np.median(sg.data)
+    sg.eliminate_zeros()
+    return sg
 
 
 def test_signed_matrix_per_node_exports_vs_oracle():
@@ -195,6 +194,7 @@ def test_signed_matrix_full_tree_vs_oracle():
     a = _signed_matrix(seed=8)
     tree = T.hierarchical_spectral_cluster(a)
     ot = O.hierarchical_spectral_cluster(a)
+    assert ot.n_nodes > 20
     assert tree.n_nodes == ot.n_nodes and tree.leaf_sets() == ot.leaf_sets()
     qo = {tuple(sorted(int(x) for x in ot.items[i])): ot.q[i] for i in range(ot.n_nodes)}
     for i in range(tree.n_nodes):
