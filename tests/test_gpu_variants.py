@@ -115,6 +115,32 @@ def test_permutation_test_vs_oracle(golden_tiny):
     db.free()
 
 
+def test_kmeans_group_in_the_sweep_engine_equals_the_per_node_composition(golden_small):
+    """KMeansGroup on one eigenvector runs inside the batched sweeps (ST_KM: one Lloyd round per sweep); TMC_KMEANS_COMPOSED=1 is
+    the per-node host recursion it replaced.  Same tree and Q, also from device-resident input and with a permutation test."""
+    import os
+    import time
+    a, _ = golden_small
+    db = T.DeviceB.from_host(a, normalize=True)
+    tb = time.perf_counter(); t_sweeps = T.hierarchical_spectral_cluster(db, eigen_group="KMeansGroup", num_runs=4); tb = time.perf_counter() - tb
+    os.environ["TMC_KMEANS_COMPOSED"] = "1"
+    try:
+        tc = time.perf_counter(); t_comp = T.hierarchical_spectral_cluster(db, eigen_group="KMeansGroup", num_runs=4); tc = time.perf_counter() - tc
+    finally:
+        del os.environ["TMC_KMEANS_COMPOSED"]
+    db.free()
+    assert t_sweeps.tree_hash() == t_comp.tree_hash() and t_sweeps.n_nodes > 10
+    qa = {tuple(sorted(int(x) for x in t_sweeps.items(i))): (t_sweeps.q[i], t_sweeps.p_val[i]) for i in range(t_sweeps.n_nodes)}
+    for i in range(t_comp.n_nodes):
+        k = tuple(sorted(int(x) for x in t_comp.items(i)))
+        if len(k) >= 2:
+            assert abs(qa[k][0] - t_comp.q[i]) <= 1e-9
+            assert (np.isnan(qa[k][1]) and np.isnan(t_comp.p_val[i])) or qa[k][1] == t_comp.p_val[i]
+    ot = O.hierarchical_spectral_cluster(a, normalize=True, eigen_group="KMeansGroup", num_eigen=1)
+    assert same_tree(t_sweeps, ot)
+    print(f"KMeansGroup, {t_sweeps.n_nodes} nodes: in the sweeps {1e3 * tb:.0f} ms, per node {1e3 * tc:.0f} ms")
+
+
 def test_batched_permutation_test_equals_the_per_node_version(golden_small):
     """The permutation test runs batched through the sweep engine (one slot per split of a tree depth, one modularity sweep per
     run); TMC_PERM_COMPOSED=1 is the per-node composition it replaced: identical p-values, also on a signed matrix."""

@@ -278,6 +278,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     c.err = w->A<int>(1);
     c.stats = w->A<unsigned long long>(4);
     c.certmin = w->A<unsigned long long>(max_active);
+    c.km = w->A<double>((size_t)KM_N * max_active);
     w->d_act = w->A<Activation>(max_active);
     c.use_t = use_t;
     if (c.use_t) {      // transposed per-node blocks, double buffered (children are written to the other buffer)
@@ -1030,7 +1031,9 @@ struct Engine {
       }
     }
     // sign-certified stop (tmc_opts.sign_stop: 0 = on, -1 = off; TMC_NO_CERT=1 switches it off too)
-    c.cert_on = (o.sign_stop >= 0 && getenv("TMC_NO_CERT") == nullptr && !c.signed_mode) ? 1 : 0;
+    // KMeansGroup on one eigenvector runs inside the sweeps (ST_KM); labels are not signs, so nothing can be sign-certified
+    c.kmeans = (o.eigen_group == 1 && o.num_eigen <= 1) ? 1 : 0;
+    c.cert_on = (o.sign_stop >= 0 && getenv("TMC_NO_CERT") == nullptr && !c.signed_mode && !c.kmeans) ? 1 : 0;
     c.cert_min_rows = getenv("TMC_CERT_MIN_ROWS") ? atoi(getenv("TMC_CERT_MIN_ROWS")) : 64;
     c.cert_safe = getenv("TMC_CERT_SAFE") ? atof(getenv("TMC_CERT_SAFE")) : 4.0;
     c.rank = g_nccl.comm ? g_nccl.rank : 0; c.world = g_nccl.comm ? g_nccl.world : 1;
@@ -1198,12 +1201,13 @@ struct Engine {
   void sweep(bool only_spmv = false) {
     int n_sc = 0, n_ga = 0, n_mod = 0, n_or = 0, n_deg = 0, live_n = 0; int64_t rows = 0;
     // collectives are issued from the SHARED slots' states only (identical on every rank); private slots never communicate
-    int sh_sc = 0, sh_or = 0, sh_live = 0, hi_shared = 0, n_lan = 0, sh_lan = 0;
+    int sh_sc = 0, sh_or = 0, sh_live = 0, hi_shared = 0, n_lan = 0, sh_lan = 0, n_km = 0;
     for (int sl = 0; sl < hi_slot; ++sl) {
       int st = hstate[sl];
       if (st < ST_DEG || st > ST_MOD) continue;
       live_n++;
       if (st == ST_LAN) n_lan++;
+      if (st == ST_KM) n_km++;
       if (sl < n_shared_slots) {
         sh_live++; hi_shared = sl + 1;
         if (st == ST_LAN) sh_lan++;
@@ -1370,6 +1374,7 @@ struct Engine {
       if (c.collectives && sh_lan)   // a shared node's cells are spread over the ranks (issued from rank-identical state only)
         nccl_check(g_nccl.AllReduce(c.certmin, c.certmin, (size_t)hi_shared, NCCL_FLOAT64, NCCL_MIN, g_nccl.comm, s), "ncclAllReduce(min |x|)");
     }
+    if (n_km && nvch) { k_km_assign<<<nvch, 256, 0, s>>>(c); n_launch++; }      // KMeansGroup: one Lloyd round of the slots in ST_KM
     if (nvch) { k_advance<<<nvch, 256, 0, s>>>(c); n_launch++; mark(PH_ADVANCE); }
     if (n_mod) {                                                             // local: every rank splits its own cells
       k_partition<<<hi_slot, 1024, 0, s>>>(c); n_launch++;
@@ -1529,9 +1534,10 @@ const char* tmc_version(void) { return "libtmc 0.1 (sm_100a)"; }
 int tmc_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 
 // the per-node exports and the sweep engine know the default variant only; tmc_make_tree* dispatch the others (tmc_variants.cuh)
-static void check_opts(const tmc_opts* o) {
+static void check_opts(const tmc_opts* o, bool allow_kmeans1 = false) {
   if (!o) throw TmcError(TMC_ERR_INVALID, "null opts");
-  if (o->eigen_group != 0) throw TmcError(TMC_ERR_UNSUPPORTED, "eigen_group KMeansGroup: only through tmc_make_tree / tmc_make_tree_dev");
+  if (o->eigen_group != 0 && !(allow_kmeans1 && o->eigen_group == 1 && o->num_eigen <= 1))
+    throw TmcError(TMC_ERR_UNSUPPORTED, "eigen_group KMeansGroup: only through tmc_make_tree / tmc_make_tree_dev");
   if (o->num_runs > 0) throw TmcError(TMC_ERR_UNSUPPORTED, "permutation test (--numRuns): only through tmc_make_tree* / tmc_permutation_test");
 }
 static void check_variant_opts(const tmc_opts* o) {
@@ -1813,7 +1819,21 @@ static int make_tree_sweeps(tmc_matrix* b, const tmc_opts* opts_in, tmc_tree** o
 int tmc_make_tree_dev(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out) {
   int st = guarded([&] { check_variant_opts(opts); });
   if (st != TMC_OK) return st;
-  st = opts->eigen_group == 1 ? make_tree_kmeans(b, nullptr, opts, out) : make_tree_sweeps(b, opts, out);
+  // KMeansGroup on one eigenvector runs inside the batched sweeps (the 2-means as Lloyd rounds, one per sweep); on several
+  // eigenvectors it is composed per node (tmc_variants.cuh).  TMC_KMEANS_COMPOSED=1: the per-node composition for num_eigen = 1 too.
+  const bool km_sweeps = opts->eigen_group == 1 && opts->num_eigen <= 1 && getenv("TMC_KMEANS_COMPOSED") == nullptr;
+  if (opts->eigen_group == 1 && !km_sweeps) st = make_tree_kmeans(b, nullptr, opts, out);
+  else if (km_sweeps) {
+    st = guarded([&] {       // single rank, or every rank as a checked replica of the resident matrix
+      LocalReplica local(b);
+      int r = make_tree_sweeps(b, opts, out);
+      if (r != TMC_OK) throw TmcError(r, g_err);
+      local.restore();
+      const TreeStorage* ts = reinterpret_cast<const TreeStorage*>(*out);
+      uint64_t h = fnv1a(0xcbf29ce484222325ull, ts->left.data(), sizeof(int64_t) * ts->left.size());
+      agree_hash(fnv1a(h, ts->perm.data(), sizeof(int64_t) * ts->perm.size()), "the KMeansGroup tree");
+    });
+  } else st = make_tree_sweeps(b, opts, out);
   return finish_variants(b, opts, out, st);
 }
 
@@ -1822,7 +1842,7 @@ static int make_tree_sweeps(tmc_matrix* b, const tmc_opts* opts_in, tmc_tree** o
     if (!b || !out) throw TmcError(TMC_ERR_INVALID, "null pointer");
     tmc_opts sweep_opts = *opts_in; sweep_opts.num_runs = 0;      // the test runs afterwards, on the finished tree
     const tmc_opts* opts = &sweep_opts;
-    check_opts(opts);
+    check_opts(opts, /*allow_kmeans1=*/true);
     if (b->n_rows_global < 1) throw TmcError(TMC_ERR_INVALID, "empty matrix (reference: error, LoadMatrix.hs:255)");
     Engine eng(b, *opts);
     struct Ev { cudaEvent_t e = nullptr; ~Ev() { if (e) cudaEventDestroy(e); } } ev0, ev1;

@@ -15,8 +15,12 @@
 namespace tmc {
 
 enum ValType : int { VT_F64 = 0, VT_U16 = 1, VT_ONE = 2 };
-enum SlotState : int { ST_IDLE = 0, ST_DEG = 1, ST_ORTH0 = 2, ST_LAN = 3, ST_MOD = 4, ST_DONE = 5 };
-enum SlotAction : int { ACT_NONE = 0, ACT_INIT = 1, ACT_NEXT = 2, ACT_RITZ_LABEL = 3, ACT_RITZ_RESTART = 4, ACT_FINISH = 5, ACT_RITZ_MULTI = 6 };
+// ST_KM (KMeansGroup only): Lloyd rounds of the 2-means on u2, one per sweep, between the eigen-solve and the modularity step
+enum SlotState : int { ST_IDLE = 0, ST_DEG = 1, ST_ORTH0 = 2, ST_LAN = 3, ST_KM = 4, ST_MOD = 5, ST_DONE = 6 };
+enum SlotAction : int { ACT_NONE = 0, ACT_INIT = 1, ACT_NEXT = 2, ACT_RITZ_LABEL = 3, ACT_RITZ_RESTART = 4, ACT_FINISH = 5, ACT_RITZ_MULTI = 6,
+                        ACT_KM_ASSIGN = 7, ACT_KM_DONE = 8 };
+// per-slot scalars of the 2-means (Ctx::km): centroids, sums of the last assignment, label changes, round, min / max keys of u2
+enum { KM_C0 = 0, KM_C1 = 1, KM_S0 = 2, KM_S1 = 3, KM_CHANGED = 4, KM_ROUND = 5, KM_MINKEY = 6, KM_MAXKEY = 7, KM_N = 8 };
 
 // scalar slots at the tail of a reduction row
 enum { R_NRM2 = 0, R_SUMD = 1, R_YNORM2 = 2, R_N1 = 3, R_SD1 = 4, R_NSCAL = 8 };
@@ -113,6 +117,8 @@ struct Ctx {
   int collectives;                 // 0 once only private (handed-off) nodes remain: ranks run free
   // sign-certified stop: certmin[slot] = min_i |x_i| of the probed Ritz vector (bit pattern of a non-negative double, atomicMin)
   unsigned long long* certmin; int cert_on, cert_min_rows; double cert_safe;
+  // KMeansGroup with one eigenvector inside the sweeps (Options.hs:172-173): labels from Lloyd's 2-means on u2 instead of its sign
+  int kmeans; double* km;          // km[slot][KM_N]
   // truncated-SVD mode (one slot): Ritz vectors of T for the top nev values [nev][K+2], output U [m][nev] (cells x nev), sigma^2 [nev]
   double* zmulti; double* uout; double* ev_out; int* svd_conv;
 };
@@ -185,6 +191,13 @@ __device__ __forceinline__ double block_sum_256(double v, double* sm8) {
   return t;
 }
 
+__device__ __forceinline__ unsigned long long f64_key(double v) {       // order-preserving map double -> uint64
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+  return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
 __device__ __forceinline__ double hash_unit(uint64_t seed, uint64_t row) {
   uint64_t x = seed + (row + 1) * 0x9E3779B97F4A7C15ull;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -1624,7 +1637,13 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
         const double resid = beta * fabs(sz[j - 1]);
         s->theta = th2; s->resid = resid;
         const bool conv = exh || breakdown || resid <= c.tol * fmax(th2, 1e-3 * th1) || resid <= 1e-14;
-        if (conv || (full && s->restarts >= c.max_restarts)) { s->action = ACT_RITZ_LABEL; scal[R_N1] = 0.0; scal[R_SD1] = 0.0; }
+        if (conv || (full && s->restarts >= c.max_restarts)) {
+          s->action = ACT_RITZ_LABEL; scal[R_N1] = 0.0; scal[R_SD1] = 0.0;
+          if (c.kmeans) {
+            unsigned long long* kb = reinterpret_cast<unsigned long long*>(c.km + (int64_t)slot * KM_N);
+            kb[KM_MINKEY] = ~0ull; kb[KM_MAXKEY] = 0ull; c.km[(int64_t)slot * KM_N + KM_ROUND] = 0.0;
+          }
+        }
         else if (full) { s->action = ACT_RITZ_RESTART; s->restarts += 1; }
         else s->action = ACT_NEXT;
         if (s->action != ACT_NEXT) { double* z = c.zvec + (int64_t)slot * K2; for (int q = 0; q < j; ++q) z[q] = sz[q]; }
@@ -1648,6 +1667,10 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
       if (conv || (full && s->restarts >= c.max_restarts)) {
         s->action = ACT_RITZ_LABEL;
         scal[R_N1] = 0.0; scal[R_SD1] = 0.0;
+        if (c.kmeans) {          // k_advance reduces min / max of u2 for the start centroids
+          unsigned long long* kb = reinterpret_cast<unsigned long long*>(c.km + (int64_t)slot * KM_N);
+          kb[KM_MINKEY] = ~0ull; kb[KM_MAXKEY] = 0ull; c.km[(int64_t)slot * KM_N + KM_ROUND] = 0.0;
+        }
       } else if (full) {
         s->action = ACT_RITZ_RESTART; s->restarts += 1; s->theta_hint = -1e300;
       } else s->action = ACT_NEXT;
@@ -1670,6 +1693,34 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
           scal[R_N1] = 0.0; scal[R_SD1] = 0.0;                      // in case the probe succeeds and k_advance labels this sweep
         }
       }
+    }
+    return;
+  }
+  if (state == ST_KM) {
+    // Lloyd's 2-means on u2, k = 2, start = smallest / largest entry, ties to cluster 1, at most 100 rounds -- the convention of
+    // variants::kmeans2_labels / oracle kmeans2_labels.  Round r's assignment is made by k_km_assign in this sweep with the
+    // centroids set here; the next sweep evaluates it (changed? one cluster empty?) and either moves the centroids or is done.
+    if (lane == 0) {
+      double* km = c.km + (int64_t)slot * KM_N;
+      const int round = (int)km[KM_ROUND];
+      const double n = (double)s->gsize;
+      bool assign = true;
+      if (round == 0) {
+        const unsigned long long* kb = reinterpret_cast<const unsigned long long*>(km);
+        const double mn = key_f64(kb[KM_MINKEY]), mx = key_f64(kb[KM_MAXKEY]);
+        if (mn == mx) { km[KM_C0] = INFINITY; km[KM_C1] = mn; }      // no spread: every cell to cluster 1 (the node becomes a leaf)
+        else { km[KM_C0] = mn; km[KM_C1] = mx; }
+      } else {
+        const double n1 = scal[R_N1];
+        const bool changed = round == 1 || km[KM_CHANGED] > 0.0;
+        if (!changed || n1 == 0.0 || n1 == n || round >= 100) assign = false;
+        else { km[KM_C0] = km[KM_S0] / (n - n1); km[KM_C1] = km[KM_S1] / n1; }
+      }
+      if (assign) {
+        km[KM_S0] = 0.0; km[KM_S1] = 0.0; km[KM_CHANGED] = 0.0; km[KM_ROUND] = (double)(round + 1);
+        scal[R_N1] = 0.0; scal[R_SD1] = 0.0;
+        s->action = ACT_KM_ASSIGN;
+      } else s->action = ACT_KM_DONE;         // labels, xin, N1, SD1 of the last assignment stand
     }
     return;
   }
@@ -1737,7 +1788,7 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
   const Slot& s = c.st[ch.slot];
   int action = s.action;
   if (action == ACT_NEXT && cert_passed(c, ch.slot, s)) action = ACT_RITZ_LABEL;      // every label certified: stop here
-  if (action == ACT_NONE || action == ACT_FINISH) return;
+  if (action == ACT_NONE || action == ACT_FINISH || action == ACT_KM_ASSIGN || action == ACT_KM_DONE) return;
   if (action == ACT_INIT && s.nev) {      // truncated SVD of B itself: no D^{-1/2}, no deflation (V_0 = 0)
     for (int i = threadIdx.x; i < ch.len; i += 256) {
       const int p = ch.begin + i;
@@ -1790,12 +1841,14 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
   const int j = s.j;
   const double* __restrict__ z = c.zvec + (int64_t)ch.slot * (c.K + 2);
   double n1 = 0.0, sd1 = 0.0;
+  double umin = INFINITY, umax = -INFINITY;
   for (int i = threadIdx.x; i < ch.len; i += 256) {
     const int p = ch.begin + i;
     double u = 0.0;
     for (int l = 1; l <= j; ++l) u += z[l - 1] * c.V[(int64_t)l * c.vstride + p];
     if (action == ACT_RITZ_RESTART) { c.w[p] = u; continue; }
     c.u2[p] = u;
+    umin = fmin(umin, u); umax = fmax(umax, u);
     const int lab = (u >= 0.0) ? 1 : 0;                   // spectralCluster sign rule (A6)
     c.label[p] = (uint8_t)lab;
     c.xin[p] = lab ? (c.vt == VT_F64 ? 1.0 : c.rrow[c.perm[p]]) : 0.0;
@@ -1805,6 +1858,43 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
     double t = block_sum_256(n1, sm8);
     double t2 = block_sum_256(sd1, sm8);
     if (threadIdx.x == 0) { atomicAdd(slot_scal(c, ch.slot) + R_N1, t); atomicAdd(slot_scal(c, ch.slot) + R_SD1, t2); }
+    if (c.kmeans) {          // smallest / largest entry of u2: the start centroids of the 2-means
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { umin = fmin(umin, __shfl_xor_sync(0xffffffffu, umin, o)); umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o)); }
+      if ((threadIdx.x & 31) == 0 && umin <= umax) {
+        unsigned long long* kb = reinterpret_cast<unsigned long long*>(c.km + (int64_t)ch.slot * KM_N);
+        atomicMin(kb + KM_MINKEY, f64_key(umin)); atomicMax(kb + KM_MAXKEY, f64_key(umax));
+      }
+    }
+  }
+}
+
+// One Lloyd round of the 2-means on u2 (slots in ST_KM whose k_finish asked for an assignment): label, xin, cluster sums
+__global__ void __launch_bounds__(256) k_km_assign(Ctx c) {
+  __shared__ double sm8[8];
+  if ((int)blockIdx.x >= *c.n_vchunks) return;
+  const Chunk ch = c.vchunks[blockIdx.x];
+  const Slot& s = c.st[ch.slot];
+  if (s.state != ST_KM || s.action != ACT_KM_ASSIGN) return;
+  double* km = c.km + (int64_t)ch.slot * KM_N;
+  const double c0 = km[KM_C0], c1 = km[KM_C1];
+  double n1 = 0.0, sd1 = 0.0, s0 = 0.0, s1 = 0.0, chg = 0.0;
+  for (int i = threadIdx.x; i < ch.len; i += 256) {
+    const int p = ch.begin + i;
+    const double u = c.u2[p];
+    const double d0 = (u - c0) * (u - c0), d1 = (u - c1) * (u - c1);
+    const int l = d1 <= d0 ? 1 : 0;                 // ties go to cluster 1
+    chg += (l != (int)c.label[p]);
+    c.label[p] = (uint8_t)l;
+    c.xin[p] = l ? (c.vt == VT_F64 ? 1.0 : c.rrow[c.perm[p]]) : 0.0;
+    n1 += l; s1 += l ? u : 0.0; s0 += l ? 0.0 : u;
+    sd1 += l ? (c.signed_mode ? c.d2[p] : c.d[p]) : 0.0;
+  }
+  const double a = block_sum_256(n1, sm8), b2 = block_sum_256(sd1, sm8), e0 = block_sum_256(s0, sm8), e1 = block_sum_256(s1, sm8),
+               g = block_sum_256(chg, sm8);
+  if (threadIdx.x == 0) {
+    atomicAdd(slot_scal(c, ch.slot) + R_N1, a); atomicAdd(slot_scal(c, ch.slot) + R_SD1, b2);
+    atomicAdd(km + KM_S0, e0); atomicAdd(km + KM_S1, e1); atomicAdd(km + KM_CHANGED, g);
   }
 }
 
@@ -1869,7 +1959,9 @@ __global__ void k_commit(Ctx c, int n_slots) {
   switch (s->action) {
     case ACT_INIT: state = ST_ORTH0; s->j = 0; break;
     case ACT_NEXT: if (state == ST_ORTH0) { state = ST_LAN; s->j = 1; } else s->j += 1; break;
-    case ACT_RITZ_LABEL: state = ST_MOD; break;
+    case ACT_RITZ_LABEL: state = c.kmeans ? ST_KM : ST_MOD; break;
+    case ACT_KM_ASSIGN: break;
+    case ACT_KM_DONE: state = ST_MOD; break;
     case ACT_RITZ_RESTART: state = ST_ORTH0; s->j = 0; break;
     case ACT_FINISH: state = ST_DONE; break;
     case ACT_RITZ_MULTI: state = ST_DONE; break;
