@@ -65,13 +65,13 @@ typedef struct {
 /* Flag contract of the make-tree engine call (src/TooManyCells/Program/Options.hs:172-178,
  * src/TooManyCells/MakeTree/Cluster.hs:147-156). Zero-initialise, then tmc_opts_default(). */
 typedef struct {
-  int32_t eigen_group;      /* 0 = SignGroup (default), 1 = KMeansGroup (2-means on eigenvectors 2..num_eigen+1; per-node
-                               host recursion over the GPU exports, single rank)        Options.hs:172 */
+  int32_t eigen_group;      /* 0 = SignGroup (default), 1 = KMeansGroup (2-means on eigenvectors 2..num_eigen+1; with num_eigen = 1 inside
+                               the batched sweeps, else a per-node host recursion over the GPU exports)   Options.hs:172 */
   int32_t num_eigen;        /* default 1; only read by KMeansGroup                      Options.hs:173 */
   double  min_modularity;   /* default 0.0; split iff Q > min_modularity                Options.hs:178 */
   int32_t min_size;         /* make-tree always passes 1 (Nothing)                      Cluster.hs:152 */
   int32_t normalize;        /* 0 from make-tree (tf-idf done by caller), 1 = idf inside Cluster.hs:150 */
-  int32_t num_runs;         /* permutation test of every split, 0 = off (fills tmc_tree.p_val; single rank)  Options.hs:174 */
+  int32_t num_runs;         /* permutation test of every split, 0 = off (fills tmc_tree.p_val; batched sweeps)  Options.hs:174 */
   uint64_t seed;            /* start-vector seed; also seeds the label shuffles of the permutation test */
   /* engine knobs (no reference counterpart) */
   double  tol;              /* Lanczos residual tolerance ||M u - theta u|| <= tol*theta; default 1e-10 */
