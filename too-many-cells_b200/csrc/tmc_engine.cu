@@ -1695,8 +1695,11 @@ extern "C" {
 // node and run -- each a degree pass plus a product on a freshly built block -- the splits of one tree depth (they are disjoint)
 // sit in one slot each: one degree sweep per depth, then ONE modularity sweep per run for all of them (CSR scatter + dense panel,
 // no column-sorted blocks to build).  The shuffles run on the host between sweeps.  TMC_PERM_COMPOSED=1: the per-node version.
-static void permutation_pvals_batched(tmc_matrix* b, const tmc_tree& t, int num_runs, uint64_t seed, double* p) {
-  for (int64_t u = 0; u < t.n_nodes; ++u) p[u] = std::numeric_limits<double>::quiet_NaN();
+// `ge` (one count per tree vertex) receives #{runs evaluated by THIS rank with Q_shuffled >= Q_observed - 1e-12}: under a
+// communicator the runs are dealt round-robin to the ranks (every rank advances every shuffle on the host, the stream is
+// cumulative, but only evaluates its own runs on its GPU); the caller sums the counts over the ranks.
+static void permutation_counts_batched(tmc_matrix* b, const tmc_tree& t, int num_runs, uint64_t seed, std::vector<double>& ge_out, int rank, int world) {
+  ge_out.assign((size_t)t.n_nodes, 0.0);
   if (num_runs < 1 || t.n_nodes < 2) return;
   std::vector<int> depth(t.n_nodes, 0); int maxd = 0;
   for (int64_t u = 1; u < t.n_nodes; ++u) { depth[u] = depth[t.parent[u]] + 1; maxd = std::max(maxd, depth[u]); }      // pre-order: parent < child
@@ -1766,6 +1769,7 @@ static void permutation_pvals_batched(tmc_matrix* b, const tmc_tree& t, int num_
               uint8_t* l = cur.data() + nbeg[i]; const int64_t n = nbeg[i + 1] - nbeg[i];
               for (int64_t a = n - 1; a > 0; --a) { const int64_t bidx = (int64_t)(rng[i].next() % (uint64_t)(a + 1)); std::swap(l[a], l[bidx]); }
             }
+          if (r > 0 && world > 1 && (r % world) != rank) continue;       // another rank evaluates this run
           CK(cudaMemcpyAsync(d_lab, cur.data(), m, cudaMemcpyHostToDevice, eng.s));
           k_force_mod_batch<<<(ns + 127) / 128, 128, 0, eng.s>>>(eng.c, ns);
           k_set_labels_batch<<<(m + 255) / 256, 256, 0, eng.s>>>(eng.c, d_lab, d_p2s, m);
@@ -1777,27 +1781,42 @@ static void permutation_pvals_batched(tmc_matrix* b, const tmc_tree& t, int num_
             else if (eng.nodes[i].q >= q_obs[i] - 1e-12) ++ge[i];
           }
         }
-        for (int i = 0; i < ns; ++i) p[level[k0 + i]] = (double)ge[i] / (double)num_runs;
+        for (int i = 0; i < ns; ++i) ge_out[level[k0 + i]] = (double)ge[i];
       }
     }
   } catch (...) { if (d_lab) { pfree(d_lab); pfree(d_p2s); } throw; }
   if (d_lab) { pfree(d_lab); pfree(d_p2s); }
 }
+// Every rank ends up with the same p-values: single rank, or (communicator, matrix resident on every rank) the runs split over
+// the ranks and the counts summed.  TMC_PERM_COMPOSED=1: the per-node composition, every rank as a replica.
 static void permutation_pvals_dispatch(tmc_matrix* b, const tmc_tree& t, int num_runs, uint64_t seed, double* p) {
-  if (getenv("TMC_PERM_COMPOSED")) variants::permutation_pvals(b, t, num_runs, seed, p);
-  else permutation_pvals_batched(b, t, num_runs, seed, p);
+  LocalReplica local(b);
+  const int rank = local.was_active() ? local.rank : 0, world = local.was_active() ? local.world : 1;
+  if (getenv("TMC_PERM_COMPOSED")) {
+    variants::permutation_pvals(b, t, num_runs, seed, p);
+    local.restore();
+  } else {
+    std::vector<double> ge;
+    permutation_counts_batched(b, t, num_runs, seed, ge, rank, world);
+    local.restore();
+    if (world > 1 && !ge.empty()) {
+      double* d = palloc<double>(ge.size());
+      cudaMemcpy(d, ge.data(), sizeof(double) * ge.size(), cudaMemcpyHostToDevice);
+      const int r = g_nccl.AllReduce(d, d, ge.size(), NCCL_FLOAT64, NCCL_SUM, g_nccl.comm, 0);
+      cudaMemcpy(ge.data(), d, sizeof(double) * ge.size(), cudaMemcpyDeviceToHost); pfree(d);
+      if (r != 0) throw TmcError(TMC_ERR_COMM, "ncclAllReduce(permutation counts) failed");
+    }
+    for (int64_t u = 0; u < t.n_nodes; ++u)
+      p[u] = (t.left[u] >= 0 && num_runs > 0) ? ge[(size_t)u] / (double)num_runs : std::numeric_limits<double>::quiet_NaN();
+  }
+  agree_hash(fnv1a(0xcbf29ce484222325ull, p, sizeof(double) * (size_t)t.n_nodes), "the permutation test");
 }
 
 // the non-default variants around a finished / instead of the sweep-engine tree
 static int finish_variants(tmc_matrix* b, const tmc_opts* opts, tmc_tree** out, int st) {
   if (st != TMC_OK || opts->num_runs < 1) return st;
   TreeStorage* ts = reinterpret_cast<TreeStorage*>(*out);
-  st = guarded([&] {
-    LocalReplica local(b);
-    permutation_pvals_dispatch(b, ts->t, opts->num_runs, opts->seed, ts->p_val.data());
-    local.restore();
-    agree_hash(fnv1a(0xcbf29ce484222325ull, ts->p_val.data(), sizeof(double) * ts->p_val.size()), "the permutation test");
-  });
+  st = guarded([&] { permutation_pvals_dispatch(b, ts->t, opts->num_runs, opts->seed, ts->p_val.data()); });
   if (st != TMC_OK) { std::string keep = g_err; tmc_tree_free(*out); *out = nullptr; g_err = keep; }
   return st;
 }
@@ -2028,10 +2047,7 @@ int tmc_permutation_test(tmc_matrix* b, const tmc_tree* tree, int num_runs, uint
     if (!b || !tree || !p_out) throw TmcError(TMC_ERR_INVALID, "null pointer");
     if (num_runs < 0) throw TmcError(TMC_ERR_INVALID, "num_runs must be >= 0");
     if (tree->n_rows != b->n_rows) throw TmcError(TMC_ERR_INVALID, "tree and matrix have different numbers of cells");
-    LocalReplica local(b);
     permutation_pvals_dispatch(b, *tree, num_runs, seed, p_out);
-    local.restore();
-    agree_hash(fnv1a(0xcbf29ce484222325ull, p_out, sizeof(double) * (size_t)tree->n_nodes), "the permutation test");
   });
 }
 
