@@ -84,7 +84,10 @@ typedef struct {
   int32_t sign_stop;        /* 0 = default: a node's Lanczos iteration stops as soon as every label (the sign of every entry of
                                u2) is certified final -- min_i |x_i| > 4 r / gap for the Ritz vector x (Davis-Kahan) --
                                instead of running on to `tol`; -1 = off (always iterate to `tol`).  The tree is the same either way. */
-  int32_t reserved[4];
+  int32_t warm_start;       /* 0 = default: a child's Lanczos run starts from the parent's Krylov space (the Ritz vector of the
+                               parent's NEXT singular direction, restricted to the child's cells) instead of a pseudo-random
+                               vector; -1 = off.  Fewer steps, the same converged vectors, the same tree. */
+  int32_t reserved[3];
 } tmc_opts;
 
 /* Result tree: flat, pre-order (node 0 = root, children [label 0, label 1]) exactly as

@@ -399,6 +399,38 @@ def test_sign_certified_stop_same_tree(name, golden_tiny, golden_small):
         assert int(t_cert.iters.sum()) <= int(t_tol.iters.sum())
 
 
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_warm_start_same_tree(name, golden_tiny, golden_small):
+    """A child's Lanczos run starts from the parent's Krylov space (tmc_opts.warm_start, default on) instead of the hash: the
+    converged vectors, hence labels, Q and the tree, are those of the cold start; only the step count differs."""
+    a, _ = golden_tiny if name == "tiny" else golden_small
+    for mm in (0.0, -1.0):
+        for sign_stop in (True, False):
+            t_warm = T.hierarchical_spectral_cluster(a, normalize=True, min_modularity=mm, sign_stop=sign_stop)
+            t_cold = T.hierarchical_spectral_cluster(a, normalize=True, min_modularity=mm, sign_stop=sign_stop, warm_start=False)
+            assert t_warm.tree_hash() == t_cold.tree_hash(), (name, mm, sign_stop)
+            # canonical eigenvector sign: not only the same tree up to child order, the same numbering and the same perm
+            assert np.array_equal(t_warm.left, t_cold.left) and np.array_equal(t_warm.right, t_cold.right)
+            assert np.array_equal(t_warm.perm, t_cold.perm) and np.array_equal(t_warm.item_begin, t_cold.item_begin)
+            assert np.max(np.abs(t_warm.q - t_cold.q)) < 1e-12
+            assert int(t_warm.iters.sum()) <= 1.02 * int(t_cold.iters.sum())
+    t_warm = T.hierarchical_spectral_cluster(a, normalize=True)
+    t_cold = T.hierarchical_spectral_cluster(a, normalize=True, warm_start=False)
+    assert int(t_warm.iters.sum()) < int(t_cold.iters.sum())
+
+
+def test_child_order_does_not_depend_on_the_start_vector(golden_small):
+    """u2 is defined up to its sign and a Krylov solver's sign follows its start vector; the engine fixes it (label 1 = the side
+    with sum_i x_i h_i >= 0, h a fixed pseudo-random vector over the global row ids), so any seed numbers the vertices alike."""
+    a, _ = golden_small
+    t0 = T.hierarchical_spectral_cluster(a, normalize=True)
+    for seed in (1, 20261020, 2**40 + 7):
+        for warm in (True, False):
+            t = T.hierarchical_spectral_cluster(a, normalize=True, seed=seed, warm_start=warm)
+            assert np.array_equal(t.left, t0.left) and np.array_equal(t.right, t0.right) and np.array_equal(t.perm, t0.perm)
+            assert np.max(np.abs(t.q - t0.q)) < 1e-12
+
+
 def test_run_to_run_reproducible_tree_and_q(golden_small):
     """SURVEY 8(e) determinism clause: the feature-dimension sums use fp64 atomics (summation order varies from run to run), so
     eigenvector entries agree to rounding, not bit for bit; labels only depend on signs that are certified with a margin
@@ -471,6 +503,12 @@ def test_full_size_config3_properties_and_sign_stop():
     assert int(t1.iters.sum()) < 0.8 * int(t2.iters.sum())
     t3 = T.hierarchical_spectral_cluster(b, seed=20261020)                        # another start vector: the same tree
     assert t3.tree_hash() == t1.tree_hash()
+    assert np.array_equal(t3.left, t1.left) and np.array_equal(t3.perm, t1.perm)  # canonical sign: the same numbering, too
+    t4 = T.hierarchical_spectral_cluster(b, warm_start=False)                     # cold starts everywhere: the same tree, more steps
+    assert t4.tree_hash() == t1.tree_hash()
+    assert np.max(np.abs(t4.q - t1.q)) < 1e-12
+    assert int(t1.iters.sum()) < int(t4.iters.sum())
+    print(f"c3 Lanczos steps: warm {int(t1.iters.sum())}, cold {int(t4.iters.sum())}, tolerance stop {int(t2.iters.sum())}")
     b.free()
     T._lib.load().tmc_cache_clear()
 

@@ -278,6 +278,7 @@ static Workspace* get_workspace(tmc_matrix* b, const tmc_opts& o) {
     c.err = w->A<int>(1);
     c.stats = w->A<unsigned long long>(4);
     c.certmin = w->A<unsigned long long>(max_active);
+    c.ws = w->A<double>(m); c.ws_tmp = w->A<double>(m); c.zvec2 = w->A<double>((size_t)(K + 2) * max_active);
     c.km = w->A<double>((size_t)KM_N * max_active);
     w->d_act = w->A<Activation>(max_active);
     c.use_t = use_t;
@@ -940,7 +941,8 @@ static tmc_matrix* upload(const tmc_csr* a, int device) {
 struct HostNode { int begin, end, gsize, parent, left, right, iters; double q, theta; long long tb = 0, te = 0; int tpar = 0;
                   int priv = 0;     // the whole node lives on this rank (handed-off subtree)
                   int hid = -1;     // >= 0: root of the hid-th handed-off subtree (same numbering on every rank)
-                  int owner = -1; };   // [begin,end) local, gsize global
+                  int owner = -1;      // [begin,end) local, gsize global
+                  int warm = 0; };     // the parent left a start vector on this node's positions (Ctx::ws)
 
 struct Engine {
   tmc_matrix* b; Workspace* w; tmc_opts o; Ctx c; cudaStream_t s;
@@ -1036,6 +1038,11 @@ struct Engine {
     c.cert_on = (o.sign_stop >= 0 && getenv("TMC_NO_CERT") == nullptr && !c.signed_mode && !c.kmeans) ? 1 : 0;
     c.cert_min_rows = getenv("TMC_CERT_MIN_ROWS") ? atoi(getenv("TMC_CERT_MIN_ROWS")) : 64;
     c.cert_safe = getenv("TMC_CERT_SAFE") ? atof(getenv("TMC_CERT_SAFE")) : 4.0;
+    // warm start of a child's Lanczos run from its parent's Krylov space (tmc_opts.warm_start: 0 = on, -1 = off; TMC_NO_WARM=1
+    // switches it off too).  The default (deflated, unsigned) solver path only.
+    c.warm_on = (o.warm_start >= 0 && getenv("TMC_NO_WARM") == nullptr && !c.signed_mode && !c.kmeans) ? 1 : 0;
+    c.warm_min_rows = getenv("TMC_WARM_MIN_ROWS") ? atoi(getenv("TMC_WARM_MIN_ROWS")) : 32;
+    c.canon_sign = (getenv("TMC_NO_CANON") == nullptr && !c.kmeans) ? 1 : 0;
     c.rank = g_nccl.comm ? g_nccl.rank : 0; c.world = g_nccl.comm ? g_nccl.world : 1;
     hstate.assign(w->max_active, ST_IDLE); slot_node.assign(w->max_active, -1);
     rmode = b->replicated && c.world > 1 && c.use_t;
@@ -1145,7 +1152,7 @@ struct Engine {
         int node = q.front(); q.pop_front();
         int slot = fs.top(); fs.pop();
         w->h_act[n++] = Activation{slot, nodes[node].begin, nodes[node].end, nodes[node].gsize, node, stop_after, nodes[node].tpar, priv,
-                                   nodes[node].tb, nodes[node].te, act_nev, 0};
+                                   nodes[node].tb, nodes[node].te, act_nev, nodes[node].warm};
         hstate[slot] = ST_DEG; slot_node[slot] = node;
         hi_slot = std::max(hi_slot, slot + 1);
       }
@@ -1418,6 +1425,7 @@ struct Engine {
         nodes.push_back(HostNode{b0 + n0l, e0, gs - n0g, node, -1, -1, 0, 0.0, 0.0, ptb + t0, pte, cpar, ppriv});
         for (int ch : {li, ri}) {
           if (nodes[ch].gsize < 2) continue;                       // single cell: a leaf, nothing to compute
+          nodes[ch].warm = (c.warm_on && r.have_z2) ? 1 : 0;
           if (ppriv) pending_priv.push_back(ch);
           else if (rmode && nodes[ch].gsize < handoff_rows) handoff_list.push_back(ch);
           else pending.push_back(ch);
@@ -1457,6 +1465,7 @@ struct Engine {
       for (int r = 1; r < G; ++r) if (owner_load[r] < owner_load[owner]) owner = r;
       owner_load[owner] += nd.gsize;
       nd.hid = n_handoffs++; nd.owner = owner;
+      nd.warm = 0;                  // the cells move to new positions; the parent's start vector does not travel with them
       if (owner != me) { nd.begin = nd.end = 0; continue; }
       if ((long long)priv_top + nd.gsize > w->m) throw TmcError(TMC_ERR_NOMEM, "internal: private position area exhausted");
       CK(cudaMemcpyAsync(c.perm + priv_top, c.perm_tmp + off[i], sizeof(int) * nd.gsize, cudaMemcpyDeviceToDevice, s));

@@ -23,7 +23,7 @@ enum SlotAction : int { ACT_NONE = 0, ACT_INIT = 1, ACT_NEXT = 2, ACT_RITZ_LABEL
 enum { KM_C0 = 0, KM_C1 = 1, KM_S0 = 2, KM_S1 = 3, KM_CHANGED = 4, KM_ROUND = 5, KM_MINKEY = 6, KM_MAXKEY = 7, KM_N = 8 };
 
 // scalar slots at the tail of a reduction row
-enum { R_NRM2 = 0, R_SUMD = 1, R_YNORM2 = 2, R_N1 = 3, R_SD1 = 4, R_NSCAL = 8 };
+enum { R_NRM2 = 0, R_SUMD = 1, R_YNORM2 = 2, R_N1 = 3, R_SD1 = 4, R_SGN = 5, R_NSCAL = 8 };
 // The scalars live at the tail of the pass-1 coefficient row so that ONE all-reduce per sweep carries both.
 
 struct Slot {              // one live tree node (device resident)
@@ -49,11 +49,15 @@ struct Slot {              // one live tree node (device resident)
   int deg_phase;           // signed matrices: 0 = degree pass on |B| (d, for D^{-1/2}), 1 = on B itself (d2, for the modularity)
   double cert_need, cert_thr;
   double sumd2;            // signed matrices: sum of d2 = ||B^T 1||^2
+  // warm start (DESIGN.md "warm start"): warm = this node's start vector comes from its parent's Krylov space (Ctx::ws) instead
+  // of the hash; have_z2 = zvec2 holds the Ritz vector of T's SECOND value at this node's stop step (the children's start)
+  int warm, have_z2;
+  int flip;                // canonical eigenvector sign: the labels written at the stop step are to be inverted before the split
 };
 
 struct Report {            // what the host reads back after every sweep
   int state, split, n0, iters;   // n0 = global label-0 count
-  int n0_local, pad;
+  int n0_local, have_z2;         // have_z2: Ctx::ws holds a start vector for the children
   long long tnnz0;
   double q, theta;
 };
@@ -61,7 +65,7 @@ struct Report {            // what the host reads back after every sweep
 #define TMC_MAX_CHUNK 256
 struct Chunk { int slot, begin, len; };
 struct TChunk { long long begin; int slot, pad; };        // entries [begin, begin + tchunk) of the slot's transposed block
-struct Activation { int slot, begin, end, gsize, node, stop_after, tpar, priv; long long tb, te; int nev, pad; };
+struct Activation { int slot, begin, end, gsize, node, stop_after, tpar, priv; long long tb, te; int nev, warm; };
 
 struct Ctx {
   // matrix B (CSR, rows = cells)
@@ -121,6 +125,10 @@ struct Ctx {
   int kmeans; double* km;          // km[slot][KM_N]
   // truncated-SVD mode (one slot): Ritz vectors of T for the top nev values [nev][K+2], output U [m][nev] (cells x nev), sigma^2 [nev]
   double* zmulti; double* uout; double* ev_out; int* svd_conv;
+  // warm start: a node that splits leaves f = D^{-1/2} (V z2) on its positions (z2 = Ritz vector of the second Ritz value of T,
+  // i.e. the next singular direction after u2), k_partition moves it with the cells, and a child starts from D_child^{1/2} f
+  int warm_on, warm_min_rows; double* ws; double* ws_tmp; double* zvec2;
+  int canon_sign;                  // canonical sign of u2 (k_finish, ST_MOD)
 };
 
 __device__ __forceinline__ double* slot_scal(const Ctx& c, int slot) { return c.redB + (int64_t)slot * (c.K + 2 + R_NSCAL) + (c.K + 2); }
@@ -468,8 +476,9 @@ __global__ void k_activate(Ctx c, const Activation* __restrict__ acts, int n) {
   s.tpar = a.tpar; s.priv = a.priv; s.nev = a.nev; s.tb = a.tb; s.te = a.te; s.tnnz0 = 0; s.tchunk0 = 0; s.ntchunk = 0;
   s.sumd = 0; s.inv_sqrt_sumd = 0; s.beta = 0; s.theta = 0; s.resid = 0; s.q = 0; s.theta_hint = -1e300;
   s.cert_req = 0; s.deg_phase = 0; s.cert_need = 0.0; s.cert_thr = 0.02; s.sumd2 = 0.0;
+  s.warm = a.warm; s.have_z2 = 0; s.flip = 0;
   c.st[a.slot] = s;
-  slot_scal(c, a.slot)[R_N1] = 0.0; slot_scal(c, a.slot)[R_SD1] = 0.0;
+  slot_scal(c, a.slot)[R_N1] = 0.0; slot_scal(c, a.slot)[R_SD1] = 0.0; slot_scal(c, a.slot)[R_SGN] = 0.0;
 }
 
 // Work lists, rebuilt on the device every sweep.  k_prepare (one CTA) scans the live slots into three offset tables
@@ -1559,6 +1568,8 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
     if (lane == 0) {
       double b = sqrt(fmax(scal[R_NRM2] - redB[0] * redB[0], 0.0));
       s->beta = b;
+      // a warm start vector that is (numerically) a multiple of u1 carries no direction: start over from the hash
+      if (s->warm && !(b * b > 1e-20 * (scal[R_NRM2] + redA[0] * redA[0]))) { s->warm = 0; s->action = ACT_INIT; return; }
       if (!(b > 0)) { s->action = ACT_FINISH; s->split = 0; s->q = 0.0; s->theta = 0.0; }   // degenerate start (cannot happen for len >= 2)
       else s->action = ACT_NEXT;
     }
@@ -1638,7 +1649,7 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
         s->theta = th2; s->resid = resid;
         const bool conv = exh || breakdown || resid <= c.tol * fmax(th2, 1e-3 * th1) || resid <= 1e-14;
         if (conv || (full && s->restarts >= c.max_restarts)) {
-          s->action = ACT_RITZ_LABEL; scal[R_N1] = 0.0; scal[R_SD1] = 0.0;
+          s->action = ACT_RITZ_LABEL; scal[R_N1] = 0.0; scal[R_SD1] = 0.0; scal[R_SGN] = 0.0;
           if (c.kmeans) {
             unsigned long long* kb = reinterpret_cast<unsigned long long*>(c.km + (int64_t)slot * KM_N);
             kb[KM_MINKEY] = ~0ull; kb[KM_MAXKEY] = 0ull; c.km[(int64_t)slot * KM_N + KM_ROUND] = 0.0;
@@ -1666,7 +1677,7 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
       bool conv = exhausted || breakdown || resid <= c.tol * theta || resid <= 1e-14;
       if (conv || (full && s->restarts >= c.max_restarts)) {
         s->action = ACT_RITZ_LABEL;
-        scal[R_N1] = 0.0; scal[R_SD1] = 0.0;
+        scal[R_N1] = 0.0; scal[R_SD1] = 0.0; scal[R_SGN] = 0.0;
         if (c.kmeans) {          // k_advance reduces min / max of u2 for the start centroids
           unsigned long long* kb = reinterpret_cast<unsigned long long*>(c.km + (int64_t)slot * KM_N);
           kb[KM_MINKEY] = ~0ull; kb[KM_MAXKEY] = 0ull; c.km[(int64_t)slot * KM_N + KM_ROUND] = 0.0;
@@ -1677,6 +1688,18 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
       // sign-certified stop: worth a look once r / theta (a lower bound of r / gap) is under the slot's probe threshold
       want_cert = s->action == ACT_NEXT && c.cert_on && s->stop_after == 0 && len >= c.cert_min_rows && j >= 3 && resid < s->cert_thr * theta;
       if (s->action != ACT_NEXT || want_cert) { double* z = c.zvec + (int64_t)slot * K2; for (int q = 0; q < j; ++q) z[q] = sz[q]; }   // k_advance forms the Ritz vector
+      s->have_z2 = 0;
+    }
+    const bool warm_ok = c.warm_on && s->stop_after == 0 && len >= c.warm_min_rows && j >= 2;
+    int want_z2 = (lane == 0 && warm_ok && s->action == ACT_RITZ_LABEL) ? 1 : 0;
+    want_z2 = __shfl_sync(0xffffffffu, want_z2, 0);
+    if (want_z2) {      // stopped on the tolerance: the children's start vector needs the second Ritz pair (three digits are plenty)
+      const double th2 = tmc_top_eig_warp(A, B, j, -1e300, theta, 2, 1e-7);
+      if (lane == 0) {
+        tmc_twisted_vector(A, B, j, th2, sdp, sdm, sz, piv);
+        double* z2 = c.zvec2 + (int64_t)slot * K2; for (int q = 0; q < j; ++q) z2[q] = sz[q];
+        s->have_z2 = 1;
+      }
     }
     want_cert = __shfl_sync(0xffffffffu, want_cert, 0);
     if (want_cert) {
@@ -1685,12 +1708,13 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
       const double th2 = tmc_top_eig_warp(A, B, j, -1e300, theta, 2, 1e-7);      // an upper bound of theta_2, good to 1e-7: all the gap needs
       if (lane == 0) {
         tmc_twisted_vector(A, B, j, th2, sdp, sdm, sz, piv);
+        if (warm_ok) { double* z2 = c.zvec2 + (int64_t)slot * K2; for (int q = 0; q < j; ++q) z2[q] = sz[q]; s->have_z2 = 1; }   // in case the probe ends the node
         const double r2 = beta * fabs(sz[j - 1]);
         const double sep = theta - th2, gap = sep - r2;
         if (gap > 0.0 && r2 < 0.25 * sep && resid < s->cert_thr * gap) {
           s->cert_req = 1; s->cert_need = c.cert_safe * resid / gap;
           c.certmin[slot] = 0x7FF0000000000000ull;                 // +inf
-          scal[R_N1] = 0.0; scal[R_SD1] = 0.0;                      // in case the probe succeeds and k_advance labels this sweep
+          scal[R_N1] = 0.0; scal[R_SD1] = 0.0; scal[R_SGN] = 0.0;                      // in case the probe succeeds and k_advance labels this sweep
         }
       }
     }
@@ -1718,7 +1742,7 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
       }
       if (assign) {
         km[KM_S0] = 0.0; km[KM_S1] = 0.0; km[KM_CHANGED] = 0.0; km[KM_ROUND] = (double)(round + 1);
-        scal[R_N1] = 0.0; scal[R_SD1] = 0.0;
+        scal[R_N1] = 0.0; scal[R_SD1] = 0.0; scal[R_SGN] = 0.0;
         s->action = ACT_KM_ASSIGN;
       } else s->action = ACT_KM_DONE;         // labels, xin, N1, SD1 of the last assignment stand
     }
@@ -1739,8 +1763,14 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
       q = (O0 / L - (L0 / L) * (L0 / L)) + (O1 / L - (L1 / L) * (L1 / L));
     }
     s->q = q;
-    s->n0 = (int)(n0 + 0.5);
-    const int in0 = s->n0, in1 = (int)(n1 + 0.5);
+    // Canonical eigenvector sign: u2 is defined up to its sign, and the sign a Krylov solver returns depends on its start
+    // vector.  Label 1 goes to the side with sum_i x_i h_i >= 0 for a fixed pseudo-random h indexed by the global row id, so
+    // the child order does not depend on the seed, the warm start, the storage mode or the number of ranks.  Q is symmetric
+    // in the two labels; the labels themselves are inverted by k_advance before the split.
+    const bool flip = c.canon_sign && s->stop_after == 0 && scal[R_SGN] < 0.0;
+    s->flip = flip ? 1 : 0;
+    const int in0 = flip ? (int)(n1 + 0.5) : (int)(n0 + 0.5), in1 = flip ? (int)(n0 + 0.5) : (int)(n1 + 0.5);
+    s->n0 = in0;
     bool split = (q > c.min_modularity) && in0 >= 1 && in1 >= 1 && in0 >= c.min_size && in1 >= c.min_size;
     if (s->stop_after == ST_DONE) split = false;     // fine-grained API: report Q only
     s->split = split ? 1 : 0;
@@ -1788,6 +1818,10 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
   const Slot& s = c.st[ch.slot];
   int action = s.action;
   if (action == ACT_NEXT && cert_passed(c, ch.slot, s)) action = ACT_RITZ_LABEL;      // every label certified: stop here
+  if (action == ACT_FINISH && s.state == ST_MOD && s.flip && s.split) {      // canonical sign (k_finish): invert the labels before the split
+    for (int i = threadIdx.x; i < ch.len; i += 256) c.label[ch.begin + i] ^= 1;
+    return;
+  }
   if (action == ACT_NONE || action == ACT_FINISH || action == ACT_KM_ASSIGN || action == ACT_KM_DONE) return;
   if (action == ACT_INIT && s.nev) {      // truncated SVD of B itself: no D^{-1/2}, no deflation (V_0 = 0)
     for (int i = threadIdx.x; i < ch.len; i += 256) {
@@ -1821,7 +1855,7 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
       const double sq = sqrt(dd);
       c.sdeg[p] = (c.vt == VT_F64 ? 1.0 : c.rrow[c.perm[p]]) / sq;      // D^{-1/2} (times the row factor in the factored modes)
       c.V[p] = c.signed_mode ? 0.0 : sq * isd;             // V_0 = u1 (nothing to deflate when B has negative entries)
-      c.w[p] = hash_unit(c.seed, (uint64_t)(c.row_offset + c.perm[p]));
+      c.w[p] = s.warm ? c.ws[p] * sq : hash_unit(c.seed, (uint64_t)(c.row_offset + c.perm[p]));
     }
     return;
   }
@@ -1840,14 +1874,22 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
   // Ritz vector u = sum_{l=1..j} z_l V_l
   const int j = s.j;
   const double* __restrict__ z = c.zvec + (int64_t)ch.slot * (c.K + 2);
-  double n1 = 0.0, sd1 = 0.0;
+  const double* __restrict__ z2 = c.zvec2 + (int64_t)ch.slot * (c.K + 2);
+  const bool leave_ws = c.warm_on && action == ACT_RITZ_LABEL && s.have_z2;      // the start vector of the children (see Ctx::ws)
+  double n1 = 0.0, sd1 = 0.0, sgn = 0.0;
   double umin = INFINITY, umax = -INFINITY;
   for (int i = threadIdx.x; i < ch.len; i += 256) {
     const int p = ch.begin + i;
-    double u = 0.0;
-    for (int l = 1; l <= j; ++l) u += z[l - 1] * c.V[(int64_t)l * c.vstride + p];
+    double u = 0.0, g = 0.0;
+    if (leave_ws) {
+      for (int l = 1; l <= j; ++l) { const double v = c.V[(int64_t)l * c.vstride + p]; u += z[l - 1] * v; g += z2[l - 1] * v; }
+      c.ws[p] = g / sqrt(c.d[p]);
+    } else {
+      for (int l = 1; l <= j; ++l) u += z[l - 1] * c.V[(int64_t)l * c.vstride + p];
+    }
     if (action == ACT_RITZ_RESTART) { c.w[p] = u; continue; }
     c.u2[p] = u;
+    if (c.canon_sign) sgn += u * hash_unit(0x7A6D635F7369676Eull, (uint64_t)(c.row_offset + c.perm[p]));
     umin = fmin(umin, u); umax = fmax(umax, u);
     const int lab = (u >= 0.0) ? 1 : 0;                   // spectralCluster sign rule (A6)
     c.label[p] = (uint8_t)lab;
@@ -1858,6 +1900,7 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
     double t = block_sum_256(n1, sm8);
     double t2 = block_sum_256(sd1, sm8);
     if (threadIdx.x == 0) { atomicAdd(slot_scal(c, ch.slot) + R_N1, t); atomicAdd(slot_scal(c, ch.slot) + R_SD1, t2); }
+    if (c.canon_sign) { const double t3 = block_sum_256(sgn, sm8); if (threadIdx.x == 0) atomicAdd(slot_scal(c, ch.slot) + R_SGN, t3); }
     if (c.kmeans) {          // smallest / largest entry of u2: the start centroids of the 2-means
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { umin = fmin(umin, __shfl_xor_sync(0xffffffffu, umin, o)); umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o)); }
@@ -1933,6 +1976,7 @@ __global__ void __launch_bounds__(1024) k_partition(Ctx c) {
       int idx = p - begin;
       int dest = f ? (begin + n0 + ones_before) : (begin + (idx - ones_before));
       c.perm_tmp[dest] = c.perm[p];
+      if (c.warm_on && s.have_z2) c.ws_tmp[dest] = c.ws[p];
       if (c.newpos) c.newpos[p] = dest;
     }
     __syncthreads();
@@ -1940,6 +1984,7 @@ __global__ void __launch_bounds__(1024) k_partition(Ctx c) {
     __syncthreads();
   }
   for (int p = begin + tid; p < end; p += 1024) c.perm[p] = c.perm_tmp[p];
+  if (c.warm_on && s.have_z2) for (int p = begin + tid; p < end; p += 1024) c.ws[p] = c.ws_tmp[p];
 }
 
 // apply the pending action to the slot state and publish the report the host reads
@@ -1970,7 +2015,7 @@ __global__ void k_commit(Ctx c, int n_slots) {
   if (s->stop_after != 0 && state == s->stop_after && state != s->state) state = ST_DONE;   // fine-grained API stop
   s->action = ACT_NONE;
   s->state = state;
-  Report r; r.state = state; r.split = s->split; r.n0 = s->n0; r.iters = s->iters; r.n0_local = s->n0_local; r.pad = 0; r.tnnz0 = s->tnnz0;
+  Report r; r.state = state; r.split = s->split; r.n0 = s->n0; r.iters = s->iters; r.n0_local = s->n0_local; r.have_z2 = s->have_z2; r.tnnz0 = s->tnnz0;
   r.q = s->q; r.theta = s->theta;
   c.rep[slot] = r;
 }

@@ -58,7 +58,7 @@ class HostCsr:
 
 def make_opts(min_modularity=0.0, min_size=1, normalize=False, eigen_group="SignGroup", num_eigen=1,
               num_runs=0, seed=None, tol=None, max_lanczos=None, max_restarts=None, max_active=None,
-              device=-1, profile=False, scatter_mode=0, sign_stop=True) -> Opts:
+              device=-1, profile=False, scatter_mode=0, sign_stop=True, warm_start=True) -> Opts:
     lib = _lib.load()
     o = Opts()
     lib.tmc_opts_default(C.byref(o))
@@ -82,6 +82,7 @@ def make_opts(min_modularity=0.0, min_size=1, normalize=False, eigen_group="Sign
     o.profile = int(bool(profile))
     o.scatter_mode = int(scatter_mode)
     o.sign_stop = 0 if sign_stop else -1      # sign-certified Lanczos stop (tmc.h); False = always iterate to `tol`
+    o.warm_start = 0 if warm_start else -1    # children start from the parent's Krylov space (tmc.h); False = pseudo-random start
     return o
 
 
