@@ -48,7 +48,16 @@ def lanczos(c, ct, d, start):
         r = beta * abs(z[-1])
         if stop is None and j >= 3 and m >= MINM:
             r2 = beta * abs(evec[-1, -2]); gap = ev[-1] - ev[-2] - r2
-            if gap > 0 and r2 < 0.25 * (ev[-1] - ev[-2]) and np.min(np.abs(x)) / np.linalg.norm(x) > SAFE * r / gap:
+            ok = gap > 0 and r2 < 0.25 * (ev[-1] - ev[-2])
+            if ok and os.environ.get("ENTRY") and beta > 0:
+                # entrywise bound through one more (free) product: x' = M x / theta = x + (beta z_j / theta) v_{j+1};
+                # |u_i sigma^2/theta - x'_i| <= ||c_i|| eps / theta = eps / (theta sqrt(d_i))
+                eps = SAFE * r / gap
+                xp = x + (beta * z[-1] / th) * (w / beta)
+                good = (np.abs(x) > eps) | ((np.abs(xp) * np.sqrt(d) * th > eps) & (np.sign(xp) == np.sign(x)))
+                if good.all():
+                    stop = (j, x >= 0, list(V), ev.copy(), evec.copy())
+            elif ok and np.min(np.abs(x)) / np.linalg.norm(x) > SAFE * r / gap:
                 stop = (j, x >= 0, list(V), ev.copy(), evec.copy())
         if r / max(th, 1e-300) <= 1e-10 or beta < 1e-13:
             if stop is None:

@@ -420,8 +420,9 @@ def test_warm_start_same_tree(name, golden_tiny, golden_small):
 
 
 def test_child_order_does_not_depend_on_the_start_vector(golden_small):
-    """u2 is defined up to its sign and a Krylov solver's sign follows its start vector; the engine fixes it (label 1 = the side
-    with sum_i x_i h_i >= 0, h a fixed pseudo-random vector over the global row ids), so any seed numbers the vertices alike."""
+    """u2 is defined up to its sign and a Krylov solver's sign follows its start vector; the engine fixes it from the partition itself
+    (label 1 = the side whose cells carry the larger sum of a fixed pseudo-random weight per global row id), so any seed, stop
+    rule or start numbers the vertices alike."""
     a, _ = golden_small
     t0 = T.hierarchical_spectral_cluster(a, normalize=True)
     for seed in (1, 20261020, 2**40 + 7):

@@ -1764,9 +1764,10 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
     }
     s->q = q;
     // Canonical eigenvector sign: u2 is defined up to its sign, and the sign a Krylov solver returns depends on its start
-    // vector.  Label 1 goes to the side with sum_i x_i h_i >= 0 for a fixed pseudo-random h indexed by the global row id, so
-    // the child order does not depend on the seed, the warm start, the storage mode or the number of ranks.  Q is symmetric
-    // in the two labels; the labels themselves are inverted by k_advance before the split.
+    // vector.  Label 1 goes to the side S with sum_{i in S} h_i - sum_{i not in S} h_i >= 0 for a fixed pseudo-random h indexed
+    // by the global row id -- a function of the PARTITION alone (not of the entries of a Ritz vector that is only converged as
+    // far as its signs need), so the child order does not depend on the seed, the warm start, the stop rule, the storage mode
+    // or the number of ranks.  Q is symmetric in the two labels; the labels themselves are inverted by k_advance before the split.
     const bool flip = c.canon_sign && s->stop_after == 0 && scal[R_SGN] < 0.0;
     s->flip = flip ? 1 : 0;
     const int in0 = flip ? (int)(n1 + 0.5) : (int)(n0 + 0.5), in1 = flip ? (int)(n0 + 0.5) : (int)(n1 + 0.5);
@@ -1889,9 +1890,9 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
     }
     if (action == ACT_RITZ_RESTART) { c.w[p] = u; continue; }
     c.u2[p] = u;
-    if (c.canon_sign) sgn += u * hash_unit(0x7A6D635F7369676Eull, (uint64_t)(c.row_offset + c.perm[p]));
     umin = fmin(umin, u); umax = fmax(umax, u);
     const int lab = (u >= 0.0) ? 1 : 0;                   // spectralCluster sign rule (A6)
+    if (c.canon_sign) { const double h = hash_unit(0x7A6D635F7369676Eull, (uint64_t)(c.row_offset + c.perm[p])); sgn += lab ? h : -h; }
     c.label[p] = (uint8_t)lab;
     c.xin[p] = lab ? (c.vt == VT_F64 ? 1.0 : c.rrow[c.perm[p]]) : 0.0;
     n1 += lab; sd1 += lab ? (c.signed_mode ? c.d2[p] : c.d[p]) : 0.0;
