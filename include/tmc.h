@@ -87,7 +87,10 @@ typedef struct {
   int32_t warm_start;       /* 0 = default: a child's Lanczos run starts from the parent's Krylov space (the Ritz vector of the
                                parent's NEXT singular direction, restricted to the child's cells) instead of a pseudo-random
                                vector; -1 = off.  Fewer steps, the same converged vectors, the same tree. */
-  int32_t reserved[3];
+  int32_t small_rows;       /* nodes of at most this many cells that live on one rank are solved directly (Gram matrix + dense
+                               eigen-solve of the whole subtree in one CTA) instead of iterating in the sweeps: 0 = default (64),
+                               -1 = off, else the threshold (at most 64).  Same arithmetic, same tree. */
+  int32_t reserved[2];
 } tmc_opts;
 
 /* Result tree: flat, pre-order (node 0 = root, children [label 0, label 1]) exactly as

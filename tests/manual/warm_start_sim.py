@@ -49,6 +49,11 @@ def lanczos(c, ct, d, start):
         if stop is None and j >= 3 and m >= MINM:
             r2 = beta * abs(evec[-1, -2]); gap = ev[-1] - ev[-2] - r2
             ok = gap > 0 and r2 < 0.25 * (ev[-1] - ev[-2])
+            if os.environ.get("ADAPT"):
+                # a start vector biased towards u2 by K = |z_1| sqrt(m) over the random level hides a near-degenerate partner
+                # K times better: scale the safety factor by it
+                kb = max(1.0, abs(z[0]) * np.sqrt(m)) ** float(os.environ.get("ADAPT"))
+                ok = ok and np.min(np.abs(x)) / np.linalg.norm(x) > kb * SAFE * r / gap
             if ok and os.environ.get("ENTRY") and beta > 0:
                 # entrywise bound through one more (free) product: x' = M x / theta = x + (beta z_j / theta) v_{j+1};
                 # |u_i sigma^2/theta - x'_i| <= ||c_i|| eps / theta = eps / (theta sqrt(d_i))

@@ -400,10 +400,12 @@ def test_sign_certified_stop_same_tree(name, golden_tiny, golden_small):
 
 
 @pytest.mark.parametrize("name", ["tiny", "small"])
-def test_warm_start_same_tree(name, golden_tiny, golden_small):
-    """A child's Lanczos run starts from the parent's Krylov space (tmc_opts.warm_start, default on) instead of the hash: the
-    converged vectors, hence labels, Q and the tree, are those of the cold start; only the step count differs."""
+def test_warm_start_same_tree(name, golden_tiny, golden_small, monkeypatch):
+    """A child's Lanczos run starts from the parent's Krylov space (tmc_opts.warm_start, default on for children of >= 512 cells)
+    instead of the hash: the converged vectors, hence labels, Q and the tree, are those of the cold start; only the step count
+    differs.  (At scale: tests/manual/warm_stress.py, 24 saturated 100 k-cell trees against cold starts run to the tolerance.)"""
     a, _ = golden_tiny if name == "tiny" else golden_small
+    monkeypatch.setenv("TMC_WARM_CHILD_ROWS", "32")      # default 512: these matrices are small, let every child of >= 32 cells start warm
     for mm in (0.0, -1.0):
         for sign_stop in (True, False):
             t_warm = T.hierarchical_spectral_cluster(a, normalize=True, min_modularity=mm, sign_stop=sign_stop)
@@ -414,16 +416,55 @@ def test_warm_start_same_tree(name, golden_tiny, golden_small):
             assert np.array_equal(t_warm.perm, t_cold.perm) and np.array_equal(t_warm.item_begin, t_cold.item_begin)
             assert np.max(np.abs(t_warm.q - t_cold.q)) < 1e-12
             assert int(t_warm.iters.sum()) <= 1.02 * int(t_cold.iters.sum())
-    t_warm = T.hierarchical_spectral_cluster(a, normalize=True)
-    t_cold = T.hierarchical_spectral_cluster(a, normalize=True, warm_start=False)
-    assert int(t_warm.iters.sum()) < int(t_cold.iters.sum())
+    t_warm = T.hierarchical_spectral_cluster(a, normalize=True, sign_stop=False, small_rows=0)
+    t_cold = T.hierarchical_spectral_cluster(a, normalize=True, sign_stop=False, small_rows=0, warm_start=False)
+    assert int(t_warm.iters.sum()) < int(t_cold.iters.sum())           # same stop rule (the tolerance), fewer steps to get there
 
 
-def test_child_order_does_not_depend_on_the_start_vector(golden_small):
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_direct_solve_of_small_nodes_same_tree(name, golden_tiny, golden_small):
+    """Nodes of at most 64 cells are solved directly (Gram matrix + dense eigen-solve of the whole subtree, tmc_opts.small_rows)
+    instead of iterating in the sweeps: the same vertices, numbering, perm, Q and theta as the sweeps alone, for every threshold,
+    for count storage (panel + residual) and for fp64 storage; and the saturated tree equals the exact-math oracle's."""
+    a, _ = golden_tiny if name == "tiny" else golden_small
+    b2 = T.tfidf_scale_sparse_mat(a)
+    rng = np.random.default_rng(5)
+    noisy = b2.copy(); noisy.data = noisy.data * (1.0 + 0.05 * rng.random(noisy.nnz))      # not factorable: B kept as fp64, no panel
+    for mat, norm in ((a, True), (noisy, False)):
+        for mm in (0.0, -1.0):
+            t_sw = T.hierarchical_spectral_cluster(mat, normalize=norm, min_modularity=mm, small_rows=0)      # sweeps only
+            assert int((t_sw.iters[t_sw.item_end - t_sw.item_begin >= 2] == 0).sum()) == 0
+            for thr in (None, 8, 33):
+                t_d = T.hierarchical_spectral_cluster(mat, normalize=norm, min_modularity=mm, small_rows=thr)
+                assert t_d.tree_hash() == t_sw.tree_hash(), (name, norm, mm, thr)
+                assert np.array_equal(t_d.left, t_sw.left) and np.array_equal(t_d.right, t_sw.right) and np.array_equal(t_d.perm, t_sw.perm)
+                assert np.max(np.abs(t_d.q - t_sw.q)) < 1e-11
+                assert np.max(np.abs(t_d.theta - t_sw.theta)) < 1e-9
+                sizes = t_d.item_end - t_d.item_begin
+                direct = (t_d.iters == 0) & (sizes >= 2)
+                assert np.all(sizes[direct] <= (thr or 64))
+                if mm < 0 or thr is None:
+                    assert direct.any()
+    # against the exact-math oracle: the default tree of the whole matrix (its lower levels are all direct solves) and a
+    # deeper one (min_modularity < 0 keeps splitting structureless nodes; not saturated, where exact ties decide the topology)
+    for mm in (0.0, -0.002):
+        t = T.hierarchical_spectral_cluster(a, normalize=True, min_modularity=mm)
+        ot = O.hierarchical_spectral_cluster(a, normalize=True, min_modularity=mm)
+        assert t.leaf_sets() == ot.leaf_sets() and same_tree(t, ot), (name, mm)
+        assert t.tree_hash() == _oracle_signature(ot)
+        qo = {tuple(sorted(int(x) for x in ot.items[i])): ot.q[i] for i in range(ot.n_nodes)}
+        for i in range(t.n_nodes):
+            key = tuple(sorted(int(x) for x in t.items(i)))
+            if len(key) >= 2:
+                assert abs(t.q[i] - qo[key]) <= 1e-9
+
+
+def test_child_order_does_not_depend_on_the_start_vector(golden_small, monkeypatch):
     """u2 is defined up to its sign and a Krylov solver's sign follows its start vector; the engine fixes it from the partition itself
     (label 1 = the side whose cells carry the larger sum of a fixed pseudo-random weight per global row id), so any seed, stop
     rule or start numbers the vertices alike."""
     a, _ = golden_small
+    monkeypatch.setenv("TMC_WARM_CHILD_ROWS", "32")      # let the children of this small matrix start warm (default: >= 512 cells)
     t0 = T.hierarchical_spectral_cluster(a, normalize=True)
     for seed in (1, 20261020, 2**40 + 7):
         for warm in (True, False):

@@ -39,7 +39,7 @@ class Opts(C.Structure):
                 ("min_size", C.c_int32), ("normalize", C.c_int32), ("num_runs", C.c_int32),
                 ("seed", C.c_uint64), ("tol", C.c_double), ("max_lanczos", C.c_int32),
                 ("max_restarts", C.c_int32), ("max_active", C.c_int32), ("device", C.c_int32),
-                ("profile", C.c_int32), ("scatter_mode", C.c_int32), ("sign_stop", C.c_int32), ("warm_start", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("profile", C.c_int32), ("scatter_mode", C.c_int32), ("sign_stop", C.c_int32), ("warm_start", C.c_int32), ("small_rows", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class Tree(C.Structure):

@@ -27,6 +27,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include "tmc_kernels.cuh"
+#include "tmc_small.cuh"
 
 using namespace tmc;
 
@@ -959,6 +960,8 @@ struct Engine {
   bool gs_chunk_fixed = false;
   int priv_top = 0; long long t_top = 0;
   std::vector<int> handoff_list; std::vector<long long> owner_load; int n_handoffs = 0;
+  int warm_child_min = 512;
+  std::vector<int> small_list; int small_rows = 0;      // nodes left to the direct solver (tmc_small.cuh), its size threshold (0 = off)
   int64_t n_sweeps = 0, n_launch = 0;
   double alg_vec_bytes = 0;     // non-matrix part of the spmv_pair algorithmic bytes
   double alg_panel_bytes = 0;   // panel bytes of the pairs: one byte per (row, panel column) and half
@@ -1043,6 +1046,17 @@ struct Engine {
     c.warm_on = (o.warm_start >= 0 && getenv("TMC_NO_WARM") == nullptr && !c.signed_mode && !c.kmeans) ? 1 : 0;
     c.warm_min_rows = getenv("TMC_WARM_MIN_ROWS") ? atoi(getenv("TMC_WARM_MIN_ROWS")) : 32;
     c.canon_sign = (getenv("TMC_NO_CANON") == nullptr && !c.kmeans) ? 1 : 0;
+    c.cert_warm_scale = getenv("TMC_CERT_WARM_SCALE") ? atoi(getenv("TMC_CERT_WARM_SCALE")) : 1;
+    c.cert_s0 = getenv("TMC_CERT_S0") ? atof(getenv("TMC_CERT_S0")) : 2e-4;
+    c.warm_mix = getenv("TMC_WARM_MIX") ? atof(getenv("TMC_WARM_MIX")) : 0.0;
+    c.cert_kfac = getenv("TMC_CERT_KFAC") ? atof(getenv("TMC_CERT_KFAC")) : 2.0;
+    // only nodes of at least this many cells start warm: the sign certificate of a small node is too easy to pass for a start
+    // vector that favours u2 (DESIGN.md "warm start"; measured: 1 wrong split in ~50 000 small certified nodes without it)
+    warm_child_min = getenv("TMC_WARM_CHILD_ROWS") ? atoi(getenv("TMC_WARM_CHILD_ROWS")) : 512;
+    // direct solve of small local nodes (tmc_opts.small_rows: 0 = default 64, -1 = off, else the threshold, at most 64)
+    small_rows = o.small_rows < 0 ? 0 : (o.small_rows == 0 ? TMC_SMALL_MAX : std::min(o.small_rows, TMC_SMALL_MAX));
+    if (getenv("TMC_SMALL_ROWS")) small_rows = std::max(0, std::min(atoi(getenv("TMC_SMALL_ROWS")), TMC_SMALL_MAX));
+    if (c.signed_mode || c.kmeans) small_rows = 0;
     c.rank = g_nccl.comm ? g_nccl.rank : 0; c.world = g_nccl.comm ? g_nccl.world : 1;
     hstate.assign(w->max_active, ST_IDLE); slot_node.assign(w->max_active, -1);
     rmode = b->replicated && c.world > 1 && c.use_t;
@@ -1425,7 +1439,9 @@ struct Engine {
         nodes.push_back(HostNode{b0 + n0l, e0, gs - n0g, node, -1, -1, 0, 0.0, 0.0, ptb + t0, pte, cpar, ppriv});
         for (int ch : {li, ri}) {
           if (nodes[ch].gsize < 2) continue;                       // single cell: a leaf, nothing to compute
-          nodes[ch].warm = (c.warm_on && r.have_z2) ? 1 : 0;
+          nodes[ch].warm = (c.warm_on && r.have_z2 && nodes[ch].gsize >= warm_child_min) ? 1 : 0;
+          // small and entirely on this rank: left to the direct solver after the sweeps (its positions are not touched again)
+          if (small_rows > 0 && nodes[ch].gsize <= small_rows && (c.world == 1 || ppriv)) { small_list.push_back(ch); continue; }
           if (ppriv) pending_priv.push_back(ch);
           else if (rmode && nodes[ch].gsize < handoff_rows) handoff_list.push_back(ch);
           else pending.push_back(ch);
@@ -1478,11 +1494,63 @@ struct Engine {
     CK(cudaStreamSynchronize(s));
     handoff_list.clear();
   }
+  // Direct solve of the small nodes collected by harvest(): one CTA per node builds its Gram matrix and its whole subtree
+  // (k_small_subtree); the pre-order records come back in one copy and become ordinary host nodes.
+  void solve_small() {
+    if (small_list.empty()) return;
+    const int n = (int)small_list.size();
+    std::vector<SmallNode> sn(n);
+    long long nrec = 0;
+    for (int i = 0; i < n; ++i) {
+      const HostNode& nd = nodes[small_list[i]];
+      sn[i] = SmallNode{nd.begin, nd.end - nd.begin, nrec};
+      nrec += 2ll * (nd.end - nd.begin) - 1;
+    }
+    const size_t smem = small_smem_bytes();
+    int grid = std::min(n, 148 * 3);
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ((int64_t)1 << 30) / ((int64_t)b->n_cols * 8)));
+    SmallNode* d_sn = nullptr; SmallRec* d_rec = nullptr; double* scr = nullptr;
+    std::vector<SmallRec> recs((size_t)nrec);
+    try {
+      d_sn = palloc<SmallNode>(n); d_rec = palloc<SmallRec>((size_t)nrec); scr = palloc<double>((size_t)grid * b->n_cols);
+      CK(cudaMemcpyAsync(d_sn, sn.data(), sizeof(SmallNode) * n, cudaMemcpyHostToDevice, s));
+      CK(cudaMemsetAsync(scr, 0, sizeof(double) * (size_t)grid * b->n_cols, s));
+      VT_DISPATCH(c.vt,
+        CK(cudaFuncSetAttribute(k_small_subtree<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_small_subtree<VT><<<grid, 256, smem, s>>>(c, d_sn, n, d_rec, scr));
+      n_launch++;
+      CK(cudaMemcpyAsync(recs.data(), d_rec, sizeof(SmallRec) * (size_t)nrec, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(w->h_err, c.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      CK(cudaGetLastError());
+    } catch (...) { if (d_sn) pfree(d_sn); if (d_rec) pfree(d_rec); if (scr) pfree(scr); throw; }
+    pfree(d_sn); pfree(d_rec); pfree(scr);
+    if (*w->h_err) { std::string msg; int st = err_to_status(*w->h_err, &msg); throw TmcError(st, msg); }
+    std::vector<int> stack;
+    for (int i = 0; i < n; ++i) {
+      long long pos = sn[i].rec0;
+      stack.clear(); stack.push_back(small_list[i]);
+      while (!stack.empty()) {
+        const int u = stack.back(); stack.pop_back();
+        const SmallRec& r = recs[(size_t)pos++];
+        nodes[u].q = r.q; nodes[u].theta = r.theta; nodes[u].iters = 0;
+        if (r.leaf) continue;
+        const int lsize = recs[(size_t)pos].size;      // pre-order: the left child's record comes next
+        const int b0 = nodes[u].begin, e0 = nodes[u].end, ppriv = nodes[u].priv;
+        const int li = (int)nodes.size(), ri = li + 1;
+        nodes[u].left = li; nodes[u].right = ri;
+        nodes.push_back(HostNode{b0, b0 + lsize, lsize, u, -1, -1, 0, 0.0, 0.0, 0, 0, 0, ppriv});
+        nodes.push_back(HostNode{b0 + lsize, e0, e0 - b0 - lsize, u, -1, -1, 0, 0.0, 0.0, 0, 0, 0, ppriv});
+        stack.push_back(ri); stack.push_back(li);
+      }
+    }
+    small_list.clear();
+  }
   int live() const { int n = 0; for (int sl = 0; sl < hi_slot; ++sl) n += (hstate[sl] >= ST_DEG && hstate[sl] <= ST_MOD); return n; }
 
   void run_tree() {
     const int m = rmode ? (int)(b->own_hi - b->own_lo) : (int)b->n_rows;
-    nodes.clear(); pending.clear(); pending_priv.clear();
+    nodes.clear(); pending.clear(); pending_priv.clear(); small_list.clear();
     nodes.push_back(HostNode{0, m, (int)b->n_rows_global, -1, -1, -1, 0, 0.0, 0.0});
     if (b->n_rows_global >= 2) { build_tblock_sorted(nodes[0]); pending.push_back(0); }      // run_tree starts from the identity perm
     priv_top = m; t_top = (nodes[0].te + 7) & ~7ll;
@@ -1505,6 +1573,9 @@ struct Engine {
       if (rmode) do_handoffs();
       if (phase_prof) host_ms[2] += now_ms() - t0;
     }
+    const double t0 = phase_prof ? now_ms() : 0.0;
+    solve_small();
+    if (phase_prof) fprintf(stderr, "[tmc] rank %d: direct solve of the small nodes %.2f ms\n", c.rank, now_ms() - t0);
   }
 
   // run slot 0 over rows [0,n) until it reports DONE

@@ -52,6 +52,8 @@ struct Slot {              // one live tree node (device resident)
   // warm start (DESIGN.md "warm start"): warm = this node's start vector comes from its parent's Krylov space (Ctx::ws) instead
   // of the hash; have_z2 = zvec2 holds the Ritz vector of T's SECOND value at this node's stop step (the children's start)
   int warm, have_z2;
+  double cert_k;           // warm-started node: how far its start vector favoured u2 over its random share (k_finish); the
+                           // certificate's safety factor of small nodes is scaled by it (cert_passed)
   int flip;                // canonical eigenvector sign: the labels written at the stop step are to be inverted before the split
 };
 
@@ -129,6 +131,8 @@ struct Ctx {
   // i.e. the next singular direction after u2), k_partition moves it with the cells, and a child starts from D_child^{1/2} f
   int warm_on, warm_min_rows; double* ws; double* ws_tmp; double* zvec2;
   int canon_sign;                  // canonical sign of u2 (k_finish, ST_MOD)
+  int cert_warm_scale;             // scale the certificate's safety factor of warm-started nodes by their start bias (k_finish)
+  double cert_s0, warm_mix, cert_kfac;
 };
 
 __device__ __forceinline__ double* slot_scal(const Ctx& c, int slot) { return c.redB + (int64_t)slot * (c.K + 2 + R_NSCAL) + (c.K + 2); }
@@ -476,7 +480,7 @@ __global__ void k_activate(Ctx c, const Activation* __restrict__ acts, int n) {
   s.tpar = a.tpar; s.priv = a.priv; s.nev = a.nev; s.tb = a.tb; s.te = a.te; s.tnnz0 = 0; s.tchunk0 = 0; s.ntchunk = 0;
   s.sumd = 0; s.inv_sqrt_sumd = 0; s.beta = 0; s.theta = 0; s.resid = 0; s.q = 0; s.theta_hint = -1e300;
   s.cert_req = 0; s.deg_phase = 0; s.cert_need = 0.0; s.cert_thr = 0.02; s.sumd2 = 0.0;
-  s.warm = a.warm; s.have_z2 = 0; s.flip = 0;
+  s.warm = a.warm; s.have_z2 = 0; s.flip = 0; s.cert_k = 1.0;
   c.st[a.slot] = s;
   slot_scal(c, a.slot)[R_N1] = 0.0; slot_scal(c, a.slot)[R_SD1] = 0.0; slot_scal(c, a.slot)[R_SGN] = 0.0;
 }
@@ -1711,6 +1715,13 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
         if (warm_ok) { double* z2 = c.zvec2 + (int64_t)slot * K2; for (int q = 0; q < j; ++q) z2[q] = sz[q]; s->have_z2 = 1; }   // in case the probe ends the node
         const double r2 = beta * fabs(sz[j - 1]);
         const double sep = theta - th2, gap = sep - r2;
+        // A start vector that favours u2 hides a nearly degenerate partner u3 (not yet resolved by the Krylov space: the gap
+        // seen from T_j is then too large) behind a residual r ~ g rho, rho = weight of u3 / weight of u2 in the start, while the
+        // Ritz vector carries the admixture rho itself.  A random start has rho ~ 1.  A warm start is mixed with a random share
+        // of about half its norm (k_advance, ACT_INIT), so rho >~ 1 / K with K = 2 |z_1| sqrt(m) (z_1 = component of the Ritz
+        // vector along the start vector, 1 / sqrt(m) = the random level); cert_passed scales the safety factor of SMALL nodes
+        // by it (the demand on r / gap of a large node is already far beyond what such a pair could pass).
+        s->cert_k = (s->warm && c.cert_warm_scale) ? fmax(1.0, c.cert_kfac * fabs(c.zvec[(int64_t)slot * K2]) * sqrt((double)len)) : 1.0;
         if (gap > 0.0 && r2 < 0.25 * sep && resid < s->cert_thr * gap) {
           s->cert_req = 1; s->cert_need = c.cert_safe * resid / gap;
           c.certmin[slot] = 0x7FF0000000000000ull;                 // +inf
@@ -1783,8 +1794,16 @@ __global__ void __launch_bounds__(32 * TMC_FINISH_WARPS) k_finish(Ctx c) {
 // The tree needs u2 only through the signs of its entries.  For the Ritz pair (theta, x = V z) with residual r, every label
 // is final once min_i |x_i| > SAFE * r / gap (||x|| = 1: z has unit norm and V is orthonormal).  k_finish requests a probe
 // (cert_req, z in zvec), this kernel reduces min_i |x_i| over the node's positions, k_advance / k_commit act on the outcome.
+// Safety scale of a warm-started node (Slot::cert_k = K).  A hidden pair passes the probe when g / gap < K mn / SAFE (mn = the
+// smallest |x_i|); for a cold start that is mn / SAFE, at most ~2.5e-4 for the smallest certified nodes (64 cells) and falling
+// like m^-1.5.  The scale keeps a warm node at or under cert_s0 = 1e-4, never above K: large nodes (tiny mn) are not touched.
+__device__ __forceinline__ double cert_scale(const Ctx& c, const Slot& s, double mn) {
+  return fmax(1.0, fmin(s.cert_k, s.cert_k * mn / (c.cert_safe * c.cert_s0)));
+}
 __device__ __forceinline__ bool cert_passed(const Ctx& c, int slot, const Slot& s) {
-  return s.cert_req && __longlong_as_double((long long)c.certmin[slot]) > s.cert_need;
+  if (!s.cert_req) return false;
+  const double mn = __longlong_as_double((long long)c.certmin[slot]);
+  return mn > s.cert_need * cert_scale(c, s, mn);
 }
 __global__ void __launch_bounds__(256) k_cert_probe(Ctx c) {
   __shared__ double sm8[8];
@@ -1856,7 +1875,10 @@ __global__ void __launch_bounds__(256) k_advance(Ctx c) {
       const double sq = sqrt(dd);
       c.sdeg[p] = (c.vt == VT_F64 ? 1.0 : c.rrow[c.perm[p]]) / sq;      // D^{-1/2} (times the row factor in the factored modes)
       c.V[p] = c.signed_mode ? 0.0 : sq * isd;             // V_0 = u1 (nothing to deflate when B has negative entries)
-      c.w[p] = s.warm ? c.ws[p] * sq : hash_unit(c.seed, (uint64_t)(c.row_offset + c.perm[p]));
+      // warm start: D_child^{1/2} f plus a random share of norm ~ warm_mix / 2 (the hash has variance 1/3 per entry; the warm
+      // part has norm ~ 0.3 - 0.8), so that every direction keeps at least the weight a cold start would give it
+      const double hsh = hash_unit(c.seed, (uint64_t)(c.row_offset + c.perm[p]));
+      c.w[p] = s.warm ? c.ws[p] * sq + hsh * (0.5 * c.warm_mix * sqrt(3.0 / (double)s.gsize)) : hsh;
     }
     return;
   }
@@ -1998,7 +2020,7 @@ __global__ void k_commit(Ctx c, int n_slots) {
     if (s->action == ACT_NEXT && cert_passed(c, slot, *s)) s->action = ACT_RITZ_LABEL;
     else {          // the smallest entry decides when the next probe can succeed
       const double mn = __longlong_as_double((long long)c.certmin[slot]);
-      s->cert_thr = (mn > 0.0 && mn < 1e300) ? fmin(mn / c.cert_safe, 0.5 * s->cert_thr) : 0.0;
+      s->cert_thr = (mn > 0.0 && mn < 1e300) ? fmin(mn / (c.cert_safe * cert_scale(c, *s, mn)), 0.5 * s->cert_thr) : 0.0;
     }
     s->cert_req = 0;
   }

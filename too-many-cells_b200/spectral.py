@@ -58,7 +58,7 @@ class HostCsr:
 
 def make_opts(min_modularity=0.0, min_size=1, normalize=False, eigen_group="SignGroup", num_eigen=1,
               num_runs=0, seed=None, tol=None, max_lanczos=None, max_restarts=None, max_active=None,
-              device=-1, profile=False, scatter_mode=0, sign_stop=True, warm_start=True) -> Opts:
+              device=-1, profile=False, scatter_mode=0, sign_stop=True, warm_start=True, small_rows=None) -> Opts:
     lib = _lib.load()
     o = Opts()
     lib.tmc_opts_default(C.byref(o))
@@ -83,6 +83,8 @@ def make_opts(min_modularity=0.0, min_size=1, normalize=False, eigen_group="Sign
     o.scatter_mode = int(scatter_mode)
     o.sign_stop = 0 if sign_stop else -1      # sign-certified Lanczos stop (tmc.h); False = always iterate to `tol`
     o.warm_start = 0 if warm_start else -1    # children start from the parent's Krylov space (tmc.h); False = pseudo-random start
+    if small_rows is not None:                # direct solve of small nodes (tmc.h): None = default threshold, 0 / False = off
+        o.small_rows = int(small_rows) if small_rows else -1
     return o
 
 
@@ -325,6 +327,15 @@ def tree_signature(left, right, begin, end, perm) -> str:
     differ in that pair -- and the hash covers (1) for every cell the name of its leaf (membership) and (2) the sorted
     list of all vertex names (topology: which sets of leaves are merged).  Two trees have the same signature iff they
     have identical leaf membership and identical topology up to swapping children."""
+    return _tree_names(left, right, begin, end, perm)[0]
+
+
+def tree_vertex_names(left, right, begin, end, perm):
+    """(smallest row id, number of cells) of every vertex, in the tree's own numbering: an (n_nodes, 2) int64 array."""
+    return _tree_names(left, right, begin, end, perm)[1]
+
+
+def _tree_names(left, right, begin, end, perm):
     import hashlib
     left = np.asarray(left, dtype=np.int64); right = np.asarray(right, dtype=np.int64)
     begin = np.asarray(begin, dtype=np.int64); end = np.asarray(end, dtype=np.int64); perm = np.asarray(perm, dtype=np.int64)
@@ -355,12 +366,12 @@ def tree_signature(left, right, begin, end, perm) -> str:
         raise ValueError("the leaves do not tile perm")
     leaf_name = np.empty(perm.size, dtype=np.int64)
     leaf_name[perm] = np.repeat(mn[nonempty], sizes)
-    names = np.stack([mn, end - begin], axis=1)
-    names = names[np.lexsort((names[:, 1], names[:, 0]))]
+    names0 = np.stack([mn, end - begin], axis=1)
+    names = names0[np.lexsort((names0[:, 1], names0[:, 0]))]
     h = hashlib.sha1()
     h.update(np.ascontiguousarray(leaf_name).tobytes())
     h.update(np.ascontiguousarray(names).tobytes())
-    return h.hexdigest()
+    return h.hexdigest(), names0
 
 
 def _tree_from_c(tp) -> ClusteringTree:
