@@ -1507,24 +1507,38 @@ struct Engine {
       nrec += 2ll * (nd.end - nd.begin) - 1;
     }
     const size_t smem = small_smem_bytes();
+    // scratch lists of the residual part: room for 1.5 x the average 64-row node, between 32 k and 256 k entries per CTA
+    // (larger nodes take the kernel's fallback path); at most 2 GB in all
+    const int64_t avg_row = b->n_rows > 0 ? b->enz() / b->n_rows + 1 : 1;
+    const int cap = (int)std::min<int64_t>(262144, std::max<int64_t>(32768, avg_row * 96));
+    const size_t stride = small_scratch_stride((int)b->n_cols, cap);
     int grid = std::min(n, 148 * 3);
-    grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ((int64_t)1 << 30) / ((int64_t)b->n_cols * 8)));
-    SmallNode* d_sn = nullptr; SmallRec* d_rec = nullptr; double* scr = nullptr;
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ((int64_t)2 << 30) / (int64_t)stride));
+    SmallNode* d_sn = nullptr; SmallRec* d_rec = nullptr; char* scr = nullptr; unsigned long long* d_prof = nullptr;
     std::vector<SmallRec> recs((size_t)nrec);
     try {
-      d_sn = palloc<SmallNode>(n); d_rec = palloc<SmallRec>((size_t)nrec); scr = palloc<double>((size_t)grid * b->n_cols);
+      d_sn = palloc<SmallNode>(n); d_rec = palloc<SmallRec>((size_t)nrec); scr = palloc<char>((size_t)grid * stride);
+      if (phase_prof) { d_prof = palloc<unsigned long long>(4); CK(cudaMemsetAsync(d_prof, 0, 4 * sizeof(unsigned long long), s)); }
       CK(cudaMemcpyAsync(d_sn, sn.data(), sizeof(SmallNode) * n, cudaMemcpyHostToDevice, s));
-      CK(cudaMemsetAsync(scr, 0, sizeof(double) * (size_t)grid * b->n_cols, s));
+      CK(cudaMemsetAsync(scr, 0, (size_t)grid * stride, s));
       VT_DISPATCH(c.vt,
         CK(cudaFuncSetAttribute(k_small_subtree<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_small_subtree<VT><<<grid, 256, smem, s>>>(c, d_sn, n, d_rec, scr));
+        k_small_subtree<VT><<<grid, 256, smem, s>>>(c, d_sn, n, d_rec, scr, cap, d_prof));
       n_launch++;
+      if (d_prof) {
+        unsigned long long hp[4];
+        CK(cudaMemcpyAsync(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const double tot = (double)(hp[0] + hp[1] + hp[2]) + 1e-9;
+        fprintf(stderr, "[tmc] rank %d: k_small_subtree over %d nodes, %d CTAs: residual Gram %.1f %%, panel Gram %.1f %%, subtree solves %.1f %% of the CTA cycles\n",
+                c.rank, n, grid, 100.0 * hp[0] / tot, 100.0 * hp[1] / tot, 100.0 * hp[2] / tot);
+      }
       CK(cudaMemcpyAsync(recs.data(), d_rec, sizeof(SmallRec) * (size_t)nrec, cudaMemcpyDeviceToHost, s));
       CK(cudaMemcpyAsync(w->h_err, c.err, sizeof(int), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
       CK(cudaGetLastError());
-    } catch (...) { if (d_sn) pfree(d_sn); if (d_rec) pfree(d_rec); if (scr) pfree(scr); throw; }
-    pfree(d_sn); pfree(d_rec); pfree(scr);
+    } catch (...) { if (d_sn) pfree(d_sn); if (d_rec) pfree(d_rec); if (scr) pfree(scr); if (d_prof) pfree(d_prof); throw; }
+    pfree(d_sn); pfree(d_rec); pfree(scr); if (d_prof) pfree(d_prof);
     if (*w->h_err) { std::string msg; int st = err_to_status(*w->h_err, &msg); throw TmcError(st, msg); }
     std::vector<int> stack;
     for (int i = 0; i < n; ++i) {

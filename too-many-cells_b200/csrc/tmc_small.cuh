@@ -38,34 +38,156 @@ __device__ __forceinline__ unsigned small_panel_cell(const Ctx& c, int row, int 
   return c.pnib ? ((b >> (4 * (col & 1))) & 15u) : (unsigned)b;
 }
 
+__device__ __forceinline__ unsigned small_nzmask(unsigned w) { unsigned m = w | (w >> 1); m |= m >> 2; return m & 0x11111111u; }   // bit 4k = nibble k != 0
+
+// per-CTA scratch in global memory: [n_cols * 8 bytes] column heads (int) of the fast path, aliased with the dense vector (double)
+// of the fallback path -- both are all-zero between uses -- then nxt int[cap], erow int[cap], ev double[cap]
+__host__ __device__ static inline size_t small_scratch_stride(int n_cols, int cap) { return ((size_t)n_cols * 8 + (size_t)cap * 16 + 255) & ~(size_t)255; }
+
 template <int VT>
 __global__ void __launch_bounds__(256) k_small_subtree(Ctx c, const SmallNode* __restrict__ nodes, int n_nodes, SmallRec* __restrict__ recs,
-                                                       double* __restrict__ scratch) {
+                                                       char* __restrict__ scratch, int cap, unsigned long long* __restrict__ prof) {
   extern __shared__ double ssm[];
   double* Gs = ssm;                                        // [64][65] Gram matrix of the node
   double* Ms = Gs + TMC_SMALL_MAX * TMC_SMALL_LD;          // [64][65] deflated normalised matrix of the current sub-node / Householder vectors
   double* w2s = Ms;                                        // (Gram phase) column weights of the panel tile: <= 512 doubles inside Ms
   unsigned* tile = reinterpret_cast<unsigned*>(Ms + 512);  // (Gram phase) [64][65] panel words, also inside Ms (512 + 2080 doubles <= 4160)
+  int* ovf = reinterpret_cast<int*>(Ms);                   // (Gram phase, residual part) entry ids / columns of the residual entries in panel columns
+  int* ovc = ovf + 4096;
   double* dd = Ms + TMC_SMALL_MAX * TMC_SMALL_LD;          // degrees of the sub-node
   double* sq = dd + 64; double* ta = sq + 64; double* tb = ta + 64; double* tz = tb + 64; double* tdp = tz + 64; double* tdm = tdp + 64;
   double* hv = tdm + 64; double* hp = hv + 64; double* tau = hp + 64; double* rr = tau + 64; double* sm2 = rr + 64;     // sm2: 4 doubles
   int* rows = reinterpret_cast<int*>(sm2 + 4); int* idx = rows + 64; int* idx2 = idx + 64; int* lab = idx2 + 64;
   int* st_lo = lab + 64; int* st_hi = st_lo + 72; int* ctl = st_hi + 72;      // ctl: [0] stack pointer, [1] records written, [2..] scalars
+  int* off = st_lo;                                        // (Gram phase) first entry id of every row, off[k] = entries of the node
   constexpr bool FACT = (VT != VT_F64);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* scr = scratch + (size_t)blockIdx.x * c.n_cols;
+  char* base = scratch + (size_t)blockIdx.x * small_scratch_stride(c.n_cols, cap);
+  double* scr = reinterpret_cast<double*>(base);
+  int* head = reinterpret_cast<int*>(base);
+  int* nxt = reinterpret_cast<int*>(base + (size_t)c.n_cols * 8);
+  int* erow = nxt + cap;
+  double* ev = reinterpret_cast<double*>(erow + cap);
   const int P = c.P;
+  long long tp0 = 0;
+  auto tick = [&](int phase) { if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + phase, (unsigned long long)(t - tp0)); tp0 = t; } };
 
   for (int nid = blockIdx.x; nid < n_nodes; nid += gridDim.x) {
     const SmallNode nd = nodes[nid];
     const int k = nd.len;
     __syncthreads();
+    if (prof && tid == 0) tp0 = clock64();
     if (tid < k) { const int r = c.perm[nd.begin + tid]; rows[tid] = r; idx[tid] = tid; rr[tid] = FACT ? c.rrow[r] : 1.0; }
     for (int e = tid; e < TMC_SMALL_MAX * TMC_SMALL_LD; e += 256) Gs[e] = 0.0;
+    if (tid == 0) { ctl[2] = 0; }
     __syncthreads();
+    // entries per row, residual entries in panel columns ("overflow": counts too large for a cell; the cell holds 0 there)
+    for (int i = warp; i < k; i += 8) {
+      const int64_t rs = c.row_ptr[rows[i]], re = c.row_ptr[rows[i] + 1];
+      int no = 0;
+      if (P > 0) for (int64_t e = rs + lane; e < re; e += 32) no += (__ldg(c.col + e) < P);
+      no = __reduce_add_sync(0xffffffffu, no);
+      if (lane == 0) { off[i + 1] = (int)min((int64_t)0x3fffffff, re - rs); if (no) atomicAdd(ctl + 2, no); }
+    }
+    __syncthreads();
+    if (tid == 0) { off[0] = 0; long long t = 0; for (int i = 0; i < k; ++i) { t += off[i + 1]; off[i + 1] = (int)min(t, (long long)0x7fffffff); } ctl[3] = (t <= cap && ctl[2] <= 4096) ? 1 : 0; ctl[2] = 0; }
+    __syncthreads();
+    const bool fast = ctl[3] != 0;
+
+    if (fast) {
+      // ---- residual CSR part, fast path: per-column lists of the node's entries (head / nxt in global scratch); every entry
+      // walks the entries inserted before it in its column: each co-occurring pair of rows is visited exactly once
+      // (sum_c n_c (n_c - 1) / 2 products instead of a gather per pair of rows and entry).
+      for (int i = warp; i < k; i += 8) {
+        const int64_t rs = c.row_ptr[rows[i]], re = c.row_ptr[rows[i] + 1];
+        double dsum = 0.0;
+        for (int64_t e = rs + lane; e < re; e += 32) {
+          const int col = __ldg(c.col + e);
+          const double v = ld_val<VT>(c.val, e);
+          const int id = off[i] + (int)(e - rs);
+          __stcg(erow + id, i); __stcg(ev + id, v);
+          __stcg(nxt + id, atomicExch(head + col, id + 1));
+          dsum += v * v * (FACT ? __ldg(c.w2col + col) : 1.0);
+          if (P > 0 && col < P) { const int o = atomicAdd(ctl + 2, 1); ovf[o] = id; ovc[o] = col; }
+        }
+        dsum = warp_sum(dsum);
+        if (lane == 0) Gs[i * TMC_SMALL_LD + i] = dsum;
+      }
+      __syncthreads();
+      for (int i = warp; i < k; i += 8) {
+        const int64_t rs = c.row_ptr[rows[i]], re = c.row_ptr[rows[i] + 1];
+        for (int64_t e = rs + lane; e < re; e += 32) {
+          int p = __ldcg(nxt + off[i] + (int)(e - rs));
+          if (!p) continue;
+          const int col = __ldg(c.col + e);
+          const double vw = ld_val<VT>(c.val, e) * (FACT ? __ldg(c.w2col + col) : 1.0);
+          while (p) {
+            atomicAdd(Gs + i * TMC_SMALL_LD + __ldcg(erow + p - 1), vw * __ldcg(ev + p - 1));
+            p = __ldcg(nxt + p - 1);
+          }
+        }
+      }
+      const int n_ovf = ctl[2];
+      for (int t = tid; t < n_ovf * k; t += 256) {
+        const int o = t / k, i2 = t % k;
+        const int id = ovf[o], col = ovc[o];
+        const int i = __ldcg(erow + id);
+        if (i2 == i) continue;
+        const unsigned pc = small_panel_cell(c, rows[i2], col);
+        if (pc) atomicAdd(Gs + i * TMC_SMALL_LD + i2, (double)pc * __ldcg(ev + id) * __ldg(c.w2col + col));
+      }
+      __syncthreads();
+      for (int i = warp; i < k; i += 8) {
+        const int64_t rs = c.row_ptr[rows[i]], re = c.row_ptr[rows[i] + 1];
+        for (int64_t e = rs + lane; e < re; e += 32) __stcg(head + __ldg(c.col + e), 0);
+      }
+      // every pair landed on one side of the diagonal or the other
+      for (int e = tid; e < k * k; e += 256) {
+        const int i = e / k, j = e % k;
+        if (i < j) { const double sxy = Gs[i * TMC_SMALL_LD + j] + Gs[j * TMC_SMALL_LD + i]; Gs[i * TMC_SMALL_LD + j] = sxy; Gs[j * TMC_SMALL_LD + i] = sxy; }
+      }
+      __syncthreads();
+    } else {
+      // ---- residual CSR part, fallback (more entries than the scratch lists hold): row j is scattered into a dense scratch
+      // vector, the rows i >= j gather from it; plus the cross terms of j's entries in panel columns with the other rows' cells.
+      for (int j = 0; j < k; ++j) {
+        const int64_t rs = c.row_ptr[rows[j]], re = c.row_ptr[rows[j] + 1];
+        for (int64_t e = rs + tid; e < re; e += 256) {
+          const int col = __ldg(c.col + e);
+          const double v = ld_val<VT>(c.val, e);
+          __stcg(scr + col, FACT ? v * __ldg(c.w2col + col) : v);
+        }
+        __syncthreads();
+        for (int i = j + warp; i < k; i += 8) {
+          const int64_t is = c.row_ptr[rows[i]], ie = c.row_ptr[rows[i] + 1];
+          double a = 0.0;
+          for (int64_t e = is + lane; e < ie; e += 32) a += ld_val<VT>(c.val, e) * __ldcg(scr + __ldg(c.col + e));
+          a = warp_sum(a);
+          if (lane == 0) { Gs[i * TMC_SMALL_LD + j] += a; if (i != j) Gs[j * TMC_SMALL_LD + i] += a; }
+        }
+        __syncthreads();
+        if (P > 0) {
+          for (int i = warp; i < k; i += 8) {
+            if (i == j) continue;
+            double a = 0.0;
+            for (int64_t e = rs + lane; e < re; e += 32) {
+              const int col = __ldg(c.col + e);
+              if (col < P) { const unsigned pc = small_panel_cell(c, rows[i], col); if (pc) a += (double)pc * __ldcg(scr + col); }
+            }
+            a = warp_sum(a);
+            if (lane == 0 && a != 0.0) { Gs[i * TMC_SMALL_LD + j] += a; Gs[j * TMC_SMALL_LD + i] += a; }
+          }
+          __syncthreads();
+        }
+        for (int64_t e = rs + tid; e < re; e += 256) __stcg(scr + __ldg(c.col + e), 0.0);
+        __syncthreads();
+      }
+    }
+    tick(0);
 
     // ---- Gram matrix, dense panel part: sum_c a_ic a_jc w_c^2 over the panel columns, tile by tile through shared memory.
     // Thread t owns column j = t % 64 and the rows i = t / 64 + 4 q (upper triangle only); a warp shares i (broadcast reads).
+    // Only cells that are non-zero in both rows are multiplied (nibble masks).
     if (P > 0) {
       const int pwords = c.pw >> 2, cpw = c.pnib ? 8 : 4;
       double acc[16];
@@ -81,30 +203,38 @@ __global__ void __launch_bounds__(256) k_small_subtree(Ctx c, const SmallNode* _
         for (int e = tid; e < TMC_SMALL_TW * cpw; e += 256) { const int col = w0 * cpw + e; w2s[e] = col < P ? __ldg(c.w2col + col) : 0.0; }
         __syncthreads();
         if (j < k) {
+          const unsigned* tj = tile + j * TMC_SMALL_TLD;
+          for (int w = 0; w < TMC_SMALL_TW; ++w) {
+            const unsigned wb = tj[w];
+            if (c.pnib) {
+              const unsigned mb = small_nzmask(wb);
+              if (!mb) continue;
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const int i = ig + 4 * q;
-            if (i < k && i <= j) {
-              const unsigned* ti = tile + i * TMC_SMALL_TLD; const unsigned* tj = tile + j * TMC_SMALL_TLD;
-              double a = 0.0;
-              for (int w = 0; w < TMC_SMALL_TW; ++w) {
-                const unsigned wa = ti[w], wb = tj[w];
-                if (c.pnib) {
-                  unsigned ma = wa | (wa >> 1); ma |= ma >> 2; unsigned mb = wb | (wb >> 1); mb |= mb >> 2;
-                  unsigned m = ma & mb & 0x11111111u;            // nibbles that are non-zero in both rows
+              for (int q = 0; q < 16; ++q) {
+                const int i = ig + 4 * q;
+                if (i < k && i <= j) {
+                  const unsigned wa = tile[i * TMC_SMALL_TLD + w];
+                  unsigned m = small_nzmask(wa) & mb;            // nibbles that are non-zero in both rows
                   while (m) {
                     const int bit = __ffs(m) - 1; m &= m - 1;
-                    a += (double)(((wa >> bit) & 15u) * ((wb >> bit) & 15u)) * w2s[w * 8 + (bit >> 2)];
-                  }
-                } else {
-#pragma unroll
-                  for (int b = 0; b < 4; ++b) {
-                    const unsigned pa = (wa >> (8 * b)) & 255u, pb = (wb >> (8 * b)) & 255u;
-                    if (pa && pb) a += (double)(pa * pb) * w2s[w * 4 + b];
+                    acc[q] += (double)(((wa >> bit) & 15u) * ((wb >> bit) & 15u)) * w2s[w * 8 + (bit >> 2)];
                   }
                 }
               }
-              acc[q] += a;
+            } else {
+              if (!wb) continue;
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int i = ig + 4 * q;
+                if (i < k && i <= j) {
+                  const unsigned wa = tile[i * TMC_SMALL_TLD + w];
+#pragma unroll
+                  for (int b = 0; b < 4; ++b) {
+                    const unsigned pa = (wa >> (8 * b)) & 255u, pb = (wb >> (8 * b)) & 255u;
+                    if (pa && pb) acc[q] += (double)(pa * pb) * w2s[w * 4 + b];
+                  }
+                }
+              }
             }
           }
         }
@@ -112,50 +242,18 @@ __global__ void __launch_bounds__(256) k_small_subtree(Ctx c, const SmallNode* _
       __syncthreads();
       if (j < k) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) { const int i = ig + 4 * q; if (i < k && i <= j) { Gs[i * TMC_SMALL_LD + j] = acc[q]; Gs[j * TMC_SMALL_LD + i] = acc[q]; } }
-      }
-      __syncthreads();
-    }
-
-    // ---- residual CSR part: row j is scattered into a dense scratch vector (global memory, one per CTA, zero between uses), the
-    // rows i >= j gather from it; plus the cross terms of j's residual entries in PANEL columns (counts too large for a cell:
-    // the cell holds 0 there) with the other rows' panel cells.
-    for (int j = 0; j < k; ++j) {
-      const int64_t rs = c.row_ptr[rows[j]], re = c.row_ptr[rows[j] + 1];
-      for (int64_t e = rs + tid; e < re; e += 256) {
-        const int col = __ldg(c.col + e);
-        const double v = ld_val<VT>(c.val, e);
-        scr[col] = FACT ? v * __ldg(c.w2col + col) : v;
-      }
-      __syncthreads();
-      for (int i = j + warp; i < k; i += 8) {
-        const int64_t is = c.row_ptr[rows[i]], ie = c.row_ptr[rows[i] + 1];
-        double a = 0.0;
-        for (int64_t e = is + lane; e < ie; e += 32) a += ld_val<VT>(c.val, e) * __ldcg(scr + __ldg(c.col + e));
-        a = warp_sum(a);
-        if (lane == 0) { Gs[i * TMC_SMALL_LD + j] += a; if (i != j) Gs[j * TMC_SMALL_LD + i] += a; }
-      }
-      __syncthreads();
-      if (P > 0) {
-        for (int i = warp; i < k; i += 8) {
-          if (i == j) continue;
-          double a = 0.0;
-          for (int64_t e = rs + lane; e < re; e += 32) {
-            const int col = __ldg(c.col + e);
-            if (col < P) { const unsigned pc = small_panel_cell(c, rows[i], col); if (pc) a += (double)pc * __ldcg(scr + col); }
-          }
-          a = warp_sum(a);
-          if (lane == 0 && a != 0.0) { Gs[i * TMC_SMALL_LD + j] += a; Gs[j * TMC_SMALL_LD + i] += a; }
+        for (int q = 0; q < 16; ++q) {
+          const int i = ig + 4 * q;
+          if (i < k && i <= j) { Gs[i * TMC_SMALL_LD + j] += acc[q]; if (i != j) Gs[j * TMC_SMALL_LD + i] += acc[q]; }
         }
-        __syncthreads();
       }
-      for (int64_t e = rs + tid; e < re; e += 256) scr[__ldg(c.col + e)] = 0.0;
       __syncthreads();
     }
     if (FACT) {
       for (int e = tid; e < k * k; e += 256) { const int i = e / k, j = e % k; Gs[i * TMC_SMALL_LD + j] *= rr[i] * rr[j]; }
       __syncthreads();
     }
+    tick(1);
 
     // ---- the subtree, depth first (pre-order records)
     if (tid == 0) { st_lo[0] = 0; st_hi[0] = k; ctl[0] = 1; ctl[1] = 0; }
@@ -305,6 +403,7 @@ __global__ void __launch_bounds__(256) k_small_subtree(Ctx c, const SmallNode* _
       __syncthreads();
     }
     __syncthreads();
+    tick(2);
     if (tid < k) c.perm[nd.begin + tid] = rows[idx[tid]];
   }
 }
