@@ -10,8 +10,9 @@ pairs, sign split, modularity, stable row partition) down to the leaves.
            H2D -> tree -> D2H of the flat tree), ms per tree
   roofline: SpMV pair kernels (y = C^T x, x' = C y): algorithmic bytes
            / CUDA-event time of those launches inside the timed steps
-  tree.hash: canonical SHA-1 of leaf membership + topology (too_many_cells_b200.tree_signature); at N > 1 it is
-           asserted equal on every rank and equal to the tree one GPU builds alone (`hash_single_gpu`)
+  tree.hash: canonical SHA-1 of leaf membership + topology (too_many_cells_b200.tree_signature; tree.hash_strict: the same with
+           every vertex named by its set of cells, tree_signature_strict); at N > 1 both are asserted equal on every rank and
+           equal to the tree one GPU builds alone (`hash_single_gpu`)
   cpu_baseline / --impl reference: the C port of the reference's CPU path (oracle/tmc_port.c), MEASURED on a bounded
            sample of the workload; the b200 arm also measures the GPU on that very sample (`same_input`).
 
@@ -243,7 +244,7 @@ def main():
     # N > 1: the tree ONE GPU builds alone (before the communicator exists), to compare the N-rank tree with
     hash_single = None
     if world > 1 and not args.no_verify_hash:
-        hash_single = step_dev(False).tree_hash()
+        hash_single = "/".join(step_dev(False).tree_hashes())
     if world > 1:
         import torch.distributed as dist
         from too_many_cells_b200 import dist as tdist
@@ -274,7 +275,9 @@ def main():
         ms_step = float(tt.item())
 
     # the tree of every timed step on every rank must be THE tree: same canonical hash everywhere, equal to the single-GPU one
-    hashes = sorted({t_.tree_hash() for t_ in trees})
+    # (both signatures: the (smallest row, size) one of the earlier rounds' records and the strict one that names every vertex by its
+    # set of cells; "legacy/strict")
+    hashes = sorted({"/".join(t_.tree_hashes()) for t_ in trees})
     if world > 1:
         allh = [None] * world
         torch.distributed.all_gather_object(allh, hashes)
@@ -313,7 +316,7 @@ def main():
         tr_e = T.hierarchical_spectral_cluster(host, normalize=True, device=local_rank, **eng)
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t) / e2e_steps
-    if tr_e.tree_hash() != hashes[0]:
+    if "/".join(tr_e.tree_hashes()) != hashes[0]:
         raise SystemExit("bench.py: the host-buffer call built a different tree than the device-resident call")
     h2d = int(h_ptr.numel() * 8 + (k1 - k0) * (np_col.itemsize + np_val.itemsize))
     d2h = int(tr_e.n_nodes * (8 * 5 + 8 * 2 + 4) + n * 8)
@@ -382,7 +385,8 @@ def main():
             "gpu_launches": launches, "roofline": roof,
             "tree": {"nodes": tr.n_nodes, "leaves": int(len(tr.leaves())), "sweeps": tr.stats["n_sweeps"],
                      "lanczos_steps": int(tr.iters.sum()), "engine_ms_last": tr.stats["engine_ms"], "gen_s": gen_s,
-                     "hash": hashes[0], "hash_single_gpu": hash_single,
+                     "hash": hashes[0].split("/")[0], "hash_strict": hashes[0].split("/")[1],
+                     "hash_single_gpu": hash_single.split("/")[0] if hash_single else None,
                      "hash_check": ("all ranks and steps equal" + (", equal to the single-GPU tree" if hash_single else "")) }}
     if not args.no_cpu_baseline and world == 1:          # reported on rank 0 at N=1 only
         r = cpu_reference_run(name, args.cpu_sample_cells)

@@ -1,7 +1,7 @@
 """Which vertices of the SATURATED c3 tree (BASELINE configs[4]) depend on how a node is solved, and who is right?
 
 Builds the tree (min_modularity = -1, every cell its own leaf) under several engine settings on the same device matrix, compares
-the vertex sets (a vertex = (smallest row id, size)), and for parents whose children differ between two settings recomputes
+the vertex sets (a vertex = its set of cells: smallest row id, size and a 64-bit set hash), and for parents whose children differ between two settings recomputes
 the split on the host in exact-math fp64 (LAPACK eigh on the node's cosine-similarity matrix, the oracle's arithmetic) -- with
 the eigen-gap and the smallest |u2| entry, which tell a genuine disagreement from a sign decided by rounding.
 
@@ -28,9 +28,9 @@ for key, kw in settings.items():
     t0 = time.perf_counter()
     tr = T.hierarchical_spectral_cluster(b, min_modularity=-1.0, max_active=16384, **kw)
     trees[key] = tr
-    nm = T.tree_vertex_names(tr.left, tr.right, tr.item_begin, tr.item_end, tr.perm)
+    nm = T.tree_vertex_names(tr.left, tr.right, tr.item_begin, tr.item_end, tr.perm, strict=True)      # (smallest row, size, set hash)
     names[key] = nm
-    print(f"{key:22s} {1e3 * (time.perf_counter() - t0):8.1f} ms  nodes {tr.n_nodes}  Lanczos steps {int(tr.iters.sum())}  hash {tr.tree_hash()}", flush=True)
+    print(f"{key:22s} {1e3 * (time.perf_counter() - t0):8.1f} ms  nodes {tr.n_nodes}  Lanczos steps {int(tr.iters.sum())}  hash {tr.tree_hash_strict()}", flush=True)
 
 df = torch.bincount(col.long(), minlength=g).double()
 idf = torch.log(torch.tensor(float(n), dtype=torch.float64, device=dev) / df.clamp(min=1.0))

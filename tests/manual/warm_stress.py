@@ -25,11 +25,11 @@ for seed in range(100, 100 + n_seeds):
     sizes = t_w.item_end - t_w.item_begin
     nodes_cert += int(((sizes >= 64) & (t_w.left >= 0)).sum())
     steps[0] += int(t_w.iters.sum()); steps[1] += int(t_c.iters.sum())
-    same = t_w.tree_hash() == t_c.tree_hash()
+    same = t_w.tree_hash_strict() == t_c.tree_hash_strict()
     if not same:
         bad += 1
-        a_ = set(map(tuple, T.tree_vertex_names(t_w.left, t_w.right, t_w.item_begin, t_w.item_end, t_w.perm).tolist()))
-        c_ = set(map(tuple, T.tree_vertex_names(t_c.left, t_c.right, t_c.item_begin, t_c.item_end, t_c.perm).tolist()))
+        a_ = set(map(tuple, T.tree_vertex_names(t_w.left, t_w.right, t_w.item_begin, t_w.item_end, t_w.perm, strict=True).tolist()))
+        c_ = set(map(tuple, T.tree_vertex_names(t_c.left, t_c.right, t_c.item_begin, t_c.item_end, t_c.perm, strict=True).tolist()))
         only = sorted(a_ - c_, key=lambda v: -v[1])
         print(f"seed {seed}: DIFFERENT, {len(only)} vertices; largest {only[:3]}", flush=True)
     b.free(); del rp, col, val

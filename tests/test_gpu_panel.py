@@ -250,7 +250,7 @@ def test_compact_host_types_build_the_same_tree_bit_for_bit(golden_small):
             continue
         m = (a.indptr, a.indices.astype(idt), a.data.astype(vdt), a.shape)
         t = T.hierarchical_spectral_cluster(m, normalize=True)
-        assert t.tree_hash() == ref.tree_hash(), (vdt, idt)
+        assert t.tree_hash_strict() == ref.tree_hash_strict(), (vdt, idt)
         assert np.array_equal(t.perm, ref.perm)
         assert np.max(np.abs(t.q - ref.q)) <= 1e-12
         db = T.DeviceB.from_host(m, normalize=True)
@@ -287,7 +287,7 @@ def test_shared_memory_gather_matches_the_plain_gather(golden_small):
         (d0, p0, t0), (d1, p1, t1) = outs
         assert np.max(np.abs(d0 - d1)) <= 1e-12 * np.max(np.abs(d0))
         assert np.max(np.abs(p0 - p1)) <= 1e-12 * np.max(np.abs(p0))
-        assert t0.tree_hash() == t1.tree_hash()
+        assert t0.tree_hash_strict() == t1.tree_hash_strict()
         assert np.max(np.abs(t0.q - t1.q)) <= 1e-12
 
 
@@ -318,4 +318,4 @@ def test_experimental_kernel_switches_build_the_same_tree(env, golden_small):
             del os.environ[k]
     assert np.max(np.abs(p0 - p1)) <= 1e-12 * np.max(np.abs(p0))
     assert np.max(np.abs(d0 - d1)) <= 1e-12 * np.max(np.abs(d0))
-    assert t0.tree_hash() == t1.tree_hash() and np.max(np.abs(t0.q - t1.q)) <= 1e-12
+    assert t0.tree_hash_strict() == t1.tree_hash_strict() and np.max(np.abs(t0.q - t1.q)) <= 1e-12

@@ -362,7 +362,7 @@ def _oracle_signature(ot):
             rec(ot.left[i]); rec(ot.right[i])
         end[i] = len(perm)
     rec(0)
-    return T.tree_signature(ot.left, ot.right, begin, end, perm)
+    return T.tree_signature_strict(ot.left, ot.right, begin, end, perm)
 
 
 def test_config1_full_tree_vs_oracle_and_port():
@@ -373,17 +373,17 @@ def test_config1_full_tree_vs_oracle_and_port():
     tree = T.hierarchical_spectral_cluster(a, normalize=True)
     ot = O.hierarchical_spectral_cluster(a, normalize=True)
     assert tree.leaf_sets() == ot.leaf_sets() and same_tree(tree, ot)
-    assert tree.tree_hash() == _oracle_signature(ot)
+    assert tree.tree_hash_strict() == _oracle_signature(ot)
     qo = {tuple(sorted(int(x) for x in ot.items[i])): ot.q[i] for i in range(ot.n_nodes)}
     for i in range(tree.n_nodes):
         key = tuple(sorted(int(x) for x in tree.items(i)))
         if len(key) >= 2:
             assert abs(tree.q[i] - qo[key]) <= 1e-9 * max(1.0, abs(qo[key])) + 1e-12      # north_star allows 1e-5 relative
     pt = P.make_tree(a, normalize=True, tol=1e-10)
-    assert T.tree_signature(pt.left, pt.right, pt.begin, pt.end, pt.perm) == tree.tree_hash()
+    assert T.tree_signature_strict(pt.left, pt.right, pt.begin, pt.end, pt.perm) == tree.tree_hash_strict()
     # the sign-certified stop and the plain tolerance stop build the same tree, the former with fewer Lanczos steps
     t_tol = T.hierarchical_spectral_cluster(a, normalize=True, sign_stop=False)
-    assert t_tol.tree_hash() == tree.tree_hash()
+    assert t_tol.tree_hash_strict() == tree.tree_hash_strict()
     assert np.max(np.abs(t_tol.q - tree.q)) < 1e-12            # Q is a function of the labels only
     assert int(tree.iters.sum()) < 0.9 * int(t_tol.iters.sum())
 
@@ -394,7 +394,7 @@ def test_sign_certified_stop_same_tree(name, golden_tiny, golden_small):
     for mm in (0.0, -1.0):          # the default tree and the saturated one (every cell its own leaf)
         t_cert = T.hierarchical_spectral_cluster(a, normalize=True, min_modularity=mm)
         t_tol = T.hierarchical_spectral_cluster(a, normalize=True, min_modularity=mm, sign_stop=False)
-        assert t_cert.tree_hash() == t_tol.tree_hash(), (name, mm)
+        assert t_cert.tree_hash_strict() == t_tol.tree_hash_strict(), (name, mm)
         assert np.max(np.abs(t_cert.q - t_tol.q)) < 1e-12
         assert int(t_cert.iters.sum()) <= int(t_tol.iters.sum())
 
@@ -410,7 +410,7 @@ def test_warm_start_same_tree(name, golden_tiny, golden_small, monkeypatch):
         for sign_stop in (True, False):
             t_warm = T.hierarchical_spectral_cluster(a, normalize=True, min_modularity=mm, sign_stop=sign_stop)
             t_cold = T.hierarchical_spectral_cluster(a, normalize=True, min_modularity=mm, sign_stop=sign_stop, warm_start=False)
-            assert t_warm.tree_hash() == t_cold.tree_hash(), (name, mm, sign_stop)
+            assert t_warm.tree_hash_strict() == t_cold.tree_hash_strict(), (name, mm, sign_stop)
             # canonical eigenvector sign: not only the same tree up to child order, the same numbering and the same perm
             assert np.array_equal(t_warm.left, t_cold.left) and np.array_equal(t_warm.right, t_cold.right)
             assert np.array_equal(t_warm.perm, t_cold.perm) and np.array_equal(t_warm.item_begin, t_cold.item_begin)
@@ -436,7 +436,7 @@ def test_direct_solve_of_small_nodes_same_tree(name, golden_tiny, golden_small):
             assert int((t_sw.iters[t_sw.item_end - t_sw.item_begin >= 2] == 0).sum()) == 0
             for thr in (None, 8, 33):
                 t_d = T.hierarchical_spectral_cluster(mat, normalize=norm, min_modularity=mm, small_rows=thr)
-                assert t_d.tree_hash() == t_sw.tree_hash(), (name, norm, mm, thr)
+                assert t_d.tree_hash_strict() == t_sw.tree_hash_strict(), (name, norm, mm, thr)
                 assert np.array_equal(t_d.left, t_sw.left) and np.array_equal(t_d.right, t_sw.right) and np.array_equal(t_d.perm, t_sw.perm)
                 assert np.max(np.abs(t_d.q - t_sw.q)) < 1e-11
                 assert np.max(np.abs(t_d.theta - t_sw.theta)) < 1e-9
@@ -451,7 +451,7 @@ def test_direct_solve_of_small_nodes_same_tree(name, golden_tiny, golden_small):
         t = T.hierarchical_spectral_cluster(a, normalize=True, min_modularity=mm)
         ot = O.hierarchical_spectral_cluster(a, normalize=True, min_modularity=mm)
         assert t.leaf_sets() == ot.leaf_sets() and same_tree(t, ot), (name, mm)
-        assert t.tree_hash() == _oracle_signature(ot)
+        assert t.tree_hash_strict() == _oracle_signature(ot)
         qo = {tuple(sorted(int(x) for x in ot.items[i])): ot.q[i] for i in range(ot.n_nodes)}
         for i in range(t.n_nodes):
             key = tuple(sorted(int(x) for x in t.items(i)))
@@ -479,7 +479,7 @@ def test_run_to_run_reproducible_tree_and_q(golden_small):
     (sign_stop) or converged to 1e-10, hence the TREE is identical run to run and Q (a function of the labels) agrees to 1e-12."""
     a, _ = golden_small
     runs = [T.hierarchical_spectral_cluster(a, normalize=True) for _ in range(3)]
-    assert len({t.tree_hash() for t in runs}) == 1
+    assert len({t.tree_hash_strict() for t in runs}) == 1
     for t in runs[1:]:
         assert np.max(np.abs(t.q - runs[0].q)) <= 1e-12
 
@@ -511,7 +511,7 @@ def test_full_size_config2_vs_port_and_arpack():
     assert abs(tree.q[0] - O.get_b_modularity(lab, bn)) <= 1e-10
     pt = P.make_tree(a, normalize=True, tol=1e-10, threads=min(os.cpu_count() or 1, 32))
     assert pt.n_nodes == tree.n_nodes
-    assert T.tree_signature(pt.left, pt.right, pt.begin, pt.end, pt.perm) == tree.tree_hash()
+    assert T.tree_signature_strict(pt.left, pt.right, pt.begin, pt.end, pt.perm) == tree.tree_hash_strict()
 
 
 def test_full_size_config3_properties_and_sign_stop():
@@ -540,14 +540,14 @@ def test_full_size_config3_properties_and_sign_stop():
     for i in leaves[:: max(1, len(leaves) // 200)]:
         assert np.all(np.diff(t1.items(i)) > 0)                                   # stable partitions: ascending rows in a leaf
     t2 = T.hierarchical_spectral_cluster(b, sign_stop=False)
-    assert t2.tree_hash() == t1.tree_hash()
+    assert t2.tree_hash_strict() == t1.tree_hash_strict()
     assert np.max(np.abs(t2.q - t1.q)) < 1e-12
     assert int(t1.iters.sum()) < 0.8 * int(t2.iters.sum())
     t3 = T.hierarchical_spectral_cluster(b, seed=20261020)                        # another start vector: the same tree
-    assert t3.tree_hash() == t1.tree_hash()
+    assert t3.tree_hash_strict() == t1.tree_hash_strict()
     assert np.array_equal(t3.left, t1.left) and np.array_equal(t3.perm, t1.perm)  # canonical sign: the same numbering, too
     t4 = T.hierarchical_spectral_cluster(b, warm_start=False)                     # cold starts everywhere: the same tree, more steps
-    assert t4.tree_hash() == t1.tree_hash()
+    assert t4.tree_hash_strict() == t1.tree_hash_strict()
     assert np.max(np.abs(t4.q - t1.q)) < 1e-12
     assert int(t1.iters.sum()) < int(t4.iters.sum())
     print(f"c3 Lanczos steps: warm {int(t1.iters.sum())}, cold {int(t4.iters.sum())}, tolerance stop {int(t2.iters.sum())}")

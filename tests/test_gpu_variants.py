@@ -129,7 +129,7 @@ def test_kmeans_group_in_the_sweep_engine_equals_the_per_node_composition(golden
     finally:
         del os.environ["TMC_KMEANS_COMPOSED"]
     db.free()
-    assert t_sweeps.tree_hash() == t_comp.tree_hash() and t_sweeps.n_nodes > 10
+    assert t_sweeps.tree_hash_strict() == t_comp.tree_hash_strict() and t_sweeps.n_nodes > 10
     qa = {tuple(sorted(int(x) for x in t_sweeps.items(i))): (t_sweeps.q[i], t_sweeps.p_val[i]) for i in range(t_sweeps.n_nodes)}
     for i in range(t_comp.n_nodes):
         k = tuple(sorted(int(x) for x in t_comp.items(i)))
@@ -229,7 +229,7 @@ def test_signed_matrix_full_tree_vs_oracle():
             assert abs(tree.q[i] - qo[key]) <= 1e-9
     # the dense call (typical after PCA / batch correction) builds the same tree
     td = T.hierarchical_spectral_cluster(np.asarray(a.todense()))
-    assert td.tree_hash() == tree.tree_hash()
+    assert td.tree_hash_strict() == tree.tree_hash_strict()
 
 
 def test_svd_and_pca_pre_reductions_vs_lapack():

@@ -51,6 +51,48 @@ def test_opts_default_and_layout():
     assert C.sizeof(_lib.Opts) == 96 and C.sizeof(_lib.Tree) == 152      # static_assert-ed in tmc_engine.cu
 
 
+def test_engine_knobs_of_round_two():
+    """tmc_opts.warm_start / small_rows (taken from the reserved words: the defaults, 0, mean "on")."""
+    o = T.make_opts()
+    assert o.sign_stop == 0 and o.warm_start == 0 and o.small_rows == 0
+    o = T.make_opts(sign_stop=False, warm_start=False, small_rows=0)          # the plain engine
+    assert o.sign_stop == -1 and o.warm_start == -1 and o.small_rows == -1
+    assert T.make_opts(small_rows=16).small_rows == 16 and T.make_opts(small_rows=None).small_rows == 0
+
+
+def test_tree_vertex_names_and_signature():
+    """A vertex is named by (smallest row id, number of cells); the signature hashes leaf membership + the sorted names, so it is
+    blind to child order and numbering but not to membership or topology."""
+    #        0            perm = [4 5 | 0 2 | 1 3]
+    #      /   \
+    #     1     2         1 = {4,5} (leaf), 2 = {0,2,1,3}, 3 = {0,2}, 4 = {1,3}
+    #          / \
+    #         3   4
+    left = [1, -1, 3, -1, -1]; right = [2, -1, 4, -1, -1]
+    begin = [0, 0, 2, 2, 4]; end = [6, 2, 6, 4, 6]; perm = [4, 5, 0, 2, 1, 3]
+    names = T.tree_vertex_names(left, right, begin, end, perm)
+    assert names.tolist() == [[0, 6], [4, 2], [0, 4], [0, 2], [1, 2]]
+    h = T.tree_signature(left, right, begin, end, perm)
+    # the same tree with the children of the root and of vertex 2 swapped, renumbered in pre-order
+    left2 = [1, 2, -1, -1, -1]; right2 = [4, 3, -1, -1, -1]
+    begin2 = [0, 0, 0, 2, 4]; end2 = [6, 4, 2, 4, 6]; perm2 = [1, 3, 0, 2, 4, 5]
+    assert T.tree_signature(left2, right2, begin2, end2, perm2) == h
+    # another topology on the same leaves: {4,5} merged with {0,2} first
+    left3 = [1, 2, -1, -1, -1]; right3 = [4, 3, -1, -1, -1]
+    begin3 = [0, 0, 0, 2, 4]; end3 = [6, 4, 2, 4, 6]; perm3 = [4, 5, 0, 2, 1, 3]
+    # the (smallest row, size) names cannot tell these two apart ({4,5,0,2} and {0,2,1,3} are both (0, 4)); the strict ones can
+    assert T.tree_signature(left3, right3, begin3, end3, perm3) == h
+    hs = T.tree_signature_strict(left, right, begin, end, perm)
+    assert T.tree_signature_strict(left2, right2, begin2, end2, perm2) == hs
+    assert T.tree_signature_strict(left3, right3, begin3, end3, perm3) != hs
+    assert T.tree_signature_strict(left, right, begin, end, [4, 5, 0, 3, 1, 2]) != hs
+    ns = T.tree_vertex_names(left, right, begin, end, perm, strict=True)
+    assert ns.shape == (5, 3) and len({tuple(r) for r in ns.tolist()}) == 5
+    assert ns[2, 2] == (ns[3, 2] + ns[4, 2]) and ns[0, 2] == (ns[1, 2] + ns[2, 2])      # set hashes add up (mod 2^64)
+    # another membership: cells 2 and 3 exchanged between the leaves
+    assert T.tree_signature(left, right, begin, end, [4, 5, 0, 3, 1, 2]) != h
+
+
 def test_no_cpu_fallback_without_device():
     lib = _lib.load()
     if lib.tmc_device_count() > 0:

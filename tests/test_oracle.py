@@ -203,8 +203,8 @@ def test_port_and_oracle_agree_on_config1_through_the_tree_signature():
             rec(ot.left[i]); rec(ot.right[i])
         end[i] = len(perm)
     rec(0)
-    sig_o = T.tree_signature(ot.left, ot.right, begin, end, perm)
-    sig_p = T.tree_signature(pt.left, pt.right, pt.begin, pt.end, pt.perm)
+    sig_o = T.tree_signature_strict(ot.left, ot.right, begin, end, perm)
+    sig_p = T.tree_signature_strict(pt.left, pt.right, pt.begin, pt.end, pt.perm)
     assert sig_o == sig_p
     # swapping the children of the root leaves the signature alone; moving one cell to another leaf changes it
     l2, r2 = list(ot.left), list(ot.right)
@@ -218,9 +218,9 @@ def test_port_and_oracle_agree_on_config1_through_the_tree_signature():
             rec2(l2[i]); rec2(r2[i])
         e2[i] = len(p2)
     rec2(0)
-    assert T.tree_signature(l2, r2, b2, e2, p2) == sig_o
+    assert T.tree_signature_strict(l2, r2, b2, e2, p2) == sig_o
     p3 = list(perm); p3[0], p3[-1] = p3[-1], p3[0]
-    assert T.tree_signature(ot.left, ot.right, begin, end, p3) != sig_o
+    assert T.tree_signature_strict(ot.left, ot.right, begin, end, p3) != sig_o
 
 
 def test_signed_input_semantics_of_the_oracle():

@@ -320,19 +320,40 @@ class ClusteringTree:
         """Canonical SHA-1 of leaf membership + topology (see `tree_signature`)."""
         return tree_signature(self.left, self.right, self.item_begin, self.item_end, self.perm)
 
+    def tree_hash_strict(self):
+        """The same with every vertex named by its SET of cells (see `tree_signature_strict`)."""
+        return tree_signature_strict(self.left, self.right, self.item_begin, self.item_end, self.perm)
+
+    def tree_hashes(self):
+        """(tree_hash(), tree_hash_strict()) from one pass over the tree."""
+        r = _tree_names(self.left, self.right, self.item_begin, self.item_end, self.perm)
+        return r[0], r[2]
+
 
 def tree_signature(left, right, begin, end, perm) -> str:
     """SHA-1 of a flat tree that does not depend on the eigenvector sign (child order), the node numbering or the rank
     count: every vertex is named by (smallest row id among its cells, number of cells) -- distinct vertices of a tree
     differ in that pair -- and the hash covers (1) for every cell the name of its leaf (membership) and (2) the sorted
     list of all vertex names (topology: which sets of leaves are merged).  Two trees have the same signature iff they
-    have identical leaf membership and identical topology up to swapping children."""
+    have identical leaf membership and identical topology up to swapping children -- with one blind spot: vertices of two
+    DIFFERENT trees can share (smallest row, size) although their cells differ ({a, b} | {c} against {a, c} | {b} inside a
+    three-cell vertex of a saturated tree).  `tree_signature_strict` closes it; this one is kept because the hashes of rounds
+    1 and 2 in profiles/ were computed with it."""
     return _tree_names(left, right, begin, end, perm)[0]
 
 
-def tree_vertex_names(left, right, begin, end, perm):
-    """(smallest row id, number of cells) of every vertex, in the tree's own numbering: an (n_nodes, 2) int64 array."""
-    return _tree_names(left, right, begin, end, perm)[1]
+def tree_signature_strict(left, right, begin, end, perm) -> str:
+    """Like `tree_signature`, with every vertex named by (smallest row id, number of cells, 64-bit hash of its SET of cells:
+    the sum mod 2^64 of a mixed row id over the cells): equal iff the two trees consist of the same sets of cells, i.e. have
+    identical leaf membership and identical topology up to swapping children (up to a 2^-64 collision)."""
+    return _tree_names(left, right, begin, end, perm)[2]
+
+
+def tree_vertex_names(left, right, begin, end, perm, strict=False):
+    """(smallest row id, number of cells) of every vertex, in the tree's own numbering: an (n_nodes, 2) int64 array;
+    strict=True appends the 64-bit hash of the vertex's set of cells as a third column (as int64 bit patterns)."""
+    r = _tree_names(left, right, begin, end, perm)
+    return np.concatenate([r[1], r[3].view(np.int64)[:, None]], axis=1) if strict else r[1]
 
 
 def _tree_names(left, right, begin, end, perm):
@@ -371,7 +392,24 @@ def _tree_names(left, right, begin, end, perm):
     h = hashlib.sha1()
     h.update(np.ascontiguousarray(leaf_name).tobytes())
     h.update(np.ascontiguousarray(names).tobytes())
-    return h.hexdigest(), names0
+    # set hash of every vertex: sum mod 2^64 of splitmix64(row id) over its cells (leaves by reduceat, inner vertices bottom-up)
+    x = perm.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    x = x ^ (x >> np.uint64(31))
+    sh = np.zeros(n, dtype=np.uint64)
+    if nonempty.size:
+        sh[nonempty] = np.add.reduceat(x, begin[nonempty])
+    for lev in reversed(levels[1:]):
+        np.add.at(sh, parent[lev], sh[lev])
+    leaf_set = np.empty(perm.size, dtype=np.uint64)
+    leaf_set[perm] = np.repeat(sh[nonempty], sizes)
+    trip = np.stack([mn.astype(np.uint64), (end - begin).astype(np.uint64), sh], axis=1)
+    trip = trip[np.lexsort((trip[:, 2], trip[:, 1], trip[:, 0]))]
+    h2 = hashlib.sha1()
+    h2.update(np.ascontiguousarray(leaf_set).tobytes())
+    h2.update(np.ascontiguousarray(trip).tobytes())
+    return h.hexdigest(), names0, h2.hexdigest(), sh
 
 
 def _tree_from_c(tp) -> ClusteringTree:

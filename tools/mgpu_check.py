@@ -42,7 +42,7 @@ ok = True
 def check(name, how, tr, ms):
     global ok
     ref = single[name]
-    same = tr.tree_hash() == ref.tree_hash()
+    same = tr.tree_hash_strict() == ref.tree_hash_strict()
     dq = float(np.max(np.abs(np.sort(tr.q) - np.sort(ref.q)))) if tr.n_nodes == ref.n_nodes else float("inf")
     good = same and dq <= 1e-12
     ok &= good
@@ -74,7 +74,7 @@ for name in names:
 for k, m in kinds.items():
     t0 = time.time(); tr = T.hierarchical_spectral_cluster(m, device=lr)
     ref = kind_single[k]
-    good = tr.tree_hash() == ref.tree_hash() and float(np.max(np.abs(np.sort(tr.q) - np.sort(ref.q)))) <= 1e-10
+    good = tr.tree_hash_strict() == ref.tree_hash_strict() and float(np.max(np.abs(np.sort(tr.q) - np.sort(ref.q)))) <= 1e-10
     ok &= good
     print(f"[rank {rank}] {names[0]:6s} {k:34s} nodes {tr.n_nodes:5d} vs {ref.n_nodes:5d}  wall {1e3 * (time.time() - t0):7.1f} ms  {'ok' if good else 'FAIL'}", flush=True)
 
@@ -100,14 +100,14 @@ good = codes == [T._lib.ERR_ZERO_ROW, T._lib.ERR_ZERO_ROW]
 ok &= good
 print(f"[rank {rank}] zero-norm row in the last rank's block -> status on this rank {codes}: {'ok' if good else 'FAIL'}", flush=True)
 t1 = T.hierarchical_spectral_cluster(mats[names[0]], normalize=True, device=lr, max_active=1)
-good = t1.tree_hash() == single[names[0]].tree_hash()
+good = t1.tree_hash_strict() == single[names[0]].tree_hash_strict()
 ok &= good
 print(f"[rank {rank}] max_active = 1 under {world} ranks builds the whole tree: {'ok' if good else 'FAIL'}", flush=True)
 
 # the non-default variants under a communicator: every rank runs them as a replica, results checked across ranks inside libtmc
 tk = T.hierarchical_spectral_cluster(mats[vname][:300], normalize=True, eigen_group="KMeansGroup", device=lr)
 tp = T.hierarchical_spectral_cluster(mats[vname][:300], normalize=True, num_runs=6, device=lr)
-good = tk.tree_hash() == v_single[0].tree_hash() and tp.tree_hash() == v_single[1].tree_hash() and \
+good = tk.tree_hash_strict() == v_single[0].tree_hash_strict() and tp.tree_hash_strict() == v_single[1].tree_hash_strict() and \
     np.array_equal(np.nan_to_num(tp.p_val, nan=-1.0), np.nan_to_num(v_single[1].p_val, nan=-1.0))
 ok &= good
 print(f"[rank {rank}] variants under {world} ranks (KMeansGroup, numRuns): {'ok' if good else 'FAIL'}", flush=True)
