@@ -1053,6 +1053,8 @@ struct Engine {
     // only nodes of at least this many cells start warm: the sign certificate of a small node is too easy to pass for a start
     // vector that favours u2 (DESIGN.md "warm start"; measured: 1 wrong split in ~50 000 small certified nodes without it)
     warm_child_min = getenv("TMC_WARM_CHILD_ROWS") ? atoi(getenv("TMC_WARM_CHILD_ROWS")) : 512;
+    // a node with fewer cells than that cannot have a child that starts warm: no second Ritz vector, no start vector left behind
+    if (!getenv("TMC_WARM_MIN_ROWS")) c.warm_min_rows = std::max(c.warm_min_rows, warm_child_min + 1);
     // direct solve of small local nodes (tmc_opts.small_rows: 0 = default 64, -1 = off, else the threshold, at most 64)
     small_rows = o.small_rows < 0 ? 0 : (o.small_rows == 0 ? TMC_SMALL_MAX : std::min(o.small_rows, TMC_SMALL_MAX));
     if (getenv("TMC_SMALL_ROWS")) small_rows = std::max(0, std::min(atoi(getenv("TMC_SMALL_ROWS")), TMC_SMALL_MAX));
