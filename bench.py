@@ -385,6 +385,8 @@ def main():
             "gpu_launches": launches, "roofline": roof,
             "tree": {"nodes": tr.n_nodes, "leaves": int(len(tr.leaves())), "sweeps": tr.stats["n_sweeps"],
                      "lanczos_steps": int(tr.iters.sum()), "engine_ms_last": tr.stats["engine_ms"], "gen_s": gen_s,
+                     # vertices of >= 2 cells that never iterated: solved directly, Gram matrix + dense eigen-solve (tmc_small.cuh)
+                     "direct_vertices": int(((tr.iters == 0) & ((tr.item_end - tr.item_begin) >= 2)).sum()),
                      "hash": hashes[0].split("/")[0], "hash_strict": hashes[0].split("/")[1],
                      "hash_single_gpu": hash_single.split("/")[0] if hash_single else None,
                      "hash_check": ("all ranks and steps equal" + (", equal to the single-GPU tree" if hash_single else "")) }}
