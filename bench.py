@@ -13,6 +13,8 @@ pairs, sign split, modularity, stable row partition) down to the leaves.
   tree.hash: canonical SHA-1 of leaf membership + topology (too_many_cells_b200.tree_signature; tree.hash_strict: the same with
            every vertex named by its set of cells, tree_signature_strict); at N > 1 both are asserted equal on every rank and
            equal to the tree one GPU builds alone (`hash_single_gpu`)
+  tree.direct_vertices: vertices of >= 2 cells that never iterated in the sweeps -- nodes of <= 64 cells on one rank are solved
+           directly (Gram matrix + dense eigen-solve of the whole subtree in one CTA, csrc/tmc_small.cuh)
   cpu_baseline / --impl reference: the C port of the reference's CPU path (oracle/tmc_port.c), MEASURED on a bounded
            sample of the workload; the b200 arm also measures the GPU on that very sample (`same_input`).
 
