@@ -1509,10 +1509,10 @@ struct Engine {
       nrec += 2ll * (nd.end - nd.begin) - 1;
     }
     const size_t smem = small_smem_bytes();
-    // scratch lists of the residual part: room for 1.5 x the average 64-row node, between 32 k and 256 k entries per CTA
-    // (larger nodes take the kernel's fallback path); at most 2 GB in all
+    // scratch lists of the residual part: room for 4 x the average 64-row node (clusters of large cells have long rows), between
+    // 32 k and 256 k entries per CTA (larger nodes take the kernel's fallback path); at most 2 GB in all
     const int64_t avg_row = b->n_rows > 0 ? b->enz() / b->n_rows + 1 : 1;
-    const int cap = (int)std::min<int64_t>(262144, std::max<int64_t>(32768, avg_row * 96));
+    const int cap = (int)std::min<int64_t>(262144, std::max<int64_t>(32768, avg_row * 256));
     const size_t stride = small_scratch_stride((int)b->n_cols, cap);
     int grid = std::min(n, 148 * 3);
     grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ((int64_t)2 << 30) / (int64_t)stride));
