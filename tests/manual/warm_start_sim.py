@@ -6,7 +6,15 @@ directions 3 and 4 of C), bring them to the random-walk picture f = D^{-1/2} x (
 and start the child from D_child^{1/2} f restricted to its rows instead of a random vector.  The stop rules are the engine's
 (tolerance 1e-10, or the sign certificate for nodes of >= MINM cells); work = rows x steps summed over the nodes.
 
-    python tests/manual/warm_start_sim.py [tiny|small|c1]      env: MINMOD, SAFE (4), MINM (64), MIX (0.7)
+    python tests/manual/warm_start_sim.py [tiny|small|c1|deep]      env: MINMOD, SAFE (4), MINM (64), MIX (0.7), NV (Ritz vectors in the
+    mix, 2), MODE (mix | w), ENTRY=1 (entrywise certificate through the purified Ritz vector), ADAPT=e (safety factor scaled by
+    (|z_1| sqrt(m))^e: the bias of the start vector towards u2)
+
+Measured (round 2, this container; ratio = work with warm starts / work with random starts, both under the sign certificate):
+    small 0.88, deep (4000 x 6000, planted depth 7) 0.88: 0.70 - 0.78 on the planted levels, 0.92 - 0.95 on the structureless ones;
+    NV = 1 .. 4 and the weighted mix change nothing (0.88 - 0.91); saturated trees 0.90 - 0.91; no wrong label in any of these runs
+    (a few hundred certified nodes -- the failure the GPU runs found has a rate of about 1 in 50 000 small certified nodes:
+    DESIGN.md section 3); ENTRY=1 saves another 2.5 %; ADAPT=1 / 0.5 leave 0.94 / 0.91 of the gain.
 """
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
